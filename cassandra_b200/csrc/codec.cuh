@@ -1,0 +1,195 @@
+// codec.cuh — chunk codec kernels (K1 decompress + CRC verify, K5 compress fused with CRC32, pack, digest).
+//
+// K5 replaces CompressedSequentialWriter.flushData (S/io/compress/CompressedSequentialWriter.java:140-206): one warp
+// per 16 KiB chunk compresses it (LZ4 bit-exact with liblz4 / Snappy), writes the chunk into a fixed-stride slot,
+// computes the CRC32 of the bytes as written (ChecksumWriter.appendDirect, S/io/util/ChecksumWriter.java:62-89) in the
+// same kernel while the bytes are still in L1/L2, and appends it big-endian. A scan over the chunk sizes gives the
+// CompressionInfo.db offsets (CompressionMetadata.Writer.addOffset), k_pack_chunks moves the slots into the dense
+// Data.db image and k_digest folds the per-chunk CRCs into Digest.crc32 with x^(8n) shifts (no re-read of the bytes).
+// K1 replaces CompressedChunkReader.readChunk (S/io/util/CompressedChunkReader.java:103-173).
+#pragma once
+#include "common.cuh"
+#include "lz4.cuh"
+#include "snappy.cuh"
+
+namespace b200c {
+
+enum { COMP_NONE = 0, COMP_LZ4 = 1, COMP_SNAPPY = 2 };
+
+__host__ __device__ __forceinline__ int chunk_max_compressed(int comp, int chunk_len) {
+    if (comp == COMP_LZ4) return 4 + lz4_compress_bound(chunk_len);
+    if (comp == COMP_SNAPPY) return snappy_max_compressed_length(chunk_len);
+    return chunk_len;
+}
+__host__ __device__ __forceinline__ int chunk_slot_stride(int comp, int chunk_len) {
+    int m = chunk_max_compressed(comp, chunk_len); if (m < chunk_len) m = chunk_len;
+    return (m + 4 + 16 + 15) & ~15;      // bytes + CRC + read slack, 16-byte aligned
+}
+
+struct ChunkErr { unsigned long long first_bad; };   // min over failing chunks of (chunk index << 8 | kind); init ~0
+
+__device__ __forceinline__ void report_chunk_err(ChunkErr* e, uint64_t chunk, int kind) {
+    atomicMin(&e->first_bad, ((unsigned long long)chunk << 8) | (unsigned long long)kind);
+}
+
+// ---- K5: compress + CRC ------------------------------------------------------------------------------------------
+// grid = nchunks blocks of one warp. dynamic smem: [hash table tab_bytes][chunk bytes chunk_len + 16]
+__global__ void __launch_bounds__(32) k_compress_chunks(const DevTables* __restrict__ T, int comp, int tab_bytes,
+        const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen,
+        uint8_t* __restrict__ slots, int slot_stride, uint32_t* __restrict__ file_len, uint32_t* __restrict__ seg_raw) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t* s_tab = (uint16_t*)smem;
+    uint8_t* s_in = smem + tab_bytes;     // lz4: 8192 x u16 (16 KiB); snappy: 16384 x u16 (32 KiB)
+    const int lane = threadIdx.x;
+    const uint64_t chunk = blockIdx.x;
+    const uint64_t start = chunk * (uint64_t)chunk_len;
+    const int ulen = (int)min((uint64_t)chunk_len, n - start);
+    const uint8_t* src = in + start;
+
+    // stage the chunk in shared memory (16-byte vectors when aligned), zero the slack
+    if ((((uintptr_t)src) & 15) == 0) {
+        const uint4* s4 = (const uint4*)src; uint4* d4 = (uint4*)s_in;
+        int nv = ulen >> 4;
+        for (int i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+        for (int i = (nv << 4) + lane; i < ulen; i += 32) s_in[i] = src[i];
+    } else {
+        for (int i = lane; i < ulen; i += 32) s_in[i] = src[i];
+    }
+    if (lane < 16) s_in[ulen + lane] = 0;
+    __syncwarp();
+
+    uint8_t* slot = slots + chunk * (uint64_t)slot_stride;
+    int clen;
+    if (comp == COMP_LZ4) {
+        if (lane == 0) { slot[0] = (uint8_t)ulen; slot[1] = (uint8_t)(ulen >> 8); slot[2] = (uint8_t)(ulen >> 16); slot[3] = (uint8_t)(ulen >> 24); }
+        clen = 4 + lz4_compress_warp(s_in, ulen, s_tab, slot + 4, lane);
+    } else if (comp == COMP_SNAPPY) {
+        clen = snappy_compress_warp(s_in, ulen, s_tab, slot, lane);
+    } else {
+        clen = ulen;
+        for (int i = lane; i < ulen; i += 32) slot[i] = s_in[i];
+    }
+    // flushData :158-177 — store raw when compression did not help enough (never with the default ratio)
+    if (comp != COMP_NONE && clen >= max_clen) {
+        for (int i = lane; i < ulen; i += 32) slot[i] = s_in[i];
+        clen = ulen;
+        if (ulen < max_clen) { for (int i = ulen + lane; i < max_clen; i += 32) slot[i] = 0; clen = max_clen; }
+    }
+    __syncwarp();
+    __threadfence_block();
+    // CRC32 over the bytes as written, appended big-endian
+    uint32_t raw = warp_crc32_raw(T, T->crc_adv128, slot, clen, lane);
+    uint32_t init = gf2_mulmod(0xFFFFFFFFu, warp_xpow8n(T, (uint32_t)clen, lane));
+    uint32_t crc = ~(raw ^ init);
+    if (lane == 0) {
+        slot[clen] = (uint8_t)(crc >> 24); slot[clen + 1] = (uint8_t)(crc >> 16); slot[clen + 2] = (uint8_t)(crc >> 8); slot[clen + 3] = (uint8_t)crc;
+        file_len[chunk] = (uint32_t)clen + 4;
+        // zero-init register of (chunk bytes || 4 CRC bytes): advance (raw ^ LE word of the CRC bytes) by 4 bytes
+        uint32_t x = raw ^ __byte_perm(crc, 0, 0x0123);
+        seg_raw[chunk] = T->crc_t[3][x & 0xff] ^ T->crc_t[2][(x >> 8) & 0xff] ^ T->crc_t[1][(x >> 16) & 0xff] ^ T->crc_t[0][x >> 24];
+    }
+}
+
+// ---- pack: slots -> dense Data.db image --------------------------------------------------------------------------
+// one warp per chunk; offs = exclusive scan of file_len
+__global__ void __launch_bounds__(128) k_pack_chunks(const uint8_t* __restrict__ slots, int slot_stride, const uint32_t* __restrict__ file_len,
+                                                     const uint64_t* __restrict__ offs, uint64_t nchunks, uint8_t* __restrict__ out) {
+    uint64_t chunk = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (chunk >= nchunks) return;
+    int lane = threadIdx.x & 31;
+    const uint8_t* s = slots + chunk * (uint64_t)slot_stride;
+    uint8_t* d = out + offs[chunk];
+    int len = (int)file_len[chunk];
+    // head bytes until d is 16-byte aligned, then 16-byte stores assembled from two aligned 16-byte loads
+    int head = (int)((16 - ((uintptr_t)d & 15)) & 15); if (head > len) head = len;
+    if (lane < head) d[lane] = s[lane];
+    int body = (len - head) >> 4;
+    const uint8_t* sb = s + head; uint8_t* db = d + head;
+    int mis = (int)((uintptr_t)sb & 15);
+    const uint4* sa = (const uint4*)(sb - mis);
+    for (int i = lane; i < body; i += 32) {
+        uint4 a = sa[i];
+        uint4 r = a;
+        if (mis) {
+            uint4 b = sa[i + 1];
+            uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+            int ws = mis >> 2, bs = (mis & 3) * 8;
+            r.x = __funnelshift_r(w[ws], w[ws + 1], bs); r.y = __funnelshift_r(w[ws + 1], w[ws + 2], bs);
+            r.z = __funnelshift_r(w[ws + 2], w[ws + 3], bs); r.w = __funnelshift_r(w[ws + 3], w[ws + 4], bs);
+        }
+        ((uint4*)db)[i] = r;
+    }
+    int done = head + (body << 4);
+    for (int i = done + lane; i < len; i += 32) d[i] = s[i];
+}
+
+// ---- digest: Digest.crc32 from per-chunk registers ---------------------------------------------------------------
+// acc[0] ^= seg_raw[i] * x^(8 * bytes after segment i); final value fixed up on the host side of the launch
+__global__ void __launch_bounds__(256) k_digest(const DevTables* __restrict__ T, const uint32_t* __restrict__ seg_raw,
+                                                const uint64_t* __restrict__ offs /*n+1*/, uint64_t nchunks, uint32_t* __restrict__ acc) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = 0;
+    if (i < nchunks) {
+        uint64_t total = offs[nchunks];
+        v = gf2_mulmod(seg_raw[i], gf2_xpow8n(T, total - offs[i + 1]));
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v ^= __shfl_xor_sync(FULL_MASK, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicXor(acc, v);
+}
+__global__ void k_digest_final(const DevTables* __restrict__ T, const uint64_t* __restrict__ offs, uint64_t nchunks, uint32_t* __restrict__ acc) {
+    uint64_t total = offs[nchunks];
+    acc[1] = ~(acc[0] ^ gf2_mulmod(0xFFFFFFFFu, gf2_xpow8n(T, total)));
+}
+
+// ---- K1: CRC verify + decompress ----------------------------------------------------------------------------------
+// grid = nchunks blocks of one warp; dynamic smem = chunk_len + 16
+__global__ void __launch_bounds__(32) k_decompress_chunks(const DevTables* __restrict__ T, int comp,
+        const uint8_t* __restrict__ data, uint64_t data_len, const uint64_t* __restrict__ offs, uint64_t nchunks,
+        int chunk_len, int max_clen, uint64_t data_length, uint8_t* __restrict__ out, int verify, ChunkErr* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* s_out = smem;
+    const int lane = threadIdx.x;
+    const uint64_t chunk = blockIdx.x;
+    const uint64_t off = offs[chunk];
+    const uint64_t next = (chunk + 1 < nchunks) ? offs[chunk + 1] : data_len;
+    const uint64_t ustart = chunk * (uint64_t)chunk_len;
+    if (off + 4 > next || next > data_len || ustart >= data_length || next - off - 4 > (uint64_t)(chunk_max_compressed(comp, chunk_len) + chunk_len)) {
+        if (lane == 0) report_chunk_err(err, chunk, 2);
+        return;
+    }
+    const int clen = (int)(next - off - 4);
+    const int ulen = (int)min((uint64_t)chunk_len, data_length - ustart);
+    const uint8_t* src = data + off;
+    if (verify) {
+        uint32_t crc = warp_crc32(T, T->crc_adv128, src, clen, lane);
+        uint32_t stored = ((uint32_t)src[clen] << 24) | ((uint32_t)src[clen + 1] << 16) | ((uint32_t)src[clen + 2] << 8) | src[clen + 3];
+        if (crc != stored) { if (lane == 0) report_chunk_err(err, chunk, 1); return; }
+    }
+    int got;
+    if (clen >= max_clen) {                 // CompressedChunkReader.java:116,219: raw chunk (possibly zero padded at the file end)
+        if (clen < ulen) { if (lane == 0) report_chunk_err(err, chunk, 2); return; }
+        for (int i = lane; i < ulen; i += 32) s_out[i] = src[i];
+        got = ulen;
+    } else if (comp == COMP_LZ4) {
+        int plen = (clen >= 4) ? (int)((uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24)) : -1;
+        got = (plen == ulen) ? lz4_decompress_warp(src + 4, clen - 4, s_out, ulen, lane) : -1;
+    } else if (comp == COMP_SNAPPY) {
+        got = snappy_decompress_warp(src, clen, s_out, ulen, lane);
+    } else {
+        got = (clen == ulen) ? ulen : -1;
+        if (got >= 0) for (int i = lane; i < ulen; i += 32) s_out[i] = src[i];
+    }
+    if (got != ulen) { if (lane == 0) report_chunk_err(err, chunk, 2); return; }
+    __syncwarp();
+    uint8_t* dst = out + ustart;
+    if ((((uintptr_t)dst) & 15) == 0) {
+        int nv = ulen >> 4;
+        for (int i = lane; i < nv; i += 32) ((uint4*)dst)[i] = ((const uint4*)s_out)[i];
+        for (int i = (nv << 4) + lane; i < ulen; i += 32) dst[i] = s_out[i];
+    } else {
+        for (int i = lane; i < ulen; i += 32) dst[i] = s_out[i];
+    }
+}
+
+} // namespace b200c

@@ -1,0 +1,77 @@
+// engine.cuh — context, workspace and launch bookkeeping shared by the C-ABI translation units.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <atomic>
+#include <chrono>
+#include "../../include/b200c.h"
+#include "common.cuh"
+
+namespace b200c {
+
+enum { WS_SLOTS = 96 };
+
+struct WsBuf { void* p = nullptr; size_t cap = 0; };
+
+} // namespace b200c
+
+struct b200c_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    b200c::DevTables* d_tables = nullptr;
+    b200c::WsBuf ws[b200c::WS_SLOTS];
+    void* h_pinned = nullptr; size_t h_pinned_cap = 0;      // small pinned scratch for scalar read-backs
+    std::string err;
+    uint64_t launches_call = 0, launches_total = 0;
+    double last_ms = 0.0;
+    std::atomic<int> cancel{0};
+    std::atomic<uint64_t> prog_scanned{0}, prog_total{0};
+    std::atomic<int> prog_stage{0};
+    bool timing = false;
+};
+
+namespace b200c {
+
+#define B200C_CUDA_TRY(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e); return B200C_ECUDA; } } while (0)
+
+#define B200C_LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+    (ctx)->launches_call++; (ctx)->launches_total++; \
+    cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+        (ctx)->err = std::string(#kernel) + " launch: " + cudaGetErrorString(_e); return B200C_ECUDA; } } while (0)
+
+#define B200C_TRY(expr) do { int _rc = (expr); if (_rc != B200C_OK) return _rc; } while (0)
+
+// workspace slot `slot` with at least `bytes` bytes (+64 bytes of readable slack); contents are NOT preserved on growth
+inline int ws_get(b200c_ctx* c, int slot, size_t bytes, void** out) {
+    WsBuf& b = c->ws[slot];
+    size_t need = bytes + 256;
+    if (b.cap < need) {
+        if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        size_t cap = need + need / 8;
+        cudaError_t e = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(" + std::to_string(cap) + "): " + cudaGetErrorString(e); b.p = nullptr; return B200C_ENOMEM; }
+        b.cap = cap;
+    }
+    *out = b.p;
+    return B200C_OK;
+}
+template <typename T> inline int ws_typed(b200c_ctx* c, int slot, size_t count, T** out) {
+    void* p; int rc = ws_get(c, slot, count * sizeof(T), &p); *out = (T*)p; return rc;
+}
+
+inline void timing_begin(b200c_ctx* c) { c->launches_call = 0; cudaEventRecord(c->ev0, c->stream); c->timing = true; }
+inline int timing_end(b200c_ctx* c) {
+    cudaEventRecord(c->ev1, c->stream);
+    B200C_CUDA_TRY(c, cudaEventSynchronize(c->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms; c->timing = false;
+    return B200C_OK;
+}
+
+// device-wide exclusive scan: out[0..n] (n+1 entries, out[n] = total). TIn = uint32_t or uint64_t. scan_slot0: first of 3 ws slots.
+template <typename TIn> int exclusive_scan(b200c_ctx* c, const TIn* in, uint64_t n, uint64_t* out, int scan_slot0, int depth = 0);
+
+} // namespace b200c

@@ -1,0 +1,196 @@
+// lz4.cuh — warp-cooperative LZ4 block codec for sm_100a, bit-exact with liblz4's LZ4_compress_default for inputs
+// below 64 KiB + 11 (the 16-bit-index hash table regime every SSTable chunk length <= 64 KiB falls in).
+//
+// Replaces the JNI boundary of S/io/compress/LZ4Compressor.java:113-134 (compress) and :136-190 (uncompress).
+// One warp owns one chunk. The greedy match finder is sequential by definition (the hash table state after position i
+// decides what position i+1 sees), so the warp speculates: 32 consecutive search attempts are evaluated at once —
+// hashes, table probes and 4-byte compares in parallel, intra-window table dependencies resolved with match.any —
+// and the first hit in attempt order wins, which is exactly what the sequential loop would have found. Literal runs,
+// match extension and back-tracking ("catch up") are done 32 bytes per step with ballots.
+#pragma once
+#include "common.cuh"
+
+namespace b200c {
+
+enum { LZ4_MINMATCH = 4, LZ4_MFLIMIT = 12, LZ4_LASTLITERALS = 5, LZ4_MINLENGTH = 13, LZ4_HASHLOG_U16 = 13,
+       LZ4_TABLE_ENTRIES = 1 << LZ4_HASHLOG_U16, LZ4_64KLIMIT = 65536 + 11 };
+
+__host__ __device__ __forceinline__ int lz4_compress_bound(int n) { return n + n / 255 + 16; }
+__device__ __forceinline__ uint32_t lz4_hash_u16(uint32_t seq) { return (seq * 2654435761u) >> (32 - LZ4_HASHLOG_U16); }
+
+// distance from the search start of attempt a: steps are 1 for the first 64 attempts after the initial one, then grow by one
+// every 64 attempts (LZ4_skipTrigger = 6, acceleration = 1)
+__device__ __forceinline__ int lz4_attempt_offset(int a) {
+    if (a <= 65) return a;
+    int m = a - 1, q = m >> 6, r = m & 63;
+    return 1 + 32 * q * (q + 1) + r * (q + 1);
+}
+
+// Writes `len` (>= 15 case handled by caller) extension bytes: (len/255) x 0xFF then len%255. Returns bytes written.
+__device__ __forceinline__ int lz4_emit_len_ext(uint8_t* out, int rem, int lane) {
+    int nff = rem / 255;
+    for (int i = lane; i < nff; i += 32) out[i] = 255;
+    if (lane == 0) out[nff] = (uint8_t)(rem - nff * 255);
+    return nff + 1;
+}
+
+// s_in: chunk bytes in shared memory (4-byte aligned, >= n + 8 bytes, tail zeroed); s_tab: 8192 x u16 (zeroed here);
+// out: destination (global), capacity >= lz4_compress_bound(n). Returns the compressed size (warp-uniform).
+__device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, uint8_t* out, int lane) {
+    const uint32_t* in32 = (const uint32_t*)s_in;
+    {   // zero the hash table: 16 KiB, 16 bytes per lane per step
+        uint4* t4 = (uint4*)s_tab;
+        for (int i = lane; i < (LZ4_TABLE_ENTRIES * 2) / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    int anchor = 0, op = 0;
+    const int mfl1 = n - LZ4_MFLIMIT + 1;        // mflimitPlusOne
+    const int matchlimit = n - LZ4_LASTLITERALS;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    if (n >= LZ4_MINLENGTH) {
+        // "First byte": position 0 is inserted with value 0 — already the zeroed state.
+        int fwd = 1;
+        for (;;) {
+            int ip, match, token_pos;
+            // ---- search: 32 attempts per step -------------------------------------------------------------------
+            bool ended = false;
+            for (int a0 = 0;; a0 += 32) {
+                int a = a0 + lane;
+                int p = fwd + lz4_attempt_offset(a);
+                int pn = fwd + lz4_attempt_offset(a + 1);
+                bool valid = pn <= mfl1;
+                uint32_t seq = valid ? rd32_at(in32, p) : 0u;
+                uint32_t h = lz4_hash_u16(seq);
+                int cand = valid ? (int)s_tab[h] : 0;
+                uint32_t same = __match_any_sync(FULL_MASK, valid ? h : (0x10000u | lane));
+                uint32_t prev = same & lt_mask;
+                int src = prev ? (31 - __clz(prev)) : lane;
+                int pc = __shfl_sync(FULL_MASK, p, src);
+                if (prev) cand = pc;
+                bool hit = valid && (rd32_at(in32, cand) == seq);
+                uint32_t hits = __ballot_sync(FULL_MASK, hit);
+                uint32_t inval = __ballot_sync(FULL_MASK, !valid);
+                int first_hit = hits ? (__ffs(hits) - 1) : 32;
+                int first_inv = inval ? (__ffs(inval) - 1) : 32;
+                if (first_hit < first_inv) {
+                    uint32_t le = (first_hit == 31) ? FULL_MASK : ((2u << first_hit) - 1u);
+                    uint32_t later_same = same & le & ~lt_mask & ~(1u << lane);
+                    if (lane <= first_hit && !later_same) s_tab[h] = (uint16_t)p;
+                    ip = __shfl_sync(FULL_MASK, p, first_hit);
+                    match = __shfl_sync(FULL_MASK, cand, first_hit);
+                    break;
+                }
+                if (first_inv < 32) { ended = true; break; }
+                {
+                    uint32_t later_same = same & ~lt_mask & ~(1u << lane);
+                    if (!later_same) s_tab[h] = (uint16_t)p;
+                }
+                __syncwarp();
+            }
+            if (ended) break;
+            __syncwarp();
+
+            // ---- catch up: extend the match backwards -----------------------------------------------------------
+            for (;;) {
+                int j = lane + 1;
+                bool ok = (ip - j >= anchor) && (match - j >= 0) && (s_in[ip - j] == s_in[match - j]);
+                uint32_t b = __ballot_sync(FULL_MASK, ok);
+                int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
+                ip -= steps; match -= steps;
+                if (steps < 32) break;
+            }
+            // ---- literals ---------------------------------------------------------------------------------------
+            int lit = ip - anchor;
+            token_pos = op++;
+            if (lit >= 15) op += lz4_emit_len_ext(out + op, lit - 15, lane);
+            for (int i = lane; i < lit; i += 32) out[op + i] = s_in[anchor + i];
+            op += lit;
+            int lit_nibble = lit < 15 ? lit : 15;
+
+            for (;;) {   // _next_match
+                if (lane == 0) { int off = ip - match; out[op] = (uint8_t)off; out[op + 1] = (uint8_t)(off >> 8); }
+                op += 2;
+                // match length beyond MINMATCH, limited by matchlimit (LZ4_count)
+                int mc = 0;
+                {
+                    int pi = ip + LZ4_MINMATCH, pm = match + LZ4_MINMATCH;
+                    for (;;) {
+                        int i = mc + lane;
+                        bool eq = (pi + i < matchlimit) && (s_in[pi + i] == s_in[pm + i]);
+                        uint32_t b = __ballot_sync(FULL_MASK, eq);
+                        if (b == FULL_MASK) { mc += 32; continue; }
+                        mc += __ffs(~b) - 1;
+                        break;
+                    }
+                }
+                ip += mc + LZ4_MINMATCH;
+                if (lane == 0) out[token_pos] = (uint8_t)((lit_nibble << 4) | (mc < 15 ? mc : 15));
+                if (mc >= 15) op += lz4_emit_len_ext(out + op, mc - 15, lane);
+                anchor = ip;
+                if (ip >= mfl1) break;
+                // fill table at ip-2, then test the position right after the match
+                int cand = 0;
+                uint32_t seq_ip = rd32_at(in32, ip);
+                if (lane == 0) {
+                    s_tab[lz4_hash_u16(rd32_at(in32, ip - 2))] = (uint16_t)(ip - 2);
+                    uint32_t h = lz4_hash_u16(seq_ip);
+                    cand = s_tab[h];
+                    s_tab[h] = (uint16_t)ip;
+                }
+                cand = __shfl_sync(FULL_MASK, cand, 0);
+                if (rd32_at(in32, cand) == seq_ip) {
+                    token_pos = op++; lit_nibble = 0; match = cand;
+                    continue;
+                }
+                break;
+            }
+            __syncwarp();
+            if (ip >= mfl1) break;
+            fwd = ip + 1;
+        }
+    }
+    // ---- last literals ------------------------------------------------------------------------------------------
+    {
+        int last = n - anchor;
+        if (lane == 0) out[op] = (uint8_t)((last < 15 ? last : 15) << 4);
+        op++;
+        if (last >= 15) op += lz4_emit_len_ext(out + op, last - 15, lane);
+        for (int i = lane; i < last; i += 32) out[op + i] = s_in[anchor + i];
+        op += last;
+    }
+    return op;
+}
+
+// LZ4_decompress_safe semantics. src: compressed block (global, n bytes); s_out: destination in shared memory (cap bytes).
+// Returns decoded size or -1 on malformed input (warp-uniform). Literal and match copies run 32 bytes per step.
+__device__ int lz4_decompress_warp(const uint8_t* __restrict__ src, int n, uint8_t* s_out, int cap, int lane) {
+    int ip = 0, op = 0;
+    if (n == 0) return cap == 0 ? 0 : -1;
+    for (;;) {
+        if (ip >= n) return -1;
+        uint32_t token = src[ip++];
+        int len = token >> 4;
+        if (len == 15) { uint32_t s; do { if (ip >= n) return -1; s = src[ip++]; len += (int)s; } while (s == 255 && len < (1 << 24)); }
+        if (n - ip < len || cap - op < len) return -1;
+        for (int i = lane; i < len; i += 32) s_out[op + i] = src[ip + i];
+        op += len; ip += len;
+        if (ip == n) break;
+        if (n - ip < 2) return -1;
+        int offset = (int)src[ip] | ((int)src[ip + 1] << 8); ip += 2;
+        if (offset == 0 || offset > op) return -1;
+        int ml = token & 15;
+        if (ml == 15) { uint32_t s; do { if (ip >= n) return -1; s = src[ip++]; ml += (int)s; } while (s == 255 && ml < (1 << 24)); }
+        ml += LZ4_MINMATCH;
+        if (cap - op < ml) return -1;
+        __syncwarp();
+        const uint8_t* m = s_out + op - offset;
+        for (int i = lane; i < ml; i += 32) { int j = i; if (j >= offset) j %= offset; s_out[op + i] = m[j]; }
+        op += ml;
+        __syncwarp();
+    }
+    __syncwarp();
+    return op;
+}
+
+} // namespace b200c

@@ -1,0 +1,218 @@
+/*
+ * b200c.h — C ABI of libb200compact.so: the B200-native (sm_100a) SSTable compaction engine.
+ *
+ * This is the drop-in boundary a JNI (or JNA) shim in org.apache.cassandra.{db.compaction, io.compress} binds.
+ * Plain pointers and sizes only. All host pointers are caller-owned (ideally pinned / registered DirectByteBuffers,
+ * see b200c_host_register); results are written into caller-provided buffers. The library is re-entrant: one
+ * b200c_ctx per calling thread (one per CompactionExecutor thread), each with its own CUDA stream and workspace.
+ * No callbacks into the caller. No CPU fallback: without a CUDA device every entry point fails with B200C_ECUDA.
+ *
+ * Reference interfaces replaced (S/ = src/java/org/apache/cassandra/ in apache/cassandra @ 7446529e):
+ *   b200c_compact              <- CompactionTask.runMayThrow hot loop              S/db/compaction/CompactionTask.java:184-236
+ *                                 (CompactionIterator S/db/compaction/CompactionIterator.java:122-160 over ISSTableScanner
+ *                                  S/io/sstable/ISSTableScanner.java:34-41, into CompactionAwareWriter.append
+ *                                  S/db/compaction/writers/CompactionAwareWriter.java:138-142)
+ *   b200c_compress_chunks      <- CompressedSequentialWriter.flushData             S/io/compress/CompressedSequentialWriter.java:140-206
+ *                                 + ChecksumWriter.appendDirect                    S/io/util/ChecksumWriter.java:62-89
+ *                                 + CompressionMetadata.Writer.addOffset           S/io/compress/CompressionMetadata.java:366-375
+ *   b200c_decompress_chunks    <- CompressedChunkReader.readChunk                  S/io/util/CompressedChunkReader.java:103-173
+ *   b200c_compress / _uncompress <- ICompressor.compress / uncompress              S/io/compress/ICompressor.java:28-86
+ *                                 (LZ4Compressor S/io/compress/LZ4Compressor.java:113-190, SnappyCompressor.java:77-105)
+ *   b200c_poll / b200c_cancel  <- CompactionInfo.Holder progress + isStopRequested S/db/compaction/CompactionIterator.java:167-176,709-742
+ */
+#ifndef B200C_H
+#define B200C_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200C_ABI_VERSION 1
+
+/* return codes (0 = success). The shim maps them to the reference's exceptions:
+ * ECORRUPT -> CorruptSSTableException + markSuspect, ECANCELLED -> CompactionInterruptedException,
+ * EUNSUPPORTED -> fall back to scheduling a stock CompactionTask (decision of the Java strategy, not of this library). */
+enum {
+    B200C_OK = 0,
+    B200C_EINVAL = -1,        /* bad argument */
+    B200C_ECUDA = -2,         /* CUDA error / no device; b200c_last_error has the text */
+    B200C_ECORRUPT = -3,      /* checksum mismatch or malformed input; see b200c_corruption */
+    B200C_ECANCELLED = -4,
+    B200C_EUNSUPPORTED = -5,  /* schema/feature outside the supported envelope (static rows, complex columns, counters...) */
+    B200C_ENOMEM = -6,        /* device or host workspace exhausted */
+    B200C_ETOOSMALL = -7      /* a caller-provided output buffer is too small; required sizes are reported */
+};
+
+enum { B200C_COMP_NONE = 0, B200C_COMP_LZ4 = 1, B200C_COMP_SNAPPY = 2 };
+
+typedef struct b200c_ctx b200c_ctx;
+
+typedef struct b200c_corruption {
+    int32_t  input;           /* index of the input sstable (0 for the codec entry points) */
+    int32_t  kind;            /* 1 = chunk CRC mismatch, 2 = malformed compressed chunk, 3 = malformed Index.db, 4 = malformed Data.db */
+    uint64_t chunk;           /* chunk index */
+    uint64_t offset;          /* byte offset in the component file */
+} b200c_corruption;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+int          b200c_abi_version(void);
+int          b200c_device_count(void);
+/* device: CUDA ordinal. workspace_bytes: initial device workspace (0 = grow on demand). NULL on failure. */
+b200c_ctx*   b200c_create(int device, size_t workspace_bytes);
+void         b200c_destroy(b200c_ctx*);
+const char*  b200c_last_error(b200c_ctx*);
+/* pin/unpin caller memory (DirectByteBuffer addresses) so cudaMemcpyAsync runs at PCIe speed */
+int          b200c_host_register(void* p, size_t n);
+int          b200c_host_unregister(void* p);
+/* device memory helpers for callers that keep buffers resident in HBM (bench `value`, GPU-side pipelines) */
+int          b200c_dev_alloc(b200c_ctx*, size_t n, void** dptr);
+int          b200c_dev_free(b200c_ctx*, void* dptr);
+int          b200c_memcpy_h2d(b200c_ctx*, void* dst_dev, const void* src_host, size_t n);
+int          b200c_memcpy_d2h(b200c_ctx*, void* dst_host, const void* src_dev, size_t n);
+int          b200c_sync(b200c_ctx*);
+/* elapsed device time (ms, CUDA events on the ctx stream) of the kernels of the last call, and how many launched */
+double       b200c_last_kernel_ms(b200c_ctx*);
+uint64_t     b200c_last_kernel_launches(b200c_ctx*);
+uint64_t     b200c_total_kernel_launches(b200c_ctx*);
+
+/* ---- chunk codec: the CompressedSequentialWriter / CompressedChunkReader data plane, batched ---------------------
+ * b200c_compress_chunks: `in[0..n)` is an uncompressed Data stream. Chunk i = bytes [i*chunk_len, min((i+1)*chunk_len, n)).
+ * Writes the Data.db image to `out`: for every chunk the compressor output (LZ4: 4-byte LE length + block) followed by the
+ * 4-byte big-endian CRC32 of the bytes as written; chunk_offsets[i] = file offset of chunk i (CompressionInfo.db payload);
+ * *digest = CRC32 of the whole image (Digest.crc32). If compressed_len >= max_compressed_len the chunk is stored raw
+ * (padded with zeroes up to max_compressed_len when shorter) exactly as flushData does; pass INT32_MAX for the default
+ * min_compress_ratio = 0. `out_cap` must be >= b200c_compress_bound(...). `flags` bit0: in/out/chunk_offsets are DEVICE pointers. */
+uint64_t     b200c_compress_bound(int compressor, uint64_t n, int chunk_len);
+uint64_t     b200c_chunk_count(uint64_t n, int chunk_len);
+int          b200c_compress_chunks(b200c_ctx*, int compressor, const uint8_t* in, uint64_t n, int chunk_len,
+                                   int max_compressed_len, uint8_t* out, uint64_t out_cap, uint64_t* out_len,
+                                   uint64_t* chunk_offsets, uint32_t* digest, int flags);
+/* b200c_decompress_chunks: inverse. `data` is a Data.db image, `chunk_offsets[nchunks]` from CompressionInfo.db,
+ * `data_length` the uncompressed length. Verifies every chunk CRC when verify_crc != 0 (crc_check_chance = 1.0).
+ * On B200C_ECORRUPT *where (optional) describes the first bad chunk. flags bit0: data/chunk_offsets/out are DEVICE pointers. */
+int          b200c_decompress_chunks(b200c_ctx*, int compressor, const uint8_t* data, uint64_t data_len,
+                                     const uint64_t* chunk_offsets, uint64_t nchunks, int chunk_len, int max_compressed_len,
+                                     uint64_t data_length, uint8_t* out, int verify_crc, b200c_corruption* where, int flags);
+#define B200C_FLAG_DEVICE_PTRS 1
+
+/* ICompressor single-buffer contract (degenerate one-chunk batch; PCIe-latency bound — the batched calls are the fast path).
+ * Return the number of bytes written to `out`, or a negative error code. */
+int          b200c_initial_compressed_buffer_length(int compressor, int chunk_len);
+int          b200c_compress(b200c_ctx*, int compressor, const uint8_t* in, int n, uint8_t* out, int out_cap);
+int          b200c_uncompress(b200c_ctx*, int compressor, const uint8_t* in, int n, uint8_t* out, int out_cap);
+
+/* ---- compaction ---------------------------------------------------------------------------------------------- */
+
+/* comparison / layout class of a CQL type, as AbstractType exposes it (S/db/marshal/AbstractType.java:66-82,212-215,490,535-552) */
+enum {
+    B200C_TYPE_BYTES = 0,     /* variable length, unsigned lexicographic compare (text, ascii, blob, varchar) */
+    B200C_TYPE_FIXED_SIGNED = 1, /* fixed length big-endian two's complement, signed compare (bigint 8, int 4, smallint 2, tinyint 1, timestamp 8, counter n/a) */
+    B200C_TYPE_FIXED_BYTES = 2,  /* fixed length, unsigned lexicographic compare (boolean 1, and any fixed type used only as a value) */
+    B200C_TYPE_VAR_SIGNED = 3    /* variable length payload holding a fixed-width signed int: empty value sorts first (LongType with empty) */
+};
+
+typedef struct b200c_column {
+    int32_t  type;            /* B200C_TYPE_* */
+    int32_t  fixed_len;       /* value length in bytes if fixed, else 0 (AbstractType.valueLengthIfFixed) */
+} b200c_column;
+
+typedef struct b200c_encoding_stats {   /* S/db/rows/EncodingStats.java: base values the deltas in the files are against */
+    int64_t  min_timestamp;
+    int64_t  min_local_deletion_time;   /* widened; as EncodingStats.minLocalDeletionTime */
+    int32_t  min_ttl;
+    int32_t  _pad;
+} b200c_encoding_stats;
+
+#define B200C_MAX_CLUSTERING 8
+#define B200C_MAX_COLUMNS    64
+#define B200C_MAX_INPUTS     128
+
+typedef struct b200c_input {
+    const uint8_t*  data;               /* Data.db image (compressed chunks + inline CRCs) */
+    uint64_t        data_len;
+    const uint8_t*  index;              /* Index.db image */
+    uint64_t        index_len;
+    const uint64_t* chunk_offsets;      /* CompressionInfo.db chunk offsets */
+    uint64_t        nchunks;
+    uint64_t        data_length;        /* uncompressed length (CompressionInfo.db dataLength) */
+    int32_t         compressor;         /* B200C_COMP_* */
+    int32_t         chunk_len;
+    int32_t         max_compressed_len; /* INT32_MAX when min_compress_ratio = 0 */
+    int32_t         ncolumns;           /* regular columns in this sstable's SerializationHeader, in header order */
+    int32_t         column_map[B200C_MAX_COLUMNS]; /* header column i -> index in manifest.columns (output header) */
+    b200c_encoding_stats header_stats;  /* SerializationHeader.Component stats used to DEcode this input */
+    int32_t         _pad;
+    int32_t         level;              /* informational (LCS level) */
+} b200c_input;
+
+typedef struct b200c_manifest {
+    uint32_t        abi_version;        /* B200C_ABI_VERSION */
+    int32_t         ninputs;
+    const b200c_input* inputs;
+    /* schema: partition key is opaque bytes ordered by (Murmur3 token, unsigned bytes) — S/db/DecoratedKey.java:79-91 */
+    int32_t         nclustering;
+    b200c_column    clustering[B200C_MAX_CLUSTERING];
+    int32_t         ncolumns;           /* regular simple columns of the OUTPUT header (union of inputs), header order */
+    b200c_column    columns[B200C_MAX_COLUMNS];
+    int32_t         has_static;         /* must be 0 (B200C_EUNSUPPORTED otherwise) */
+    /* output encoding: SerializationHeader.make (S/db/SerializationHeader.java:77-100) = min over inputs' StatsMetadata */
+    b200c_encoding_stats out_stats;
+    int32_t         out_compressor;
+    int32_t         out_chunk_len;
+    int32_t         out_max_compressed_len;
+    int32_t         column_index_size;  /* bytes; 65536 default for big format (BigFormatPartitionWriter.java:49,73) */
+    /* determinism inputs: */
+    int64_t         now_in_sec;         /* CompactionTask.java:183 */
+    int64_t         gc_before;          /* CompactionManager.java:2001-2006 */
+    int64_t         purge_max_timestamp;/* getPurgeEvaluator threshold: tombstones purgeable iff timestamp < this. INT64_MAX = no overlaps */
+    int32_t         tombstone_option;   /* must be 0 (NONE) */
+    int32_t         enforce_strict_liveness; /* must be 0 */
+    /* token range (lo, hi] handled by this call; lo = INT64_MIN and hi = INT64_MAX for the whole ring */
+    int64_t         token_lo;
+    int64_t         token_hi;
+    /* LCS: switch output file when on-disk bytes exceed this (MaxSSTableSizeWriter.java:76-79); 0 = single output */
+    uint64_t        max_sstable_bytes;
+} b200c_manifest;
+
+typedef struct b200c_output {           /* one output sstable; caller provides the buffers */
+    uint8_t*  data;        uint64_t data_cap;     uint64_t data_len;      /* Data.db image */
+    uint8_t*  index;       uint64_t index_cap;    uint64_t index_len;     /* Index.db image */
+    uint64_t* chunk_offsets; uint64_t chunk_cap;  uint64_t nchunks;       /* CompressionInfo.db chunk offsets */
+    uint64_t  data_length;                                                /* uncompressed length */
+    uint32_t  digest;                                                     /* Digest.crc32 value */
+    uint32_t  _pad;
+    uint64_t  partitions;                                                 /* partitions written */
+    uint64_t  rows;                                                       /* rows + markers written */
+} b200c_output;
+
+typedef struct b200c_result {
+    int32_t   noutputs_cap;             /* in: entries in outputs[] */
+    int32_t   noutputs;                 /* out */
+    b200c_output* outputs;
+    uint64_t  bytes_read;               /* uncompressed input bytes (metric numerator, CompactionTask.java:258) */
+    uint64_t  bytes_written;            /* uncompressed output bytes */
+    uint64_t  total_source_rows;        /* rows + markers read, CompactionIterator.totalSourceCQLRows :368 */
+    uint64_t  input_partitions;
+    uint64_t  merged_row_counts[B200C_MAX_INPUTS]; /* [i] = output partitions merged from i+1 inputs, CompactionIterator.java:188-197 */
+    uint64_t  required_data_cap;        /* set on B200C_ETOOSMALL */
+    uint64_t  required_index_cap;
+    uint64_t  required_chunk_cap;
+    b200c_corruption corruption;        /* set on B200C_ECORRUPT */
+    double    kernel_ms;                /* device time of all kernels of this call */
+    double    total_ms;                 /* host wall time of the call incl. copies */
+    uint64_t  kernel_launches;
+} b200c_result;
+
+/* flags: bit0 = input/outputs buffers are DEVICE pointers (inputs resident in HBM; used for the kernel-only metric) */
+int          b200c_compact(b200c_ctx*, const b200c_manifest*, b200c_result*, int flags);
+
+typedef struct b200c_progress { uint64_t bytes_scanned; uint64_t bytes_total; int32_t stage; int32_t _pad; } b200c_progress;
+int          b200c_poll(b200c_ctx*, b200c_progress*);   /* callable from another thread */
+void         b200c_cancel(b200c_ctx*);                  /* callable from another thread; the running call returns B200C_ECANCELLED */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200C_H */

@@ -1,0 +1,105 @@
+"""SSTable component files (big format, version `oa`) as the host side needs them: read the components of an input
+sstable, derive what the C-ABI manifest carries (schema classes, EncodingStats, StatsMetadata minima), write outputs.
+
+Mirrors what the Java shim gets for free from SSTableReader (`sstable.header`, `getSSTableMetadata()`, `getCompressionMetadata()`):
+  Statistics.db layout  S/io/sstable/metadata/MetadataSerializer.java:67-112 (toc + per-component CRC)
+  HEADER component      S/db/SerializationHeader.java:451-460 ; EncodingStats S/db/rows/EncodingStats.java:262-277
+  STATS component       S/io/sstable/metadata/StatsMetadata.java:402-425
+"""
+import os, struct
+from .. import native
+from .compress import CompressionMetadata
+
+TIMESTAMP_EPOCH = 1442880000000000      # EncodingStats.TIMESTAMP_EPOCH (2015-09-22T00:00Z in µs), EncodingStats.java:47-64
+DELETION_TIME_EPOCH = 1442880000
+NO_DELETION_TIME = (1 << 63) - 1
+MARSHAL = "org.apache.cassandra.db.marshal."
+
+def _vint(b, p):
+    f = b[p]
+    if f < 0x80: return f, p + 1
+    extra = 8 if f == 0xFF else (8 - (f ^ 0xFF).bit_length())
+    v = f & (0xFF >> extra)
+    for i in range(extra): v = (v << 8) | b[p + 1 + i]
+    return v, p + 1 + extra
+
+def _vbytes(b, p):
+    n, p = _vint(b, p); return b[p:p + n], p + n
+
+def type_class(type_string: str):
+    """AbstractType -> (B200C_TYPE_*, valueLengthIfFixed) for the comparison/layout classes the engine implements."""
+    t = type_string
+    if t.startswith(MARSHAL): t = t[len(MARSHAL):]
+    fixed_signed = {"LongType": 8, "TimestampType": 8, "DateType": 8, "Int32Type": 4}
+    fixed_bytes = {"DoubleType": 8, "FloatType": 4, "BooleanType": 1, "UUIDType": 16, "TimeUUIDType": 16, "LexicalUUIDType": 16}
+    if t in fixed_signed: return native.TYPE_FIXED_SIGNED, fixed_signed[t]
+    if t in fixed_bytes: return native.TYPE_FIXED_BYTES, fixed_bytes[t]
+    if t in ("ShortType", "ByteType"): return native.TYPE_VAR_SIGNED, 0
+    if t in ("UTF8Type", "AsciiType", "BytesType"): return native.TYPE_BYTES, 0
+    raise native.UnsupportedError(native.EUNSUPPORTED, "type outside the supported envelope: " + type_string)
+
+CLUSTERING_OK = {"LongType", "TimestampType", "DateType", "Int32Type", "ShortType", "ByteType", "UTF8Type", "AsciiType", "BytesType"}
+
+def parse_statistics(b: bytes):
+    (n,) = struct.unpack_from(">i", b, 0)
+    toc = {}
+    p = 8                                              # count + crc
+    for _ in range(n):
+        t, pos = struct.unpack_from(">ii", b, p); p += 8; toc[t] = pos
+    out = {}
+    # STATS (2)
+    p = toc[2]
+    for _ in range(2):                                 # two EstimatedHistograms
+        (sz,) = struct.unpack_from(">i", b, p); p += 4 + 16 * sz
+    p += 12                                            # CommitLogPosition
+    mn_ts, mx_ts, mn_ldt, mx_ldt, mn_ttl, mx_ttl = struct.unpack_from(">qqIIii", b, p)
+    out["min_timestamp"] = mn_ts; out["max_timestamp"] = mx_ts
+    out["min_local_deletion_time"] = NO_DELETION_TIME if mn_ldt == 0xFFFFFFFF else mn_ldt
+    out["min_ttl"] = mn_ttl
+    # HEADER (3)
+    p = toc[3]
+    v, p = _vint(b, p); hts = v + TIMESTAMP_EPOCH
+    v, p = _vint(b, p); hldt = (v & 0xFFFFFFFF) + DELETION_TIME_EPOCH if v < (1 << 32) else ((v - (1 << 64)) + DELETION_TIME_EPOCH)
+    v, p = _vint(b, p); httl = v
+    out["header_stats"] = (hts, hldt, httl)
+    kt, p = _vbytes(b, p); out["key_type"] = kt.decode()
+    nc, p = _vint(b, p); cl = []
+    for _ in range(nc):
+        t, p = _vbytes(b, p); cl.append(t.decode())
+    out["clustering_types"] = cl
+    cols = {}
+    for kind in ("static_columns", "regular_columns"):
+        k, p = _vint(b, p); lst = []
+        for _ in range(k):
+            name, p = _vbytes(b, p); t, p = _vbytes(b, p); lst.append((bytes(name), t.decode()))
+        cols[kind] = lst
+    out.update(cols)
+    return out
+
+class SSTable:
+    """The components of one big-format sstable, in memory (what SSTableReader holds open for a compaction input)."""
+    def __init__(self, data, index, compression: CompressionMetadata, header_stats, stats_min, clustering_types, regular_columns,
+                 static_columns=(), key_type=MARSHAL + "BytesType", level=0, generation=0):
+        self.data = data; self.index = index; self.compression = compression
+        self.header_stats = tuple(header_stats)            # (minTimestamp, minLocalDeletionTime, minTTL) of the HEADER component
+        self.stats_min = tuple(stats_min)                  # (minTimestamp, minLocalDeletionTime, minTTL) of the STATS component
+        self.clustering_types = list(clustering_types)
+        self.regular_columns = list(regular_columns)       # [(name bytes, type string)] in header order
+        self.static_columns = list(static_columns)
+        self.key_type = key_type; self.level = level; self.generation = generation
+
+    @classmethod
+    def open(cls, base_path: str, generation=0):
+        """base_path: '<dir>/oa-1-big-' (descriptor prefix)."""
+        rd = lambda c: open(base_path + c, "rb").read()
+        st = parse_statistics(rd("Statistics.db"))
+        return cls(rd("Data.db"), rd("Index.db"), CompressionMetadata.parse(rd("CompressionInfo.db")), st["header_stats"],
+                   (st["min_timestamp"], st["min_local_deletion_time"], st["min_ttl"]), st["clustering_types"],
+                   st["regular_columns"], st["static_columns"], st["key_type"], generation=generation)
+
+def write_components(base_path: str, data: bytes, index: bytes, compression: CompressionMetadata, digest: int):
+    """Writes the components the engine produces (Data, Index, CompressionInfo, Digest). Statistics/Filter/Summary are
+    SURVEY §8f 'next' rows and stay with the Java writer for now."""
+    for comp, payload in (("Data.db", data), ("Index.db", index), ("CompressionInfo.db", compression.serialize()),
+                          ("Digest.crc32", str(digest).encode())):
+        with open(base_path + comp, "wb") as f: f.write(payload)

@@ -1,0 +1,708 @@
+// oracle/compaction.cc — TEST INFRASTRUCTURE (CPU oracle). Not part of the product path.
+//
+// CPU restatement of Cassandra's compaction hot path for big-format `oa` SSTables, driven by the same manifest struct as
+// the product's C ABI (include/b200c.h) so that tests can hand both sides identical inputs and compare outputs byte for byte.
+// One call = one CompactionTask.runMayThrow hot loop (S/db/compaction/CompactionTask.java:184-236), single threaded as the
+// reference is. S/ = /root/reference/src/java/org/apache/cassandra/. Each block cites the file:line it follows.
+//
+// Scope restated: simple regular columns, no static rows, no complex columns/counters, tombstoneOption NONE, no 2i
+// (rowProcessingNeeded() == false), forward order. Anything else returns B200C_EUNSUPPORTED — same envelope as the GPU engine.
+#include "codec.h"
+#include "../include/b200c.h"
+#include <cstring>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <chrono>
+#include <climits>
+
+namespace oracle {
+
+static const int64_t NO_TS = INT64_MIN;          // LivenessInfo.NO_TIMESTAMP
+static const int64_t NO_DEL = INT64_MAX;         // Cell.NO_DELETION_TIME / LivenessInfo.NO_EXPIRATION_TIME
+static const int32_t EXPIRED_TTL = INT32_MAX;    // LivenessInfo.EXPIRED_LIVENESS_TTL
+
+struct Unsupported { std::string what; };
+struct Corrupt { int input; int kind; uint64_t chunk; uint64_t offset; std::string what; };
+
+// ---- DeletionTime: S/db/DeletionTime.java:46 (LIVE), :158-176 (supersedes/deletes) -------------------------------
+struct DT {
+    int64_t mfda = INT64_MIN; int64_t ldt = INT64_MAX;
+    bool live() const { return mfda == INT64_MIN && ldt == INT64_MAX; }
+    bool supersedes(const DT& o) const { return mfda > o.mfda || (mfda == o.mfda && ldt > o.ldt); }
+    bool deletes(int64_t ts) const { return ts <= mfda; }
+    bool operator==(const DT& o) const { return mfda == o.mfda && ldt == o.ldt; }
+};
+// ---- LivenessInfo: S/db/LivenessInfo.java:40-340 ----------------------------------------------------------------------
+struct Live {
+    int64_t ts = NO_TS; int32_t ttl = 0; int64_t ldt = NO_DEL;
+    bool empty() const { return ts == NO_TS; }
+    bool expiring() const { return ttl != 0; }
+    bool expired() const { return ttl == EXPIRED_TTL; }
+    bool is_live(int64_t now) const { if (empty()) return false; if (expired()) return false; if (expiring()) return now < ldt; return true; }
+    // :216-225
+    bool supersedes(const Live& o) const {
+        if (ts != o.ts) return ts > o.ts;
+        if (expired() != o.expired()) return expired();
+        if (expiring() == o.expiring()) return ldt > o.ldt;
+        return expiring();
+    }
+};
+struct Val { const uint8_t* p = nullptr; int32_t len = 0; bool null = false; };
+struct Clust { uint8_t kind = 4; int n = 0; Val v[B200C_MAX_CLUSTERING]; };
+struct CellV {
+    int col; int64_t ts; int32_t ttl; int64_t ldt; const uint8_t* val; int32_t vlen;
+    bool tombstone() const { return ldt != NO_DEL && ttl == 0; }       // AbstractCell.java:58-61
+    bool expiring() const { return ttl != 0; }
+    bool is_live(int64_t now) const { return ldt == NO_DEL || (ttl != 0 && now < ldt); }   // :53-56
+};
+struct Unf {
+    bool is_row = true;
+    Clust c;
+    // row
+    Live info; DT del; std::vector<CellV> cells;
+    // marker: bound -> dt_open or dt_close by kind; boundary -> both
+    DT m_close, m_open;
+};
+
+// ClusteringPrefix.Kind: S/db/ClusteringPrefix.java:65-82
+enum { K_EXCL_END = 0, K_INCL_START = 1, K_EXCL_END_INCL_START = 2, K_STATIC = 3, K_CLUSTERING = 4, K_INCL_END_EXCL_START = 5, K_INCL_END = 6, K_EXCL_START = 7 };
+static inline int kind_comparison(int k) { static const int c[8] = {0, 0, 0, 1, 2, 3, 3, 3}; return c[k]; }
+static inline int kind_vs_clustering(int k) { static const int c[8] = {-1, -1, -1, -1, 0, 1, 1, 1}; return c[k]; }
+static inline bool kind_is_boundary(int k) { return k == K_EXCL_END_INCL_START || k == K_INCL_END_EXCL_START; }
+static inline bool kind_is_start(int k) { return k == K_INCL_START || k == K_EXCL_START; }
+
+struct Schema {
+    int nclust; b200c_column clust[B200C_MAX_CLUSTERING];
+    int ncols; b200c_column cols[B200C_MAX_COLUMNS];
+};
+
+// AbstractType.compare for the supported comparison classes (S/db/marshal/AbstractType.java:212-215; LongType.compareLongs:
+// empty < non-empty, first byte signed then unsigned bytes; BytesType/UTF8Type: unsigned lexicographic)
+static int compare_value(const b200c_column& t, const Val& a, const Val& b) {
+    if (t.type == B200C_TYPE_FIXED_SIGNED || t.type == B200C_TYPE_VAR_SIGNED) {
+        if (a.len == 0 || b.len == 0) return a.len == 0 ? (b.len == 0 ? 0 : -1) : 1;
+        int d = (int)(int8_t)a.p[0] - (int)(int8_t)b.p[0];
+        if (d) return d < 0 ? -1 : 1;
+        int n = std::min(a.len, b.len);
+        int c = memcmp(a.p + 1, b.p + 1, n - 1);
+        if (c) return c < 0 ? -1 : 1;
+        return a.len == b.len ? 0 : (a.len < b.len ? -1 : 1);
+    }
+    int n = std::min(a.len, b.len);
+    int c = n ? memcmp(a.p, b.p, n) : 0;
+    if (c) return c < 0 ? -1 : 1;
+    return a.len == b.len ? 0 : (a.len < b.len ? -1 : 1);
+}
+// ClusteringComparator.compare: S/db/ClusteringComparator.java:140-157,184-192
+static int compare_clust(const Schema& s, const Clust& a, const Clust& b) {
+    int m = std::min(a.n, b.n);
+    for (int i = 0; i < m; i++) {
+        const Val& x = a.v[i]; const Val& y = b.v[i];
+        if (x.null) { if (!y.null) return -1; continue; }
+        if (y.null) return 1;
+        int c = compare_value(s.clust[i], x, y);
+        if (c) return c;
+    }
+    if (a.n == b.n) { int d = kind_comparison(a.kind) - kind_comparison(b.kind); return d < 0 ? -1 : (d > 0 ? 1 : 0); }
+    return a.n < b.n ? kind_vs_clustering(a.kind) : -kind_vs_clustering(b.kind);
+}
+
+// ---- input side ---------------------------------------------------------------------------------------------------------
+struct Source {
+    int idx;
+    const b200c_input* in;
+    std::vector<uint8_t> data;      // uncompressed Data stream
+    uint64_t pos = 0;               // cursor: start of the current partition
+    // Index.db cursor (BigTableScanner walks Index.db: S/io/sstable/format/big/BigTableScanner.java:135-184)
+    uint64_t ipos = 0;
+    // current partition
+    bool has = false;
+    const uint8_t* key = nullptr; int keylen = 0; int64_t token = 0;
+    DT pdel; uint64_t upos = 0;     // cursor inside the partition (next unfiltered)
+    uint64_t part_start = 0;
+};
+
+struct Reader {
+    const uint8_t* p; const uint8_t* end; int input;
+    uint8_t u8() { need(1); return *p++; }
+    uint16_t u16() { need(2); uint16_t v = (uint16_t)((p[0] << 8) | p[1]); p += 2; return v; }
+    uint64_t vint() { uint64_t v; int n = vint_read(p, end, &v); if (n < 0) throw Corrupt{input, 4, 0, 0, "truncated vint"}; p += n; return v; }
+    // readUnsignedVInt32 = checkedCast(readUnsignedVInt): S/utils/vint/VIntCoding.java:269-272
+    int32_t vint32() { uint64_t v = vint(); int32_t r = (int32_t)v; if ((int64_t)r != (int64_t)v) throw Corrupt{input, 4, 0, 0, "vint32 out of range"}; return r; }
+    void need(size_t n) { if ((size_t)(end - p) < n) throw Corrupt{input, 4, 0, 0, "truncated data"}; }
+    const uint8_t* bytes(size_t n) { need(n); const uint8_t* r = p; p += n; return r; }
+};
+
+// ClusteringPrefix.Serializer.deserializeValuesWithoutSize: S/db/ClusteringPrefix.java:502-522 (header :548-562)
+static void read_clust_values(Reader& r, const Schema& s, int n, Clust& c) {
+    c.n = n;
+    int off = 0;
+    while (off < n) {
+        int limit = std::min(n, off + 32);
+        uint64_t header = r.vint();
+        for (; off < limit; off++) {
+            Val& v = c.v[off];
+            int bit = (off % 32) * 2;          // shifts are modulo 64 in the reference (:555-559)
+            if ((header >> (bit + 1)) & 1) { v = Val{nullptr, 0, true}; continue; }
+            if ((header >> bit) & 1) { v = Val{r.p, 0, false}; continue; }
+            const b200c_column& t = s.clust[off];
+            int len = t.fixed_len > 0 ? t.fixed_len : (int)r.vint32();
+            if (len < 0) throw Corrupt{r.input, 4, 0, 0, "negative value length"};
+            v.p = r.bytes(len); v.len = len; v.null = false;
+        }
+    }
+}
+
+// header.readDeletionTime: S/db/SerializationHeader.java:186-200
+static DT read_delta_dt(Reader& r, const b200c_encoding_stats& hs) {
+    DT d; d.mfda = (int64_t)(r.vint() + (uint64_t)hs.min_timestamp); d.ldt = (int64_t)r.vint32() + hs.min_local_deletion_time; return d;
+}
+
+// DeletionTime.Serializer.deserialize (oa): S/db/DeletionTime.java:222-243
+static DT read_partition_dt(Reader& r) {
+    uint8_t flags = r.u8();
+    if (flags & 0x80) { if (flags != 0x80) throw Corrupt{r.input, 4, 0, 0, "bad DeletionTime flags"}; return DT(); }
+    const uint8_t* b = r.bytes(11);
+    DT d; uint64_t m = flags; for (int i = 0; i < 7; i++) m = (m << 8) | b[i];
+    d.mfda = (int64_t)m; d.ldt = (int64_t)(((uint32_t)b[7] << 24) | ((uint32_t)b[8] << 16) | ((uint32_t)b[9] << 8) | b[10]);
+    return d;
+}
+
+// Cell.decodeLocalDeletionTime: S/db/rows/Cell.java:221-239 (messaging version >= 5.0 for oa)
+static int64_t decode_ldt(int64_t ldt, int32_t ttl) {
+    if (ldt >= ttl) return ldt;
+    if (ldt < 0) return (int64_t)(uint32_t)(int32_t)ldt;
+    if (ttl == EXPIRED_TTL) return ldt;
+    return (int64_t)UINT32_MAX - 1;    // INVALID_DELETION_TIME
+}
+
+// UnfilteredSerializer.deserialize: S/db/rows/UnfilteredSerializer.java:433-645. Returns false at end of partition.
+static bool read_unfiltered(Source& src, const Schema& s, Unf& u) {
+    const b200c_input& in = *src.in;
+    Reader r{src.data.data() + src.upos, src.data.data() + src.data.size(), src.idx};
+    uint8_t flags = r.u8();
+    if (flags & 0x01) { src.upos = r.p - src.data.data(); return false; }
+    const b200c_encoding_stats& hs = in.header_stats;
+    if (flags & 0x02) {
+        u.is_row = false; u.cells.clear();
+        u.c.kind = r.u8();
+        if (u.c.kind > 7 || u.c.kind == K_STATIC || u.c.kind == K_CLUSTERING) throw Corrupt{src.idx, 4, 0, 0, "bad bound kind"};
+        int n = r.u16();
+        if (n > s.nclust) throw Corrupt{src.idx, 4, 0, 0, "bound size"};
+        read_clust_values(r, s, n, u.c);
+        r.vint(); r.vint();                                   // body size, previous unfiltered size
+        if (kind_is_boundary(u.c.kind)) { u.m_close = read_delta_dt(r, hs); u.m_open = read_delta_dt(r, hs); }
+        else if (kind_is_start(u.c.kind)) { u.m_open = read_delta_dt(r, hs); u.m_close = DT(); }
+        else { u.m_close = read_delta_dt(r, hs); u.m_open = DT(); }
+    } else {
+        u.is_row = true;
+        uint8_t ext = (flags & 0x80) ? r.u8() : 0;
+        if (ext & 0x01) throw Unsupported{"static row"};
+        if (ext & 0x02) throw Unsupported{"shadowable deletion"};
+        if (flags & 0x40) throw Unsupported{"complex deletion"};
+        u.c.kind = K_CLUSTERING;
+        read_clust_values(r, s, s.nclust, u.c);
+        r.vint(); r.vint();                                   // row size, previous unfiltered size
+        u.info = Live(); u.del = DT();
+        if (flags & 0x04) u.info.ts = (int64_t)(r.vint() + (uint64_t)hs.min_timestamp);
+        if (flags & 0x08) { u.info.ttl = r.vint32() + hs.min_ttl; u.info.ldt = (int64_t)r.vint32() + hs.min_local_deletion_time; }
+        if (flags & 0x10) u.del = read_delta_dt(r, hs);
+        uint64_t missing = 0;
+        if (!(flags & 0x20)) {                                // Columns.deserializeSubset: S/db/Columns.java:533-560
+            if (in.ncolumns >= 64) throw Unsupported{">= 64 columns"};
+            missing = r.vint();
+        }
+        u.cells.clear();
+        for (int i = 0; i < in.ncolumns; i++) {
+            if ((missing >> i) & 1) continue;
+            int oc = in.column_map[i];
+            const b200c_column& t = s.cols[oc];
+            uint8_t cf = r.u8();                              // Cell.Serializer.deserialize: S/db/rows/Cell.java:307-349
+            bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
+            CellV c; c.col = oc;
+            c.ts = use_ts ? u.info.ts : (int64_t)(r.vint() + (uint64_t)hs.min_timestamp);
+            c.ldt = use_ttl ? u.info.ldt : ((deleted || expiring) ? (int64_t)r.vint32() + hs.min_local_deletion_time : NO_DEL);
+            c.ttl = use_ttl ? u.info.ttl : (expiring ? r.vint32() + hs.min_ttl : 0);
+            c.val = r.p; c.vlen = 0;
+            if (has_value) {
+                int len = t.fixed_len > 0 ? t.fixed_len : (int)r.vint32();
+                if (len < 0) throw Corrupt{src.idx, 4, 0, 0, "negative value length"};
+                c.val = r.bytes(len); c.vlen = len;
+            }
+            if (c.ttl < 0) throw Corrupt{src.idx, 4, 0, 0, "Invalid TTL"};
+            if (c.ldt != NO_DEL) c.ldt = decode_ldt(c.ldt, c.ttl);
+            u.cells.push_back(c);
+        }
+        std::sort(u.cells.begin(), u.cells.end(), [](const CellV& a, const CellV& b) { return a.col < b.col; });
+    }
+    src.upos = r.p - src.data.data();
+    return true;
+}
+
+// CompressedChunkReader.readChunk for every chunk: S/io/util/CompressedChunkReader.java:103-173
+static void load_source(Source& src) {
+    const b200c_input& in = *src.in;
+    src.data.resize(in.data_length + 16);
+    uint64_t nch = in.nchunks;
+    if (nch != (in.data_length + in.chunk_len - 1) / (uint64_t)in.chunk_len) throw Corrupt{src.idx, 2, 0, 0, "chunk count"};
+    for (uint64_t i = 0; i < nch; i++) {
+        uint64_t off = in.chunk_offsets[i];
+        uint64_t next = (i + 1 < nch) ? in.chunk_offsets[i + 1] : in.data_len;
+        if (off + 4 > next || next > in.data_len) throw Corrupt{src.idx, 2, i, off, "chunk bounds"};
+        uint32_t clen = (uint32_t)(next - off - 4);
+        const uint8_t* c = in.data + off;
+        uint32_t stored = ((uint32_t)c[clen] << 24) | ((uint32_t)c[clen + 1] << 16) | ((uint32_t)c[clen + 2] << 8) | c[clen + 3];
+        if (crc32_ieee(0, c, clen) != stored) throw Corrupt{src.idx, 1, i, off, "chunk CRC mismatch"};
+        uint64_t ustart = i * (uint64_t)in.chunk_len;
+        int ulen = (int)std::min<uint64_t>(in.chunk_len, in.data_length - ustart);
+        if ((int64_t)clen >= (int64_t)in.max_compressed_len) {              // raw chunk (:116,219)
+            if ((int)clen < ulen) throw Corrupt{src.idx, 2, i, off, "short raw chunk"};
+            memcpy(src.data.data() + ustart, c, ulen);
+        } else {
+            int got = chunk_decompress(in.compressor, c, (int)clen, src.data.data() + ustart, ulen);
+            if (got != ulen) throw Corrupt{src.idx, 2, i, off, "malformed compressed chunk"};
+        }
+    }
+    src.data.resize(in.data_length);
+}
+
+// advance to the next partition via Index.db (key, position, promoted index skipped): BigTableScanner.java:135-184,
+// RowIndexEntry.Serializer.deserialize S/io/sstable/format/big/RowIndexEntry.java:340-377
+static void next_partition(Source& src, int64_t tok_lo, int64_t tok_hi) {
+    const b200c_input& in = *src.in;
+    for (;;) {
+        if (src.ipos >= in.index_len) { src.has = false; return; }
+        Reader ir{in.index + src.ipos, in.index + in.index_len, src.idx};
+        try {
+            int kl = ir.u16(); const uint8_t* key = ir.bytes(kl);
+            uint64_t pos = ir.vint(); int32_t psize = ir.vint32();
+            if (psize < 0) throw Corrupt{src.idx, 3, 0, src.ipos, "promoted index size"};
+            ir.bytes(psize);
+            src.ipos = ir.p - in.index;
+            int64_t tok = murmur3_token(key, kl);
+            if (!((tok_lo == INT64_MIN || tok > tok_lo) && tok <= tok_hi)) continue;
+            if (pos + 2 + kl > src.data.size() || ((src.data[pos] << 8) | src.data[pos + 1]) != kl || memcmp(src.data.data() + pos + 2, key, kl) != 0)
+                throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db entry does not match Data.db"};
+            Reader r{src.data.data() + pos + 2 + kl, src.data.data() + src.data.size(), src.idx};
+            src.pdel = read_partition_dt(r);                               // SSTableIdentityIterator.create :62-78
+            src.key = src.data.data() + pos + 2; src.keylen = kl; src.token = tok; src.part_start = pos;
+            src.upos = r.p - src.data.data();
+            src.has = true;
+            return;
+        } catch (Corrupt& c) { if (c.kind == 4) { c.kind = 3; c.offset = src.ipos; } throw; }
+    }
+}
+
+// DecoratedKey.compareTo: S/db/DecoratedKey.java:79-91
+static int compare_key(const Source& a, const Source& b) {
+    if (a.token != b.token) return a.token < b.token ? -1 : 1;
+    int n = std::min(a.keylen, b.keylen);
+    int c = n ? memcmp(a.key, b.key, n) : 0;
+    if (c) return c < 0 ? -1 : 1;
+    return a.keylen == b.keylen ? 0 : (a.keylen < b.keylen ? -1 : 1);
+}
+
+// ---- purge: PurgeFunction S/db/partitions/PurgeFunction.java:36-145 -------------------------------------------------------
+struct Purger {
+    int64_t now, gc_before, max_ts;
+    // :39-42 with onlyPurgeRepairedTombstones = false; evaluator = ts < min timestamp of overlapping sstables (CompactionController.java:247-286)
+    bool should_purge(int64_t ts, int64_t ldt) const { return ldt < gc_before && (max_ts == INT64_MAX || ts < max_ts); }
+    bool should_purge(const DT& d) const { return !d.live() && should_purge(d.mfda, d.ldt); }       // DeletionPurger.java:28-31
+    bool should_purge(const Live& l) const { return !l.is_live(now) && should_purge(l.ts, l.ldt); } // :33-36
+};
+
+// AbstractCell.purge: S/db/rows/AbstractCell.java:78-99. Returns false if the cell is dropped.
+static bool purge_cell(CellV& c, const Purger& pg) {
+    if (!c.is_live(pg.now)) {
+        if (pg.should_purge(c.ts, c.ldt)) return false;
+        if (c.expiring()) {                       // expired TTL cell -> tombstone with ldt - ttl, value dropped, then purged again
+            c.ldt = c.ldt - c.ttl; c.ttl = 0; c.vlen = 0;
+            if (!c.is_live(pg.now) && pg.should_purge(c.ts, c.ldt)) return false;
+        }
+    }
+    return true;
+}
+// BTreeRow.purge: S/db/rows/BTreeRow.java:457-470,488-499. Returns false if the row disappears.
+static bool purge_row(Unf& r, const Purger& pg) {
+    if (pg.should_purge(r.info)) r.info = Live();
+    if (pg.should_purge(r.del)) r.del = DT();
+    size_t w = 0;
+    for (size_t i = 0; i < r.cells.size(); i++) if (purge_cell(r.cells[i], pg)) r.cells[w++] = r.cells[i];
+    r.cells.resize(w);
+    return !(r.info.empty() && r.del.live() && r.cells.empty());
+}
+// PurgeFunction.applyToMarker :116-143. Returns false if the marker disappears.
+static bool purge_marker(Unf& m, const Purger& pg) {
+    if (kind_is_boundary(m.c.kind)) {
+        bool pc = pg.should_purge(m.m_close), po = pg.should_purge(m.m_open);
+        if (pc) {
+            if (po) return false;
+            m.c.kind = (m.c.kind == K_EXCL_END_INCL_START) ? K_INCL_START : K_EXCL_START;   // createCorrespondingOpenMarker
+            m.m_close = DT();
+            return true;
+        }
+        if (po) { m.c.kind = (m.c.kind == K_EXCL_END_INCL_START) ? K_EXCL_END : K_INCL_END; m.m_open = DT(); }   // ...CloseMarker
+        return true;
+    }
+    const DT& d = kind_is_start(m.c.kind) ? m.m_open : m.m_close;
+    return !pg.should_purge(d);
+}
+
+// ---- Cells.reconcile: S/db/rows/Cells.java:68-121 ---------------------------------------------------------------------
+static const CellV& reconcile(const CellV& l, const CellV& r) {
+    if (l.ts != r.ts) return l.ts > r.ts ? l : r;
+    bool le = l.ldt != NO_DEL, re = r.ldt != NO_DEL;
+    if (le | re) {
+        if (le != re) return le ? l : r;
+        bool lt = !l.expiring(), rt = !r.expiring();
+        if (lt != rt) return lt ? l : r;
+        if (l.ldt != r.ldt) return l.ldt > r.ldt ? l : r;
+    }
+    int n = std::min(l.vlen, r.vlen);
+    int c = n ? memcmp(l.val, r.val, n) : 0;
+    if (c == 0) c = l.vlen - r.vlen;
+    return c >= 0 ? l : r;
+}
+
+// Row.Merger.merge: S/db/rows/Row.java:730-781 (simple columns only: ColumnDataReducer :838-849). Returns false for null.
+static bool merge_rows(std::vector<Unf*>& versions, DT active, Unf& out) {
+    if (versions.size() == 1 && active.live()) { out = *versions[0]; return true; }
+    Live info; DT del;
+    for (Unf* v : versions) {
+        if (v->info.supersedes(info)) info = v->info;
+        if (v->del.supersedes(del)) del = v->del;
+    }
+    if (del.supersedes(active)) active = del; else del = DT();
+    if (active.deletes(info.ts)) info = Live();          // deletes(LivenessInfo) = deletes(timestamp); EMPTY ts = MIN is always "deleted" but stays EMPTY
+    out.is_row = true; out.c = versions[0]->c; out.info = info; out.del = del; out.cells.clear();
+    size_t cur[B200C_MAX_INPUTS] = {0};
+    for (;;) {
+        int col = INT_MAX;
+        for (size_t i = 0; i < versions.size(); i++) if (cur[i] < versions[i]->cells.size()) col = std::min(col, versions[i]->cells[cur[i]].col);
+        if (col == INT_MAX) break;
+        const CellV* merged = nullptr;
+        for (size_t i = 0; i < versions.size(); i++) {
+            if (cur[i] < versions[i]->cells.size() && versions[i]->cells[cur[i]].col == col) {
+                const CellV& c = versions[i]->cells[cur[i]++];
+                if (!active.deletes(c.ts)) merged = merged ? &reconcile(*merged, c) : &c;
+            }
+        }
+        if (merged) out.cells.push_back(*merged);
+    }
+    return !(out.info.empty() && out.del.live() && out.cells.empty());
+}
+
+// RangeTombstoneMarker.Merger: S/db/rows/RangeTombstoneMarker.java:72-199 (forward order)
+struct MarkerMerger {
+    DT partition_del; std::vector<DT> open; std::vector<bool> has_open; int biggest = -1;
+    void init(size_t n, DT pd) { partition_del = pd; open.assign(n, DT()); has_open.assign(n, false); biggest = -1; }
+    DT current_open() const {            // :160-168
+        if (biggest < 0) return DT();
+        return !open[biggest].supersedes(partition_del) ? DT() : open[biggest];
+    }
+    DT active() const { DT o = current_open(); return o.live() ? partition_del : o; }   // :191-197
+    // versions: (source slot, marker). Returns false when nothing is emitted.
+    bool merge(const std::vector<std::pair<int, Unf*>>& versions, Unf& out) {
+        DT prev = current_open();
+        for (auto& pr : versions) {      // updateOpenMarkers :170-189
+            Unf* m = pr.second; bool is_open = kind_is_boundary(m->c.kind) || kind_is_start(m->c.kind);
+            if (is_open) { open[pr.first] = m->m_open; has_open[pr.first] = true; } else has_open[pr.first] = false;
+        }
+        biggest = -1;
+        for (size_t i = 0; i < open.size(); i++) if (has_open[i] && (biggest < 0 || open[i].supersedes(open[biggest]))) biggest = (int)i;
+        DT now = current_open();
+        if (prev == now) return false;
+        const Clust& bound = versions.back().second->c;     // `bound` = clustering of the last marker added (:99-103)
+        bool before = kind_vs_clustering(bound.kind) < 0;
+        out.is_row = false; out.cells.clear(); out.c = bound; out.m_close = DT(); out.m_open = DT();
+        if (prev.live()) { out.c.kind = before ? K_INCL_START : K_EXCL_START; out.m_open = now; }
+        else if (now.live()) { out.c.kind = before ? K_EXCL_END : K_INCL_END; out.m_close = prev; }
+        else { out.c.kind = before ? K_EXCL_END_INCL_START : K_INCL_END_EXCL_START; out.m_close = prev; out.m_open = now; }
+        return true;
+    }
+};
+
+// ---- output side ----------------------------------------------------------------------------------------------------------
+struct OutBuf { std::vector<uint8_t> b; void u8(uint8_t v) { b.push_back(v); } void put(const void* p, size_t n) { const uint8_t* q = (const uint8_t*)p; b.insert(b.end(), q, q + n); }
+    void vint(uint64_t v) { uint8_t t[9]; int n = vint_write(t, v); put(t, n); }
+    void be16(uint16_t v) { u8(v >> 8); u8(v & 0xff); } void be32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
+    void be64(uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); } size_t size() const { return b.size(); } };
+
+// DeletionTime.Serializer.serialize (oa): S/db/DeletionTime.java:205-220
+static void write_partition_dt(OutBuf& o, const DT& d) { if (d.live()) o.u8(0x80); else { o.be64((uint64_t)d.mfda); o.be32((uint32_t)d.ldt); } }
+static int partition_dt_size(const DT& d) { return d.live() ? 1 : 12; }
+
+struct Writer {
+    const b200c_manifest* m; Schema sc;
+    // one output sstable
+    struct Sst { std::vector<uint8_t> data; std::vector<uint8_t> index; std::vector<uint64_t> offs; uint64_t ulen = 0; uint32_t digest = 0; uint64_t parts = 0, rows = 0; };
+    std::vector<Sst> outs;
+    std::vector<uint8_t> chunk;         // CompressedSequentialWriter buffer (S/io/compress/CompressedSequentialWriter.java:140-206)
+    std::vector<uint8_t> comp;
+    uint64_t position = 0;              // uncompressed position in the current output
+    uint64_t chunk_offset = 0;          // on-disk bytes flushed (getEstimatedOnDiskBytesWritten :128-131)
+    // partition state (SortedTablePartitionWriter / BigFormatPartitionWriter)
+    uint64_t part_start = 0, header_len = 0, prev_row_start = 0, block_start = 0;
+    bool have_first = false; Clust first_c, last_c; DT open_marker, start_open_marker;
+    std::vector<std::vector<uint8_t>> index_infos;
+    OutBuf body, tmp;
+
+    void start_output() { outs.emplace_back(); position = 0; chunk_offset = 0; chunk.clear(); }
+    void flush_chunk() {                // flushData :140-206
+        if (chunk.empty()) return;
+        Sst& o = outs.back();
+        comp.resize(chunk_max_compressed(m->out_compressor, m->out_chunk_len) + 64);
+        int clen = chunk_compress(m->out_compressor, chunk.data(), (int)chunk.size(), comp.data());
+        const uint8_t* w = comp.data(); int wlen = clen;
+        std::vector<uint8_t> raw;
+        if ((int64_t)clen >= (int64_t)m->out_max_compressed_len) {
+            raw = chunk;
+            if ((int64_t)raw.size() < (int64_t)m->out_max_compressed_len) raw.resize(m->out_max_compressed_len, 0);
+            w = raw.data(); wlen = (int)raw.size();
+        }
+        o.offs.push_back(chunk_offset);
+        o.data.insert(o.data.end(), w, w + wlen);
+        uint32_t crc = crc32_ieee(0, w, wlen);           // ChecksumWriter.appendDirect :62-89
+        uint8_t cb[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+        o.data.insert(o.data.end(), cb, cb + 4);
+        chunk_offset += wlen + 4;
+        o.ulen += chunk.size();
+        chunk.clear();
+    }
+    void write(const uint8_t* p, size_t n) {             // BufferedDataOutputStreamPlus fill-then-flush :87-139
+        while (n) {
+            size_t room = (size_t)m->out_chunk_len - chunk.size();
+            size_t k = std::min(room, n);
+            chunk.insert(chunk.end(), p, p + k); p += k; n -= k; position += k;
+            if (chunk.size() == (size_t)m->out_chunk_len) flush_chunk();
+        }
+    }
+    void finish_output() { flush_chunk(); Sst& o = outs.back(); o.digest = crc32_ieee(0, o.data.data(), o.data.size()); }
+
+    // ClusteringPrefix.Serializer.serializeValuesWithoutSize: S/db/ClusteringPrefix.java:455-477
+    void write_clust_values(OutBuf& o, const Clust& c) {
+        int off = 0;
+        while (off < c.n) {
+            int limit = std::min(c.n, off + 32);
+            uint64_t header = 0;
+            for (int i = off; i < limit; i++) { if (c.v[i].null) header |= 1ull << (((i % 32) * 2) + 1); else if (c.v[i].len == 0) header |= 1ull << ((i % 32) * 2); }
+            o.vint(header);
+            for (; off < limit; off++) {
+                const Val& v = c.v[off];
+                if (v.null || v.len == 0) continue;
+                if (sc.clust[off].fixed_len <= 0) o.vint((uint64_t)v.len);     // AbstractType.writeValue :535-552
+                o.put(v.p, v.len);
+            }
+        }
+    }
+    // ClusteringPrefix.Serializer.serialize (IndexInfo names): :408-421; ClusteringBoundOrBoundary.Serializer :101-108
+    void write_clust_prefix(OutBuf& o, const Clust& c) {
+        o.u8(c.kind);
+        if (c.kind != K_CLUSTERING) o.be16((uint16_t)c.n);
+        write_clust_values(o, c);
+    }
+    void write_delta_dt(OutBuf& o, const DT& d) {        // SerializationHeader.writeDeletionTime :181-184
+        o.vint((uint64_t)d.mfda - (uint64_t)m->out_stats.min_timestamp);
+        o.vint((uint64_t)(int64_t)(int32_t)(d.ldt - m->out_stats.min_local_deletion_time));
+    }
+
+    void start_partition(const uint8_t* key, int keylen, const DT& pdel) {     // SortedTablePartitionWriter.start :97-115
+        part_start = position;
+        tmp.b.clear(); tmp.be16((uint16_t)keylen); tmp.put(key, keylen); write_partition_dt(tmp, pdel);
+        write(tmp.b.data(), tmp.b.size());
+        header_len = position - part_start;
+        prev_row_start = 0; have_first = false; open_marker = DT(); index_infos.clear(); block_start = 0;
+    }
+    uint64_t cur_pos() const { return position - part_start; }
+
+    void add_index_block() {                              // BigFormatPartitionWriter.addIndexBlock :128-190, IndexInfo.Serializer :107-117
+        OutBuf o;
+        write_clust_prefix(o, first_c); write_clust_prefix(o, last_c);
+        o.vint(block_start);
+        o.vint(zigzag_enc((int64_t)(cur_pos() - block_start) - 65536));
+        o.u8(open_marker.live() ? 0 : 1);
+        if (!open_marker.live()) write_partition_dt(o, open_marker);
+        index_infos.push_back(std::move(o.b));
+        have_first = false;
+    }
+
+    void add_unfiltered(const Unf& u) {                   // SortedTablePartitionWriter.addUnfiltered :128-154 + UnfilteredSerializer.serialize :131-305
+        uint64_t pos = cur_pos();
+        if (!have_first) { first_c = u.c; start_open_marker = open_marker; block_start = pos; have_first = true; }
+        uint64_t prev_size = pos - prev_row_start;
+        tmp.b.clear(); body.b.clear();
+        if (!u.is_row) {
+            tmp.u8(0x02); tmp.u8(u.c.kind); tmp.be16((uint16_t)u.c.n); write_clust_values(tmp, u.c);
+            if (kind_is_boundary(u.c.kind)) { write_delta_dt(body, u.m_close); write_delta_dt(body, u.m_open); }
+            else write_delta_dt(body, kind_is_start(u.c.kind) ? u.m_open : u.m_close);
+            tmp.vint(body.size() + vint_size(prev_size)); tmp.vint(prev_size);
+        } else {
+            int flags = 0;
+            if (!u.info.empty()) flags |= 0x04;
+            if (u.info.expiring()) flags |= 0x08;
+            if (!u.del.live()) flags |= 0x10;
+            bool all = (int)u.cells.size() == sc.ncols;
+            if (all) flags |= 0x20;
+            tmp.u8((uint8_t)flags);
+            write_clust_values(tmp, u.c);
+            if (flags & 0x04) body.vint((uint64_t)u.info.ts - (uint64_t)m->out_stats.min_timestamp);
+            if (flags & 0x08) { body.vint((uint64_t)(int64_t)(u.info.ttl - m->out_stats.min_ttl));
+                                body.vint((uint64_t)(int64_t)(int32_t)(u.info.ldt - m->out_stats.min_local_deletion_time)); }
+            if (flags & 0x10) write_delta_dt(body, u.del);
+            if (!all) {                                   // Columns.serializeSubset :503-531, encodeBitmap :586-608
+                if (sc.ncols >= 64) throw Unsupported{">= 64 columns"};
+                uint64_t missing = (sc.ncols == 64 ? ~0ull : ((1ull << sc.ncols) - 1));
+                for (const CellV& c : u.cells) missing &= ~(1ull << c.col);
+                body.vint(missing);
+            }
+            for (const CellV& c : u.cells) {              // Cell.Serializer.serialize: S/db/rows/Cell.java:268-305
+                bool has_value = c.vlen > 0, deleted = c.tombstone(), expiring = c.expiring();
+                bool use_ts = !u.info.empty() && c.ts == u.info.ts;
+                bool use_ttl = expiring && u.info.expiring() && c.ttl == u.info.ttl && c.ldt == u.info.ldt;
+                int cf = 0;
+                if (!has_value) cf |= 0x04;
+                if (deleted) cf |= 0x01; else if (expiring) cf |= 0x02;
+                if (use_ts) cf |= 0x08;
+                if (use_ttl) cf |= 0x10;
+                body.u8((uint8_t)cf);
+                if (!use_ts) body.vint((uint64_t)c.ts - (uint64_t)m->out_stats.min_timestamp);
+                if ((deleted || expiring) && !use_ttl) body.vint((uint64_t)(int64_t)(int32_t)(c.ldt - m->out_stats.min_local_deletion_time));
+                if (expiring && !use_ttl) body.vint((uint64_t)(int64_t)(c.ttl - m->out_stats.min_ttl));
+                if (has_value) { if (sc.cols[c.col].fixed_len <= 0) body.vint((uint64_t)c.vlen); body.put(c.val, c.vlen); }
+            }
+            tmp.vint(body.size() + vint_size(prev_size)); tmp.vint(prev_size);
+        }
+        write(tmp.b.data(), tmp.b.size());
+        write(body.b.data(), body.b.size());
+        last_c = u.c; prev_row_start = pos;
+        if (!u.is_row) open_marker = (kind_is_boundary(u.c.kind) || kind_is_start(u.c.kind)) ? u.m_open : DT();
+        outs.back().rows++;
+        if (cur_pos() - block_start >= (uint64_t)m->column_index_size) add_index_block();     // BigFormatPartitionWriter.addUnfiltered :208-215
+    }
+
+    void end_partition(const uint8_t* key, int keylen, const DT& pdel, uint64_t written) {   // finish :217-243 + RowIndexEntry / IndexWriter.append
+        uint8_t eop = 0x01; write(&eop, 1);
+        if (written && have_first) add_index_block();
+        Sst& o = outs.back();
+        OutBuf e; e.be16((uint16_t)keylen); e.put(key, keylen);
+        e.vint(part_start);
+        if (index_infos.size() > 1) {                     // RowIndexEntry.create :217-243; IndexedEntry.serialize :625-642
+            uint64_t infos = 0; for (auto& ii : index_infos) infos += ii.size();
+            uint64_t size = vint_size(header_len) + partition_dt_size(pdel) + vint_size(index_infos.size()) + infos + 4 * index_infos.size();
+            e.vint(size); e.vint(header_len); write_partition_dt(e, pdel); e.vint(index_infos.size());
+            for (auto& ii : index_infos) e.put(ii.data(), ii.size());
+            uint32_t off = 0; for (auto& ii : index_infos) { e.be32(off); off += (uint32_t)ii.size(); }
+        } else e.vint(0);
+        o.index.insert(o.index.end(), e.b.begin(), e.b.end());
+        o.parts++;
+    }
+};
+
+static int compact_impl(const b200c_manifest* m, b200c_result* res) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (m->abi_version != B200C_ABI_VERSION || m->ninputs <= 0 || m->ninputs > B200C_MAX_INPUTS) return B200C_EINVAL;
+    if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) return B200C_EUNSUPPORTED;
+    if (m->nclustering > B200C_MAX_CLUSTERING || m->ncolumns > B200C_MAX_COLUMNS || m->ncolumns >= 64) return B200C_EUNSUPPORTED;
+    Schema sc; sc.nclust = m->nclustering; sc.ncols = m->ncolumns;
+    memcpy(sc.clust, m->clustering, sizeof(sc.clust)); memcpy(sc.cols, m->columns, sizeof(sc.cols));
+    std::vector<Source> srcs(m->ninputs);
+    uint64_t bytes_read = 0;
+    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; load_source(srcs[i]); bytes_read += srcs[i].data.size(); next_partition(srcs[i], m->token_lo, m->token_hi); }
+    Purger pg{m->now_in_sec, m->gc_before, m->purge_max_timestamp};
+    Writer w; w.m = m; w.sc = sc; w.start_output();
+    memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
+    uint64_t total_source_rows = 0, input_partitions = 0;
+    std::vector<Unf> heads(m->ninputs);
+    std::vector<bool> head_ok(m->ninputs);
+    for (;;) {
+        // MergeIterator over partitions (S/utils/MergeIterator.java:154-219): equal keys reduce together, source order
+        int best = -1;
+        for (int i = 0; i < m->ninputs; i++) if (srcs[i].has && (best < 0 || compare_key(srcs[i], srcs[best]) < 0)) best = i;
+        if (best < 0) break;
+        std::vector<int> group;
+        for (int i = 0; i < m->ninputs; i++) if (srcs[i].has && compare_key(srcs[i], srcs[best]) == 0) group.push_back(i);
+        res->merged_row_counts[group.size() - 1]++;       // CompactionIterator.updateCounterFor :220-232
+        input_partitions += group.size();
+        // LCS: CompactionAwareWriter.maybeSwitchWriter / MaxSSTableSizeWriter.shouldSwitchWriterInCurrentLocation :76-79 (before each partition)
+        if (m->max_sstable_bytes && w.chunk_offset > m->max_sstable_bytes) { w.finish_output(); w.start_output(); }
+        // partition deletion: collectPartitionLevelDeletion S/db/rows/UnfilteredRowIterators.java:465-482
+        DT pdel;
+        for (int i : group) if (!pdel.supersedes(srcs[i].pdel)) pdel = srcs[i].pdel;
+        DT out_pdel = pg.should_purge(pdel) ? DT() : pdel;     // PurgeFunction.applyToDeletion :95-99
+        std::string keycopy((const char*)srcs[group[0]].key, srcs[group[0]].keylen);
+        bool started = false; uint64_t written = 0;
+        auto emit = [&](Unf& u) {
+            total_source_rows++;                               // Purger.updateProgress :366-371
+            bool keep = u.is_row ? purge_row(u, pg) : purge_marker(u, pg);
+            if (!keep) return;
+            if (!started) { w.start_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel); started = true; }
+            w.add_unfiltered(u); written++;
+        };
+        if (group.size() == 1) {
+            // single source: MergeIterator.get -> TrivialOneToOne (trivialReduceIsTrivial() == true without a listener,
+            // UnfilteredRowIterators.java:552-556): unfiltereds pass through untouched, then purge
+            Source& s = srcs[group[0]]; Unf u;
+            while (read_unfiltered(s, sc, u)) emit(u);
+        } else {
+            MarkerMerger mm; mm.init(group.size(), pdel);
+            for (size_t g = 0; g < group.size(); g++) head_ok[g] = read_unfiltered(srcs[group[g]], sc, heads[g]);
+            for (;;) {
+                int b = -1;
+                for (size_t g = 0; g < group.size(); g++) if (head_ok[g] && (b < 0 || compare_clust(sc, heads[g].c, heads[b].c) < 0)) b = (int)g;
+                if (b < 0) break;
+                std::vector<size_t> eq;
+                for (size_t g = 0; g < group.size(); g++) if (head_ok[g] && compare_clust(sc, heads[g].c, heads[b].c) == 0) eq.push_back(g);
+                Unf out; bool have;
+                if (heads[b].is_row) {                         // MergeReducer.getReduced :575-591
+                    std::vector<Unf*> vs; for (size_t g : eq) vs.push_back(&heads[g]);
+                    have = merge_rows(vs, mm.active(), out);
+                } else {
+                    std::vector<std::pair<int, Unf*>> vs; for (size_t g : eq) vs.push_back({(int)g, &heads[g]});
+                    have = mm.merge(vs, out);
+                }
+                if (have) emit(out);
+                for (size_t g : eq) head_ok[g] = read_unfiltered(srcs[group[g]], sc, heads[g]);
+            }
+        }
+        // partition.isEmpty(): S/db/rows/UnfilteredRowIterator.java:63-68; SortedTableWriter.append :134
+        if (!started && !out_pdel.live()) { w.start_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel); started = true; }
+        if (started) w.end_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel, written);
+        for (int i : group) next_partition(srcs[i], m->token_lo, m->token_hi);
+    }
+    w.finish_output();
+    if (w.outs.size() > 1 && w.outs.back().parts == 0) w.outs.pop_back();
+    res->noutputs = (int)w.outs.size();
+    res->bytes_read = bytes_read; res->total_source_rows = total_source_rows; res->input_partitions = input_partitions;
+    uint64_t bw = 0; int rc = B200C_OK;
+    res->required_data_cap = res->required_index_cap = res->required_chunk_cap = 0;
+    for (size_t i = 0; i < w.outs.size(); i++) {
+        auto& o = w.outs[i]; bw += o.ulen;
+        res->required_data_cap = std::max<uint64_t>(res->required_data_cap, o.data.size());
+        res->required_index_cap = std::max<uint64_t>(res->required_index_cap, o.index.size());
+        res->required_chunk_cap = std::max<uint64_t>(res->required_chunk_cap, o.offs.size());
+        if ((int)i >= res->noutputs_cap) { rc = B200C_ETOOSMALL; continue; }
+        b200c_output& out = res->outputs[i];
+        if (o.data.size() > out.data_cap || o.index.size() > out.index_cap || o.offs.size() > out.chunk_cap) { rc = B200C_ETOOSMALL; continue; }
+        memcpy(out.data, o.data.data(), o.data.size()); out.data_len = o.data.size();
+        memcpy(out.index, o.index.data(), o.index.size()); out.index_len = o.index.size();
+        memcpy(out.chunk_offsets, o.offs.data(), o.offs.size() * 8); out.nchunks = o.offs.size();
+        out.data_length = o.ulen; out.digest = o.digest; out.partitions = o.parts; out.rows = o.rows;
+    }
+    res->bytes_written = bw;
+    res->kernel_ms = 0; res->kernel_launches = 0;
+    res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+} // namespace oracle
+
+extern "C" int orc_compact(const b200c_manifest* m, b200c_result* res, char* errbuf, int errcap) {
+    try { return oracle::compact_impl(m, res); }
+    catch (oracle::Unsupported& u) { if (errbuf) snprintf(errbuf, errcap, "unsupported: %s", u.what.c_str()); return B200C_EUNSUPPORTED; }
+    catch (oracle::Corrupt& c) {
+        res->corruption.input = c.input; res->corruption.kind = c.kind; res->corruption.chunk = c.chunk; res->corruption.offset = c.offset;
+        if (errbuf) snprintf(errbuf, errcap, "corrupt: %s", c.what.c_str());
+        return B200C_ECORRUPT;
+    }
+}

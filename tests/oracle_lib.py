@@ -67,3 +67,16 @@ def vint(v: int) -> bytes:
 
 def token(key: bytes) -> int:
     return lib().orc_murmur3_token(key, len(key))
+
+class OracleEngine:
+    """orc_compact: the CPU oracle behind the same manifest/result structs as b200c_compact (TEST INFRASTRUCTURE)."""
+    needs_lib_bound = False
+    def __call__(self, manifest, result):
+        from cassandra_b200 import native
+        L = lib()
+        L.orc_compact.restype = C.c_int
+        err = C.create_string_buffer(256)
+        rc = L.orc_compact(C.byref(manifest), C.byref(result), err, 256)
+        if rc == native.ECORRUPT: raise native.CorruptSSTableError(rc, err.value.decode(), result.corruption)
+        if rc == native.EUNSUPPORTED: raise native.UnsupportedError(rc, err.value.decode())
+        if rc != 0: raise native.B200CError(rc, err.value.decode())

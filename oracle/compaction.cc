@@ -178,7 +178,16 @@ static int64_t decode_ldt(int64_t ldt, int32_t ttl) {
 }
 
 // UnfilteredSerializer.deserialize: S/db/rows/UnfilteredSerializer.java:433-645. Returns false at end of partition.
+static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u);
 static bool read_unfiltered(Source& src, const Schema& s, Unf& u) {
+    // UnfilteredSerializer.deserialize :433-447: empty rows (e.g. all columns dropped) are skipped at read time
+    for (;;) {
+        if (!read_unfiltered_one(src, s, u)) return false;
+        if (u.is_row && u.info.empty() && u.del.live() && u.cells.empty()) continue;
+        return true;
+    }
+}
+static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u) {
     const b200c_input& in = *src.in;
     Reader r{src.data.data() + src.upos, src.data.data() + src.data.size(), src.idx};
     uint8_t flags = r.u8();

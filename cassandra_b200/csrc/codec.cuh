@@ -11,26 +11,9 @@
 #include "common.cuh"
 #include "lz4.cuh"
 #include "snappy.cuh"
+#include "codec_defs.cuh"
 
 namespace b200c {
-
-enum { COMP_NONE = 0, COMP_LZ4 = 1, COMP_SNAPPY = 2 };
-
-__host__ __device__ __forceinline__ int chunk_max_compressed(int comp, int chunk_len) {
-    if (comp == COMP_LZ4) return 4 + lz4_compress_bound(chunk_len);
-    if (comp == COMP_SNAPPY) return snappy_max_compressed_length(chunk_len);
-    return chunk_len;
-}
-__host__ __device__ __forceinline__ int chunk_slot_stride(int comp, int chunk_len) {
-    int m = chunk_max_compressed(comp, chunk_len); if (m < chunk_len) m = chunk_len;
-    return (m + 4 + 16 + 15) & ~15;      // bytes + CRC + read slack, 16-byte aligned
-}
-
-struct ChunkErr { unsigned long long first_bad; };   // min over failing chunks of (chunk index << 8 | kind); init ~0
-
-__device__ __forceinline__ void report_chunk_err(ChunkErr* e, uint64_t chunk, int kind) {
-    atomicMin(&e->first_bad, ((unsigned long long)chunk << 8) | (unsigned long long)kind);
-}
 
 // ---- K5: compress + CRC ------------------------------------------------------------------------------------------
 // grid = nchunks blocks of one warp. dynamic smem: [hash table tab_bytes][chunk bytes chunk_len + 16]

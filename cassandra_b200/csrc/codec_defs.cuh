@@ -1,0 +1,25 @@
+// codec_defs.cuh — chunk codec constants shared by the codec kernels (codec.cuh) and the compaction driver (compact.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200c {
+
+enum { COMP_NONE = 0, COMP_LZ4 = 1, COMP_SNAPPY = 2 };
+
+__host__ __device__ __forceinline__ int chunk_max_compressed(int comp, int chunk_len) {
+    if (comp == COMP_LZ4) return 4 + (chunk_len + chunk_len / 255 + 16);
+    if (comp == COMP_SNAPPY) return (32 + chunk_len + chunk_len / 6);
+    return chunk_len;
+}
+__host__ __device__ __forceinline__ int chunk_slot_stride(int comp, int chunk_len) {
+    int m = chunk_max_compressed(comp, chunk_len); if (m < chunk_len) m = chunk_len;
+    return (m + 4 + 16 + 15) & ~15;      // bytes + CRC + read slack, 16-byte aligned
+}
+
+struct ChunkErr { unsigned long long first_bad; };   // min over failing chunks of (chunk index << 8 | kind); init ~0
+
+__device__ __forceinline__ void report_chunk_err(ChunkErr* e, uint64_t chunk, int kind) {
+    atomicMin(&e->first_bad, ((unsigned long long)chunk << 8) | (unsigned long long)kind);
+}
+
+} // namespace b200c

@@ -1,15 +1,679 @@
-// compact.cu — b200c_compact (placeholder until the merge pipeline lands in this file), poll and cancel.
+// compact.cu — b200c_compact: the whole CompactionTask hot loop (S/db/compaction/CompactionTask.java:184-236) as a chain of
+// data-parallel kernels on one B200:
+//
+//   K1  k_decompress_chunks      every input chunk -> U (CRC verified)                          [codec.cuh]
+//   K2  k_index_find/chain/emit  Index.db walk of BigTableScanner (format/big/BigTableScanner.java:135-184) done speculatively in
+//                                256-byte blocks, proven equal to the sequential parse, + Murmur3 token per key
+//   K3  k_bucket_bounds + k_merge_buckets   the partition-level MergeIterator (S/utils/MergeIterator.java:154-219): token space is
+//                                cut into buckets, one warp per bucket runs a tournament over its <= 64 sources (one or two
+//                                per lane, warp-min by shuffles); equal keys reduce together in source order
+//   K4  k_partition_size/emit    row merge + reconcile + purge + big-format serialisation, size -> scan -> emit   [partition.cuh]
+//   K5  k_compress_chunks ...    CompressedSequentialWriter + ChecksumWriter                    [codec.cuh]
+//
+// No CPU fallback; every error is reported through the return code (B200C_ECORRUPT carries the location).
 #include "engine.cuh"
+#include "scan.cuh"
+#include "codec_defs.cuh"
+#include "partition.cuh"
+#include <climits>
+#include <vector>
+#include <algorithm>
+
 using namespace b200c;
-extern "C" {
-int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* r, int flags) {
-    if (!c || !m || !r) return B200C_EINVAL;
-    c->err = "b200c_compact: not implemented yet"; return B200C_EUNSUPPORTED;
+
+namespace b200c {
+
+int compress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
+                           uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs, uint64_t* out_len, uint32_t* digest, int ws_base);
+int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
+                             int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err);
+
+enum { IB = 256 };                       // Index.db speculation block
+#define NONE64 (~0ull)
+
+enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
+       WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
+       WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2,
+       WS_SCANA = 60, WS_CODEC = 70 };
+
+struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
+
+__device__ __forceinline__ void report_err(DevErr* e, int kind, int input, uint64_t off) {
+    atomicMin(&e->code, ((unsigned long long)kind << 56) | ((unsigned long long)(input & 0xFF) << 48) | (off & 0xFFFFFFFFFFFFull));
 }
+
+// ---- Murmur3 (Cassandra variant): S/utils/MurmurHash.java:178-260, token = Murmur3Partitioner.getToken :256-296 ---------------
+__device__ __forceinline__ uint64_t rotl64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
+__device__ __forceinline__ uint64_t fmix64(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k; }
+__device__ int64_t murmur3_token(const uint8_t* key, uint32_t len) {
+    if (len == 0) return I64_MIN;
+    const uint32_t nblocks = len >> 4;
+    uint64_t h1 = 0, h2 = 0;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    for (uint32_t i = 0; i < nblocks; i++) {
+        uint64_t k1 = 0, k2 = 0;
+        for (int b = 0; b < 8; b++) { k1 |= (uint64_t)key[i * 16 + b] << (8 * b); k2 |= (uint64_t)key[i * 16 + 8 + b] << (8 * b); }
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const uint8_t* t = key + nblocks * 16;
+    uint64_t k1 = 0, k2 = 0;
+    int rem = len & 15;
+    for (int i = rem - 1; i >= 8; i--) k2 ^= (uint64_t)(int64_t)(int8_t)t[i] << (8 * (i - 8));     // signed tail bytes (:214-233)
+    if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    for (int i = (rem < 8 ? rem : 8) - 1; i >= 0; i--) k1 ^= (uint64_t)(int64_t)(int8_t)t[i] << (8 * i);
+    if (rem > 0) { k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1; h1 = fmix64(h1); h2 = fmix64(h2); h1 += h2;
+    int64_t v = (int64_t)h1;
+    return v == I64_MIN ? I64_MAX : v;
+}
+
+// ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
+// One Index.db entry = u16 keyLen | key | vint dataPosition | vint32 payloadSize | payload (RowIndexEntry.java:468-473).
+// Structural parse of the entry at offset o of input i; returns its length (0 = not an entry). check_data additionally requires
+// Data.db at dataPosition to start with the same u16 keyLen | key (used only to pick speculation starts).
+__device__ uint64_t idx_entry(const CParams& P, const uint8_t* __restrict__ IDX, int i, uint64_t o, bool check_data, uint64_t* dpos_out, uint32_t* klen_out) {
+    const InDesc& in = P.in[i];
+    const uint8_t* b = IDX + in.ibase;
+    if (o + 2 > in.ilen) return 0;
+    uint32_t kl = ((uint32_t)b[o] << 8) | b[o + 1];
+    uint64_t p = o + 2 + kl;
+    if (p + 2 > in.ilen) return 0;
+    uint64_t pos, ps;
+    int n = vint_read(b + p, b + in.ilen, &pos); if (!n) return 0; p += n;
+    n = vint_read(b + p, b + in.ilen, &ps); if (!n) return 0; p += n;
+    if (ps > 0x7FFFFFFFull || p + ps > in.ilen) return 0;
+    if (pos >= in.ulen || pos + 2 + kl + 2 > in.ulen) return 0;
+    if (check_data) {
+        const uint8_t* d = P.U + in.ubase + pos;
+        for (uint32_t k = 0; k < 2 + kl; k++) if (d[k] != b[o + k]) return 0;
+    }
+    *dpos_out = pos; *klen_out = kl;
+    return p + ps - o;
+}
+
+__device__ __forceinline__ int input_of_block(const uint64_t* __restrict__ bbase, int ninputs, uint64_t b) {
+    int i = 0; while (i + 1 < ninputs && bbase[i + 1] <= b) i++; return i;
+}
+
+__global__ void __launch_bounds__(256) k_index_find(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase,
+                                                    uint64_t nblocks, uint64_t* __restrict__ start) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const CParams& P = *Pp;
+    int i = input_of_block(bbase, P.ninputs, b);
+    uint64_t lb = b - bbase[i], lo = lb * IB, hi = min(lo + IB, P.in[i].ilen);
+    uint64_t dpos; uint32_t kl; uint64_t found = NONE64;
+    if (lb == 0) { if (idx_entry(P, IDX, i, 0, true, &dpos, &kl)) found = 0; }
+    else for (uint64_t o = lo; o < hi; o++) if (idx_entry(P, IDX, i, o, true, &dpos, &kl)) { found = o; break; }
+    start[b] = found;
+}
+
+__global__ void __launch_bounds__(256) k_index_chain(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase,
+                                                     uint64_t nblocks, const uint64_t* __restrict__ start, uint32_t* __restrict__ cnt, uint64_t* __restrict__ chain_end) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const CParams& P = *Pp;
+    int i = input_of_block(bbase, P.ninputs, b);
+    uint64_t lb = b - bbase[i], hi = min((lb + 1) * IB, P.in[i].ilen);
+    uint64_t o = start[b]; uint32_t n = 0;
+    if (o == NONE64) { cnt[b] = 0; chain_end[b] = NONE64; return; }
+    while (o < hi) {
+        uint64_t dpos; uint32_t kl;
+        uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
+        if (!len) { o = NONE64 - 1; break; }             // structurally broken chain: caught by verification
+        n++; o += len;
+    }
+    cnt[b] = n; chain_end[b] = o;
+}
+
+// every chain must end exactly on the next block's speculated start (or at EOF), and every start must be the end of a chain
+__global__ void __launch_bounds__(256) k_index_verify_a(const CParams* __restrict__ Pp, const uint64_t* __restrict__ bbase, uint64_t nblocks,
+                                                        const uint64_t* __restrict__ start, const uint64_t* __restrict__ chain_end,
+                                                        uint32_t* __restrict__ hit, uint32_t* __restrict__ bad) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const CParams& P = *Pp;
+    int i = input_of_block(bbase, P.ninputs, b);
+    uint64_t lb = b - bbase[i];
+    if (lb == 0 && P.in[i].ilen > 0 && start[b] != 0) { bad[i] = 1; return; }
+    if (start[b] == NONE64) return;
+    uint64_t e = chain_end[b];
+    if (e == P.in[i].ilen) return;
+    if (e > P.in[i].ilen) { bad[i] = 1; return; }
+    uint64_t nb = bbase[i] + e / IB;
+    if (start[nb] != e) { bad[i] = 1; return; }
+    hit[nb] = 1;
+    for (uint64_t k = b + 1; k < nb; k++) if (start[k] != NONE64) { bad[i] = 1; return; }
+}
+__global__ void __launch_bounds__(256) k_index_verify_b(const CParams* __restrict__ Pp, const uint64_t* __restrict__ bbase, uint64_t nblocks,
+                                                        const uint64_t* __restrict__ start, const uint32_t* __restrict__ hit, uint32_t* __restrict__ bad) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    int i = input_of_block(bbase, Pp->ninputs, b);
+    if (b != bbase[i] && start[b] != NONE64 && !hit[b]) bad[i] = 1;
+}
+// slow but always-correct path for an input whose speculation could not be proven: one thread walks the file like
+// BigTableScanner does and rewrites start[]/cnt[] of its blocks. A structural error here is real corruption.
+__global__ void k_index_seq(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase,
+                            uint64_t* __restrict__ start, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ bad, DevErr* __restrict__ err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const CParams& P = *Pp;
+    if (i >= P.ninputs || !bad[i]) return;
+    uint64_t nb = bbase[i + 1] - bbase[i];
+    for (uint64_t k = 0; k < nb; k++) { start[bbase[i] + k] = NONE64; cnt[bbase[i] + k] = 0; }
+    uint64_t o = 0;
+    while (o < P.in[i].ilen) {
+        uint64_t dpos; uint32_t kl;
+        uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
+        if (!len) { report_err(err, 3, i, o); return; }
+        uint64_t b = bbase[i] + o / IB;
+        if (start[b] == NONE64) start[b] = o;
+        cnt[b]++;
+        o += len;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_index_emit(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase,
+        uint64_t nblocks, const uint64_t* __restrict__ start, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ scan,
+        const uint64_t* __restrict__ pbase, int64_t* __restrict__ tok, uint64_t* __restrict__ kp, uint16_t* __restrict__ klen,
+        uint64_t* __restrict__ upos, DevErr* __restrict__ err) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const CParams& P = *Pp;
+    uint32_t n = cnt[b];
+    if (!n) return;
+    int i = input_of_block(bbase, P.ninputs, b);
+    const InDesc& in = P.in[i];
+    uint64_t g = pbase[i] + (scan[b] - scan[bbase[i]]);
+    uint64_t o = start[b];
+    for (uint32_t k = 0; k < n; k++, g++) {
+        uint64_t dpos; uint32_t kl;
+        uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
+        if (!len) { report_err(err, 3, i, o); return; }
+        const uint8_t* key = IDX + in.ibase + o + 2;
+        const uint8_t* d = P.U + in.ubase + dpos;           // the Data.db partition must start with the same key
+        bool same = (((uint32_t)d[0] << 8) | d[1]) == kl;
+        for (uint32_t q = 0; same && q < kl; q++) same = d[2 + q] == key[q];
+        if (!same) { report_err(err, 3, i, o); return; }
+        tok[g] = murmur3_token(key, kl);
+        uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0);
+        kp[g] = pre; klen[g] = (uint16_t)kl; upos[g] = in.ubase + dpos;
+        o += len;
+    }
+}
+
+// per input: sentinel position, token-range bounds [plo, phi) (inputs are token sorted), and a sortedness check
+__global__ void k_input_ranges(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ pcount,
+                               const int64_t* __restrict__ tok, uint64_t* __restrict__ upos, int64_t tlo, int64_t thi, uint64_t* __restrict__ range /*[2*K]*/) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const CParams& P = *Pp;
+    if (i >= P.ninputs) return;
+    uint64_t n = pcount[i]; const int64_t* t = tok + pbase[i];
+    upos[pbase[i] + n] = P.in[i].ubase + P.in[i].ulen;
+    uint64_t lo = 0, hi = n;
+    if (tlo != I64_MIN) { uint64_t a = 0, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= tlo) a = m + 1; else b = m; } lo = a; }   // first > tlo
+    { uint64_t a = lo, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= thi) a = m + 1; else b = m; } hi = a; }                     // first > thi
+    range[2 * i] = lo; range[2 * i + 1] = hi;
+}
+
+// ---- K3: partition-level merge -------------------------------------------------------------------------------------------------
+struct MergeGeom { uint64_t umin, width, nbuckets; };     // bucket b covers unsigned-token range [umin + b*width, umin + (b+1)*width)
+
+__global__ void k_merge_geom(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ range,
+                             const int64_t* __restrict__ tok, uint64_t nbuckets, MergeGeom* __restrict__ g) {
+    const CParams& P = *Pp;
+    uint64_t umin = ~0ull, umax = 0; bool any = false;
+    for (int i = 0; i < P.ninputs; i++) {
+        uint64_t lo = range[2 * i], hi = range[2 * i + 1];
+        if (lo >= hi) continue;
+        uint64_t a = (uint64_t)tok[pbase[i] + lo] ^ 0x8000000000000000ull, b = (uint64_t)tok[pbase[i] + hi - 1] ^ 0x8000000000000000ull;
+        umin = min(umin, a); umax = max(umax, b); any = true;
+    }
+    if (!any) { umin = 0; umax = 0; }
+    g->umin = umin; g->nbuckets = nbuckets; g->width = (umax - umin) / nbuckets + 1;
+}
+
+// bstart[b * K + i] = first partition of input i (absolute index in its arrays) whose token falls in bucket >= b
+__global__ void __launch_bounds__(256) k_bucket_bounds(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ range,
+                                                       const int64_t* __restrict__ tok, const MergeGeom* __restrict__ gp, uint64_t* __restrict__ bstart) {
+    const CParams& P = *Pp; const int K = P.ninputs;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nb = gp->nbuckets;
+    if (t >= (nb + 1) * (uint64_t)K) return;
+    uint64_t b = t / K; int i = (int)(t % K);
+    uint64_t lo = range[2 * i], hi = range[2 * i + 1];
+    uint64_t res;
+    if (b == 0) res = lo;
+    else if (b >= nb) res = hi;
+    else {
+        unsigned long long hi128 = __umul64hi(b, gp->width), lo128 = b * gp->width;
+        uint64_t bound = gp->umin + lo128;
+        if (hi128 || bound < lo128) res = hi;                 // boundary beyond the token space
+        else {
+            const int64_t* tk = tok + pbase[i];
+            uint64_t a = lo, z = hi;
+            while (a < z) { uint64_t m = (a + z) / 2; if (((uint64_t)tk[m] ^ 0x8000000000000000ull) < bound) a = m + 1; else z = m; }
+            res = a;
+        }
+    }
+    bstart[t] = res;
+}
+
+__device__ __forceinline__ int64_t warp_min_i64(int64_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { int64_t o = __shfl_xor_sync(FULL_MASK, v, d); v = o < v ? o : v; }
+    return v;
+}
+
+// full key comparison of two partitions (DecoratedKey.compareTo tie on token: unsigned lexicographic, S/db/DecoratedKey.java:79-91)
+__device__ int cmp_keys(const uint8_t* __restrict__ U, uint64_t ua, uint32_t la, uint64_t kpa, uint64_t ub, uint32_t lb, uint64_t kpb) {
+    if (kpa != kpb) return kpa < kpb ? -1 : 1;
+    if (la <= 8 || lb <= 8) return la == lb ? 0 : (la < lb ? -1 : 1);
+    return cmp_bytes(U + ua + 2 + 8, (int)la - 8, U + ub + 2 + 8, (int)lb - 8);
+}
+
+// One warp per token bucket. Lane l owns sources l and l+32. Each step: warp-min of the head tokens (the tournament), ties on
+// token are resolved by key bytes, all heads equal to the winner are emitted as one output partition (contributors in source
+// order, first one flagged) and advanced. contrib entry = head<<63 | src<<56 | partition index (40 bits).
+__global__ void __launch_bounds__(128) k_merge_buckets(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ range,
+        const int64_t* __restrict__ tok, const uint64_t* __restrict__ kp, const uint16_t* __restrict__ klen, const uint64_t* __restrict__ upos,
+        const uint64_t* __restrict__ bstart, uint64_t nbuckets, uint64_t* __restrict__ contrib, uint32_t* __restrict__ head, unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t s_hist[MAXK];
+    const CParams& P = *Pp; const int K = P.ninputs;
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < MAXK; k += blockDim.x) s_hist[k] = 0;
+    __syncthreads();
+    uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b < nbuckets) {
+        uint64_t cur[2], end[2], base[2]; int64_t t[2]; bool valid[2];
+        uint64_t cpos = 0;
+        for (int s = 0; s < 2; s++) {
+            int src = lane + 32 * s;
+            cur[s] = end[s] = 0; base[s] = 0; valid[s] = false; t[s] = I64_MAX;
+            if (src < K) {
+                cur[s] = bstart[b * K + src]; end[s] = bstart[(b + 1) * K + src]; base[s] = pbase[src];
+                cpos += cur[s] - range[2 * src];
+                valid[s] = cur[s] < end[s];
+                if (valid[s]) t[s] = tok[base[s] + cur[s]];
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) cpos += __shfl_xor_sync(FULL_MASK, cpos, d);
+        for (;;) {
+            bool any = __any_sync(FULL_MASK, valid[0] || valid[1]);
+            if (!any) break;
+            int64_t lmin = I64_MAX;
+            if (valid[0]) lmin = t[0];
+            if (valid[1] && t[1] < lmin) lmin = t[1];
+            int64_t wmin = warp_min_i64(lmin);
+            bool tie0 = valid[0] && t[0] == wmin, tie1 = valid[1] && t[1] == wmin;
+            uint32_t m0 = __ballot_sync(FULL_MASK, tie0), m1 = __ballot_sync(FULL_MASK, tie1);
+            if (__popc(m0) + __popc(m1) > 1) {
+                // same token from several sources: almost always the same key; compare key bytes to be exact
+                for (;;) {
+                    int ls = m0 ? 0 : 1; int ll = __ffs(ls == 0 ? m0 : m1) - 1;             // leader = lowest source among the tied
+                    uint64_t g0 = base[0] + cur[0], g1 = base[1] + cur[1];
+                    uint64_t lg = __shfl_sync(FULL_MASK, ls == 0 ? g0 : g1, ll);
+                    uint64_t lkp = kp[lg]; uint32_t lkl = klen[lg]; uint64_t lup = upos[lg];
+                    int c0 = 0, c1 = 0;
+                    if (tie0) c0 = cmp_keys(P.U, upos[g0], klen[g0], kp[g0], lup, lkl, lkp);
+                    if (tie1) c1 = cmp_keys(P.U, upos[g1], klen[g1], kp[g1], lup, lkl, lkp);
+                    uint32_t less0 = __ballot_sync(FULL_MASK, tie0 && c0 < 0), less1 = __ballot_sync(FULL_MASK, tie1 && c1 < 0);
+                    if (less0 | less1) { tie0 = tie0 && c0 < 0; tie1 = tie1 && c1 < 0; m0 = less0; m1 = less1; continue; }
+                    tie0 = tie0 && c0 == 0; tie1 = tie1 && c1 == 0;
+                    m0 = __ballot_sync(FULL_MASK, tie0); m1 = __ballot_sync(FULL_MASK, tie1);
+                    break;
+                }
+            }
+            int n0 = __popc(m0), gsize = n0 + __popc(m1);
+            uint32_t ltm = (1u << lane) - 1u;
+            if (tie0) { uint64_t p = cpos + __popc(m0 & ltm); contrib[p] = ((uint64_t)(p == cpos) << 63) | ((uint64_t)lane << 56) | cur[0]; head[p] = (p == cpos); }
+            if (tie1) { uint64_t p = cpos + n0 + __popc(m1 & ltm); contrib[p] = ((uint64_t)(p == cpos) << 63) | ((uint64_t)(lane + 32) << 56) | cur[1]; head[p] = (p == cpos); }
+            if (lane == 0) atomicAdd(&s_hist[gsize - 1], 1u);
+            cpos += gsize;
+            if (tie0) { cur[0]++; valid[0] = cur[0] < end[0]; if (valid[0]) t[0] = tok[base[0] + cur[0]]; }
+            if (tie1) { cur[1]++; valid[1] = cur[1] < end[1]; if (valid[1]) t[1] = tok[base[1] + cur[1]]; }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < MAXK; k += blockDim.x) if (s_hist[k]) atomicAdd(&hist[k], (unsigned long long)s_hist[k]);
+}
+
+__global__ void __launch_bounds__(256) k_op_first(const uint32_t* __restrict__ head, const uint64_t* __restrict__ opidx, uint64_t ncontrib, uint64_t* __restrict__ op_first) {
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncontrib && head[c]) op_first[opidx[c]] = c;
+    if (c == ncontrib) op_first[opidx[ncontrib]] = ncontrib;
+}
+
+// ---- K4 wrappers -----------------------------------------------------------------------------------------------------------------
+struct RunStats { unsigned long long merged_unfiltereds, rows_out, partitions_out; };
+
+__global__ void __launch_bounds__(128) k_partition_size(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
+        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
+        RunStats* __restrict__ stats, DevErr* __restrict__ err) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    PartStats st{0, 0}; unsigned long long wrote = 0;
+    if (j < nparts) {
+        uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
+        PartOut out{0, 0, 0, 0}; int e = 0;
+        process_partition<false>(*Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, out, st, e);
+        if (e) { uint64_t en = contrib[c0]; report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, (int)((en >> 56) & 0x7F), upos[pbase[(en >> 56) & 0x7F] + (en & 0xFFFFFFFFFFull)] - Pp->in[(en >> 56) & 0x7F].ubase); out = PartOut{0, 0, 0, 0}; }
+        dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
+        wrote = out.dsize ? 1 : 0;
+    }
+    unsigned long long a = st.merged_unfiltereds, r = st.rows_out;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { a += __shfl_xor_sync(FULL_MASK, a, d); r += __shfl_xor_sync(FULL_MASK, r, d); wrote += __shfl_xor_sync(FULL_MASK, wrote, d); }
+    if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(&stats->merged_unfiltereds, a); if (r) atomicAdd(&stats->rows_out, r); if (wrote) atomicAdd(&stats->partitions_out, wrote); }
+}
+
+// Index.db entry size once the data position is known: u16 keyLen | key | vint position | vint32 payload size | payload
+__global__ void __launch_bounds__(256) k_index_sizes(uint64_t nparts, const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos,
+                                                     const uint32_t* __restrict__ ipay, const uint32_t* __restrict__ ihead, uint32_t* __restrict__ isize) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nparts) return;
+    isize[j] = dsize[j] ? ihead[j] + vint_size(dpos[j]) + vint_size(ipay[j]) + ipay[j] : 0;
+}
+
+__global__ void __launch_bounds__(128) k_partition_emit(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
+        const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos, const uint32_t* __restrict__ ipay, const uint32_t* __restrict__ nblk,
+        const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nparts || !dsize[j]) return;
+    uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
+    PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+    process_partition<true>(*Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], out, st, e);
+    if (e || out.dsize != dsize[j]) report_err(err, 8, 0, j);
+}
+
+} // namespace b200c
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int flags) {
+    if (!c || !m || !res) return B200C_EINVAL;
+    auto t_start = std::chrono::steady_clock::now();
+    cudaSetDevice(c->device);
+    c->cancel.store(0); c->prog_stage.store(0);
+    if (m->abi_version != B200C_ABI_VERSION || m->ninputs <= 0) { c->err = "bad manifest"; return B200C_EINVAL; }
+    if (m->ninputs > MAXK) { c->err = "more than 64 inputs per call"; return B200C_EUNSUPPORTED; }
+    if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) { c->err = "static rows / tombstone_option / strict liveness"; return B200C_EUNSUPPORTED; }
+    if (m->nclustering > MAXCLUST || m->ncolumns >= 64 || m->ncolumns < 0) { c->err = "schema outside the supported envelope"; return B200C_EUNSUPPORTED; }
+    if (m->max_sstable_bytes) { c->err = "max_sstable_bytes (LCS output switching) is not implemented on the GPU yet"; return B200C_EUNSUPPORTED; }
+    if (res->noutputs_cap < 1 || !res->outputs) { c->err = "no output slot"; return B200C_EINVAL; }
+    const bool dev = flags & B200C_FLAG_DEVICE_PTRS;
+    const int K = m->ninputs;
+
+    // ---- layout of the concatenated device buffers -------------------------------------------------------------------------------
+    std::vector<uint64_t> ubase(K + 1), ibase(K + 1), cbase(K + 1), obase(K + 1), bbase(K + 1);
+    CParams hp; memset(&hp, 0, sizeof(hp));
+    uint64_t uo = 0, io = 0, co = 0, oo = 0, bo = 0;
+    for (int i = 0; i < K; i++) {
+        const b200c_input& in = m->inputs[i];
+        if (in.chunk_len <= 0 || in.chunk_len > 65536 || (in.chunk_len & (in.chunk_len - 1))) { c->err = "input chunk_len"; return B200C_EUNSUPPORTED; }
+        if (in.ncolumns < 0 || in.ncolumns >= 64) { c->err = "input columns"; return B200C_EUNSUPPORTED; }
+        if (in.nchunks != (in.data_length + in.chunk_len - 1) / (uint64_t)in.chunk_len) { c->err = "chunk count does not match data_length"; return B200C_EINVAL; }
+        ubase[i] = uo; uo += (in.data_length + 64 + 65535) & ~65535ull;
+        ibase[i] = io; io += (in.index_len + 64 + 255) & ~255ull;
+        cbase[i] = co; co += (in.data_len + 64 + 255) & ~255ull;
+        obase[i] = oo; oo += in.nchunks + 1;
+        bbase[i] = bo; bo += (in.index_len + IB - 1) / IB;
+        InDesc& d = hp.in[i];
+        d.ubase = ubase[i]; d.ulen = in.data_length; d.ibase = ibase[i]; d.ilen = in.index_len;
+        d.min_ts = in.header_stats.min_timestamp; d.min_ldt = in.header_stats.min_local_deletion_time; d.min_ttl = in.header_stats.min_ttl;
+        d.ncols = in.ncolumns;
+        for (int k = 0; k < in.ncolumns; k++) { if (in.column_map[k] < 0 || in.column_map[k] >= m->ncolumns) { c->err = "column_map"; return B200C_EINVAL; } d.colmap[k] = in.column_map[k]; }
+    }
+    ubase[K] = uo; ibase[K] = io; cbase[K] = co; obase[K] = oo; bbase[K] = bo;
+    const uint64_t nblocks = bo;
+    hp.ninputs = K; hp.nclust = m->nclustering; hp.ncols = m->ncolumns; hp.column_index_size = m->column_index_size > 0 ? m->column_index_size : 65536;
+    for (int k = 0; k < m->nclustering; k++) { hp.ctype[k] = m->clustering[k].type; hp.cfix[k] = m->clustering[k].fixed_len; }
+    for (int k = 0; k < m->ncolumns; k++) hp.vfix[k] = m->columns[k].fixed_len;
+    hp.o_min_ts = m->out_stats.min_timestamp; hp.o_min_ldt = m->out_stats.min_local_deletion_time; hp.o_min_ttl = m->out_stats.min_ttl;
+    hp.now = m->now_in_sec; hp.gc_before = m->gc_before; hp.purge_max_ts = m->purge_max_timestamp;
+
+    uint8_t *U, *CD, *IDX; uint64_t* CO; CParams* dP; uint64_t* d_bbase; DevErr* d_err; ChunkErr* d_cerr; RunStats* d_stats; unsigned long long* d_hist;
+    B200C_TRY(ws_typed(c, WS_U, uo + 64, &U));
+    B200C_TRY(ws_typed(c, WS_CD, co + 64, &CD));
+    B200C_TRY(ws_typed(c, WS_CO, oo + 1, &CO));
+    B200C_TRY(ws_typed(c, WS_IDX, io + 64, &IDX));
+    B200C_TRY(ws_typed(c, WS_PARAMS, 1, &dP));
+    B200C_TRY(ws_typed(c, WS_BBASE, (size_t)K + 1, &d_bbase));
+    { uint8_t* p; B200C_TRY(ws_typed(c, WS_ERR2, 4096, &p)); d_err = (DevErr*)p; d_cerr = (ChunkErr*)(p + 64); d_stats = (RunStats*)(p + 128); d_hist = (unsigned long long*)(p + 256); }
+    hp.U = U;
+    cudaStream_t st = c->stream;
+    B200C_CUDA_TRY(c, cudaMemsetAsync(d_err, 0xFF, 64, st));
+    B200C_CUDA_TRY(c, cudaMemsetAsync(d_cerr, 0xFF, 64, st));
+    B200C_CUDA_TRY(c, cudaMemsetAsync(d_stats, 0, 128 + MAXK * 8 + 128, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(d_bbase, bbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
+    cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    uint64_t bytes_read = 0;
+    for (int i = 0; i < K; i++) {
+        const b200c_input& in = m->inputs[i];
+        bytes_read += in.data_length;
+        if (in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, st));
+        if (in.index_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index, in.index_len, kind, st));
+        if (in.nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(CO + obase[i], in.chunk_offsets, in.nchunks * 8, kind, st));
+    }
+    c->prog_total.store(bytes_read); c->prog_scanned.store(0);
+    timing_begin(c);
+
+    // ---- K1: decompress + verify ------------------------------------------------------------------------------------------------
+    c->prog_stage.store(1);
+    for (int i = 0; i < K; i++) {
+        const b200c_input& in = m->inputs[i];
+        if (in.compressor != COMP_LZ4 && in.compressor != COMP_SNAPPY && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
+        B200C_TRY(decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
+                                           in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr));
+    }
+    uint64_t* h = (uint64_t*)c->h_pinned;
+    auto check_cancel = [&]() -> int { if (c->cancel.load()) { c->err = "cancelled"; cudaStreamSynchronize(st); return B200C_ECANCELLED; } return B200C_OK; };
+
+    // ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
+    c->prog_stage.store(2);
+    uint64_t *d_istart, *d_iend, *d_iscan; uint32_t *d_icnt, *d_ihit, *d_ibad;
+    B200C_TRY(ws_typed(c, WS_ISTART, nblocks + 1, &d_istart));
+    B200C_TRY(ws_typed(c, WS_IEND, nblocks + 1, &d_iend));
+    B200C_TRY(ws_typed(c, WS_ICNT, nblocks + 1, &d_icnt));
+    B200C_TRY(ws_typed(c, WS_IHIT, nblocks + 1, &d_ihit));
+    B200C_TRY(ws_typed(c, WS_IBAD, (size_t)K + 1, &d_ibad));
+    B200C_TRY(ws_typed(c, WS_ISCAN, nblocks + 2, &d_iscan));
+    uint64_t total_parts = 0;
+    std::vector<uint64_t> pcount(K, 0), pbase(K + 1, 0);
+    if (nblocks) {
+        unsigned g = (unsigned)((nblocks + 255) / 256);
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_ihit, 0, nblocks * 4, st));
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_ibad, 0, (K + 1) * 4, st));
+        B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, nblocks, d_istart);
+        B200C_LAUNCH(c, k_index_chain, g, 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iend);
+        B200C_LAUNCH(c, k_index_verify_a, g, 256, 0, dP, d_bbase, nblocks, d_istart, d_iend, d_ihit, d_ibad);
+        B200C_LAUNCH(c, k_index_verify_b, g, 256, 0, dP, d_bbase, nblocks, d_istart, d_ihit, d_ibad);
+        B200C_LAUNCH(c, k_index_seq, (K + 63) / 64, 64, 0, dP, IDX, d_bbase, d_istart, d_icnt, d_ibad, d_err);
+        B200C_TRY(exclusive_scan<uint32_t>(c, d_icnt, nblocks, d_iscan, WS_SCANA, 0));
+    } else B200C_CUDA_TRY(c, cudaMemsetAsync(d_iscan, 0, 16, st));
+    // read back: chunk errors, index errors, per-input partition counts
+    {
+        std::vector<uint64_t> tmp(K + 1);
+        for (int i = 0; i <= K; i++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8 + i, d_iscan + bbase[i], 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cerr, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_err, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (h[0] != ~0ull) {
+            // the decompress kernels share one error word; re-run attribution on the host side: find the input owning the failing launch
+            uint64_t chunk = h[0] >> 8; int kindc = (int)(h[0] & 0xff);
+            int which = 0;   // first input whose chunk index range contains a failure: verify per input (rare path, so simply re-run per input)
+            for (int i = 0; i < K; i++) {
+                const b200c_input& in = m->inputs[i];
+                B200C_CUDA_TRY(c, cudaMemsetAsync(d_cerr, 0xFF, 64, st));
+                B200C_TRY(decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
+                                                   in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr));
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cerr, 8, cudaMemcpyDeviceToHost, st));
+                B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                if (h[0] != ~0ull) { which = i; chunk = h[0] >> 8; kindc = (int)(h[0] & 0xff); break; }
+            }
+            res->corruption.input = which; res->corruption.kind = kindc; res->corruption.chunk = chunk; res->corruption.offset = 0;
+            c->err = std::string(kindc == 1 ? "chunk CRC mismatch" : "malformed compressed chunk") + " in input " + std::to_string(which) + " chunk " + std::to_string(chunk);
+            timing_end(c);
+            return B200C_ECORRUPT;
+        }
+        if (h[1] != ~0ull) {
+            res->corruption.input = (int)((h[1] >> 48) & 0xFF); res->corruption.kind = (int)(h[1] >> 56); res->corruption.chunk = 0; res->corruption.offset = h[1] & 0xFFFFFFFFFFFFull;
+            c->err = "malformed Index.db in input " + std::to_string(res->corruption.input);
+            timing_end(c);
+            return B200C_ECORRUPT;
+        }
+        for (int i = 0; i < K; i++) { pcount[i] = h[8 + i + 1] - h[8 + i]; pbase[i] = total_parts; total_parts += pcount[i] + 1; }
+        pbase[K] = total_parts;
+    }
+    B200C_TRY(check_cancel());
+    c->prog_scanned.store(bytes_read / 4);
+    if (total_parts - K >= (1ull << 40)) { c->err = "too many partitions"; return B200C_EUNSUPPORTED; }
+
+    int64_t* d_tok; uint64_t *d_kp, *d_upos, *d_pbase, *d_pcount, *d_range; uint16_t* d_klen;
+    B200C_TRY(ws_typed(c, WS_TOK, total_parts + 1, &d_tok));
+    B200C_TRY(ws_typed(c, WS_KP, total_parts + 1, &d_kp));
+    B200C_TRY(ws_typed(c, WS_KLEN, total_parts + 1, &d_klen));
+    B200C_TRY(ws_typed(c, WS_UPOS, total_parts + 1, &d_upos));
+    B200C_TRY(ws_typed(c, WS_PBASE, (size_t)2 * K + 2, &d_pbase)); d_pcount = d_pbase + K + 1;
+    B200C_TRY(ws_typed(c, WS_RANGE, (size_t)2 * K + 16, &d_range));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pbase, pbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pcount, pcount.data(), K * 8, cudaMemcpyHostToDevice, st));
+    if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
+                              d_tok, d_kp, d_klen, d_upos, d_err);
+    B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range);
+
+    // ---- K3: partition merge -------------------------------------------------------------------------------------------------------
+    c->prog_stage.store(3);
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
+    B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (h[200] != ~0ull) {
+        res->corruption.input = (int)((h[200] >> 48) & 0xFF); res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = h[200] & 0xFFFFFFFFFFFFull;
+        c->err = "Index.db does not match Data.db in input " + std::to_string(res->corruption.input);
+        timing_end(c);
+        return B200C_ECORRUPT;
+    }
+    uint64_t ncontrib = 0;
+    for (int i = 0; i < K; i++) ncontrib += h[2 * i + 1] - h[2 * i];
+    const uint64_t nbuckets = std::max<uint64_t>(1, ncontrib / 256);
+    uint64_t *d_bstart, *d_contrib, *d_opidx, *d_opfirst; uint32_t* d_head; MergeGeom* d_geom;
+    B200C_TRY(ws_typed(c, WS_BSTART, (nbuckets + 1) * K + 8, &d_bstart)); d_geom = (MergeGeom*)(d_range + 2 * K + 2);
+    B200C_TRY(ws_typed(c, WS_CONTRIB, ncontrib + 1, &d_contrib));
+    B200C_TRY(ws_typed(c, WS_HEAD, ncontrib + 1, &d_head));
+    B200C_TRY(ws_typed(c, WS_OPIDX, ncontrib + 2, &d_opidx));
+    uint64_t nparts = 0;
+    if (ncontrib) {
+        B200C_LAUNCH(c, k_merge_geom, 1, 1, 0, dP, d_pbase, d_range, d_tok, nbuckets, d_geom);
+        B200C_LAUNCH(c, k_bucket_bounds, (unsigned)(((nbuckets + 1) * K + 255) / 256), 256, 0, dP, d_pbase, d_range, d_tok, d_geom, d_bstart);
+        B200C_LAUNCH(c, k_merge_buckets, (unsigned)((nbuckets + 3) / 4), 128, 0, dP, d_pbase, d_range, d_tok, d_kp, d_klen, d_upos, d_bstart, nbuckets, d_contrib, d_head, d_hist);
+        B200C_TRY(exclusive_scan<uint32_t>(c, d_head, ncontrib, d_opidx, WS_SCANA, 0));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_opidx + ncontrib, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        nparts = h[0];
+    }
+    B200C_TRY(ws_typed(c, WS_OPFIRST, nparts + 2, &d_opfirst));
+    if (ncontrib) B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
+    B200C_TRY(check_cancel());
+    c->prog_scanned.store(bytes_read / 2);
+
+    // ---- K4: row merge + serialise ---------------------------------------------------------------------------------------------------
+    c->prog_stage.store(4);
+    uint64_t *d_dsize, *d_dpos, *d_ipos; uint32_t *d_ipay, *d_nblk, *d_ihead, *d_isize;
+    B200C_TRY(ws_typed(c, WS_DSIZE, nparts + 1, &d_dsize));
+    B200C_TRY(ws_typed(c, WS_DPOS, nparts + 2, &d_dpos));
+    B200C_TRY(ws_typed(c, WS_IPOS, nparts + 2, &d_ipos));
+    B200C_TRY(ws_typed(c, WS_IPAY, nparts + 1, &d_ipay));
+    B200C_TRY(ws_typed(c, WS_NBLK, nparts + 1, &d_nblk));
+    B200C_TRY(ws_typed(c, WS_IHEAD, nparts + 1, &d_ihead));
+    B200C_TRY(ws_typed(c, WS_ISIZE, nparts + 1, &d_isize));
+    uint64_t ulen_out = 0, ilen_out = 0;
+    if (nparts) {
+        unsigned g = (unsigned)((nparts + 127) / 128);
+        B200C_LAUNCH(c, k_partition_size, g, 128, 0, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
+        B200C_TRY(exclusive_scan<uint64_t>(c, d_dsize, nparts, d_dpos, WS_SCANA, 0));
+        B200C_LAUNCH(c, k_index_sizes, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_dsize, d_dpos, d_ipay, d_ihead, d_isize);
+        B200C_TRY(exclusive_scan<uint32_t>(c, d_isize, nparts, d_ipos, WS_SCANA + 3, 0));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_dpos + nparts, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_ipos + nparts, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 2, d_err, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (h[2] != ~0ull) {
+            int kinde = (int)(h[2] >> 56);
+            res->corruption.input = (int)((h[2] >> 48) & 0xFF); res->corruption.kind = 4; res->corruption.chunk = 0; res->corruption.offset = h[2] & 0xFFFFFFFFFFFFull;
+            timing_end(c);
+            if (kinde == 9) { c->err = "unsupported feature in input " + std::to_string(res->corruption.input) + " (static row, complex column or shadowable deletion)"; return B200C_EUNSUPPORTED; }
+            c->err = "malformed Data.db in input " + std::to_string(res->corruption.input) + " near offset " + std::to_string(res->corruption.offset);
+            return B200C_ECORRUPT;
+        }
+        ulen_out = h[0]; ilen_out = h[1];
+    }
+    B200C_TRY(check_cancel());
+    uint8_t *UOUT, *IOUT;
+    B200C_TRY(ws_typed(c, WS_UOUT, ulen_out + 64, &UOUT));
+    B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
+    if (nparts && ulen_out)
+        B200C_LAUNCH(c, k_partition_emit, (unsigned)((nparts + 127) / 128), 128, 0, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_dsize, d_dpos, d_ipay, d_nblk,
+                     d_ipos, UOUT, IOUT, d_err);
+    c->prog_scanned.store(bytes_read * 3 / 4);
+
+    // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------
+    c->prog_stage.store(5);
+    b200c_output& out = res->outputs[0];
+    const uint64_t nchunks_out = (ulen_out + m->out_chunk_len - 1) / m->out_chunk_len;
+    const uint64_t bound = b200c_compress_bound(m->out_compressor, ulen_out, m->out_chunk_len);
+    res->required_data_cap = bound; res->required_index_cap = ilen_out; res->required_chunk_cap = nchunks_out;
+    if (m->out_chunk_len <= 0 || m->out_chunk_len > 65536 || (m->out_chunk_len & (m->out_chunk_len - 1))) { c->err = "output chunk_len"; return B200C_EUNSUPPORTED; }
+    uint8_t* d_dout = out.data; uint64_t* d_ooffs;
+    if (!dev) B200C_TRY(ws_typed(c, WS_DOUT, bound + 64, &d_dout));
+    else if (out.data_cap < bound) { c->err = "output data buffer too small"; timing_end(c); return B200C_ETOOSMALL; }
+    B200C_TRY(ws_typed(c, WS_OOFFS, nchunks_out + 2, &d_ooffs));
+    uint64_t out_len = 0; uint32_t digest = 0;
+    B200C_TRY(compress_stream_device(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound, d_ooffs, &out_len, &digest, WS_CODEC));
+    // final error word + stats
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
+    int trc = timing_end(c);
+    if (trc != B200C_OK) return trc;
+    if (h[0] != ~0ull) { c->err = "internal error: size/emit pass disagreement at output partition " + std::to_string(h[0] & 0xFFFFFFFFFFFFull); return B200C_ECUDA; }
+    RunStats rs; memcpy(&rs, h + 8, sizeof(rs));
+    res->noutputs = 1;
+    res->bytes_read = bytes_read; res->bytes_written = ulen_out; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib;
+    memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
+    for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
+    out.data_len = out_len; out.index_len = ilen_out; out.nchunks = nchunks_out; out.data_length = ulen_out; out.digest = digest;
+    out.partitions = rs.partitions_out; out.rows = rs.rows_out;
+    res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
+    int rc = B200C_OK;
+    if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
+    else if (!dev) {
+        if (out_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.data, d_dout, out_len, cudaMemcpyDeviceToHost, st));
+        if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToHost, st));
+        if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+    } else {
+        if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToDevice, st));
+        if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToDevice, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+    }
+    c->prog_scanned.store(bytes_read); c->prog_stage.store(6);
+    res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    return rc;
+}
+
 int b200c_poll(b200c_ctx* c, b200c_progress* p) {
     if (!c || !p) return B200C_EINVAL;
     p->bytes_scanned = c->prog_scanned.load(); p->bytes_total = c->prog_total.load(); p->stage = c->prog_stage.load(); p->_pad = 0;
     return B200C_OK;
 }
 void b200c_cancel(b200c_ctx* c) { if (c) c->cancel.store(1); }
-}
+
+} // extern "C"

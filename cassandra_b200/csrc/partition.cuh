@@ -1,0 +1,575 @@
+// partition.cuh — per-partition row merge, tombstone/timestamp reconciliation, purge and big-format serialisation.
+//
+// One thread owns one OUTPUT partition (the group of same-key input partitions found by the tournament merge) and runs
+// the same code twice: a size pass (counting sinks) and an emit pass (byte sinks) — "size -> exclusive scan -> emit".
+// Replaces, for that partition, the reference's lazy iterator stack:
+//   UnfilteredRowIterators.UnfilteredRowMergeIterator   S/db/rows/UnfilteredRowIterators.java:398-601
+//   Row.Merger.merge / ColumnDataReducer                S/db/rows/Row.java:730-849
+//   Cells.reconcile / resolveRegular                    S/db/rows/Cells.java:68-121
+//   RangeTombstoneMarker.Merger                         S/db/rows/RangeTombstoneMarker.java:72-199
+//   PurgeFunction + BTreeRow.purge + AbstractCell.purge S/db/partitions/PurgeFunction.java:36-145, S/db/rows/BTreeRow.java:457-499,
+//                                                       S/db/rows/AbstractCell.java:78-99
+//   SortedTablePartitionWriter / UnfilteredSerializer   S/io/sstable/format/SortedTablePartitionWriter.java:97-166,
+//                                                       S/db/rows/UnfilteredSerializer.java:151-305, S/db/rows/Cell.java:268-305
+//   BigFormatPartitionWriter / IndexInfo / RowIndexEntry S/io/sstable/format/big/BigFormatPartitionWriter.java:128-251,
+//                                                       S/io/sstable/IndexInfo.java:107-117, .../big/RowIndexEntry.java:625-642
+// Envelope: simple regular columns (< 64), <= 8 clustering columns, no static rows / complex columns / counters.
+#pragma once
+#include "common.cuh"
+
+namespace b200c {
+
+enum { MAXK = 64, MAXCOLS = 64, MAXCLUST = 8 };
+enum { TYPE_BYTES = 0, TYPE_FIXED_SIGNED = 1, TYPE_FIXED_BYTES = 2, TYPE_VAR_SIGNED = 3 };
+enum { K_EXCL_END = 0, K_INCL_START = 1, K_EXCL_END_INCL_START = 2, K_STATIC = 3, K_CLUSTERING = 4, K_INCL_END_EXCL_START = 5, K_INCL_END = 6, K_EXCL_START = 7 };
+enum { PERR_NONE = 0, PERR_CORRUPT = 1, PERR_UNSUPPORTED = 2 };
+
+#define I64_MIN ((int64_t)0x8000000000000000LL)
+#define I64_MAX ((int64_t)0x7FFFFFFFFFFFFFFFLL)
+
+struct InDesc {
+    uint64_t ubase, ulen;          // this input's uncompressed stream inside U
+    uint64_t ibase, ilen;          // this input's Index.db inside IDX
+    int64_t min_ts, min_ldt; int32_t min_ttl; int32_t ncols;
+    int32_t colmap[MAXCOLS];
+};
+struct CParams {
+    const uint8_t* U;              // all inputs' uncompressed Data streams, back to back (16-byte aligned bases)
+    int32_t ninputs, nclust, ncols, column_index_size;
+    int32_t ctype[MAXCLUST], cfix[MAXCLUST], vfix[MAXCOLS];
+    int64_t o_min_ts, o_min_ldt; int32_t o_min_ttl, _pad;
+    int64_t now, gc_before, purge_max_ts;
+    InDesc in[MAXK];
+};
+
+struct DT { int64_t mfda, ldt; };
+__device__ __forceinline__ DT dt_live() { DT d; d.mfda = I64_MIN; d.ldt = I64_MAX; return d; }
+__device__ __forceinline__ bool dt_is_live(const DT& d) { return d.mfda == I64_MIN && d.ldt == I64_MAX; }
+__device__ __forceinline__ bool dt_supersedes(const DT& a, const DT& b) { return a.mfda > b.mfda || (a.mfda == b.mfda && a.ldt > b.ldt); }
+__device__ __forceinline__ bool dt_deletes(const DT& d, int64_t ts) { return ts <= d.mfda; }
+__device__ __forceinline__ bool dt_eq(const DT& a, const DT& b) { return a.mfda == b.mfda && a.ldt == b.ldt; }
+
+struct Live { int64_t ts, ldt; int32_t ttl; };
+__device__ __forceinline__ Live live_empty() { Live l; l.ts = I64_MIN; l.ldt = I64_MAX; l.ttl = 0; return l; }
+__device__ __forceinline__ bool live_is_empty(const Live& l) { return l.ts == I64_MIN; }
+__device__ __forceinline__ bool live_is_live(const Live& l, int64_t now) {
+    if (l.ts == I64_MIN) return false; if (l.ttl == 0x7FFFFFFF) return false; if (l.ttl != 0) return now < l.ldt; return true; }
+__device__ __forceinline__ bool live_supersedes(const Live& a, const Live& b) {      // LivenessInfo.supersedes :216-225
+    if (a.ts != b.ts) return a.ts > b.ts;
+    bool ae = a.ttl == 0x7FFFFFFF, be = b.ttl == 0x7FFFFFFF;
+    if (ae != be) return ae;
+    if ((a.ttl != 0) == (b.ttl != 0)) return a.ldt > b.ldt;
+    return a.ttl != 0;
+}
+
+struct MCell { int64_t ts, ldt; uint64_t voff; int32_t ttl, vlen; bool present; };
+
+__device__ __forceinline__ int kind_comparison(int k) { return (0x33321000 >> (4 * k)) & 0xF; }          // {0,0,0,1,2,3,3,3}
+__device__ __forceinline__ int kind_vs_clustering(int k) { return k < 4 ? -1 : (k == 4 ? 0 : 1); }
+__device__ __forceinline__ bool kind_is_boundary(int k) { return k == K_EXCL_END_INCL_START || k == K_INCL_END_EXCL_START; }
+__device__ __forceinline__ bool kind_is_start(int k) { return k == K_INCL_START || k == K_EXCL_START; }
+
+// ---- bounded reader over U ------------------------------------------------------------------------------------------------
+struct Rd {
+    const uint8_t* U; uint64_t p, end; int err;
+    __device__ __forceinline__ uint32_t u8() { if (p >= end) { err = PERR_CORRUPT; return 1; } return U[p++]; }
+    __device__ __forceinline__ uint32_t be16() { uint32_t a = u8(); return (a << 8) | u8(); }
+    __device__ __forceinline__ uint64_t vint() {
+        if (p >= end) { err = PERR_CORRUPT; return 0; }
+        uint32_t first = U[p];
+        if (first < 0x80) { p++; return first; }
+        int extra = __clz((int)(~(first << 24)));
+        if (p + 1 + extra > end) { err = PERR_CORRUPT; p = end; return 0; }
+        uint64_t r = first & (0xffu >> extra);
+        for (int i = 0; i < extra; i++) r = (r << 8) | U[p + 1 + i];
+        p += 1 + extra;
+        return r;
+    }
+    __device__ __forceinline__ int32_t vint32() { uint64_t v = vint(); int32_t r = (int32_t)v; if ((int64_t)r != (int64_t)v) err = PERR_CORRUPT; return r; }
+    __device__ __forceinline__ void skip(uint64_t n) { if (end - p < n) { err = PERR_CORRUPT; p = end; } else p += n; }
+};
+
+// ---- sinks ----------------------------------------------------------------------------------------------------------------
+template <bool EMIT> struct Sink {
+    uint8_t* base; uint64_t pos;
+    __device__ __forceinline__ void u8(uint32_t v) { if (EMIT) base[pos] = (uint8_t)v; pos++; }
+    __device__ __forceinline__ void be16(uint32_t v) { u8(v >> 8); u8(v); }
+    __device__ __forceinline__ void be32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
+    __device__ __forceinline__ void be64(uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); }
+    __device__ __forceinline__ void vint(uint64_t v) {
+        int size = vint_size(v);
+        if (EMIT) {
+            if (size == 1) base[pos] = (uint8_t)v;
+            else if (size < 9) {
+                uint64_t reg = (v << ((8 - size) << 3)) | ((uint64_t)(uint8_t)(~(0xffu >> (size - 1))) << 56);
+                for (int i = 0; i < size; i++) base[pos + i] = (uint8_t)(reg >> (56 - 8 * i));
+            } else { base[pos] = 0xFF; for (int i = 0; i < 8; i++) base[pos + 1 + i] = (uint8_t)(v >> (56 - 8 * i)); }
+        }
+        pos += size;
+    }
+    __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
+};
+
+struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialised clustering values (header vint + values) in U
+
+struct Cur {                       // cursor of one contributing input partition
+    uint64_t pos, next, end;       // current unfiltered, the one after it, end of the partition
+    uint32_t ck_rel, ckend_rel, body_rel;
+    uint8_t flags, ext, kind, n, src; bool done;
+};
+
+// parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
+__device__ void cur_load(const CParams& P, Cur& c, int& err) {
+    for (;;) {
+        Rd r{P.U, c.pos, c.end, 0};
+        uint32_t flags = r.u8();
+        if (r.err) { err = PERR_CORRUPT; c.done = true; return; }
+        if (flags & 0x01) { c.done = true; c.next = r.p; return; }
+        c.flags = (uint8_t)flags; c.ext = 0;
+        if (flags & 0x02) {
+            c.kind = (uint8_t)r.u8(); c.n = (uint8_t)r.be16();
+            if (c.kind > 7 || c.kind == K_STATIC || c.kind == K_CLUSTERING || c.n > P.nclust) { err = PERR_CORRUPT; c.done = true; return; }
+        } else {
+            if (flags & 0x80) c.ext = (uint8_t)r.u8();
+            if ((c.ext & 0x03) || (flags & 0x40)) { err = PERR_UNSUPPORTED; c.done = true; return; }
+            c.kind = K_CLUSTERING; c.n = (uint8_t)P.nclust;
+        }
+        c.ck_rel = (uint32_t)(r.p - c.pos);
+        if (c.n) {
+            uint64_t header = r.vint();
+            for (int i = 0; i < c.n; i++) {
+                if ((header >> (2 * i)) & 3) continue;
+                uint64_t len = P.cfix[i] > 0 ? (uint64_t)P.cfix[i] : r.vint();
+                r.skip(len);
+            }
+        }
+        c.ckend_rel = (uint32_t)(r.p - c.pos);
+        uint64_t sz = r.vint();
+        uint64_t after = r.p;
+        r.vint();                                   // previous unfiltered size
+        c.body_rel = (uint32_t)(r.p - c.pos);
+        c.next = after + sz;
+        if (r.err || c.next > c.end || c.next < r.p) { err = PERR_CORRUPT; c.done = true; return; }
+        if (!(flags & 0x02) && !(flags & 0x14)) {   // maybe an empty row: no liveness, no deletion — any cells?
+            int ncin = P.in[c.src].ncols; bool any;
+            if (flags & 0x20) any = ncin > 0;
+            else { Rd b{P.U, c.pos + c.body_rel, c.next, 0}; uint64_t missing = b.vint(); uint64_t mask = ncin >= 64 ? ~0ull : ((1ull << ncin) - 1); any = ((~missing) & mask) != 0; }
+            if (!any) { c.pos = c.next; continue; }
+        }
+        return;
+    }
+}
+
+__device__ __forceinline__ int cmp_bytes(const uint8_t* a, int la, const uint8_t* b, int lb) {
+    int n = la < lb ? la : lb;
+    for (int i = 0; i < n; i++) { int d = (int)a[i] - (int)b[i]; if (d) return d < 0 ? -1 : 1; }
+    return la == lb ? 0 : (la < lb ? -1 : 1);
+}
+__device__ __forceinline__ int cmp_value(int type, const uint8_t* a, int la, const uint8_t* b, int lb) {
+    if (type == TYPE_FIXED_SIGNED || type == TYPE_VAR_SIGNED) {
+        if (la == 0 || lb == 0) return la == 0 ? (lb == 0 ? 0 : -1) : 1;
+        int d = (int)(int8_t)a[0] - (int)(int8_t)b[0];
+        if (d) return d < 0 ? -1 : 1;
+        return cmp_bytes(a + 1, la - 1, b + 1, lb - 1);
+    }
+    return cmp_bytes(a, la, b, lb);
+}
+
+// ClusteringComparator.compare: S/db/ClusteringComparator.java:140-157
+__device__ int cmp_clust(const CParams& P, const Cur& a, const Cur& b) {
+    const uint8_t* pa = P.U + a.pos + a.ck_rel; const uint8_t* pb = P.U + b.pos + b.ck_rel;
+    const uint8_t* ea = P.U + a.pos + a.ckend_rel; const uint8_t* eb = P.U + b.pos + b.ckend_rel;
+    int m = a.n < b.n ? a.n : b.n;
+    uint64_t ha = 0, hb = 0;
+    if (a.n) pa += vint_read(pa, ea, &ha);
+    if (b.n) pb += vint_read(pb, eb, &hb);
+    for (int i = 0; i < m; i++) {
+        bool na = (ha >> (2 * i + 1)) & 1, nb = (hb >> (2 * i + 1)) & 1;
+        bool xa = (ha >> (2 * i)) & 1, xb = (hb >> (2 * i)) & 1;
+        int la = 0, lb = 0;
+        if (!na && !xa) { if (P.cfix[i] > 0) la = P.cfix[i]; else { uint64_t v = 0; pa += vint_read(pa, ea, &v); la = (int)v; } }
+        if (!nb && !xb) { if (P.cfix[i] > 0) lb = P.cfix[i]; else { uint64_t v = 0; pb += vint_read(pb, eb, &v); lb = (int)v; } }
+        if (na || nb) { if (na != nb) return na ? -1 : 1; }
+        else { int c = cmp_value(P.ctype[i], pa, la, pb, lb); if (c) return c; }
+        pa += la; pb += lb;
+    }
+    if (a.n == b.n) { int d = kind_comparison(a.kind) - kind_comparison(b.kind); return d < 0 ? -1 : (d > 0 ? 1 : 0); }
+    return a.n < b.n ? kind_vs_clustering(a.kind) : -kind_vs_clustering(b.kind);
+}
+
+__device__ __forceinline__ DT read_delta_dt(Rd& r, const InDesc& in) {
+    DT d; d.mfda = (int64_t)(r.vint() + (uint64_t)in.min_ts); d.ldt = (int64_t)r.vint32() + in.min_ldt; return d;
+}
+__device__ __forceinline__ int64_t decode_ldt(int64_t ldt, int32_t ttl) {          // Cell.decodeLocalDeletionTime :221-239
+    if (ldt >= ttl) return ldt;
+    if (ldt < 0) return (int64_t)(uint32_t)(int32_t)ldt;
+    if (ttl == 0x7FFFFFFF) return ldt;
+    return (int64_t)0xFFFFFFFEu;
+}
+// DeletionTime.Serializer.deserialize (oa): S/db/DeletionTime.java:222-243
+__device__ __forceinline__ DT read_partition_dt(Rd& r) {
+    uint32_t f = r.u8();
+    if (f & 0x80) { if (f != 0x80) r.err = PERR_CORRUPT; return dt_live(); }
+    uint64_t m = f; for (int i = 0; i < 7; i++) m = (m << 8) | r.u8();
+    uint64_t l = 0; for (int i = 0; i < 4; i++) l = (l << 8) | r.u8();
+    DT d; d.mfda = (int64_t)m; d.ldt = (int64_t)l; return d;
+}
+
+struct Purger {
+    int64_t now, gc_before, max_ts;
+    __device__ __forceinline__ bool ts_ldt(int64_t ts, int64_t ldt) const { return ldt < gc_before && (max_ts == I64_MAX || ts < max_ts); }
+    __device__ __forceinline__ bool dt(const DT& d) const { return !dt_is_live(d) && ts_ldt(d.mfda, d.ldt); }
+    __device__ __forceinline__ bool live(const Live& l) const { return !live_is_live(l, now) && ts_ldt(l.ts, l.ldt); }
+};
+
+// Cells.resolveRegular: S/db/rows/Cells.java:83-121. true => keep `l`, false => take `r`
+__device__ bool reconcile_keep_left(const CParams& P, const MCell& l, const MCell& r) {
+    if (l.ts != r.ts) return l.ts > r.ts;
+    bool le = l.ldt != I64_MAX, re = r.ldt != I64_MAX;
+    if (le | re) {
+        if (le != re) return le;
+        bool lt = l.ttl == 0, rt = r.ttl == 0;
+        if (lt != rt) return lt;
+        if (l.ldt != r.ldt) return l.ldt > r.ldt;
+    }
+    return cmp_bytes(P.U + l.voff, l.vlen, P.U + r.voff, r.vlen) >= 0;
+}
+
+// ---- partition writer (SortedTablePartitionWriter + BigFormatPartitionWriter state) ------------------------------------------
+template <bool EMIT> struct PWriter {
+    Sink<EMIT> d;                 // Data stream, positioned at the partition start
+    Sink<EMIT> ix;                // IndexInfo bytes of the promoted index (only emitted when nblocks_final > 1)
+    uint8_t* ix_offs;             // where the int32 offsets array goes (EMIT and nblocks_final > 1)
+    uint64_t start, header_len, prev_row_start, block_start;
+    uint32_t nblocks, nblocks_final;
+    bool started, have_first;
+    CkRef first, last;
+    DT open_marker;
+    uint64_t rows_out;
+};
+
+template <bool EMIT> __device__ __forceinline__ void write_partition_dt(Sink<EMIT>& s, const DT& d) {
+    if (dt_is_live(d)) s.u8(0x80); else { s.be64((uint64_t)d.mfda); s.be32((uint32_t)d.ldt); }
+}
+template <bool EMIT> __device__ __forceinline__ void write_delta_dt(Sink<EMIT>& s, const CParams& P, const DT& d) {
+    s.vint((uint64_t)d.mfda - (uint64_t)P.o_min_ts);
+    s.vint((uint64_t)(int64_t)(int32_t)(d.ldt - P.o_min_ldt));
+}
+template <bool EMIT> __device__ __forceinline__ void write_prefix(Sink<EMIT>& s, const CParams& P, const CkRef& c) {   // ClusteringPrefix.Serializer.serialize :408-421
+    s.u8(c.kind);
+    if (c.kind != K_CLUSTERING) s.be16(c.n);
+    s.copy(P.U + c.off, c.len);
+}
+
+template <bool EMIT> __device__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
+    uint64_t cur = w.d.pos - w.start;
+    bool emit_info = EMIT && w.nblocks_final > 1;
+    if (emit_info) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
+    if (!EMIT || emit_info) {
+        write_prefix(w.ix, P, w.first); write_prefix(w.ix, P, w.last);
+        w.ix.vint(w.block_start);
+        w.ix.vint(zigzag_enc((int64_t)(cur - w.block_start) - 65536));
+        w.ix.u8(dt_is_live(w.open_marker) ? 0 : 1);
+        if (!dt_is_live(w.open_marker)) write_partition_dt(w.ix, w.open_marker);
+    }
+    w.nblocks++;
+    w.have_first = false;
+}
+
+// book-keeping around one serialised unfiltered (SortedTablePartitionWriter.addUnfiltered :128-154, BigFormatPartitionWriter :208-215)
+template <bool EMIT> __device__ __forceinline__ uint64_t pw_begin_unf(PWriter<EMIT>& w, const CkRef& ck) {
+    uint64_t pos = w.d.pos - w.start;
+    if (!w.have_first) { w.first = ck; w.block_start = pos; w.have_first = true; }
+    return pos;
+}
+template <bool EMIT> __device__ __forceinline__ void pw_end_unf(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, uint64_t pos) {
+    w.last = ck; w.prev_row_start = pos; w.rows_out++;
+    if ((w.d.pos - w.start) - w.block_start >= (uint64_t)P.column_index_size) pw_add_index_block(w, P);
+}
+
+// row body: UnfilteredSerializer.serializeRowBody :213-269 + Cell.Serializer.serialize S/db/rows/Cell.java:268-305
+template <bool E> __device__ void put_row_body(Sink<E>& s, const CParams& P, int flags, const Live& info, const DT& del, const MCell* cells, int ncells_present) {
+    if (flags & 0x04) s.vint((uint64_t)info.ts - (uint64_t)P.o_min_ts);
+    if (flags & 0x08) { s.vint((uint64_t)(int64_t)(info.ttl - P.o_min_ttl)); s.vint((uint64_t)(int64_t)(int32_t)(info.ldt - P.o_min_ldt)); }
+    if (flags & 0x10) write_delta_dt(s, P, del);
+    if (!(flags & 0x20)) {
+        uint64_t missing = 0;
+        for (int c = 0; c < P.ncols; c++) if (!cells[c].present) missing |= 1ull << c;
+        s.vint(missing);
+    }
+    for (int c = 0; c < P.ncols; c++) {
+        const MCell& m = cells[c]; if (!m.present) continue;
+        bool has_value = m.vlen > 0, deleted = m.ldt != I64_MAX && m.ttl == 0, expiring = m.ttl != 0;
+        bool use_ts = !live_is_empty(info) && m.ts == info.ts;
+        bool use_ttl = expiring && info.ttl != 0 && m.ttl == info.ttl && m.ldt == info.ldt;
+        int cf = (has_value ? 0 : 0x04) | (deleted ? 0x01 : (expiring ? 0x02 : 0)) | (use_ts ? 0x08 : 0) | (use_ttl ? 0x10 : 0);
+        s.u8(cf);
+        if (!use_ts) s.vint((uint64_t)m.ts - (uint64_t)P.o_min_ts);
+        if ((deleted || expiring) && !use_ttl) s.vint((uint64_t)(int64_t)(int32_t)(m.ldt - P.o_min_ldt));
+        if (expiring && !use_ttl) s.vint((uint64_t)(int64_t)(m.ttl - P.o_min_ttl));
+        if (has_value) { if (P.vfix[c] <= 0) s.vint((uint64_t)m.vlen); s.copy(P.U + m.voff, (uint32_t)m.vlen); }
+    }
+}
+
+struct PartStats { uint64_t merged_unfiltereds; uint64_t rows_out; };
+
+// decodes the row at cursor `c` : liveness + deletion; returns a reader positioned at the columns subset / cells
+__device__ __forceinline__ Rd row_header(const CParams& P, const Cur& c, Live& info, DT& del) {
+    const InDesc& in = P.in[c.src];
+    Rd r{P.U, c.pos + c.body_rel, c.next, 0};
+    info = live_empty(); del = dt_live();
+    if (c.flags & 0x04) info.ts = (int64_t)(r.vint() + (uint64_t)in.min_ts);
+    if (c.flags & 0x08) { info.ttl = r.vint32() + in.min_ttl; info.ldt = (int64_t)r.vint32() + in.min_ldt; }
+    if (c.flags & 0x10) del = read_delta_dt(r, in);
+    return r;
+}
+
+// folds the cells of the row at cursor `c` into merged[] (ColumnDataReducer.getReduced :838-849)
+__device__ void fold_cells(const CParams& P, const Cur& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
+    const InDesc& in = P.in[c.src];
+    uint64_t missing = 0;
+    if (!(c.flags & 0x20)) missing = r.vint();
+    for (int i = 0; i < in.ncols; i++) {
+        if ((missing >> i) & 1) continue;
+        int oc = in.colmap[i];
+        uint32_t cf = r.u8();
+        bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
+        MCell m; m.present = true;
+        m.ts = use_ts ? info.ts : (int64_t)(r.vint() + (uint64_t)in.min_ts);
+        m.ldt = use_ttl ? info.ldt : ((deleted || expiring) ? (int64_t)r.vint32() + in.min_ldt : I64_MAX);
+        m.ttl = use_ttl ? info.ttl : (expiring ? r.vint32() + in.min_ttl : 0);
+        m.voff = r.p; m.vlen = 0;
+        if (has_value) {
+            int64_t len = P.vfix[oc] > 0 ? P.vfix[oc] : (int64_t)r.vint32();
+            if (len < 0) { r.err = PERR_CORRUPT; len = 0; }
+            m.voff = r.p; m.vlen = (int32_t)len; r.skip((uint64_t)len);
+        }
+        if (m.ttl < 0) r.err = PERR_CORRUPT;
+        if (m.ldt != I64_MAX) m.ldt = decode_ldt(m.ldt, m.ttl);
+        if (r.err) { err = r.err; return; }
+        if (apply_deletion && dt_deletes(active, m.ts)) continue;
+        if (!merged[oc].present || !reconcile_keep_left(P, merged[oc], m)) merged[oc] = m;
+    }
+}
+
+// BTreeRow.purge :457-499 + AbstractCell.purge :78-99. Returns the number of surviving cells, or -1 when the row disappears.
+__device__ int purge_row(const CParams& P, const Purger& pg, Live& info, DT& del, MCell* cells) {
+    if (pg.live(info)) info = live_empty();
+    if (pg.dt(del)) del = dt_live();
+    int present = 0;
+    for (int c = 0; c < P.ncols; c++) {
+        MCell& m = cells[c]; if (!m.present) continue;
+        bool is_live = m.ldt == I64_MAX || (m.ttl != 0 && pg.now < m.ldt);
+        if (!is_live) {
+            if (pg.ts_ldt(m.ts, m.ldt)) { m.present = false; continue; }
+            if (m.ttl != 0) {                       // expired TTL cell -> tombstone (ldt - ttl), value dropped, purged again
+                m.ldt = m.ldt - m.ttl; m.ttl = 0; m.vlen = 0;
+                if (pg.ts_ldt(m.ts, m.ldt)) { m.present = false; continue; }
+            }
+        }
+        present++;
+    }
+    if (live_is_empty(info) && dt_is_live(del) && present == 0) return -1;
+    return present;
+}
+
+template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, const CParams& P, uint64_t key_off, uint32_t klen, const DT& out_pdel) {
+    w.d.be16(klen); w.d.copy(P.U + key_off, klen); write_partition_dt(w.d, out_pdel);      // SortedTablePartitionWriter.start :97-115
+    w.header_len = w.d.pos - w.start; w.started = true;
+}
+
+template <bool EMIT> __device__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
+    int flags = 0;
+    if (!live_is_empty(info)) flags |= 0x04;
+    if (info.ttl != 0) flags |= 0x08;
+    if (!dt_is_live(del)) flags |= 0x10;
+    if (present == P.ncols) flags |= 0x20;
+    uint64_t pos = pw_begin_unf(w, ck);
+    uint64_t prev = pos - w.prev_row_start;
+    Sink<false> cs{nullptr, 0};
+    put_row_body(cs, P, flags, info, del, cells, present);
+    w.d.u8(flags); w.d.copy(P.U + ck.off, ck.len);
+    w.d.vint(cs.pos + vint_size(prev)); w.d.vint(prev);
+    put_row_body(w.d, P, flags, info, del, cells, present);
+    pw_end_unf(w, P, ck, pos);
+}
+
+// UnfilteredSerializer.serialize(RangeTombstoneMarker) :282-305
+template <bool EMIT> __device__ void write_marker(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const DT& m_close, const DT& m_open) {
+    uint64_t pos = pw_begin_unf(w, ck);
+    uint64_t prev = pos - w.prev_row_start;
+    Sink<false> cs{nullptr, 0};
+    bool boundary = kind_is_boundary(ck.kind), start = kind_is_start(ck.kind);
+    if (boundary) { write_delta_dt(cs, P, m_close); write_delta_dt(cs, P, m_open); } else write_delta_dt(cs, P, start ? m_open : m_close);
+    w.d.u8(0x02); w.d.u8(ck.kind); w.d.be16(ck.n); w.d.copy(P.U + ck.off, ck.len);
+    w.d.vint(cs.pos + vint_size(prev)); w.d.vint(prev);
+    if (boundary) { write_delta_dt(w.d, P, m_close); write_delta_dt(w.d, P, m_open); } else write_delta_dt(w.d, P, start ? m_open : m_close);
+    w.open_marker = (boundary || start) ? m_open : dt_live();
+    pw_end_unf(w, P, ck, pos);
+}
+
+// PurgeFunction.applyToMarker :116-143. Returns false when the marker disappears; may turn a boundary into a bound.
+__device__ __forceinline__ bool purge_marker(const Purger& pg, uint8_t& kind, DT& m_close, DT& m_open) {
+    if (kind_is_boundary(kind)) {
+        bool pc = pg.dt(m_close), po = pg.dt(m_open);
+        if (pc) { if (po) return false; kind = (kind == K_EXCL_END_INCL_START) ? K_INCL_START : K_EXCL_START; m_close = dt_live(); return true; }
+        if (po) { kind = (kind == K_EXCL_END_INCL_START) ? K_EXCL_END : K_INCL_END; m_open = dt_live(); }
+        return true;
+    }
+    return !pg.dt(kind_is_start(kind) ? m_open : m_close);
+}
+
+__device__ __forceinline__ void read_marker_dts(const CParams& P, const Cur& c, DT& m_close, DT& m_open, int& err) {
+    const InDesc& in = P.in[c.src];
+    Rd r{P.U, c.pos + c.body_rel, c.next, 0};
+    m_close = dt_live(); m_open = dt_live();
+    if (kind_is_boundary(c.kind)) { m_close = read_delta_dt(r, in); m_open = read_delta_dt(r, in); }
+    else if (kind_is_start(c.kind)) m_open = read_delta_dt(r, in);
+    else m_close = read_delta_dt(r, in);
+    if (r.err) err = r.err;
+}
+
+struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; };
+
+// The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
+template <bool EMIT>
+__device__ void process_partition(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
+                                  const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
+                                  uint8_t* dout, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
+                                  PartOut& out, PartStats& st, int& err) {
+    Cur cur[MAXK];
+    MCell merged[MAXCOLS];
+    DT open_dt[MAXK];
+    Purger pg{P.now, P.gc_before, P.purge_max_ts};
+    DT pdel = dt_live();
+    uint64_t key_off = 0; uint32_t klen = 0;
+    if (m > MAXK) { err = PERR_UNSUPPORTED; return; }
+    for (uint32_t v = 0; v < m; v++) {
+        uint64_t e = contrib[c0 + v];
+        int src = (int)((e >> 56) & 0x7F); uint64_t pidx = e & 0xFFFFFFFFFFull;
+        uint64_t g = pbase[src] + pidx;
+        uint64_t pos = part_upos[g], end = part_upos[g + 1];
+        Rd r{P.U, pos, end, 0};
+        uint32_t kl = r.be16(); r.skip(kl);
+        DT pd = read_partition_dt(r);
+        if (r.err) { err = r.err; return; }
+        if (v == 0) { key_off = pos + 2; klen = kl; }
+        if (!dt_supersedes(pdel, pd)) pdel = pd;                  // collectPartitionLevelDeletion :465-482
+        Cur& c = cur[v]; c.src = (uint8_t)src; c.pos = r.p; c.end = end; c.done = false; c.next = r.p;
+    }
+    DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;                 // PurgeFunction.applyToDeletion :95-99
+
+    PWriter<EMIT> w;
+    w.d.base = dout; w.d.pos = 0; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
+    w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
+    w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
+    // index entry layout (EMIT): [u16 kl][key][vint dpos][vint ipay]{[vint headerLen][DT][vint nblocks][IndexInfo..][i32 offsets..]}
+    uint32_t hdr_len_known = 2 + klen + (dt_is_live(out_pdel) ? 1 : 12);
+    uint32_t fixed = 2 + klen + vint_size(dpos) + vint_size(ipay_final);
+    uint32_t pre = fixed + vint_size(hdr_len_known) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
+    w.ix.base = EMIT ? iout + pre : nullptr; w.ix.pos = 0;
+    w.ix_offs = EMIT ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
+
+    if (m == 1) {
+        // single source: TrivialOneToOne (UnfilteredRowIterators.java:552-556) — no Row.Merger, only the purge transformation
+        Cur& c = cur[0];
+        for (;;) {
+            cur_load(P, c, err);
+            if (err || c.done) break;
+            st.merged_unfiltereds++;
+            CkRef ck{c.pos + c.ck_rel, c.ckend_rel - c.ck_rel, c.kind, c.n};
+            if (c.flags & 0x02) {
+                DT mc, mo; read_marker_dts(P, c, mc, mo, err); if (err) break;
+                if (purge_marker(pg, ck.kind, mc, mo)) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_marker(w, P, ck, mc, mo); }
+            } else {
+                Live info; DT del; Rd r = row_header(P, c, info, del);
+                for (int k = 0; k < P.ncols; k++) merged[k].present = false;
+                fold_cells(P, c, r, info, false, dt_live(), merged, err); if (r.err) err = r.err; if (err) break;
+                int present = purge_row(P, pg, info, del, merged);
+                if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
+            }
+            c.pos = c.next;
+        }
+    } else {
+        uint64_t has_open = 0; int biggest = -1;
+        for (uint32_t v = 0; v < m; v++) cur_load(P, cur[v], err);
+        while (!err) {
+            int b = -1;
+            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && (b < 0 || cmp_clust(P, cur[v], cur[b]) < 0)) b = (int)v;
+            if (b < 0) break;
+            uint64_t grp = 0; int gcount = 0, last = b;
+            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && ((int)v == b || cmp_clust(P, cur[v], cur[b]) == 0)) { grp |= 1ull << v; gcount++; last = (int)v; }
+            // current open deletion in the merged stream (RangeTombstoneMarker.Merger.currentOpenDeletionTimeInMerged :160-168)
+            DT cur_open = (biggest >= 0 && dt_supersedes(open_dt[biggest], pdel)) ? open_dt[biggest] : dt_live();
+            if (!(cur[b].flags & 0x02)) {
+                DT active = dt_is_live(cur_open) ? pdel : cur_open;          // activeDeletion() :191-197
+                Live info = live_empty(); DT del = dt_live();
+                for (int k = 0; k < P.ncols; k++) merged[k].present = false;
+                bool as_is = (gcount == 1) && dt_is_live(active);            // Row.Merger.merge :734-739
+                for (uint32_t v = 0; v < m; v++) if ((grp >> v) & 1) {
+                    Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) err = r.err;
+                    if (live_supersedes(vi, info)) info = vi;
+                    if (dt_supersedes(vd, del)) del = vd;
+                }
+                if (!as_is) {
+                    if (dt_supersedes(del, active)) active = del; else del = dt_live();
+                    if (dt_deletes(active, info.ts)) info = live_empty();
+                }
+                for (uint32_t v = 0; v < m && !err; v++) if ((grp >> v) & 1) {
+                    Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd);
+                    fold_cells(P, cur[v], r, vi, !as_is, active, merged, err); if (r.err) err = r.err;
+                }
+                if (err) break;
+                int npresent = 0; for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;
+                bool have = !(live_is_empty(info) && dt_is_live(del) && npresent == 0);
+                if (have) {
+                    st.merged_unfiltereds++;
+                    Cur& f = cur[b];
+                    CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, K_CLUSTERING, f.n};
+                    int present = purge_row(P, pg, info, del, merged);
+                    if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
+                }
+            } else {
+                // RangeTombstoneMarker.Merger.merge :94-153
+                for (uint32_t v = 0; v < m; v++) if ((grp >> v) & 1) {
+                    DT mc, mo; read_marker_dts(P, cur[v], mc, mo, err);
+                    bool is_open = kind_is_boundary(cur[v].kind) || kind_is_start(cur[v].kind);
+                    if (is_open) { open_dt[v] = mo; has_open |= 1ull << v; } else has_open &= ~(1ull << v);
+                }
+                biggest = -1;
+                for (uint32_t v = 0; v < m; v++) if (((has_open >> v) & 1) && (biggest < 0 || dt_supersedes(open_dt[v], open_dt[biggest]))) biggest = (int)v;
+                DT now_open = (biggest >= 0 && dt_supersedes(open_dt[biggest], pdel)) ? open_dt[biggest] : dt_live();
+                if (!dt_eq(cur_open, now_open) && !err) {
+                    st.merged_unfiltereds++;
+                    Cur& f = cur[last];                                       // `bound` = clustering of the last marker added (:99-103)
+                    bool before = kind_vs_clustering(f.kind) < 0;
+                    CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, 0, f.n};
+                    DT mc = dt_live(), mo = dt_live();
+                    if (dt_is_live(cur_open)) { ck.kind = before ? K_INCL_START : K_EXCL_START; mo = now_open; }
+                    else if (dt_is_live(now_open)) { ck.kind = before ? K_EXCL_END : K_INCL_END; mc = cur_open; }
+                    else { ck.kind = before ? K_EXCL_END_INCL_START : K_INCL_END_EXCL_START; mc = cur_open; mo = now_open; }
+                    if (purge_marker(pg, ck.kind, mc, mo)) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_marker(w, P, ck, mc, mo); }
+                }
+            }
+            for (uint32_t v = 0; v < m; v++) if ((grp >> v) & 1) { cur[v].pos = cur[v].next; cur_load(P, cur[v], err); }
+        }
+    }
+    if (err) return;
+    // partition.isEmpty() (UnfilteredRowIterator.java:63-68) / SortedTableWriter.append :134
+    if (!w.started && !dt_is_live(out_pdel)) pw_start(w, P, key_off, klen, out_pdel);
+    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen;
+    if (w.started) {
+        w.d.u8(0x01);                                                        // end of partition, then the trailing index block (finish() :217-243)
+        if (w.rows_out && w.have_first) pw_add_index_block(w, P);
+        out.dsize = w.d.pos; out.nblk = w.nblocks;
+        if (w.nblocks > 1) out.ipay = vint_size(w.header_len) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(w.nblocks) + (uint32_t)w.ix.pos + 4 * w.nblocks;
+        st.rows_out += w.rows_out;
+        if (EMIT) {                                                          // RowIndexEntry.serialize :468-473, IndexedEntry.serialize :625-642
+            Sink<true> e{iout, 0};
+            e.be16(klen); e.copy(P.U + key_off, klen); e.vint(dpos); e.vint(ipay_final);
+            if (nblocks_final > 1) { e.vint(w.header_len); write_partition_dt(e, out_pdel); e.vint(nblocks_final); }
+        }
+    }
+}
+
+} // namespace b200c

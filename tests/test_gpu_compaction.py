@@ -1,0 +1,172 @@
+"""GPU parity tests of b200c_compact through the C ABI: for the same manifest the CUDA engine must return the same Data.db,
+Index.db, chunk offsets, Digest.crc32 and counters as the CPU oracle (itself pinned by the reference's golden SSTables),
+and reproduce the golden `oa` files directly."""
+import os, random, struct, zlib, pytest
+import oracle_lib as O
+from sstable_builder import *
+from synth_util import synth_tables, decompress_output
+from cassandra_b200.io.sstable import SSTable
+from cassandra_b200.db.compaction import CompactionTask, CompactionController, GpuEngine
+
+pytestmark = pytest.mark.gpu
+NOW = 1700000000
+I32 = lambda v: struct.pack(">i", v)
+
+@pytest.fixture(scope="module")
+def ctx():
+    from cassandra_b200 import native
+    c = native.Context(0)
+    yield c
+    c.close()
+
+def both(ctx, tables, controller, **kw):
+    for g, t in enumerate(tables): t.generation = g
+    want = CompactionTask(tables, controller, **kw).execute(O.OracleEngine())
+    got = CompactionTask(tables, controller, **kw).execute(GpuEngine(ctx))
+    assert len(got.outputs) == len(want.outputs) == 1
+    g, w = got.outputs[0], want.outputs[0]
+    if g.data != w.data:                      # localise the first difference in the uncompressed stream for the report
+        a, b = decompress_output(g), decompress_output(w)
+        i = next((k for k in range(min(len(a), len(b))) if a[k] != b[k]), min(len(a), len(b)))
+        raise AssertionError("Data stream differs at %d (len %d vs %d): gpu %s | oracle %s" % (i, len(a), len(b), a[max(0, i - 24):i + 16].hex(), b[max(0, i - 24):i + 16].hex()))
+    assert g.index == w.index
+    assert g.compression.chunk_offsets == w.compression.chunk_offsets and g.compression.data_length == w.compression.data_length
+    assert g.digest == w.digest == zlib.crc32(g.data)
+    assert (g.partitions, g.rows) == (w.partitions, w.rows)
+    for k in ("bytes_read", "bytes_written", "total_source_rows", "input_partitions", "merged_row_counts"):
+        assert got.stats[k] == want.stats[k], k
+    assert got.stats["kernel_launches"] > 0
+    return got, want
+
+def _golden(golden_dir, name): return os.path.join(golden_dir, "oa", "legacy_tables", name, "oa-1-big-")
+
+@pytest.mark.parametrize("name", ["legacy_oa_simple", "legacy_oa_clust"])
+def test_golden_identity_compaction(ctx, golden_dir, name):
+    base = _golden(golden_dir, name)
+    got, _ = both(ctx, [SSTable.open(base)], CompactionController(NOW), column_index_size=4096)
+    comp = got.outputs[0].components()
+    for c in ("Data.db", "Index.db", "CompressionInfo.db", "Digest.crc32"):
+        assert comp[c] == open(base + c, "rb").read(), c
+
+def test_golden_self_merge(ctx, golden_dir):
+    base = _golden(golden_dir, "legacy_oa_clust")
+    got, _ = both(ctx, [SSTable.open(base, 1), SSTable.open(base, 2), SSTable.open(base, 3)], CompactionController(NOW), column_index_size=4096)
+    assert got.outputs[0].data == open(base + "Data.db", "rb").read()
+    assert got.stats["merged_row_counts"] == [0, 0, 5]
+
+@pytest.mark.parametrize("schema,n,universe,rpp,cis", [(0, 4, 20000, 0, 65536), (0, 16, 6000, 0, 65536), (1, 3, 60, 1000, 65536), (1, 4, 80, 300, 4096)])
+def test_synthetic_configs_match_oracle(ctx, schema, n, universe, rpp, cis):
+    tabs = synth_tables(schema, n, 0xCA550000 + schema + n, universe, rows_per_partition=rpp, column_index_size=cis)
+    got, want = both(ctx, tabs, CompactionController(NOW), column_index_size=cis)
+    assert want.stats["bytes_written"] < want.stats["bytes_read"]
+    # nothing purgeable / expired: a different code path through purge
+    both(ctx, tabs, CompactionController(0, 0), column_index_size=cis)
+    # overlapping-sstable rule blocks part of the purge
+    both(ctx, tabs, CompactionController(NOW, overlapping_min_timestamp=1600000000000000 + 1500000000), column_index_size=cis)
+
+def test_snappy_output_and_input(ctx):
+    tabs = synth_tables(0, 3, 11, 5000, comp=O.COMP_SNAPPY)
+    both(ctx, tabs, CompactionController(NOW))
+
+def test_sixty_four_inputs(ctx):
+    tabs = synth_tables(0, 64, 64, 3000, p=0.3)
+    got, _ = both(ctx, tabs, CompactionController(NOW))
+    assert sum(got.stats["merged_row_counts"][32:]) >= 0
+
+def test_random_range_tombstone_merges(ctx):
+    S1 = Schema(["Int32Type"], [("val", "UTF8Type")])
+    rng = random.Random(99); b = Builder(S1, (0, 0, 0))
+    for it in range(25):
+        parts_per_table = []
+        nsrc = rng.randint(1, 5)
+        for s in range(nsrc):
+            parts = []
+            for key in (b"p1", b"p2", b"p3", b"key-%d" % rng.randint(0, 3)):
+                if rng.random() < 0.3: continue
+                us = []; pos = 0; open_dt = None
+                while pos < 60:
+                    pos += rng.randint(1, 5); r = rng.random()
+                    if open_dt is None and r < 0.3:
+                        t = rng.randint(100, 200); us.append(Marker(rng.choice((K_INCL_START, K_EXCL_START)), (I32(pos),), None, (t, NOW - rng.randint(0, 2000000)))); open_dt = us[-1].open
+                    elif open_dt is not None and r < 0.35:
+                        if rng.random() < 0.3:
+                            t = (rng.randint(100, 200), NOW - rng.randint(0, 2000000))
+                            us.append(Marker(rng.choice((K_EXCL_END_INCL_START, K_INCL_END_EXCL_START)), (I32(pos),), open_dt, t)); open_dt = t
+                        else:
+                            us.append(Marker(rng.choice((K_INCL_END, K_EXCL_END)), (I32(pos),), open_dt, None)); open_dt = None
+                    else:
+                        kind = rng.random()
+                        ts = rng.randint(90, 210)
+                        if kind < 0.15: us.append(Row((I32(pos),), [], deletion=(ts, NOW - rng.randint(0, 2000000))))
+                        elif kind < 0.3: us.append(Row((I32(pos),), [Cell.tombstone(0, ts, NOW - rng.randint(0, 2000000))], ts=rng.randint(90, 210)))
+                        elif kind < 0.45: us.append(Row((I32(pos),), [Cell(0, ts, b"ttl", 3600, NOW + rng.randint(-5000, 5000))], ts=ts, ttl=3600, ldt=NOW + rng.randint(-5000, 5000)))
+                        else: us.append(Row((I32(pos),), [Cell(0, rng.randint(90, 210), rng.choice([b"", b"v", b"value-%d" % it]))], ts=ts if rng.random() < 0.8 else NO_TS))
+                if open_dt is not None: us.append(Marker(K_INCL_END, (I32(pos + 1),), open_dt, None))
+                pd = (rng.randint(100, 160), NOW - rng.randint(0, 2000000)) if rng.random() < 0.25 else None
+                if us or pd: parts.append(Partition(key, us, pd))
+            if not parts: parts = [Partition(b"p1", [Row((I32(1),), [Cell(0, 100, b"x")], ts=100)])]
+            uniq = {p.key: p for p in parts}
+            parts_per_table.append(b.build(list(uniq.values())))
+        both(ctx, parts_per_table, CompactionController(NOW, rng.choice([864000, 0, 10**9])))
+
+def test_mixed_types_variable_keys(ctx):
+    rng = random.Random(5)
+    s = Schema(["LongType", "UTF8Type"], [("a", "LongType"), ("b", "UTF8Type"), ("c", "Int32Type"), ("d", "DoubleType")])
+    tables = []
+    keys = [bytes(rng.getrandbits(8) for _ in range(rng.choice([1, 3, 8, 9, 17, 40]))) for _ in range(300)] + [b""]
+    for t in range(5):
+        parts = []
+        for k in keys:
+            if rng.random() < 0.5: continue
+            us = []
+            for ck in sorted({(rng.randint(-3, 3), rng.choice([b"", b"x", b"yy", b"zzzzzzzz" * 30])) for _ in range(rng.randint(1, 12))}):
+                cells = [Cell(ci, 1000 + rng.randint(0, 5), v) for ci, v in ((0, struct.pack(">q", rng.getrandbits(40))), (1, rng.choice([b"", b"hello", b"w" * 200])),
+                         (2, I32(rng.randint(-9, 9))), (3, struct.pack(">d", rng.random()))) if rng.random() < 0.7]
+                us.append(Row((struct.pack(">q", ck[0]), ck[1]), cells, ts=1000 + rng.randint(0, 5) if (rng.random() < 0.8 or not cells) else NO_TS))
+            parts.append(Partition(k, us, (1002, NOW) if rng.random() < 0.1 else None))
+        tables.append(Builder(s, (1000 - t, 0, 0), column_index_size=1024).build(parts))
+    both(ctx, tables, CompactionController(NOW, 10**9), column_index_size=1024)
+    both(ctx, tables[:1], CompactionController(NOW, 10**9), column_index_size=1024)
+
+def test_token_range_shards_partition_the_output(ctx):
+    tabs = synth_tables(0, 4, 21, 8000)
+    full, _ = both(ctx, tabs, CompactionController(NOW))
+    cuts = [-(1 << 63), -(1 << 62), 0, 1 << 61, (1 << 63) - 1]
+    parts = rows = 0; streams = b""
+    for lo, hi in zip(cuts, cuts[1:]):
+        g, _ = both(ctx, tabs, CompactionController(NOW), token_range=(lo, hi))
+        parts += g.outputs[0].partitions; rows += g.outputs[0].rows; streams += decompress_output(g.outputs[0])
+    assert (parts, rows) == (full.outputs[0].partitions, full.outputs[0].rows)
+    assert streams == decompress_output(full.outputs[0])          # partition records are position independent: shards concatenate exactly
+
+def test_corrupt_chunk_is_reported_with_its_input(ctx):
+    from cassandra_b200 import native
+    tabs = synth_tables(0, 3, 31, 4000)
+    bad = bytearray(tabs[1].data); bad[tabs[1].compression.chunk_offsets[2] + 9] ^= 0x10; tabs[1].data = bytes(bad)
+    with pytest.raises(native.CorruptSSTableError) as e:
+        CompactionTask(tabs, CompactionController(NOW)).execute(GpuEngine(ctx))
+    assert (e.value.corruption.input, e.value.corruption.kind, e.value.corruption.chunk) == (1, 1, 2)
+    with pytest.raises(native.CorruptSSTableError) as e2:
+        CompactionTask(tabs, CompactionController(NOW)).execute(O.OracleEngine())
+    assert (e2.value.corruption.input, e2.value.corruption.chunk) == (1, 2)
+
+def test_corrupt_index_is_rejected(ctx):
+    from cassandra_b200 import native
+    tabs = synth_tables(0, 2, 32, 3000)
+    bad = bytearray(tabs[0].index); bad[len(bad) // 2] ^= 0xFF; tabs[0].index = bytes(bad)
+    with pytest.raises(native.CorruptSSTableError):
+        CompactionTask(tabs, CompactionController(NOW)).execute(GpuEngine(ctx))
+
+def test_unsupported_is_refused_not_faked(ctx):
+    from cassandra_b200 import native
+    tabs = synth_tables(0, 2, 33, 1000)
+    with pytest.raises(native.UnsupportedError):
+        CompactionTask(tabs, CompactionController(NOW), max_sstable_bytes=1 << 20).execute(GpuEngine(ctx), max_outputs=4)
+
+def test_empty_result_and_tiny_inputs(ctx):
+    S1 = Schema(["Int32Type"], [("val", "UTF8Type")]); b = Builder(S1, (0, 0, 0))
+    t = b.build([Partition(b"k", [], (5, 7))])                      # only a purgeable partition deletion -> empty output
+    got, _ = both(ctx, [t], CompactionController(NOW))
+    assert got.outputs[0].data == b"" and got.outputs[0].index == b"" and got.outputs[0].partitions == 0
+    t2 = b.build([Partition(b"k", [Row((I32(1),), [Cell(0, 5, b"v")], ts=5)])])
+    both(ctx, [t2], CompactionController(NOW)); both(ctx, [t2, t], CompactionController(NOW))

@@ -465,6 +465,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     }
     c->prog_total.store(bytes_read); c->prog_scanned.store(0);
     timing_begin(c);
+    c->nstages = 0;
+    cudaEventRecord(c->ev_stage[0], st);
 
     // ---- K1: decompress + verify ------------------------------------------------------------------------------------------------
     c->prog_stage.store(1);
@@ -478,6 +480,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     auto check_cancel = [&]() -> int { if (c->cancel.load()) { c->err = "cancelled"; cudaStreamSynchronize(st); return B200C_ECANCELLED; } return B200C_OK; };
 
     // ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
+    cudaEventRecord(c->ev_stage[1], st);
     c->prog_stage.store(2);
     uint64_t *d_istart, *d_iend, *d_iscan; uint32_t *d_icnt, *d_ihit, *d_ibad;
     B200C_TRY(ws_typed(c, WS_ISTART, nblocks + 1, &d_istart));
@@ -551,6 +554,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range);
 
     // ---- K3: partition merge -------------------------------------------------------------------------------------------------------
+    cudaEventRecord(c->ev_stage[2], st);
     c->prog_stage.store(3);
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
@@ -585,6 +589,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     c->prog_scanned.store(bytes_read / 2);
 
     // ---- K4: row merge + serialise ---------------------------------------------------------------------------------------------------
+    cudaEventRecord(c->ev_stage[3], st);
     c->prog_stage.store(4);
     uint64_t *d_dsize, *d_dpos, *d_ipos; uint32_t *d_ipay, *d_nblk, *d_ihead, *d_isize;
     B200C_TRY(ws_typed(c, WS_DSIZE, nparts + 1, &d_dsize));
@@ -616,6 +621,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         ulen_out = h[0]; ilen_out = h[1];
     }
     B200C_TRY(check_cancel());
+    cudaEventRecord(c->ev_stage[4], st);
     uint8_t *UOUT, *IOUT;
     B200C_TRY(ws_typed(c, WS_UOUT, ulen_out + 64, &UOUT));
     B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
@@ -625,6 +631,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     c->prog_scanned.store(bytes_read * 3 / 4);
 
     // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------
+    cudaEventRecord(c->ev_stage[5], st);
     c->prog_stage.store(5);
     b200c_output& out = res->outputs[0];
     const uint64_t nchunks_out = (ulen_out + m->out_chunk_len - 1) / m->out_chunk_len;
@@ -641,8 +648,11 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(c->ev_stage[6], st);
     int trc = timing_end(c);
     if (trc != B200C_OK) return trc;
+    for (int k = 0; k < 6; k++) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_stage[k], c->ev_stage[k + 1]); c->stage_ms[k] = ms; }
+    c->nstages = 6;
     if (h[0] != ~0ull) { c->err = "internal error: size/emit pass disagreement at output partition " + std::to_string(h[0] & 0xFFFFFFFFFFFFull); return B200C_ECUDA; }
     RunStats rs; memcpy(&rs, h + 8, sizeof(rs));
     res->noutputs = 1;

@@ -108,6 +108,7 @@ b200c_ctx* b200c_create(int device, size_t workspace_bytes) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    for (auto& e : c->ev_stage) cudaEventCreate(&e);
     DevTables* h = new DevTables(); build_tables(h);
     if (cudaMalloc(&c->d_tables, sizeof(DevTables)) != cudaSuccess) { delete h; delete c; return nullptr; }
     cudaMemcpy(c->d_tables, h, sizeof(DevTables), cudaMemcpyHostToDevice);
@@ -128,6 +129,7 @@ void b200c_destroy(b200c_ctx* c) {
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    for (auto& e : c->ev_stage) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -158,6 +160,12 @@ int b200c_sync(b200c_ctx* c) { if (!c) return B200C_EINVAL; B200C_CUDA_TRY(c, cu
 double b200c_last_kernel_ms(b200c_ctx* c) { return c ? c->last_ms : 0.0; }
 uint64_t b200c_last_kernel_launches(b200c_ctx* c) { return c ? c->launches_call : 0; }
 uint64_t b200c_total_kernel_launches(b200c_ctx* c) { return c ? c->launches_total : 0; }
+int b200c_last_stage_ms(b200c_ctx* c, double* out, int n) {
+    if (!c || !out) return 0;
+    int k = c->nstages < n ? c->nstages : n;
+    for (int i = 0; i < k; i++) out[i] = c->stage_ms[i];
+    return k;
+}
 
 uint64_t b200c_chunk_count(uint64_t n, int chunk_len) { return chunk_len > 0 ? (n + chunk_len - 1) / chunk_len : 0; }
 uint64_t b200c_compress_bound(int comp, uint64_t n, int chunk_len) {

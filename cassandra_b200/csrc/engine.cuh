@@ -30,6 +30,9 @@ struct b200c_ctx {
     std::atomic<uint64_t> prog_scanned{0}, prog_total{0};
     std::atomic<int> prog_stage{0};
     bool timing = false;
+    cudaEvent_t ev_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nstages = 0;
 };
 
 namespace b200c {

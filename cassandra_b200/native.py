@@ -71,6 +71,7 @@ SYMBOLS = {
     "b200c_last_kernel_ms": (C.c_double, [_vp]),
     "b200c_last_kernel_launches": (_u64, [_vp]),
     "b200c_total_kernel_launches": (_u64, [_vp]),
+    "b200c_last_stage_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_int]),
     "b200c_compress_bound": (_u64, [_i, _u64, _i]),
     "b200c_chunk_count": (_u64, [_u64, _i]),
     "b200c_compress_chunks": (C.c_int, [_vp, _i, _u8p, _u64, _i, _i, _u8p, _u64, C.POINTER(_u64), _vp, C.POINTER(C.c_uint32), _i]),
@@ -138,6 +139,8 @@ class Context:
     def last_kernel_launches(self): return self._lib.b200c_last_kernel_launches(self._h)
     @property
     def total_kernel_launches(self): return self._lib.b200c_total_kernel_launches(self._h)
+    def last_stage_ms(self):
+        a = (C.c_double * 8)(); n = self._lib.b200c_last_stage_ms(self._h, a, 8); return [a[i] for i in range(n)]
 
     # ---- batched chunk codec -------------------------------------------------------------------------------------
     def compress_chunks(self, compressor, data, chunk_len=16384, max_compressed_len=INT32_MAX):

@@ -76,6 +76,9 @@ int          b200c_sync(b200c_ctx*);
 double       b200c_last_kernel_ms(b200c_ctx*);
 uint64_t     b200c_last_kernel_launches(b200c_ctx*);
 uint64_t     b200c_total_kernel_launches(b200c_ctx*);
+/* device time (ms) of the stages of the last b200c_compact: [0] K1 decompress+verify, [1] K2 index scan, [2] K3 partition merge,
+ * [3] K4 size pass, [4] K4 emit pass, [5] K5 compress+CRC+pack. Returns the number of entries written (<= n). */
+int          b200c_last_stage_ms(b200c_ctx*, double* out, int n);
 
 /* ---- chunk codec: the CompressedSequentialWriter / CompressedChunkReader data plane, batched ---------------------
  * b200c_compress_chunks: `in[0..n)` is an uncompressed Data stream. Chunk i = bytes [i*chunk_len, min((i+1)*chunk_len, n)).

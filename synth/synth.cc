@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <mutex>
 #include <map>
+#include <chrono>
+#include <cstdio>
 
 namespace {
 
@@ -112,8 +114,9 @@ struct Gen {
     struct CellSpec { bool present; int kind; /*0 live 1 tombstone 2 expiring*/ int64_t ts; int64_t ldt; int32_t ttl; const uint8_t* val; int vlen; bool fixed; };
 
     // serialises one row; returns bytes appended. prev = previous-unfiltered size
+    Buf scratch;
     void row(Buf& out, int64_t ck, int64_t row_ts, bool has_liveness, bool row_deleted, int64_t del_ldt, CellSpec* cells, int ncells, int ncols, uint64_t prev) {
-        Buf body;
+        Buf& body = scratch; body.b.clear();
         int flags = 0;
         if (has_liveness) flags |= 0x04;
         if (row_deleted) flags |= 0x10;
@@ -136,12 +139,13 @@ struct Gen {
         out.vint(body.size() + Buf::vsize(prev)); out.vint(prev); out.put(body.b.data(), body.size());
     }
     void marker(Buf& out, int kind, int64_t ck, int64_t mfda, int64_t ldt, uint64_t prev) {
-        Buf body; delta_dt(body, mfda, ldt);
+        Buf& body = scratch; body.b.clear(); delta_dt(body, mfda, ldt);
         out.u8(0x02); out.u8((uint8_t)kind); out.be16(1); clustering8(out, ck);
         out.vint(body.size() + Buf::vsize(prev)); out.vint(prev); out.put(body.b.data(), body.size());
     }
 
     struct Block { int fkind, lkind; int64_t fck, lck; uint64_t off, width; bool open; int64_t omf, oldt; };
+    std::vector<Block> blocks;
     void prefix(Buf& o, int kind, int64_t ck) { o.u8((uint8_t)kind); if (kind != 4) o.be16(1); clustering8(o, ck); }
 
     void partition(Slice& s, uint64_t key) {
@@ -156,7 +160,7 @@ struct Gen {
         int64_t pdel_ts = base_ts + (int64_t)(hps >> 20) % 500000000, pdel_ldt = NOW - 2 * GC_GRACE + (int64_t)((hps >> 8) % (2 * GC_GRACE));
         d.be16(8); d.put(kb, 8); part_dt(d, !pdel, pdel_ts, pdel_ldt);
         uint64_t header_len = d.size() - start, prev_start = 0;
-        std::vector<Block> blocks; bool have_first = false; Block cur{}; bool open = false; int64_t omf = 0, oldt = 0; uint64_t nunf = 0;
+        blocks.clear(); bool have_first = false; Block cur{}; bool open = false; int64_t omf = 0, oldt = 0; uint64_t nunf = 0;
         auto begin_unf = [&](int kind, int64_t ck) { uint64_t pos = d.size() - start; if (!have_first) { cur.fkind = kind; cur.fck = ck; cur.off = pos; have_first = true; } return pos; };
         auto end_unf = [&](int kind, int64_t ck, uint64_t pos) {
             prev_start = pos; cur.lkind = kind; cur.lck = ck; nunf++; s.rows++;
@@ -282,6 +286,7 @@ int synth_generate(const synth_config* cfg, synth_result* out) {
         for (int sl = t; sl < nslices; sl += T) {
             size_t lo = n * sl / nslices, hi = n * (sl + 1) / nslices;
             Slice& s = slices[sl];
+            s.data.b.reserve((size_t)((hi - lo) * c.p * (c.schema == 0 ? 70 : 80.0 * c.rows_per_partition)) + 4096);
             for (size_t i = lo; i < hi; i++) {
                 uint64_t key = u->keys[i].second;
                 if (c.band_count > 0 && c.sstable >= c.band_overlap_l0) {       // LCS L1: one token band per input
@@ -293,7 +298,9 @@ int synth_generate(const synth_config* cfg, synth_result* out) {
             }
         }
     };
+    auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
     uint64_t total = 0, parts = 0, rows = 0; for (auto& s : slices) { total += s.data.size(); parts += s.parts; rows += s.rows; }
     uint8_t* data = (uint8_t*)malloc(total + 64);
     if (!data) return -1;
@@ -308,6 +315,7 @@ int synth_generate(const synth_config* cfg, synth_result* out) {
     uint8_t* idx = (uint8_t*)malloc(index.size() + 64); if (!idx) { free(data); return -1; }
     memcpy(idx, index.b.data(), index.size());
     Gen g(c);
+    if (getenv("SYNTH_DEBUG")) fprintf(stderr, "synth: gen %.3fs, stitch+index %.3fs\n", std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     out->data = data; out->data_len = total; out->index = idx; out->index_len = index.size(); out->partitions = parts; out->rows = rows;
     out->min_timestamp = g.min_ts; out->min_local_deletion_time = g.min_ldt; out->min_ttl = g.min_ttl; out->_pad = 0;
     return 0;

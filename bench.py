@@ -208,7 +208,7 @@ def run_b200(args):
             "merged_row_counts": [int(x) for x in last.merged_row_counts[:nsst]],
             "bytes": {"u_in": u_in, "c_in": c_in, "index_in": i_in, "u_out": u_out, "c_out": c_out, "index_out": i_out},
             "e2e": {"value": round(e2e, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(edt / e_steps * 1e3, 2)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+            "gpu_launches": int(launches), "index_slow_path_inputs": int(last.index_slow_path_inputs), "clocks": clocks, "roofline": roof}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(1, args.cpu_sample_mib, 1)
     if rank == 0:

@@ -15,6 +15,7 @@
 #include "scan.cuh"
 #include "codec_defs.cuh"
 #include "partition.cuh"
+#include "partition_tile.cuh"
 #include <climits>
 #include <vector>
 #include <algorithm>
@@ -88,7 +89,9 @@ __device__ uint64_t idx_entry(const CParams& P, const uint8_t* __restrict__ IDX,
     if (ps > 0x7FFFFFFFull || p + ps > in.ilen) return 0;
     if (pos >= in.ulen || pos + 2 + kl + 2 > in.ulen) return 0;
     if (check_data) {
+        // a partition starts right after the previous partition's end-of-partition flag and repeats u16 keyLen | key
         const uint8_t* d = P.U + in.ubase + pos;
+        if (pos > 0 && d[-1] != 0x01) return 0;
         for (uint32_t k = 0; k < 2 + kl; k++) if (d[k] != b[o + k]) return 0;
     }
     *dpos_out = pos; *klen_out = kl;
@@ -106,9 +109,23 @@ __global__ void __launch_bounds__(256) k_index_find(const CParams* __restrict__ 
     const CParams& P = *Pp;
     int i = input_of_block(bbase, P.ninputs, b);
     uint64_t lb = b - bbase[i], lo = lb * IB, hi = min(lo + IB, P.in[i].ilen);
-    uint64_t dpos; uint32_t kl; uint64_t found = NONE64;
-    if (lb == 0) { if (idx_entry(P, IDX, i, 0, true, &dpos, &kl)) found = 0; }
-    else for (uint64_t o = lo; o < hi; o++) if (idx_entry(P, IDX, i, o, true, &dpos, &kl)) { found = o; break; }
+    // a speculated start must open a chain of 3 entries that all match Data.db with strictly increasing positions (or run into
+    // EOF): single-entry matches are too weak (keyLen 0 / 1 candidates inside key or value bytes do occur at GB scale)
+    auto chain3 = [&](uint64_t o) -> bool {
+        uint64_t prev = 0;
+        for (int k = 0; k < 3; k++) {
+            uint64_t dpos; uint32_t kl;
+            uint64_t len = idx_entry(P, IDX, i, o, true, &dpos, &kl);
+            if (!len) return false;
+            if (k && dpos <= prev) return false;
+            prev = dpos; o += len;
+            if (o == P.in[i].ilen) return true;
+        }
+        return true;
+    };
+    uint64_t found = NONE64;
+    if (lb == 0) { if (chain3(0)) found = 0; }
+    else for (uint64_t o = lo; o < hi; o++) if (chain3(o)) { found = o; break; }
     start[b] = found;
 }
 
@@ -392,6 +409,60 @@ __global__ void __launch_bounds__(128) k_partition_emit(const CParams* __restric
     if (e || out.dsize != dsize[j]) report_err(err, 8, 0, j);
 }
 
+// ---- K4, cooperative version: a tile of G lanes per output partition (partition_tile.cuh). mlo < m <= mhi selects the class ----------
+template <int G, int S>
+__global__ void __launch_bounds__(128) k_partition_size_tile(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint32_t mlo, uint32_t mhi,
+        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
+        RunStats* __restrict__ stats, DevErr* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ unsigned long long s_stat[3];
+    if (threadIdx.x < 3) s_stat[threadIdx.x] = 0;
+    __syncthreads();
+    auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int tid = threadIdx.x / G;
+    MCell* s_cells = (MCell*)s_raw + (size_t)tid * Pp->ncols;
+    uint64_t j = (uint64_t)blockIdx.x * (128 / G) + tid;
+    uint32_t m = 0; uint64_t c0 = 0;
+    if (j < nparts) { c0 = op_first[j]; m = (uint32_t)(op_first[j + 1] - c0); }
+    if (m > mlo && m <= mhi) {
+        PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+        process_partition_tile<G, S, false>(tile, *Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, s_cells, out, st, e);
+        if (tile.thread_rank() == 0) {
+            if (e) { uint64_t en = contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, src, upos[pbase[src] + (en & 0xFFFFFFFFFFull)] - Pp->in[src].ubase); out = PartOut{0, 0, 0, 0}; }
+            dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
+            if (st.merged_unfiltereds) atomicAdd(&s_stat[0], (unsigned long long)st.merged_unfiltereds);
+            if (st.rows_out) atomicAdd(&s_stat[1], (unsigned long long)st.rows_out);
+            if (out.dsize) atomicAdd(&s_stat[2], 1ull);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_stat[0]) atomicAdd(&stats->merged_unfiltereds, s_stat[0]);
+        if (s_stat[1]) atomicAdd(&stats->rows_out, s_stat[1]);
+        if (s_stat[2]) atomicAdd(&stats->partitions_out, s_stat[2]);
+    }
+}
+
+template <int G, int S>
+__global__ void __launch_bounds__(128) k_partition_emit_tile(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint32_t mlo, uint32_t mhi,
+        const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos, const uint32_t* __restrict__ ipay, const uint32_t* __restrict__ nblk,
+        const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int tid = threadIdx.x / G;
+    MCell* s_cells = (MCell*)s_raw + (size_t)tid * Pp->ncols;
+    uint64_t j = (uint64_t)blockIdx.x * (128 / G) + tid;
+    uint32_t m = 0; uint64_t c0 = 0;
+    if (j < nparts && dsize[j]) { c0 = op_first[j]; m = (uint32_t)(op_first[j + 1] - c0); }
+    if (m > mlo && m <= mhi) {
+        PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+        process_partition_tile<G, S, true>(tile, *Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], s_cells, out, st, e);
+        if (tile.thread_rank() == 0 && (e || out.dsize != dsize[j])) report_err(err, 8, 0, j);
+    }
+}
+
 } // namespace b200c
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -429,7 +500,10 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         d.ubase = ubase[i]; d.ulen = in.data_length; d.ibase = ibase[i]; d.ilen = in.index_len;
         d.min_ts = in.header_stats.min_timestamp; d.min_ldt = in.header_stats.min_local_deletion_time; d.min_ttl = in.header_stats.min_ttl;
         d.ncols = in.ncolumns;
-        for (int k = 0; k < in.ncolumns; k++) { if (in.column_map[k] < 0 || in.column_map[k] >= m->ncolumns) { c->err = "column_map"; return B200C_EINVAL; } d.colmap[k] = in.column_map[k]; }
+        for (int k = 0; k < in.ncolumns; k++) {
+            if (in.column_map[k] < 0 || in.column_map[k] >= m->ncolumns || (k && in.column_map[k] <= in.column_map[k - 1])) { c->err = "column_map must be strictly increasing (both headers are name ordered)"; return B200C_EINVAL; }
+            d.colmap[k] = in.column_map[k];
+        }
     }
     ubase[K] = uo; ibase[K] = io; cbase[K] = co; obase[K] = oo; bbase[K] = bo;
     const uint64_t nblocks = bo;
@@ -508,7 +582,10 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         for (int i = 0; i <= K; i++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8 + i, d_iscan + bbase[i], 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cerr, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_err, 8, cudaMemcpyDeviceToHost, st));
+        if (nblocks) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 300, d_ibad, (K + 1) * 4, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        res->index_slow_path_inputs = 0;
+        if (nblocks) for (int i = 0; i < K; i++) res->index_slow_path_inputs += ((uint32_t*)(h + 300))[i] ? 1 : 0;
         if (h[0] != ~0ull) {
             // the decompress kernels share one error word; re-run attribution on the host side: find the input owning the failing launch
             uint64_t chunk = h[0] >> 8; int kindc = (int)(h[0] & 0xff);
@@ -600,9 +677,17 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_IHEAD, nparts + 1, &d_ihead));
     B200C_TRY(ws_typed(c, WS_ISIZE, nparts + 1, &d_isize));
     uint64_t ulen_out = 0, ilen_out = 0;
+    static const bool k4_thread = getenv("B200C_K4_THREAD") != nullptr;      // A/B switch: the first-generation thread-per-partition kernels
+    const size_t cell_smem8 = (size_t)16 * m->ncolumns * sizeof(MCell), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
     if (nparts) {
         unsigned g = (unsigned)((nparts + 127) / 128);
+        if (k4_thread) {
         B200C_LAUNCH(c, k_partition_size, g, 128, 0, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
+        } else {
+            B200C_LAUNCH(c, (k_partition_size_tile<8, 1>), (unsigned)((nparts + 15) / 16), 128, cell_smem8, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 0u, 8u, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
+            if (K > 8) B200C_LAUNCH(c, (k_partition_size_tile<32, 1>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 8u, 32u, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
+            if (K > 32) B200C_LAUNCH(c, (k_partition_size_tile<32, 2>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 32u, 64u, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
+        }
         B200C_TRY(exclusive_scan<uint64_t>(c, d_dsize, nparts, d_dpos, WS_SCANA, 0));
         B200C_LAUNCH(c, k_index_sizes, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_dsize, d_dpos, d_ipay, d_ihead, d_isize);
         B200C_TRY(exclusive_scan<uint32_t>(c, d_isize, nparts, d_ipos, WS_SCANA + 3, 0));
@@ -625,9 +710,16 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     uint8_t *UOUT, *IOUT;
     B200C_TRY(ws_typed(c, WS_UOUT, ulen_out + 64, &UOUT));
     B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
-    if (nparts && ulen_out)
+    if (nparts && ulen_out) {
+        if (k4_thread) {
         B200C_LAUNCH(c, k_partition_emit, (unsigned)((nparts + 127) / 128), 128, 0, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_dsize, d_dpos, d_ipay, d_nblk,
                      d_ipos, UOUT, IOUT, d_err);
+        } else {
+            B200C_LAUNCH(c, (k_partition_emit_tile<8, 1>), (unsigned)((nparts + 15) / 16), 128, cell_smem8, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 0u, 8u, d_dsize, d_dpos, d_ipay, d_nblk, d_ipos, UOUT, IOUT, d_err);
+            if (K > 8) B200C_LAUNCH(c, (k_partition_emit_tile<32, 1>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 8u, 32u, d_dsize, d_dpos, d_ipay, d_nblk, d_ipos, UOUT, IOUT, d_err);
+            if (K > 32) B200C_LAUNCH(c, (k_partition_emit_tile<32, 2>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 32u, 64u, d_dsize, d_dpos, d_ipay, d_nblk, d_ipos, UOUT, IOUT, d_err);
+        }
+    }
     c->prog_scanned.store(bytes_read * 3 / 4);
 
     // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------

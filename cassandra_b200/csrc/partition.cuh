@@ -91,14 +91,14 @@ struct Rd {
 
 // ---- sinks ----------------------------------------------------------------------------------------------------------------
 template <bool EMIT> struct Sink {
-    uint8_t* base; uint64_t pos;
-    __device__ __forceinline__ void u8(uint32_t v) { if (EMIT) base[pos] = (uint8_t)v; pos++; }
+    uint8_t* base; uint64_t pos; bool on;      // on: this lane performs the stores (tile mode: lane 0 only; every lane tracks pos)
+    __device__ __forceinline__ void u8(uint32_t v) { if (EMIT && on) base[pos] = (uint8_t)v; pos++; }
     __device__ __forceinline__ void be16(uint32_t v) { u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be64(uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); }
     __device__ __forceinline__ void vint(uint64_t v) {
         int size = vint_size(v);
-        if (EMIT) {
+        if (EMIT && on) {
             if (size == 1) base[pos] = (uint8_t)v;
             else if (size < 9) {
                 uint64_t reg = (v << ((8 - size) << 3)) | ((uint64_t)(uint8_t)(~(0xffu >> (size - 1))) << 56);
@@ -107,7 +107,7 @@ template <bool EMIT> struct Sink {
         }
         pos += size;
     }
-    __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
+    __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
 };
 
 struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialised clustering values (header vint + values) in U
@@ -264,7 +264,7 @@ template <bool EMIT> __device__ __forceinline__ void write_prefix(Sink<EMIT>& s,
 template <bool EMIT> __device__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
     uint64_t cur = w.d.pos - w.start;
     bool emit_info = EMIT && w.nblocks_final > 1;
-    if (emit_info) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
+    if (emit_info && w.d.on) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
     if (!EMIT || emit_info) {
         write_prefix(w.ix, P, w.first); write_prefix(w.ix, P, w.last);
         w.ix.vint(w.block_start);
@@ -386,7 +386,7 @@ template <bool EMIT> __device__ void write_row(PWriter<EMIT>& w, const CParams& 
     if (present == P.ncols) flags |= 0x20;
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
-    Sink<false> cs{nullptr, 0};
+    Sink<false> cs{nullptr, 0, false};
     put_row_body(cs, P, flags, info, del, cells, present);
     w.d.u8(flags); w.d.copy(P.U + ck.off, ck.len);
     w.d.vint(cs.pos + vint_size(prev)); w.d.vint(prev);
@@ -398,7 +398,7 @@ template <bool EMIT> __device__ void write_row(PWriter<EMIT>& w, const CParams& 
 template <bool EMIT> __device__ void write_marker(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const DT& m_close, const DT& m_open) {
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
-    Sink<false> cs{nullptr, 0};
+    Sink<false> cs{nullptr, 0, false};
     bool boundary = kind_is_boundary(ck.kind), start = kind_is_start(ck.kind);
     if (boundary) { write_delta_dt(cs, P, m_close); write_delta_dt(cs, P, m_open); } else write_delta_dt(cs, P, start ? m_open : m_close);
     w.d.u8(0x02); w.d.u8(ck.kind); w.d.be16(ck.n); w.d.copy(P.U + ck.off, ck.len);
@@ -460,7 +460,7 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;                 // PurgeFunction.applyToDeletion :95-99
 
     PWriter<EMIT> w;
-    w.d.base = dout; w.d.pos = 0; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
+    w.d.base = dout; w.d.pos = 0; w.d.on = true; w.ix.on = true; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
     w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
     // index entry layout (EMIT): [u16 kl][key][vint dpos][vint ipay]{[vint headerLen][DT][vint nblocks][IndexInfo..][i32 offsets..]}
@@ -565,7 +565,7 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         if (w.nblocks > 1) out.ipay = vint_size(w.header_len) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(w.nblocks) + (uint32_t)w.ix.pos + 4 * w.nblocks;
         st.rows_out += w.rows_out;
         if (EMIT) {                                                          // RowIndexEntry.serialize :468-473, IndexedEntry.serialize :625-642
-            Sink<true> e{iout, 0};
+            Sink<true> e{iout, 0, true};
             e.be16(klen); e.copy(P.U + key_off, klen); e.vint(dpos); e.vint(ipay_final);
             if (nblocks_final > 1) { e.vint(w.header_len); write_partition_dt(e, out_pdel); e.vint(nblocks_final); }
         }

@@ -128,7 +128,7 @@ class CompactionTask:
             r.outputs.append(OutputSSTable(d[:o.data_len].tobytes(), ix[:o.index_len].tobytes(), meta, int(o.digest), int(o.partitions), int(o.rows)))
         r.stats = dict(bytes_read=int(res.bytes_read), bytes_written=int(res.bytes_written), total_source_rows=int(res.total_source_rows),
                        input_partitions=int(res.input_partitions), merged_row_counts=[int(x) for x in res.merged_row_counts[:len(self.inputs)]],
-                       kernel_ms=res.kernel_ms, total_ms=res.total_ms, kernel_launches=int(res.kernel_launches), wall_s=wall)
+                       kernel_ms=res.kernel_ms, total_ms=res.total_ms, kernel_launches=int(res.kernel_launches), index_slow_path_inputs=int(res.index_slow_path_inputs), wall_s=wall)
         return r
 
 class GpuEngine:

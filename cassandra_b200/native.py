@@ -49,7 +49,8 @@ class Result(C.Structure):
                 ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64), ("total_source_rows", C.c_uint64),
                 ("input_partitions", C.c_uint64), ("merged_row_counts", C.c_uint64 * MAX_INPUTS),
                 ("required_data_cap", C.c_uint64), ("required_index_cap", C.c_uint64), ("required_chunk_cap", C.c_uint64),
-                ("corruption", Corruption), ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+                ("corruption", Corruption), ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_uint64),
+                ("index_slow_path_inputs", C.c_uint64)]
 class Progress(C.Structure):
     _fields_ = [("bytes_scanned", C.c_uint64), ("bytes_total", C.c_uint64), ("stage", C.c_int32), ("_pad", C.c_int32)]
 

@@ -206,6 +206,7 @@ typedef struct b200c_result {
     double    kernel_ms;                /* device time of all kernels of this call */
     double    total_ms;                 /* host wall time of the call incl. copies */
     uint64_t  kernel_launches;
+    uint64_t  index_slow_path_inputs;   /* inputs whose Index.db speculation could not be proven and were walked sequentially on the GPU */
 } b200c_result;
 
 /* flags: bit0 = input/outputs buffers are DEVICE pointers (inputs resident in HBM; used for the kernel-only metric) */

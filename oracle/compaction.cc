@@ -699,7 +699,7 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
         out.data_length = o.ulen; out.digest = o.digest; out.partitions = o.parts; out.rows = o.rows;
     }
     res->bytes_written = bw;
-    res->kernel_ms = 0; res->kernel_launches = 0;
+    res->kernel_ms = 0; res->kernel_launches = 0; res->index_slow_path_inputs = 0;
     res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
 }

@@ -36,6 +36,7 @@ def both(ctx, tables, controller, **kw):
     for k in ("bytes_read", "bytes_written", "total_source_rows", "input_partitions", "merged_row_counts"):
         assert got.stats[k] == want.stats[k], k
     assert got.stats["kernel_launches"] > 0
+    assert got.stats["index_slow_path_inputs"] == 0, "Index.db speculation fell back to the sequential walk"
     return got, want
 
 def _golden(golden_dir, name): return os.path.join(golden_dir, "oa", "legacy_tables", name, "oa-1-big-")

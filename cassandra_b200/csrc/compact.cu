@@ -91,6 +91,7 @@ __device__ uint64_t idx_entry(const CParams& P, const uint8_t* __restrict__ IDX,
     if (check_data) {
         // a partition starts right after the previous partition's end-of-partition flag and repeats u16 keyLen | key
         const uint8_t* d = P.U + in.ubase + pos;
+        if ((pos == 0) != (o == 0)) return 0;        // positions increase strictly with the entry offset: only the first entry sits at 0
         if (pos > 0 && d[-1] != 0x01) return 0;
         for (uint32_t k = 0; k < 2 + kl; k++) if (d[k] != b[o + k]) return 0;
     }

@@ -7,7 +7,8 @@
 //   K3  k_bucket_bounds + k_merge_buckets   the partition-level MergeIterator (S/utils/MergeIterator.java:154-219): token space is
 //                                cut into buckets, one warp per bucket runs a tournament over its <= 64 sources (one or two
 //                                per lane, warp-min by shuffles); equal keys reduce together in source order
-//   K4  k_partition_size/emit    row merge + reconcile + purge + big-format serialisation, size -> scan -> emit   [partition.cuh]
+//   K4  k_partition_thr/warp     row merge + reconcile + purge + big-format serialisation, size -> scan -> emit, output partitions
+//                                counting-sorted by fan-in; cursors in shared memory (fan-in <= 16) or one warp each  [partition*.cuh]
 //   K5  k_compress_chunks ...    CompressedSequentialWriter + ChecksumWriter                    [codec.cuh]
 //
 // No CPU fallback; every error is reported through the return code (B200C_ECORRUPT carries the location).
@@ -34,7 +35,7 @@ enum { IB = 256 };                       // Index.db speculation block
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -368,26 +369,83 @@ __global__ void __launch_bounds__(256) k_op_first(const uint32_t* __restrict__ h
 }
 
 // ---- K4 wrappers -----------------------------------------------------------------------------------------------------------------
+// Output partitions are processed in fan-in order (`list` = counting sort of the partitions by m, so a warp's threads run the same
+// number of cursors). Per-partition results go to arrays indexed by the partition number j; totals come from k_sum_stats.
 struct RunStats { unsigned long long merged_unfiltereds, rows_out, partitions_out; };
 
-__global__ void __launch_bounds__(128) k_partition_size(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
-        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
-        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
-        RunStats* __restrict__ stats, DevErr* __restrict__ err) {
+// warp-aggregated counting-sort scatter: list[cursor[m]++] = j
+__global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restrict__ op_first, uint64_t nparts, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    PartStats st{0, 0}; unsigned long long wrote = 0;
-    if (j < nparts) {
-        uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
-        PartOut out{0, 0, 0, 0}; int e = 0;
-        process_partition<false>(*Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, out, st, e);
-        if (e) { uint64_t en = contrib[c0]; report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, (int)((en >> 56) & 0x7F), upos[pbase[(en >> 56) & 0x7F] + (en & 0xFFFFFFFFFFull)] - Pp->in[(en >> 56) & 0x7F].ubase); out = PartOut{0, 0, 0, 0}; }
-        dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
-        wrote = out.dsize ? 1 : 0;
-    }
-    unsigned long long a = st.merged_unfiltereds, r = st.rows_out;
+    bool valid = j < nparts;
+    uint32_t m = valid ? (uint32_t)(op_first[j + 1] - op_first[j]) : 0xFFFFFFFFu;
+    uint32_t peers = __match_any_sync(FULL_MASK, m);
+    int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (valid && lane == leader) base = atomicAdd(&cursor[m], (unsigned long long)__popc(peers));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    if (valid) list[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)j;
+}
+
+enum { SLOT_BYTES = sizeof(Cur) };          // per-source cursor in shared memory
+
+template <int M_CAP, int NT, bool EMIT>
+__global__ void __launch_bounds__(NT) k_partition_thr(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        const uint32_t* __restrict__ list, uint64_t lo, uint64_t hi, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
+        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
+        uint32_t* __restrict__ st_munf, uint32_t* __restrict__ st_rows,
+        const uint64_t* __restrict__ dpos, const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    constexpr int STRIDE = M_CAP * SLOT_BYTES + 8;       // +8: spread the threads over the banks
+    Cur* cur = (Cur*)(s_raw + (size_t)threadIdx.x * STRIDE);
+    MCell merged[MAXCOLS];
+    DT open_dt[M_CAP];                                   // only touched when the partition holds range tombstone markers
+    uint64_t t = lo + (uint64_t)blockIdx.x * NT + threadIdx.x;
+    if (t >= hi) return;
+    uint64_t j = list[t];
+    if (EMIT && !dsize[j]) return;
+    uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
+    PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+    if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
+    else if (EMIT) process_partition<true>(*Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], cur, open_dt, merged, out, st, e);
+    else process_partition<false>(*Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, cur, open_dt, merged, out, st, e);
+    if (EMIT) { if (e || out.dsize != dsize[j]) report_err(err, 8, 0, j); return; }
+    if (e) { uint64_t en = contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, src, upos[pbase[src] + (en & 0xFFFFFFFFFFull)] - Pp->in[src].ubase); out = PartOut{0, 0, 0, 0}; st = PartStats{0, 0}; }
+    dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
+    st_munf[j] = (uint32_t)st.merged_unfiltereds; st_rows[j] = (uint32_t)st.rows_out;
+}
+
+// fan-in above 16: a whole warp per partition, cursors in registers (partition_tile.cuh)
+template <int S, bool EMIT>
+__global__ void __launch_bounds__(128) k_partition_warp(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        const uint32_t* __restrict__ list, uint64_t lo, uint64_t hi, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
+        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
+        uint32_t* __restrict__ st_munf, uint32_t* __restrict__ st_rows,
+        const uint64_t* __restrict__ dpos, const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    auto tile = cg::tiled_partition<32>(cg::this_thread_block());
+    const int tid = threadIdx.x / 32;
+    MCell* s_cells = (MCell*)s_raw + (size_t)tid * Pp->ncols;
+    uint64_t t = lo + (uint64_t)blockIdx.x * 4 + tid;
+    if (t >= hi) return;
+    uint64_t j = list[t];
+    if (EMIT && !dsize[j]) return;
+    uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
+    PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+    if (EMIT) process_partition_tile<32, S, true>(tile, *Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], s_cells, out, st, e);
+    else process_partition_tile<32, S, false>(tile, *Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, s_cells, out, st, e);
+    if (tile.thread_rank() != 0) return;
+    if (EMIT) { if (e || out.dsize != dsize[j]) report_err(err, 8, 0, j); return; }
+    if (e) { uint64_t en = contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, src, upos[pbase[src] + (en & 0xFFFFFFFFFFull)] - Pp->in[src].ubase); out = PartOut{0, 0, 0, 0}; st = PartStats{0, 0}; }
+    dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
+    st_munf[j] = (uint32_t)st.merged_unfiltereds; st_rows[j] = (uint32_t)st.rows_out;
+}
+
+__global__ void __launch_bounds__(256) k_sum_stats(uint64_t nparts, const uint64_t* __restrict__ dsize, const uint32_t* __restrict__ st_munf, const uint32_t* __restrict__ st_rows, RunStats* __restrict__ stats) {
+    unsigned long long a = 0, r = 0, w = 0;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nparts; j += (uint64_t)gridDim.x * blockDim.x) { a += st_munf[j]; r += st_rows[j]; w += dsize[j] ? 1 : 0; }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) { a += __shfl_xor_sync(FULL_MASK, a, d); r += __shfl_xor_sync(FULL_MASK, r, d); wrote += __shfl_xor_sync(FULL_MASK, wrote, d); }
-    if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(&stats->merged_unfiltereds, a); if (r) atomicAdd(&stats->rows_out, r); if (wrote) atomicAdd(&stats->partitions_out, wrote); }
+    for (int d = 16; d; d >>= 1) { a += __shfl_xor_sync(FULL_MASK, a, d); r += __shfl_xor_sync(FULL_MASK, r, d); w += __shfl_xor_sync(FULL_MASK, w, d); }
+    if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(&stats->merged_unfiltereds, a); if (r) atomicAdd(&stats->rows_out, r); if (w) atomicAdd(&stats->partitions_out, w); }
 }
 
 // Index.db entry size once the data position is known: u16 keyLen | key | vint position | vint32 payload size | payload
@@ -396,72 +454,6 @@ __global__ void __launch_bounds__(256) k_index_sizes(uint64_t nparts, const uint
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nparts) return;
     isize[j] = dsize[j] ? ihead[j] + vint_size(dpos[j]) + vint_size(ipay[j]) + ipay[j] : 0;
-}
-
-__global__ void __launch_bounds__(128) k_partition_emit(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
-        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
-        const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos, const uint32_t* __restrict__ ipay, const uint32_t* __restrict__ nblk,
-        const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
-    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nparts || !dsize[j]) return;
-    uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
-    PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-    process_partition<true>(*Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], out, st, e);
-    if (e || out.dsize != dsize[j]) report_err(err, 8, 0, j);
-}
-
-// ---- K4, cooperative version: a tile of G lanes per output partition (partition_tile.cuh). mlo < m <= mhi selects the class ----------
-template <int G, int S>
-__global__ void __launch_bounds__(128) k_partition_size_tile(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
-        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint32_t mlo, uint32_t mhi,
-        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
-        RunStats* __restrict__ stats, DevErr* __restrict__ err) {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    __shared__ unsigned long long s_stat[3];
-    if (threadIdx.x < 3) s_stat[threadIdx.x] = 0;
-    __syncthreads();
-    auto tile = cg::tiled_partition<G>(cg::this_thread_block());
-    const int tid = threadIdx.x / G;
-    MCell* s_cells = (MCell*)s_raw + (size_t)tid * Pp->ncols;
-    uint64_t j = (uint64_t)blockIdx.x * (128 / G) + tid;
-    uint32_t m = 0; uint64_t c0 = 0;
-    if (j < nparts) { c0 = op_first[j]; m = (uint32_t)(op_first[j + 1] - c0); }
-    if (m > mlo && m <= mhi) {
-        PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-        process_partition_tile<G, S, false>(tile, *Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, s_cells, out, st, e);
-        if (tile.thread_rank() == 0) {
-            if (e) { uint64_t en = contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, src, upos[pbase[src] + (en & 0xFFFFFFFFFFull)] - Pp->in[src].ubase); out = PartOut{0, 0, 0, 0}; }
-            dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
-            if (st.merged_unfiltereds) atomicAdd(&s_stat[0], (unsigned long long)st.merged_unfiltereds);
-            if (st.rows_out) atomicAdd(&s_stat[1], (unsigned long long)st.rows_out);
-            if (out.dsize) atomicAdd(&s_stat[2], 1ull);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_stat[0]) atomicAdd(&stats->merged_unfiltereds, s_stat[0]);
-        if (s_stat[1]) atomicAdd(&stats->rows_out, s_stat[1]);
-        if (s_stat[2]) atomicAdd(&stats->partitions_out, s_stat[2]);
-    }
-}
-
-template <int G, int S>
-__global__ void __launch_bounds__(128) k_partition_emit_tile(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
-        uint64_t nparts, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint32_t mlo, uint32_t mhi,
-        const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos, const uint32_t* __restrict__ ipay, const uint32_t* __restrict__ nblk,
-        const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    auto tile = cg::tiled_partition<G>(cg::this_thread_block());
-    const int tid = threadIdx.x / G;
-    MCell* s_cells = (MCell*)s_raw + (size_t)tid * Pp->ncols;
-    uint64_t j = (uint64_t)blockIdx.x * (128 / G) + tid;
-    uint32_t m = 0; uint64_t c0 = 0;
-    if (j < nparts && dsize[j]) { c0 = op_first[j]; m = (uint32_t)(op_first[j + 1] - c0); }
-    if (m > mlo && m <= mhi) {
-        PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-        process_partition_tile<G, S, true>(tile, *Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], s_cells, out, st, e);
-        if (tile.thread_rank() == 0 && (e || out.dsize != dsize[j])) report_err(err, 8, 0, j);
-    }
 }
 
 } // namespace b200c
@@ -658,11 +650,24 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_LAUNCH(c, k_merge_buckets, (unsigned)((nbuckets + 3) / 4), 128, 0, dP, d_pbase, d_range, d_tok, d_kp, d_klen, d_upos, d_bstart, nbuckets, d_contrib, d_head, d_hist);
         B200C_TRY(exclusive_scan<uint32_t>(c, d_head, ncontrib, d_opidx, WS_SCANA, 0));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_opidx + ncontrib, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
         nparts = h[0];
     }
+    if (nparts >= (1ull << 32)) { c->err = "too many output partitions"; return B200C_EUNSUPPORTED; }
+    // counting sort of the output partitions by fan-in m (histogram = mergedRowCounts, already built by the merge kernel)
+    uint64_t fan_base[MAXK + 2]; fan_base[0] = fan_base[1] = 0;
+    for (int k = 1; k <= MAXK; k++) fan_base[k + 1] = fan_base[k] + (ncontrib ? h[16 + k - 1] : 0);      // fan_base[m] = first list slot of fan-in m
+    const uint64_t n_le8 = fan_base[9], n_le16 = fan_base[17], n_le32 = fan_base[33];
     B200C_TRY(ws_typed(c, WS_OPFIRST, nparts + 2, &d_opfirst));
-    if (ncontrib) B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
+    uint32_t* d_list; unsigned long long* d_cursor;
+    B200C_TRY(ws_typed(c, WS_LIST, nparts + 1, &d_list));
+    B200C_TRY(ws_typed(c, WS_CURSOR, (size_t)MAXK + 2, &d_cursor));
+    if (ncontrib) {
+        B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_cursor, fan_base, (MAXK + 2) * 8, cudaMemcpyHostToDevice, st));
+        B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, nparts, d_cursor, d_list);
+    }
     B200C_TRY(check_cancel());
     c->prog_scanned.store(bytes_read / 2);
 
@@ -678,17 +683,37 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_IHEAD, nparts + 1, &d_ihead));
     B200C_TRY(ws_typed(c, WS_ISIZE, nparts + 1, &d_isize));
     uint64_t ulen_out = 0, ilen_out = 0;
-    static const bool k4_thread = getenv("B200C_K4_THREAD") != nullptr;      // A/B switch: the first-generation thread-per-partition kernels
-    const size_t cell_smem8 = (size_t)16 * m->ncolumns * sizeof(MCell), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
-    if (nparts) {
-        unsigned g = (unsigned)((nparts + 127) / 128);
-        if (k4_thread) {
-        B200C_LAUNCH(c, k_partition_size, g, 128, 0, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
-        } else {
-            B200C_LAUNCH(c, (k_partition_size_tile<8, 1>), (unsigned)((nparts + 15) / 16), 128, cell_smem8, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 0u, 8u, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
-            if (K > 8) B200C_LAUNCH(c, (k_partition_size_tile<32, 1>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 8u, 32u, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
-            if (K > 32) B200C_LAUNCH(c, (k_partition_size_tile<32, 2>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 32u, 64u, d_dsize, d_ipay, d_nblk, d_ihead, d_stats, d_err);
+    uint32_t *d_stmunf, *d_strows;
+    B200C_TRY(ws_typed(c, WS_STMUNF, nparts + 1, &d_stmunf));
+    B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
+    const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
+    // one launch per fan-in class over its slice of the sorted list; `emit` selects the pass
+    auto launch_k4 = [&](bool emit, uint8_t* uout, uint8_t* iout) -> int {
+        if (n_le8) {
+            unsigned g = (unsigned)((n_le8 + 127) / 128);
+            if (emit) B200C_LAUNCH(c, (k_partition_thr<8, 128, true>), g, 128, smem8, dP, d_contrib, d_opfirst, d_list, 0ull, n_le8, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            else B200C_LAUNCH(c, (k_partition_thr<8, 128, false>), g, 128, smem8, dP, d_contrib, d_opfirst, d_list, 0ull, n_le8, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
         }
+        if (n_le16 > n_le8) {
+            unsigned g = (unsigned)((n_le16 - n_le8 + 63) / 64);
+            if (emit) B200C_LAUNCH(c, (k_partition_thr<16, 64, true>), g, 64, smem16, dP, d_contrib, d_opfirst, d_list, n_le8, n_le16, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            else B200C_LAUNCH(c, (k_partition_thr<16, 64, false>), g, 64, smem16, dP, d_contrib, d_opfirst, d_list, n_le8, n_le16, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+        }
+        if (n_le32 > n_le16) {
+            unsigned g = (unsigned)((n_le32 - n_le16 + 3) / 4);
+            if (emit) B200C_LAUNCH(c, (k_partition_warp<1, true>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le16, n_le32, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            else B200C_LAUNCH(c, (k_partition_warp<1, false>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le16, n_le32, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+        }
+        if (nparts > n_le32) {
+            unsigned g = (unsigned)((nparts - n_le32 + 3) / 4);
+            if (emit) B200C_LAUNCH(c, (k_partition_warp<2, true>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le32, nparts, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            else B200C_LAUNCH(c, (k_partition_warp<2, false>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le32, nparts, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+        }
+        return B200C_OK;
+    };
+    if (nparts) {
+        B200C_TRY(launch_k4(false, nullptr, nullptr));
+        B200C_LAUNCH(c, k_sum_stats, 1184, 256, 0, nparts, d_dsize, d_stmunf, d_strows, d_stats);
         B200C_TRY(exclusive_scan<uint64_t>(c, d_dsize, nparts, d_dpos, WS_SCANA, 0));
         B200C_LAUNCH(c, k_index_sizes, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_dsize, d_dpos, d_ipay, d_ihead, d_isize);
         B200C_TRY(exclusive_scan<uint32_t>(c, d_isize, nparts, d_ipos, WS_SCANA + 3, 0));
@@ -711,16 +736,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     uint8_t *UOUT, *IOUT;
     B200C_TRY(ws_typed(c, WS_UOUT, ulen_out + 64, &UOUT));
     B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
-    if (nparts && ulen_out) {
-        if (k4_thread) {
-        B200C_LAUNCH(c, k_partition_emit, (unsigned)((nparts + 127) / 128), 128, 0, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_dsize, d_dpos, d_ipay, d_nblk,
-                     d_ipos, UOUT, IOUT, d_err);
-        } else {
-            B200C_LAUNCH(c, (k_partition_emit_tile<8, 1>), (unsigned)((nparts + 15) / 16), 128, cell_smem8, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 0u, 8u, d_dsize, d_dpos, d_ipay, d_nblk, d_ipos, UOUT, IOUT, d_err);
-            if (K > 8) B200C_LAUNCH(c, (k_partition_emit_tile<32, 1>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 8u, 32u, d_dsize, d_dpos, d_ipay, d_nblk, d_ipos, UOUT, IOUT, d_err);
-            if (K > 32) B200C_LAUNCH(c, (k_partition_emit_tile<32, 2>), (unsigned)((nparts + 3) / 4), 128, cell_smem32, dP, d_contrib, d_opfirst, nparts, d_upos, d_pbase, 32u, 64u, d_dsize, d_dpos, d_ipay, d_nblk, d_ipos, UOUT, IOUT, d_err);
-        }
-    }
+    if (nparts && ulen_out) B200C_TRY(launch_k4(true, UOUT, IOUT));
     c->prog_scanned.store(bytes_read * 3 / 4);
 
     // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------

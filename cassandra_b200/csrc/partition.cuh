@@ -112,14 +112,15 @@ template <bool EMIT> struct Sink {
 
 struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialised clustering values (header vint + values) in U
 
-struct Cur {                       // cursor of one contributing input partition
+struct Cur {                       // cursor of one contributing input partition (40 bytes: it lives in shared memory)
     uint64_t pos, next, end;       // current unfiltered, the one after it, end of the partition
-    uint32_t ck_rel, ckend_rel, body_rel;
+    uint32_t ckend_rel, body_rel;  // offsets from pos: end of the clustering values, start of the body
+    uint8_t ck_rel;                // offset from pos of the clustering values (1..4)
     uint8_t flags, ext, kind, n, src; bool done;
 };
 
 // parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
-__device__ void cur_load(const CParams& P, Cur& c, int& err) {
+__device__ __noinline__ void cur_load(const CParams& P, Cur& c, int& err) {
     for (;;) {
         Rd r{P.U, c.pos, c.end, 0};
         uint32_t flags = r.u8();
@@ -134,7 +135,7 @@ __device__ void cur_load(const CParams& P, Cur& c, int& err) {
             if ((c.ext & 0x03) || (flags & 0x40)) { err = PERR_UNSUPPORTED; c.done = true; return; }
             c.kind = K_CLUSTERING; c.n = (uint8_t)P.nclust;
         }
-        c.ck_rel = (uint32_t)(r.p - c.pos);
+        c.ck_rel = (uint8_t)(r.p - c.pos);
         if (c.n) {
             uint64_t header = r.vint();
             for (int i = 0; i < c.n; i++) {
@@ -176,7 +177,7 @@ __device__ __forceinline__ int cmp_value(int type, const uint8_t* a, int la, con
 }
 
 // ClusteringComparator.compare: S/db/ClusteringComparator.java:140-157
-__device__ int cmp_clust(const CParams& P, const Cur& a, const Cur& b) {
+__device__ __noinline__ int cmp_clust(const CParams& P, const Cur& a, const Cur& b) {
     const uint8_t* pa = P.U + a.pos + a.ck_rel; const uint8_t* pb = P.U + b.pos + b.ck_rel;
     const uint8_t* ea = P.U + a.pos + a.ckend_rel; const uint8_t* eb = P.U + b.pos + b.ckend_rel;
     int m = a.n < b.n ? a.n : b.n;
@@ -261,7 +262,7 @@ template <bool EMIT> __device__ __forceinline__ void write_prefix(Sink<EMIT>& s,
     s.copy(P.U + c.off, c.len);
 }
 
-template <bool EMIT> __device__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
+template <bool EMIT> __device__ __noinline__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
     uint64_t cur = w.d.pos - w.start;
     bool emit_info = EMIT && w.nblocks_final > 1;
     if (emit_info && w.d.on) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
@@ -325,7 +326,7 @@ __device__ __forceinline__ Rd row_header(const CParams& P, const Cur& c, Live& i
 }
 
 // folds the cells of the row at cursor `c` into merged[] (ColumnDataReducer.getReduced :838-849)
-__device__ void fold_cells(const CParams& P, const Cur& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
+__device__ __noinline__ void fold_cells(const CParams& P, const Cur& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
     const InDesc& in = P.in[c.src];
     uint64_t missing = 0;
     if (!(c.flags & 0x20)) missing = r.vint();
@@ -353,7 +354,7 @@ __device__ void fold_cells(const CParams& P, const Cur& c, Rd& r, const Live& in
 }
 
 // BTreeRow.purge :457-499 + AbstractCell.purge :78-99. Returns the number of surviving cells, or -1 when the row disappears.
-__device__ int purge_row(const CParams& P, const Purger& pg, Live& info, DT& del, MCell* cells) {
+__device__ __noinline__ int purge_row(const CParams& P, const Purger& pg, Live& info, DT& del, MCell* cells) {
     if (pg.live(info)) info = live_empty();
     if (pg.dt(del)) del = dt_live();
     int present = 0;
@@ -378,7 +379,7 @@ template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, 
     w.header_len = w.d.pos - w.start; w.started = true;
 }
 
-template <bool EMIT> __device__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
+template <bool EMIT> __device__ __noinline__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
     int flags = 0;
     if (!live_is_empty(info)) flags |= 0x04;
     if (info.ttl != 0) flags |= 0x08;
@@ -395,7 +396,7 @@ template <bool EMIT> __device__ void write_row(PWriter<EMIT>& w, const CParams& 
 }
 
 // UnfilteredSerializer.serialize(RangeTombstoneMarker) :282-305
-template <bool EMIT> __device__ void write_marker(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const DT& m_close, const DT& m_open) {
+template <bool EMIT> __device__ __noinline__ void write_marker(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const DT& m_close, const DT& m_open) {
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
     Sink<false> cs{nullptr, 0, false};
@@ -432,14 +433,14 @@ __device__ __forceinline__ void read_marker_dts(const CParams& P, const Cur& c, 
 struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; };
 
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
+// cur[0..m) / open_dt[0..m): per-source cursor state owned by this thread (the caller places it in shared memory);
+// merged[0..ncols): scratch for the merged row.
 template <bool EMIT>
 __device__ void process_partition(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                   const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
                                   uint8_t* dout, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
+                                  Cur* cur, DT* open_dt, MCell* merged,
                                   PartOut& out, PartStats& st, int& err) {
-    Cur cur[MAXK];
-    MCell merged[MAXCOLS];
-    DT open_dt[MAXK];
     Purger pg{P.now, P.gc_before, P.purge_max_ts};
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;

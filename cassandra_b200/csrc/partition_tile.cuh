@@ -19,7 +19,7 @@ template <int G> __device__ __forceinline__ uint64_t tshflu64(const cg::thread_b
 template <int G> __device__ __forceinline__ DT tshfl_dt(const cg::thread_block_tile<G>& t, const DT& d, int src) { DT r; r.mfda = tshfl64<G>(t, d.mfda, src); r.ldt = tshfl64<G>(t, d.ldt, src); return r; }
 template <int G> __device__ __forceinline__ Cur tshfl_cur(const cg::thread_block_tile<G>& t, const Cur& c, int src) {
     Cur r; r.pos = tshflu64<G>(t, c.pos, src); r.next = 0; r.end = 0;
-    r.ck_rel = t.shfl(c.ck_rel, src); r.ckend_rel = t.shfl(c.ckend_rel, src); r.body_rel = 0;
+    r.ck_rel = (uint8_t)t.shfl((uint32_t)c.ck_rel, src); r.ckend_rel = t.shfl(c.ckend_rel, src); r.body_rel = 0;
     uint32_t packed = (uint32_t)c.flags | ((uint32_t)c.kind << 8) | ((uint32_t)c.n << 16);
     packed = t.shfl(packed, src);
     r.flags = (uint8_t)packed; r.kind = (uint8_t)(packed >> 8); r.n = (uint8_t)(packed >> 16); r.ext = 0; r.src = 0; r.done = false;

@@ -35,7 +35,7 @@ enum { IB = 256 };                       // Index.db speculation block
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -388,12 +388,33 @@ __global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restric
 
 enum { SLOT_BYTES = sizeof(Cur) };          // per-source cursor in shared memory
 
+// mode 0: size pass only (EMIT = false). mode 1: the single serialisation pass — bytes go to scratch at dbase + doff[j] (capacity
+// dcapv[j]), sizes/stats are recorded, no Index.db. mode 2: final emit of every written partition at dbase + dpos[j] with its Index.db
+// entry. mode 3: like 2 but only partitions the gather could not finish (more than one column-index block, or scratch overflow).
+struct K4Args {
+    const CParams* P; const uint64_t* contrib; const uint64_t* op_first; const uint32_t* list; const uint64_t* upos; const uint64_t* pbase;
+    uint64_t* dsize; uint32_t* ipay; uint32_t* nblk; uint32_t* ihead; uint32_t* st_munf; uint32_t* st_rows; uint8_t* ovf;
+    const uint64_t* doff; const uint64_t* dcapv; const uint64_t* dpos; const uint64_t* ipos; uint8_t* dbase; uint8_t* iout; DevErr* err; int mode;
+};
+
+template <bool EMIT> __device__ __forceinline__ bool k4_prologue(const K4Args& a, uint64_t j, uint8_t*& dout, uint64_t& dcap, uint64_t& dposv, uint8_t*& iout, uint32_t& nbf, uint32_t& ipf) {
+    dout = nullptr; dcap = ~0ull; dposv = 0; iout = nullptr; nbf = 0; ipf = 0;
+    if (!EMIT) return true;
+    if (a.mode == 1) { dout = a.dbase + a.doff[j]; dcap = a.dcapv[j]; return true; }
+    if (!a.dsize[j]) return false;
+    if (a.mode == 3 && !(a.nblk[j] > 1 || a.ovf[j])) return false;
+    dout = a.dbase + a.dpos[j]; dposv = a.dpos[j]; iout = a.iout + a.ipos[j]; nbf = a.nblk[j]; ipf = a.ipay[j];
+    return true;
+}
+template <bool EMIT> __device__ __forceinline__ void k4_epilogue(const K4Args& a, uint64_t j, uint64_t c0, PartOut out, PartStats st, int e) {
+    if (EMIT && a.mode >= 2) { if (e || out.dsize != a.dsize[j]) report_err(a.err, 8, 0, j); return; }
+    if (e) { uint64_t en = a.contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(a.err, e == PERR_UNSUPPORTED ? 9 : 4, src, a.upos[a.pbase[src] + (en & 0xFFFFFFFFFFull)] - a.P->in[src].ubase); out = PartOut{0, 0, 0, 0, 0}; st = PartStats{0, 0}; }
+    a.dsize[j] = out.dsize; a.ipay[j] = out.ipay; a.nblk[j] = out.nblk; a.ihead[j] = out.ihead; a.ovf[j] = (uint8_t)out.ovf;
+    a.st_munf[j] = (uint32_t)st.merged_unfiltereds; a.st_rows[j] = (uint32_t)st.rows_out;
+}
+
 template <int M_CAP, int NT, bool EMIT>
-__global__ void __launch_bounds__(NT) k_partition_thr(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
-        const uint32_t* __restrict__ list, uint64_t lo, uint64_t hi, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
-        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
-        uint32_t* __restrict__ st_munf, uint32_t* __restrict__ st_rows,
-        const uint64_t* __restrict__ dpos, const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
+__global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t lo, uint64_t hi) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     constexpr int STRIDE = M_CAP * SLOT_BYTES + 8;       // +8: spread the threads over the banks
     Cur* cur = (Cur*)(s_raw + (size_t)threadIdx.x * STRIDE);
@@ -401,43 +422,68 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const CParams* __restrict_
     DT open_dt[M_CAP];                                   // only touched when the partition holds range tombstone markers
     uint64_t t = lo + (uint64_t)blockIdx.x * NT + threadIdx.x;
     if (t >= hi) return;
-    uint64_t j = list[t];
-    if (EMIT && !dsize[j]) return;
-    uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
-    PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+    uint64_t j = a.list[t];
+    uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf;
+    if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf)) return;
+    uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
+    PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
     if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
-    else if (EMIT) process_partition<true>(*Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], cur, open_dt, merged, out, st, e);
-    else process_partition<false>(*Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, cur, open_dt, merged, out, st, e);
-    if (EMIT) { if (e || out.dsize != dsize[j]) report_err(err, 8, 0, j); return; }
-    if (e) { uint64_t en = contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, src, upos[pbase[src] + (en & 0xFFFFFFFFFFull)] - Pp->in[src].ubase); out = PartOut{0, 0, 0, 0}; st = PartStats{0, 0}; }
-    dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
-    st_munf[j] = (uint32_t)st.merged_unfiltereds; st_rows[j] = (uint32_t)st.rows_out;
+    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, dout, dcap, dposv, iout, nbf, ipf, cur, open_dt, merged, out, st, e);
+    k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
 // fan-in above 16: a whole warp per partition, cursors in registers (partition_tile.cuh)
 template <int S, bool EMIT>
-__global__ void __launch_bounds__(128) k_partition_warp(const CParams* __restrict__ Pp, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
-        const uint32_t* __restrict__ list, uint64_t lo, uint64_t hi, const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase,
-        uint64_t* __restrict__ dsize, uint32_t* __restrict__ ipay, uint32_t* __restrict__ nblk, uint32_t* __restrict__ ihead,
-        uint32_t* __restrict__ st_munf, uint32_t* __restrict__ st_rows,
-        const uint64_t* __restrict__ dpos, const uint64_t* __restrict__ ipos, uint8_t* __restrict__ uout, uint8_t* __restrict__ iout, DevErr* __restrict__ err) {
+__global__ void __launch_bounds__(128) k_partition_warp(const K4Args a, uint64_t lo, uint64_t hi) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     auto tile = cg::tiled_partition<32>(cg::this_thread_block());
     const int tid = threadIdx.x / 32;
-    MCell* s_cells = (MCell*)s_raw + (size_t)tid * Pp->ncols;
+    MCell* s_cells = (MCell*)s_raw + (size_t)tid * a.P->ncols;
     uint64_t t = lo + (uint64_t)blockIdx.x * 4 + tid;
     if (t >= hi) return;
-    uint64_t j = list[t];
-    if (EMIT && !dsize[j]) return;
-    uint64_t c0 = op_first[j]; uint32_t m = (uint32_t)(op_first[j + 1] - c0);
-    PartOut out{0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-    if (EMIT) process_partition_tile<32, S, true>(tile, *Pp, contrib, c0, m, upos, pbase, uout + dpos[j], dpos[j], iout + ipos[j], nblk[j], ipay[j], s_cells, out, st, e);
-    else process_partition_tile<32, S, false>(tile, *Pp, contrib, c0, m, upos, pbase, nullptr, 0, nullptr, 0, 0, s_cells, out, st, e);
-    if (tile.thread_rank() != 0) return;
-    if (EMIT) { if (e || out.dsize != dsize[j]) report_err(err, 8, 0, j); return; }
-    if (e) { uint64_t en = contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(err, e == PERR_UNSUPPORTED ? 9 : 4, src, upos[pbase[src] + (en & 0xFFFFFFFFFFull)] - Pp->in[src].ubase); out = PartOut{0, 0, 0, 0}; st = PartStats{0, 0}; }
-    dsize[j] = out.dsize; ipay[j] = out.ipay; nblk[j] = out.nblk; ihead[j] = out.ihead;
-    st_munf[j] = (uint32_t)st.merged_unfiltereds; st_rows[j] = (uint32_t)st.rows_out;
+    uint64_t j = a.list[t];
+    uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf;
+    if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf)) return;
+    uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
+    PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, dout, dcap, dposv, iout, nbf, ipf, s_cells, out, st, e);
+    if (tile.thread_rank() == 0) k4_epilogue<EMIT>(a, j, c0, out, st, e);
+}
+
+// upper bound of an output partition's size: the sum of its input partitions plus 25 % + 32 bytes (re-based deltas can lengthen
+// vints by a byte or two per field; a partition that still does not fit is caught by the overflow flag and re-emitted by mode 3)
+__global__ void __launch_bounds__(256) k_bounds(const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first, uint64_t nparts,
+                                                const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint64_t* __restrict__ bound) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nparts) return;
+    uint64_t sum = 0;
+    for (uint64_t c = op_first[j]; c < op_first[j + 1]; c++) { uint64_t e = contrib[c]; uint64_t g = pbase[(e >> 56) & 0x7F] + (e & 0xFFFFFFFFFFull); sum += upos[g + 1] - upos[g]; }
+    bound[j] = (sum + (sum >> 2) + 32 + 15) & ~15ull;
+}
+
+// scratch -> dense Data stream; one warp per output partition (partitions are tens of bytes to a few KB)
+__global__ void __launch_bounds__(256) k_gather(uint64_t nparts, const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos, const uint64_t* __restrict__ bpos,
+                                                const uint8_t* __restrict__ ovf, const uint8_t* __restrict__ scratch, uint8_t* __restrict__ uout) {
+    uint64_t j = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= nparts) return;
+    uint64_t n = dsize[j];
+    if (!n || ovf[j]) return;
+    const uint8_t* s = scratch + bpos[j]; uint8_t* d = uout + dpos[j];
+    int lane = threadIdx.x & 31;
+    for (uint64_t i = lane; i < n; i += 32) d[i] = s[i];
+}
+
+// Index.db entries of partitions without a promoted index: u16 keyLen | key | vint position | vint32 0  (RowIndexEntry.serialize :468-473)
+__global__ void __launch_bounds__(256) k_index_simple(const CParams* __restrict__ Pp, uint64_t nparts, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos,
+        const uint32_t* __restrict__ nblk, const uint8_t* __restrict__ ovf, const uint32_t* __restrict__ ihead, const uint64_t* __restrict__ ipos, uint8_t* __restrict__ iout) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nparts || !dsize[j] || nblk[j] > 1 || ovf[j]) return;
+    uint64_t e = contrib[op_first[j]]; uint64_t g = pbase[(e >> 56) & 0x7F] + (e & 0xFFFFFFFFFFull);
+    const uint8_t* k = Pp->U + upos[g];
+    uint32_t n = ihead[j];                          // 2 + keyLen: the bytes are identical to the partition header in Data.db
+    Sink<true> s{iout + ipos[j], 0, true, ~0ull};
+    s.copy(k, n); s.vint(dpos[j]); s.u8(0);
 }
 
 __global__ void __launch_bounds__(256) k_sum_stats(uint64_t nparts, const uint64_t* __restrict__ dsize, const uint32_t* __restrict__ st_munf, const uint32_t* __restrict__ st_rows, RunStats* __restrict__ stats) {
@@ -683,36 +729,58 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_IHEAD, nparts + 1, &d_ihead));
     B200C_TRY(ws_typed(c, WS_ISIZE, nparts + 1, &d_isize));
     uint64_t ulen_out = 0, ilen_out = 0;
-    uint32_t *d_stmunf, *d_strows;
+    uint32_t *d_stmunf, *d_strows; uint8_t* d_ovf; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
     B200C_TRY(ws_typed(c, WS_STMUNF, nparts + 1, &d_stmunf));
     B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
+    B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
     const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
-    // one launch per fan-in class over its slice of the sorted list; `emit` selects the pass
-    auto launch_k4 = [&](bool emit, uint8_t* uout, uint8_t* iout) -> int {
+    static const bool two_pass = getenv("B200C_K4_TWO_PASS") != nullptr;     // A/B switch: size pass + full emit pass instead of scratch + gather
+    K4Args ka; memset(&ka, 0, sizeof(ka));
+    ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase;
+    ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
+    ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err;
+    // one launch per fan-in class over its slice of the sorted list
+    auto launch_k4 = [&](int mode) -> int {
+        ka.mode = mode;
+        const bool emit = mode != 0;
         if (n_le8) {
             unsigned g = (unsigned)((n_le8 + 127) / 128);
-            if (emit) B200C_LAUNCH(c, (k_partition_thr<8, 128, true>), g, 128, smem8, dP, d_contrib, d_opfirst, d_list, 0ull, n_le8, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
-            else B200C_LAUNCH(c, (k_partition_thr<8, 128, false>), g, 128, smem8, dP, d_contrib, d_opfirst, d_list, 0ull, n_le8, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            if (emit) B200C_LAUNCH(c, (k_partition_thr<8, 128, true>), g, 128, smem8, ka, 0ull, n_le8);
+            else B200C_LAUNCH(c, (k_partition_thr<8, 128, false>), g, 128, smem8, ka, 0ull, n_le8);
         }
         if (n_le16 > n_le8) {
             unsigned g = (unsigned)((n_le16 - n_le8 + 63) / 64);
-            if (emit) B200C_LAUNCH(c, (k_partition_thr<16, 64, true>), g, 64, smem16, dP, d_contrib, d_opfirst, d_list, n_le8, n_le16, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
-            else B200C_LAUNCH(c, (k_partition_thr<16, 64, false>), g, 64, smem16, dP, d_contrib, d_opfirst, d_list, n_le8, n_le16, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            if (emit) B200C_LAUNCH(c, (k_partition_thr<16, 64, true>), g, 64, smem16, ka, n_le8, n_le16);
+            else B200C_LAUNCH(c, (k_partition_thr<16, 64, false>), g, 64, smem16, ka, n_le8, n_le16);
         }
         if (n_le32 > n_le16) {
             unsigned g = (unsigned)((n_le32 - n_le16 + 3) / 4);
-            if (emit) B200C_LAUNCH(c, (k_partition_warp<1, true>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le16, n_le32, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
-            else B200C_LAUNCH(c, (k_partition_warp<1, false>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le16, n_le32, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            if (emit) B200C_LAUNCH(c, (k_partition_warp<1, true>), g, 128, cell_smem32, ka, n_le16, n_le32);
+            else B200C_LAUNCH(c, (k_partition_warp<1, false>), g, 128, cell_smem32, ka, n_le16, n_le32);
         }
         if (nparts > n_le32) {
             unsigned g = (unsigned)((nparts - n_le32 + 3) / 4);
-            if (emit) B200C_LAUNCH(c, (k_partition_warp<2, true>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le32, nparts, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
-            else B200C_LAUNCH(c, (k_partition_warp<2, false>), g, 128, cell_smem32, dP, d_contrib, d_opfirst, d_list, n_le32, nparts, d_upos, d_pbase, d_dsize, d_ipay, d_nblk, d_ihead, d_stmunf, d_strows, d_dpos, d_ipos, uout, iout, d_err);
+            if (emit) B200C_LAUNCH(c, (k_partition_warp<2, true>), g, 128, cell_smem32, ka, n_le32, nparts);
+            else B200C_LAUNCH(c, (k_partition_warp<2, false>), g, 128, cell_smem32, ka, n_le32, nparts);
         }
         return B200C_OK;
     };
+    uint8_t* SCRATCH = nullptr;
     if (nparts) {
-        B200C_TRY(launch_k4(false, nullptr, nullptr));
+        if (two_pass) {
+            B200C_CUDA_TRY(c, cudaMemsetAsync(d_ovf, 0, nparts, st));
+            B200C_TRY(launch_k4(0));
+        } else {
+            B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
+            B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
+            B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound);
+            B200C_TRY(exclusive_scan<uint64_t>(c, d_bound, nparts, d_bpos, WS_SCANA, 0));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_bpos + nparts, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+            B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
+            ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr;
+            B200C_TRY(launch_k4(1));
+        }
         B200C_LAUNCH(c, k_sum_stats, 1184, 256, 0, nparts, d_dsize, d_stmunf, d_strows, d_stats);
         B200C_TRY(exclusive_scan<uint64_t>(c, d_dsize, nparts, d_dpos, WS_SCANA, 0));
         B200C_LAUNCH(c, k_index_sizes, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_dsize, d_dpos, d_ipay, d_ihead, d_isize);
@@ -736,7 +804,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     uint8_t *UOUT, *IOUT;
     B200C_TRY(ws_typed(c, WS_UOUT, ulen_out + 64, &UOUT));
     B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
-    if (nparts && ulen_out) B200C_TRY(launch_k4(true, UOUT, IOUT));
+    if (nparts && ulen_out) {
+        ka.dbase = UOUT; ka.iout = IOUT; ka.doff = nullptr; ka.dcapv = nullptr;
+        if (two_pass) B200C_TRY(launch_k4(2));
+        else {
+            B200C_LAUNCH(c, k_gather, (unsigned)((nparts + 7) / 8), 256, 0, nparts, d_dsize, d_dpos, d_bpos, d_ovf, SCRATCH, UOUT);
+            B200C_LAUNCH(c, k_index_simple, (unsigned)((nparts + 255) / 256), 256, 0, dP, nparts, d_contrib, d_opfirst, d_upos, d_pbase, d_dsize, d_dpos, d_nblk, d_ovf, d_ihead, d_ipos, IOUT);
+            B200C_TRY(launch_k4(3));
+        }
+    }
     c->prog_scanned.store(bytes_read * 3 / 4);
 
     // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------

@@ -92,13 +92,14 @@ struct Rd {
 // ---- sinks ----------------------------------------------------------------------------------------------------------------
 template <bool EMIT> struct Sink {
     uint8_t* base; uint64_t pos; bool on;      // on: this lane performs the stores (tile mode: lane 0 only; every lane tracks pos)
-    __device__ __forceinline__ void u8(uint32_t v) { if (EMIT && on) base[pos] = (uint8_t)v; pos++; }
+    uint64_t cap;                              // bytes available at base: stores beyond it are dropped (the caller sees pos > cap)
+    __device__ __forceinline__ void u8(uint32_t v) { if (EMIT && on && pos < cap) base[pos] = (uint8_t)v; pos++; }
     __device__ __forceinline__ void be16(uint32_t v) { u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be64(uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); }
     __device__ __forceinline__ void vint(uint64_t v) {
         int size = vint_size(v);
-        if (EMIT && on) {
+        if (EMIT && on && pos + size <= cap) {
             if (size == 1) base[pos] = (uint8_t)v;
             else if (size < 9) {
                 uint64_t reg = (v << ((8 - size) << 3)) | ((uint64_t)(uint8_t)(~(0xffu >> (size - 1))) << 56);
@@ -107,16 +108,18 @@ template <bool EMIT> struct Sink {
         }
         pos += size;
     }
-    __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
+    __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on && pos + n <= cap) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
 };
 
 struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialised clustering values (header vint + values) in U
 
-struct Cur {                       // cursor of one contributing input partition (40 bytes: it lives in shared memory)
+struct Cur {                       // cursor of one contributing input partition (48 bytes: it lives in shared memory)
     uint64_t pos, next, end;       // current unfiltered, the one after it, end of the partition
+    uint64_t k0;                   // order-preserving 64-bit prefix of the first clustering component (see cur_load)
     uint32_t ckend_rel, body_rel;  // offsets from pos: end of the clustering values, start of the body
     uint8_t ck_rel;                // offset from pos of the clustering values (1..4)
     uint8_t flags, ext, kind, n, src; bool done;
+    uint8_t fast;                  // 0: no prefix key; 1: k0 orders unequal prefixes, ties need cmp_clust; 2: k0 is the whole clustering
 };
 
 // parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
@@ -136,11 +139,21 @@ __device__ __noinline__ void cur_load(const CParams& P, Cur& c, int& err) {
             c.kind = K_CLUSTERING; c.n = (uint8_t)P.nclust;
         }
         c.ck_rel = (uint8_t)(r.p - c.pos);
+        c.fast = 0; c.k0 = 0;
         if (c.n) {
             uint64_t header = r.vint();
             for (int i = 0; i < c.n; i++) {
                 if ((header >> (2 * i)) & 3) continue;
                 uint64_t len = P.cfix[i] > 0 ? (uint64_t)P.cfix[i] : r.vint();
+                if (i == 0 && !r.err && r.end - r.p >= len) {
+                    // first component, non-null and non-empty: big-endian prefix, sign bit flipped for the signed classes
+                    int t = P.ctype[0]; uint64_t k = 0; int take = len < 8 ? (int)len : 8;
+                    for (int b = 0; b < take; b++) k |= (uint64_t)P.U[r.p + b] << (56 - 8 * b);
+                    if (t == TYPE_FIXED_SIGNED || t == TYPE_VAR_SIGNED) k ^= 0x8000000000000000ull;
+                    c.k0 = k;
+                    bool whole = (t == TYPE_FIXED_SIGNED || t == TYPE_FIXED_BYTES) && len <= 8;      // equal prefix <=> equal value
+                    c.fast = (whole && P.nclust == 1 && c.n == 1) ? 2 : ((t == TYPE_VAR_SIGNED && len > 8) ? 0 : 1);
+                }
                 r.skip(len);
             }
         }
@@ -196,6 +209,15 @@ __device__ __noinline__ int cmp_clust(const CParams& P, const Cur& a, const Cur&
     }
     if (a.n == b.n) { int d = kind_comparison(a.kind) - kind_comparison(b.kind); return d < 0 ? -1 : (d > 0 ? 1 : 0); }
     return a.n < b.n ? kind_vs_clustering(a.kind) : -kind_vs_clustering(b.kind);
+}
+
+// cmp_clust with the cached prefix keys in front: unequal prefixes decide, equal "whole" keys only need the kind comparison
+__device__ __forceinline__ int cmp_heads(const CParams& P, const Cur& a, const Cur& b) {
+    if (a.fast && b.fast) {
+        if (a.k0 != b.k0) return a.k0 < b.k0 ? -1 : 1;
+        if (a.fast == 2 && b.fast == 2) { int d = kind_comparison(a.kind) - kind_comparison(b.kind); return d < 0 ? -1 : (d > 0 ? 1 : 0); }
+    }
+    return cmp_clust(P, a, b);
 }
 
 __device__ __forceinline__ DT read_delta_dt(Rd& r, const InDesc& in) {
@@ -264,9 +286,9 @@ template <bool EMIT> __device__ __forceinline__ void write_prefix(Sink<EMIT>& s,
 
 template <bool EMIT> __device__ __noinline__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
     uint64_t cur = w.d.pos - w.start;
-    bool emit_info = EMIT && w.nblocks_final > 1;
-    if (emit_info && w.d.on) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
-    if (!EMIT || emit_info) {
+    bool emit_info = EMIT && w.ix.on;              // ix.on: this lane stores IndexInfos (final emit of a partition with > 1 block)
+    if (emit_info) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
+    {                                              // the ix sink always counts; it stores only when ix.on
         write_prefix(w.ix, P, w.first); write_prefix(w.ix, P, w.last);
         w.ix.vint(w.block_start);
         w.ix.vint(zigzag_enc((int64_t)(cur - w.block_start) - 65536));
@@ -387,7 +409,7 @@ template <bool EMIT> __device__ __noinline__ void write_row(PWriter<EMIT>& w, co
     if (present == P.ncols) flags |= 0x20;
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
-    Sink<false> cs{nullptr, 0, false};
+    Sink<false> cs{nullptr, 0, false, 0};
     put_row_body(cs, P, flags, info, del, cells, present);
     w.d.u8(flags); w.d.copy(P.U + ck.off, ck.len);
     w.d.vint(cs.pos + vint_size(prev)); w.d.vint(prev);
@@ -399,7 +421,7 @@ template <bool EMIT> __device__ __noinline__ void write_row(PWriter<EMIT>& w, co
 template <bool EMIT> __device__ __noinline__ void write_marker(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const DT& m_close, const DT& m_open) {
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
-    Sink<false> cs{nullptr, 0, false};
+    Sink<false> cs{nullptr, 0, false, 0};
     bool boundary = kind_is_boundary(ck.kind), start = kind_is_start(ck.kind);
     if (boundary) { write_delta_dt(cs, P, m_close); write_delta_dt(cs, P, m_open); } else write_delta_dt(cs, P, start ? m_open : m_close);
     w.d.u8(0x02); w.d.u8(ck.kind); w.d.be16(ck.n); w.d.copy(P.U + ck.off, ck.len);
@@ -430,7 +452,7 @@ __device__ __forceinline__ void read_marker_dts(const CParams& P, const Cur& c, 
     if (r.err) err = r.err;
 }
 
-struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; };
+struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; };
 
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
 // cur[0..m) / open_dt[0..m): per-source cursor state owned by this thread (the caller places it in shared memory);
@@ -438,7 +460,7 @@ struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; };
 template <bool EMIT>
 __device__ void process_partition(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                   const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
-                                  uint8_t* dout, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
+                                  uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
                                   Cur* cur, DT* open_dt, MCell* merged,
                                   PartOut& out, PartStats& st, int& err) {
     Purger pg{P.now, P.gc_before, P.purge_max_ts};
@@ -461,15 +483,15 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;                 // PurgeFunction.applyToDeletion :95-99
 
     PWriter<EMIT> w;
-    w.d.base = dout; w.d.pos = 0; w.d.on = true; w.ix.on = true; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
+    w.d.base = dout; w.d.pos = 0; w.d.on = true; w.d.cap = dcap; w.ix.on = EMIT && iout && nblocks_final > 1; w.ix.cap = ~0ull; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
     w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
     // index entry layout (EMIT): [u16 kl][key][vint dpos][vint ipay]{[vint headerLen][DT][vint nblocks][IndexInfo..][i32 offsets..]}
     uint32_t hdr_len_known = 2 + klen + (dt_is_live(out_pdel) ? 1 : 12);
     uint32_t fixed = 2 + klen + vint_size(dpos) + vint_size(ipay_final);
     uint32_t pre = fixed + vint_size(hdr_len_known) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
-    w.ix.base = EMIT ? iout + pre : nullptr; w.ix.pos = 0;
-    w.ix_offs = EMIT ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
+    w.ix.base = (EMIT && iout) ? iout + pre : nullptr; w.ix.pos = 0;
+    w.ix_offs = (EMIT && iout) ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
 
     if (m == 1) {
         // single source: TrivialOneToOne (UnfilteredRowIterators.java:552-556) — no Row.Merger, only the purge transformation
@@ -496,10 +518,10 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         for (uint32_t v = 0; v < m; v++) cur_load(P, cur[v], err);
         while (!err) {
             int b = -1;
-            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && (b < 0 || cmp_clust(P, cur[v], cur[b]) < 0)) b = (int)v;
+            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && (b < 0 || cmp_heads(P, cur[v], cur[b]) < 0)) b = (int)v;
             if (b < 0) break;
             uint64_t grp = 0; int gcount = 0, last = b;
-            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && ((int)v == b || cmp_clust(P, cur[v], cur[b]) == 0)) { grp |= 1ull << v; gcount++; last = (int)v; }
+            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && ((int)v == b || cmp_heads(P, cur[v], cur[b]) == 0)) { grp |= 1ull << v; gcount++; last = (int)v; }
             // current open deletion in the merged stream (RangeTombstoneMarker.Merger.currentOpenDeletionTimeInMerged :160-168)
             DT cur_open = (biggest >= 0 && dt_supersedes(open_dt[biggest], pdel)) ? open_dt[biggest] : dt_live();
             if (!(cur[b].flags & 0x02)) {
@@ -558,15 +580,16 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     if (err) return;
     // partition.isEmpty() (UnfilteredRowIterator.java:63-68) / SortedTableWriter.append :134
     if (!w.started && !dt_is_live(out_pdel)) pw_start(w, P, key_off, klen, out_pdel);
-    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen;
+    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen; out.ovf = 0;
     if (w.started) {
         w.d.u8(0x01);                                                        // end of partition, then the trailing index block (finish() :217-243)
         if (w.rows_out && w.have_first) pw_add_index_block(w, P);
         out.dsize = w.d.pos; out.nblk = w.nblocks;
         if (w.nblocks > 1) out.ipay = vint_size(w.header_len) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(w.nblocks) + (uint32_t)w.ix.pos + 4 * w.nblocks;
         st.rows_out += w.rows_out;
-        if (EMIT) {                                                          // RowIndexEntry.serialize :468-473, IndexedEntry.serialize :625-642
-            Sink<true> e{iout, 0, true};
+        out.ovf = (EMIT && w.d.pos > dcap) ? 1 : 0;
+        if (EMIT && iout) {                                                  // RowIndexEntry.serialize :468-473, IndexedEntry.serialize :625-642
+            Sink<true> e{iout, 0, true, ~0ull};
             e.be16(klen); e.copy(P.U + key_off, klen); e.vint(dpos); e.vint(ipay_final);
             if (nblocks_final > 1) { e.vint(w.header_len); write_partition_dt(e, out_pdel); e.vint(nblocks_final); }
         }

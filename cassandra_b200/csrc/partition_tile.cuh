@@ -18,11 +18,11 @@ template <int G> __device__ __forceinline__ int64_t tshfl64(const cg::thread_blo
 template <int G> __device__ __forceinline__ uint64_t tshflu64(const cg::thread_block_tile<G>& t, uint64_t v, int src) { return (uint64_t)t.shfl((unsigned long long)v, src); }
 template <int G> __device__ __forceinline__ DT tshfl_dt(const cg::thread_block_tile<G>& t, const DT& d, int src) { DT r; r.mfda = tshfl64<G>(t, d.mfda, src); r.ldt = tshfl64<G>(t, d.ldt, src); return r; }
 template <int G> __device__ __forceinline__ Cur tshfl_cur(const cg::thread_block_tile<G>& t, const Cur& c, int src) {
-    Cur r; r.pos = tshflu64<G>(t, c.pos, src); r.next = 0; r.end = 0;
+    Cur r; r.pos = tshflu64<G>(t, c.pos, src); r.next = 0; r.end = 0; r.k0 = tshflu64<G>(t, c.k0, src);
     r.ck_rel = (uint8_t)t.shfl((uint32_t)c.ck_rel, src); r.ckend_rel = t.shfl(c.ckend_rel, src); r.body_rel = 0;
-    uint32_t packed = (uint32_t)c.flags | ((uint32_t)c.kind << 8) | ((uint32_t)c.n << 16);
+    uint32_t packed = (uint32_t)c.flags | ((uint32_t)c.kind << 8) | ((uint32_t)c.n << 16) | ((uint32_t)c.fast << 24);
     packed = t.shfl(packed, src);
-    r.flags = (uint8_t)packed; r.kind = (uint8_t)(packed >> 8); r.n = (uint8_t)(packed >> 16); r.ext = 0; r.src = 0; r.done = false;
+    r.flags = (uint8_t)packed; r.kind = (uint8_t)(packed >> 8); r.n = (uint8_t)(packed >> 16); r.fast = (uint8_t)(packed >> 24); r.ext = 0; r.src = 0; r.done = false;
     return r;
 }
 
@@ -59,7 +59,7 @@ __device__ __forceinline__ MCell read_cell(const CParams& P, const InDesc& in, R
 template <int G, int S, bool EMIT>
 __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                        const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
-                                       uint8_t* dout, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
+                                       uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
                                        MCell* s_cells, PartOut& out, PartStats& st, int& err) {
     const int lane = tile.thread_rank();
     const bool multi = m > 1;
@@ -71,7 +71,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
     for (int s = 0; s < S; s++) {
         uint32_t v = lane + G * s;
         have[s] = v < m; cur[s].done = true; cur[s].pos = cur[s].next = cur[s].end = 0; cur[s].src = 0; my_pd[s] = dt_live();
-        cur[s].flags = cur[s].kind = cur[s].n = cur[s].ext = 0; cur[s].ck_rel = cur[s].ckend_rel = cur[s].body_rel = 0;
+        cur[s].flags = cur[s].kind = cur[s].n = cur[s].ext = cur[s].fast = 0; cur[s].k0 = 0; cur[s].ck_rel = 0; cur[s].ckend_rel = cur[s].body_rel = 0;
         if (have[s]) {
             uint64_t e = contrib[c0 + v];
             int src = (int)((e >> 56) & 0x7F); uint64_t g = pbase[src] + (e & 0xFFFFFFFFFFull);
@@ -95,7 +95,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
     const DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;
 
     PWriter<EMIT> w;
-    w.d.base = dout; w.d.pos = 0; w.d.on = (lane == 0); w.ix.on = (lane == 0);
+    w.d.base = dout; w.d.pos = 0; w.d.on = (lane == 0); w.d.cap = dcap; w.ix.on = (lane == 0) && EMIT && iout && nblocks_final > 1; w.ix.cap = ~0ull;
     w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
     w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
@@ -103,8 +103,8 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
         uint32_t hdr_len_known = 2 + klen + (dt_is_live(out_pdel) ? 1 : 12);
         uint32_t fixed = 2 + klen + vint_size(dpos) + vint_size(ipay_final);
         uint32_t pre = fixed + vint_size(hdr_len_known) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
-        w.ix.base = EMIT ? iout + pre : nullptr; w.ix.pos = 0;
-        w.ix_offs = EMIT ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
+        w.ix.base = (EMIT && iout) ? iout + pre : nullptr; w.ix.pos = 0;
+        w.ix_offs = (EMIT && iout) ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
     }
 
 #pragma unroll
@@ -132,7 +132,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 c[s] = 1;
-                if (have[s] && !cur[s].done) c[s] = (lane == ll && s == ls) ? 0 : cmp_clust(P, cur[s], L);
+                if (have[s] && !cur[s].done) c[s] = (lane == ll && s == ls) ? 0 : cmp_heads(P, cur[s], L);
                 less[s] = tile.ballot(c[s] < 0); anyless |= less[s];
             }
             if (anyless) {
@@ -280,7 +280,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
     }
     if (tile.any(lerr != 0)) { err = tile.any(lerr == PERR_UNSUPPORTED) ? PERR_UNSUPPORTED : PERR_CORRUPT; return; }
     if (!w.started && !dt_is_live(out_pdel)) pw_start(w, P, key_off, klen, out_pdel);
-    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen;
+    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen; out.ovf = 0;
     st.merged_unfiltereds += merged_unf;
     if (w.started) {
         w.d.u8(0x01);
@@ -288,8 +288,9 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
         out.dsize = w.d.pos; out.nblk = w.nblocks;
         if (w.nblocks > 1) out.ipay = vint_size(w.header_len) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(w.nblocks) + (uint32_t)w.ix.pos + 4 * w.nblocks;
         st.rows_out += w.rows_out;
-        if (EMIT && lane == 0) {
-            Sink<true> e{iout, 0, true};
+        out.ovf = (EMIT && w.d.pos > dcap) ? 1 : 0;
+        if (EMIT && iout && lane == 0) {
+            Sink<true> e{iout, 0, true, ~0ull};
             e.be16(klen); e.copy(P.U + key_off, klen); e.vint(dpos); e.vint(ipay_final);
             if (nblocks_final > 1) { e.vint(w.header_len); write_partition_dt(e, out_pdel); e.vint(nblocks_final); }
         }

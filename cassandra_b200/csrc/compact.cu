@@ -765,6 +765,13 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         return B200C_OK;
     };
+    if (!c->k4_attr_set) {      // > 48 KiB of dynamic shared memory needs an explicit opt-in, once per context/device
+        cudaFuncSetAttribute(k_partition_thr<8, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+        cudaFuncSetAttribute(k_partition_thr<8, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+        cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+        cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+        c->k4_attr_set = true;
+    }
     uint8_t* SCRATCH = nullptr;
     if (nparts) {
         if (two_pass) {

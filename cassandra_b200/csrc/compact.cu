@@ -373,15 +373,32 @@ __global__ void __launch_bounds__(256) k_op_first(const uint32_t* __restrict__ h
 // number of cursors). Per-partition results go to arrays indexed by the partition number j; totals come from k_sum_stats.
 struct RunStats { unsigned long long merged_unfiltereds, rows_out, partitions_out; };
 
-// warp-aggregated counting-sort scatter: list[cursor[m]++] = j
-__global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restrict__ op_first, uint64_t nparts, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
+// Work-list order: partitions are counting-sorted by (fan-in m, average input partition size bucket) so that the threads of a warp
+// run the same number of cursors over similarly sized partitions (less divergence). key = (m - 1) * 16 + bucket.
+enum { SORT_BUCKETS = 16, SORT_BINS = MAXK * SORT_BUCKETS };
+__device__ __forceinline__ uint32_t sort_key(uint32_t m, uint64_t bound) {
+    uint64_t avg = bound / (m ? m : 1);
+    uint32_t bucket = (uint32_t)min((uint64_t)(SORT_BUCKETS - 1), avg >> 5);
+    return (m - 1) * SORT_BUCKETS + bucket;
+}
+__global__ void __launch_bounds__(256) k_class_hist(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts, unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t s_h[SORT_BINS];
+    for (int k = threadIdx.x; k < SORT_BINS; k += blockDim.x) s_h[k] = 0;
+    __syncthreads();
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nparts; j += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&s_h[sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j])], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < SORT_BINS; k += blockDim.x) if (s_h[k]) atomicAdd(&hist[k], (unsigned long long)s_h[k]);
+}
+// warp-aggregated counting-sort scatter: list[cursor[key]++] = j
+__global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = j < nparts;
-    uint32_t m = valid ? (uint32_t)(op_first[j + 1] - op_first[j]) : 0xFFFFFFFFu;
-    uint32_t peers = __match_any_sync(FULL_MASK, m);
+    uint32_t key = valid ? sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j]) : 0xFFFFFFFFu;
+    uint32_t peers = __match_any_sync(FULL_MASK, key);
     int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
     unsigned long long base = 0;
-    if (valid && lane == leader) base = atomicAdd(&cursor[m], (unsigned long long)__popc(peers));
+    if (valid && lane == leader) base = atomicAdd(&cursor[key], (unsigned long long)__popc(peers));
     base = __shfl_sync(FULL_MASK, base, leader);
     if (valid) list[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)j;
 }
@@ -684,7 +701,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     uint64_t ncontrib = 0;
     for (int i = 0; i < K; i++) ncontrib += h[2 * i + 1] - h[2 * i];
     const uint64_t nbuckets = std::max<uint64_t>(1, ncontrib / 256);
-    uint64_t *d_bstart, *d_contrib, *d_opidx, *d_opfirst; uint32_t* d_head; MergeGeom* d_geom;
+    uint64_t *d_bstart, *d_contrib, *d_opidx; uint32_t* d_head; MergeGeom* d_geom;
     B200C_TRY(ws_typed(c, WS_BSTART, (nbuckets + 1) * K + 8, &d_bstart)); d_geom = (MergeGeom*)(d_range + 2 * K + 2);
     B200C_TRY(ws_typed(c, WS_CONTRIB, ncontrib + 1, &d_contrib));
     B200C_TRY(ws_typed(c, WS_HEAD, ncontrib + 1, &d_head));
@@ -701,18 +718,31 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         nparts = h[0];
     }
     if (nparts >= (1ull << 32)) { c->err = "too many output partitions"; return B200C_EUNSUPPORTED; }
-    // counting sort of the output partitions by fan-in m (histogram = mergedRowCounts, already built by the merge kernel)
-    uint64_t fan_base[MAXK + 2]; fan_base[0] = fan_base[1] = 0;
-    for (int k = 1; k <= MAXK; k++) fan_base[k + 1] = fan_base[k] + (ncontrib ? h[16 + k - 1] : 0);      // fan_base[m] = first list slot of fan-in m
-    const uint64_t n_le8 = fan_base[9], n_le16 = fan_base[17], n_le32 = fan_base[33];
+    uint64_t* d_opfirst;
     B200C_TRY(ws_typed(c, WS_OPFIRST, nparts + 2, &d_opfirst));
-    uint32_t* d_list; unsigned long long* d_cursor;
+    uint32_t* d_list; unsigned long long* d_cursor; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
     B200C_TRY(ws_typed(c, WS_LIST, nparts + 1, &d_list));
-    B200C_TRY(ws_typed(c, WS_CURSOR, (size_t)MAXK + 2, &d_cursor));
+    B200C_TRY(ws_typed(c, WS_CURSOR, (size_t)SORT_BINS + 2, &d_cursor));
+    B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
+    B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
+    uint64_t n_le8 = 0, n_le16 = 0, n_le32 = 0;
     if (ncontrib) {
         B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_cursor, fan_base, (MAXK + 2) * 8, cudaMemcpyHostToDevice, st));
-        B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, nparts, d_cursor, d_list);
+        // counting sort of the output partitions by (fan-in, size bucket)
+        B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound);
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_cursor, 0, (SORT_BINS + 2) * 8, st));
+        B200C_LAUNCH(c, k_class_hist, 592, 256, 0, d_opfirst, d_bound, nparts, d_cursor);
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512, d_cursor, SORT_BINS * 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        uint64_t run = 0;
+        for (int k = 0; k < SORT_BINS; k++) {
+            if (k == 8 * SORT_BUCKETS) n_le8 = run;
+            if (k == 16 * SORT_BUCKETS) n_le16 = run;
+            if (k == 32 * SORT_BUCKETS) n_le32 = run;
+            uint64_t cnt = h[512 + k]; h[512 + k] = run; run += cnt;
+        }
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_cursor, h + 512, SORT_BINS * 8, cudaMemcpyHostToDevice, st));
+        B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, d_cursor, d_list);
     }
     B200C_TRY(check_cancel());
     c->prog_scanned.store(bytes_read / 2);
@@ -729,7 +759,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_IHEAD, nparts + 1, &d_ihead));
     B200C_TRY(ws_typed(c, WS_ISIZE, nparts + 1, &d_isize));
     uint64_t ulen_out = 0, ilen_out = 0;
-    uint32_t *d_stmunf, *d_strows; uint8_t* d_ovf; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
+    uint32_t *d_stmunf, *d_strows; uint8_t* d_ovf;
     B200C_TRY(ws_typed(c, WS_STMUNF, nparts + 1, &d_stmunf));
     B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
     B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
@@ -778,9 +808,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             B200C_CUDA_TRY(c, cudaMemsetAsync(d_ovf, 0, nparts, st));
             B200C_TRY(launch_k4(0));
         } else {
-            B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
-            B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
-            B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound);
             B200C_TRY(exclusive_scan<uint64_t>(c, d_bound, nparts, d_bpos, WS_SCANA, 0));
             B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_bpos + nparts, 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));

@@ -74,7 +74,7 @@ struct Rd {
     const uint8_t* U; uint64_t p, end; int err;
     __device__ __forceinline__ uint32_t u8() { if (p >= end) { err = PERR_CORRUPT; return 1; } return U[p++]; }
     __device__ __forceinline__ uint32_t be16() { uint32_t a = u8(); return (a << 8) | u8(); }
-    __device__ __forceinline__ uint64_t vint() {
+    __device__ __noinline__ uint64_t vint() {
         if (p >= end) { err = PERR_CORRUPT; return 0; }
         uint32_t first = U[p];
         if (first < 0x80) { p++; return first; }
@@ -97,7 +97,7 @@ template <bool EMIT> struct Sink {
     __device__ __forceinline__ void be16(uint32_t v) { u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be64(uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); }
-    __device__ __forceinline__ void vint(uint64_t v) {
+    __device__ __noinline__ void vint(uint64_t v) {
         int size = vint_size(v);
         if (EMIT && on && pos + size <= cap) {
             if (size == 1) base[pos] = (uint8_t)v;
@@ -108,7 +108,7 @@ template <bool EMIT> struct Sink {
         }
         pos += size;
     }
-    __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on && pos + n <= cap) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
+    __device__ __noinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on && pos + n <= cap) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
 };
 
 struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialised clustering values (header vint + values) in U
@@ -311,7 +311,7 @@ template <bool EMIT> __device__ __forceinline__ void pw_end_unf(PWriter<EMIT>& w
 }
 
 // row body: UnfilteredSerializer.serializeRowBody :213-269 + Cell.Serializer.serialize S/db/rows/Cell.java:268-305
-template <bool E> __device__ void put_row_body(Sink<E>& s, const CParams& P, int flags, const Live& info, const DT& del, const MCell* cells, int ncells_present) {
+template <bool E> __device__ __noinline__ void put_row_body(Sink<E>& s, const CParams& P, int flags, const Live& info, const DT& del, const MCell* cells, int ncells_present) {
     if (flags & 0x04) s.vint((uint64_t)info.ts - (uint64_t)P.o_min_ts);
     if (flags & 0x08) { s.vint((uint64_t)(int64_t)(info.ttl - P.o_min_ttl)); s.vint((uint64_t)(int64_t)(int32_t)(info.ldt - P.o_min_ldt)); }
     if (flags & 0x10) write_delta_dt(s, P, del);
@@ -493,89 +493,84 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     w.ix.base = (EMIT && iout) ? iout + pre : nullptr; w.ix.pos = 0;
     w.ix_offs = (EMIT && iout) ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
 
-    if (m == 1) {
-        // single source: TrivialOneToOne (UnfilteredRowIterators.java:552-556) — no Row.Merger, only the purge transformation
-        Cur& c = cur[0];
-        for (;;) {
-            cur_load(P, c, err);
-            if (err || c.done) break;
-            st.merged_unfiltereds++;
-            CkRef ck{c.pos + c.ck_rel, c.ckend_rel - c.ck_rel, c.kind, c.n};
-            if (c.flags & 0x02) {
-                DT mc, mo; read_marker_dts(P, c, mc, mo, err); if (err) break;
-                if (purge_marker(pg, ck.kind, mc, mo)) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_marker(w, P, ck, mc, mo); }
-            } else {
-                Live info; DT del; Rd r = row_header(P, c, info, del);
-                for (int k = 0; k < P.ncols; k++) merged[k].present = false;
-                fold_cells(P, c, r, info, false, dt_live(), merged, err); if (r.err) err = r.err; if (err) break;
-                int present = purge_row(P, pg, info, del, merged);
-                if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
-            }
-            c.pos = c.next;
-        }
-    } else {
-        uint64_t has_open = 0; int biggest = -1;
-        for (uint32_t v = 0; v < m; v++) cur_load(P, cur[v], err);
-        while (!err) {
-            int b = -1;
-            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && (b < 0 || cmp_heads(P, cur[v], cur[b]) < 0)) b = (int)v;
-            if (b < 0) break;
-            uint64_t grp = 0; int gcount = 0, last = b;
-            for (uint32_t v = 0; v < m; v++) if (!cur[v].done && ((int)v == b || cmp_heads(P, cur[v], cur[b]) == 0)) { grp |= 1ull << v; gcount++; last = (int)v; }
-            // current open deletion in the merged stream (RangeTombstoneMarker.Merger.currentOpenDeletionTimeInMerged :160-168)
-            DT cur_open = (biggest >= 0 && dt_supersedes(open_dt[biggest], pdel)) ? open_dt[biggest] : dt_live();
-            if (!(cur[b].flags & 0x02)) {
-                DT active = dt_is_live(cur_open) ? pdel : cur_open;          // activeDeletion() :191-197
-                Live info = live_empty(); DT del = dt_live();
-                for (int k = 0; k < P.ncols; k++) merged[k].present = false;
-                bool as_is = (gcount == 1) && dt_is_live(active);            // Row.Merger.merge :734-739
-                for (uint32_t v = 0; v < m; v++) if ((grp >> v) & 1) {
+    // One code path for every fan-in. m == 1 is the reference's TrivialOneToOne case (UnfilteredRowIterators.java:552-556): rows
+    // and markers pass through untouched (no Row.Merger, no marker merger) and only the purge transformation applies.
+    const bool multi = m > 1;
+    uint64_t has_open = 0; int biggest = -1;
+    DT cur_open = dt_live();                       // open deletion in the merged stream
+    for (uint32_t v = 0; v < m; v++) cur_load(P, cur[v], err);
+    while (!err) {
+        int b = -1;
+        for (uint32_t v = 0; v < m; v++) if (!cur[v].done && (b < 0 || cmp_heads(P, cur[v], cur[b]) < 0)) b = (int)v;
+        if (b < 0) break;
+        uint64_t grp = 1ull << b; int gcount = 1, last = b;
+        for (uint32_t v = b + 1; v < m; v++) if (!cur[v].done && cmp_heads(P, cur[v], cur[b]) == 0) { grp |= 1ull << v; gcount++; last = (int)v; }
+        if (!(cur[b].flags & 0x02)) {
+            DT active = multi ? (dt_is_live(cur_open) ? pdel : cur_open) : dt_live();      // activeDeletion() :191-197
+            const bool as_is = !multi || ((gcount == 1) && dt_is_live(active));            // Row.Merger.merge :734-739
+            Live info = live_empty(); DT del = dt_live();
+            for (int k = 0; k < P.ncols; k++) merged[k].present = false;
+            if (gcount > 1) {
+                for (uint64_t bits = grp; bits; bits &= bits - 1) {
+                    int v = __ffsll((long long)bits) - 1;
                     Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) err = r.err;
                     if (live_supersedes(vi, info)) info = vi;
                     if (dt_supersedes(vd, del)) del = vd;
                 }
-                if (!as_is) {
-                    if (dt_supersedes(del, active)) active = del; else del = dt_live();
-                    if (dt_deletes(active, info.ts)) info = live_empty();
-                }
-                for (uint32_t v = 0; v < m && !err; v++) if ((grp >> v) & 1) {
-                    Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd);
-                    fold_cells(P, cur[v], r, vi, !as_is, active, merged, err); if (r.err) err = r.err;
-                }
-                if (err) break;
-                int npresent = 0; for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;
-                bool have = !(live_is_empty(info) && dt_is_live(del) && npresent == 0);
-                if (have) {
-                    st.merged_unfiltereds++;
-                    Cur& f = cur[b];
-                    CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, K_CLUSTERING, f.n};
-                    int present = purge_row(P, pg, info, del, merged);
-                    if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
-                }
-            } else {
+            }
+            if (!as_is) {
+                if (dt_supersedes(del, active)) active = del; else del = dt_live();
+                if (dt_deletes(active, info.ts)) info = live_empty();
+            }
+            for (uint64_t bits = grp; bits && !err; bits &= bits - 1) {
+                int v = __ffsll((long long)bits) - 1;
+                Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd);
+                if (gcount == 1) { if (as_is) { info = vi; del = vd; } else { /* single version under an active deletion */
+                        info = vi; del = vd;
+                        if (dt_supersedes(del, active)) active = del; else del = dt_live();
+                        if (dt_deletes(active, info.ts)) info = live_empty(); } }
+                fold_cells(P, cur[v], r, vi, !as_is, active, merged, err); if (r.err) err = r.err;
+            }
+            if (err) break;
+            int npresent = 0; for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;
+            if (!(live_is_empty(info) && dt_is_live(del) && npresent == 0)) {
+                st.merged_unfiltereds++;
+                Cur& f = cur[b];
+                CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, K_CLUSTERING, f.n};
+                int present = purge_row(P, pg, info, del, merged);
+                if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
+            }
+        } else {
+            Cur& f = cur[last];                                       // `bound` = clustering of the last marker added (:99-103)
+            CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, f.kind, f.n};
+            DT mc = dt_live(), mo = dt_live(); bool emit = false;
+            if (!multi) { read_marker_dts(P, f, mc, mo, err); emit = true; }
+            else {
                 // RangeTombstoneMarker.Merger.merge :94-153
-                for (uint32_t v = 0; v < m; v++) if ((grp >> v) & 1) {
-                    DT mc, mo; read_marker_dts(P, cur[v], mc, mo, err);
+                for (uint64_t bits = grp; bits; bits &= bits - 1) {
+                    int v = __ffsll((long long)bits) - 1;
+                    DT a, o; read_marker_dts(P, cur[v], a, o, err);
                     bool is_open = kind_is_boundary(cur[v].kind) || kind_is_start(cur[v].kind);
-                    if (is_open) { open_dt[v] = mo; has_open |= 1ull << v; } else has_open &= ~(1ull << v);
+                    if (is_open) { open_dt[v] = o; has_open |= 1ull << v; } else has_open &= ~(1ull << v);
                 }
                 biggest = -1;
-                for (uint32_t v = 0; v < m; v++) if (((has_open >> v) & 1) && (biggest < 0 || dt_supersedes(open_dt[v], open_dt[biggest]))) biggest = (int)v;
+                for (uint64_t bits = has_open; bits; bits &= bits - 1) { int v = __ffsll((long long)bits) - 1; if (biggest < 0 || dt_supersedes(open_dt[v], open_dt[biggest])) biggest = v; }
                 DT now_open = (biggest >= 0 && dt_supersedes(open_dt[biggest], pdel)) ? open_dt[biggest] : dt_live();
-                if (!dt_eq(cur_open, now_open) && !err) {
-                    st.merged_unfiltereds++;
-                    Cur& f = cur[last];                                       // `bound` = clustering of the last marker added (:99-103)
+                if (!dt_eq(cur_open, now_open)) {
                     bool before = kind_vs_clustering(f.kind) < 0;
-                    CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, 0, f.n};
-                    DT mc = dt_live(), mo = dt_live();
                     if (dt_is_live(cur_open)) { ck.kind = before ? K_INCL_START : K_EXCL_START; mo = now_open; }
                     else if (dt_is_live(now_open)) { ck.kind = before ? K_EXCL_END : K_INCL_END; mc = cur_open; }
                     else { ck.kind = before ? K_EXCL_END_INCL_START : K_INCL_END_EXCL_START; mc = cur_open; mo = now_open; }
-                    if (purge_marker(pg, ck.kind, mc, mo)) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_marker(w, P, ck, mc, mo); }
+                    emit = true;
                 }
+                cur_open = now_open;
             }
-            for (uint32_t v = 0; v < m; v++) if ((grp >> v) & 1) { cur[v].pos = cur[v].next; cur_load(P, cur[v], err); }
+            if (emit && !err) {
+                st.merged_unfiltereds++;
+                if (purge_marker(pg, ck.kind, mc, mo)) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_marker(w, P, ck, mc, mo); }
+            }
         }
+        for (uint64_t bits = grp; bits; bits &= bits - 1) { int v = __ffsll((long long)bits) - 1; cur[v].pos = cur[v].next; cur_load(P, cur[v], err); }
     }
     if (err) return;
     // partition.isEmpty() (UnfilteredRowIterator.java:63-68) / SortedTableWriter.append :134

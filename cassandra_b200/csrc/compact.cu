@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restric
     if (valid) list[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)j;
 }
 
-enum { SLOT_BYTES = sizeof(Cur) };          // per-source cursor in shared memory
+enum { SLOT_BYTES = sizeof(Cur), K4_SMEM_COLS = 8 };          // per-source cursor in shared memory
 
 // mode 0: size pass only (EMIT = false). mode 1: the single serialisation pass — bytes go to scratch at dbase + doff[j] (capacity
 // dcapv[j]), sizes/stats are recorded, no Index.db. mode 2: final emit of every written partition at dbase + dpos[j] with its Index.db
@@ -433,9 +433,13 @@ template <bool EMIT> __device__ __forceinline__ void k4_epilogue(const K4Args& a
 template <int M_CAP, int NT, bool EMIT>
 __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t lo, uint64_t hi) {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    constexpr int STRIDE = M_CAP * SLOT_BYTES + 8;       // +8: spread the threads over the banks
-    Cur* cur = (Cur*)(s_raw + (size_t)threadIdx.x * STRIDE);
-    MCell merged[MAXCOLS];
+    // per thread in shared memory: M_CAP cursors, then (for tables with <= K4_SMEM_COLS columns) the merged-row scratch; +8 bytes
+    // so that consecutive threads start in different banks. Wider tables keep the merged row in local memory.
+    const int ncols_s = a.P->ncols <= K4_SMEM_COLS ? a.P->ncols : 0;
+    const int stride = M_CAP * SLOT_BYTES + ncols_s * (int)sizeof(MCell) + 8;
+    Cur* cur = (Cur*)(s_raw + (size_t)threadIdx.x * stride);
+    MCell merged_local[MAXCOLS];
+    MCell* merged = ncols_s ? (MCell*)(cur + M_CAP) : merged_local;
     DT open_dt[M_CAP];                                   // only touched when the partition holds range tombstone markers
     uint64_t t = lo + (uint64_t)blockIdx.x * NT + threadIdx.x;
     if (t >= hi) return;
@@ -763,7 +767,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_STMUNF, nparts + 1, &d_stmunf));
     B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
     B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
-    const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
+    const size_t cols_s = m->ncolumns <= K4_SMEM_COLS ? (size_t)m->ncolumns * sizeof(MCell) : 0;
+    const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
     static const bool two_pass = getenv("B200C_K4_TWO_PASS") != nullptr;     // A/B switch: size pass + full emit pass instead of scratch + gather
     K4Args ka; memset(&ka, 0, sizeof(ka));
     ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase;
@@ -795,12 +800,12 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         return B200C_OK;
     };
-    if (!c->k4_attr_set) {      // > 48 KiB of dynamic shared memory needs an explicit opt-in, once per context/device
+    if (c->k4_attr_set != (int)(smem8 + 1)) {      // > 48 KiB of dynamic shared memory needs an explicit opt-in, once per context/device
         cudaFuncSetAttribute(k_partition_thr<8, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
         cudaFuncSetAttribute(k_partition_thr<8, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
         cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
         cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
-        c->k4_attr_set = true;
+        c->k4_attr_set = (int)(smem8 + 1);
     }
     uint8_t* SCRATCH = nullptr;
     if (nparts) {

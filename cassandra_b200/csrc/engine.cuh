@@ -33,7 +33,7 @@ struct b200c_ctx {
     cudaEvent_t ev_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int nstages = 0;
-    bool k4_attr_set = false;
+    int k4_attr_set = 0;
 };
 
 namespace b200c {

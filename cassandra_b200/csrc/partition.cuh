@@ -69,21 +69,41 @@ __device__ __forceinline__ int kind_vs_clustering(int k) { return k < 4 ? -1 : (
 __device__ __forceinline__ bool kind_is_boundary(int k) { return k == K_EXCL_END_INCL_START || k == K_INCL_END_EXCL_START; }
 __device__ __forceinline__ bool kind_is_start(int k) { return k == K_INCL_START || k == K_EXCL_START; }
 
+// vint decode / encode as free functions with by-value arguments and results: member functions that are not inlined would take
+// `this`, which forces the reader / sink / writer objects out of registers and into local memory.
+struct VintR { uint64_t v; uint32_t n; };
+__device__ __noinline__ VintR vint_decode(const uint8_t* p, uint32_t avail) {      // avail = bytes readable at p (capped at 9)
+    VintR r; r.v = 0; r.n = 0;
+    if (!avail) return r;
+    uint32_t first = p[0];
+    if (first < 0x80) { r.v = first; r.n = 1; return r; }
+    uint32_t extra = __clz((int)(~(first << 24)));
+    if (1 + extra > avail) return r;
+    uint64_t v = first & (0xffu >> extra);
+    for (uint32_t i = 0; i < extra; i++) v = (v << 8) | p[1 + i];
+    r.v = v; r.n = 1 + extra; return r;
+}
+__device__ __noinline__ void vint_store(uint8_t* dst, uint64_t v, int size) {
+    if (size == 1) { dst[0] = (uint8_t)v; return; }
+    if (size < 9) {
+        uint64_t reg = (v << ((8 - size) << 3)) | ((uint64_t)(uint8_t)(~(0xffu >> (size - 1))) << 56);
+        for (int i = 0; i < size; i++) dst[i] = (uint8_t)(reg >> (56 - 8 * i));
+        return;
+    }
+    dst[0] = 0xFF; for (int i = 0; i < 8; i++) dst[1 + i] = (uint8_t)(v >> (56 - 8 * i));
+}
+__device__ __noinline__ void bytes_copy(uint8_t* dst, const uint8_t* src, uint32_t n) { for (uint32_t i = 0; i < n; i++) dst[i] = src[i]; }
+
 // ---- bounded reader over U ------------------------------------------------------------------------------------------------
 struct Rd {
     const uint8_t* U; uint64_t p, end; int err;
     __device__ __forceinline__ uint32_t u8() { if (p >= end) { err = PERR_CORRUPT; return 1; } return U[p++]; }
     __device__ __forceinline__ uint32_t be16() { uint32_t a = u8(); return (a << 8) | u8(); }
-    __device__ __noinline__ uint64_t vint() {
-        if (p >= end) { err = PERR_CORRUPT; return 0; }
-        uint32_t first = U[p];
-        if (first < 0x80) { p++; return first; }
-        int extra = __clz((int)(~(first << 24)));
-        if (p + 1 + extra > end) { err = PERR_CORRUPT; p = end; return 0; }
-        uint64_t r = first & (0xffu >> extra);
-        for (int i = 0; i < extra; i++) r = (r << 8) | U[p + 1 + i];
-        p += 1 + extra;
-        return r;
+    __device__ __forceinline__ uint64_t vint() {
+        uint64_t left = end - p;
+        VintR r = vint_decode(U + p, p < end ? (uint32_t)(left < 9 ? left : 9) : 0u);
+        if (!r.n) { err = PERR_CORRUPT; p = end; return 0; }
+        p += r.n; return r.v;
     }
     __device__ __forceinline__ int32_t vint32() { uint64_t v = vint(); int32_t r = (int32_t)v; if ((int64_t)r != (int64_t)v) err = PERR_CORRUPT; return r; }
     __device__ __forceinline__ void skip(uint64_t n) { if (end - p < n) { err = PERR_CORRUPT; p = end; } else p += n; }
@@ -97,18 +117,12 @@ template <bool EMIT> struct Sink {
     __device__ __forceinline__ void be16(uint32_t v) { u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
     __device__ __forceinline__ void be64(uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); }
-    __device__ __noinline__ void vint(uint64_t v) {
+    __device__ __forceinline__ void vint(uint64_t v) {
         int size = vint_size(v);
-        if (EMIT && on && pos + size <= cap) {
-            if (size == 1) base[pos] = (uint8_t)v;
-            else if (size < 9) {
-                uint64_t reg = (v << ((8 - size) << 3)) | ((uint64_t)(uint8_t)(~(0xffu >> (size - 1))) << 56);
-                for (int i = 0; i < size; i++) base[pos + i] = (uint8_t)(reg >> (56 - 8 * i));
-            } else { base[pos] = 0xFF; for (int i = 0; i < 8; i++) base[pos + 1 + i] = (uint8_t)(v >> (56 - 8 * i)); }
-        }
+        if (EMIT && on && pos + size <= cap) vint_store(base + pos, v, size);
         pos += size;
     }
-    __device__ __noinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on && pos + n <= cap) for (uint32_t i = 0; i < n; i++) base[pos + i] = src[i]; pos += n; }
+    __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on && pos + n <= cap) bytes_copy(base + pos, src, n); pos += n; }
 };
 
 struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialised clustering values (header vint + values) in U
@@ -123,19 +137,20 @@ struct Cur {                       // cursor of one contributing input partition
 };
 
 // parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
-__device__ __noinline__ void cur_load(const CParams& P, Cur& c, int& err) {
+__device__ __noinline__ int cur_load_impl(const CParams& P, Cur& c) {
+    int err = 0;
     for (;;) {
         Rd r{P.U, c.pos, c.end, 0};
         uint32_t flags = r.u8();
-        if (r.err) { err = PERR_CORRUPT; c.done = true; return; }
-        if (flags & 0x01) { c.done = true; c.next = r.p; return; }
+        if (r.err) { c.done = true; return PERR_CORRUPT; }
+        if (flags & 0x01) { c.done = true; c.next = r.p; return 0; }
         c.flags = (uint8_t)flags; c.ext = 0;
         if (flags & 0x02) {
             c.kind = (uint8_t)r.u8(); c.n = (uint8_t)r.be16();
-            if (c.kind > 7 || c.kind == K_STATIC || c.kind == K_CLUSTERING || c.n > P.nclust) { err = PERR_CORRUPT; c.done = true; return; }
+            if (c.kind > 7 || c.kind == K_STATIC || c.kind == K_CLUSTERING || c.n > P.nclust) { c.done = true; return PERR_CORRUPT; }
         } else {
             if (flags & 0x80) c.ext = (uint8_t)r.u8();
-            if ((c.ext & 0x03) || (flags & 0x40)) { err = PERR_UNSUPPORTED; c.done = true; return; }
+            if ((c.ext & 0x03) || (flags & 0x40)) { c.done = true; return PERR_UNSUPPORTED; }
             c.kind = K_CLUSTERING; c.n = (uint8_t)P.nclust;
         }
         c.ck_rel = (uint8_t)(r.p - c.pos);
@@ -163,16 +178,17 @@ __device__ __noinline__ void cur_load(const CParams& P, Cur& c, int& err) {
         r.vint();                                   // previous unfiltered size
         c.body_rel = (uint32_t)(r.p - c.pos);
         c.next = after + sz;
-        if (r.err || c.next > c.end || c.next < r.p) { err = PERR_CORRUPT; c.done = true; return; }
+        if (r.err || c.next > c.end || c.next < r.p) { c.done = true; return PERR_CORRUPT; }
         if (!(flags & 0x02) && !(flags & 0x14)) {   // maybe an empty row: no liveness, no deletion — any cells?
             int ncin = P.in[c.src].ncols; bool any;
             if (flags & 0x20) any = ncin > 0;
             else { Rd b{P.U, c.pos + c.body_rel, c.next, 0}; uint64_t missing = b.vint(); uint64_t mask = ncin >= 64 ? ~0ull : ((1ull << ncin) - 1); any = ((~missing) & mask) != 0; }
             if (!any) { c.pos = c.next; continue; }
         }
-        return;
+        return err;
     }
 }
+__device__ __forceinline__ void cur_load(const CParams& P, Cur& c, int& err) { int e = cur_load_impl(P, c); if (e) err = e; }
 
 __device__ __forceinline__ int cmp_bytes(const uint8_t* a, int la, const uint8_t* b, int lb) {
     int n = la < lb ? la : lb;
@@ -284,7 +300,7 @@ template <bool EMIT> __device__ __forceinline__ void write_prefix(Sink<EMIT>& s,
     s.copy(P.U + c.off, c.len);
 }
 
-template <bool EMIT> __device__ __noinline__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
+template <bool EMIT> __device__ __forceinline__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
     uint64_t cur = w.d.pos - w.start;
     bool emit_info = EMIT && w.ix.on;              // ix.on: this lane stores IndexInfos (final emit of a partition with > 1 block)
     if (emit_info) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
@@ -311,7 +327,7 @@ template <bool EMIT> __device__ __forceinline__ void pw_end_unf(PWriter<EMIT>& w
 }
 
 // row body: UnfilteredSerializer.serializeRowBody :213-269 + Cell.Serializer.serialize S/db/rows/Cell.java:268-305
-template <bool E> __device__ __noinline__ void put_row_body(Sink<E>& s, const CParams& P, int flags, const Live& info, const DT& del, const MCell* cells, int ncells_present) {
+template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const CParams& P, int flags, Live info, DT del, const MCell* cells) {
     if (flags & 0x04) s.vint((uint64_t)info.ts - (uint64_t)P.o_min_ts);
     if (flags & 0x08) { s.vint((uint64_t)(int64_t)(info.ttl - P.o_min_ttl)); s.vint((uint64_t)(int64_t)(int32_t)(info.ldt - P.o_min_ldt)); }
     if (flags & 0x10) write_delta_dt(s, P, del);
@@ -332,6 +348,7 @@ template <bool E> __device__ __noinline__ void put_row_body(Sink<E>& s, const CP
         if (expiring && !use_ttl) s.vint((uint64_t)(int64_t)(m.ttl - P.o_min_ttl));
         if (has_value) { if (P.vfix[c] <= 0) s.vint((uint64_t)m.vlen); s.copy(P.U + m.voff, (uint32_t)m.vlen); }
     }
+    return s.pos;
 }
 
 struct PartStats { uint64_t merged_unfiltereds; uint64_t rows_out; };
@@ -348,7 +365,7 @@ __device__ __forceinline__ Rd row_header(const CParams& P, const Cur& c, Live& i
 }
 
 // folds the cells of the row at cursor `c` into merged[] (ColumnDataReducer.getReduced :838-849)
-__device__ __noinline__ void fold_cells(const CParams& P, const Cur& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
+__device__ __noinline__ int fold_cells_impl(const CParams& P, const Cur& c, Rd r, Live info, bool apply_deletion, DT active, MCell* merged) {
     const InDesc& in = P.in[c.src];
     uint64_t missing = 0;
     if (!(c.flags & 0x20)) missing = r.vint();
@@ -369,14 +386,18 @@ __device__ __noinline__ void fold_cells(const CParams& P, const Cur& c, Rd& r, c
         }
         if (m.ttl < 0) r.err = PERR_CORRUPT;
         if (m.ldt != I64_MAX) m.ldt = decode_ldt(m.ldt, m.ttl);
-        if (r.err) { err = r.err; return; }
+        if (r.err) return r.err;
         if (apply_deletion && dt_deletes(active, m.ts)) continue;
         if (!merged[oc].present || !reconcile_keep_left(P, merged[oc], m)) merged[oc] = m;
     }
+    return r.err;
+}
+__device__ __forceinline__ void fold_cells(const CParams& P, const Cur& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
+    int e = fold_cells_impl(P, c, r, info, apply_deletion, active, merged); if (e) err = e;
 }
 
 // BTreeRow.purge :457-499 + AbstractCell.purge :78-99. Returns the number of surviving cells, or -1 when the row disappears.
-__device__ __noinline__ int purge_row(const CParams& P, const Purger& pg, Live& info, DT& del, MCell* cells) {
+__device__ __forceinline__ int purge_row(const CParams& P, const Purger& pg, Live& info, DT& del, MCell* cells) {
     if (pg.live(info)) info = live_empty();
     if (pg.dt(del)) del = dt_live();
     int present = 0;
@@ -401,7 +422,7 @@ template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, 
     w.header_len = w.d.pos - w.start; w.started = true;
 }
 
-template <bool EMIT> __device__ __noinline__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
+template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
     int flags = 0;
     if (!live_is_empty(info)) flags |= 0x04;
     if (info.ttl != 0) flags |= 0x08;
@@ -409,19 +430,19 @@ template <bool EMIT> __device__ __noinline__ void write_row(PWriter<EMIT>& w, co
     if (present == P.ncols) flags |= 0x20;
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
-    Sink<false> cs{nullptr, 0, false, 0};
-    put_row_body(cs, P, flags, info, del, cells, present);
+    Sink<EMIT> cs{nullptr, 0, false, 0};                       // same instantiation as the real sink, stores off: counts the body
+    uint64_t body = put_row_body(cs, P, flags, info, del, cells);
     w.d.u8(flags); w.d.copy(P.U + ck.off, ck.len);
-    w.d.vint(cs.pos + vint_size(prev)); w.d.vint(prev);
-    put_row_body(w.d, P, flags, info, del, cells, present);
+    w.d.vint(body + vint_size(prev)); w.d.vint(prev);
+    w.d.pos = put_row_body(w.d, P, flags, info, del, cells);
     pw_end_unf(w, P, ck, pos);
 }
 
 // UnfilteredSerializer.serialize(RangeTombstoneMarker) :282-305
-template <bool EMIT> __device__ __noinline__ void write_marker(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const DT& m_close, const DT& m_open) {
+template <bool EMIT> __device__ __forceinline__ void write_marker(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const DT& m_close, const DT& m_open) {
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
-    Sink<false> cs{nullptr, 0, false, 0};
+    Sink<EMIT> cs{nullptr, 0, false, 0};
     bool boundary = kind_is_boundary(ck.kind), start = kind_is_start(ck.kind);
     if (boundary) { write_delta_dt(cs, P, m_close); write_delta_dt(cs, P, m_open); } else write_delta_dt(cs, P, start ? m_open : m_close);
     w.d.u8(0x02); w.d.u8(ck.kind); w.d.be16(ck.n); w.d.copy(P.U + ck.off, ck.len);

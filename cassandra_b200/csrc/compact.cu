@@ -590,12 +590,18 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_CUDA_TRY(c, cudaMemcpyAsync(d_bbase, bbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
     cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     uint64_t bytes_read = 0;
+    // inputs are staged on a second stream, one event per input, so that K1 of input i overlaps the copy of input i+1
+    // (the workspace was possibly re-allocated above: make sure that is ordered before the copies)
+    cudaStream_t cs = c->copy_stream;
+    B200C_CUDA_TRY(c, cudaEventRecord(c->ev0, st));
+    B200C_CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev0, 0));
     for (int i = 0; i < K; i++) {
         const b200c_input& in = m->inputs[i];
         bytes_read += in.data_length;
-        if (in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, st));
-        if (in.index_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index, in.index_len, kind, st));
-        if (in.nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(CO + obase[i], in.chunk_offsets, in.nchunks * 8, kind, st));
+        if (in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, cs));
+        if (in.nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(CO + obase[i], in.chunk_offsets, in.nchunks * 8, kind, cs));
+        if (in.index_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index, in.index_len, kind, cs));
+        B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[i], cs));
     }
     c->prog_total.store(bytes_read); c->prog_scanned.store(0);
     timing_begin(c);
@@ -607,6 +613,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     for (int i = 0; i < K; i++) {
         const b200c_input& in = m->inputs[i];
         if (in.compressor != COMP_LZ4 && in.compressor != COMP_SNAPPY && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
+        B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0));
         B200C_TRY(decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
                                            in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr));
     }

@@ -109,6 +109,8 @@ b200c_ctx* b200c_create(int device, size_t workspace_bytes) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     for (auto& e : c->ev_stage) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (auto& e : c->ev_in) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     DevTables* h = new DevTables(); build_tables(h);
     if (cudaMalloc(&c->d_tables, sizeof(DevTables)) != cudaSuccess) { delete h; delete c; return nullptr; }
     cudaMemcpy(c->d_tables, h, sizeof(DevTables), cudaMemcpyHostToDevice);
@@ -130,6 +132,8 @@ void b200c_destroy(b200c_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (auto& e : c->ev_stage) cudaEventDestroy(e);
+    for (auto& e : c->ev_in) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }

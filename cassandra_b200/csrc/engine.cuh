@@ -34,6 +34,8 @@ struct b200c_ctx {
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int nstages = 0;
     int k4_attr_set = 0;
+    cudaStream_t copy_stream = nullptr;            // host->device staging of the inputs, overlapped with K1 input by input
+    cudaEvent_t ev_in[64] = {};
 };
 
 namespace b200c {

@@ -121,6 +121,26 @@ __device__ __forceinline__ uint32_t warp_crc32(const DevTables* T, const uint32_
     return ~(raw ^ init);
 }
 
+// 8 bytes at an arbitrary address as a big-endian integer (p[0] in the most significant byte): two aligned 8-byte loads + shifts.
+// Reads up to 15 bytes past p's 8-byte-aligned start: every engine buffer carries >= 64 bytes of slack.
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+__device__ __forceinline__ uint64_t load_be64(const uint8_t* p) {
+    uintptr_t a = (uintptr_t)p; const uint64_t* q = (const uint64_t*)(a & ~(uintptr_t)7); uint32_t sh = (uint32_t)(a & 7) * 8;
+    uint64_t lo = q[0];
+    if (sh) lo = (lo >> sh) | (q[1] << (64 - sh));
+    return bswap64(lo);
+}
+// 16 bytes at an arbitrary address as two big-endian words (three aligned 8-byte loads)
+__device__ __forceinline__ void load_be128(const uint8_t* p, uint64_t& w0, uint64_t& w1) {
+    uintptr_t a = (uintptr_t)p; const uint64_t* q = (const uint64_t*)(a & ~(uintptr_t)7); uint32_t sh = (uint32_t)(a & 7) * 8;
+    uint64_t q0 = q[0], q1 = q[1];
+    if (sh) { uint64_t q2 = q[2]; q0 = (q0 >> sh) | (q1 << (64 - sh)); q1 = (q1 >> sh) | (q2 << (64 - sh)); }
+    w0 = bswap64(q0); w1 = bswap64(q1);
+}
+
 // unaligned little-endian 32-bit read from a 4-byte aligned base (shared or global); needs base[.. p+7] readable
 __device__ __forceinline__ uint32_t rd32_at(const uint32_t* base32, int p) {
     uint32_t lo = base32[p >> 2];

@@ -71,18 +71,6 @@ __device__ __forceinline__ bool kind_is_start(int k) { return k == K_INCL_START 
 
 // vint decode / encode as free functions with by-value arguments and results: member functions that are not inlined would take
 // `this`, which forces the reader / sink / writer objects out of registers and into local memory.
-struct VintR { uint64_t v; uint32_t n; };
-__device__ __noinline__ VintR vint_decode(const uint8_t* p, uint32_t avail) {      // avail = bytes readable at p (capped at 9)
-    VintR r; r.v = 0; r.n = 0;
-    if (!avail) return r;
-    uint32_t first = p[0];
-    if (first < 0x80) { r.v = first; r.n = 1; return r; }
-    uint32_t extra = __clz((int)(~(first << 24)));
-    if (1 + extra > avail) return r;
-    uint64_t v = first & (0xffu >> extra);
-    for (uint32_t i = 0; i < extra; i++) v = (v << 8) | p[1 + i];
-    r.v = v; r.n = 1 + extra; return r;
-}
 __device__ __noinline__ void vint_store(uint8_t* dst, uint64_t v, int size) {
     if (size == 1) { dst[0] = (uint8_t)v; return; }
     if (size < 9) {
@@ -92,18 +80,44 @@ __device__ __noinline__ void vint_store(uint8_t* dst, uint64_t v, int size) {
     }
     dst[0] = 0xFF; for (int i = 0; i < 8; i++) dst[1 + i] = (uint8_t)(v >> (56 - 8 * i));
 }
-__device__ __noinline__ void bytes_copy(uint8_t* dst, const uint8_t* src, uint32_t n) { for (uint32_t i = 0; i < n; i++) dst[i] = src[i]; }
+__device__ __noinline__ void bytes_copy(uint8_t* dst, const uint8_t* src, uint32_t n) {
+    for (uint32_t i = 0; i < n; i += 8) {                // one wide (unaligned) load per 8 bytes, byte stores
+        uint64_t x = load_be64(src + i);
+        uint32_t k = n - i < 8 ? n - i : 8;
+        for (uint32_t b = 0; b < k; b++) dst[i + b] = (uint8_t)(x >> (56 - 8 * b));
+    }
+}
 
 // ---- bounded reader over U ------------------------------------------------------------------------------------------------
+// Sequential parser with a 16-byte register window [wb, wb+16) of U: header bytes and vints are extracted with shifts instead of
+// one global load per byte (the profile of the byte-wise version was dominated by vint byte loops and single-byte load latency).
 struct Rd {
     const uint8_t* U; uint64_t p, end; int err;
-    __device__ __forceinline__ uint32_t u8() { if (p >= end) { err = PERR_CORRUPT; return 1; } return U[p++]; }
+    uint64_t wb = ~0ull, w0 = 0, w1 = 0;
+    __device__ __forceinline__ void refill() { wb = p; load_be128(U + p, w0, w1); }
+    // 8 bytes starting at window offset d (0..8), big-endian
+    __device__ __forceinline__ uint64_t win64(uint32_t d) const { return d == 0 ? w0 : (d >= 8 ? w1 : ((w0 << (8 * d)) | (w1 >> (64 - 8 * d)))); }
+    __device__ __forceinline__ uint32_t u8() {
+        if (p >= end) { err = PERR_CORRUPT; return 1; }
+        uint64_t d = p - wb;
+        if (d >= 16) { refill(); d = 0; }
+        uint32_t b = (uint32_t)((d < 8 ? (w0 >> (56 - 8 * d)) : (w1 >> (120 - 8 * d))) & 0xff);
+        p++; return b;
+    }
     __device__ __forceinline__ uint32_t be16() { uint32_t a = u8(); return (a << 8) | u8(); }
     __device__ __forceinline__ uint64_t vint() {
-        uint64_t left = end - p;
-        VintR r = vint_decode(U + p, p < end ? (uint32_t)(left < 9 ? left : 9) : 0u);
-        if (!r.n) { err = PERR_CORRUPT; p = end; return 0; }
-        p += r.n; return r.v;
+        if (p >= end) { err = PERR_CORRUPT; return 0; }
+        uint64_t d = p - wb;
+        if (d > 6) { refill(); d = 0; }                  // up to 9 bytes are needed: keep d + 10 <= 16
+        uint64_t x = win64((uint32_t)d);                 // p[0..7]
+        uint32_t first = (uint32_t)(x >> 56);
+        if (first < 0x80) { p++; return first; }
+        uint32_t extra = __clz((int)(~(first << 24)));   // leading one bits = extra bytes (8 for 0xFF)
+        if (p + 1 + extra > end) { err = PERR_CORRUPT; p = end; return 0; }
+        p += 1 + extra;
+        if (extra == 8) return win64((uint32_t)d + 1);   // 0xFF + 8 raw bytes
+        uint32_t nbits = 8 * (extra + 1) - extra;        // value bits: n bytes minus the length prefix ones
+        return (x >> (8 * (7 - extra))) & ((1ull << nbits) - 1ull);
     }
     __device__ __forceinline__ int32_t vint32() { uint64_t v = vint(); int32_t r = (int32_t)v; if ((int64_t)r != (int64_t)v) err = PERR_CORRUPT; return r; }
     __device__ __forceinline__ void skip(uint64_t n) { if (end - p < n) { err = PERR_CORRUPT; p = end; } else p += n; }
@@ -162,8 +176,9 @@ __device__ __noinline__ int cur_load_impl(const CParams& P, Cur& c) {
                 uint64_t len = P.cfix[i] > 0 ? (uint64_t)P.cfix[i] : r.vint();
                 if (i == 0 && !r.err && r.end - r.p >= len) {
                     // first component, non-null and non-empty: big-endian prefix, sign bit flipped for the signed classes
-                    int t = P.ctype[0]; uint64_t k = 0; int take = len < 8 ? (int)len : 8;
-                    for (int b = 0; b < take; b++) k |= (uint64_t)P.U[r.p + b] << (56 - 8 * b);
+                    int t = P.ctype[0]; int take = len < 8 ? (int)len : 8;
+                    uint64_t k = load_be64(P.U + r.p);
+                    if (take < 8) k &= ~0ull << (8 * (8 - take));
                     if (t == TYPE_FIXED_SIGNED || t == TYPE_VAR_SIGNED) k ^= 0x8000000000000000ull;
                     c.k0 = k;
                     bool whole = (t == TYPE_FIXED_SIGNED || t == TYPE_FIXED_BYTES) && len <= 8;      // equal prefix <=> equal value
@@ -192,7 +207,12 @@ __device__ __forceinline__ void cur_load(const CParams& P, Cur& c, int& err) { i
 
 __device__ __forceinline__ int cmp_bytes(const uint8_t* a, int la, const uint8_t* b, int lb) {
     int n = la < lb ? la : lb;
-    for (int i = 0; i < n; i++) { int d = (int)a[i] - (int)b[i]; if (d) return d < 0 ? -1 : 1; }
+    for (int i = 0; i < n; i += 8) {                     // unsigned lexicographic order == big-endian integer order
+        uint64_t x = load_be64(a + i), y = load_be64(b + i);
+        int k = n - i;
+        if (k < 8) { uint64_t mk = ~0ull << (8 * (8 - k)); x &= mk; y &= mk; }
+        if (x != y) return x < y ? -1 : 1;
+    }
     return la == lb ? 0 : (la < lb ? -1 : 1);
 }
 __device__ __forceinline__ int cmp_value(int type, const uint8_t* a, int la, const uint8_t* b, int lb) {

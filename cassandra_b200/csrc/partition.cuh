@@ -91,10 +91,12 @@ __device__ __noinline__ void bytes_copy(uint8_t* dst, const uint8_t* src, uint32
 // ---- bounded reader over U ------------------------------------------------------------------------------------------------
 // Sequential parser with a 16-byte register window [wb, wb+16) of U: header bytes and vints are extracted with shifts instead of
 // one global load per byte (the profile of the byte-wise version was dominated by vint byte loops and single-byte load latency).
+struct U128 { uint64_t a, b; };
+__device__ __noinline__ U128 load_be128v(const uint8_t* p) { U128 r; load_be128(p, r.a, r.b); return r; }
 struct Rd {
     const uint8_t* U; uint64_t p, end; int err;
-    uint64_t wb = ~0ull, w0 = 0, w1 = 0;
-    __device__ __forceinline__ void refill() { wb = p; load_be128(U + p, w0, w1); }
+    uint64_t wb = 1ull << 63, w0 = 0, w1 = 0;        // wb far away from any offset: the first access refills
+    __device__ __forceinline__ void refill() { wb = p; U128 w = load_be128v(U + p); w0 = w.a; w1 = w.b; }
     // 8 bytes starting at window offset d (0..8), big-endian
     __device__ __forceinline__ uint64_t win64(uint32_t d) const { return d == 0 ? w0 : (d >= 8 ? w1 : ((w0 << (8 * d)) | (w1 >> (64 - 8 * d)))); }
     __device__ __forceinline__ uint32_t u8() {

@@ -89,37 +89,31 @@ __device__ __noinline__ void bytes_copy(uint8_t* dst, const uint8_t* src, uint32
 }
 
 // ---- bounded reader over U ------------------------------------------------------------------------------------------------
-// Sequential parser with a 16-byte register window [wb, wb+16) of U: header bytes and vints are extracted with shifts instead of
-// one global load per byte (the profile of the byte-wise version was dominated by vint byte loops and single-byte load latency).
-struct U128 { uint64_t a, b; };
-__device__ __noinline__ U128 load_be128v(const uint8_t* p) { U128 r; load_be128(p, r.a, r.b); return r; }
+// vint decode as a free noinline function with by-value result (one copy in the instruction cache, nothing forced to local
+// memory); the bytes of a multi-byte vint come from one unaligned 8-byte fetch instead of a byte loop.
+struct VintR { uint64_t v; uint32_t n; };
+__device__ __noinline__ VintR vint_decode(const uint8_t* p, uint32_t avail) {      // avail = bytes readable at p (capped at 9)
+    VintR r; r.v = 0; r.n = 0;
+    if (!avail) return r;
+    uint32_t first = p[0];
+    if (first < 0x80) { r.v = first; r.n = 1; return r; }
+    uint32_t extra = __clz((int)(~(first << 24)));                                 // leading one bits = extra bytes (8 for 0xFF)
+    if (1 + extra > avail) return r;
+    if (extra == 8) { r.v = load_be64(p + 1); r.n = 9; return r; }
+    uint64_t x = load_be64(p);                                                     // p[0..7], big-endian
+    uint32_t nbits = 8 * (extra + 1) - extra;                                      // value bits of the (extra + 1)-byte field
+    r.v = (x >> (8 * (7 - extra))) & ((1ull << nbits) - 1ull); r.n = 1 + extra;
+    return r;
+}
 struct Rd {
     const uint8_t* U; uint64_t p, end; int err;
-    uint64_t wb = 1ull << 63, w0 = 0, w1 = 0;        // wb far away from any offset: the first access refills
-    __device__ __forceinline__ void refill() { wb = p; U128 w = load_be128v(U + p); w0 = w.a; w1 = w.b; }
-    // 8 bytes starting at window offset d (0..8), big-endian
-    __device__ __forceinline__ uint64_t win64(uint32_t d) const { return d == 0 ? w0 : (d >= 8 ? w1 : ((w0 << (8 * d)) | (w1 >> (64 - 8 * d)))); }
-    __device__ __forceinline__ uint32_t u8() {
-        if (p >= end) { err = PERR_CORRUPT; return 1; }
-        uint64_t d = p - wb;
-        if (d >= 16) { refill(); d = 0; }
-        uint32_t b = (uint32_t)((d < 8 ? (w0 >> (56 - 8 * d)) : (w1 >> (120 - 8 * d))) & 0xff);
-        p++; return b;
-    }
+    __device__ __forceinline__ uint32_t u8() { if (p >= end) { err = PERR_CORRUPT; return 1; } return U[p++]; }
     __device__ __forceinline__ uint32_t be16() { uint32_t a = u8(); return (a << 8) | u8(); }
     __device__ __forceinline__ uint64_t vint() {
-        if (p >= end) { err = PERR_CORRUPT; return 0; }
-        uint64_t d = p - wb;
-        if (d > 6) { refill(); d = 0; }                  // up to 9 bytes are needed: keep d + 10 <= 16
-        uint64_t x = win64((uint32_t)d);                 // p[0..7]
-        uint32_t first = (uint32_t)(x >> 56);
-        if (first < 0x80) { p++; return first; }
-        uint32_t extra = __clz((int)(~(first << 24)));   // leading one bits = extra bytes (8 for 0xFF)
-        if (p + 1 + extra > end) { err = PERR_CORRUPT; p = end; return 0; }
-        p += 1 + extra;
-        if (extra == 8) return win64((uint32_t)d + 1);   // 0xFF + 8 raw bytes
-        uint32_t nbits = 8 * (extra + 1) - extra;        // value bits: n bytes minus the length prefix ones
-        return (x >> (8 * (7 - extra))) & ((1ull << nbits) - 1ull);
+        uint64_t left = end - p;
+        VintR r = vint_decode(U + p, p < end ? (uint32_t)(left < 9 ? left : 9) : 0u);
+        if (!r.n) { err = PERR_CORRUPT; p = end; return 0; }
+        p += r.n; return r.v;
     }
     __device__ __forceinline__ int32_t vint32() { uint64_t v = vint(); int32_t r = (int32_t)v; if ((int64_t)r != (int64_t)v) err = PERR_CORRUPT; return r; }
     __device__ __forceinline__ void skip(uint64_t n) { if (end - p < n) { err = PERR_CORRUPT; p = end; } else p += n; }

@@ -126,14 +126,16 @@ __global__ void k_digest_final(const DevTables* __restrict__ T, const uint64_t* 
 }
 
 // ---- K1: CRC verify + decompress ----------------------------------------------------------------------------------
-// grid = nchunks blocks of one warp; dynamic smem = chunk_len + 16
-__global__ void __launch_bounds__(32) k_decompress_chunks(const DevTables* __restrict__ T, int comp,
+// One warp per chunk, two chunks per block, NO shared-memory image: literals and matches are written straight to the output
+// stream in global memory and match sources are read back from it (a warp may read what its other lanes stored after
+// __syncwarp()). Dropping the 16 KiB staging buffer raises residency from 13 to 32 warps per SM, which is what this
+// latency-bound, strictly sequential format needs.
+__global__ void __launch_bounds__(64) k_decompress_chunks(const DevTables* __restrict__ T, int comp,
         const uint8_t* __restrict__ data, uint64_t data_len, const uint64_t* __restrict__ offs, uint64_t nchunks,
-        int chunk_len, int max_clen, uint64_t data_length, uint8_t* __restrict__ out, int verify, ChunkErr* __restrict__ err) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* s_out = smem;
-    const int lane = threadIdx.x;
-    const uint64_t chunk = blockIdx.x;
+        int chunk_len, int max_clen, uint64_t data_length, uint8_t* out, int verify, ChunkErr* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t chunk = (uint64_t)blockIdx.x * 2 + (threadIdx.x >> 5);
+    if (chunk >= nchunks) return;
     const uint64_t off = offs[chunk];
     const uint64_t next = (chunk + 1 < nchunks) ? offs[chunk + 1] : data_len;
     const uint64_t ustart = chunk * (uint64_t)chunk_len;
@@ -149,30 +151,22 @@ __global__ void __launch_bounds__(32) k_decompress_chunks(const DevTables* __res
         uint32_t stored = ((uint32_t)src[clen] << 24) | ((uint32_t)src[clen + 1] << 16) | ((uint32_t)src[clen + 2] << 8) | src[clen + 3];
         if (crc != stored) { if (lane == 0) report_chunk_err(err, chunk, 1); return; }
     }
+    uint8_t* dst = out + ustart;
     int got;
     if (clen >= max_clen) {                 // CompressedChunkReader.java:116,219: raw chunk (possibly zero padded at the file end)
         if (clen < ulen) { if (lane == 0) report_chunk_err(err, chunk, 2); return; }
-        for (int i = lane; i < ulen; i += 32) s_out[i] = src[i];
+        for (int i = lane; i < ulen; i += 32) dst[i] = src[i];
         got = ulen;
     } else if (comp == COMP_LZ4) {
         int plen = (clen >= 4) ? (int)((uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24)) : -1;
-        got = (plen == ulen) ? lz4_decompress_warp(src + 4, clen - 4, s_out, ulen, lane) : -1;
+        got = (plen == ulen) ? lz4_decompress_warp(src + 4, clen - 4, dst, ulen, lane) : -1;
     } else if (comp == COMP_SNAPPY) {
-        got = snappy_decompress_warp(src, clen, s_out, ulen, lane);
+        got = snappy_decompress_warp(src, clen, dst, ulen, lane);
     } else {
         got = (clen == ulen) ? ulen : -1;
-        if (got >= 0) for (int i = lane; i < ulen; i += 32) s_out[i] = src[i];
+        if (got >= 0) for (int i = lane; i < ulen; i += 32) dst[i] = src[i];
     }
-    if (got != ulen) { if (lane == 0) report_chunk_err(err, chunk, 2); return; }
-    __syncwarp();
-    uint8_t* dst = out + ustart;
-    if ((((uintptr_t)dst) & 15) == 0) {
-        int nv = ulen >> 4;
-        for (int i = lane; i < nv; i += 32) ((uint4*)dst)[i] = ((const uint4*)s_out)[i];
-        for (int i = (nv << 4) + lane; i < ulen; i += 32) dst[i] = s_out[i];
-    } else {
-        for (int i = lane; i < ulen; i += 32) dst[i] = s_out[i];
-    }
+    if (got != ulen && lane == 0) report_chunk_err(err, chunk, 2);
 }
 
 } // namespace b200c

@@ -83,8 +83,7 @@ int compress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
                              int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err) {
     if (nchunks == 0) return B200C_OK;
-    size_t smem = (size_t)chunk_len + 16;
-    B200C_LAUNCH(c, k_decompress_chunks, (unsigned)nchunks, 32, smem, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
+    B200C_LAUNCH(c, k_decompress_chunks, (unsigned)((nchunks + 1) / 2), 64, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
                  chunk_len, max_clen, data_length, d_out, verify, d_err);
     return B200C_OK;
 }
@@ -118,7 +117,6 @@ b200c_ctx* b200c_create(int device, size_t workspace_bytes) {
     c->h_pinned_cap = 1 << 16;
     if (cudaMallocHost(&c->h_pinned, c->h_pinned_cap) != cudaSuccess) { cudaFree(c->d_tables); delete c; return nullptr; }
     cudaFuncSetAttribute(k_compress_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 65536 + 16);
-    cudaFuncSetAttribute(k_decompress_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16);
     (void)workspace_bytes;
     return c;
 }

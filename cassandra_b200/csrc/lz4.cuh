@@ -162,7 +162,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
     return op;
 }
 
-// LZ4_decompress_safe semantics. src: compressed block (global, n bytes); s_out: destination in shared memory (cap bytes).
+// LZ4_decompress_safe semantics. src: compressed block (global, n bytes); s_out: destination (global or shared memory, cap bytes).
 // Returns decoded size or -1 on malformed input (warp-uniform). Literal and match copies run 32 bytes per step.
 __device__ int lz4_decompress_warp(const uint8_t* __restrict__ src, int n, uint8_t* s_out, int cap, int lane) {
     int ip = 0, op = 0;

@@ -187,8 +187,8 @@ def run_b200(args):
 
     # roofline of the dominant stage, algorithmic bytes per SURVEY §8(d): every compressed byte read once, every uncompressed byte
     # produced once, merged stream written once and compressed once
-    names = ["K1 decompress+verify", "K2 index scan", "K3 partition merge", "K4 size pass", "K4 emit pass", "K5 compress+crc+pack"]
-    alg = [c_in + u_in, i_in + 26 * parts_in, 26 * parts_in + 20 * parts_in, u_in, u_in + u_out + i_out, u_out + c_out]
+    names = ["K1 decompress+verify", "K2 index scan", "K3 partition merge", "K4 merge+purge+serialise", "K4 gather+index", "K5 compress+crc+pack"]
+    alg = [c_in + u_in, i_in + 26 * parts_in, 26 * parts_in + 20 * parts_in, u_in + u_out, 2 * u_out + i_out, u_out + c_out]
     dom = max(range(6), key=lambda i: stages[i])
     peak, which = peaks()
     b_alg = c_in + i_in + u_in + u_out + c_out + i_out
@@ -212,7 +212,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(1, args.cpu_sample_mib, 1)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1: dist.destroy_process_group()
 
@@ -256,9 +256,19 @@ def run_reference(args):
                        "algorithm (the JVM cannot run in this image), one compaction task per host thread"},
             "rows_merged_per_s": cb["rows_merged_per_s"], "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+_REAL_STDOUT = None
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n"); out.flush()
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) are diverted to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

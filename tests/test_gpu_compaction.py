@@ -202,3 +202,16 @@ def test_two_pass_mode_matches(golden_dir):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, B200C_K4_TWO_PASS="1"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+def test_config0_full_size_4x64mb(ctx):
+    """BASELINE.json configs[0]: STCS 4 SSTables x 64 MB, LZ4, single token range — full size, byte for byte against the oracle"""
+    import synth
+    tabs = synth_tables(0, 4, 0xCA550001, synth.universe_for(0, 64 << 20, 0.5))
+    got, want = both(ctx, tabs, CompactionController(NOW))
+    assert want.stats["bytes_read"] > 4 * 60 * (1 << 20)
+
+def test_wide_partitions_medium(ctx):
+    """schema W at ~70 KB per partition: every partition has a promoted index (2 column-index blocks) and takes the re-emit route"""
+    tabs = synth_tables(1, 4, 0xCA550005, 400, rows_per_partition=1000)
+    got, want = both(ctx, tabs, CompactionController(NOW))
+    assert len(want.outputs[0].index) > 400 * 100

@@ -214,4 +214,4 @@ def test_wide_partitions_medium(ctx):
     """schema W at ~70 KB per partition: every partition has a promoted index (2 column-index blocks) and takes the re-emit route"""
     tabs = synth_tables(1, 4, 0xCA550005, 400, rows_per_partition=1000)
     got, want = both(ctx, tabs, CompactionController(NOW))
-    assert len(want.outputs[0].index) > 400 * 100
+    assert len(want.outputs[0].index) > want.outputs[0].partitions * 90        # promoted index present on every partition

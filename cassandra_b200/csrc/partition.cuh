@@ -504,18 +504,24 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
     if (m > MAXK) { err = PERR_UNSUPPORTED; return; }
+    // prologue in three sweeps so that the m dependent chains (contrib -> upos -> Data bytes) overlap instead of serialising:
+    // (1) resolve the input partitions, (2) prefetch their first lines, (3) parse the partition headers
     for (uint32_t v = 0; v < m; v++) {
         uint64_t e = contrib[c0 + v];
-        int src = (int)((e >> 56) & 0x7F); uint64_t pidx = e & 0xFFFFFFFFFFull;
-        uint64_t g = pbase[src] + pidx;
-        uint64_t pos = part_upos[g], end = part_upos[g + 1];
-        Rd r{P.U, pos, end, 0};
+        int src = (int)((e >> 56) & 0x7F); uint64_t g = pbase[src] + (e & 0xFFFFFFFFFFull);
+        Cur& c = cur[v]; c.src = (uint8_t)src; c.pos = part_upos[g]; c.end = part_upos[g + 1]; c.done = false;
+    }
+    for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
+    for (uint32_t v = 0; v < m; v++) {
+        Cur& c = cur[v];
+        uint64_t pos = c.pos;
+        Rd r{P.U, pos, c.end, 0};
         uint32_t kl = r.be16(); r.skip(kl);
         DT pd = read_partition_dt(r);
         if (r.err) { err = r.err; return; }
         if (v == 0) { key_off = pos + 2; klen = kl; }
         if (!dt_supersedes(pdel, pd)) pdel = pd;                  // collectPartitionLevelDeletion :465-482
-        Cur& c = cur[v]; c.src = (uint8_t)src; c.pos = r.p; c.end = end; c.done = false; c.next = r.p;
+        c.pos = r.p; c.next = r.p;
     }
     DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;                 // PurgeFunction.applyToDeletion :95-99
 

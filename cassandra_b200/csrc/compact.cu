@@ -209,16 +209,6 @@ __global__ void __launch_bounds__(256) k_index_emit(const CParams* __restrict__ 
     const InDesc& in = P.in[i];
     uint64_t g = pbase[i] + (scan[b] - scan[bbase[i]]);
     uint64_t o = start[b];
-    {   // sweep 1: walk the entries only to prefetch the Data.db lines the verification below will touch (hides one DRAM latency per entry)
-        uint64_t o2 = o;
-        for (uint32_t k = 0; k < n; k++) {
-            uint64_t dpos; uint32_t kl;
-            uint64_t len = idx_entry(P, IDX, i, o2, false, &dpos, &kl);
-            if (!len) break;
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(P.U + in.ubase + dpos));
-            o2 += len;
-        }
-    }
     for (uint32_t k = 0; k < n; k++, g++) {
         uint64_t dpos; uint32_t kl;
         uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);

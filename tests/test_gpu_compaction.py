@@ -215,3 +215,24 @@ def test_wide_partitions_medium(ctx):
     tabs = synth_tables(1, 4, 0xCA550005, 400, rows_per_partition=1000)
     got, want = both(ctx, tabs, CompactionController(NOW))
     assert len(want.outputs[0].index) > want.outputs[0].partitions * 90        # promoted index present on every partition
+
+def test_output_buffers_too_small_reports_required_sizes(ctx):
+    import ctypes as C, numpy as np
+    from cassandra_b200 import native
+    tabs = synth_tables(0, 2, 41, 3000)
+    task = CompactionTask(tabs, CompactionController(NOW)); m = task.build_manifest()
+    res = native.Result(); outs = (native.Output * 1)(); tiny = np.empty(64, dtype=np.uint8); co = np.zeros(4, dtype=np.uint64)
+    outs[0].data, outs[0].data_cap, outs[0].index, outs[0].index_cap, outs[0].chunk_offsets, outs[0].chunk_cap = tiny.ctypes.data, 64, tiny.ctypes.data, 64, co.ctypes.data, 4
+    res.noutputs_cap = 1; res.outputs = outs
+    rc = native.lib().b200c_compact(ctx.handle, C.byref(m), C.byref(res), 0)
+    assert rc == native.ETOOSMALL
+    assert res.required_data_cap > 64 and res.required_index_cap > 64 and res.required_chunk_cap >= 1
+
+def test_poll_reports_progress(ctx):
+    import ctypes as C
+    from cassandra_b200 import native
+    tabs = synth_tables(0, 2, 42, 3000)
+    CompactionTask(tabs, CompactionController(NOW)).execute(GpuEngine(ctx))
+    p = native.Progress()
+    assert native.lib().b200c_poll(ctx.handle, C.byref(p)) == 0
+    assert p.stage == 6 and p.bytes_scanned == p.bytes_total == sum(t.compression.data_length for t in tabs)

@@ -127,9 +127,9 @@ def run_b200(args):
     nsst, per = args.sstables, int(args.sstable_mib * 2**20)
     seed = 0xCA550002 + 1000 * rank
     # the run manifest (workload shape) is broadcast once over NCCL so every rank compacts the same shape of shard
-    shape = torch.tensor([nsst, per, args.steps, args.warmup], dtype=torch.int64, device="cuda")
-    if world > 1: dist.broadcast(shape, 0)
-    nsst, per = int(shape[0]), int(shape[1])
+    from cassandra_b200 import parallel
+    shape = parallel.broadcast_manifest(dict(nsst=nsst, per=per, steps=args.steps, warmup=args.warmup, now=NOW) if rank == 0 else None)
+    nsst, per = shape["nsst"], shape["per"]
     threads = max(1, (os.cpu_count() or 8) // max(1, world))
     t0 = time.time()
     tabs = make_inputs_gpu(ctx, 0, nsst, seed, per, 0.5, threads)
@@ -168,9 +168,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
         clocks = sampler.stop() if sampler else None
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt[0]), kms / steps, [s / steps for s in stages], last, ctx.total_kernel_launches - launches0, clocks
+        return parallel.max_over_ranks(dt, device="cuda"), kms / steps, [s / steps for s in stages], last, ctx.total_kernel_launches - launches0, clocks
 
     for _ in range(args.warmup): step(True)
     dt, kms, stages, last, launches, clocks = timed(True, args.steps, ClockSampler(local))

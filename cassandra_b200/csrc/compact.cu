@@ -27,6 +27,10 @@ namespace b200c {
 
 int compress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
                            uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs, uint64_t* out_len, uint32_t* digest, int ws_base);
+int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
+                          uint8_t* slots, int stride, uint32_t* file_len, uint32_t* seg_raw);
+int pack_digest_device(b200c_ctx* c, const uint8_t* slots, int stride, const uint32_t* file_len, const uint32_t* seg_raw, uint64_t nchunks,
+                       uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs, uint64_t* out_len, uint32_t* digest, int ws_base);
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
                              int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err);
 
@@ -35,7 +39,7 @@ enum { IB = 256 };                       // Index.db speculation block
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -412,13 +416,14 @@ struct K4Args {
     const CParams* P; const uint64_t* contrib; const uint64_t* op_first; const uint32_t* list; const uint64_t* upos; const uint64_t* pbase;
     uint64_t* dsize; uint32_t* ipay; uint32_t* nblk; uint32_t* ihead; uint32_t* st_munf; uint32_t* st_rows; uint8_t* ovf;
     const uint64_t* doff; const uint64_t* dcapv; const uint64_t* dpos; const uint64_t* ipos; uint8_t* dbase; uint8_t* iout; DevErr* err; int mode;
+    uint64_t jlo, jhi;               // modes 2/3: only partitions jlo <= j < jhi (one output file of a multi-file compaction)
 };
 
 template <bool EMIT> __device__ __forceinline__ bool k4_prologue(const K4Args& a, uint64_t j, uint8_t*& dout, uint64_t& dcap, uint64_t& dposv, uint8_t*& iout, uint32_t& nbf, uint32_t& ipf) {
     dout = nullptr; dcap = ~0ull; dposv = 0; iout = nullptr; nbf = 0; ipf = 0;
     if (!EMIT) return true;
     if (a.mode == 1) { dout = a.dbase + a.doff[j]; dcap = a.dcapv[j]; return true; }
-    if (!a.dsize[j]) return false;
+    if (!a.dsize[j] || j < a.jlo || j >= a.jhi) return false;
     if (a.mode == 3 && !(a.nblk[j] > 1 || a.ovf[j])) return false;
     dout = a.dbase + a.dpos[j]; dposv = a.dpos[j]; iout = a.iout + a.ipos[j]; nbf = a.nblk[j]; ipf = a.ipay[j];
     return true;
@@ -523,6 +528,28 @@ __global__ void __launch_bounds__(256) k_index_sizes(uint64_t nparts, const uint
     isize[j] = dsize[j] ? ihead[j] + vint_size(dpos[j]) + vint_size(ipay[j]) + ipay[j] : 0;
 }
 
+// ---- LCS output switching (MaxSSTableSizeWriter.shouldSwitchWriterInCurrentLocation, S/db/compaction/writers/MaxSSTableSizeWriter.java:76-79;
+// CompactionAwareWriter.maybeSwitchWriter :166-173): before each partition the writer starts a new file when the bytes already
+// flushed to disk (whole compressed chunks + CRCs) exceed the limit. woffs = exclusive scan of the compressed chunk sizes of the
+// window that starts at byte start_b of the merged stream.
+__global__ void k_find_cut(const uint64_t* __restrict__ dpos, uint64_t jlo, uint64_t nparts, uint64_t start_b, const uint64_t* __restrict__ woffs,
+                           uint64_t nwin, uint32_t L, uint64_t limit, uint64_t* __restrict__ out /*[0]=j, [1]=status 0 found / 1 end / 2 need a longer window*/) {
+    uint64_t a = jlo + 1, b = nparts;
+    while (a < b) {
+        uint64_t mid = (a + b) / 2; uint64_t full = (dpos[mid] - start_b) / L;
+        bool cond = full > nwin || woffs[full] > limit;
+        if (cond) b = mid; else a = mid + 1;
+    }
+    out[0] = a;
+    if (a >= nparts) { out[1] = 1; return; }
+    uint64_t full = (dpos[a] - start_b) / L;
+    out[1] = full > nwin ? 2 : 0;
+}
+__global__ void __launch_bounds__(256) k_rel_pos(const uint64_t* __restrict__ dpos, uint64_t jlo, uint64_t jhi, uint64_t start_b, uint64_t* __restrict__ dposf) {
+    uint64_t j = jlo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= jhi) dposf[j] = dpos[j] - start_b;
+}
+
 } // namespace b200c
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -537,7 +564,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (m->ninputs > MAXK) { c->err = "more than 64 inputs per call"; return B200C_EUNSUPPORTED; }
     if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) { c->err = "static rows / tombstone_option / strict liveness"; return B200C_EUNSUPPORTED; }
     if (m->nclustering > MAXCLUST || m->ncolumns >= 64 || m->ncolumns < 0) { c->err = "schema outside the supported envelope"; return B200C_EUNSUPPORTED; }
-    if (m->max_sstable_bytes) { c->err = "max_sstable_bytes (LCS output switching) is not implemented on the GPU yet"; return B200C_EUNSUPPORTED; }
     if (res->noutputs_cap < 1 || !res->outputs) { c->err = "no output slot"; return B200C_EINVAL; }
     const bool dev = flags & B200C_FLAG_DEVICE_PTRS;
     const int K = m->ninputs;
@@ -780,7 +806,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     K4Args ka; memset(&ka, 0, sizeof(ka));
     ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase;
     ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
-    ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err;
+    ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts;
     // one launch per fan-in class over its slice of the sorted list
     auto launch_k4 = [&](int mode) -> int {
         ka.mode = mode;
@@ -864,46 +890,148 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------
     cudaEventRecord(c->ev_stage[5], st);
     c->prog_stage.store(5);
-    b200c_output& out = res->outputs[0];
-    const uint64_t nchunks_out = (ulen_out + m->out_chunk_len - 1) / m->out_chunk_len;
-    const uint64_t bound = b200c_compress_bound(m->out_compressor, ulen_out, m->out_chunk_len);
-    res->required_data_cap = bound; res->required_index_cap = ilen_out; res->required_chunk_cap = nchunks_out;
     if (m->out_chunk_len <= 0 || m->out_chunk_len > 65536 || (m->out_chunk_len & (m->out_chunk_len - 1))) { c->err = "output chunk_len"; return B200C_EUNSUPPORTED; }
-    uint8_t* d_dout = out.data; uint64_t* d_ooffs;
-    if (!dev) B200C_TRY(ws_typed(c, WS_DOUT, bound + 64, &d_dout));
-    else if (out.data_cap < bound) { c->err = "output data buffer too small"; timing_end(c); return B200C_ETOOSMALL; }
-    B200C_TRY(ws_typed(c, WS_OOFFS, nchunks_out + 2, &d_ooffs));
-    uint64_t out_len = 0; uint32_t digest = 0;
-    B200C_TRY(compress_stream_device(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound, d_ooffs, &out_len, &digest, WS_CODEC));
-    // final error word + stats
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
-    cudaEventRecord(c->ev_stage[6], st);
-    int trc = timing_end(c);
-    if (trc != B200C_OK) return trc;
-    for (int k = 0; k < 6; k++) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_stage[k], c->ev_stage[k + 1]); c->stage_ms[k] = ms; }
-    c->nstages = 6;
-    if (h[0] != ~0ull) { c->err = "internal error: size/emit pass disagreement at output partition " + std::to_string(h[0] & 0xFFFFFFFFFFFFull); return B200C_ECUDA; }
-    RunStats rs; memcpy(&rs, h + 8, sizeof(rs));
-    res->noutputs = 1;
-    res->bytes_read = bytes_read; res->bytes_written = ulen_out; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib;
-    memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
-    for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
-    out.data_len = out_len; out.index_len = ilen_out; out.nchunks = nchunks_out; out.data_length = ulen_out; out.digest = digest;
-    out.partitions = rs.partitions_out; out.rows = rs.rows_out;
-    res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
     int rc = B200C_OK;
-    if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
-    else if (!dev) {
-        if (out_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.data, d_dout, out_len, cudaMemcpyDeviceToHost, st));
-        if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToHost, st));
-        if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (!m->max_sstable_bytes) {
+        b200c_output& out = res->outputs[0];
+        const uint64_t nchunks_out = (ulen_out + m->out_chunk_len - 1) / m->out_chunk_len;
+        const uint64_t bound = b200c_compress_bound(m->out_compressor, ulen_out, m->out_chunk_len);
+        res->required_data_cap = bound; res->required_index_cap = ilen_out; res->required_chunk_cap = nchunks_out;
+        uint8_t* d_dout = out.data; uint64_t* d_ooffs;
+        if (!dev) B200C_TRY(ws_typed(c, WS_DOUT, bound + 64, &d_dout));
+        else if (out.data_cap < bound) { c->err = "output data buffer too small"; timing_end(c); return B200C_ETOOSMALL; }
+        B200C_TRY(ws_typed(c, WS_OOFFS, nchunks_out + 2, &d_ooffs));
+        uint64_t out_len = 0; uint32_t digest = 0;
+        B200C_TRY(compress_stream_device(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound, d_ooffs, &out_len, &digest, WS_CODEC));
+        // final error word + stats
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(c->ev_stage[6], st);
+        int trc = timing_end(c);
+        if (trc != B200C_OK) return trc;
+        for (int k = 0; k < 6; k++) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_stage[k], c->ev_stage[k + 1]); c->stage_ms[k] = ms; }
+        c->nstages = 6;
+        if (h[0] != ~0ull) { c->err = "internal error: size/emit pass disagreement at output partition " + std::to_string(h[0] & 0xFFFFFFFFFFFFull); return B200C_ECUDA; }
+        RunStats rs; memcpy(&rs, h + 8, sizeof(rs));
+        res->noutputs = 1;
+        res->bytes_read = bytes_read; res->bytes_written = ulen_out; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib;
+        memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
+        for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
+        out.data_len = out_len; out.index_len = ilen_out; out.nchunks = nchunks_out; out.data_length = ulen_out; out.digest = digest;
+        out.partitions = rs.partitions_out; out.rows = rs.rows_out;
+        res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
+        if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
+        else if (!dev) {
+            if (out_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.data, d_dout, out_len, cudaMemcpyDeviceToHost, st));
+            if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToHost, st));
+            if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        } else {
+            if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToDevice, st));
+            if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToDevice, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        }
+
     } else {
-        if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToDevice, st));
-        if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToDevice, st));
+        // ---- multi-file output: one pass per file over a compressed window (see k_find_cut) ----------------------------------------
+        const uint32_t L = (uint32_t)m->out_chunk_len; const int comp = m->out_compressor; const int stride = chunk_slot_stride(comp, (int)L);
+        const uint64_t nch_total = (ulen_out + L - 1) / L;
+        uint8_t* slots; uint32_t *file_len, *seg_raw; uint64_t *woffs, *d_dposf, *d_iposf, *d_cut, *d_ooffs; uint8_t *IOUTF, *d_dout; RunStats* d_fstats;
+        B200C_TRY(ws_typed(c, WS_CODEC + 2, (nch_total + 2) * (uint64_t)stride, &slots));
+        B200C_TRY(ws_typed(c, WS_CODEC + 3, nch_total + 2, &file_len));
+        B200C_TRY(ws_typed(c, WS_CODEC + 4, nch_total + 2, &seg_raw));
+        B200C_TRY(ws_typed(c, WS_LCS0, nch_total + 4, &woffs));
+        B200C_TRY(ws_typed(c, WS_LCS1, nparts + 2, &d_dposf));
+        B200C_TRY(ws_typed(c, WS_LCS2, nparts + 2, &d_iposf));
+        B200C_TRY(ws_typed(c, WS_LCS3, 64, &d_cut)); d_fstats = (RunStats*)(d_cut + 8);
+        B200C_TRY(ws_typed(c, WS_IOUT + 0, ilen_out + 64, &IOUT));
+        B200C_TRY(ws_typed(c, WS_LCS4, ilen_out + 64, &IOUTF));
+        B200C_TRY(ws_typed(c, WS_OOFFS, nch_total + 4, &d_ooffs));
+        const uint64_t file_bound = b200c_compress_bound(comp, ulen_out, (int)L);
+        B200C_TRY(ws_typed(c, WS_DOUT, file_bound + 64, &d_dout));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 100, d_dpos + nparts, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        RunStats rs; memcpy(&rs, h + 8, sizeof(rs));
+        memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
+        for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
+        res->required_data_cap = res->required_index_cap = res->required_chunk_cap = 0;
+        uint64_t jlo = 0, start_b = 0; int f = 0;
+        while (jlo < nparts && start_b < ulen_out) {
+            B200C_TRY(check_cancel());
+            const uint64_t remaining = ulen_out - start_b, rem_chunks = (remaining + L - 1) / L;
+            uint64_t want = std::max<uint64_t>(64, 2 * m->max_sstable_bytes / L + 8), done = 0, jhi = nparts, status = 2;
+            while (status == 2) {
+                uint64_t W = std::min(rem_chunks, want);
+                if (W > done) B200C_TRY(compress_slots_device(c, comp, UOUT + start_b + done * L, std::min(remaining - done * L, (W - done) * (uint64_t)L), (int)L,
+                                                              m->out_max_compressed_len, slots + done * stride, stride, file_len + done, seg_raw + done));
+                done = W;
+                // bytes flushed before a partition = whole chunks only: a trailing partial chunk of the window is not "flushed"
+                uint64_t nfull_known = (W == rem_chunks) ? (remaining / L) : W;
+                B200C_TRY(exclusive_scan<uint32_t>(c, file_len, nfull_known, woffs, WS_SCANA, 0));
+                B200C_LAUNCH(c, k_find_cut, 1, 1, 0, d_dpos, jlo, nparts, start_b, woffs, (W == rem_chunks) ? ~0ull >> 1 : nfull_known, L, m->max_sstable_bytes, d_cut);
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cut, 16, cudaMemcpyDeviceToHost, st));
+                B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                jhi = h[0]; status = h[1];
+                if (status == 2) { if (W == rem_chunks) { status = 1; jhi = nparts; } else want *= 2; }
+            }
+            // the file is partitions [jlo, jhi), bytes [start_b, end_b)
+            uint64_t end_b = ulen_out;
+            if (jhi < nparts) { B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_dpos + jhi, 8, cudaMemcpyDeviceToHost, st)); B200C_CUDA_TRY(c, cudaStreamSynchronize(st)); end_b = h[0]; }
+            const uint64_t flen = end_b - start_b, fchunks = (flen + L - 1) / L, nfull = flen / L, tail = flen % L;
+            if (tail && !(end_b == ulen_out && done == rem_chunks))      // the last chunk of the file is shorter than what the window compressed there
+                B200C_TRY(compress_slots_device(c, comp, UOUT + start_b + nfull * L, tail, (int)L, m->out_max_compressed_len, slots + nfull * stride, stride, file_len + nfull, seg_raw + nfull));
+            uint64_t out_len = 0; uint32_t digest = 0;
+            B200C_TRY(pack_digest_device(c, slots, stride, file_len, seg_raw, fchunks, d_dout, file_bound, d_ooffs, &out_len, &digest, WS_CODEC));
+            // Index.db of this file: positions relative to the file start
+            const uint64_t cnt = jhi - jlo;
+            B200C_LAUNCH(c, k_rel_pos, (unsigned)((cnt + 1 + 255) / 256), 256, 0, d_dpos, jlo, jhi, start_b, d_dposf);
+            B200C_LAUNCH(c, k_index_sizes, (unsigned)((cnt + 255) / 256), 256, 0, cnt, d_dsize + jlo, d_dposf + jlo, d_ipay + jlo, d_ihead + jlo, d_isize + jlo);
+            B200C_TRY(exclusive_scan<uint32_t>(c, d_isize + jlo, cnt, d_iposf + jlo, WS_SCANA + 3, 0));
+            B200C_CUDA_TRY(c, cudaMemsetAsync(d_fstats, 0, sizeof(RunStats), st));
+            B200C_LAUNCH(c, k_sum_stats, 296, 256, 0, cnt, d_dsize + jlo, d_stmunf + jlo, d_strows + jlo, d_fstats);
+            B200C_LAUNCH(c, k_index_simple, (unsigned)((cnt + 255) / 256), 256, 0, dP, cnt, d_contrib, d_opfirst + jlo, d_upos, d_pbase, d_dsize + jlo, d_dposf + jlo,
+                         d_nblk + jlo, d_ovf + jlo, d_ihead + jlo, d_iposf + jlo, IOUTF);
+            ka.dbase = UOUT + start_b; ka.iout = IOUTF; ka.dpos = d_dposf; ka.ipos = d_iposf; ka.jlo = jlo; ka.jhi = jhi;
+            B200C_TRY(launch_k4(3));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_iposf + jhi, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_fstats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+            const uint64_t filen = h[0]; RunStats fs; memcpy(&fs, h + 8, sizeof(fs));
+            res->required_data_cap = std::max<uint64_t>(res->required_data_cap, out_len);
+            res->required_index_cap = std::max<uint64_t>(res->required_index_cap, filen);
+            res->required_chunk_cap = std::max<uint64_t>(res->required_chunk_cap, fchunks);
+            if (fs.partitions_out) {
+                if (f >= res->noutputs_cap) { c->err = "more output files than output slots"; rc = B200C_ETOOSMALL; }
+                else {
+                    b200c_output& o = res->outputs[f];
+                    if (out_len > o.data_cap || filen > o.index_cap || fchunks > o.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
+                    else {
+                        cudaMemcpyKind k = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+                        if (out_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(o.data, d_dout, out_len, k, st));
+                        if (filen) B200C_CUDA_TRY(c, cudaMemcpyAsync(o.index, IOUTF, filen, k, st));
+                        if (fchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(o.chunk_offsets, d_ooffs, fchunks * 8, k, st));
+                        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                        o.data_len = out_len; o.index_len = filen; o.nchunks = fchunks; o.data_length = flen; o.digest = digest;
+                        o.partitions = fs.partitions_out; o.rows = fs.rows_out;
+                    }
+                }
+                f++;
+            }
+            jlo = jhi; start_b = end_b;
+        }
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(c->ev_stage[6], st);
+        int trc = timing_end(c);
+        if (trc != B200C_OK) return trc;
+        for (int k = 0; k < 6; k++) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_stage[k], c->ev_stage[k + 1]); c->stage_ms[k] = ms; }
+        c->nstages = 6;
+        if (h[0] != ~0ull) { c->err = "internal error: size/emit pass disagreement at output partition " + std::to_string(h[0] & 0xFFFFFFFFFFFFull); return B200C_ECUDA; }
+        res->noutputs = f;
+        res->bytes_read = bytes_read; res->bytes_written = ulen_out; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib;
+        res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
     }
     c->prog_scanned.store(bytes_read); c->prog_stage.store(6);
     res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();

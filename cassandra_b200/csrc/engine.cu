@@ -46,26 +46,26 @@ int exclusive_scan(b200c_ctx* c, const TIn* in, uint64_t n, uint64_t* out, int s
 template int exclusive_scan<uint32_t>(b200c_ctx*, const uint32_t*, uint64_t, uint64_t*, int, int);
 template int exclusive_scan<uint64_t>(b200c_ctx*, const uint64_t*, uint64_t, uint64_t*, int, int);
 
-// device-side chunk compression of a resident stream: d_in[0..n) -> d_out (dense image), d_offs[nchunks+1], digest.
-// Used by b200c_compress_chunks and by the compaction writer.
-int compress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
-                           uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs /*nchunks+1*/, uint64_t* out_len, uint32_t* digest, int ws_base) {
+// device-side chunk compression of a resident stream, in two halves so that the LCS writer can compress a window, look at the
+// chunk sizes, and only then decide where the file ends:
+//   compress_slots_device: every chunk of d_in[0..n) -> its fixed-stride slot (+ CRC), file_len[i] = bytes + 4, seg_raw[i] for the digest
+//   pack_digest_device:    first nchunks slots -> dense Data.db image, chunk offsets (nchunks + 1), Digest.crc32
+int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
+                          uint8_t* slots, int stride, uint32_t* file_len, uint32_t* seg_raw) {
     uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
-    if (nchunks == 0) { *out_len = 0; *digest = 0; B200C_CUDA_TRY(c, cudaMemsetAsync(d_offs, 0, 8, c->stream)); return B200C_OK; }
-    if (nchunks > 0x7fffffffull) { c->err = "too many chunks"; return B200C_EINVAL; }
-    int stride = chunk_slot_stride(comp, chunk_len);
-    uint8_t* slots; uint32_t* file_len; uint32_t* seg_raw; uint32_t* acc;
-    B200C_TRY(ws_typed(c, ws_base + WSC_SLOTS, nchunks * (uint64_t)stride, &slots));
-    B200C_TRY(ws_typed(c, ws_base + WSC_FILELEN, nchunks, &file_len));
-    B200C_TRY(ws_typed(c, ws_base + WSC_SEGRAW, nchunks, &seg_raw));
-    B200C_TRY(ws_typed(c, ws_base + WSC_ACC, 4, &acc));
+    if (!nchunks) return B200C_OK;
     int tab_bytes = comp == COMP_SNAPPY ? 32768 : 16384;
     size_t smem = (size_t)tab_bytes + chunk_len + 16;
-    B200C_CUDA_TRY(c, cudaMemsetAsync(acc, 0, 16, c->stream));
     B200C_LAUNCH(c, k_compress_chunks, (unsigned)nchunks, 32, smem, c->d_tables, comp, tab_bytes, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
+    return B200C_OK;
+}
+int pack_digest_device(b200c_ctx* c, const uint8_t* slots, int stride, const uint32_t* file_len, const uint32_t* seg_raw, uint64_t nchunks,
+                       uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs, uint64_t* out_len, uint32_t* digest, int ws_base) {
+    if (!nchunks) { *out_len = 0; *digest = 0; B200C_CUDA_TRY(c, cudaMemsetAsync(d_offs, 0, 8, c->stream)); return B200C_OK; }
+    uint32_t* acc; B200C_TRY(ws_typed(c, ws_base + WSC_ACC, 4, &acc));
+    B200C_CUDA_TRY(c, cudaMemsetAsync(acc, 0, 16, c->stream));
     B200C_TRY(exclusive_scan<uint32_t>(c, file_len, nchunks, d_offs, ws_base + WSC_SCAN0, 0));
-    // total size must be known on the host before packing into the caller's buffer
-    uint64_t* h = (uint64_t*)c->h_pinned;
+    uint64_t* h = (uint64_t*)c->h_pinned;                 // the total size must be known on the host before packing into the caller's buffer
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_offs + nchunks, 8, cudaMemcpyDeviceToHost, c->stream));
     B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     *out_len = h[0];
@@ -78,6 +78,18 @@ int compress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t
     B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     *digest = h32[0];
     return B200C_OK;
+}
+int compress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
+                           uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs /*nchunks+1*/, uint64_t* out_len, uint32_t* digest, int ws_base) {
+    uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
+    if (nchunks > 0x7fffffffull) { c->err = "too many chunks"; return B200C_EINVAL; }
+    int stride = chunk_slot_stride(comp, chunk_len);
+    uint8_t* slots = nullptr; uint32_t* file_len = nullptr; uint32_t* seg_raw = nullptr;
+    B200C_TRY(ws_typed(c, ws_base + WSC_SLOTS, nchunks * (uint64_t)stride, &slots));
+    B200C_TRY(ws_typed(c, ws_base + WSC_FILELEN, nchunks + 1, &file_len));
+    B200C_TRY(ws_typed(c, ws_base + WSC_SEGRAW, nchunks + 1, &seg_raw));
+    B200C_TRY(compress_slots_device(c, comp, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw));
+    return pack_digest_device(c, slots, stride, file_len, seg_raw, nchunks, d_out, out_cap, d_offs, out_len, digest, ws_base);
 }
 
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,

@@ -160,9 +160,35 @@ def test_corrupt_index_is_rejected(ctx):
 
 def test_unsupported_is_refused_not_faked(ctx):
     from cassandra_b200 import native
-    tabs = synth_tables(0, 2, 33, 1000)
+    s_static = Schema(["Int32Type"], [("val", "UTF8Type")])
+    t = Builder(s_static, (0, 0, 0)).build([Partition(b"k", [Row((I32(1),), [Cell(0, 5, b"v")], ts=5)])])
+    t.static_columns = [(b"s", "org.apache.cassandra.db.marshal.UTF8Type")]
     with pytest.raises(native.UnsupportedError):
-        CompactionTask(tabs, CompactionController(NOW), max_sstable_bytes=1 << 20).execute(GpuEngine(ctx), max_outputs=4)
+        CompactionTask([t], CompactionController(NOW)).execute(GpuEngine(ctx))
+
+@pytest.mark.parametrize("limit,n,universe", [(200_000, 6, 30000), (1 << 20, 8, 60000), (50_000, 3, 8000)])
+def test_lcs_output_switching_matches_oracle(ctx, limit, n, universe):
+    """MaxSSTableSizeWriter: a new output file starts before the first partition that sees more than `limit` flushed on-disk bytes.
+    Every file (Data, Index with file-relative positions, chunk offsets, digest, counters) must equal the oracle's."""
+    tabs = synth_tables(0, n, 0x1C5 + n, universe)
+    kw = dict(max_sstable_bytes=limit)
+    want = CompactionTask(tabs, CompactionController(NOW), **kw).execute(O.OracleEngine(), max_outputs=64)
+    got = CompactionTask(tabs, CompactionController(NOW), **kw).execute(GpuEngine(ctx), max_outputs=64)
+    assert len(want.outputs) >= 3 and len(got.outputs) == len(want.outputs)
+    for g, w in zip(got.outputs, want.outputs):
+        assert g.data == w.data and g.index == w.index and g.digest == w.digest
+        assert g.compression.chunk_offsets == w.compression.chunk_offsets and g.compression.data_length == w.compression.data_length
+        assert (g.partitions, g.rows) == (w.partitions, w.rows)
+    for k in ("bytes_read", "bytes_written", "total_source_rows", "merged_row_counts"): assert got.stats[k] == want.stats[k]
+
+def test_lcs_wide_partitions(ctx):
+    tabs = synth_tables(1, 3, 0x1C9, 120, rows_per_partition=1000)
+    kw = dict(max_sstable_bytes=1 << 20)
+    want = CompactionTask(tabs, CompactionController(NOW), **kw).execute(O.OracleEngine(), max_outputs=64)
+    got = CompactionTask(tabs, CompactionController(NOW), **kw).execute(GpuEngine(ctx), max_outputs=64)
+    assert len(want.outputs) >= 2 and len(got.outputs) == len(want.outputs)
+    for g, w in zip(got.outputs, want.outputs):
+        assert g.data == w.data and g.index == w.index and g.digest == w.digest and g.compression.chunk_offsets == w.compression.chunk_offsets
 
 def test_empty_result_and_tiny_inputs(ctx):
     S1 = Schema(["Int32Type"], [("val", "UTF8Type")]); b = Builder(S1, (0, 0, 0))

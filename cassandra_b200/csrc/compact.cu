@@ -218,10 +218,15 @@ __global__ void __launch_bounds__(256) k_index_emit(const CParams* __restrict__ 
         uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
         if (!len) { report_err(err, 3, i, o); return; }
         const uint8_t* key = IDX + in.ibase + o + 2;
-        const uint8_t* d = P.U + in.ubase + dpos;           // the Data.db partition must start with the same key
-        bool same = (((uint32_t)d[0] << 8) | d[1]) == kl;
-        for (uint32_t q = 0; same && q < kl; q++) same = d[2 + q] == key[q];
-        if (!same) { report_err(err, 3, i, o); return; }
+        if (kl > 8) {
+            // Index.db <-> Data.db consistency: the Data.db partition must start with the same key. Keys of up to 8 bytes are
+            // checked for free by K4 (it compares klen + the 8-byte prefix with the partition header it reads anyway), which
+            // saves one random Data.db sector read per partition here; longer keys are compared in full.
+            const uint8_t* d = P.U + in.ubase + dpos;
+            bool same = (((uint32_t)d[0] << 8) | d[1]) == kl;
+            for (uint32_t q = 0; same && q < kl; q++) same = d[2 + q] == key[q];
+            if (!same) { report_err(err, 3, i, o); return; }
+        }
         tok[g] = murmur3_token(key, kl);
         uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0);
         kp[g] = pre; klen[g] = (uint16_t)kl; upos[g] = in.ubase + dpos;
@@ -414,6 +419,7 @@ enum { SLOT_BYTES = sizeof(Cur), K4_SMEM_COLS = 8 };          // per-source curs
 // entry. mode 3: like 2 but only partitions the gather could not finish (more than one column-index block, or scratch overflow).
 struct K4Args {
     const CParams* P; const uint64_t* contrib; const uint64_t* op_first; const uint32_t* list; const uint64_t* upos; const uint64_t* pbase;
+    const uint64_t* kp; const uint16_t* klen;
     uint64_t* dsize; uint32_t* ipay; uint32_t* nblk; uint32_t* ihead; uint32_t* st_munf; uint32_t* st_rows; uint8_t* ovf;
     const uint64_t* doff; const uint64_t* dcapv; const uint64_t* dpos; const uint64_t* ipos; uint8_t* dbase; uint8_t* iout; DevErr* err; int mode;
     uint64_t jlo, jhi;               // modes 2/3: only partitions jlo <= j < jhi (one output file of a multi-file compaction)
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
     if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
-    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, dout, dcap, dposv, iout, nbf, ipf, cur, open_dt, merged, out, st, e);
+    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, cur, open_dt, merged, out, st, e);
     k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(128) k_partition_warp(const K4Args a, uint64_t
     if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf)) return;
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, dout, dcap, dposv, iout, nbf, ipf, s_cells, out, st, e);
+    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, s_cells, out, st, e);
     if (tile.thread_rank() == 0) k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
@@ -804,7 +810,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
     static const bool two_pass = getenv("B200C_K4_TWO_PASS") != nullptr;     // A/B switch: size pass + full emit pass instead of scratch + gather
     K4Args ka; memset(&ka, 0, sizeof(ka));
-    ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase;
+    ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen;
     ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
     ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts;
     // one launch per fan-in class over its slice of the sorted list

@@ -497,6 +497,7 @@ struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; };
 template <bool EMIT>
 __device__ void process_partition(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                   const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
+                                  const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen,
                                   uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
                                   Cur* cur, DT* open_dt, MCell* merged,
                                   PartOut& out, PartStats& st, int& err) {
@@ -510,13 +511,20 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         uint64_t e = contrib[c0 + v];
         int src = (int)((e >> 56) & 0x7F); uint64_t g = pbase[src] + (e & 0xFFFFFFFFFFull);
         Cur& c = cur[v]; c.src = (uint8_t)src; c.pos = part_upos[g]; c.end = part_upos[g + 1]; c.done = false;
+        c.k0 = part_kp[g]; c.ckend_rel = part_klen[g];           // what Index.db said about this partition's key (checked below)
     }
     for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
     for (uint32_t v = 0; v < m; v++) {
         Cur& c = cur[v];
         uint64_t pos = c.pos;
         Rd r{P.U, pos, c.end, 0};
-        uint32_t kl = r.be16(); r.skip(kl);
+        uint32_t kl = r.be16();
+        {   // Index.db <-> Data.db consistency (K2 only verified keys longer than 8 bytes): key length and 8-byte prefix must agree
+            uint64_t pre = load_be64(P.U + pos + 2);
+            if (kl < 8) pre &= kl ? (~0ull << (8 * (8 - kl))) : 0ull;
+            if (kl != c.ckend_rel || pre != c.k0) { err = PERR_CORRUPT; return; }
+        }
+        r.skip(kl);
         DT pd = read_partition_dt(r);
         if (r.err) { err = r.err; return; }
         if (v == 0) { key_off = pos + 2; klen = kl; }

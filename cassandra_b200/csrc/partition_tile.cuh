@@ -59,6 +59,7 @@ __device__ __forceinline__ MCell read_cell(const CParams& P, const InDesc& in, R
 template <int G, int S, bool EMIT>
 __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                        const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
+                                       const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen,
                                        uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
                                        MCell* s_cells, PartOut& out, PartStats& st, int& err) {
     const int lane = tile.thread_rank();
@@ -77,7 +78,13 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
             int src = (int)((e >> 56) & 0x7F); uint64_t g = pbase[src] + (e & 0xFFFFFFFFFFull);
             uint64_t pos = part_upos[g], end = part_upos[g + 1];
             Rd r{P.U, pos, end, 0};
-            uint32_t kl = r.be16(); r.skip(kl);
+            uint32_t kl = r.be16();
+            {   // Index.db <-> Data.db consistency for keys up to 8 bytes (longer keys are compared in full by K2)
+                uint64_t pre = load_be64(P.U + pos + 2);
+                if (kl < 8) pre &= kl ? (~0ull << (8 * (8 - kl))) : 0ull;
+                if (kl != part_klen[g] || pre != part_kp[g]) lerr = PERR_CORRUPT;
+            }
+            r.skip(kl);
             my_pd[s] = read_partition_dt(r);
             if (r.err) lerr = r.err;
             if (v == 0) { my_key_off = pos + 2; my_klen = kl; }

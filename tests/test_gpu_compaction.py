@@ -262,3 +262,17 @@ def test_poll_reports_progress(ctx):
     p = native.Progress()
     assert native.lib().b200c_poll(ctx.handle, C.byref(p)) == 0
     assert p.stage == 6 and p.bytes_scanned == p.bytes_total == sum(t.compression.data_length for t in tabs)
+
+def test_config2_shape_lcs_l0_l1_snappy(ctx):
+    """BASELINE.json configs[2] at reduced scale: LCS L0->L1, 32 overlapping inputs (4 L0 tables over the whole ring + 28 L1 tables
+    in 8 disjoint token bands), Snappy in and out, output switched at a fixed on-disk size. Byte parity is against the oracle's
+    Snappy restatement (parity with snappy-java itself is unpinned)."""
+    tabs = synth_tables(0, 32, 0xCA550003, 40000, p=0.25, comp=O.COMP_SNAPPY, band_count=8, l0_count=4)
+    kw = dict(max_sstable_bytes=160 * 1024)
+    want = CompactionTask(tabs, CompactionController(NOW), **kw).execute(O.OracleEngine(), max_outputs=64)
+    got = CompactionTask(tabs, CompactionController(NOW), **kw).execute(GpuEngine(ctx), max_outputs=64)
+    assert len(want.outputs) >= 3 and len(got.outputs) == len(want.outputs)
+    for g, w in zip(got.outputs, want.outputs):
+        assert g.data == w.data and g.index == w.index and g.digest == w.digest and g.compression.chunk_offsets == w.compression.chunk_offsets
+        assert g.compression.compressor_name == "SnappyCompressor"
+    assert got.stats["merged_row_counts"] == want.stats["merged_row_counts"]

@@ -223,10 +223,17 @@ def cpu_sample(threads, sstable_mib, steps, warmup=0):
     from synth_util import synth_tables
     from cassandra_b200.db.compaction import CompactionTask, CompactionController
     universe = synth.universe_for(0, int(sstable_mib * 2**20), 0.5)
-    tasks = []
-    for t in range(threads):
-        tabs = synth_tables(0, 16, 0xCA550002 + 7777 * (t + 1), universe)
-        tasks.append(CompactionTask(tabs, CompactionController(NOW)))
+    from concurrent.futures import ThreadPoolExecutor
+    def make_task(t):            # inputs are synthesised and LZ4-compressed (oracle codec) in parallel; ctypes releases the GIL
+        tabs = []
+        for s_ in range(16):
+            raw = synth.generate_raw(0, s_, 16, 0xCA550002 + 7777 * (t + 1), universe, 0.5, threads=1)
+            from synth_util import oracle_compress
+            tb = synth.make_sstable(raw, 0, lambda st, cl: oracle_compress(st, cl), "LZ4Compressor", generation=s_)
+            tabs.append(tb)
+        return CompactionTask(tabs, CompactionController(NOW))
+    with ThreadPoolExecutor(max_workers=min(threads, os.cpu_count() or 8)) as ex:
+        tasks = list(ex.map(make_task, range(threads)))
     total = sum(i.compression.data_length for task in tasks for i in task.inputs)
     rows = [0] * threads
     def work(k):

@@ -19,3 +19,17 @@ int      orc_chunk_max_compressed(int c, int n) { return chunk_max_compressed(c,
 int      orc_chunk_compress(int c, const uint8_t* s, int n, uint8_t* d) { return chunk_compress(c, s, n, d); }
 int      orc_chunk_decompress(int c, const uint8_t* s, int n, uint8_t* d, int cap) { return chunk_decompress(c, s, n, d, cap); }
 }
+
+// Whole-stream CompressedSequentialWriter on the CPU (S/io/compress/CompressedSequentialWriter.java:140-206 with min_compress_ratio 0):
+// chunk + big-endian CRC32 per chunk, chunk offsets, returns the image length. out_cap >= nchunks * (chunk_max_compressed + 4).
+extern "C" uint64_t orc_compress_stream(int comp, const uint8_t* in, uint64_t n, int chunk_len, uint8_t* out, uint64_t* offs) {
+    uint64_t o = 0, k = 0;
+    for (uint64_t i = 0; i < n; i += chunk_len, k++) {
+        int len = (int)((n - i) < (uint64_t)chunk_len ? (n - i) : (uint64_t)chunk_len);
+        int c = chunk_compress(comp, in + i, len, out + o);
+        uint32_t crc = crc32_ieee(0, out + o, c);
+        offs[k] = o; o += c;
+        out[o] = (uint8_t)(crc >> 24); out[o + 1] = (uint8_t)(crc >> 16); out[o + 2] = (uint8_t)(crc >> 8); out[o + 3] = (uint8_t)crc; o += 4;
+    }
+    return o;
+}

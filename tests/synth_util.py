@@ -5,11 +5,16 @@ import oracle_lib as O
 import synth
 
 def oracle_compress(stream, chunk_length, comp=O.COMP_LZ4):
-    b = stream.tobytes() if hasattr(stream, "tobytes") else bytes(stream)
-    image = bytearray(); offs = []
-    for i in range(0, len(b), chunk_length):
-        c = O.chunk_compress(comp, b[i:i + chunk_length]); offs.append(len(image)); image += c + struct.pack(">I", O.crc32(c))
-    return bytes(image), offs
+    """CPU oracle's CompressedSequentialWriter over a whole stream (one C call: releases the GIL)."""
+    import ctypes as C
+    a = np.ascontiguousarray(np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else stream)
+    n = len(a); nch = (n + chunk_length - 1) // chunk_length
+    L = O.lib()
+    L.orc_compress_stream.restype = C.c_uint64
+    L.orc_compress_stream.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    out = np.empty(nch * (L.orc_chunk_max_compressed(comp, chunk_length) + 4) + 64, dtype=np.uint8); offs = np.zeros(max(nch, 1), dtype=np.uint64)
+    m = L.orc_compress_stream(comp, a.ctypes.data, n, chunk_length, out.ctypes.data, offs.ctypes.data)
+    return out[:m].tobytes(), [int(x) for x in offs[:nch]]
 
 def synth_tables(schema, n, seed, universe, p=0.5, rows_per_partition=1000, comp=O.COMP_LZ4, **kw):
     name = {O.COMP_LZ4: "LZ4Compressor", O.COMP_SNAPPY: "SnappyCompressor"}[comp]

@@ -276,3 +276,41 @@ def test_config2_shape_lcs_l0_l1_snappy(ctx):
         assert g.data == w.data and g.index == w.index and g.digest == w.digest and g.compression.chunk_offsets == w.compression.chunk_offsets
         assert g.compression.compressor_name == "SnappyCompressor"
     assert got.stats["merged_row_counts"] == want.stats["merged_row_counts"]
+
+def test_edge_shapes(ctx):
+    """ragged and extreme shapes the reference's own tests exercise: empty input file, 65535-byte key, 60 columns with sparse rows,
+    8 clustering columns with empty / long components, values larger than a chunk and than column_index_size, single-row tables"""
+    rng = random.Random(17)
+    # (1) wide schema: 8 clustering columns, 60 regular columns
+    s = Schema(["Int32Type", "UTF8Type", "LongType", "BytesType", "Int32Type", "UTF8Type", "LongType", "BytesType"],
+               [("c%02d" % i, ("UTF8Type", "LongType", "Int32Type", "DoubleType")[i % 4]) for i in range(60)])
+    def val(ci):
+        t = ci % 4
+        return (rng.choice([b"", b"x" * rng.randint(1, 40)]), struct.pack(">q", rng.getrandbits(50)), I32(rng.randint(-5, 5)), struct.pack(">d", rng.random()))[t]
+    def ck():
+        return (I32(rng.randint(0, 3)), rng.choice([b"", b"a", b"b" * 70]), struct.pack(">q", rng.randint(-2, 2)), rng.choice([b"", b"\x00", b"\xff\xfe"]),
+                I32(rng.randint(0, 1)), rng.choice([b"k", b""]), struct.pack(">q", rng.randint(0, 1)), rng.choice([b"", b"zz"]))
+    tables = []
+    for t in range(3):
+        parts = []
+        for k in (b"\x01", b"k" * 65535, b"mid-key", b"another"):
+            if rng.random() < 0.3: continue
+            rows = {}
+            for _ in range(rng.randint(1, 10)):
+                c = ck(); cols = rng.sample(range(60), rng.randint(0, 12))
+                rows[c] = Row(c, [Cell(ci, 1000 + rng.randint(0, 3), val(ci)) for ci in cols], ts=1000 + rng.randint(0, 3))
+            def sk(c):   # clustering order: ints signed, text/bytes unsigned lexicographic
+                return (struct.unpack(">i", c[0])[0], c[1], struct.unpack(">q", c[2])[0], c[3], struct.unpack(">i", c[4])[0], c[5], struct.unpack(">q", c[6])[0], c[7])
+            parts.append(Partition(k, [rows[c] for c in sorted(rows, key=sk)]))
+        if not parts: parts = [Partition(b"\x01", [Row(ck(), [Cell(0, 1000, b"v")], ts=1000)])]
+        tables.append(Builder(s, (1000, 0, 0), column_index_size=512).build(parts))
+    both(ctx, tables, CompactionController(NOW, 10**9), column_index_size=512)
+    # (2) values larger than a chunk / an index block; an input file with no partitions at all
+    s2 = Schema(["Int32Type"], [("val", "BytesType")])
+    big = Builder(s2, (0, 0, 0)).build([Partition(b"p%d" % i, [Row((I32(j),), [Cell(0, 10 + j, bytes(rng.getrandbits(8) for _ in range(rng.choice([10, 40000, 70000]))))], ts=10 + j) for j in range(3)]) for i in range(4)])
+    empty = Builder(s2, (0, 0, 0)).build([])
+    one = Builder(s2, (0, 0, 0)).build([Partition(b"p1", [Row((I32(1),), [Cell(0, 99, b"newer")], ts=99)])])
+    both(ctx, [big, empty, one], CompactionController(NOW, 10**9))
+    both(ctx, [empty, one], CompactionController(NOW, 10**9))
+    g, _ = both(ctx, [empty], CompactionController(NOW, 10**9))
+    assert g.outputs[0].data == b"" and g.outputs[0].partitions == 0

@@ -382,28 +382,29 @@ __global__ void __launch_bounds__(256) k_op_first(const uint32_t* __restrict__ h
 // number of cursors). Per-partition results go to arrays indexed by the partition number j; totals come from k_sum_stats.
 struct RunStats { unsigned long long merged_unfiltereds, rows_out, partitions_out; };
 
-// Work-list order: partitions are counting-sorted by (fan-in m, average input partition size bucket) so that the threads of a warp
-// run the same number of cursors over similarly sized partitions (less divergence). key = (m - 1) * 16 + bucket.
+// Work-list order. Partitions are counting-sorted by key = (class, tile, fan-in m, size bucket):
+//   class  = which kernel handles the fan-in (<= 8, <= 16, <= 32, <= 64): each class is one contiguous slice of the list,
+//   tile   = j >> tile_shift: token-contiguous groups of output partitions whose input bytes (~32 MiB) stay L2 resident, so every
+//            class streams through U once instead of once per (m, size) bin,
+//   m, size bucket: threads of a warp run the same number of cursors over similarly sized partitions (less divergence).
 enum { SORT_BUCKETS = 16, SORT_BINS = MAXK * SORT_BUCKETS };
-__device__ __forceinline__ uint32_t sort_key(uint32_t m, uint64_t bound) {
+__device__ __forceinline__ uint32_t fanin_class(uint32_t m) { return m <= 8 ? 0u : (m <= 16 ? 1u : (m <= 32 ? 2u : 3u)); }
+__device__ __forceinline__ uint64_t sort_key(uint32_t m, uint64_t bound, uint64_t j, uint32_t tile_shift, uint64_t ntiles) {
     uint64_t avg = bound / (m ? m : 1);
     uint32_t bucket = (uint32_t)min((uint64_t)(SORT_BUCKETS - 1), avg >> 5);
-    return (m - 1) * SORT_BUCKETS + bucket;
+    return ((uint64_t)fanin_class(m) * ntiles + (j >> tile_shift)) * SORT_BINS + (m - 1) * SORT_BUCKETS + bucket;
 }
-__global__ void __launch_bounds__(256) k_class_hist(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts, unsigned long long* __restrict__ hist) {
-    __shared__ uint32_t s_h[SORT_BINS];
-    for (int k = threadIdx.x; k < SORT_BINS; k += blockDim.x) s_h[k] = 0;
-    __syncthreads();
+__global__ void __launch_bounds__(256) k_class_hist(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts,
+                                                    uint32_t tile_shift, uint64_t ntiles, unsigned long long* __restrict__ hist) {
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nparts; j += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&s_h[sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j])], 1u);
-    __syncthreads();
-    for (int k = threadIdx.x; k < SORT_BINS; k += blockDim.x) if (s_h[k]) atomicAdd(&hist[k], (unsigned long long)s_h[k]);
+        atomicAdd(&hist[sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j], j, tile_shift, ntiles)], 1ull);
 }
 // warp-aggregated counting-sort scatter: list[cursor[key]++] = j
-__global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
+__global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts,
+                                                       uint32_t tile_shift, uint64_t ntiles, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = j < nparts;
-    uint32_t key = valid ? sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j]) : 0xFFFFFFFFu;
+    uint64_t key = valid ? sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j], j, tile_shift, ntiles) : ~0ull;
     uint32_t peers = __match_any_sync(FULL_MASK, key);
     int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
     unsigned long long base = 0;
@@ -763,9 +764,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (nparts >= (1ull << 32)) { c->err = "too many output partitions"; return B200C_EUNSUPPORTED; }
     uint64_t* d_opfirst;
     B200C_TRY(ws_typed(c, WS_OPFIRST, nparts + 2, &d_opfirst));
-    uint32_t* d_list; unsigned long long* d_cursor; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
+    uint32_t* d_list; unsigned long long* d_cursor = nullptr; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
     B200C_TRY(ws_typed(c, WS_LIST, nparts + 1, &d_list));
-    B200C_TRY(ws_typed(c, WS_CURSOR, (size_t)SORT_BINS + 2, &d_cursor));
     B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
     B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
     uint64_t n_le8 = 0, n_le16 = 0, n_le32 = 0;
@@ -773,19 +773,18 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
         // counting sort of the output partitions by (fan-in, size bucket)
         B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound);
-        B200C_CUDA_TRY(c, cudaMemsetAsync(d_cursor, 0, (SORT_BINS + 2) * 8, st));
-        B200C_LAUNCH(c, k_class_hist, 592, 256, 0, d_opfirst, d_bound, nparts, d_cursor);
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512, d_cursor, SORT_BINS * 8, cudaMemcpyDeviceToHost, st));
+        // tile = token-contiguous run of output partitions whose inputs total ~32 MiB
+        uint64_t per_part = std::max<uint64_t>(1, bytes_read / std::max<uint64_t>(1, nparts));
+        uint32_t tile_shift = 12; while (tile_shift < 24 && ((1ull << (tile_shift + 1)) * per_part) <= (32ull << 20)) tile_shift++;
+        const uint64_t ntiles = (nparts >> tile_shift) + 1, nkeys = 4 * ntiles * SORT_BINS;
+        B200C_TRY(ws_typed(c, WS_CURSOR, nkeys + 2, &d_cursor));
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_cursor, 0, (nkeys + 2) * 8, st));
+        B200C_LAUNCH(c, k_class_hist, 1184, 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor);
+        B200C_TRY(exclusive_scan<uint64_t>(c, (const uint64_t*)d_cursor, nkeys, (uint64_t*)d_cursor, WS_SCANA, 0));
+        for (int k = 1; k <= 3; k++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512 + k, (uint64_t*)d_cursor + (uint64_t)k * ntiles * SORT_BINS, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-        uint64_t run = 0;
-        for (int k = 0; k < SORT_BINS; k++) {
-            if (k == 8 * SORT_BUCKETS) n_le8 = run;
-            if (k == 16 * SORT_BUCKETS) n_le16 = run;
-            if (k == 32 * SORT_BUCKETS) n_le32 = run;
-            uint64_t cnt = h[512 + k]; h[512 + k] = run; run += cnt;
-        }
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_cursor, h + 512, SORT_BINS * 8, cudaMemcpyHostToDevice, st));
-        B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, d_cursor, d_list);
+        n_le8 = h[513]; n_le16 = h[514]; n_le32 = h[515];
+        B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor, d_list);
     }
     B200C_TRY(check_cancel());
     c->prog_scanned.store(bytes_read / 2);

@@ -253,7 +253,7 @@ def cpu_sample(threads, sstable_mib, steps, warmup=0):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0: return
-    threads = args.ref_threads or min(os.cpu_count() or 8, 64)
+    threads = args.ref_threads or (os.cpu_count() or 8)          # every host thread: one independent compaction task each
     cb = cpu_sample(threads, args.ref_sample_mib, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",

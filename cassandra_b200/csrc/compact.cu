@@ -108,9 +108,9 @@ __device__ __forceinline__ int input_of_block(const uint64_t* __restrict__ bbase
     int i = 0; while (i + 1 < ninputs && bbase[i + 1] <= b) i++; return i;
 }
 
-__global__ void __launch_bounds__(256) k_index_find(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase,
+__global__ void __launch_bounds__(256) k_index_find(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase, uint64_t b0,
                                                     uint64_t nblocks, uint64_t* __restrict__ start) {
-    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const CParams& P = *Pp;
     int i = input_of_block(bbase, P.ninputs, b);
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(256) k_index_find(const CParams* __restrict__ 
     start[b] = found;
 }
 
-__global__ void __launch_bounds__(256) k_index_chain(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase,
+__global__ void __launch_bounds__(256) k_index_chain(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase, uint64_t b0,
                                                      uint64_t nblocks, const uint64_t* __restrict__ start, uint32_t* __restrict__ cnt, uint64_t* __restrict__ chain_end) {
-    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const CParams& P = *Pp;
     int i = input_of_block(bbase, P.ninputs, b);
@@ -154,10 +154,10 @@ __global__ void __launch_bounds__(256) k_index_chain(const CParams* __restrict__
 }
 
 // every chain must end exactly on the next block's speculated start (or at EOF), and every start must be the end of a chain
-__global__ void __launch_bounds__(256) k_index_verify_a(const CParams* __restrict__ Pp, const uint64_t* __restrict__ bbase, uint64_t nblocks,
+__global__ void __launch_bounds__(256) k_index_verify_a(const CParams* __restrict__ Pp, const uint64_t* __restrict__ bbase, uint64_t b0, uint64_t nblocks,
                                                         const uint64_t* __restrict__ start, const uint64_t* __restrict__ chain_end,
                                                         uint32_t* __restrict__ hit, uint32_t* __restrict__ bad) {
-    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const CParams& P = *Pp;
     int i = input_of_block(bbase, P.ninputs, b);
@@ -172,9 +172,9 @@ __global__ void __launch_bounds__(256) k_index_verify_a(const CParams* __restric
     hit[nb] = 1;
     for (uint64_t k = b + 1; k < nb; k++) if (start[k] != NONE64) { bad[i] = 1; return; }
 }
-__global__ void __launch_bounds__(256) k_index_verify_b(const CParams* __restrict__ Pp, const uint64_t* __restrict__ bbase, uint64_t nblocks,
+__global__ void __launch_bounds__(256) k_index_verify_b(const CParams* __restrict__ Pp, const uint64_t* __restrict__ bbase, uint64_t b0, uint64_t nblocks,
                                                         const uint64_t* __restrict__ start, const uint32_t* __restrict__ hit, uint32_t* __restrict__ bad) {
-    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     int i = input_of_block(bbase, Pp->ninputs, b);
     if (b != bbase[i] && start[b] != NONE64 && !hit[b]) bad[i] = 1;
@@ -641,21 +641,9 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     c->nstages = 0;
     cudaEventRecord(c->ev_stage[0], st);
 
-    // ---- K1: decompress + verify ------------------------------------------------------------------------------------------------
+    // ---- K1: decompress + verify, with the speculative part of K2 (find / chain / prove) per input right behind it so that both
+    //      run underneath the host->device copies of the following inputs -------------------------------------------------------------
     c->prog_stage.store(1);
-    for (int i = 0; i < K; i++) {
-        const b200c_input& in = m->inputs[i];
-        if (in.compressor != COMP_LZ4 && in.compressor != COMP_SNAPPY && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
-        B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0));
-        B200C_TRY(decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
-                                           in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr));
-    }
-    uint64_t* h = (uint64_t*)c->h_pinned;
-    auto check_cancel = [&]() -> int { if (c->cancel.load()) { c->err = "cancelled"; cudaStreamSynchronize(st); return B200C_ECANCELLED; } return B200C_OK; };
-
-    // ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
-    cudaEventRecord(c->ev_stage[1], st);
-    c->prog_stage.store(2);
     uint64_t *d_istart, *d_iend, *d_iscan; uint32_t *d_icnt, *d_ihit, *d_ibad;
     B200C_TRY(ws_typed(c, WS_ISTART, nblocks + 1, &d_istart));
     B200C_TRY(ws_typed(c, WS_IEND, nblocks + 1, &d_iend));
@@ -663,16 +651,32 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_IHIT, nblocks + 1, &d_ihit));
     B200C_TRY(ws_typed(c, WS_IBAD, (size_t)K + 1, &d_ibad));
     B200C_TRY(ws_typed(c, WS_ISCAN, nblocks + 2, &d_iscan));
+    if (nblocks) B200C_CUDA_TRY(c, cudaMemsetAsync(d_ihit, 0, nblocks * 4, st));
+    B200C_CUDA_TRY(c, cudaMemsetAsync(d_ibad, 0, (K + 1) * 4, st));
+    for (int i = 0; i < K; i++) {
+        const b200c_input& in = m->inputs[i];
+        if (in.compressor != COMP_LZ4 && in.compressor != COMP_SNAPPY && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
+        B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0));
+        B200C_TRY(decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
+                                           in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr));
+        const uint64_t nb = bbase[i + 1] - bbase[i];
+        if (nb) {
+            unsigned g = (unsigned)((nb + 255) / 256);
+            B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart);
+            B200C_LAUNCH(c, k_index_chain, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart, d_icnt, d_iend);
+            B200C_LAUNCH(c, k_index_verify_a, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_iend, d_ihit, d_ibad);
+            B200C_LAUNCH(c, k_index_verify_b, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_ihit, d_ibad);
+        }
+    }
+    uint64_t* h = (uint64_t*)c->h_pinned;
+    auto check_cancel = [&]() -> int { if (c->cancel.load()) { c->err = "cancelled"; cudaStreamSynchronize(st); return B200C_ECANCELLED; } return B200C_OK; };
+
+    // ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
+    cudaEventRecord(c->ev_stage[1], st);
+    c->prog_stage.store(2);
     uint64_t total_parts = 0;
     std::vector<uint64_t> pcount(K, 0), pbase(K + 1, 0);
     if (nblocks) {
-        unsigned g = (unsigned)((nblocks + 255) / 256);
-        B200C_CUDA_TRY(c, cudaMemsetAsync(d_ihit, 0, nblocks * 4, st));
-        B200C_CUDA_TRY(c, cudaMemsetAsync(d_ibad, 0, (K + 1) * 4, st));
-        B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, nblocks, d_istart);
-        B200C_LAUNCH(c, k_index_chain, g, 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iend);
-        B200C_LAUNCH(c, k_index_verify_a, g, 256, 0, dP, d_bbase, nblocks, d_istart, d_iend, d_ihit, d_ibad);
-        B200C_LAUNCH(c, k_index_verify_b, g, 256, 0, dP, d_bbase, nblocks, d_istart, d_ihit, d_ibad);
         B200C_LAUNCH(c, k_index_seq, (K + 63) / 64, 64, 0, dP, IDX, d_bbase, d_istart, d_icnt, d_ibad, d_err);
         B200C_TRY(exclusive_scan<uint32_t>(c, d_icnt, nblocks, d_iscan, WS_SCANA, 0));
     } else B200C_CUDA_TRY(c, cudaMemsetAsync(d_iscan, 0, 16, st));
@@ -895,6 +899,14 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------
     cudaEventRecord(c->ev_stage[5], st);
     c->prog_stage.store(5);
+    bool index_copied = false;
+    if (!dev && !m->max_sstable_bytes && ilen_out && ilen_out <= res->outputs[0].index_cap) {
+        // Index.db is final after K4: read it back on the copy stream while K5 compresses
+        B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[0], st));
+        B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_in[0], 0));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(res->outputs[0].index, IOUT, ilen_out, cudaMemcpyDeviceToHost, c->copy_stream));
+        index_copied = true;
+    }
     if (m->out_chunk_len <= 0 || m->out_chunk_len > 65536 || (m->out_chunk_len & (m->out_chunk_len - 1))) { c->err = "output chunk_len"; return B200C_EUNSUPPORTED; }
     int rc = B200C_OK;
     if (!m->max_sstable_bytes) {
@@ -929,7 +941,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
         else if (!dev) {
             if (out_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.data, d_dout, out_len, cudaMemcpyDeviceToHost, st));
-            if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToHost, st));
+            if (ilen_out && !index_copied) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToHost, st));
+            if (index_copied) B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
             if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
         } else {

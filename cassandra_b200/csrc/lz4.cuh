@@ -50,16 +50,25 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
 
     if (n >= LZ4_MINLENGTH) {
         // "First byte": position 0 is inserted with value 0 — already the zeroed state.
-        int fwd = 1;
+        // After every match liblz4 (1) inserts position ip-2, (2) tests position ip (lookup + insert; a hit is an immediate match
+        // with no literals and no back-tracking), (3) otherwise resumes the search at ip+1. Those three steps are folded into
+        // the FIRST window after a match: lane 0 = insert-only ip-2, lane 1 = the test of ip, lanes 2..31 = search attempts 0..29.
+        // The lane order equals the sequential order, so the same-hash resolution below needs no special case.
+        int fwd = 1; bool have_prefix = false; int pre_ip = 0;
         for (;;) {
-            int ip, match, token_pos;
-            // ---- search: 32 attempts per step -------------------------------------------------------------------
-            bool ended = false;
-            for (int a0 = 0;; a0 += 32) {
-                int a = a0 + lane;
-                int p = fwd + lz4_attempt_offset(a);
-                int pn = fwd + lz4_attempt_offset(a + 1);
-                bool valid = pn <= mfl1;
+            int ip = 0, match = 0, token_pos; bool ended = false, immediate = false;
+            // ---- search: up to 32 attempts per step -----------------------------------------------------------------
+            int a0 = 0;
+            for (bool first = true;; first = false) {
+                const bool prefixed = first && have_prefix;
+                int p; bool valid, putonly = false;
+                if (prefixed && lane < 2) { p = lane == 0 ? pre_ip - 2 : pre_ip; valid = true; putonly = lane == 0; }
+                else {
+                    int a = a0 + lane - (prefixed ? 2 : 0);
+                    p = fwd + lz4_attempt_offset(a);
+                    int pn = fwd + lz4_attempt_offset(a + 1);
+                    valid = pn <= mfl1;
+                }
                 uint32_t seq = valid ? rd32_at(in32, p) : 0u;
                 uint32_t h = lz4_hash_u16(seq);
                 int cand = valid ? (int)s_tab[h] : 0;
@@ -68,7 +77,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                 int src = prev ? (31 - __clz(prev)) : lane;
                 int pc = __shfl_sync(FULL_MASK, p, src);
                 if (prev) cand = pc;
-                bool hit = valid && (rd32_at(in32, cand) == seq);
+                bool hit = valid && !putonly && (rd32_at(in32, cand) == seq);
                 uint32_t hits = __ballot_sync(FULL_MASK, hit);
                 uint32_t inval = __ballot_sync(FULL_MASK, !valid);
                 int first_hit = hits ? (__ffs(hits) - 1) : 32;
@@ -79,6 +88,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                     if (lane <= first_hit && !later_same) s_tab[h] = (uint16_t)p;
                     ip = __shfl_sync(FULL_MASK, p, first_hit);
                     match = __shfl_sync(FULL_MASK, cand, first_hit);
+                    immediate = prefixed && first_hit == 1;
                     break;
                 }
                 if (first_inv < 32) { ended = true; break; }
@@ -87,67 +97,52 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                     if (!later_same) s_tab[h] = (uint16_t)p;
                 }
                 __syncwarp();
+                a0 += prefixed ? 30 : 32;
             }
             if (ended) break;
             __syncwarp();
 
-            // ---- catch up: extend the match backwards -----------------------------------------------------------
-            for (;;) {
-                int j = lane + 1;
-                bool ok = (ip - j >= anchor) && (match - j >= 0) && (s_in[ip - j] == s_in[match - j]);
-                uint32_t b = __ballot_sync(FULL_MASK, ok);
-                int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
-                ip -= steps; match -= steps;
-                if (steps < 32) break;
-            }
-            // ---- literals ---------------------------------------------------------------------------------------
-            int lit = ip - anchor;
-            token_pos = op++;
-            if (lit >= 15) op += lz4_emit_len_ext(out + op, lit - 15, lane);
-            for (int i = lane; i < lit; i += 32) out[op + i] = s_in[anchor + i];
-            op += lit;
-            int lit_nibble = lit < 15 ? lit : 15;
+            int lit_nibble = 0;
+            if (!immediate) {
+                // ---- catch up: extend the match backwards -----------------------------------------------------------
+                for (;;) {
+                    int j = lane + 1;
+                    bool ok = (ip - j >= anchor) && (match - j >= 0) && (s_in[ip - j] == s_in[match - j]);
+                    uint32_t b = __ballot_sync(FULL_MASK, ok);
+                    int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
+                    ip -= steps; match -= steps;
+                    if (steps < 32) break;
+                }
+                // ---- literals ---------------------------------------------------------------------------------------
+                int lit = ip - anchor;
+                token_pos = op++;
+                if (lit >= 15) op += lz4_emit_len_ext(out + op, lit - 15, lane);
+                for (int i = lane; i < lit; i += 32) out[op + i] = s_in[anchor + i];
+                op += lit;
+                lit_nibble = lit < 15 ? lit : 15;
+            } else token_pos = op++;                      // immediate match: token with literal length 0
 
-            for (;;) {   // _next_match
-                if (lane == 0) { int off = ip - match; out[op] = (uint8_t)off; out[op + 1] = (uint8_t)(off >> 8); }
-                op += 2;
-                // match length beyond MINMATCH, limited by matchlimit (LZ4_count)
-                int mc = 0;
-                {
-                    int pi = ip + LZ4_MINMATCH, pm = match + LZ4_MINMATCH;
-                    for (;;) {
-                        int i = mc + lane;
-                        bool eq = (pi + i < matchlimit) && (s_in[pi + i] == s_in[pm + i]);
-                        uint32_t b = __ballot_sync(FULL_MASK, eq);
-                        if (b == FULL_MASK) { mc += 32; continue; }
-                        mc += __ffs(~b) - 1;
-                        break;
-                    }
+            // ---- the match: offset, length beyond MINMATCH limited by matchlimit (LZ4_count) --------------------------
+            if (lane == 0) { int off = ip - match; out[op] = (uint8_t)off; out[op + 1] = (uint8_t)(off >> 8); }
+            op += 2;
+            int mc = 0;
+            {
+                int pi = ip + LZ4_MINMATCH, pm = match + LZ4_MINMATCH;
+                for (;;) {
+                    int i = mc + lane;
+                    bool eq = (pi + i < matchlimit) && (s_in[pi + i] == s_in[pm + i]);
+                    uint32_t b = __ballot_sync(FULL_MASK, eq);
+                    if (b == FULL_MASK) { mc += 32; continue; }
+                    mc += __ffs(~b) - 1;
+                    break;
                 }
-                ip += mc + LZ4_MINMATCH;
-                if (lane == 0) out[token_pos] = (uint8_t)((lit_nibble << 4) | (mc < 15 ? mc : 15));
-                if (mc >= 15) op += lz4_emit_len_ext(out + op, mc - 15, lane);
-                anchor = ip;
-                if (ip >= mfl1) break;
-                // fill table at ip-2, then test the position right after the match
-                int cand = 0;
-                uint32_t seq_ip = rd32_at(in32, ip);
-                if (lane == 0) {
-                    s_tab[lz4_hash_u16(rd32_at(in32, ip - 2))] = (uint16_t)(ip - 2);
-                    uint32_t h = lz4_hash_u16(seq_ip);
-                    cand = s_tab[h];
-                    s_tab[h] = (uint16_t)ip;
-                }
-                cand = __shfl_sync(FULL_MASK, cand, 0);
-                if (rd32_at(in32, cand) == seq_ip) {
-                    token_pos = op++; lit_nibble = 0; match = cand;
-                    continue;
-                }
-                break;
             }
-            __syncwarp();
+            ip += mc + LZ4_MINMATCH;
+            if (lane == 0) out[token_pos] = (uint8_t)((lit_nibble << 4) | (mc < 15 ? mc : 15));
+            if (mc >= 15) op += lz4_emit_len_ext(out + op, mc - 15, lane);
+            anchor = ip;
             if (ip >= mfl1) break;
-            fwd = ip + 1;
+            have_prefix = true; pre_ip = ip; fwd = ip + 1;
         }
     }
     // ---- last literals ------------------------------------------------------------------------------------------

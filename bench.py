@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 # ---------------------------------------------------------------------------------------------------------------------------
-def make_inputs_gpu(ctx, schema, nsst, seed, per_sstable_bytes, p, threads, pinned=True):
+def make_inputs_gpu(ctx, schema, nsst, seed, per_sstable_bytes, p, threads, pinned=True, rpp=1000):
     """Synthesises nsst input SSTables and compresses them with the engine's own K5 (b200c_compress_chunks). Returns SSTable
     objects whose data/index/offsets live in pinned host memory (torch tensors kept alive in .hold)."""
     import numpy as np, torch, synth
@@ -62,11 +62,11 @@ def make_inputs_gpu(ctx, schema, nsst, seed, per_sstable_bytes, p, threads, pinn
     from cassandra_b200.io.sstable import SSTable
     from cassandra_b200.io.compress import CompressionMetadata
     L = native.lib()
-    universe = synth.universe_for(schema, per_sstable_bytes, p)
+    universe = synth.universe_for(schema, per_sstable_bytes, p, rpp)
     tabs = []
     for s in range(nsst):
         t0 = time.time()
-        raw = synth.generate_raw(schema, s, nsst, seed, universe, p, threads=threads)
+        raw = synth.generate_raw(schema, s, nsst, seed, universe, p, rows_per_partition=rpp, threads=threads)
         n = len(raw["stream"]); cap = L.b200c_compress_bound(native.COMP_LZ4, n, 16384); nch = L.b200c_chunk_count(n, 16384)
         out = np.empty(cap, dtype=np.uint8); offs = np.zeros(max(nch, 1), dtype=np.uint64); out_len = C.c_uint64(); dig = C.c_uint32()
         ctx.check(L.b200c_compress_chunks(ctx.handle, native.COMP_LZ4, raw["stream"].ctypes.data, n, 16384, native.INT32_MAX,
@@ -132,12 +132,13 @@ def run_b200(args):
     nsst, per = shape["nsst"], shape["per"]
     threads = max(1, (os.cpu_count() or 8) // max(1, world))
     t0 = time.time()
-    tabs = make_inputs_gpu(ctx, 0, nsst, seed, per, 0.5, threads)
+    schema = 0 if args.schema == "N" else 1
+    tabs = make_inputs_gpu(ctx, schema, nsst, seed, per, 0.5, threads, rpp=args.rows_per_partition)
     log("rank %d: inputs ready in %.1fs" % (rank, time.time() - t0))
     u_in = sum(t.compression.data_length for t in tabs); c_in = sum(t.hold[0].numel() for t in tabs); i_in = sum(t.hold[1].numel() for t in tabs)
 
     # host (e2e) manifest + outputs in pinned memory
-    m_host = build_manifest(tabs, 0)
+    m_host = build_manifest(tabs, schema)
     cap_d = L.b200c_compress_bound(native.COMP_LZ4, u_in, 16384); cap_i = i_in + (1 << 20); cap_c = u_in // 16384 + 16
     ho = (torch.empty(cap_d, dtype=torch.uint8).pin_memory(), torch.empty(cap_i, dtype=torch.uint8).pin_memory(), torch.empty(cap_c, dtype=torch.int64).pin_memory())
     def result_for(bufs):
@@ -147,7 +148,7 @@ def run_b200(args):
         return res
     # device-resident copies of the inputs and outputs (value)
     dev_in = [(t.hold[0].cuda(), t.hold[1].cuda(), t.hold[2].cuda()) for t in tabs]
-    m_dev = build_manifest(tabs, 0, [(a.data_ptr(), b.data_ptr(), c.data_ptr()) for a, b, c in dev_in])
+    m_dev = build_manifest(tabs, schema, [(a.data_ptr(), b.data_ptr(), c.data_ptr()) for a, b, c in dev_in])
     do = (torch.empty(cap_d, dtype=torch.uint8, device="cuda"), torch.empty(cap_i, dtype=torch.uint8, device="cuda"), torch.empty(cap_c, dtype=torch.int64, device="cuda"))
 
     def step(dev):
@@ -198,8 +199,9 @@ def run_b200(args):
     line = {"metric": METRIC, "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "STCS %d SSTables x %d MiB (uncompressed), LZ4 16 KiB chunks, schema N, 1 output; %s" %
-                       (nsst, per >> 20, "BASELINE.json configs[1]" if (nsst, per >> 20) == (16, 1024) else "REDUCED from configs[1] (16 x 1024 MiB)"),
+            "config": {"workload": "STCS %d SSTables x %d MiB (uncompressed), LZ4 16 KiB chunks, schema %s, 1 output; %s" %
+                       (nsst, per >> 20, args.schema if args.schema == "N" else "W (%d rows/partition)" % args.rows_per_partition,
+                        "BASELINE.json configs[1]" if (nsst, per >> 20, args.schema) == (16, 1024, "N") else "NOT configs[1] (16 x 1024 MiB, schema N)"),
                        "per_gpu_uncompressed_in_bytes": u_in, "l2": "inputs (%.1f GB/step) larger than L2" % ((c_in + u_in) / 1e9),
                        "parallelism": "token-range shard per GPU, no data-path collective", "now_in_sec": NOW, "gc_grace": 864000, "seed": seed},
             "rows_merged_per_s": round(rows * world * args.steps / dt, 0), "input_partitions_per_step": parts_in,
@@ -281,6 +283,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sstables", type=int, default=16)
     ap.add_argument("--sstable-mib", type=float, default=1024.0, help="uncompressed size of each input (configs[1]: 1024)")
+    ap.add_argument("--schema", default="N", choices=["N", "W"], help="N: narrow rows (configs[1..3]); W: wide time-series partitions (configs[4] shape)")
+    ap.add_argument("--rows-per-partition", type=int, default=1000)
     ap.add_argument("--cpu-sample-mib", type=float, default=32.0)
     ap.add_argument("--ref-sample-mib", type=float, default=16.0)
     ap.add_argument("--ref-threads", type=int, default=0)

@@ -33,13 +33,16 @@ int pack_digest_device(b200c_ctx* c, const uint8_t* slots, int stride, const uin
                        uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs, uint64_t* out_len, uint32_t* digest, int ws_base);
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
                              int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err);
+int compress_stream_to_host(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
+                            uint8_t* d_img, uint64_t img_cap, uint8_t* h_out, uint64_t h_cap, uint64_t* d_offs,
+                            uint64_t* out_len, uint32_t* digest, int ws_base);
 
 enum { IB = 256 };                       // Index.db speculation block
 #define NONE64 (~0ull)
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -417,21 +420,29 @@ enum { SLOT_BYTES = sizeof(Cur), K4_SMEM_COLS = 8 };          // per-source curs
 
 // mode 0: size pass only (EMIT = false). mode 1: the single serialisation pass — bytes go to scratch at dbase + doff[j] (capacity
 // dcapv[j]), sizes/stats are recorded, no Index.db. mode 2: final emit of every written partition at dbase + dpos[j] with its Index.db
-// entry. mode 3: like 2 but only partitions the gather could not finish (more than one column-index block, or scratch overflow).
+// entry. mode 3: like 2 but only partitions whose scratch (Data bytes or promoted-index slot) overflowed in mode 1.
 struct K4Args {
     const CParams* P; const uint64_t* contrib; const uint64_t* op_first; const uint32_t* list; const uint64_t* upos; const uint64_t* pbase;
     const uint64_t* kp; const uint16_t* klen;
     uint64_t* dsize; uint32_t* ipay; uint32_t* nblk; uint32_t* ihead; uint32_t* st_munf; uint32_t* st_rows; uint8_t* ovf;
     const uint64_t* doff; const uint64_t* dcapv; const uint64_t* dpos; const uint64_t* ipos; uint8_t* dbase; uint8_t* iout; DevErr* err; int mode;
     uint64_t jlo, jhi;               // modes 2/3: only partitions jlo <= j < jhi (one output file of a multi-file compaction)
+    // mode 1: promoted-index slots (IXS_* layout in partition.cuh) of the partitions that can exceed one column-index block
+    const uint64_t* ioff; const uint32_t* icapv; uint8_t* iscr;
+    int m3_nblk;                     // mode 3 also re-emits partitions with a promoted index (two-pass A/B mode: there are no slots)
 };
 
-template <bool EMIT> __device__ __forceinline__ bool k4_prologue(const K4Args& a, uint64_t j, uint8_t*& dout, uint64_t& dcap, uint64_t& dposv, uint8_t*& iout, uint32_t& nbf, uint32_t& ipf) {
-    dout = nullptr; dcap = ~0ull; dposv = 0; iout = nullptr; nbf = 0; ipf = 0;
+template <bool EMIT> __device__ __forceinline__ bool k4_prologue(const K4Args& a, uint64_t j, uint8_t*& dout, uint64_t& dcap, uint64_t& dposv, uint8_t*& iout, uint32_t& nbf, uint32_t& ipf, uint32_t& ixs_cap) {
+    dout = nullptr; dcap = ~0ull; dposv = 0; iout = nullptr; nbf = 0; ipf = 0; ixs_cap = 0;
     if (!EMIT) return true;
-    if (a.mode == 1) { dout = a.dbase + a.doff[j]; dcap = a.dcapv[j]; return true; }
+    if (a.mode == 1) {
+        dout = a.dbase + a.doff[j]; dcap = a.dcapv[j];
+        uint32_t slot = a.icapv[j];
+        if (slot) { iout = a.iscr + a.ioff[j]; nbf = (slot - IXS_HEAD) / IXS_BLOCK_STRIDE; ixs_cap = nbf * IXS_PER_BLOCK; }
+        return true;
+    }
     if (!a.dsize[j] || j < a.jlo || j >= a.jhi) return false;
-    if (a.mode == 3 && !(a.nblk[j] > 1 || a.ovf[j])) return false;
+    if (a.mode == 3 && !(a.ovf[j] || (a.m3_nblk && a.nblk[j] > 1))) return false;
     dout = a.dbase + a.dpos[j]; dposv = a.dpos[j]; iout = a.iout + a.ipos[j]; nbf = a.nblk[j]; ipf = a.ipay[j];
     return true;
 }
@@ -456,12 +467,12 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     uint64_t t = lo + (uint64_t)blockIdx.x * NT + threadIdx.x;
     if (t >= hi) return;
     uint64_t j = a.list[t];
-    uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf;
-    if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf)) return;
+    uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf, ixs_cap;
+    if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) return;
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
     if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
-    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, cur, open_dt, merged, out, st, e);
+    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e);
     k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
@@ -475,23 +486,28 @@ __global__ void __launch_bounds__(128) k_partition_warp(const K4Args a, uint64_t
     uint64_t t = lo + (uint64_t)blockIdx.x * 4 + tid;
     if (t >= hi) return;
     uint64_t j = a.list[t];
-    uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf;
-    if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf)) return;
+    uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf, ixs_cap;
+    if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) return;
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, s_cells, out, st, e);
+    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, s_cells, out, st, e);
     if (tile.thread_rank() == 0) k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
 // upper bound of an output partition's size: the sum of its input partitions plus 25 % + 32 bytes (re-based deltas can lengthen
 // vints by a byte or two per field; a partition that still does not fit is caught by the overflow flag and re-emitted by mode 3)
+// icap[j]: bytes of promoted-index slot (0 when the partition cannot reach a second column-index block)
 __global__ void __launch_bounds__(256) k_bounds(const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first, uint64_t nparts,
-                                                const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint64_t* __restrict__ bound) {
+                                                const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint64_t* __restrict__ bound,
+                                                uint32_t column_index_size, uint32_t* __restrict__ icap) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nparts) return;
     uint64_t sum = 0;
     for (uint64_t c = op_first[j]; c < op_first[j + 1]; c++) { uint64_t e = contrib[c]; uint64_t g = pbase[(e >> 56) & 0x7F] + (e & 0xFFFFFFFFFFull); sum += upos[g + 1] - upos[g]; }
-    bound[j] = (sum + (sum >> 2) + 32 + 15) & ~15ull;
+    uint64_t b = (sum + (sum >> 2) + 32 + 15) & ~15ull;
+    bound[j] = b;
+    uint64_t nb_max = b / column_index_size + 2;          // a block closes once it holds >= column_index_size bytes
+    icap[j] = (b > column_index_size && nb_max < (1u << 23)) ? (uint32_t)(IXS_HEAD + nb_max * IXS_BLOCK_STRIDE) : 0u;
 }
 
 // scratch -> dense Data stream; one warp per output partition (partitions are tens of bytes to a few KB)
@@ -517,6 +533,28 @@ __global__ void __launch_bounds__(256) k_index_simple(const CParams* __restrict_
     uint32_t n = ihead[j];                          // 2 + keyLen: the bytes are identical to the partition header in Data.db
     Sink<true> s{iout + ipos[j], 0, true, ~0ull};
     s.copy(k, n); s.vint(dpos[j]); s.u8(0);
+}
+
+// Index.db entries with a promoted index (IndexedEntry.serialize, S/io/sstable/format/big/RowIndexEntry.java:625-642), assembled from
+// the slot the scratch pass filled: u16 keyLen | key | vint position | vint32 payload | vint headerLength | DeletionTime | vint32 nBlocks |
+// IndexInfo x n | i32 offset x n
+__global__ void __launch_bounds__(128) k_index_promoted(const CParams* __restrict__ Pp, uint64_t nparts, const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first,
+        const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ dsize, const uint64_t* __restrict__ dpos,
+        const uint32_t* __restrict__ nblk, const uint8_t* __restrict__ ovf, const uint32_t* __restrict__ ihead, const uint32_t* __restrict__ ipay, const uint64_t* __restrict__ ipos,
+        const uint64_t* __restrict__ ioff, const uint32_t* __restrict__ icap, const uint8_t* __restrict__ iscr, uint8_t* __restrict__ iout) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nparts || !dsize[j] || nblk[j] <= 1 || ovf[j]) return;
+    uint64_t e = contrib[op_first[j]]; uint64_t g = pbase[(e >> 56) & 0x7F] + (e & 0xFFFFFFFFFFull);
+    const uint8_t* k = Pp->U + upos[g];
+    const uint8_t* slot = iscr + ioff[j];
+    const uint32_t nb_max = (icap[j] - IXS_HEAD) / IXS_BLOCK_STRIDE, nb = nblk[j], n = ihead[j];
+    DT pd; pd.mfda = ((const int64_t*)slot)[0]; pd.ldt = ((const int64_t*)slot)[1];
+    const uint32_t pdsz = dt_is_live(pd) ? 1u : 12u, hdr_len = n + pdsz;
+    const uint32_t infos = ipay[j] - vint_size(hdr_len) - pdsz - vint_size(nb) - 4 * nb;
+    Sink<true> s{iout + ipos[j], 0, true, ~0ull};
+    s.copy(k, n); s.vint(dpos[j]); s.vint(ipay[j]);
+    s.vint(hdr_len); write_partition_dt(s, pd); s.vint(nb);
+    s.copy(slot + IXS_HEAD + 4 * (size_t)nb_max, infos); s.copy(slot + IXS_HEAD, 4 * nb);
 }
 
 __global__ void __launch_bounds__(256) k_sum_stats(uint64_t nparts, const uint64_t* __restrict__ dsize, const uint32_t* __restrict__ st_munf, const uint32_t* __restrict__ st_rows, RunStats* __restrict__ stats) {
@@ -772,11 +810,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_LIST, nparts + 1, &d_list));
     B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
     B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
+    uint32_t* d_icap; uint64_t* d_ioff;
+    B200C_TRY(ws_typed(c, WS_ICAP, nparts + 1, &d_icap));
+    B200C_TRY(ws_typed(c, WS_IOFF, nparts + 2, &d_ioff));
     uint64_t n_le8 = 0, n_le16 = 0, n_le32 = 0;
     if (ncontrib) {
         B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
         // counting sort of the output partitions by (fan-in, size bucket)
-        B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound);
+        B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound,
+                     (uint32_t)std::min<uint64_t>(std::max<int64_t>(1, m->column_index_size), 0x7fffffff), d_icap);
         // tile = token-contiguous run of output partitions whose inputs total ~32 MiB
         uint64_t per_part = std::max<uint64_t>(1, bytes_read / std::max<uint64_t>(1, nparts));
         uint32_t tile_shift = 12; while (tile_shift < 24 && ((1ull << (tile_shift + 1)) * per_part) <= (32ull << 20)) tile_shift++;
@@ -815,7 +857,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     K4Args ka; memset(&ka, 0, sizeof(ka));
     ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen;
     ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
-    ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts;
+    ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts; ka.m3_nblk = two_pass ? 1 : 0;
     // one launch per fan-in class over its slice of the sorted list
     auto launch_k4 = [&](int mode) -> int {
         ka.mode = mode;
@@ -849,17 +891,20 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
         c->k4_attr_set = (int)(smem8 + 1);
     }
-    uint8_t* SCRATCH = nullptr;
+    uint8_t *SCRATCH = nullptr, *ISCR = nullptr;
     if (nparts) {
         if (two_pass) {
             B200C_CUDA_TRY(c, cudaMemsetAsync(d_ovf, 0, nparts, st));
             B200C_TRY(launch_k4(0));
         } else {
             B200C_TRY(exclusive_scan<uint64_t>(c, d_bound, nparts, d_bpos, WS_SCANA, 0));
+            B200C_TRY(exclusive_scan<uint32_t>(c, d_icap, nparts, d_ioff, WS_SCANA + 3, 0));
             B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_bpos + nparts, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_ioff + nparts, 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
             B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
-            ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr;
+            B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
+            ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
             B200C_TRY(launch_k4(1));
         }
         B200C_LAUNCH(c, k_sum_stats, 1184, 256, 0, nparts, d_dsize, d_stmunf, d_strows, d_stats);
@@ -891,6 +936,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         else {
             B200C_LAUNCH(c, k_gather, (unsigned)((nparts + 7) / 8), 256, 0, nparts, d_dsize, d_dpos, d_bpos, d_ovf, SCRATCH, UOUT);
             B200C_LAUNCH(c, k_index_simple, (unsigned)((nparts + 255) / 256), 256, 0, dP, nparts, d_contrib, d_opfirst, d_upos, d_pbase, d_dsize, d_dpos, d_nblk, d_ovf, d_ihead, d_ipos, IOUT);
+            B200C_LAUNCH(c, k_index_promoted, (unsigned)((nparts + 127) / 128), 128, 0, dP, nparts, d_contrib, d_opfirst, d_upos, d_pbase, d_dsize, d_dpos, d_nblk, d_ovf, d_ihead, d_ipay, d_ipos,
+                         d_ioff, d_icap, ISCR, IOUT);
             B200C_TRY(launch_k4(3));
         }
     }
@@ -919,7 +966,9 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         else if (out.data_cap < bound) { c->err = "output data buffer too small"; timing_end(c); return B200C_ETOOSMALL; }
         B200C_TRY(ws_typed(c, WS_OOFFS, nchunks_out + 2, &d_ooffs));
         uint64_t out_len = 0; uint32_t digest = 0;
-        B200C_TRY(compress_stream_device(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound, d_ooffs, &out_len, &digest, WS_CODEC));
+        if (dev) B200C_TRY(compress_stream_device(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound, d_ooffs, &out_len, &digest, WS_CODEC));
+        else B200C_TRY(compress_stream_to_host(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound,
+                                               out.data, out.data ? out.data_cap : 0, d_ooffs, &out_len, &digest, WS_CODEC));   // Data.db leaves slice by slice under K5
         // final error word + stats
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
@@ -938,11 +987,12 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         out.data_len = out_len; out.index_len = ilen_out; out.nchunks = nchunks_out; out.data_length = ulen_out; out.digest = digest;
         out.partitions = rs.partitions_out; out.rows = rs.rows_out;
         res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
-        if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
-        else if (!dev) {
-            if (out_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.data, d_dout, out_len, cudaMemcpyDeviceToHost, st));
+        if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) {
+            c->err = "output buffers too small"; rc = B200C_ETOOSMALL;
+            if (!dev) B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));      // slices that did fit may still be in flight
+        } else if (!dev) {
             if (ilen_out && !index_copied) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToHost, st));
-            if (index_copied) B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
             if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
         } else {
@@ -1012,6 +1062,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             B200C_LAUNCH(c, k_sum_stats, 296, 256, 0, cnt, d_dsize + jlo, d_stmunf + jlo, d_strows + jlo, d_fstats);
             B200C_LAUNCH(c, k_index_simple, (unsigned)((cnt + 255) / 256), 256, 0, dP, cnt, d_contrib, d_opfirst + jlo, d_upos, d_pbase, d_dsize + jlo, d_dposf + jlo,
                          d_nblk + jlo, d_ovf + jlo, d_ihead + jlo, d_iposf + jlo, IOUTF);
+            if (!two_pass) B200C_LAUNCH(c, k_index_promoted, (unsigned)((cnt + 127) / 128), 128, 0, dP, cnt, d_contrib, d_opfirst + jlo, d_upos, d_pbase, d_dsize + jlo, d_dposf + jlo,
+                                        d_nblk + jlo, d_ovf + jlo, d_ihead + jlo, d_ipay + jlo, d_iposf + jlo, d_ioff + jlo, d_icap + jlo, ISCR, IOUTF);
             ka.dbase = UOUT + start_b; ka.iout = IOUTF; ka.dpos = d_dposf; ka.ipos = d_iposf; ka.jlo = jlo; ka.jhi = jhi;
             B200C_TRY(launch_k4(3));
             B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_iposf + jhi, 8, cudaMemcpyDeviceToHost, st));

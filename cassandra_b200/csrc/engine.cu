@@ -92,6 +92,77 @@ int compress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t
     return pack_digest_device(c, slots, stride, file_len, seg_raw, nchunks, d_out, out_cap, d_offs, out_len, digest, ws_base);
 }
 
+// slice-relative chunk offsets -> absolute offsets in the file image; bases[0] = offset of this slice, bases[1] := offset of the next
+__global__ void __launch_bounds__(256) k_offs_add_base(const uint64_t* __restrict__ rel, uint64_t count, uint64_t* __restrict__ bases, uint64_t* __restrict__ offs_abs) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t b = bases[0];
+    if (i <= count) offs_abs[i] = b + rel[i];
+    if (i == count) bases[1] = b + rel[count];
+}
+
+// Same result as compress_stream_device followed by a device->host copy of the file image, but in slices: slice s is copied to the
+// caller's host buffer on the copy stream while slice s+1 is being compressed, so that the PCIe read-back hides behind K5.
+// d_img: device staging of the whole image (cap img_cap); h_out/h_cap: the caller's buffer. When the image does not fit h_cap the
+// copies stop, *out_len is still the full size and the caller reports B200C_ETOOSMALL.
+int compress_stream_to_host(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
+                            uint8_t* d_img, uint64_t img_cap, uint8_t* h_out, uint64_t h_cap, uint64_t* d_offs /*nchunks+1*/,
+                            uint64_t* out_len, uint32_t* digest, int ws_base) {
+    const uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
+    if (nchunks > 0x7fffffffull) { c->err = "too many chunks"; return B200C_EINVAL; }
+    if (!nchunks) { *out_len = 0; *digest = 0; B200C_CUDA_TRY(c, cudaMemsetAsync(d_offs, 0, 8, c->stream)); return B200C_OK; }
+    enum { MAX_SLICES = 16, MIN_SLICE_CHUNKS = 8192 };
+    const int nslices = (int)std::min<uint64_t>(MAX_SLICES, std::max<uint64_t>(1, nchunks / MIN_SLICE_CHUNKS));
+    const uint64_t per = (nchunks + nslices - 1) / nslices;
+    const int stride = chunk_slot_stride(comp, chunk_len);
+    uint8_t* slots; uint32_t *file_len, *seg_raw, *acc; uint64_t *rel, *bases;
+    B200C_TRY(ws_typed(c, ws_base + WSC_SLOTS, nchunks * (uint64_t)stride, &slots));
+    B200C_TRY(ws_typed(c, ws_base + WSC_FILELEN, nchunks + 1, &file_len));
+    B200C_TRY(ws_typed(c, ws_base + WSC_SEGRAW, nchunks + 1, &seg_raw));
+    B200C_TRY(ws_typed(c, ws_base + WSC_IN, per + 2, &rel));
+    B200C_TRY(ws_typed(c, ws_base + WSC_CHOFFS, MAX_SLICES + 2, &bases));
+    B200C_TRY(ws_typed(c, ws_base + WSC_ACC, 4, &acc));
+    {   // scan scratch is sized by the first slice; allocate it before the loop so that no slot grows (and synchronises) mid-pipeline
+        uint64_t* tmp; uint64_t tiles = (per + SCAN_TILE - 1) / SCAN_TILE;
+        B200C_TRY(ws_typed(c, ws_base + WSC_SCAN0, tiles + 1, &tmp));
+        B200C_TRY(ws_typed(c, ws_base + WSC_SCAN0 + 1, (tiles + SCAN_TILE - 1) / SCAN_TILE + 1, &tmp));
+    }
+    B200C_CUDA_TRY(c, cudaMemsetAsync(acc, 0, 16, c->stream));
+    B200C_CUDA_TRY(c, cudaMemsetAsync(bases, 0, 8, c->stream));
+    uint64_t* h = (uint64_t*)c->h_pinned + 1024;          // slice end offsets land here
+    uint64_t copied = 0; bool fits = true;
+    auto drain = [&](int s) -> int {                      // slice s is packed once ev_in[1 + s] fires: hand its bytes to the copy engine
+        B200C_CUDA_TRY(c, cudaEventSynchronize(c->ev_in[1 + s]));
+        uint64_t end = h[s];
+        if (end > img_cap) { c->err = "internal error: compressed image exceeds its bound"; return B200C_ECUDA; }
+        if (end > h_cap) fits = false;
+        if (fits && end > copied) {
+            B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_in[1 + s], 0));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h_out + copied, d_img + copied, end - copied, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+        copied = end;
+        return B200C_OK;
+    };
+    for (int s = 0; s < nslices; s++) {
+        const uint64_t a = (uint64_t)s * per, b = std::min<uint64_t>(nchunks, a + per);
+        if (a >= b) { h[s] = s ? h[s - 1] : 0; cudaEventRecord(c->ev_in[1 + s], c->stream); continue; }
+        const uint64_t nb = std::min<uint64_t>(n, b * (uint64_t)chunk_len) - a * (uint64_t)chunk_len;
+        B200C_TRY(compress_slots_device(c, comp, d_in + a * (uint64_t)chunk_len, nb, chunk_len, max_clen, slots + a * (uint64_t)stride, stride, file_len + a, seg_raw + a));
+        B200C_TRY(exclusive_scan<uint32_t>(c, file_len + a, b - a, rel, ws_base + WSC_SCAN0, 0));
+        B200C_LAUNCH(c, k_offs_add_base, (unsigned)((b - a + 1 + 255) / 256), 256, 0, rel, b - a, bases + s, d_offs + a);
+        B200C_LAUNCH(c, k_pack_chunks, (unsigned)((b - a + 3) / 4), 128, 0, slots + a * (uint64_t)stride, stride, file_len + a, d_offs + a, b - a, d_img);
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + s, bases + s + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+        B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[1 + s], c->stream));
+        if (s) B200C_TRY(drain(s - 1));                   // after slice s is queued, so the GPU never waits for the host
+    }
+    B200C_LAUNCH(c, k_digest, (unsigned)((nchunks + 255) / 256), 256, 0, c->d_tables, seg_raw, d_offs, nchunks, acc);
+    B200C_LAUNCH(c, k_digest_final, 1, 1, 0, c->d_tables, d_offs, nchunks, acc);
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + MAX_SLICES, acc + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    B200C_TRY(drain(nslices - 1));
+    B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *out_len = copied; *digest = (uint32_t)h[MAX_SLICES];
+    return B200C_OK;
+}
+
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
                              int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err) {
     if (nchunks == 0) return B200C_OK;

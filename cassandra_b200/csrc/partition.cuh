@@ -290,6 +290,9 @@ __device__ bool reconcile_keep_left(const CParams& P, const MCell& l, const MCel
     return cmp_bytes(P.U + l.voff, l.vlen, P.U + r.voff, r.vlen) >= 0;
 }
 
+// promoted-index slot of the scratch pass: [16 B partition deletion (mfda, ldt)][i32 offsets x nb_max][IndexInfo bytes, IXS_PER_BLOCK budget per block]
+enum { IXS_HEAD = 16, IXS_PER_BLOCK = 204, IXS_BLOCK_STRIDE = 4 + IXS_PER_BLOCK };
+
 // ---- partition writer (SortedTablePartitionWriter + BigFormatPartitionWriter state) ------------------------------------------
 template <bool EMIT> struct PWriter {
     Sink<EMIT> d;                 // Data stream, positioned at the partition start
@@ -319,7 +322,7 @@ template <bool EMIT> __device__ __forceinline__ void write_prefix(Sink<EMIT>& s,
 template <bool EMIT> __device__ __forceinline__ void pw_add_index_block(PWriter<EMIT>& w, const CParams& P) {
     uint64_t cur = w.d.pos - w.start;
     bool emit_info = EMIT && w.ix.on;              // ix.on: this lane stores IndexInfos (final emit of a partition with > 1 block)
-    if (emit_info) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
+    if (emit_info && w.nblocks < w.nblocks_final) { uint32_t o = (uint32_t)w.ix.pos; uint8_t* q = w.ix_offs + 4 * w.nblocks; q[0] = (uint8_t)(o >> 24); q[1] = (uint8_t)(o >> 16); q[2] = (uint8_t)(o >> 8); q[3] = (uint8_t)o; }
     {                                              // the ix sink always counts; it stores only when ix.on
         write_prefix(w.ix, P, w.first); write_prefix(w.ix, P, w.last);
         w.ix.vint(w.block_start);
@@ -498,7 +501,7 @@ template <bool EMIT>
 __device__ void process_partition(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                   const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
                                   const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen,
-                                  uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
+                                  uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
                                   Cur* cur, DT* open_dt, MCell* merged,
                                   PartOut& out, PartStats& st, int& err) {
     Purger pg{P.now, P.gc_before, P.purge_max_ts};
@@ -534,7 +537,9 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;                 // PurgeFunction.applyToDeletion :95-99
 
     PWriter<EMIT> w;
-    w.d.base = dout; w.d.pos = 0; w.d.on = true; w.d.cap = dcap; w.ix.on = EMIT && iout && nblocks_final > 1; w.ix.cap = ~0ull; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
+    // ixs (scratch pass): iout is this partition's promoted-index slot (IXS_* layout), nblocks_final its block capacity, ixs_cap its IndexInfo capacity
+    const bool ixs = EMIT && ixs_cap != 0;
+    w.d.base = dout; w.d.pos = 0; w.d.on = true; w.d.cap = dcap; w.ix.on = EMIT && iout && (ixs || nblocks_final > 1); w.ix.cap = ixs ? (uint64_t)ixs_cap : ~0ull; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
     w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
     // index entry layout (EMIT): [u16 kl][key][vint dpos][vint ipay]{[vint headerLen][DT][vint nblocks][IndexInfo..][i32 offsets..]}
@@ -543,6 +548,7 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     uint32_t pre = fixed + vint_size(hdr_len_known) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
     w.ix.base = (EMIT && iout) ? iout + pre : nullptr; w.ix.pos = 0;
     w.ix_offs = (EMIT && iout) ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
+    if (ixs) { w.ix_offs = iout + IXS_HEAD; w.ix.base = iout + IXS_HEAD + 4 * (size_t)nblocks_final; }
 
     // One code path for every fan-in. m == 1 is the reference's TrivialOneToOne case (UnfilteredRowIterators.java:552-556): rows
     // and markers pass through untouched (no Row.Merger, no marker merger) and only the purge transformation applies.
@@ -634,7 +640,13 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         if (w.nblocks > 1) out.ipay = vint_size(w.header_len) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(w.nblocks) + (uint32_t)w.ix.pos + 4 * w.nblocks;
         st.rows_out += w.rows_out;
         out.ovf = (EMIT && w.d.pos > dcap) ? 1 : 0;
-        if (EMIT && iout) {                                                  // RowIndexEntry.serialize :468-473, IndexedEntry.serialize :625-642
+        if (ixs) {                                                           // the entry itself is assembled by k_index_promoted once positions are known
+            if (w.nblocks > 1) {
+                if (w.ix.pos > w.ix.cap || w.nblocks > nblocks_final) out.ovf = 1;
+                ((int64_t*)iout)[0] = out_pdel.mfda; ((int64_t*)iout)[1] = out_pdel.ldt;
+            }
+        } else if (EMIT && !iout && w.nblocks > 1) out.ovf = 1;              // scratch pass without a slot: re-emit in mode 3
+        else if (EMIT && iout) {                                             // RowIndexEntry.serialize :468-473, IndexedEntry.serialize :625-642
             Sink<true> e{iout, 0, true, ~0ull};
             e.be16(klen); e.copy(P.U + key_off, klen); e.vint(dpos); e.vint(ipay_final);
             if (nblocks_final > 1) { e.vint(w.header_len); write_partition_dt(e, out_pdel); e.vint(nblocks_final); }

@@ -60,7 +60,7 @@ template <int G, int S, bool EMIT>
 __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                        const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
                                        const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen,
-                                       uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final,
+                                       uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
                                        MCell* s_cells, PartOut& out, PartStats& st, int& err) {
     const int lane = tile.thread_rank();
     const bool multi = m > 1;
@@ -102,7 +102,8 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
     const DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;
 
     PWriter<EMIT> w;
-    w.d.base = dout; w.d.pos = 0; w.d.on = (lane == 0); w.d.cap = dcap; w.ix.on = (lane == 0) && EMIT && iout && nblocks_final > 1; w.ix.cap = ~0ull;
+    const bool ixs = EMIT && ixs_cap != 0;           // scratch pass with a promoted-index slot (see process_partition)
+    w.d.base = dout; w.d.pos = 0; w.d.on = (lane == 0); w.d.cap = dcap; w.ix.on = (lane == 0) && EMIT && iout && (ixs || nblocks_final > 1); w.ix.cap = ixs ? (uint64_t)ixs_cap : ~0ull;
     w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
     w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
@@ -112,6 +113,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
         uint32_t pre = fixed + vint_size(hdr_len_known) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
         w.ix.base = (EMIT && iout) ? iout + pre : nullptr; w.ix.pos = 0;
         w.ix_offs = (EMIT && iout) ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
+        if (ixs) { w.ix_offs = iout + IXS_HEAD; w.ix.base = iout + IXS_HEAD + 4 * (size_t)nblocks_final; }
     }
 
 #pragma unroll
@@ -296,7 +298,13 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
         if (w.nblocks > 1) out.ipay = vint_size(w.header_len) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(w.nblocks) + (uint32_t)w.ix.pos + 4 * w.nblocks;
         st.rows_out += w.rows_out;
         out.ovf = (EMIT && w.d.pos > dcap) ? 1 : 0;
-        if (EMIT && iout && lane == 0) {
+        if (ixs) {
+            if (w.nblocks > 1) {
+                if (w.ix.pos > w.ix.cap || w.nblocks > nblocks_final) out.ovf = 1;
+                if (lane == 0) { ((int64_t*)iout)[0] = out_pdel.mfda; ((int64_t*)iout)[1] = out_pdel.ldt; }
+            }
+        } else if (EMIT && !iout && w.nblocks > 1) out.ovf = 1;
+        else if (EMIT && iout && lane == 0) {
             Sink<true> e{iout, 0, true, ~0ull};
             e.be16(klen); e.copy(P.U + key_off, klen); e.vint(dpos); e.vint(ipay_final);
             if (nblocks_final > 1) { e.vint(w.header_len); write_partition_dt(e, out_pdel); e.vint(nblocks_final); }

@@ -180,7 +180,7 @@ def run_b200(args):
     # e2e (host buffers) — fewer steps are fine, the copies dominate
     step(False)
     e_steps = max(1, min(args.steps, 3))
-    edt, ekms, _, elast, _, _ = timed(False, e_steps)
+    edt, ekms, estages, elast, _, _ = timed(False, e_steps)
     e2e = total_in_all * e_steps / edt / 1e6
     h2d = c_in + i_in + 8 * sum(t.nchunks for t in tabs); d2h = c_out + i_out + 8 * int(elast.outputs[0].nchunks)
 
@@ -207,7 +207,8 @@ def run_b200(args):
             "rows_merged_per_s": round(rows * world * args.steps / dt, 0), "input_partitions_per_step": parts_in,
             "merged_row_counts": [int(x) for x in last.merged_row_counts[:nsst]],
             "bytes": {"u_in": u_in, "c_in": c_in, "index_in": i_in, "u_out": u_out, "c_out": c_out, "index_out": i_out},
-            "e2e": {"value": round(e2e, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(edt / e_steps * 1e3, 2)},
+            "e2e": {"value": round(e2e, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(edt / e_steps * 1e3, 2),
+                    "device_ms_per_step": round(ekms, 2), "stage_ms": {n: round(s_, 2) for n, s_ in zip(names, estages)}},
             "gpu_launches": int(launches), "index_slow_path_inputs": int(last.index_slow_path_inputs), "clocks": clocks, "roofline": roof}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(1, args.cpu_sample_mib, 1)

@@ -72,53 +72,34 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                 uint32_t seq = valid ? rd32_at(in32, p) : 0u;
                 uint32_t h = lz4_hash_u16(seq);
                 int cand = valid ? (int)s_tab[h] : 0;
-                // Intra-window dependencies: attempt k must see the table as left by attempts < k. Every valid lane stores its
-                // position tentatively and reads it back: if all read-backs agree, the 32 hashes are distinct, no attempt depends
-                // on another and the candidates loaded above are exact (fast path; lanes past the first hit put the old entry
-                // back). Otherwise the old entries are restored and match.any resolves the chains (slow path).
-                __syncwarp();
-                if (valid) s_tab[h] = (uint16_t)p;
-                __syncwarp();
-                const bool clash = valid && s_tab[h] != (uint16_t)p;
+                // lanes with the same hash. match.any costs several hundred cycles here (one pass per distinct value); 13 ballots, one
+                // per hash bit, are independent of each other and give the same mask. Invalid lanes form a suffix that neither
+                // `prev` (lower lanes only) nor the masked `later_same` tests below can reach, so they need no special key.
+                uint32_t same = FULL_MASK;
+#pragma unroll
+                for (int b = 0; b < LZ4_HASHLOG_U16; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
+                uint32_t prev = same & lt_mask;
+                int src = prev ? (31 - __clz(prev)) : lane;
+                int pc = __shfl_sync(FULL_MASK, p, src);
+                if (prev) cand = pc;
                 bool hit = valid && !putonly && (rd32_at(in32, cand) == seq);
+                uint32_t hits = __ballot_sync(FULL_MASK, hit);
                 uint32_t inval = __ballot_sync(FULL_MASK, !valid);
+                int first_hit = hits ? (__ffs(hits) - 1) : 32;
                 int first_inv = inval ? (__ffs(inval) - 1) : 32;
-                if (!__any_sync(FULL_MASK, clash)) {
-                    uint32_t hits = __ballot_sync(FULL_MASK, hit);
-                    int first_hit = hits ? (__ffs(hits) - 1) : 32;
-                    if (first_hit < first_inv) {
-                        if (valid && lane > first_hit) s_tab[h] = (uint16_t)cand;
-                        ip = __shfl_sync(FULL_MASK, p, first_hit);
-                        match = __shfl_sync(FULL_MASK, cand, first_hit);
-                        immediate = prefixed && first_hit == 1;
-                        break;
-                    }
-                    if (first_inv < 32) { ended = true; break; }
-                } else {
-                    if (valid) s_tab[h] = (uint16_t)cand;          // lanes sharing a hash loaded the same old entry
-                    __syncwarp();
-                    uint32_t same = __match_any_sync(FULL_MASK, valid ? h : (0x10000u | lane));
-                    uint32_t prev = same & lt_mask;
-                    int src = prev ? (31 - __clz(prev)) : lane;
-                    int pc = __shfl_sync(FULL_MASK, p, src);
-                    if (prev) cand = pc;
-                    hit = valid && !putonly && (rd32_at(in32, cand) == seq);
-                    uint32_t hits = __ballot_sync(FULL_MASK, hit);
-                    int first_hit = hits ? (__ffs(hits) - 1) : 32;
-                    if (first_hit < first_inv) {
-                        uint32_t le = (first_hit == 31) ? FULL_MASK : ((2u << first_hit) - 1u);
-                        uint32_t later_same = same & le & ~lt_mask & ~(1u << lane);
-                        if (lane <= first_hit && !later_same) s_tab[h] = (uint16_t)p;
-                        ip = __shfl_sync(FULL_MASK, p, first_hit);
-                        match = __shfl_sync(FULL_MASK, cand, first_hit);
-                        immediate = prefixed && first_hit == 1;
-                        break;
-                    }
-                    if (first_inv < 32) { ended = true; break; }
-                    {
-                        uint32_t later_same = same & ~lt_mask & ~(1u << lane);
-                        if (!later_same) s_tab[h] = (uint16_t)p;
-                    }
+                if (first_hit < first_inv) {
+                    uint32_t le = (first_hit == 31) ? FULL_MASK : ((2u << first_hit) - 1u);
+                    uint32_t later_same = same & le & ~lt_mask & ~(1u << lane);
+                    if (lane <= first_hit && !later_same) s_tab[h] = (uint16_t)p;
+                    ip = __shfl_sync(FULL_MASK, p, first_hit);
+                    match = __shfl_sync(FULL_MASK, cand, first_hit);
+                    immediate = prefixed && first_hit == 1;
+                    break;
+                }
+                if (first_inv < 32) { ended = true; break; }
+                {
+                    uint32_t later_same = same & ~lt_mask & ~(1u << lane);
+                    if (!later_same) s_tab[h] = (uint16_t)p;
                 }
                 __syncwarp();
                 a0 += prefixed ? 30 : 32;

@@ -75,13 +75,15 @@ __global__ void __launch_bounds__(32) k_compress_chunks(const DevTables* __restr
 
 // ---- pack: slots -> dense Data.db image --------------------------------------------------------------------------
 // one warp per chunk; offs = exclusive scan of file_len
+// out_base (optional): device scalar subtracted from the offsets, for an image buffer that holds only a window of the file
 __global__ void __launch_bounds__(128) k_pack_chunks(const uint8_t* __restrict__ slots, int slot_stride, const uint32_t* __restrict__ file_len,
-                                                     const uint64_t* __restrict__ offs, uint64_t nchunks, uint8_t* __restrict__ out) {
+                                                     const uint64_t* __restrict__ offs, uint64_t nchunks, uint8_t* __restrict__ out,
+                                                     const uint64_t* __restrict__ out_base) {
     uint64_t chunk = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (chunk >= nchunks) return;
     int lane = threadIdx.x & 31;
     const uint8_t* s = slots + chunk * (uint64_t)slot_stride;
-    uint8_t* d = out + offs[chunk];
+    uint8_t* d = out + (offs[chunk] - (out_base ? *out_base : 0ull));
     int len = (int)file_len[chunk];
     // head bytes until d is 16-byte aligned, then 16-byte stores assembled from two aligned 16-byte loads
     int head = (int)((16 - ((uintptr_t)d & 15)) & 15); if (head > len) head = len;
@@ -132,15 +134,16 @@ __global__ void k_digest_final(const DevTables* __restrict__ T, const uint64_t* 
 // latency-bound, strictly sequential format needs.
 __global__ void __launch_bounds__(64) k_decompress_chunks(const DevTables* __restrict__ T, int comp,
         const uint8_t* __restrict__ data, uint64_t data_len, const uint64_t* __restrict__ offs, uint64_t nchunks,
-        int chunk_len, int max_clen, uint64_t data_length, uint8_t* out, int verify, ChunkErr* __restrict__ err) {
+        int chunk_len, int max_clen, uint64_t data_length, uint8_t* out, int verify, ChunkErr* __restrict__ err,
+        uint64_t chunk0, uint64_t chunk_end, int tag) {        // this launch covers chunks [chunk0, chunk_end) of the file; tag = input number for error reports
     const int lane = threadIdx.x & 31;
-    const uint64_t chunk = (uint64_t)blockIdx.x * 2 + (threadIdx.x >> 5);
-    if (chunk >= nchunks) return;
+    const uint64_t chunk = chunk0 + (uint64_t)blockIdx.x * 2 + (threadIdx.x >> 5);
+    if (chunk >= chunk_end || chunk >= nchunks) return;
     const uint64_t off = offs[chunk];
     const uint64_t next = (chunk + 1 < nchunks) ? offs[chunk + 1] : data_len;
     const uint64_t ustart = chunk * (uint64_t)chunk_len;
     if (off + 4 > next || next > data_len || ustart >= data_length || next - off - 4 > (uint64_t)(chunk_max_compressed(comp, chunk_len) + chunk_len)) {
-        if (lane == 0) report_chunk_err(err, chunk, 2);
+        if (lane == 0) report_chunk_err(err, ((uint64_t)tag << 40) | chunk, 2);
         return;
     }
     const int clen = (int)(next - off - 4);
@@ -149,12 +152,12 @@ __global__ void __launch_bounds__(64) k_decompress_chunks(const DevTables* __res
     if (verify) {
         uint32_t crc = warp_crc32(T, T->crc_adv128, src, clen, lane);
         uint32_t stored = ((uint32_t)src[clen] << 24) | ((uint32_t)src[clen + 1] << 16) | ((uint32_t)src[clen + 2] << 8) | src[clen + 3];
-        if (crc != stored) { if (lane == 0) report_chunk_err(err, chunk, 1); return; }
+        if (crc != stored) { if (lane == 0) report_chunk_err(err, ((uint64_t)tag << 40) | chunk, 1); return; }
     }
     uint8_t* dst = out + ustart;
     int got;
     if (clen >= max_clen) {                 // CompressedChunkReader.java:116,219: raw chunk (possibly zero padded at the file end)
-        if (clen < ulen) { if (lane == 0) report_chunk_err(err, chunk, 2); return; }
+        if (clen < ulen) { if (lane == 0) report_chunk_err(err, ((uint64_t)tag << 40) | chunk, 2); return; }
         for (int i = lane; i < ulen; i += 32) dst[i] = src[i];
         got = ulen;
     } else if (comp == COMP_LZ4) {
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(64) k_decompress_chunks(const DevTables* __res
         got = (clen == ulen) ? ulen : -1;
         if (got >= 0) for (int i = lane; i < ulen; i += 32) dst[i] = src[i];
     }
-    if (got != ulen && lane == 0) report_chunk_err(err, chunk, 2);
+    if (got != ulen && lane == 0) report_chunk_err(err, ((uint64_t)tag << 40) | chunk, 2);
 }
 
 } // namespace b200c

@@ -16,7 +16,7 @@ __host__ __device__ __forceinline__ int chunk_slot_stride(int comp, int chunk_le
     return (m + 4 + 16 + 15) & ~15;      // bytes + CRC + read slack, 16-byte aligned
 }
 
-struct ChunkErr { unsigned long long first_bad; };   // min over failing chunks of (chunk index << 8 | kind); init ~0
+struct ChunkErr { unsigned long long first_bad; };   // min over failing chunks of (input << 48 | chunk index << 8 | kind); init ~0
 
 __device__ __forceinline__ void report_chunk_err(ChunkErr* e, uint64_t chunk, int kind) {
     atomicMin(&e->first_bad, ((unsigned long long)chunk << 8) | (unsigned long long)kind);

@@ -20,6 +20,7 @@
 #include <climits>
 #include <vector>
 #include <algorithm>
+#include <functional>
 
 using namespace b200c;
 
@@ -32,17 +33,18 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
 int pack_digest_device(b200c_ctx* c, const uint8_t* slots, int stride, const uint32_t* file_len, const uint32_t* seg_raw, uint64_t nchunks,
                        uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs, uint64_t* out_len, uint32_t* digest, int ws_base);
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
-                             int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err);
+                             int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err, uint64_t chunk0, uint64_t count, int tag);
 int compress_stream_to_host(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
                             uint8_t* d_img, uint64_t img_cap, uint8_t* h_out, uint64_t h_cap, uint64_t* d_offs,
                             uint64_t* out_len, uint32_t* digest, int ws_base);
 
 enum { IB = 256 };                       // Index.db speculation block
+enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pieces per call; slots of b200c_ctx::ev_pool
 #define NONE64 (~0ull)
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -249,6 +251,26 @@ __global__ void k_input_ranges(const CParams* __restrict__ Pp, const uint64_t* _
     if (tlo != I64_MIN) { uint64_t a = 0, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= tlo) a = m + 1; else b = m; } lo = a; }   // first > tlo
     { uint64_t a = lo, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= thi) a = m + 1; else b = m; } hi = a; }                     // first > thi
     range[2 * i] = lo; range[2 * i + 1] = hi;
+}
+
+// token-range pieces: for piece r and input i the byte range [plan[2k], plan[2k+1]) of U (k = r * K + i) holding the partitions with
+// token in (T[r], T[r+1]]; same bounds as k_input_ranges
+__global__ void k_range_plan(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ pcount,
+                             const int64_t* __restrict__ tok, const uint64_t* __restrict__ upos, const int64_t* __restrict__ T, int nr, uint64_t* __restrict__ plan) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const CParams& P = *Pp;
+    if (k >= nr * P.ninputs) return;
+    int r = k / P.ninputs, i = k % P.ninputs;
+    uint64_t n = pcount[i]; const int64_t* t = tok + pbase[i];
+    int64_t tlo = T[r], thi = T[r + 1];
+    uint64_t lo = 0, hi = n;
+    if (tlo != I64_MIN) { uint64_t a = 0, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= tlo) a = m + 1; else b = m; } lo = a; }
+    { uint64_t a = lo, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= thi) a = m + 1; else b = m; } hi = a; }
+    plan[2 * k] = upos[pbase[i] + lo]; plan[2 * k + 1] = upos[pbase[i] + hi];
+}
+__global__ void __launch_bounds__(256) k_add_u64(uint64_t* __restrict__ a, uint64_t n, uint64_t v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += v;
 }
 
 // ---- K3: partition-level merge -------------------------------------------------------------------------------------------------
@@ -610,8 +632,12 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) { c->err = "static rows / tombstone_option / strict liveness"; return B200C_EUNSUPPORTED; }
     if (m->nclustering > MAXCLUST || m->ncolumns >= 64 || m->ncolumns < 0) { c->err = "schema outside the supported envelope"; return B200C_EUNSUPPORTED; }
     if (res->noutputs_cap < 1 || !res->outputs) { c->err = "no output slot"; return B200C_EINVAL; }
+    if (m->out_chunk_len <= 0 || m->out_chunk_len > 65536 || (m->out_chunk_len & (m->out_chunk_len - 1))) { c->err = "output chunk_len"; return B200C_EUNSUPPORTED; }
     const bool dev = flags & B200C_FLAG_DEVICE_PTRS;
+    const bool lcs = m->max_sstable_bytes != 0;
     const int K = m->ninputs;
+    // whatever way this call ends, nothing may still be copying from or into the caller's buffers
+    struct CopyGuard { b200c_ctx* c; ~CopyGuard() { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->copy_out); } } copy_guard{c};
 
     // ---- layout of the concatenated device buffers -------------------------------------------------------------------------------
     std::vector<uint64_t> ubase(K + 1), ibase(K + 1), cbase(K + 1), obase(K + 1), bbase(K + 1);
@@ -622,6 +648,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (in.chunk_len <= 0 || in.chunk_len > 65536 || (in.chunk_len & (in.chunk_len - 1))) { c->err = "input chunk_len"; return B200C_EUNSUPPORTED; }
         if (in.ncolumns < 0 || in.ncolumns >= 64) { c->err = "input columns"; return B200C_EUNSUPPORTED; }
         if (in.nchunks != (in.data_length + in.chunk_len - 1) / (uint64_t)in.chunk_len) { c->err = "chunk count does not match data_length"; return B200C_EINVAL; }
+        if (in.compressor != COMP_LZ4 && in.compressor != COMP_SNAPPY && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
         ubase[i] = uo; uo += (in.data_length + 64 + 65535) & ~65535ull;
         ibase[i] = io; io += (in.index_len + 64 + 255) & ~255ull;
         cbase[i] = co; co += (in.data_len + 64 + 255) & ~255ull;
@@ -644,6 +671,17 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     hp.o_min_ts = m->out_stats.min_timestamp; hp.o_min_ldt = m->out_stats.min_local_deletion_time; hp.o_min_ttl = m->out_stats.min_ttl;
     hp.now = m->now_in_sec; hp.gc_before = m->gc_before; hp.purge_max_ts = m->purge_max_timestamp;
 
+    // Token-range streaming (host buffers, one output file): Index.db goes to the device first; once K2 has turned it into tokens and
+    // positions the token space is cut into `want_ranges` pieces, the Data.db chunks each piece needs are copied piece by piece on the
+    // copy stream, and K1/K3/K4/K5 of piece r run underneath the copies of the pieces after it and the read-back of the pieces before
+    // it. Device-resident inputs and multi-file (LCS) outputs run as one piece.
+    int want_ranges = 1; bool forced_ranges = false;      // B200C_RANGES=n: test/tuning override of the piece count
+    if (!dev && !lcs) {
+        want_ranges = (int)std::min<uint64_t>(MAX_RANGES, std::max<uint64_t>(1, co / (768ull << 20)));
+        if (const char* e = getenv("B200C_RANGES")) { want_ranges = std::max(1, std::min((int)MAX_RANGES, atoi(e))); forced_ranges = true; }
+    }
+    const bool deferred = !dev && !lcs;               // Data.db copies are scheduled after K2 (even when a single piece results)
+
     uint8_t *U, *CD, *IDX; uint64_t* CO; CParams* dP; uint64_t* d_bbase; DevErr* d_err; ChunkErr* d_cerr; RunStats* d_stats; unsigned long long* d_hist;
     B200C_TRY(ws_typed(c, WS_U, uo + 64, &U));
     B200C_TRY(ws_typed(c, WS_CD, co + 64, &CD));
@@ -661,26 +699,52 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_CUDA_TRY(c, cudaMemcpyAsync(d_bbase, bbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
     cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     uint64_t bytes_read = 0;
-    // inputs are staged on a second stream, one event per input, so that K1 of input i overlaps the copy of input i+1
+    // inputs are staged on a second stream, one event per input, so that the kernels of input i overlap the copy of input i+1
     // (the workspace was possibly re-allocated above: make sure that is ordered before the copies)
     cudaStream_t cs = c->copy_stream;
     B200C_CUDA_TRY(c, cudaEventRecord(c->ev0, st));
     B200C_CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev0, 0));
+    std::vector<uint64_t> h2d_next(K, 0), k1_next(K, 0);      // deferred mode: first chunk of input i not yet copied / not yet decompressed
+    auto chunk_off = [&](int i, uint64_t ch) -> uint64_t { const b200c_input& in = m->inputs[i]; return ch >= in.nchunks ? in.data_len : in.chunk_offsets[ch]; };
+    auto copy_chunks = [&](int i, uint64_t a, uint64_t b) -> int {      // compressed bytes of chunks [a, b) of input i -> CD (host pointers only)
+        const b200c_input& in = m->inputs[i];
+        if (a >= b) return B200C_OK;
+        uint64_t lo = chunk_off(i, a), hi = chunk_off(i, b);
+        if (lo > hi || hi > in.data_len) { c->err = "chunk offsets of input " + std::to_string(i) + " are not increasing"; res->corruption.input = i; res->corruption.kind = 2; res->corruption.chunk = a; res->corruption.offset = 0; return B200C_ECORRUPT; }
+        if (hi > lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i] + lo, in.data + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+        return B200C_OK;
+    };
     for (int i = 0; i < K; i++) {
         const b200c_input& in = m->inputs[i];
         bytes_read += in.data_length;
-        if (in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, cs));
+        if (!deferred && in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, cs));
         if (in.nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(CO + obase[i], in.chunk_offsets, in.nchunks * 8, kind, cs));
         if (in.index_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index, in.index_len, kind, cs));
         B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[i], cs));
     }
+    if (deferred && want_ranges > 1)         // keep the link busy while K2 finishes: the head of every Data.db is needed by the first piece
+        for (int i = 0; i < K; i++) { uint64_t pre = m->inputs[i].nchunks / want_ranges; B200C_TRY(copy_chunks(i, 0, pre)); h2d_next[i] = pre; }
     c->prog_total.store(bytes_read); c->prog_scanned.store(0);
     timing_begin(c);
+
+    // stage clock: marks on the main stream; the time between two marks is charged to the stage of the first
+    struct Mark { int stage; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    auto mark = [&](int stage) {
+        size_t k = marks.size();
+        if (k >= c->ev_marks.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_marks.push_back(e); }
+        cudaEventRecord(c->ev_marks[k], st); marks.push_back(Mark{stage, c->ev_marks[k]});
+    };
+    auto finish_marks = [&]() {
+        for (int k = 0; k < 8; k++) c->stage_ms[k] = 0;
+        for (size_t k = 0; k + 1 < marks.size(); k++) { float ms = 0; cudaEventElapsedTime(&ms, marks[k].ev, marks[k + 1].ev); if (marks[k].stage >= 0) c->stage_ms[marks[k].stage] += ms; }
+        c->nstages = 6;
+    };
     c->nstages = 0;
-    cudaEventRecord(c->ev_stage[0], st);
+    mark(0);
 
     // ---- K1: decompress + verify, with the speculative part of K2 (find / chain / prove) per input right behind it so that both
-    //      run underneath the host->device copies of the following inputs -------------------------------------------------------------
+    //      run underneath the host->device copies of the following inputs (deferred mode: K1 runs per token range further down) ------
     c->prog_stage.store(1);
     uint64_t *d_istart, *d_iend, *d_iscan; uint32_t *d_icnt, *d_ihit, *d_ibad;
     B200C_TRY(ws_typed(c, WS_ISTART, nblocks + 1, &d_istart));
@@ -691,12 +755,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_ISCAN, nblocks + 2, &d_iscan));
     if (nblocks) B200C_CUDA_TRY(c, cudaMemsetAsync(d_ihit, 0, nblocks * 4, st));
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_ibad, 0, (K + 1) * 4, st));
-    for (int i = 0; i < K; i++) {
+    auto k1 = [&](int i, uint64_t a, uint64_t b) -> int {           // chunks [a, b) of input i
         const b200c_input& in = m->inputs[i];
-        if (in.compressor != COMP_LZ4 && in.compressor != COMP_SNAPPY && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
+        if (a >= b) return B200C_OK;
+        return decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
+                                        in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr, a, b - a, i);
+    };
+    for (int i = 0; i < K; i++) {
         B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0));
-        B200C_TRY(decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
-                                           in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr));
+        if (!deferred) B200C_TRY(k1(i, 0, m->inputs[i].nchunks));
         const uint64_t nb = bbase[i + 1] - bbase[i];
         if (nb) {
             unsigned g = (unsigned)((nb + 255) / 256);
@@ -708,9 +775,16 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     }
     uint64_t* h = (uint64_t*)c->h_pinned;
     auto check_cancel = [&]() -> int { if (c->cancel.load()) { c->err = "cancelled"; cudaStreamSynchronize(st); return B200C_ECANCELLED; } return B200C_OK; };
+    auto chunk_error = [&](uint64_t word) -> int {                  // word = d_cerr: (input << 48 | chunk << 8 | kind)
+        int which = (int)(word >> 48), kindc = (int)(word & 0xff); uint64_t chunk = (word >> 8) & 0xFFFFFFFFFFull;
+        res->corruption.input = which; res->corruption.kind = kindc; res->corruption.chunk = chunk; res->corruption.offset = 0;
+        c->err = std::string(kindc == 1 ? "chunk CRC mismatch" : "malformed compressed chunk") + " in input " + std::to_string(which) + " chunk " + std::to_string(chunk);
+        timing_end(c);
+        return B200C_ECORRUPT;
+    };
 
     // ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
-    cudaEventRecord(c->ev_stage[1], st);
+    mark(1);
     c->prog_stage.store(2);
     uint64_t total_parts = 0;
     std::vector<uint64_t> pcount(K, 0), pbase(K + 1, 0);
@@ -720,7 +794,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     } else B200C_CUDA_TRY(c, cudaMemsetAsync(d_iscan, 0, 16, st));
     // read back: chunk errors, index errors, per-input partition counts
     {
-        std::vector<uint64_t> tmp(K + 1);
         for (int i = 0; i <= K; i++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8 + i, d_iscan + bbase[i], 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cerr, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_err, 8, cudaMemcpyDeviceToHost, st));
@@ -728,24 +801,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
         res->index_slow_path_inputs = 0;
         if (nblocks) for (int i = 0; i < K; i++) res->index_slow_path_inputs += ((uint32_t*)(h + 300))[i] ? 1 : 0;
-        if (h[0] != ~0ull) {
-            // the decompress kernels share one error word; re-run attribution on the host side: find the input owning the failing launch
-            uint64_t chunk = h[0] >> 8; int kindc = (int)(h[0] & 0xff);
-            int which = 0;   // first input whose chunk index range contains a failure: verify per input (rare path, so simply re-run per input)
-            for (int i = 0; i < K; i++) {
-                const b200c_input& in = m->inputs[i];
-                B200C_CUDA_TRY(c, cudaMemsetAsync(d_cerr, 0xFF, 64, st));
-                B200C_TRY(decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
-                                                   in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr));
-                B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cerr, 8, cudaMemcpyDeviceToHost, st));
-                B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-                if (h[0] != ~0ull) { which = i; chunk = h[0] >> 8; kindc = (int)(h[0] & 0xff); break; }
-            }
-            res->corruption.input = which; res->corruption.kind = kindc; res->corruption.chunk = chunk; res->corruption.offset = 0;
-            c->err = std::string(kindc == 1 ? "chunk CRC mismatch" : "malformed compressed chunk") + " in input " + std::to_string(which) + " chunk " + std::to_string(chunk);
-            timing_end(c);
-            return B200C_ECORRUPT;
-        }
+        if (h[0] != ~0ull) return chunk_error(h[0]);
         if (h[1] != ~0ull) {
             res->corruption.input = (int)((h[1] >> 48) & 0xFF); res->corruption.kind = (int)(h[1] >> 56); res->corruption.chunk = 0; res->corruption.offset = h[1] & 0xFFFFFFFFFFFFull;
             c->err = "malformed Index.db in input " + std::to_string(res->corruption.input);
@@ -756,7 +812,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         pbase[K] = total_parts;
     }
     B200C_TRY(check_cancel());
-    c->prog_scanned.store(bytes_read / 4);
     if (total_parts - K >= (1ull << 40)) { c->err = "too many partitions"; return B200C_EUNSUPPORTED; }
 
     int64_t* d_tok; uint64_t *d_kp, *d_upos, *d_pbase, *d_pcount, *d_range; uint16_t* d_klen;
@@ -771,239 +826,343 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
                               d_tok, d_kp, d_klen, d_upos, d_err);
     B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range);
-
-    // ---- K3: partition merge -------------------------------------------------------------------------------------------------------
-    cudaEventRecord(c->ev_stage[2], st);
-    c->prog_stage.store(3);
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-    if (h[200] != ~0ull) {
-        res->corruption.input = (int)((h[200] >> 48) & 0xFF); res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = h[200] & 0xFFFFFFFFFFFFull;
+    auto index_data_mismatch = [&](uint64_t word) -> int {
+        res->corruption.input = (int)((word >> 48) & 0xFF); res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = word & 0xFFFFFFFFFFFFull;
         c->err = "Index.db does not match Data.db in input " + std::to_string(res->corruption.input);
         timing_end(c);
         return B200C_ECORRUPT;
-    }
-    uint64_t ncontrib = 0;
-    for (int i = 0; i < K; i++) ncontrib += h[2 * i + 1] - h[2 * i];
-    const uint64_t nbuckets = std::max<uint64_t>(1, ncontrib / 256);
-    uint64_t *d_bstart, *d_contrib, *d_opidx; uint32_t* d_head; MergeGeom* d_geom;
-    B200C_TRY(ws_typed(c, WS_BSTART, (nbuckets + 1) * K + 8, &d_bstart)); d_geom = (MergeGeom*)(d_range + 2 * K + 2);
-    B200C_TRY(ws_typed(c, WS_CONTRIB, ncontrib + 1, &d_contrib));
-    B200C_TRY(ws_typed(c, WS_HEAD, ncontrib + 1, &d_head));
-    B200C_TRY(ws_typed(c, WS_OPIDX, ncontrib + 2, &d_opidx));
-    uint64_t nparts = 0;
-    if (ncontrib) {
-        B200C_LAUNCH(c, k_merge_geom, 1, 1, 0, dP, d_pbase, d_range, d_tok, nbuckets, d_geom);
-        B200C_LAUNCH(c, k_bucket_bounds, (unsigned)(((nbuckets + 1) * K + 255) / 256), 256, 0, dP, d_pbase, d_range, d_tok, d_geom, d_bstart);
-        B200C_LAUNCH(c, k_merge_buckets, (unsigned)((nbuckets + 3) / 4), 128, 0, dP, d_pbase, d_range, d_tok, d_kp, d_klen, d_upos, d_bstart, nbuckets, d_contrib, d_head, d_hist);
-        B200C_TRY(exclusive_scan<uint32_t>(c, d_head, ncontrib, d_opidx, WS_SCANA, 0));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_opidx + ncontrib, 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-        nparts = h[0];
-    }
-    if (nparts >= (1ull << 32)) { c->err = "too many output partitions"; return B200C_EUNSUPPORTED; }
-    uint64_t* d_opfirst;
-    B200C_TRY(ws_typed(c, WS_OPFIRST, nparts + 2, &d_opfirst));
-    uint32_t* d_list; unsigned long long* d_cursor = nullptr; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
-    B200C_TRY(ws_typed(c, WS_LIST, nparts + 1, &d_list));
-    B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
-    B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
-    uint32_t* d_icap; uint64_t* d_ioff;
-    B200C_TRY(ws_typed(c, WS_ICAP, nparts + 1, &d_icap));
-    B200C_TRY(ws_typed(c, WS_IOFF, nparts + 2, &d_ioff));
-    uint64_t n_le8 = 0, n_le16 = 0, n_le32 = 0;
-    if (ncontrib) {
-        B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
-        // counting sort of the output partitions by (fan-in, size bucket)
-        B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound,
-                     (uint32_t)std::min<uint64_t>(std::max<int64_t>(1, m->column_index_size), 0x7fffffff), d_icap);
-        // tile = token-contiguous run of output partitions whose inputs total ~32 MiB
-        uint64_t per_part = std::max<uint64_t>(1, bytes_read / std::max<uint64_t>(1, nparts));
-        uint32_t tile_shift = 12; while (tile_shift < 24 && ((1ull << (tile_shift + 1)) * per_part) <= (32ull << 20)) tile_shift++;
-        const uint64_t ntiles = (nparts >> tile_shift) + 1, nkeys = 4 * ntiles * SORT_BINS;
-        B200C_TRY(ws_typed(c, WS_CURSOR, nkeys + 2, &d_cursor));
-        B200C_CUDA_TRY(c, cudaMemsetAsync(d_cursor, 0, (nkeys + 2) * 8, st));
-        B200C_LAUNCH(c, k_class_hist, 1184, 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor);
-        B200C_TRY(exclusive_scan<uint64_t>(c, (const uint64_t*)d_cursor, nkeys, (uint64_t*)d_cursor, WS_SCANA, 0));
-        for (int k = 1; k <= 3; k++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512 + k, (uint64_t*)d_cursor + (uint64_t)k * ntiles * SORT_BINS, 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-        n_le8 = h[513]; n_le16 = h[514]; n_le32 = h[515];
-        B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor, d_list);
-    }
-    B200C_TRY(check_cancel());
-    c->prog_scanned.store(bytes_read / 2);
-
-    // ---- K4: row merge + serialise ---------------------------------------------------------------------------------------------------
-    cudaEventRecord(c->ev_stage[3], st);
-    c->prog_stage.store(4);
-    uint64_t *d_dsize, *d_dpos, *d_ipos; uint32_t *d_ipay, *d_nblk, *d_ihead, *d_isize;
-    B200C_TRY(ws_typed(c, WS_DSIZE, nparts + 1, &d_dsize));
-    B200C_TRY(ws_typed(c, WS_DPOS, nparts + 2, &d_dpos));
-    B200C_TRY(ws_typed(c, WS_IPOS, nparts + 2, &d_ipos));
-    B200C_TRY(ws_typed(c, WS_IPAY, nparts + 1, &d_ipay));
-    B200C_TRY(ws_typed(c, WS_NBLK, nparts + 1, &d_nblk));
-    B200C_TRY(ws_typed(c, WS_IHEAD, nparts + 1, &d_ihead));
-    B200C_TRY(ws_typed(c, WS_ISIZE, nparts + 1, &d_isize));
-    uint64_t ulen_out = 0, ilen_out = 0;
-    uint32_t *d_stmunf, *d_strows; uint8_t* d_ovf;
-    B200C_TRY(ws_typed(c, WS_STMUNF, nparts + 1, &d_stmunf));
-    B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
-    B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
-    const size_t cols_s = m->ncolumns <= K4_SMEM_COLS ? (size_t)m->ncolumns * sizeof(MCell) : 0;
-    const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
-    static const bool two_pass = getenv("B200C_K4_TWO_PASS") != nullptr;     // A/B switch: size pass + full emit pass instead of scratch + gather
-    K4Args ka; memset(&ka, 0, sizeof(ka));
-    ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen;
-    ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
-    ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts; ka.m3_nblk = two_pass ? 1 : 0;
-    // one launch per fan-in class over its slice of the sorted list
-    auto launch_k4 = [&](int mode) -> int {
-        ka.mode = mode;
-        const bool emit = mode != 0;
-        if (n_le8) {
-            unsigned g = (unsigned)((n_le8 + 127) / 128);
-            if (emit) B200C_LAUNCH(c, (k_partition_thr<8, 128, true>), g, 128, smem8, ka, 0ull, n_le8);
-            else B200C_LAUNCH(c, (k_partition_thr<8, 128, false>), g, 128, smem8, ka, 0ull, n_le8);
-        }
-        if (n_le16 > n_le8) {
-            unsigned g = (unsigned)((n_le16 - n_le8 + 63) / 64);
-            if (emit) B200C_LAUNCH(c, (k_partition_thr<16, 64, true>), g, 64, smem16, ka, n_le8, n_le16);
-            else B200C_LAUNCH(c, (k_partition_thr<16, 64, false>), g, 64, smem16, ka, n_le8, n_le16);
-        }
-        if (n_le32 > n_le16) {
-            unsigned g = (unsigned)((n_le32 - n_le16 + 3) / 4);
-            if (emit) B200C_LAUNCH(c, (k_partition_warp<1, true>), g, 128, cell_smem32, ka, n_le16, n_le32);
-            else B200C_LAUNCH(c, (k_partition_warp<1, false>), g, 128, cell_smem32, ka, n_le16, n_le32);
-        }
-        if (nparts > n_le32) {
-            unsigned g = (unsigned)((nparts - n_le32 + 3) / 4);
-            if (emit) B200C_LAUNCH(c, (k_partition_warp<2, true>), g, 128, cell_smem32, ka, n_le32, nparts);
-            else B200C_LAUNCH(c, (k_partition_warp<2, false>), g, 128, cell_smem32, ka, n_le32, nparts);
-        }
-        return B200C_OK;
     };
-    if (c->k4_attr_set != (int)(smem8 + 1)) {      // > 48 KiB of dynamic shared memory needs an explicit opt-in, once per context/device
-        cudaFuncSetAttribute(k_partition_thr<8, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
-        cudaFuncSetAttribute(k_partition_thr<8, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
-        cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
-        cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
-        c->k4_attr_set = (int)(smem8 + 1);
-    }
-    uint8_t *SCRATCH = nullptr, *ISCR = nullptr;
-    if (nparts) {
-        if (two_pass) {
-            B200C_CUDA_TRY(c, cudaMemsetAsync(d_ovf, 0, nparts, st));
-            B200C_TRY(launch_k4(0));
-        } else {
-            B200C_TRY(exclusive_scan<uint64_t>(c, d_bound, nparts, d_bpos, WS_SCANA, 0));
-            B200C_TRY(exclusive_scan<uint32_t>(c, d_icap, nparts, d_ioff, WS_SCANA + 3, 0));
-            B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_bpos + nparts, 8, cudaMemcpyDeviceToHost, st));
-            B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_ioff + nparts, 8, cudaMemcpyDeviceToHost, st));
+    if (h[200] != ~0ull) return index_data_mismatch(h[200]);
+
+    // ---- token ranges --------------------------------------------------------------------------------------------------------------
+    // T[0] < T[1] < ... < T[nr]: piece r merges the partitions with token in (T[r], T[r+1]] (T[0] = I64_MIN: from the first one)
+    std::vector<int64_t> T{m->token_lo, m->token_hi};
+    if (want_ranges > 1) {
+        int imax = 0; uint64_t nmax = 0;
+        for (int i = 0; i < K; i++) { uint64_t n = h[2 * i + 1] - h[2 * i]; if (n > nmax) { nmax = n; imax = i; } }
+        if (nmax >= (uint64_t)want_ranges * (forced_ranges ? 2 : 4096)) {   // quantiles of the largest input's tokens
+            const uint64_t lo = h[2 * imax];
+            for (int r = 1; r < want_ranges; r++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 600 + r, d_tok + pbase[imax] + lo + nmax * r / want_ranges, 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-            B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
-            B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
-            ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
-            B200C_TRY(launch_k4(1));
+            T.pop_back();
+            for (int r = 1; r < want_ranges; r++) { int64_t t = (int64_t)h[600 + r]; if (t > T.back() && t < m->token_hi) T.push_back(t); }
+            T.push_back(m->token_hi);
         }
-        B200C_LAUNCH(c, k_sum_stats, 1184, 256, 0, nparts, d_dsize, d_stmunf, d_strows, d_stats);
-        B200C_TRY(exclusive_scan<uint64_t>(c, d_dsize, nparts, d_dpos, WS_SCANA, 0));
-        B200C_LAUNCH(c, k_index_sizes, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_dsize, d_dpos, d_ipay, d_ihead, d_isize);
-        B200C_TRY(exclusive_scan<uint32_t>(c, d_isize, nparts, d_ipos, WS_SCANA + 3, 0));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_dpos + nparts, 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_ipos + nparts, 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 2, d_err, 8, cudaMemcpyDeviceToHost, st));
+    }
+    const int nr = (int)T.size() - 1;
+    // what each piece needs from each input: chunks to copy (deferred mode) and to decompress
+    struct Need { uint64_t h2d_a, h2d_b, k1_a, k1_b; };
+    std::vector<Need> need((size_t)nr * K, Need{0, 0, 0, 0});
+    std::vector<uint64_t> range_bytes(nr, bytes_read);
+    if (deferred) {
+        int64_t* d_T; uint64_t* d_plan;
+        B200C_TRY(ws_typed(c, WS_PLAN, (size_t)nr + 2 + 2 * (size_t)nr * K, &d_T)); d_plan = (uint64_t*)(d_T + nr + 2);
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_T, T.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, st));
+        B200C_LAUNCH(c, k_range_plan, (unsigned)((nr * K + 63) / 64), 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, d_T, nr, d_plan);
+        uint64_t* hplan = h + 2048;
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(hplan, d_plan, 2 * (size_t)nr * K * 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-        if (h[2] != ~0ull) {
-            int kinde = (int)(h[2] >> 56);
-            res->corruption.input = (int)((h[2] >> 48) & 0xFF); res->corruption.kind = 4; res->corruption.chunk = 0; res->corruption.offset = h[2] & 0xFFFFFFFFFFFFull;
-            timing_end(c);
-            if (kinde == 9) { c->err = "unsupported feature in input " + std::to_string(res->corruption.input) + " (static row, complex column or shadowable deletion)"; return B200C_EUNSUPPORTED; }
-            c->err = "malformed Data.db in input " + std::to_string(res->corruption.input) + " near offset " + std::to_string(res->corruption.offset);
-            return B200C_ECORRUPT;
+        for (int r = 0; r < nr; r++) {
+            uint64_t tot = 0;
+            for (int i = 0; i < K; i++) {
+                const b200c_input& in = m->inputs[i];
+                uint64_t a = hplan[2 * ((size_t)r * K + i)], b = hplan[2 * ((size_t)r * K + i) + 1];
+                if (a < ubase[i] || b < a || b > ubase[i] + in.data_length) return index_data_mismatch(((uint64_t)i << 48));
+                a -= ubase[i]; b -= ubase[i]; tot += b - a;
+                Need& nd = need[(size_t)r * K + i];
+                if (b > a) {
+                    uint64_t ca = a / in.chunk_len, cb = std::min<uint64_t>(in.nchunks, (b + in.chunk_len - 1) / in.chunk_len);
+                    nd.h2d_a = std::max(ca, h2d_next[i]); nd.h2d_b = std::max(cb, nd.h2d_a); h2d_next[i] = nd.h2d_b;
+                    nd.k1_a = std::max(ca, k1_next[i]); nd.k1_b = std::max(cb, nd.k1_a); k1_next[i] = nd.k1_b;
+                }
+            }
+            range_bytes[r] = tot;
         }
-        ulen_out = h[0]; ilen_out = h[1];
-    }
-    B200C_TRY(check_cancel());
-    cudaEventRecord(c->ev_stage[4], st);
-    uint8_t *UOUT, *IOUT;
-    B200C_TRY(ws_typed(c, WS_UOUT, ulen_out + 64, &UOUT));
-    B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
-    if (nparts && ulen_out) {
-        ka.dbase = UOUT; ka.iout = IOUT; ka.doff = nullptr; ka.dcapv = nullptr;
-        if (two_pass) B200C_TRY(launch_k4(2));
-        else {
-            B200C_LAUNCH(c, k_gather, (unsigned)((nparts + 7) / 8), 256, 0, nparts, d_dsize, d_dpos, d_bpos, d_ovf, SCRATCH, UOUT);
-            B200C_LAUNCH(c, k_index_simple, (unsigned)((nparts + 255) / 256), 256, 0, dP, nparts, d_contrib, d_opfirst, d_upos, d_pbase, d_dsize, d_dpos, d_nblk, d_ovf, d_ihead, d_ipos, IOUT);
-            B200C_LAUNCH(c, k_index_promoted, (unsigned)((nparts + 127) / 128), 128, 0, dP, nparts, d_contrib, d_opfirst, d_upos, d_pbase, d_dsize, d_dpos, d_nblk, d_ovf, d_ihead, d_ipay, d_ipos,
-                         d_ioff, d_icap, ISCR, IOUT);
-            B200C_TRY(launch_k4(3));
+        // all copies are queued now, piece after piece; EV_RANGE + r fires when piece r is on the device
+        for (int r = 0; r < nr; r++) {
+            for (int i = 0; i < K; i++) B200C_TRY(copy_chunks(i, need[(size_t)r * K + i].h2d_a, need[(size_t)r * K + i].h2d_b));
+            B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[EV_RANGE + r], cs));
         }
     }
+
+    // ---- per-piece state -------------------------------------------------------------------------------------------------------------
+    const bool to_host_stream = !dev && !lcs;          // one output file in host memory: K5 pieces leave through an OutStream
+    static const bool two_pass = getenv("B200C_K4_TWO_PASS") != nullptr;     // A/B switch: size pass + full emit pass instead of scratch + gather
+    b200c_output& out0 = res->outputs[0];
+    OutStream os;
+    if (to_host_stream) B200C_TRY(out_stream_begin(os, c, m->out_compressor, m->out_chunk_len, m->out_max_compressed_len, out0.data, out0.data_cap, WS_CODEC));
+    const uint64_t L = (uint64_t)m->out_chunk_len;
+    uint64_t ubase_total = 0, ilen_total = 0, ncontrib_total = 0, nparts_total = 0;
+    uint64_t tail_len = 0; const uint8_t* tail_ptr = nullptr;       // bytes of the merged stream not yet handed to K5 (< one chunk)
+    bool index_fits = true;
+    // arrays that outlive the loop when there is a single piece (the LCS writer below works on them)
+    uint64_t nparts = 0, ulen_out = 0, ilen_out = 0;
+    uint64_t *d_dsize = nullptr, *d_dpos = nullptr, *d_ipos = nullptr, *d_contrib = nullptr, *d_opfirst = nullptr, *d_ioff = nullptr; uint32_t *d_ipay = nullptr, *d_nblk = nullptr, *d_ihead = nullptr, *d_isize = nullptr, *d_icap = nullptr;
+    uint32_t *d_stmunf = nullptr, *d_strows = nullptr; uint8_t* d_ovf = nullptr;
+    uint8_t *UOUT = nullptr, *IOUT = nullptr, *ISCR = nullptr;
+    K4Args ka; memset(&ka, 0, sizeof(ka));
+    std::function<int(int)> launch_k4;
+
+    for (int r = 0; r < nr; r++) {
+        B200C_TRY(check_cancel());
+        // ---- K1 of this piece (deferred mode) -----------------------------------------------------------------------------------------
+        mark(0);
+        c->prog_stage.store(1);
+        if (deferred) {
+            B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_pool[EV_RANGE + r], 0));
+            for (int i = 0; i < K; i++) B200C_TRY(k1(i, need[(size_t)r * K + i].k1_a, need[(size_t)r * K + i].k1_b));
+        }
+        // ---- K3: partition merge -------------------------------------------------------------------------------------------------------
+        mark(2);
+        c->prog_stage.store(3);
+        B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, T[r], T[r + 1], d_range);
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_cerr, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (h[200] != ~0ull) return chunk_error(h[200]);
+        uint64_t ncontrib = 0;
+        for (int i = 0; i < K; i++) ncontrib += h[2 * i + 1] - h[2 * i];
+        ncontrib_total += ncontrib;
+        const uint64_t nbuckets = std::max<uint64_t>(1, ncontrib / 256);
+        uint64_t *d_bstart, *d_opidx; uint32_t* d_head; MergeGeom* d_geom;
+        B200C_TRY(ws_typed(c, WS_BSTART, (nbuckets + 1) * K + 8, &d_bstart)); d_geom = (MergeGeom*)(d_range + 2 * K + 2);
+        B200C_TRY(ws_typed(c, WS_CONTRIB, ncontrib + 1, &d_contrib));
+        B200C_TRY(ws_typed(c, WS_HEAD, ncontrib + 1, &d_head));
+        B200C_TRY(ws_typed(c, WS_OPIDX, ncontrib + 2, &d_opidx));
+        nparts = 0;
+        if (ncontrib) {
+            B200C_LAUNCH(c, k_merge_geom, 1, 1, 0, dP, d_pbase, d_range, d_tok, nbuckets, d_geom);
+            B200C_LAUNCH(c, k_bucket_bounds, (unsigned)(((nbuckets + 1) * K + 255) / 256), 256, 0, dP, d_pbase, d_range, d_tok, d_geom, d_bstart);
+            B200C_LAUNCH(c, k_merge_buckets, (unsigned)((nbuckets + 3) / 4), 128, 0, dP, d_pbase, d_range, d_tok, d_kp, d_klen, d_upos, d_bstart, nbuckets, d_contrib, d_head, d_hist);
+            B200C_TRY(exclusive_scan<uint32_t>(c, d_head, ncontrib, d_opidx, WS_SCANA, 0));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_opidx + ncontrib, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+            nparts = h[0];
+        }
+        if (nparts >= (1ull << 32)) { c->err = "too many output partitions"; return B200C_EUNSUPPORTED; }
+        nparts_total += nparts;
+        B200C_TRY(ws_typed(c, WS_OPFIRST, nparts + 2, &d_opfirst));
+        uint32_t* d_list; unsigned long long* d_cursor = nullptr; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
+        B200C_TRY(ws_typed(c, WS_LIST, nparts + 1, &d_list));
+        B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
+        B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
+        B200C_TRY(ws_typed(c, WS_ICAP, nparts + 1, &d_icap));
+        B200C_TRY(ws_typed(c, WS_IOFF, nparts + 2, &d_ioff));
+        uint64_t n_le8 = 0, n_le16 = 0, n_le32 = 0;
+        if (ncontrib) {
+            B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
+            // counting sort of the output partitions by (fan-in, size bucket)
+            B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound,
+                         (uint32_t)std::min<uint64_t>(std::max<int64_t>(1, m->column_index_size), 0x7fffffff), d_icap);
+            // tile = token-contiguous run of output partitions whose inputs total ~32 MiB
+            uint64_t per_part = std::max<uint64_t>(1, range_bytes[r] / std::max<uint64_t>(1, nparts));
+            uint32_t tile_shift = 12; while (tile_shift < 24 && ((1ull << (tile_shift + 1)) * per_part) <= (32ull << 20)) tile_shift++;
+            const uint64_t ntiles = (nparts >> tile_shift) + 1, nkeys = 4 * ntiles * SORT_BINS;
+            B200C_TRY(ws_typed(c, WS_CURSOR, nkeys + 2, &d_cursor));
+            B200C_CUDA_TRY(c, cudaMemsetAsync(d_cursor, 0, (nkeys + 2) * 8, st));
+            B200C_LAUNCH(c, k_class_hist, 1184, 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor);
+            B200C_TRY(exclusive_scan<uint64_t>(c, (const uint64_t*)d_cursor, nkeys, (uint64_t*)d_cursor, WS_SCANA, 0));
+            for (int k = 1; k <= 3; k++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512 + k, (uint64_t*)d_cursor + (uint64_t)k * ntiles * SORT_BINS, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+            n_le8 = h[513]; n_le16 = h[514]; n_le32 = h[515];
+            B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor, d_list);
+        }
+        B200C_TRY(check_cancel());
+
+        // ---- K4: row merge + serialise ---------------------------------------------------------------------------------------------------
+        mark(3);
+        c->prog_stage.store(4);
+        B200C_TRY(ws_typed(c, WS_DSIZE, nparts + 1, &d_dsize));
+        B200C_TRY(ws_typed(c, WS_DPOS, nparts + 2, &d_dpos));
+        B200C_TRY(ws_typed(c, WS_IPOS, nparts + 2, &d_ipos));
+        B200C_TRY(ws_typed(c, WS_IPAY, nparts + 1, &d_ipay));
+        B200C_TRY(ws_typed(c, WS_NBLK, nparts + 1, &d_nblk));
+        B200C_TRY(ws_typed(c, WS_IHEAD, nparts + 1, &d_ihead));
+        B200C_TRY(ws_typed(c, WS_ISIZE, nparts + 1, &d_isize));
+        B200C_TRY(ws_typed(c, WS_STMUNF, nparts + 1, &d_stmunf));
+        B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
+        B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
+        const size_t cols_s = m->ncolumns <= K4_SMEM_COLS ? (size_t)m->ncolumns * sizeof(MCell) : 0;
+        const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
+        memset(&ka, 0, sizeof(ka));
+        ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen;
+        ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
+        ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts; ka.m3_nblk = two_pass ? 1 : 0;
+        // one launch per fan-in class over its slice of the sorted list
+        const uint64_t np_ = nparts;
+        launch_k4 = [&, n_le8, n_le16, n_le32, np_, smem8, smem16, cell_smem32](int mode) -> int {
+            ka.mode = mode;
+            const bool emit = mode != 0;
+            if (n_le8) {
+                unsigned g = (unsigned)((n_le8 + 127) / 128);
+                if (emit) B200C_LAUNCH(c, (k_partition_thr<8, 128, true>), g, 128, smem8, ka, 0ull, n_le8);
+                else B200C_LAUNCH(c, (k_partition_thr<8, 128, false>), g, 128, smem8, ka, 0ull, n_le8);
+            }
+            if (n_le16 > n_le8) {
+                unsigned g = (unsigned)((n_le16 - n_le8 + 63) / 64);
+                if (emit) B200C_LAUNCH(c, (k_partition_thr<16, 64, true>), g, 64, smem16, ka, n_le8, n_le16);
+                else B200C_LAUNCH(c, (k_partition_thr<16, 64, false>), g, 64, smem16, ka, n_le8, n_le16);
+            }
+            if (n_le32 > n_le16) {
+                unsigned g = (unsigned)((n_le32 - n_le16 + 3) / 4);
+                if (emit) B200C_LAUNCH(c, (k_partition_warp<1, true>), g, 128, cell_smem32, ka, n_le16, n_le32);
+                else B200C_LAUNCH(c, (k_partition_warp<1, false>), g, 128, cell_smem32, ka, n_le16, n_le32);
+            }
+            if (np_ > n_le32) {
+                unsigned g = (unsigned)((np_ - n_le32 + 3) / 4);
+                if (emit) B200C_LAUNCH(c, (k_partition_warp<2, true>), g, 128, cell_smem32, ka, n_le32, np_);
+                else B200C_LAUNCH(c, (k_partition_warp<2, false>), g, 128, cell_smem32, ka, n_le32, np_);
+            }
+            return B200C_OK;
+        };
+        if (c->k4_attr_set != (int)(smem8 + 1)) {      // > 48 KiB of dynamic shared memory needs an explicit opt-in, once per context/device
+            cudaFuncSetAttribute(k_partition_thr<8, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(k_partition_thr<8, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            c->k4_attr_set = (int)(smem8 + 1);
+        }
+        uint8_t* SCRATCH = nullptr;
+        ulen_out = 0; ilen_out = 0;
+        if (nparts) {
+            if (two_pass) {
+                B200C_CUDA_TRY(c, cudaMemsetAsync(d_ovf, 0, nparts, st));
+                B200C_TRY(launch_k4(0));
+            } else {
+                B200C_TRY(exclusive_scan<uint64_t>(c, d_bound, nparts, d_bpos, WS_SCANA, 0));
+                B200C_TRY(exclusive_scan<uint32_t>(c, d_icap, nparts, d_ioff, WS_SCANA + 3, 0));
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_bpos + nparts, 8, cudaMemcpyDeviceToHost, st));
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_ioff + nparts, 8, cudaMemcpyDeviceToHost, st));
+                B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
+                B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
+                ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
+                B200C_TRY(launch_k4(1));
+            }
+            B200C_LAUNCH(c, k_sum_stats, 1184, 256, 0, nparts, d_dsize, d_stmunf, d_strows, d_stats);
+            B200C_TRY(exclusive_scan<uint64_t>(c, d_dsize, nparts, d_dpos, WS_SCANA, 0));
+            if (ubase_total) B200C_LAUNCH(c, k_add_u64, (unsigned)((nparts + 1 + 255) / 256), 256, 0, d_dpos, nparts + 1, ubase_total);     // positions in the file, not in the piece
+            B200C_LAUNCH(c, k_index_sizes, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_dsize, d_dpos, d_ipay, d_ihead, d_isize);
+            B200C_TRY(exclusive_scan<uint32_t>(c, d_isize, nparts, d_ipos, WS_SCANA + 3, 0));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_dpos + nparts, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_ipos + nparts, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 2, d_err, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+            if (h[2] != ~0ull) {
+                int kinde = (int)(h[2] >> 56);
+                res->corruption.input = (int)((h[2] >> 48) & 0xFF); res->corruption.kind = 4; res->corruption.chunk = 0; res->corruption.offset = h[2] & 0xFFFFFFFFFFFFull;
+                timing_end(c);
+                if (kinde == 9) { c->err = "unsupported feature in input " + std::to_string(res->corruption.input) + " (static row, complex column or shadowable deletion)"; return B200C_EUNSUPPORTED; }
+                c->err = "malformed Data.db in input " + std::to_string(res->corruption.input) + " near offset " + std::to_string(res->corruption.offset);
+                return B200C_ECORRUPT;
+            }
+            ulen_out = h[0] - ubase_total; ilen_out = h[1];
+        }
+        B200C_TRY(check_cancel());
+        mark(4);
+        // the merged stream of this piece goes behind the unconsumed tail of the previous one; UOUT + tail_len is file offset ubase_total
+        B200C_TRY(ws_typed(c, (r & 1) ? WS_UOUT2 : WS_UOUT, tail_len + ulen_out + 64, &UOUT));
+        if (r) B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_pool[EV_INDEX], 0));          // IOUT of the previous piece has left
+        B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
+        if (tail_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(UOUT, tail_ptr, tail_len, cudaMemcpyDeviceToDevice, st));
+        uint8_t* const ubias = (uint8_t*)((uintptr_t)UOUT + tail_len - ubase_total);          // ubias + (file offset) = address
+        if (nparts && ulen_out) {
+            ka.dbase = ubias; ka.iout = IOUT; ka.doff = nullptr; ka.dcapv = nullptr;
+            if (two_pass) B200C_TRY(launch_k4(2));
+            else {
+                B200C_LAUNCH(c, k_gather, (unsigned)((nparts + 7) / 8), 256, 0, nparts, d_dsize, d_dpos, d_bpos, d_ovf, SCRATCH, ubias);
+                B200C_LAUNCH(c, k_index_simple, (unsigned)((nparts + 255) / 256), 256, 0, dP, nparts, d_contrib, d_opfirst, d_upos, d_pbase, d_dsize, d_dpos, d_nblk, d_ovf, d_ihead, d_ipos, IOUT);
+                B200C_LAUNCH(c, k_index_promoted, (unsigned)((nparts + 127) / 128), 128, 0, dP, nparts, d_contrib, d_opfirst, d_upos, d_pbase, d_dsize, d_dpos, d_nblk, d_ovf, d_ihead, d_ipay, d_ipos,
+                             d_ioff, d_icap, ISCR, IOUT);
+                B200C_TRY(launch_k4(3));
+            }
+        }
+        c->prog_scanned.store(bytes_read * (4 * (uint64_t)r + 3) / (4 * (uint64_t)nr));
+
+        // ---- K5 of this piece (one output file in host memory): whole chunks go out now, the rest waits for the next piece -------------
+        mark(5);
+        c->prog_stage.store(5);
+        if (to_host_stream) {
+            if (ilen_out) {                                  // Index.db is final after K4: read it back while K5 compresses
+                if (ilen_total + ilen_out > out0.index_cap || !out0.index) index_fits = false;
+                if (index_fits) {
+                    B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[EV_INDEX + 1], st));
+                    B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_out, c->ev_pool[EV_INDEX + 1], 0));
+                    B200C_CUDA_TRY(c, cudaMemcpyAsync(out0.index + ilen_total, IOUT, ilen_out, cudaMemcpyDeviceToHost, c->copy_out));
+                }
+            }
+            B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[EV_INDEX], c->copy_out));
+            const uint64_t avail = tail_len + ulen_out;
+            uint64_t take = (r == nr - 1) ? avail : avail / L * L;
+            const uint64_t slice = std::max<uint64_t>(L, std::max<uint64_t>(512ull << 20, bytes_read / 32) / L * L);      // pieces of ~512 MiB keep the read-back close behind
+            for (uint64_t off = 0; off < take; off += slice) B200C_TRY(out_stream_append(os, UOUT + off, std::min(slice, take - off)));
+            tail_len = avail - take; tail_ptr = UOUT + take;
+        }
+        ubase_total += ulen_out; ilen_total += ilen_out;
+    }
+    mark(-1);
     c->prog_scanned.store(bytes_read * 3 / 4);
 
-    // ---- K5: compress + CRC ------------------------------------------------------------------------------------------------------------
-    cudaEventRecord(c->ev_stage[5], st);
-    c->prog_stage.store(5);
-    bool index_copied = false;
-    if (!dev && !m->max_sstable_bytes && ilen_out && ilen_out <= res->outputs[0].index_cap) {
-        // Index.db is final after K4: read it back on the copy stream while K5 compresses
-        B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[0], st));
-        B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_in[0], 0));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(res->outputs[0].index, IOUT, ilen_out, cudaMemcpyDeviceToHost, c->copy_stream));
-        index_copied = true;
-    }
-    if (m->out_chunk_len <= 0 || m->out_chunk_len > 65536 || (m->out_chunk_len & (m->out_chunk_len - 1))) { c->err = "output chunk_len"; return B200C_EUNSUPPORTED; }
+    // ---- K5 wrap-up / remaining writers ------------------------------------------------------------------------------------------------
     int rc = B200C_OK;
-    if (!m->max_sstable_bytes) {
-        b200c_output& out = res->outputs[0];
-        const uint64_t nchunks_out = (ulen_out + m->out_chunk_len - 1) / m->out_chunk_len;
-        const uint64_t bound = b200c_compress_bound(m->out_compressor, ulen_out, m->out_chunk_len);
-        res->required_data_cap = bound; res->required_index_cap = ilen_out; res->required_chunk_cap = nchunks_out;
-        uint8_t* d_dout = out.data; uint64_t* d_ooffs;
-        if (!dev) B200C_TRY(ws_typed(c, WS_DOUT, bound + 64, &d_dout));
-        else if (out.data_cap < bound) { c->err = "output data buffer too small"; timing_end(c); return B200C_ETOOSMALL; }
-        B200C_TRY(ws_typed(c, WS_OOFFS, nchunks_out + 2, &d_ooffs));
-        uint64_t out_len = 0; uint32_t digest = 0;
-        if (dev) B200C_TRY(compress_stream_device(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound, d_ooffs, &out_len, &digest, WS_CODEC));
-        else B200C_TRY(compress_stream_to_host(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, d_dout, bound,
-                                               out.data, out.data ? out.data_cap : 0, d_ooffs, &out_len, &digest, WS_CODEC));   // Data.db leaves slice by slice under K5
-        // final error word + stats
+    auto finish_common = [&](RunStats& rs) -> int {          // error word, stats, histogram, stage clock
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
-        cudaEventRecord(c->ev_stage[6], st);
+        mark(-1);
         int trc = timing_end(c);
         if (trc != B200C_OK) return trc;
-        for (int k = 0; k < 6; k++) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_stage[k], c->ev_stage[k + 1]); c->stage_ms[k] = ms; }
-        c->nstages = 6;
+        finish_marks();
         if (h[0] != ~0ull) { c->err = "internal error: size/emit pass disagreement at output partition " + std::to_string(h[0] & 0xFFFFFFFFFFFFull); return B200C_ECUDA; }
-        RunStats rs; memcpy(&rs, h + 8, sizeof(rs));
-        res->noutputs = 1;
-        res->bytes_read = bytes_read; res->bytes_written = ulen_out; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib;
+        memcpy(&rs, h + 8, sizeof(rs));
         memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
         for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
-        out.data_len = out_len; out.index_len = ilen_out; out.nchunks = nchunks_out; out.data_length = ulen_out; out.digest = digest;
-        out.partitions = rs.partitions_out; out.rows = rs.rows_out;
+        res->bytes_read = bytes_read; res->bytes_written = ubase_total; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib_total;
         res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
-        if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) {
-            c->err = "output buffers too small"; rc = B200C_ETOOSMALL;
-            if (!dev) B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));      // slices that did fit may still be in flight
-        } else if (!dev) {
-            if (ilen_out && !index_copied) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToHost, st));
-            B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+        return B200C_OK;
+    };
+    if (to_host_stream) {
+        b200c_output& out = out0;
+        uint64_t out_len = 0; uint32_t digest = 0; uint64_t* d_ooffs = nullptr;
+        B200C_TRY(out_stream_finish(os, &out_len, &digest, &d_ooffs));
+        const uint64_t nchunks_out = os.nchunks;
+        RunStats rs; B200C_TRY(finish_common(rs));
+        res->noutputs = 1;
+        res->required_data_cap = std::max<uint64_t>(out_len, 1); res->required_index_cap = ilen_total; res->required_chunk_cap = nchunks_out;
+        out.data_len = out_len; out.index_len = ilen_total; out.nchunks = nchunks_out; out.data_length = ubase_total; out.digest = digest;
+        out.partitions = rs.partitions_out; out.rows = rs.rows_out;
+        if (!os.fits || !index_fits || out_len > out.data_cap || ilen_total > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
+        else {
             if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-        } else {
+        }
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_out));
+    } else if (!lcs) {
+        // one output file in device memory
+        b200c_output& out = out0;
+        const uint64_t nchunks_out = (ulen_out + L - 1) / L;
+        const uint64_t bound = b200c_compress_bound(m->out_compressor, ulen_out, m->out_chunk_len);
+        res->required_data_cap = bound; res->required_index_cap = ilen_out; res->required_chunk_cap = nchunks_out;
+        if (out.data_cap < bound) { c->err = "output data buffer too small"; timing_end(c); return B200C_ETOOSMALL; }
+        uint64_t* d_ooffs; B200C_TRY(ws_typed(c, WS_OOFFS, nchunks_out + 2, &d_ooffs));
+        uint64_t out_len = 0; uint32_t digest = 0;
+        B200C_TRY(compress_stream_device(c, m->out_compressor, UOUT, ulen_out, m->out_chunk_len, m->out_max_compressed_len, out.data, bound, d_ooffs, &out_len, &digest, WS_CODEC));
+        RunStats rs; B200C_TRY(finish_common(rs));
+        res->noutputs = 1;
+        out.data_len = out_len; out.index_len = ilen_out; out.nchunks = nchunks_out; out.data_length = ulen_out; out.digest = digest;
+        out.partitions = rs.partitions_out; out.rows = rs.rows_out;
+        if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
+        else {
             if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToDevice, st));
             if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToDevice, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
         }
-
     } else {
         // ---- multi-file output: one pass per file over a compressed window (see k_find_cut) ----------------------------------------
-        const uint32_t L = (uint32_t)m->out_chunk_len; const int comp = m->out_compressor; const int stride = chunk_slot_stride(comp, (int)L);
+        const int comp = m->out_compressor; const int stride = chunk_slot_stride(comp, (int)L);
         const uint64_t nch_total = (ulen_out + L - 1) / L;
         uint8_t* slots; uint32_t *file_len, *seg_raw; uint64_t *woffs, *d_dposf, *d_iposf, *d_cut, *d_ooffs; uint8_t *IOUTF, *d_dout; RunStats* d_fstats;
         B200C_TRY(ws_typed(c, WS_CODEC + 2, (nch_total + 2) * (uint64_t)stride, &slots));
@@ -1018,13 +1177,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_TRY(ws_typed(c, WS_OOFFS, nch_total + 4, &d_ooffs));
         const uint64_t file_bound = b200c_compress_bound(comp, ulen_out, (int)L);
         B200C_TRY(ws_typed(c, WS_DOUT, file_bound + 64, &d_dout));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 100, d_dpos + nparts, 8, cudaMemcpyDeviceToHost, st));
-        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-        RunStats rs; memcpy(&rs, h + 8, sizeof(rs));
-        memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
-        for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
         res->required_data_cap = res->required_index_cap = res->required_chunk_cap = 0;
         uint64_t jlo = 0, start_b = 0; int f = 0;
         while (jlo < nparts && start_b < ulen_out) {
@@ -1092,16 +1244,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             }
             jlo = jhi; start_b = end_b;
         }
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
-        cudaEventRecord(c->ev_stage[6], st);
-        int trc = timing_end(c);
-        if (trc != B200C_OK) return trc;
-        for (int k = 0; k < 6; k++) { float ms = 0; cudaEventElapsedTime(&ms, c->ev_stage[k], c->ev_stage[k + 1]); c->stage_ms[k] = ms; }
-        c->nstages = 6;
-        if (h[0] != ~0ull) { c->err = "internal error: size/emit pass disagreement at output partition " + std::to_string(h[0] & 0xFFFFFFFFFFFFull); return B200C_ECUDA; }
+        RunStats rs; B200C_TRY(finish_common(rs));
         res->noutputs = f;
-        res->bytes_read = bytes_read; res->bytes_written = ulen_out; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib;
-        res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
     }
     c->prog_scanned.store(bytes_read); c->prog_stage.store(6);
     res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();

@@ -70,7 +70,7 @@ int pack_digest_device(b200c_ctx* c, const uint8_t* slots, int stride, const uin
     B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     *out_len = h[0];
     if (h[0] > out_cap) { c->err = "output buffer too small"; return B200C_ETOOSMALL; }
-    B200C_LAUNCH(c, k_pack_chunks, (unsigned)((nchunks + 3) / 4), 128, 0, slots, stride, file_len, d_offs, nchunks, d_out);
+    B200C_LAUNCH(c, k_pack_chunks, (unsigned)((nchunks + 3) / 4), 128, 0, slots, stride, file_len, d_offs, nchunks, d_out, (const uint64_t*)nullptr);
     B200C_LAUNCH(c, k_digest, (unsigned)((nchunks + 255) / 256), 256, 0, c->d_tables, seg_raw, d_offs, nchunks, acc);
     B200C_LAUNCH(c, k_digest_final, 1, 1, 0, c->d_tables, d_offs, nchunks, acc);
     uint32_t* h32 = (uint32_t*)c->h_pinned;
@@ -100,74 +100,107 @@ __global__ void __launch_bounds__(256) k_offs_add_base(const uint64_t* __restric
     if (i == count) bases[1] = b + rel[count];
 }
 
-// Same result as compress_stream_device followed by a device->host copy of the file image, but in slices: slice s is copied to the
-// caller's host buffer on the copy stream while slice s+1 is being compressed, so that the PCIe read-back hides behind K5.
-// d_img: device staging of the whole image (cap img_cap); h_out/h_cap: the caller's buffer. When the image does not fit h_cap the
-// copies stop, *out_len is still the full size and the caller reports B200C_ETOOSMALL.
-int compress_stream_to_host(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
-                            uint8_t* d_img, uint64_t img_cap, uint8_t* h_out, uint64_t h_cap, uint64_t* d_offs /*nchunks+1*/,
-                            uint64_t* out_len, uint32_t* digest, int ws_base) {
-    const uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
-    if (nchunks > 0x7fffffffull) { c->err = "too many chunks"; return B200C_EINVAL; }
-    if (!nchunks) { *out_len = 0; *digest = 0; B200C_CUDA_TRY(c, cudaMemsetAsync(d_offs, 0, 8, c->stream)); return B200C_OK; }
-    enum { MAX_SLICES = 16, MIN_SLICE_CHUNKS = 8192 };
-    const int nslices = (int)std::min<uint64_t>(MAX_SLICES, std::max<uint64_t>(1, nchunks / MIN_SLICE_CHUNKS));
-    const uint64_t per = (nchunks + nslices - 1) / nslices;
-    const int stride = chunk_slot_stride(comp, chunk_len);
-    uint8_t* slots; uint32_t *file_len, *seg_raw, *acc; uint64_t *rel, *bases;
-    B200C_TRY(ws_typed(c, ws_base + WSC_SLOTS, nchunks * (uint64_t)stride, &slots));
-    B200C_TRY(ws_typed(c, ws_base + WSC_FILELEN, nchunks + 1, &file_len));
-    B200C_TRY(ws_typed(c, ws_base + WSC_SEGRAW, nchunks + 1, &seg_raw));
-    B200C_TRY(ws_typed(c, ws_base + WSC_IN, per + 2, &rel));
-    B200C_TRY(ws_typed(c, ws_base + WSC_CHOFFS, MAX_SLICES + 2, &bases));
-    B200C_TRY(ws_typed(c, ws_base + WSC_ACC, 4, &acc));
-    {   // scan scratch is sized by the first slice; allocate it before the loop so that no slot grows (and synchronises) mid-pipeline
-        uint64_t* tmp; uint64_t tiles = (per + SCAN_TILE - 1) / SCAN_TILE;
-        B200C_TRY(ws_typed(c, ws_base + WSC_SCAN0, tiles + 1, &tmp));
-        B200C_TRY(ws_typed(c, ws_base + WSC_SCAN0 + 1, (tiles + SCAN_TILE - 1) / SCAN_TILE + 1, &tmp));
+// workspace slot that keeps its first `used` bytes when it has to grow (whole-file arrays of an OutStream)
+template <typename T> static int ws_grow_keep(b200c_ctx* c, int slot, size_t count, size_t used, T** out) {
+    WsBuf& b = c->ws[slot];
+    size_t need = count * sizeof(T) + 256;
+    if (b.cap < need) {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_out);
+        void* np = nullptr; size_t cap = need * 2;
+        cudaError_t e = cudaMalloc(&np, cap);
+        if (e != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(" + std::to_string(cap) + "): " + cudaGetErrorString(e); return B200C_ENOMEM; }
+        if (b.p && used) cudaMemcpy(np, b.p, std::min(used * sizeof(T), b.cap), cudaMemcpyDeviceToDevice);
+        if (b.p) cudaFree(b.p);
+        b.p = np; b.cap = cap;
     }
-    B200C_CUDA_TRY(c, cudaMemsetAsync(acc, 0, 16, c->stream));
-    B200C_CUDA_TRY(c, cudaMemsetAsync(bases, 0, 8, c->stream));
-    uint64_t* h = (uint64_t*)c->h_pinned + 1024;          // slice end offsets land here
-    uint64_t copied = 0; bool fits = true;
-    auto drain = [&](int s) -> int {                      // slice s is packed once ev_in[1 + s] fires: hand its bytes to the copy engine
-        B200C_CUDA_TRY(c, cudaEventSynchronize(c->ev_in[1 + s]));
-        uint64_t end = h[s];
-        if (end > img_cap) { c->err = "internal error: compressed image exceeds its bound"; return B200C_ECUDA; }
-        if (end > h_cap) fits = false;
-        if (fits && end > copied) {
-            B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_in[1 + s], 0));
-            B200C_CUDA_TRY(c, cudaMemcpyAsync(h_out + copied, d_img + copied, end - copied, cudaMemcpyDeviceToHost, c->copy_stream));
-        }
-        copied = end;
-        return B200C_OK;
-    };
-    for (int s = 0; s < nslices; s++) {
-        const uint64_t a = (uint64_t)s * per, b = std::min<uint64_t>(nchunks, a + per);
-        if (a >= b) { h[s] = s ? h[s - 1] : 0; cudaEventRecord(c->ev_in[1 + s], c->stream); continue; }
-        const uint64_t nb = std::min<uint64_t>(n, b * (uint64_t)chunk_len) - a * (uint64_t)chunk_len;
-        B200C_TRY(compress_slots_device(c, comp, d_in + a * (uint64_t)chunk_len, nb, chunk_len, max_clen, slots + a * (uint64_t)stride, stride, file_len + a, seg_raw + a));
-        B200C_TRY(exclusive_scan<uint32_t>(c, file_len + a, b - a, rel, ws_base + WSC_SCAN0, 0));
-        B200C_LAUNCH(c, k_offs_add_base, (unsigned)((b - a + 1 + 255) / 256), 256, 0, rel, b - a, bases + s, d_offs + a);
-        B200C_LAUNCH(c, k_pack_chunks, (unsigned)((b - a + 3) / 4), 128, 0, slots + a * (uint64_t)stride, stride, file_len + a, d_offs + a, b - a, d_img);
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + s, bases + s + 1, 8, cudaMemcpyDeviceToHost, c->stream));
-        B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[1 + s], c->stream));
-        if (s) B200C_TRY(drain(s - 1));                   // after slice s is queued, so the GPU never waits for the host
-    }
-    B200C_LAUNCH(c, k_digest, (unsigned)((nchunks + 255) / 256), 256, 0, c->d_tables, seg_raw, d_offs, nchunks, acc);
-    B200C_LAUNCH(c, k_digest_final, 1, 1, 0, c->d_tables, d_offs, nchunks, acc);
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + MAX_SLICES, acc + 1, 4, cudaMemcpyDeviceToHost, c->stream));
-    B200C_TRY(drain(nslices - 1));
-    B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    *out_len = copied; *digest = (uint32_t)h[MAX_SLICES];
+    *out = (T*)b.p;
     return B200C_OK;
 }
 
+// ---- OutStream: K5 for one output file whose uncompressed stream is handed over in pieces -------------------------------------------
+// Every piece is compressed into slots, its chunk sizes are scanned and re-based onto the running file offset (a device scalar, so
+// no host round trip sits between the kernels), packed into one of two image buffers and copied to the caller's host buffer on the
+// copy stream while the next piece is being produced. The host learns each piece's end offset one piece late (drain).
+int out_stream_begin(OutStream& o, b200c_ctx* c, int comp, int chunk_len, int max_clen, uint8_t* h_out, uint64_t h_cap, int ws_base) {
+    o = OutStream();
+    o.c = c; o.comp = comp; o.L = chunk_len; o.max_clen = max_clen; o.stride = chunk_slot_stride(comp, chunk_len); o.ws_base = ws_base;
+    o.h_out = h_out; o.h_cap = h_out ? h_cap : 0;
+    B200C_TRY(ws_typed(c, ws_base + WSC_CHOFFS, (size_t)OutStream::MAX_PIECES + 2, &o.bases));
+    B200C_TRY(ws_typed(c, ws_base + WSC_ACC, 4, &o.acc));
+    B200C_CUDA_TRY(c, cudaMemsetAsync(o.acc, 0, 16, c->stream));
+    B200C_CUDA_TRY(c, cudaMemsetAsync(o.bases, 0, 8, c->stream));
+    return B200C_OK;
+}
+
+static int out_stream_drain(OutStream& o, int s) {       // piece s is packed once its event fires: hand its bytes to the copy engine
+    b200c_ctx* c = o.c;
+    uint64_t* h = (uint64_t*)c->h_pinned + 1024;
+    B200C_CUDA_TRY(c, cudaEventSynchronize(c->ev_pool[2 * s]));
+    const uint64_t end = h[s];
+    if (end - o.copied > o.img_cap[s & 1]) { c->err = "internal error: compressed piece exceeds its bound"; return B200C_ECUDA; }
+    if (end > o.h_cap) o.fits = false;
+    if (o.fits && end > o.copied) {
+        B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_out, c->ev_pool[2 * s], 0));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(o.h_out + o.copied, o.img[s & 1], end - o.copied, cudaMemcpyDeviceToHost, c->copy_out));
+    }
+    B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[2 * s + 1], c->copy_out));
+    o.copied = end;
+    return B200C_OK;
+}
+
+// d_in: the next nbytes of the uncompressed stream, starting on a chunk boundary of the file; every call but the last must pass a
+// multiple of the chunk length
+int out_stream_append(OutStream& o, const uint8_t* d_in, uint64_t nbytes) {
+    b200c_ctx* c = o.c;
+    if (!nbytes) return B200C_OK;
+    if (o.piece >= OutStream::MAX_PIECES) { c->err = "internal error: too many output pieces"; return B200C_ECUDA; }
+    const uint64_t k = (nbytes + o.L - 1) / o.L, a = o.nchunks;
+    if (a + k > 0x7fffffffull) { c->err = "too many chunks"; return B200C_EINVAL; }
+    uint8_t* slots; uint64_t* rel; const int s = o.piece;
+    B200C_TRY(ws_grow_keep(c, o.ws_base + WSC_FILELEN, a + k + 2, a, &o.file_len));
+    B200C_TRY(ws_grow_keep(c, o.ws_base + WSC_SEGRAW, a + k + 2, a, &o.seg_raw));
+    B200C_TRY(ws_grow_keep(c, o.ws_base + WSC_OFFS, a + k + 2, a + 1, &o.d_offs));
+    B200C_TRY(ws_typed(c, o.ws_base + WSC_SLOTS, k * (uint64_t)o.stride, &slots));
+    B200C_TRY(ws_typed(c, o.ws_base + WSC_IN, k + 2, &rel));
+    B200C_TRY(ws_typed(c, o.ws_base + (s & 1 ? WSC_OUT : WSC_ERR), k * (uint64_t)o.stride + 64, &o.img[s & 1]));
+    o.img_cap[s & 1] = k * (uint64_t)o.stride;
+    if (s >= 2) B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_pool[2 * (s - 2) + 1], 0));   // the image buffer is free again
+    B200C_TRY(compress_slots_device(c, o.comp, d_in, nbytes, o.L, o.max_clen, slots, o.stride, o.file_len + a, o.seg_raw + a));
+    B200C_TRY(exclusive_scan<uint32_t>(c, o.file_len + a, k, rel, o.ws_base + WSC_SCAN0, 0));
+    B200C_LAUNCH(c, k_offs_add_base, (unsigned)((k + 1 + 255) / 256), 256, 0, rel, k, o.bases + s, o.d_offs + a);
+    B200C_LAUNCH(c, k_pack_chunks, (unsigned)((k + 3) / 4), 128, 0, slots, o.stride, o.file_len + a, o.d_offs + a, k, o.img[s & 1], (const uint64_t*)(o.bases + s));
+    uint64_t* h = (uint64_t*)c->h_pinned + 1024;
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + s, o.bases + s + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[2 * s], c->stream));
+    if (s) B200C_TRY(out_stream_drain(o, s - 1));        // after piece s is queued, so the GPU never waits for the host
+    o.nchunks += k; o.ulen += nbytes; o.piece++;
+    return B200C_OK;
+}
+
+// drains the last piece, computes Digest.crc32 and waits for everything; *d_offs_out: the nchunks + 1 chunk offsets (device)
+int out_stream_finish(OutStream& o, uint64_t* out_len, uint32_t* digest, uint64_t** d_offs_out) {
+    b200c_ctx* c = o.c;
+    *out_len = 0; *digest = 0; *d_offs_out = nullptr;
+    if (!o.nchunks) return B200C_OK;
+    uint32_t* h32 = (uint32_t*)((uint64_t*)c->h_pinned + 1024 + OutStream::MAX_PIECES + 1);
+    B200C_LAUNCH(c, k_digest, (unsigned)((o.nchunks + 255) / 256), 256, 0, c->d_tables, o.seg_raw, o.d_offs, o.nchunks, o.acc);
+    B200C_LAUNCH(c, k_digest_final, 1, 1, 0, c->d_tables, o.d_offs, o.nchunks, o.acc);
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h32, o.acc + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    B200C_TRY(out_stream_drain(o, o.piece - 1));
+    B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    B200C_CUDA_TRY(c, cudaStreamSynchronize(c->copy_out));
+    *out_len = o.copied; *digest = h32[0]; *d_offs_out = o.d_offs;
+    return B200C_OK;
+}
+
+// chunks [chunk0, chunk0 + count) of the file (count = ~0: through the last chunk)
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
-                             int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err) {
-    if (nchunks == 0) return B200C_OK;
-    B200C_LAUNCH(c, k_decompress_chunks, (unsigned)((nchunks + 1) / 2), 64, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
-                 chunk_len, max_clen, data_length, d_out, verify, d_err);
+                             int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err,
+                             uint64_t chunk0, uint64_t count, int tag) {
+    if (chunk0 >= nchunks || count == 0) return B200C_OK;
+    const uint64_t end = count > nchunks - chunk0 ? nchunks : chunk0 + count;
+    B200C_LAUNCH(c, k_decompress_chunks, (unsigned)((end - chunk0 + 1) / 2), 64, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
+                 chunk_len, max_clen, data_length, d_out, verify, d_err, chunk0, end, tag);
     return B200C_OK;
 }
 
@@ -193,6 +226,8 @@ b200c_ctx* b200c_create(int device, size_t workspace_bytes) {
     for (auto& e : c->ev_stage) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& e : c->ev_in) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : c->ev_pool) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking);
     DevTables* h = new DevTables(); build_tables(h);
     if (cudaMalloc(&c->d_tables, sizeof(DevTables)) != cudaSuccess) { delete h; delete c; return nullptr; }
     cudaMemcpy(c->d_tables, h, sizeof(DevTables), cudaMemcpyHostToDevice);
@@ -214,6 +249,9 @@ void b200c_destroy(b200c_ctx* c) {
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (auto& e : c->ev_stage) cudaEventDestroy(e);
     for (auto& e : c->ev_in) cudaEventDestroy(e);
+    for (auto& e : c->ev_pool) cudaEventDestroy(e);
+    for (auto& e : c->ev_marks) cudaEventDestroy(e);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -313,7 +351,7 @@ int b200c_decompress_chunks(b200c_ctx* c, int comp, const uint8_t* data, uint64_
     ChunkErr* d_err; B200C_TRY(ws_typed(c, WSC_ERR, 1, &d_err));
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_err, 0xFF, sizeof(ChunkErr), c->stream));
     timing_begin(c);
-    int rc = decompress_stream_device(c, comp, d_data, data_len, d_offs, nchunks, chunk_len, max_clen, data_length, d_out, verify_crc, d_err);
+    int rc = decompress_stream_device(c, comp, d_data, data_len, d_offs, nchunks, chunk_len, max_clen, data_length, d_out, verify_crc, d_err, 0, ~0ull, 0);
     int rc2 = timing_end(c);
     if (rc != B200C_OK) return rc;
     if (rc2 != B200C_OK) return rc2;
@@ -321,7 +359,7 @@ int b200c_decompress_chunks(b200c_ctx* c, int comp, const uint8_t* data, uint64_
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, sizeof(ChunkErr), cudaMemcpyDeviceToHost, c->stream));
     B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (h->first_bad != ~0ull) {
-        uint64_t chunk = h->first_bad >> 8; int kind = (int)(h->first_bad & 0xff);
+        uint64_t chunk = (h->first_bad >> 8) & 0xFFFFFFFFFFull; int kind = (int)(h->first_bad & 0xff);
         if (where) { where->input = 0; where->kind = kind; where->chunk = chunk; where->offset = 0; }
         c->err = std::string(kind == 1 ? "chunk CRC mismatch" : "malformed compressed chunk") + " at chunk " + std::to_string(chunk);
         return B200C_ECORRUPT;

@@ -5,6 +5,7 @@
 #include <string>
 #include <atomic>
 #include <chrono>
+#include <vector>
 #include "../../include/b200c.h"
 #include "common.cuh"
 
@@ -36,6 +37,9 @@ struct b200c_ctx {
     int k4_attr_set = 0;
     cudaStream_t copy_stream = nullptr;            // host->device staging of the inputs, overlapped with K1 input by input
     cudaEvent_t ev_in[64] = {};
+    std::vector<cudaEvent_t> ev_marks;             // timed events of the stage clock (grown on demand)
+    cudaEvent_t ev_pool[256] = {};                 // untimed events: OutStream pieces (2 each), token-range staging
+    cudaStream_t copy_out = nullptr;               // device->host stream of the outputs (the other copy engine)
 };
 
 namespace b200c {
@@ -56,7 +60,7 @@ inline int ws_get(b200c_ctx* c, int slot, size_t bytes, void** out) {
     WsBuf& b = c->ws[slot];
     size_t need = bytes + 256;
     if (b.cap < need) {
-        if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        if (b.p) { cudaStreamSynchronize(c->stream); if (c->copy_stream) cudaStreamSynchronize(c->copy_stream); if (c->copy_out) cudaStreamSynchronize(c->copy_out); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
         size_t cap = need + need / 8;
         cudaError_t e = cudaMalloc(&b.p, cap);
         if (e != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(" + std::to_string(cap) + "): " + cudaGetErrorString(e); b.p = nullptr; return B200C_ENOMEM; }
@@ -76,6 +80,19 @@ inline int timing_end(b200c_ctx* c) {
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms; c->timing = false;
     return B200C_OK;
 }
+
+// K5 of one output file fed in pieces (engine.cu)
+struct OutStream {
+    enum { MAX_PIECES = 96 };
+    b200c_ctx* c = nullptr; int comp = 0, L = 0, max_clen = 0, stride = 0, ws_base = 0;
+    uint8_t* h_out = nullptr; uint64_t h_cap = 0;           // the caller's Data.db buffer
+    uint32_t *file_len = nullptr, *seg_raw = nullptr, *acc = nullptr; uint64_t *d_offs = nullptr, *bases = nullptr;
+    uint8_t* img[2] = {nullptr, nullptr}; uint64_t img_cap[2] = {0, 0};
+    uint64_t nchunks = 0, ulen = 0, copied = 0; int piece = 0; bool fits = true;
+};
+int out_stream_begin(OutStream& o, b200c_ctx* c, int comp, int chunk_len, int max_clen, uint8_t* h_out, uint64_t h_cap, int ws_base);
+int out_stream_append(OutStream& o, const uint8_t* d_in, uint64_t nbytes);
+int out_stream_finish(OutStream& o, uint64_t* out_len, uint32_t* digest, uint64_t** d_offs_out);
 
 // device-wide exclusive scan: out[0..n] (n+1 entries, out[n] = total). TIn = uint32_t or uint64_t. scan_slot0: first of 3 ws slots.
 template <typename TIn> int exclusive_scan(b200c_ctx* c, const TIn* in, uint64_t n, uint64_t* out, int scan_slot0, int depth = 0);

@@ -314,3 +314,30 @@ def test_edge_shapes(ctx):
     both(ctx, [empty, one], CompactionController(NOW, 10**9))
     g, _ = both(ctx, [empty], CompactionController(NOW, 10**9))
     assert g.outputs[0].data == b"" and g.outputs[0].partitions == 0
+
+
+@pytest.mark.parametrize("ranges", [2, 5, 16])
+def test_token_range_streaming_matches_oracle(ctx, ranges, monkeypatch):
+    """host-buffer compactions are cut into token-range pieces (Data.db copies, K1, K3-K5 and the read-back overlap piece by piece);
+    B200C_RANGES forces the piece count on inputs that would otherwise run as one piece. Every output byte must stay the same."""
+    monkeypatch.setenv("B200C_RANGES", str(ranges))
+    tabs = synth_tables(0, 6, 0x57E + ranges, 20000)
+    got, _ = both(ctx, tabs, CompactionController(NOW))
+    assert got.outputs[0].partitions > 1000
+    wide = synth_tables(1, 3, 0x57F + ranges, 60, rows_per_partition=600, column_index_size=4096)
+    both(ctx, wide, CompactionController(NOW), column_index_size=4096)
+    both(ctx, tabs[:1], CompactionController(NOW))                       # single input
+    # a token sub-range on top of the pieces
+    lo, hi = -(1 << 62), (1 << 61)
+    want = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine()).outputs[0]
+    g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(GpuEngine(ctx)).outputs[0]
+    assert g.data == want.data and g.index == want.index and g.digest == want.digest and g.compression.chunk_offsets == want.compression.chunk_offsets
+
+def test_token_range_streaming_tiny_and_empty(ctx, monkeypatch):
+    monkeypatch.setenv("B200C_RANGES", "4")
+    S1 = Schema(["Int32Type"], [("val", "UTF8Type")]); b = Builder(S1, (0, 0, 0))
+    few = b.build([Partition(b"k%d" % i, [Row((I32(1),), [Cell(0, 5, b"v" * (i % 7))], ts=5)]) for i in range(9)])
+    both(ctx, [few, few], CompactionController(NOW))
+    gone = b.build([Partition(b"k", [], (5, 7))])
+    got, _ = both(ctx, [gone], CompactionController(NOW))
+    assert got.outputs[0].data == b""

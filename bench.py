@@ -75,9 +75,10 @@ def make_inputs_gpu(ctx, schema, nsst, seed, per_sstable_bytes, p, threads, pinn
             t = torch.from_numpy(np.ascontiguousarray(a))
             return t.pin_memory() if pinned else t
         d = pin(out[:out_len.value]); ix = pin(np.frombuffer(raw["index"], dtype=np.uint8)); of = pin(offs[:nch].view(np.int64))
+        sm = pin(raw["summary"].view(np.int64))                     # Summary.db sample positions (every 128th Index.db entry)
         meta = CompressionMetadata("LZ4Compressor", 16384, native.INT32_MAX, n, [])
         t = SSTable(None, None, meta, raw["stats"], raw["stats"], synth.SCHEMAS[schema]["clustering"], synth.SCHEMAS[schema]["columns"], generation=s)
-        t.hold = (d, ix, of); t.nchunks = nch; t.partitions = raw["partitions"]; t.rows = raw["rows"]
+        t.hold = (d, ix, of); t.summary = sm; t.nchunks = nch; t.partitions = raw["partitions"]; t.rows = raw["rows"]
         tabs.append(t)
         log("input %d/%d: %.1f MiB uncompressed -> %.1f MiB, %d partitions (%.1fs)" % (s + 1, nsst, n / 2**20, out_len.value / 2**20, raw["partitions"], time.time() - t0))
         del raw, out
@@ -94,8 +95,9 @@ def build_manifest(tabs, schema, device_copies=None):
     for k, t in enumerate(tabs):
         d, ix, of = t.hold
         a = arr[k]
-        if device_copies: a.data, a.index, a.chunk_offsets = device_copies[k]
-        else: a.data, a.index, a.chunk_offsets = d.data_ptr(), ix.data_ptr(), of.data_ptr()
+        if device_copies: a.data, a.index, a.chunk_offsets, a.summary_positions = device_copies[k]
+        else: a.data, a.index, a.chunk_offsets, a.summary_positions = d.data_ptr(), ix.data_ptr(), of.data_ptr(), t.summary.data_ptr()
+        a.nsummary = t.summary.numel()
         a.data_len = d.numel(); a.index_len = ix.numel(); a.nchunks = t.nchunks; a.data_length = t.compression.data_length
         a.compressor = native.COMP_LZ4; a.chunk_len = 16384; a.max_compressed_len = native.INT32_MAX
         a.ncolumns = len(t.regular_columns)
@@ -147,8 +149,8 @@ def run_b200(args):
         res.noutputs_cap = 1; res.outputs = outs; res._keep = outs
         return res
     # device-resident copies of the inputs and outputs (value)
-    dev_in = [(t.hold[0].cuda(), t.hold[1].cuda(), t.hold[2].cuda()) for t in tabs]
-    m_dev = build_manifest(tabs, schema, [(a.data_ptr(), b.data_ptr(), c.data_ptr()) for a, b, c in dev_in])
+    dev_in = [(t.hold[0].cuda(), t.hold[1].cuda(), t.hold[2].cuda(), t.summary.cuda()) for t in tabs]
+    m_dev = build_manifest(tabs, schema, [(a.data_ptr(), b.data_ptr(), c.data_ptr(), d_.data_ptr()) for a, b, c, d_ in dev_in])
     do = (torch.empty(cap_d, dtype=torch.uint8, device="cuda"), torch.empty(cap_i, dtype=torch.uint8, device="cuda"), torch.empty(cap_c, dtype=torch.int64, device="cuda"))
 
     def step(dev):
@@ -182,7 +184,7 @@ def run_b200(args):
     e_steps = max(1, min(args.steps, 3))
     edt, ekms, estages, elast, _, _ = timed(False, e_steps)
     e2e = total_in_all * e_steps / edt / 1e6
-    h2d = c_in + i_in + 8 * sum(t.nchunks for t in tabs); d2h = c_out + i_out + 8 * int(elast.outputs[0].nchunks)
+    h2d = c_in + i_in + 8 * sum(t.nchunks for t in tabs) + 8 * sum(t.summary.numel() for t in tabs); d2h = c_out + i_out + 8 * int(elast.outputs[0].nchunks)
 
     # roofline of the dominant stage, algorithmic bytes per SURVEY §8(d): every compressed byte read once, every uncompressed byte
     # produced once, merged stream written once and compressed once

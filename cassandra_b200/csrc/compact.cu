@@ -44,7 +44,7 @@ enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pi
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -140,6 +140,28 @@ __global__ void __launch_bounds__(256) k_index_find(const CParams* __restrict__ 
     start[b] = found;
 }
 
+// Speculation from Summary.db: anchors[] are Index.db offsets of sampled entries (every 128th by default). One thread walks the
+// entries between two anchors and records, per block, the lowest entry start it meets. Nothing is taken on trust: chain / verify
+// below still prove the result against the sequential parse, a wrong anchor only costs the sequential fallback.
+__global__ void __launch_bounds__(128) k_index_find_anchors(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase, int i,
+                                                            const uint64_t* __restrict__ anchors, uint64_t n, unsigned long long* __restrict__ start) {
+    uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const CParams& P = *Pp;
+    const uint64_t ilen = P.in[i].ilen;
+    uint64_t o = anchors[a], end = (a + 1 < n) ? anchors[a + 1] : ilen;
+    if (o >= ilen || end > ilen || end <= o) return;
+    uint64_t prev_block = NONE64;
+    while (o < end) {
+        uint64_t dpos; uint32_t kl;
+        uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
+        if (!len) return;
+        uint64_t b = o / IB;
+        if (b != prev_block) { atomicMin(&start[bbase[i] + b], (unsigned long long)o); prev_block = b; }
+        o += len;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_index_chain(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase, uint64_t b0,
                                                      uint64_t nblocks, const uint64_t* __restrict__ start, uint32_t* __restrict__ cnt, uint64_t* __restrict__ chain_end) {
     uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,15 +245,8 @@ __global__ void __launch_bounds__(256) k_index_emit(const CParams* __restrict__ 
         uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
         if (!len) { report_err(err, 3, i, o); return; }
         const uint8_t* key = IDX + in.ibase + o + 2;
-        if (kl > 8) {
-            // Index.db <-> Data.db consistency: the Data.db partition must start with the same key. Keys of up to 8 bytes are
-            // checked for free by K4 (it compares klen + the 8-byte prefix with the partition header it reads anyway), which
-            // saves one random Data.db sector read per partition here; longer keys are compared in full.
-            const uint8_t* d = P.U + in.ubase + dpos;
-            bool same = (((uint32_t)d[0] << 8) | d[1]) == kl;
-            for (uint32_t q = 0; same && q < kl; q++) same = d[2 + q] == key[q];
-            if (!same) { report_err(err, 3, i, o); return; }
-        }
+        // Index.db <-> Data.db consistency is checked by K4 when it parses the partition header: key length + 8-byte prefix, and for
+        // longer keys the token (so this kernel needs Index.db only and can run before Data.db is on the device)
         tok[g] = murmur3_token(key, kl);
         uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0);
         kp[g] = pre; klen[g] = (uint16_t)kl; upos[g] = in.ubase + dpos;
@@ -445,7 +460,7 @@ enum { SLOT_BYTES = sizeof(Cur), K4_SMEM_COLS = 8 };          // per-source curs
 // entry. mode 3: like 2 but only partitions whose scratch (Data bytes or promoted-index slot) overflowed in mode 1.
 struct K4Args {
     const CParams* P; const uint64_t* contrib; const uint64_t* op_first; const uint32_t* list; const uint64_t* upos; const uint64_t* pbase;
-    const uint64_t* kp; const uint16_t* klen;
+    const uint64_t* kp; const uint16_t* klen; const int64_t* tok;
     uint64_t* dsize; uint32_t* ipay; uint32_t* nblk; uint32_t* ihead; uint32_t* st_munf; uint32_t* st_rows; uint8_t* ovf;
     const uint64_t* doff; const uint64_t* dcapv; const uint64_t* dpos; const uint64_t* ipos; uint8_t* dbase; uint8_t* iout; DevErr* err; int mode;
     uint64_t jlo, jhi;               // modes 2/3: only partitions jlo <= j < jhi (one output file of a multi-file compaction)
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
     if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
-    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e);
+    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e);
     k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(128) k_partition_warp(const K4Args a, uint64_t
     if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) return;
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, s_cells, out, st, e);
+    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, s_cells, out, st, e);
     if (tile.thread_rank() == 0) k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
@@ -680,13 +695,20 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         want_ranges = (int)std::min<uint64_t>(MAX_RANGES, std::max<uint64_t>(1, co / (768ull << 20)));
         if (const char* e = getenv("B200C_RANGES")) { want_ranges = std::max(1, std::min((int)MAX_RANGES, atoi(e))); forced_ranges = true; }
     }
-    const bool deferred = !dev && !lcs;               // Data.db copies are scheduled after K2 (even when a single piece results)
+    // with Summary.db positions for every input the Index.db walk does not need Data.db: its copies are then scheduled after K2
+    bool have_summaries = true;
+    for (int i = 0; i < K; i++) if (m->inputs[i].index_len && !(m->inputs[i].summary_positions && m->inputs[i].nsummary)) have_summaries = false;
+    const bool deferred = !dev && !lcs && have_summaries;
+    if (!deferred) want_ranges = 1;
 
     uint8_t *U, *CD, *IDX; uint64_t* CO; CParams* dP; uint64_t* d_bbase; DevErr* d_err; ChunkErr* d_cerr; RunStats* d_stats; unsigned long long* d_hist;
     B200C_TRY(ws_typed(c, WS_U, uo + 64, &U));
     B200C_TRY(ws_typed(c, WS_CD, co + 64, &CD));
     B200C_TRY(ws_typed(c, WS_CO, oo + 1, &CO));
     B200C_TRY(ws_typed(c, WS_IDX, io + 64, &IDX));
+    std::vector<uint64_t> sbase(K + 1, 0);
+    for (int i = 0; i < K; i++) sbase[i + 1] = sbase[i] + (have_summaries ? m->inputs[i].nsummary : 0);
+    uint64_t* d_summ; B200C_TRY(ws_typed(c, WS_SUMM, sbase[K] + 1, &d_summ));
     B200C_TRY(ws_typed(c, WS_PARAMS, 1, &dP));
     B200C_TRY(ws_typed(c, WS_BBASE, (size_t)K + 1, &d_bbase));
     { uint8_t* p; B200C_TRY(ws_typed(c, WS_ERR2, 4096, &p)); d_err = (DevErr*)p; d_cerr = (ChunkErr*)(p + 64); d_stats = (RunStats*)(p + 128); d_hist = (unsigned long long*)(p + 256); }
@@ -720,6 +742,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (!deferred && in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, cs));
         if (in.nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(CO + obase[i], in.chunk_offsets, in.nchunks * 8, kind, cs));
         if (in.index_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index, in.index_len, kind, cs));
+        if (have_summaries && in.nsummary) B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + sbase[i], in.summary_positions, in.nsummary * 8, kind, cs));
         B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[i], cs));
     }
     if (deferred && want_ranges > 1)         // keep the link busy while K2 finishes: the head of every Data.db is needed by the first piece
@@ -767,7 +790,11 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         const uint64_t nb = bbase[i + 1] - bbase[i];
         if (nb) {
             unsigned g = (unsigned)((nb + 255) / 256);
-            B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart);
+            if (have_summaries) {
+                B200C_CUDA_TRY(c, cudaMemsetAsync(d_istart + bbase[i], 0xFF, nb * 8, st));
+                const uint64_t ns = sbase[i + 1] - sbase[i];
+                B200C_LAUNCH(c, k_index_find_anchors, (unsigned)((ns + 127) / 128), 128, 0, dP, IDX, d_bbase, i, d_summ + sbase[i], ns, (unsigned long long*)d_istart);
+            } else B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart);
             B200C_LAUNCH(c, k_index_chain, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart, d_icnt, d_iend);
             B200C_LAUNCH(c, k_index_verify_a, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_iend, d_ihit, d_ibad);
             B200C_LAUNCH(c, k_index_verify_b, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_ihit, d_ibad);
@@ -988,7 +1015,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         const size_t cols_s = m->ncolumns <= K4_SMEM_COLS ? (size_t)m->ncolumns * sizeof(MCell) : 0;
         const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
         memset(&ka, 0, sizeof(ka));
-        ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen;
+        ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen; ka.tok = d_tok;
         ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
         ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts; ka.m3_nblk = two_pass ? 1 : 0;
         // one launch per fan-in class over its slice of the sorted list

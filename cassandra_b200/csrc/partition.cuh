@@ -497,10 +497,12 @@ struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; };
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
 // cur[0..m) / open_dt[0..m): per-source cursor state owned by this thread (the caller places it in shared memory);
 // merged[0..ncols): scratch for the merged row.
+__device__ int64_t murmur3_token(const uint8_t* key, uint32_t len);     // compact.cu
+
 template <bool EMIT>
 __device__ void process_partition(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                   const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
-                                  const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen,
+                                  const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen, const int64_t* __restrict__ part_tok,
                                   uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
                                   Cur* cur, DT* open_dt, MCell* merged,
                                   PartOut& out, PartStats& st, int& err) {
@@ -515,6 +517,7 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         int src = (int)((e >> 56) & 0x7F); uint64_t g = pbase[src] + (e & 0xFFFFFFFFFFull);
         Cur& c = cur[v]; c.src = (uint8_t)src; c.pos = part_upos[g]; c.end = part_upos[g + 1]; c.done = false;
         c.k0 = part_kp[g]; c.ckend_rel = part_klen[g];           // what Index.db said about this partition's key (checked below)
+        c.next = (uint64_t)part_tok[g];                          // (parked here until the header is parsed)
     }
     for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
     for (uint32_t v = 0; v < m; v++) {
@@ -530,6 +533,8 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         r.skip(kl);
         DT pd = read_partition_dt(r);
         if (r.err) { err = r.err; return; }
+        // keys longer than the 8-byte prefix: the token K2 computed from the Index.db key must be the token of the Data.db key
+        if (kl > 8 && murmur3_token(P.U + pos + 2, kl) != (int64_t)c.next) { err = PERR_CORRUPT; return; }
         if (v == 0) { key_off = pos + 2; klen = kl; }
         if (!dt_supersedes(pdel, pd)) pdel = pd;                  // collectPartitionLevelDeletion :465-482
         c.pos = r.p; c.next = r.p;

@@ -59,7 +59,7 @@ __device__ __forceinline__ MCell read_cell(const CParams& P, const InDesc& in, R
 template <int G, int S, bool EMIT>
 __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                        const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
-                                       const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen,
+                                       const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen, const int64_t* __restrict__ part_tok,
                                        uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
                                        MCell* s_cells, PartOut& out, PartStats& st, int& err) {
     const int lane = tile.thread_rank();
@@ -87,6 +87,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
             r.skip(kl);
             my_pd[s] = read_partition_dt(r);
             if (r.err) lerr = r.err;
+            else if (kl > 8 && murmur3_token(P.U + pos + 2, kl) != part_tok[g]) lerr = PERR_CORRUPT;      // see process_partition
             if (v == 0) { my_key_off = pos + 2; my_klen = kl; }
             cur[s].src = (uint8_t)src; cur[s].pos = r.p; cur[s].end = end; cur[s].next = r.p; cur[s].done = false;
         }

@@ -83,6 +83,11 @@ class CompactionTask:
             for ci, (name, _) in enumerate(s.regular_columns): a.column_map[ci] = names.index(name)
             a.header_stats.min_timestamp, a.header_stats.min_local_deletion_time, a.header_stats.min_ttl = s.header_stats
             a.level = s.level
+            sp = getattr(s, "summary_positions", None)
+            if sp is not None and len(sp):
+                sp = np.ascontiguousarray(sp, dtype=np.uint64); self._keep.append(sp)
+                a.summary_positions = sp.ctypes.data; a.nsummary = len(sp)
+            else: a.summary_positions = None; a.nsummary = 0
         m.inputs = arr
         m.nclustering = len(ct)
         for k, t in enumerate(ct):

@@ -87,15 +87,46 @@ class SSTable:
         self.regular_columns = list(regular_columns)       # [(name bytes, type string)] in header order
         self.static_columns = list(static_columns)
         self.key_type = key_type; self.level = level; self.generation = generation
+        self.summary_positions = None                      # Index.db offsets of the Summary.db samples (numpy uint64) when known
 
     @classmethod
     def open(cls, base_path: str, generation=0):
         """base_path: '<dir>/oa-1-big-' (descriptor prefix)."""
         rd = lambda c: open(base_path + c, "rb").read()
         st = parse_statistics(rd("Statistics.db"))
-        return cls(rd("Data.db"), rd("Index.db"), CompressionMetadata.parse(rd("CompressionInfo.db")), st["header_stats"],
+        t = cls(rd("Data.db"), rd("Index.db"), CompressionMetadata.parse(rd("CompressionInfo.db")), st["header_stats"],
                    (st["min_timestamp"], st["min_local_deletion_time"], st["min_ttl"]), st["clustering_types"],
                    st["regular_columns"], st["static_columns"], st["key_type"], generation=generation)
+        if os.path.exists(base_path + "Summary.db"): t.summary_positions = parse_summary_positions(rd("Summary.db"))
+        return t
+
+def parse_summary_positions(buf: bytes):
+    """Index.db offsets of the sampled entries of a Summary.db (IndexSummary.IndexSummarySerializer.serialize,
+    S/io/sstable/indexsummary/IndexSummary.java:401-423): big-endian header (minIndexInterval, offsetCount, offHeapSize,
+    samplingLevel, sizeAtFullSampling), then offsetCount native-order (little-endian) int32 offsets relative to the start of the
+    offsets region, then per sample `key bytes | int64 Index.db position` (native order, :190-193)."""
+    import numpy as np
+    _min_interval, count, offheap, _level, _full = struct.unpack_from(">iiqii", buf, 0)
+    base = 24
+    offs = np.frombuffer(buf, dtype="<i4", count=count, offset=base).astype(np.int64)
+    ends = np.append(offs[1:], offheap)
+    pos = np.empty(count, dtype=np.uint64)
+    for i in range(count):
+        pos[i] = struct.unpack_from("<q", buf, base + int(ends[i]) - 8)[0]
+    return pos
+
+def index_summary_positions(index: bytes, interval: int = 128):
+    """walks an Index.db image and returns the offset of every `interval`-th entry (what IndexSummaryBuilder.maybeAddEntry,
+    S/io/sstable/indexsummary/IndexSummaryBuilder.java:200-228, records at the default min_index_interval). Python loop: for test-sized files."""
+    import numpy as np
+    out = []; o = 0; n = 0; L = len(index)
+    while o < L:
+        if n % interval == 0: out.append(o)
+        kl = (index[o] << 8) | index[o + 1]; p = o + 2 + kl
+        _, p = _vint(index, p)
+        ps, p = _vint(index, p)
+        o = p + ps; n += 1
+    return np.asarray(out, dtype=np.uint64)
 
 def write_components(base_path: str, data: bytes, index: bytes, compression: CompressionMetadata, digest: int):
     """Writes the components the engine produces (Data, Index, CompressionInfo, Digest). Statistics/Filter/Summary are

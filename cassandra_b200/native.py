@@ -28,7 +28,8 @@ class Input(C.Structure):
     _fields_ = [("data", C.c_void_p), ("data_len", C.c_uint64), ("index", C.c_void_p), ("index_len", C.c_uint64),
                 ("chunk_offsets", C.c_void_p), ("nchunks", C.c_uint64), ("data_length", C.c_uint64),
                 ("compressor", C.c_int32), ("chunk_len", C.c_int32), ("max_compressed_len", C.c_int32), ("ncolumns", C.c_int32),
-                ("column_map", C.c_int32 * MAX_COLUMNS), ("header_stats", EncodingStats), ("_pad", C.c_int32), ("level", C.c_int32)]
+                ("column_map", C.c_int32 * MAX_COLUMNS), ("header_stats", EncodingStats), ("_pad", C.c_int32), ("level", C.c_int32),
+                ("summary_positions", C.c_void_p), ("nsummary", C.c_uint64)]
 class Manifest(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("ninputs", C.c_int32), ("inputs", C.POINTER(Input)),
                 ("nclustering", C.c_int32), ("clustering", Column * MAX_CLUSTERING),

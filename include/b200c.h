@@ -148,6 +148,13 @@ typedef struct b200c_input {
     b200c_encoding_stats header_stats;  /* SerializationHeader.Component stats used to DEcode this input */
     int32_t         _pad;
     int32_t         level;              /* informational (LCS level) */
+    /* Summary.db (IndexSummary, S/io/sstable/indexsummary/IndexSummary.java:190-193 getPosition): Index.db offsets of the sampled
+       entries, ascending, the first one 0. They are what BigTableScanner seeks with (S/io/sstable/format/big/BigTableScanner.java:
+       105-132); here they seed the parallel Index.db walk, whose result is still proven against the sequential parse. Optional
+       (NULL / 0): without them the walk has to speculate on entry starts with the help of Data.db, and host-buffer compactions
+       cannot overlap their Data.db copies with the kernels (no token-range streaming). */
+    const uint64_t* summary_positions;
+    uint64_t        nsummary;
 } b200c_input;
 
 typedef struct b200c_manifest {

@@ -20,7 +20,8 @@ class Config(C.Structure):
 class Result(C.Structure):
     _fields_ = [("data", C.c_void_p), ("data_len", C.c_uint64), ("index", C.c_void_p), ("index_len", C.c_uint64),
                 ("partitions", C.c_uint64), ("rows", C.c_uint64), ("min_timestamp", C.c_int64),
-                ("min_local_deletion_time", C.c_int64), ("min_ttl", C.c_int32), ("_pad", C.c_int32)]
+                ("min_local_deletion_time", C.c_int64), ("min_ttl", C.c_int32), ("_pad", C.c_int32),
+                ("summary", C.c_void_p), ("nsummary", C.c_uint64)]
 
 def build():
     out = os.path.join(_HERE, "_build", "libsynth.so")
@@ -51,7 +52,8 @@ def generate_raw(schema, sstable, nsstables, seed, universe, p=0.5, rows_per_par
     try:
         stream = np.ctypeslib.as_array(C.cast(res.data, C.POINTER(C.c_uint8)), shape=(res.data_len,)).copy() if res.data_len else np.zeros(0, np.uint8)
         index = C.string_at(res.index, res.index_len)
-        return dict(stream=stream, index=index, partitions=res.partitions, rows=res.rows,
+        summary = np.ctypeslib.as_array(C.cast(res.summary, C.POINTER(C.c_uint64)), shape=(res.nsummary,)).copy() if res.nsummary else np.zeros(0, np.uint64)
+        return dict(stream=stream, index=index, partitions=res.partitions, rows=res.rows, summary=summary,
                     stats=(res.min_timestamp, res.min_local_deletion_time, res.min_ttl))
     finally:
         lib().synth_free(C.byref(res))
@@ -64,5 +66,5 @@ def make_sstable(raw, schema, compress, compressor_name="LZ4Compressor", chunk_l
     meta = CompressionMetadata(compressor_name, chunk_length, 0x7FFFFFFF, len(raw["stream"]), offs)
     sc = SCHEMAS[schema]
     t = SSTable(image, raw["index"], meta, raw["stats"], raw["stats"], sc["clustering"], sc["columns"], generation=generation, level=level)
-    t.partitions = raw["partitions"]; t.rows = raw["rows"]
+    t.partitions = raw["partitions"]; t.rows = raw["rows"]; t.summary_positions = raw.get("summary")
     return t

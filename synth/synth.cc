@@ -266,6 +266,7 @@ struct synth_result {
     uint8_t* data; uint64_t data_len; uint8_t* index; uint64_t index_len;
     uint64_t partitions; uint64_t rows;
     int64_t min_timestamp; int64_t min_local_deletion_time; int32_t min_ttl; int32_t _pad;
+    uint64_t* summary; uint64_t nsummary;      // Index.db offset of every 128th entry (what Summary.db holds at min_index_interval 128)
 };
 
 uint64_t synth_universe_for(int schema, uint64_t target_bytes, double p, int rows_per_partition) {
@@ -307,8 +308,9 @@ int synth_generate(const synth_config* cfg, synth_result* out) {
     std::vector<uint64_t> base(nslices); uint64_t o = 0; for (int i = 0; i < nslices; i++) { base[i] = o; o += slices[i].data.size(); }
     std::vector<std::thread> th3; for (int t = 0; t < T; t++) th3.emplace_back([&, t]() { for (int i = t; i < nslices; i += T) memcpy(data + base[i], slices[i].data.b.data(), slices[i].data.size()); });
     for (auto& x : th3) x.join();
-    Buf index;
+    Buf index; std::vector<uint64_t> summary; uint64_t nentry = 0;
     for (int i = 0; i < nslices; i++) for (auto& e : slices[i].idx) {
+        if ((nentry++ & 127) == 0) summary.push_back(index.size());
         index.be16(8); index.be64(e.key); index.vint(base[i] + e.rel_pos);
         if (e.promoted.empty()) index.vint(0); else index.put(e.promoted.data(), e.promoted.size());
     }
@@ -317,10 +319,12 @@ int synth_generate(const synth_config* cfg, synth_result* out) {
     Gen g(c);
     if (getenv("SYNTH_DEBUG")) fprintf(stderr, "synth: gen %.3fs, stitch+index %.3fs\n", std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     out->data = data; out->data_len = total; out->index = idx; out->index_len = index.size(); out->partitions = parts; out->rows = rows;
+    out->summary = (uint64_t*)malloc(summary.size() * 8 + 8); out->nsummary = summary.size();
+    if (out->summary) memcpy(out->summary, summary.data(), summary.size() * 8);
     out->min_timestamp = g.min_ts; out->min_local_deletion_time = g.min_ldt; out->min_ttl = g.min_ttl; out->_pad = 0;
     return 0;
 }
-void synth_free(synth_result* r) { free(r->data); free(r->index); r->data = r->index = nullptr; }
+void synth_free(synth_result* r) { free(r->data); free(r->index); free(r->summary); r->data = r->index = nullptr; r->summary = nullptr; }
 void synth_drop_universes() { std::lock_guard<std::mutex> lk(g_mu); for (auto& kv : g_universes) delete kv.second; g_universes.clear(); }
 
 }

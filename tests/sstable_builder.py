@@ -107,9 +107,10 @@ class Builder:
 
     def build(self, partitions, chunk_length=16384, compressor=O.COMP_LZ4, generation=0):
         parts = sorted(partitions, key=lambda p: (O.token(p.key), p.key))
-        data = bytearray(); index = bytearray()
-        for p in parts:
+        data = bytearray(); index = bytearray(); summary = []
+        for pi, p in enumerate(parts):
             start = len(data)
+            if pi % getattr(self, 'summary_interval', 3) == 0: summary.append(len(index))      # Summary.db sample (tiny interval: many anchors even in small tables)
             data += struct.pack(">H", len(p.key)) + p.key + _part_dt(p.deletion)
             header_len = len(data) - start
             prev_start = 0; infos = []; first = None; block_start = 0; open_marker = None; last = None
@@ -141,6 +142,8 @@ class Builder:
         stats = (self.min_ts, self.min_ldt, self.min_ttl)
         t = SSTable(bytes(image), bytes(index), meta, stats, stats, self.s.clustering_types, self.s.columns, generation=generation)
         t.uncompressed = data
+        import numpy as _np
+        t.summary_positions = _np.asarray(summary, dtype=_np.uint64)
         return t
     def _index_info(self, first, last, offset, width, open_marker):
         zz = ((width - 65536) << 1) ^ ((width - 65536) >> 63)

@@ -37,6 +37,16 @@ def both(ctx, tables, controller, **kw):
         assert got.stats[k] == want.stats[k], k
     assert got.stats["kernel_launches"] > 0
     assert got.stats["index_slow_path_inputs"] == 0, "Index.db speculation fell back to the sequential walk"
+    if len(tables) <= 6 and any(getattr(t, "summary_positions", None) is not None for t in tables):
+        # same compaction without Summary.db positions: K2 then speculates on entry starts with Data.db's help (and cannot stream)
+        saved = [t.summary_positions for t in tables]
+        try:
+            for t in tables: t.summary_positions = None
+            g2 = CompactionTask(tables, controller, **kw).execute(GpuEngine(ctx))
+        finally:
+            for t, sp in zip(tables, saved): t.summary_positions = sp
+        o2 = g2.outputs[0]
+        assert o2.data == w.data and o2.index == w.index and o2.digest == w.digest and g2.stats["index_slow_path_inputs"] == 0
     return got, want
 
 def _golden(golden_dir, name): return os.path.join(golden_dir, "oa", "legacy_tables", name, "oa-1-big-")
@@ -341,3 +351,16 @@ def test_token_range_streaming_tiny_and_empty(ctx, monkeypatch):
     gone = b.build([Partition(b"k", [], (5, 7))])
     got, _ = both(ctx, [gone], CompactionController(NOW))
     assert got.outputs[0].data == b""
+
+
+def test_wrong_summary_positions_only_cost_the_sequential_walk(ctx):
+    """Summary positions are hints: the Index.db walk is proven against the sequential parse, so garbage hints must not change a byte"""
+    import numpy as np
+    tabs = synth_tables(0, 3, 0x5AD, 5000)
+    for g, t in enumerate(tabs): t.generation = g
+    want = CompactionTask(tabs, CompactionController(NOW)).execute(O.OracleEngine()).outputs[0]
+    tabs[1].summary_positions = np.asarray([0, 7, 1001, len(tabs[1].index) // 2 + 1], dtype=np.uint64)
+    got = CompactionTask(tabs, CompactionController(NOW)).execute(GpuEngine(ctx))
+    g = got.outputs[0]
+    assert g.data == want.data and g.index == want.index and g.digest == want.digest
+    assert got.stats["index_slow_path_inputs"] == 1

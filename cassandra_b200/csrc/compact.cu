@@ -1130,7 +1130,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         ubase_total += ulen_out; ilen_total += ilen_out;
     }
-    mark(-1);
     c->prog_scanned.store(bytes_read * 3 / 4);
 
     // ---- K5 wrap-up / remaining writers ------------------------------------------------------------------------------------------------

@@ -268,6 +268,18 @@ __global__ void k_input_ranges(const CParams* __restrict__ Pp, const uint64_t* _
     range[2 * i] = lo; range[2 * i + 1] = hi;
 }
 
+// an SSTable is ordered by (token, key) and its partitions do not overlap: tokens must not decrease and Data.db positions must
+// increase along Index.db (everything downstream binary-searches these arrays)
+__global__ void __launch_bounds__(256) k_check_order(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ pcount,
+                                                     const int64_t* __restrict__ tok, const uint64_t* __restrict__ upos, DevErr* __restrict__ err) {
+    const CParams& P = *Pp;
+    for (int i = 0; i < P.ninputs; i++) {
+        const uint64_t n = pcount[i], b = pbase[i];
+        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g + 1 < n; g += (uint64_t)gridDim.x * blockDim.x)
+            if (tok[b + g + 1] < tok[b + g] || upos[b + g + 1] <= upos[b + g]) report_err(err, 3, i, upos[b + g] - P.in[i].ubase);
+    }
+}
+
 // token-range pieces: for piece r and input i the byte range [plan[2k], plan[2k+1]) of U (k = r * K + i) holding the partitions with
 // token in (T[r], T[r+1]]; same bounds as k_input_ranges
 __global__ void k_range_plan(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ pcount,
@@ -690,16 +702,24 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // positions the token space is cut into `want_ranges` pieces, the Data.db chunks each piece needs are copied piece by piece on the
     // copy stream, and K1/K3/K4/K5 of piece r run underneath the copies of the pieces after it and the read-back of the pieces before
     // it. Device-resident inputs and multi-file (LCS) outputs run as one piece.
-    int want_ranges = 1; bool forced_ranges = false;      // B200C_RANGES=n: test/tuning override of the piece count
+    // Piece boundaries as fractions of the token-sorted input: small pieces first (the kernels can start as soon as little data
+    // has arrived), doubling afterwards (few pieces = little per-piece overhead). B200C_RANGES=n forces n equal pieces (tests, tuning).
+    std::vector<double> cuts; bool forced_ranges = false;          // interior cut points in (0, 1)
     if (!dev && !lcs) {
-        want_ranges = (int)std::min<uint64_t>(MAX_RANGES, std::max<uint64_t>(1, co / (768ull << 20)));
-        if (const char* e = getenv("B200C_RANGES")) { want_ranges = std::max(1, std::min((int)MAX_RANGES, atoi(e))); forced_ranges = true; }
+        if (const char* e = getenv("B200C_RANGES")) {
+            int n = std::max(1, std::min((int)MAX_RANGES, atoi(e))); forced_ranges = true;
+            for (int r = 1; r < n; r++) cuts.push_back((double)r / n);
+        } else if (co >= (1536ull << 20)) {
+            double f = std::min(0.5, std::max(1.0 / 16, (double)(512ull << 20) / (double)co));
+            for (; f < 1.0 && cuts.size() + 1 < MAX_RANGES; f *= 2) cuts.push_back(f);
+        }
     }
+    int want_ranges = (int)cuts.size() + 1;
     // with Summary.db positions for every input the Index.db walk does not need Data.db: its copies are then scheduled after K2
     bool have_summaries = true;
     for (int i = 0; i < K; i++) if (m->inputs[i].index_len && !(m->inputs[i].summary_positions && m->inputs[i].nsummary)) have_summaries = false;
     const bool deferred = !dev && !lcs && have_summaries;
-    if (!deferred) want_ranges = 1;
+    if (!deferred) { want_ranges = 1; cuts.clear(); }
 
     uint8_t *U, *CD, *IDX; uint64_t* CO; CParams* dP; uint64_t* d_bbase; DevErr* d_err; ChunkErr* d_cerr; RunStats* d_stats; unsigned long long* d_hist;
     B200C_TRY(ws_typed(c, WS_U, uo + 64, &U));
@@ -746,7 +766,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[i], cs));
     }
     if (deferred && want_ranges > 1)         // keep the link busy while K2 finishes: the head of every Data.db is needed by the first piece
-        for (int i = 0; i < K; i++) { uint64_t pre = m->inputs[i].nchunks / want_ranges; B200C_TRY(copy_chunks(i, 0, pre)); h2d_next[i] = pre; }
+        for (int i = 0; i < K; i++) { uint64_t pre = (uint64_t)(m->inputs[i].nchunks * cuts[0]); B200C_TRY(copy_chunks(i, 0, pre)); h2d_next[i] = pre; }
     c->prog_total.store(bytes_read); c->prog_scanned.store(0);
     timing_begin(c);
 
@@ -852,6 +872,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pcount, pcount.data(), K * 8, cudaMemcpyHostToDevice, st));
     if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
                               d_tok, d_kp, d_klen, d_upos, d_err);
+    if (total_parts > (uint64_t)K) B200C_LAUNCH(c, k_check_order, 1184, 256, 0, dP, d_pbase, d_pcount, d_tok, d_upos, d_err);
     B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range);
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
@@ -863,6 +884,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         return B200C_ECORRUPT;
     };
     if (h[200] != ~0ull) return index_data_mismatch(h[200]);
+    for (int i = 0; i < K; i++) if (h[2 * i] > h[2 * i + 1] || h[2 * i + 1] > pcount[i]) return index_data_mismatch((uint64_t)i << 48);
 
     // ---- token ranges --------------------------------------------------------------------------------------------------------------
     // T[0] < T[1] < ... < T[nr]: piece r merges the partitions with token in (T[r], T[r+1]] (T[0] = I64_MIN: from the first one)
@@ -872,7 +894,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         for (int i = 0; i < K; i++) { uint64_t n = h[2 * i + 1] - h[2 * i]; if (n > nmax) { nmax = n; imax = i; } }
         if (nmax >= (uint64_t)want_ranges * (forced_ranges ? 2 : 4096)) {   // quantiles of the largest input's tokens
             const uint64_t lo = h[2 * imax];
-            for (int r = 1; r < want_ranges; r++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 600 + r, d_tok + pbase[imax] + lo + nmax * r / want_ranges, 8, cudaMemcpyDeviceToHost, st));
+            for (int r = 1; r < want_ranges; r++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 600 + r, d_tok + pbase[imax] + lo + std::min<uint64_t>(nmax - 1, (uint64_t)(nmax * cuts[r - 1])), 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
             T.pop_back();
             for (int r = 1; r < want_ranges; r++) { int64_t t = (int64_t)h[600 + r]; if (t > T.back() && t < m->token_hi) T.push_back(t); }

@@ -199,8 +199,13 @@ int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint
                              uint64_t chunk0, uint64_t count, int tag) {
     if (chunk0 >= nchunks || count == 0) return B200C_OK;
     const uint64_t end = count > nchunks - chunk0 ? nchunks : chunk0 + count;
-    B200C_LAUNCH(c, k_decompress_chunks, (unsigned)((end - chunk0 + 1) / 2), 64, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
-                 chunk_len, max_clen, data_length, d_out, verify, d_err, chunk0, end, tag);
+    static const int k1_mode = []() { const char* e = getenv("B200C_K1"); return e ? atoi(e) : 1; }();      // 0: warp per chunk, 1: thread per chunk (LZ4)
+    if (k1_mode == 1 && comp == COMP_LZ4 && (chunk_len & 7) == 0 && ((uintptr_t)d_out & 7) == 0)
+        B200C_LAUNCH(c, k_decompress_chunks_thr, (unsigned)((end - chunk0 + 127) / 128), 128, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
+                     chunk_len, max_clen, data_length, d_out, verify, d_err, chunk0, end, tag);
+    else
+        B200C_LAUNCH(c, k_decompress_chunks, (unsigned)((end - chunk0 + 1) / 2), 64, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
+                     chunk_len, max_clen, data_length, d_out, verify, d_err, chunk0, end, tag);
     return B200C_OK;
 }
 

@@ -2,6 +2,7 @@
 // include/b200c.h (b200c_compress_chunks / b200c_decompress_chunks / ICompressor single-buffer calls).
 // No CPU fallback: every compute entry point needs a CUDA device and fails with B200C_ECUDA otherwise.
 #include "engine.cuh"
+#include <algorithm>
 #include "scan.cuh"
 #include "codec.cuh"
 #include <climits>
@@ -54,6 +55,17 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
                           uint8_t* slots, int stride, uint32_t* file_len, uint32_t* seg_raw) {
     uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
     if (!nchunks) return B200C_OK;
+    static const int k5_mode = []() { const char* e = getenv("B200C_K5"); return e ? atoi(e) : 0; }();      // 0: warp per chunk, 1: thread per chunk (LZ4)
+    if (k5_mode == 1 && comp == COMP_LZ4 && (chunk_len & 15) == 0 && ((uintptr_t)d_in & 15) == 0) {
+        const uint64_t batch = 262144;                    // hash tables of one launch: 16 KiB each in global memory
+        uint16_t* tabs; B200C_TRY(ws_typed(c, 93, std::min(nchunks, batch) * (uint64_t)LZ4_TABLE_ENTRIES, &tabs));
+        for (uint64_t a = 0; a < nchunks; a += batch) {
+            const uint64_t b = std::min(nchunks, a + batch);
+            B200C_CUDA_TRY(c, cudaMemsetAsync(tabs, 0, (b - a) * (uint64_t)LZ4_TABLE_ENTRIES * 2, c->stream));
+            B200C_LAUNCH(c, k_compress_chunks_thr, (unsigned)((b - a + 127) / 128), 128, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw, tabs, a, b);
+        }
+        return B200C_OK;
+    }
     int tab_bytes = comp == COMP_SNAPPY ? 32768 : 16384;
     size_t smem = (size_t)tab_bytes + chunk_len + 16;
     B200C_LAUNCH(c, k_compress_chunks, (unsigned)nchunks, 32, smem, c->d_tables, comp, tab_bytes, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);

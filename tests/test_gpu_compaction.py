@@ -364,3 +364,14 @@ def test_wrong_summary_positions_only_cost_the_sequential_walk(ctx):
     g = got.outputs[0]
     assert g.data == want.data and g.index == want.index and g.digest == want.digest
     assert got.stats["index_slow_path_inputs"] == 1
+
+@pytest.mark.parametrize("env", [{"B200C_K5": "1"}, {"B200C_K1": "0"}])
+def test_alternate_codec_kernels_match(env):
+    """both mappings of the chunk codec stay selectable for A/B (B200C_K1: 0 = warp per chunk, 1 = thread per chunk; same for
+    B200C_K5): the parity tests must pass with either"""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_codec.py", "tests/test_gpu_compaction.py",
+                        "-k", "codec or golden or synthetic_configs or lcs_wide or streaming_matches"], cwd=root, env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

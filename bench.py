@@ -191,6 +191,15 @@ def run_b200(args):
         sdt, _, sst, _, _, _ = timed(False, e_steps)
         sweep[rr] = {"ms_per_step": round(sdt / e_steps * 1e3, 2), "stage_ms": [round(x, 1) for x in sst]}
         del os.environ["B200C_RANGES"]
+    ab = None
+    if args.ab_env:
+        k_, v_ = args.ab_env.split("=", 1); os.environ[k_] = v_
+        step(True); step(False)
+        adt, _, ast_, _, _, _ = timed(True, args.steps)
+        bdt, _, bst_, _, _, _ = timed(False, e_steps)
+        ab = {"env": args.ab_env, "value": round(total_in_all * args.steps / adt / 1e6, 1), "e2e": round(total_in_all * e_steps / bdt / 1e6, 1),
+              "stage_ms": [round(x, 1) for x in ast_], "e2e_stage_ms": [round(x, 1) for x in bst_]}
+        del os.environ[k_]
     h2d = c_in + i_in + 8 * sum(t.nchunks for t in tabs) + 8 * sum(t.summary.numel() for t in tabs); d2h = c_out + i_out + 8 * int(elast.outputs[0].nchunks)
 
     # roofline of the dominant stage, algorithmic bytes per SURVEY §8(d): every compressed byte read once, every uncompressed byte
@@ -218,7 +227,7 @@ def run_b200(args):
             "bytes": {"u_in": u_in, "c_in": c_in, "index_in": i_in, "u_out": u_out, "c_out": c_out, "index_out": i_out},
             "e2e": {"value": round(e2e, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(edt / e_steps * 1e3, 2),
                     "device_ms_per_step": round(ekms, 2), "stage_ms": {n: round(s_, 2) for n, s_ in zip(names, estages)}},
-            "e2e_ranges_sweep": sweep, "gpu_launches": int(launches), "index_slow_path_inputs": int(last.index_slow_path_inputs), "clocks": clocks, "roofline": roof}
+            "e2e_ranges_sweep": sweep, "ab": ab, "gpu_launches": int(launches), "index_slow_path_inputs": int(last.index_slow_path_inputs), "clocks": clocks, "roofline": roof}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(1, args.cpu_sample_mib, 1)
     if rank == 0:
@@ -294,6 +303,7 @@ def main():
     ap.add_argument("--sstables", type=int, default=16)
     ap.add_argument("--sstable-mib", type=float, default=1024.0, help="uncompressed size of each input (configs[1]: 1024)")
     ap.add_argument("--e2e-ranges", default="", help="development aid: also time the e2e path with B200C_RANGES forced to each of these comma-separated values")
+    ap.add_argument("--ab-env", default="", help="development aid: NAME=VALUE; after the normal measurement, time both legs again with this environment variable set")
     ap.add_argument("--schema", default="N", choices=["N", "W"], help="N: narrow rows (configs[1..3]); W: wide time-series partitions (configs[4] shape)")
     ap.add_argument("--rows-per-partition", type=int, default=1000)
     ap.add_argument("--cpu-sample-mib", type=float, default=32.0)

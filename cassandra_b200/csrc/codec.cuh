@@ -237,15 +237,9 @@ __device__ int lz4_decompress_thread(const uint8_t* __restrict__ src, int n, uin
     return w.op;
 }
 
-__global__ void __launch_bounds__(128) k_decompress_chunks_thr(const DevTables* __restrict__ T, int comp,
+__device__ __forceinline__ void decompress_chunk_thread(const uint32_t (*s_crc)[256], int comp,
         const uint8_t* __restrict__ data, uint64_t data_len, const uint64_t* __restrict__ offs, uint64_t nchunks,
-        int chunk_len, int max_clen, uint64_t data_length, uint8_t* out, int verify, ChunkErr* __restrict__ err,
-        uint64_t chunk0, uint64_t chunk_end, int tag) {
-    __shared__ uint32_t s_crc[4][256];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i >> 8][i & 255] = T->crc_t[i >> 8][i & 255];
-    __syncthreads();
-    const uint64_t chunk = chunk0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= chunk_end || chunk >= nchunks) return;
+        int chunk_len, int max_clen, uint64_t data_length, uint8_t* out, int verify, ChunkErr* __restrict__ err, uint64_t chunk, int tag) {
     const uint64_t off = offs[chunk];
     const uint64_t next = (chunk + 1 < nchunks) ? offs[chunk + 1] : data_len;
     const uint64_t ustart = chunk * (uint64_t)chunk_len;
@@ -285,132 +279,32 @@ __global__ void __launch_bounds__(128) k_decompress_chunks_thr(const DevTables* 
     if (got != ulen) report_chunk_err(err, ctag, 2);
 }
 
-// ---- K5, thread-per-chunk variant (LZ4) ------------------------------------------------------------------------------------
-// Same trade as k_decompress_chunks_thr: liblz4's scalar loop (LZ4_compress_generic, byU16 table, acceleration 1) runs unchanged in
-// every thread, the 16 KiB hash table of each chunk lives in global memory (zeroed by the caller), the chunk is read in place and
-// the output goes through the 8-byte write-combining sink. Match length is counted before the token is written so that no byte
-// already handed to the sink has to be patched.
-__device__ __forceinline__ void lz4_put_len(WordSink& w, int rem) {            // length extension bytes: (rem / 255) x 0xFF, rem % 255
-    for (; rem >= 255; rem -= 255) w.put(255ull, 1);
-    w.put((uint64_t)rem, 1);
-}
-__device__ __forceinline__ void lz4_put_run(WordSink& w, const uint8_t* src, int from, int len) {
-    for (; len >= 8; len -= 8, from += 8) w.put(ld_le64(src + from), 8);
-    if (len) w.put(low_bytes(ld_le64(src + from), len), len);
-}
-// src: chunk bytes (4-byte aligned, >= 16 readable bytes behind it), tab: 8192 x u16 zeroed. Appends the block to w.
-__device__ void lz4_compress_thread(const uint8_t* __restrict__ src, int n, uint16_t* __restrict__ tab, WordSink& w) {
-    const uint32_t* in32 = (const uint32_t*)src;
-    int ip = 0, anchor = 0;
-    const int mfl1 = n - LZ4_MFLIMIT + 1, matchlimit = n - LZ4_LASTLITERALS;
-    if (n >= LZ4_MINLENGTH) {
-        // position 0 goes into the table with value 0: the zeroed state
-        ip = 1;
-        uint32_t forwardH = lz4_hash_u16(rd32_at(in32, ip));
-        for (;;) {
-            int match; bool immediate = false;
-            {   // find a match
-                int forwardIp = ip, step = 1, searchMatchNb = 1 << 6;
-                bool found_end = false;
-                for (;;) {
-                    uint32_t h = forwardH;
-                    int current = forwardIp;
-                    match = (int)tab[h];
-                    ip = forwardIp;
-                    forwardIp += step;
-                    step = searchMatchNb++ >> 6;
-                    if (forwardIp > mfl1) { found_end = true; break; }
-                    forwardH = lz4_hash_u16(rd32_at(in32, forwardIp));
-                    tab[h] = (uint16_t)current;
-                    if (rd32_at(in32, match) == rd32_at(in32, ip)) break;
-                }
-                if (found_end) break;
-            }
-            while (ip > anchor && match > 0 && src[ip - 1] == src[match - 1]) { ip--; match--; }      // catch up
-            for (;;) {      // one sequence per iteration; repeats while the position right after a match matches again
-                const int lit = immediate ? 0 : ip - anchor;
-                int mc = 0;
-                {   // LZ4_count from ip + 4 / match + 4, limited by matchlimit
-                    const int pi = ip + LZ4_MINMATCH, pm = match + LZ4_MINMATCH;
-                    while (pi + mc + 8 <= matchlimit) {
-                        uint64_t x = ld_le64(src + pi + mc) ^ ld_le64(src + pm + mc);
-                        if (x) { mc += (__ffsll((long long)x) - 1) >> 3; goto counted; }
-                        mc += 8;
-                    }
-                    while (pi + mc < matchlimit && src[pi + mc] == src[pm + mc]) mc++;
-                }
-            counted:
-                w.put((uint64_t)(((lit < 15 ? lit : 15) << 4) | (mc < 15 ? mc : 15)), 1);
-                if (lit >= 15) lz4_put_len(w, lit - 15);
-                if (lit) lz4_put_run(w, src, anchor, lit);
-                w.put((uint64_t)(uint16_t)(ip - match), 2);
-                if (mc >= 15) lz4_put_len(w, mc - 15);
-                ip += mc + LZ4_MINMATCH;
-                anchor = ip;
-                if (ip >= mfl1) goto last_literals;
-                tab[lz4_hash_u16(rd32_at(in32, ip - 2))] = (uint16_t)(ip - 2);
-                uint32_t h = lz4_hash_u16(rd32_at(in32, ip));
-                match = (int)tab[h];
-                tab[h] = (uint16_t)ip;
-                if (rd32_at(in32, match) == rd32_at(in32, ip)) { immediate = true; continue; }
-                break;
-            }
-            forwardH = lz4_hash_u16(rd32_at(in32, ++ip));
-        }
-    }
-last_literals:
-    {
-        const int last = n - anchor;
-        w.put((uint64_t)((last < 15 ? last : 15) << 4), 1);
-        if (last >= 15) lz4_put_len(w, last - 15);
-        if (last) lz4_put_run(w, src, anchor, last);
-    }
-}
-
-// zero-init CRC register of buf[0..len) (slice-by-4, tables in shared memory)
-__device__ __forceinline__ uint32_t crc_raw_thread(const uint32_t (*s_crc)[256], const uint8_t* buf, int len) {
-    uint32_t crc = 0; int i = 0;
-    for (; i + 8 <= len; i += 8) {
-        uint64_t v = ld_le64(buf + i);
-        uint32_t x = crc ^ (uint32_t)v;
-        crc = s_crc[3][x & 0xff] ^ s_crc[2][(x >> 8) & 0xff] ^ s_crc[1][(x >> 16) & 0xff] ^ s_crc[0][x >> 24];
-        x = crc ^ (uint32_t)(v >> 32);
-        crc = s_crc[3][x & 0xff] ^ s_crc[2][(x >> 8) & 0xff] ^ s_crc[1][(x >> 16) & 0xff] ^ s_crc[0][x >> 24];
-    }
-    for (; i < len; i++) crc = s_crc[0][(crc ^ buf[i]) & 0xff] ^ (crc >> 8);
-    return crc;
-}
-
-__global__ void __launch_bounds__(128) k_compress_chunks_thr(const DevTables* __restrict__ T, const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen,
-        uint8_t* __restrict__ slots, int slot_stride, uint32_t* __restrict__ file_len, uint32_t* __restrict__ seg_raw,
-        uint16_t* __restrict__ tabs, uint64_t chunk0, uint64_t chunk_end) {       // tabs: LZ4_TABLE_ENTRIES u16 per chunk of this launch, zeroed
+__global__ void __launch_bounds__(128) k_decompress_chunks_thr(const DevTables* __restrict__ T, int comp,
+        const uint8_t* __restrict__ data, uint64_t data_len, const uint64_t* __restrict__ offs, uint64_t nchunks,
+        int chunk_len, int max_clen, uint64_t data_length, uint8_t* out, int verify, ChunkErr* __restrict__ err,
+        uint64_t chunk0, uint64_t chunk_end, int tag) {
     __shared__ uint32_t s_crc[4][256];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i >> 8][i & 255] = T->crc_t[i >> 8][i & 255];
     __syncthreads();
     const uint64_t chunk = chunk0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= chunk_end) return;
-    const uint64_t start = chunk * (uint64_t)chunk_len;
-    const int ulen = (int)min((uint64_t)chunk_len, n - start);
-    const uint8_t* src = in + start;
-    uint8_t* slot = slots + chunk * (uint64_t)slot_stride;
-    WordSink w{slot, 0, 0ull};
-    w.put((uint64_t)(uint32_t)ulen, 4);
-    lz4_compress_thread(src, ulen, tabs + (chunk - chunk0) * (uint64_t)LZ4_TABLE_ENTRIES, w);
-    w.flush_bytes();
-    int clen = w.op;
-    if (clen >= max_clen) {                     // flushData :158-177 — stored chunk (never with the default ratio)
-        WordSink r{slot, 0, 0ull};
-        lz4_put_run(r, src, 0, ulen);
-        for (int i = ulen; i < max_clen; i++) r.put(0ull, 1);
-        r.flush_bytes();
-        clen = ulen < max_clen ? max_clen : ulen;
-    }
-    const uint32_t raw = crc_raw_thread(s_crc, slot, clen);
-    const uint32_t crc = ~(raw ^ gf2_mulmod(0xFFFFFFFFu, gf2_xpow8n(T, (uint64_t)clen)));
-    slot[clen] = (uint8_t)(crc >> 24); slot[clen + 1] = (uint8_t)(crc >> 16); slot[clen + 2] = (uint8_t)(crc >> 8); slot[clen + 3] = (uint8_t)crc;
-    file_len[chunk] = (uint32_t)clen + 4;
-    uint32_t x = raw ^ __byte_perm(crc, 0, 0x0123);
-    seg_raw[chunk] = s_crc[3][x & 0xff] ^ s_crc[2][(x >> 8) & 0xff] ^ s_crc[1][(x >> 16) & 0xff] ^ s_crc[0][x >> 24];
+    if (chunk >= chunk_end || chunk >= nchunks) return;
+    decompress_chunk_thread(s_crc, comp, data, data_len, offs, nchunks, chunk_len, max_clen, data_length, out, verify, err, chunk, tag);
+}
+
+// the same over chunk ranges of several inputs in ONE launch: thread-per-chunk only pays off with >= ~10^5 chunks in flight
+__global__ void __launch_bounds__(128) k_decompress_multi_thr(const DevTables* __restrict__ T, const K1Seg* __restrict__ segs, int nseg, uint64_t total,
+                                                              int verify, ChunkErr* __restrict__ err) {
+    __shared__ uint32_t s_crc[4][256];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i >> 8][i & 255] = T->crc_t[i >> 8][i & 255];
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (segs[mid].first <= t) lo = mid; else hi = mid - 1; }
+    const K1Seg g = segs[lo];
+    const uint64_t chunk = g.chunk0 + (t - g.first);
+    if (chunk >= g.nchunks) return;
+    decompress_chunk_thread(s_crc, COMP_LZ4, g.data, g.data_len, g.offs, g.nchunks, g.chunk_len, g.max_clen, g.data_length, g.out, verify, err, chunk, g.tag);
 }
 
 } // namespace b200c

@@ -22,4 +22,8 @@ __device__ __forceinline__ void report_chunk_err(ChunkErr* e, uint64_t chunk, in
     atomicMin(&e->first_bad, ((unsigned long long)chunk << 8) | (unsigned long long)kind);
 }
 
+// one input's chunk range [chunk0, chunk0 + count) in a multi-input K1 launch; first = threads of the launch before this segment
+struct K1Seg { const uint8_t* data; uint64_t data_len; const uint64_t* offs; uint64_t nchunks; uint64_t data_length; uint8_t* out;
+               uint64_t chunk0, count, first; int chunk_len, max_clen, tag, _pad; };
+
 } // namespace b200c

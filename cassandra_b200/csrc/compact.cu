@@ -34,17 +34,18 @@ int pack_digest_device(b200c_ctx* c, const uint8_t* slots, int stride, const uin
                        uint8_t* d_out, uint64_t out_cap, uint64_t* d_offs, uint64_t* out_len, uint32_t* digest, int ws_base);
 int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint64_t data_len, const uint64_t* d_offs, uint64_t nchunks,
                              int chunk_len, int max_clen, uint64_t data_length, uint8_t* d_out, int verify, ChunkErr* d_err, uint64_t chunk0, uint64_t count, int tag);
-int compress_stream_to_host(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t n, int chunk_len, int max_clen,
-                            uint8_t* d_img, uint64_t img_cap, uint8_t* h_out, uint64_t h_cap, uint64_t* d_offs,
-                            uint64_t* out_len, uint32_t* digest, int ws_base);
+int decompress_multi_device(b200c_ctx* c, K1Seg* segs, int nseg, int verify, ChunkErr* d_err, int ws_slot);
 
 enum { IB = 256 };                       // Index.db speculation block
+#ifndef B200C_K1_BATCH_DEFAULT
+#define B200C_K1_BATCH_DEFAULT false
+#endif
 enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pieces per call; slots of b200c_ctx::ev_pool
 #define NONE64 (~0ull)
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_K1SEG_UNUSED, WS_K1SEG,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -806,9 +807,37 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         return decompress_stream_device(c, in.compressor, CD + cbase[i], in.data_len, CO + obase[i], in.nchunks, in.chunk_len,
                                         in.max_compressed_len, in.data_length, U + ubase[i], 1, d_cerr, a, b - a, i);
     };
+    // several inputs' chunk ranges in one thread-per-chunk launch when there are enough of them (B200C_K1_BATCH=0 switches it off)
+    const int k1_batch_env = []() { const char* e = getenv("B200C_K1_BATCH"); return e ? atoi(e) : (B200C_K1_BATCH_DEFAULT ? 1 : 0); }();     // 2: batch even tiny launches (tests)
+    const bool k1_batching = k1_batch_env != 0;
+    std::vector<K1Seg> segs; segs.reserve(K);
+    auto k1_many = [&](const std::vector<uint64_t>& from, const std::vector<uint64_t>& to) -> int {      // chunks [from[i], to[i]) of every input
+        segs.clear(); uint64_t total = 0;
+        for (int i = 0; i < K && k1_batching; i++) {
+            const b200c_input& in = m->inputs[i];
+            if (from[i] >= to[i] || in.compressor != COMP_LZ4 || (in.chunk_len & 7)) continue;
+            K1Seg g; memset(&g, 0, sizeof(g));
+            g.data = CD + cbase[i]; g.data_len = in.data_len; g.offs = CO + obase[i]; g.nchunks = in.nchunks; g.data_length = in.data_length; g.out = U + ubase[i];
+            g.chunk0 = from[i]; g.count = to[i] - from[i]; g.chunk_len = in.chunk_len; g.max_clen = in.max_compressed_len; g.tag = i;
+            segs.push_back(g); total += g.count;
+        }
+        const bool batched = total >= (k1_batch_env == 2 ? 1u : 32768u);
+        if (batched) B200C_TRY(decompress_multi_device(c, segs.data(), (int)segs.size(), 1, d_cerr, WS_K1SEG));
+        for (int i = 0; i < K; i++) {
+            const b200c_input& in = m->inputs[i];
+            if (batched && in.compressor == COMP_LZ4 && !(in.chunk_len & 7)) continue;
+            B200C_TRY(k1(i, from[i], to[i]));
+        }
+        return B200C_OK;
+    };
+    if (dev && k1_batching) {                       // device-resident inputs: the staging copies are device-to-device, wait for all and decode in one launch
+        std::vector<uint64_t> z(K, 0), e(K);
+        for (int i = 0; i < K; i++) { B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0)); e[i] = m->inputs[i].nchunks; }
+        B200C_TRY(k1_many(z, e));
+    }
     for (int i = 0; i < K; i++) {
         B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0));
-        if (!deferred) B200C_TRY(k1(i, 0, m->inputs[i].nchunks));
+        if (!deferred && !(dev && k1_batching)) B200C_TRY(k1(i, 0, m->inputs[i].nchunks));
         const uint64_t nb = bbase[i + 1] - bbase[i];
         if (nb) {
             unsigned g = (unsigned)((nb + 255) / 256);
@@ -964,7 +993,9 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         c->prog_stage.store(1);
         if (deferred) {
             B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_pool[EV_RANGE + r], 0));
-            for (int i = 0; i < K; i++) B200C_TRY(k1(i, need[(size_t)r * K + i].k1_a, need[(size_t)r * K + i].k1_b));
+            std::vector<uint64_t> a(K), b(K);
+            for (int i = 0; i < K; i++) { a[i] = need[(size_t)r * K + i].k1_a; b[i] = need[(size_t)r * K + i].k1_b; }
+            B200C_TRY(k1_many(a, b));
         }
         // ---- K3: partition merge -------------------------------------------------------------------------------------------------------
         mark(2);

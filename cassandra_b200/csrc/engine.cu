@@ -55,17 +55,6 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
                           uint8_t* slots, int stride, uint32_t* file_len, uint32_t* seg_raw) {
     uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
     if (!nchunks) return B200C_OK;
-    static const int k5_mode = []() { const char* e = getenv("B200C_K5"); return e ? atoi(e) : 0; }();      // 0: warp per chunk, 1: thread per chunk (LZ4)
-    if (k5_mode == 1 && comp == COMP_LZ4 && (chunk_len & 15) == 0 && ((uintptr_t)d_in & 15) == 0) {
-        const uint64_t batch = 262144;                    // hash tables of one launch: 16 KiB each in global memory
-        uint16_t* tabs; B200C_TRY(ws_typed(c, 93, std::min(nchunks, batch) * (uint64_t)LZ4_TABLE_ENTRIES, &tabs));
-        for (uint64_t a = 0; a < nchunks; a += batch) {
-            const uint64_t b = std::min(nchunks, a + batch);
-            B200C_CUDA_TRY(c, cudaMemsetAsync(tabs, 0, (b - a) * (uint64_t)LZ4_TABLE_ENTRIES * 2, c->stream));
-            B200C_LAUNCH(c, k_compress_chunks_thr, (unsigned)((b - a + 127) / 128), 128, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw, tabs, a, b);
-        }
-        return B200C_OK;
-    }
     int tab_bytes = comp == COMP_SNAPPY ? 32768 : 16384;
     size_t smem = (size_t)tab_bytes + chunk_len + 16;
     B200C_LAUNCH(c, k_compress_chunks, (unsigned)nchunks, 32, smem, c->d_tables, comp, tab_bytes, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
@@ -212,12 +201,25 @@ int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint
     if (chunk0 >= nchunks || count == 0) return B200C_OK;
     const uint64_t end = count > nchunks - chunk0 ? nchunks : chunk0 + count;
     static const int k1_mode = []() { const char* e = getenv("B200C_K1"); return e ? atoi(e) : 1; }();      // 0: warp per chunk, 1: thread per chunk (LZ4)
-    if (k1_mode == 1 && comp == COMP_LZ4 && (chunk_len & 7) == 0 && ((uintptr_t)d_out & 7) == 0)
+    // thread per chunk needs tens of thousands of chunks in flight to beat the warp kernel; small launches (token-range pieces of one
+    // input) keep the warp mapping unless compact.cu has batched them (decompress_multi_device)
+    if (k1_mode == 1 && comp == COMP_LZ4 && (chunk_len & 7) == 0 && ((uintptr_t)d_out & 7) == 0 && end - chunk0 >= 32768)
         B200C_LAUNCH(c, k_decompress_chunks_thr, (unsigned)((end - chunk0 + 127) / 128), 128, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
                      chunk_len, max_clen, data_length, d_out, verify, d_err, chunk0, end, tag);
     else
         B200C_LAUNCH(c, k_decompress_chunks, (unsigned)((end - chunk0 + 1) / 2), 64, 0, c->d_tables, comp, d_data, data_len, d_offs, nchunks,
                      chunk_len, max_clen, data_length, d_out, verify, d_err, chunk0, end, tag);
+    return B200C_OK;
+}
+
+// LZ4 chunk ranges of several inputs in one thread-per-chunk launch (segs: host array, first/_pad filled here)
+int decompress_multi_device(b200c_ctx* c, K1Seg* segs, int nseg, int verify, ChunkErr* d_err, int ws_slot) {
+    uint64_t total = 0;
+    for (int i = 0; i < nseg; i++) { segs[i].first = total; segs[i].count = segs[i].nchunks > segs[i].chunk0 ? std::min(segs[i].count, segs[i].nchunks - segs[i].chunk0) : 0; total += segs[i].count; }
+    if (!total) return B200C_OK;
+    K1Seg* d; B200C_TRY(ws_typed(c, ws_slot, (size_t)nseg, &d));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(d, segs, sizeof(K1Seg) * nseg, cudaMemcpyHostToDevice, c->stream));
+    B200C_LAUNCH(c, k_decompress_multi_thr, (unsigned)((total + 127) / 128), 128, 0, c->d_tables, d, nseg, total, verify, d_err);
     return B200C_OK;
 }
 

@@ -38,7 +38,7 @@ int decompress_multi_device(b200c_ctx* c, K1Seg* segs, int nseg, int verify, Chu
 
 enum { IB = 256 };                       // Index.db speculation block
 #ifndef B200C_K1_BATCH_DEFAULT
-#define B200C_K1_BATCH_DEFAULT false
+#define B200C_K1_BATCH_DEFAULT true
 #endif
 enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pieces per call; slots of b200c_ctx::ev_pool
 #define NONE64 (~0ull)

@@ -216,7 +216,11 @@ typedef struct b200c_result {
     uint64_t  index_slow_path_inputs;   /* inputs whose Index.db speculation could not be proven and were walked sequentially on the GPU */
 } b200c_result;
 
-/* flags: bit0 = input/outputs buffers are DEVICE pointers (inputs resident in HBM; used for the kernel-only metric) */
+/* flags: bit0 = input/outputs buffers are DEVICE pointers (inputs resident in HBM; used for the kernel-only metric).
+   With HOST buffers, one output file (max_sstable_bytes == 0) and summary_positions on every input, the call streams: Index.db is
+   copied first, then Data.db chunk ranges token range by token range while earlier ranges are already being merged, compressed and
+   copied back (pin the buffers with b200c_host_register, pageable memory serialises the copies). Every output byte is the same as
+   in the one-piece run. Buffers must stay valid until the call returns; nothing is in flight afterwards, whatever the return code. */
 int          b200c_compact(b200c_ctx*, const b200c_manifest*, b200c_result*, int flags);
 
 typedef struct b200c_progress { uint64_t bytes_scanned; uint64_t bytes_total; int32_t stage; int32_t _pad; } b200c_progress;

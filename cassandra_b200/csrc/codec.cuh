@@ -12,6 +12,7 @@
 #include "lz4.cuh"
 #include "snappy.cuh"
 #include "codec_defs.cuh"
+#include "lz4_thread.cuh"
 
 namespace b200c {
 
@@ -177,66 +178,6 @@ __global__ void __launch_bounds__(64) k_decompress_chunks(const DevTables* __res
 // chunk per THREAD (2048 x 148 in flight), i.e. it trades coalescing for 64 times the memory-level parallelism. To keep the
 // traffic at word granularity the output goes through an 8-byte write-combining register (aligned 64-bit stores only) and all
 // sources are read with two aligned 64-bit loads + a funnel shift. CRC32: slice-by-4 with the tables in shared memory.
-__device__ __forceinline__ uint64_t ld_le64(const uint8_t* p) {
-    uintptr_t a = (uintptr_t)p; const uint64_t* q = (const uint64_t*)(a & ~(uintptr_t)7); uint32_t sh = (uint32_t)(a & 7) * 8;
-    uint64_t lo = q[0];
-    if (sh) lo = (lo >> sh) | (q[1] << (64 - sh));
-    return lo;
-}
-struct WordSink {                       // acc = the bytes of the aligned word around dst + op that lie before dst + op
-    uint8_t* dst; int op; uint64_t acc;
-    __device__ __forceinline__ void put(uint64_t v, int n) {        // 1 <= n <= 8, bytes of v above n are zero
-        int k = (int)((uintptr_t)(dst + op) & 7);
-        acc |= v << (8 * k);
-        if (k + n >= 8) { *(uint64_t*)(dst + op - k) = acc; acc = k ? (v >> (8 * (8 - k))) : 0ull; }
-        op += n;
-    }
-    __device__ __forceinline__ void flush_bytes() {                 // make the pending bytes visible in memory (acc stays valid)
-        int k = (int)((uintptr_t)(dst + op) & 7);
-        for (int j = 0; j < k; j++) dst[op - k + j] = (uint8_t)(acc >> (8 * j));
-    }
-    __device__ __forceinline__ void reload() {                      // after byte-wise stores: pick the partial word up again
-        int k = (int)((uintptr_t)(dst + op) & 7);
-        acc = k ? (*(const uint64_t*)(dst + op - k) & ((1ull << (8 * k)) - 1ull)) : 0ull;
-    }
-};
-__device__ __forceinline__ uint64_t low_bytes(uint64_t v, int n) { return n >= 8 ? v : (v & ((1ull << (8 * n)) - 1ull)); }
-
-// LZ4_decompress_safe semantics; dst is 8-byte aligned, src arbitrary (>= 16 readable bytes of slack behind both buffers)
-__device__ int lz4_decompress_thread(const uint8_t* __restrict__ src, int n, uint8_t* dst, int cap) {
-    if (n == 0) return cap == 0 ? 0 : -1;
-    WordSink w{dst, 0, 0ull};
-    int ip = 0;
-    for (;;) {
-        if (ip >= n) return -1;
-        uint32_t token = src[ip++];
-        int len = (int)(token >> 4);
-        if (len == 15) { uint32_t s; do { if (ip >= n) return -1; s = src[ip++]; len += (int)s; } while (s == 255 && len < (1 << 24)); }
-        if (n - ip < len || cap - w.op < len) return -1;
-        for (; len >= 8; len -= 8, ip += 8) w.put(ld_le64(src + ip), 8);
-        if (len) { w.put(low_bytes(ld_le64(src + ip), len), len); ip += len; }
-        if (ip == n) break;
-        if (n - ip < 2) return -1;
-        int offset = (int)src[ip] | ((int)src[ip + 1] << 8); ip += 2;
-        if (offset == 0 || offset > w.op) return -1;
-        int ml = (int)(token & 15);
-        if (ml == 15) { uint32_t s; do { if (ip >= n) return -1; s = src[ip++]; ml += (int)s; } while (s == 255 && ml < (1 << 24)); }
-        ml += LZ4_MINMATCH;
-        if (cap - w.op < ml) return -1;
-        if (offset >= 16) {                 // the 8 source bytes end at least 8 bytes before op: all of them are in memory already
-            for (; ml >= 8; ml -= 8) w.put(ld_le64(dst + w.op - offset), 8);
-            if (ml) w.put(low_bytes(ld_le64(dst + w.op - offset), ml), ml);
-        } else {                            // short period: byte by byte through memory
-            w.flush_bytes();
-            for (int i = 0; i < ml; i++) dst[w.op + i] = dst[w.op - offset + i];
-            w.op += ml;
-            w.reload();
-        }
-    }
-    w.flush_bytes();
-    return w.op;
-}
-
 __device__ __forceinline__ void decompress_chunk_thread(const uint32_t (*s_crc)[256], int comp,
         const uint8_t* __restrict__ data, uint64_t data_len, const uint64_t* __restrict__ offs, uint64_t nchunks,
         int chunk_len, int max_clen, uint64_t data_length, uint8_t* out, int verify, ChunkErr* __restrict__ err, uint64_t chunk, int tag) {

@@ -519,7 +519,9 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         c.k0 = part_kp[g]; c.ckend_rel = part_klen[g];           // what Index.db said about this partition's key (checked below)
         c.next = (uint64_t)part_tok[g];                          // (parked here until the header is parsed)
     }
+#ifdef __CUDA_ARCH__
     for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
+#endif
     for (uint32_t v = 0; v < m; v++) {
         Cur& c = cur[v];
         uint64_t pos = c.pos;

@@ -1,0 +1,82 @@
+"""CPU parity of the engine's K4 source. tests/native/k4_host.cc compiles cassandra_b200/csrc/partition.cuh — the code every GPU
+thread of k_partition_thr runs: row merge, reconciliation, purge, serialisation, promoted index — with g++ behind a few intrinsic
+shims and feeds it from host-side stand-ins for K1-K3. Its merged Data stream and Index.db must equal the oracle's byte for byte.
+(The GPU tests prove the same for the CUDA build; this one runs without a GPU and lets K4 logic be developed and fuzzed on the CPU.)"""
+import ctypes as C, os, shutil, struct, subprocess, random
+import numpy as np, pytest
+import oracle_lib as O
+from sstable_builder import *
+from synth_util import synth_tables, decompress_output
+from cassandra_b200 import native
+from cassandra_b200.db.compaction import CompactionTask, CompactionController
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NOW = 1700000000
+I32 = lambda v: struct.pack(">i", v)
+
+@pytest.fixture(scope="module")
+def k4lib():
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"): pytest.skip("needs g++ and the CUDA headers")
+    out = os.path.join(ROOT, "tests", "native", "_build", "libk4host.so")
+    srcs = [os.path.join(ROOT, "tests", "native", "k4_host.cc"), os.path.join(ROOT, "oracle", "codec.cc")]
+    deps = srcs + [os.path.join(ROOT, "cassandra_b200", "csrc", f) for f in ("partition.cuh", "common.cuh")] + [os.path.join(ROOT, "include", "b200c.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        r = subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fno-strict-aliasing", "-I/usr/local/cuda/include", "-Wno-attributes",
+                            "-Wno-unknown-pragmas", "-o", out] + srcs, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(out)
+    L.k4host_compact.restype = C.c_int
+    L.k4host_compact.argtypes = [C.POINTER(native.Manifest), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
+    return L
+
+def host_k4(L, task):
+    m = task.build_manifest()
+    total = sum(t.compression.data_length for t in task.inputs)
+    ucap = int(total * 1.5) + 4096; icap = sum(len(t.index) for t in task.inputs) * 2 + 4096
+    u = np.zeros(ucap, dtype=np.uint8); ix = np.zeros(icap, dtype=np.uint8); ul = C.c_uint64(); il = C.c_uint64(); st = (C.c_uint64 * 3)(); err = C.create_string_buffer(256)
+    rc = L.k4host_compact(C.byref(m), u.ctypes.data, ucap, C.byref(ul), ix.ctypes.data, icap, C.byref(il), st, err, 256)
+    assert rc == 0, err.value
+    return bytes(u[:ul.value]), bytes(ix[:il.value]), list(st)
+
+def check(L, tables, controller, **kw):
+    for g, t in enumerate(tables): t.generation = g
+    want = CompactionTask(tables, controller, **kw).execute(O.OracleEngine())
+    data, index, st = host_k4(L, CompactionTask(tables, controller, **kw))
+    w = want.outputs[0]
+    assert data == decompress_output(w), "Data stream of the K4 host build differs from the oracle"
+    assert index == w.index
+    assert st[0] == want.stats["total_source_rows"] and st[2] == w.partitions and st[1] == w.rows
+    return want
+
+@pytest.mark.parametrize("schema,n,universe,rpp,cis", [(0, 4, 6000, 0, 65536), (0, 16, 1500, 0, 65536), (1, 3, 40, 600, 65536), (1, 4, 50, 200, 4096)])
+def test_k4_source_matches_oracle_on_synthetic_tables(k4lib, schema, n, universe, rpp, cis):
+    tabs = synth_tables(schema, n, 0x4B34 + schema + n, universe, rows_per_partition=rpp, column_index_size=cis)
+    check(k4lib, tabs, CompactionController(NOW), column_index_size=cis)
+    check(k4lib, tabs, CompactionController(0, 0), column_index_size=cis)
+    check(k4lib, tabs, CompactionController(NOW, overlapping_min_timestamp=1600000000000000 + 1500000000), column_index_size=cis)
+
+def test_k4_source_on_golden_files(k4lib, golden_dir):
+    from cassandra_b200.io.sstable import SSTable
+    for name in ("legacy_oa_simple", "legacy_oa_clust"):
+        t = SSTable.open(os.path.join(golden_dir, "oa", "legacy_tables", name, "oa-1-big-"))
+        check(k4lib, [t], CompactionController(NOW, 0))
+
+def test_k4_source_mixed_types_and_token_range(k4lib):
+    rng = random.Random(11)
+    s = Schema(["LongType", "UTF8Type"], [("a", "LongType"), ("b", "UTF8Type"), ("c", "Int32Type")])
+    keys = sorted({bytes(rng.getrandbits(8) for _ in range(rng.choice([1, 3, 8, 9, 17]))) for _ in range(120)} | {b""})
+    tables = []
+    for t in range(4):
+        parts = []
+        for k in keys:
+            if rng.random() < 0.5: continue
+            us = []
+            for ck in sorted({(rng.randint(-3, 3), rng.choice([b"", b"x", b"yy", b"zzzz" * 40])) for _ in range(rng.randint(1, 10))}):
+                cells = [Cell(ci, 1000 + rng.randint(0, 5), v) for ci, v in ((0, struct.pack(">q", rng.getrandbits(40))), (1, rng.choice([b"", b"hello", b"w" * 150])), (2, I32(rng.randint(-9, 9)))) if rng.random() < 0.7]
+                us.append(Row((struct.pack(">q", ck[0]), ck[1]), cells, ts=1000 + rng.randint(0, 5) if (rng.random() < 0.8 or not cells) else NO_TS))
+            parts.append(Partition(k, us, (1002, NOW) if rng.random() < 0.1 else None))
+        tables.append(Builder(s, (1000 - t, 0, 0), column_index_size=1024).build(parts))
+    check(k4lib, tables, CompactionController(NOW, 10**9), column_index_size=1024)
+    check(k4lib, tables, CompactionController(NOW, 10**9), column_index_size=1024, token_range=(-(1 << 62), 1 << 61))

@@ -80,3 +80,59 @@ def test_k4_source_mixed_types_and_token_range(k4lib):
         tables.append(Builder(s, (1000 - t, 0, 0), column_index_size=1024).build(parts))
     check(k4lib, tables, CompactionController(NOW, 10**9), column_index_size=1024)
     check(k4lib, tables, CompactionController(NOW, 10**9), column_index_size=1024, token_range=(-(1 << 62), 1 << 61))
+
+def _corruption_fuzz(lib_path, trials):
+    """child process body (runs under LD_PRELOAD=libasan): damaged Data.db contents must end in 'corrupt data' / 'unsupported' or in a
+    normal result — never outside the buffers (ASan aborts the process on any out-of-bounds access of the K4 source)"""
+    L = C.CDLL(lib_path)
+    L.k4host_compact.restype = C.c_int
+    L.k4host_compact.argtypes = [C.POINTER(native.Manifest), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
+    rng = random.Random(77)
+    s = Schema(["LongType", "UTF8Type"], [("a", "LongType"), ("b", "UTF8Type"), ("c", "Int32Type")])
+    keys = sorted({bytes(rng.getrandbits(8) for _ in range(rng.choice([2, 8, 11]))) for _ in range(40)})
+    def table(t):
+        parts = []
+        for k in keys:
+            if rng.random() < 0.4: continue
+            us = [Row((struct.pack(">q", a), b), [Cell(ci, 1000 + rng.randint(0, 5), v) for ci, v in ((0, struct.pack(">q", rng.getrandbits(40))), (1, rng.choice([b"", b"hello", b"w" * 90])), (2, I32(rng.randint(-9, 9)))) if rng.random() < 0.7],
+                      ts=1000 + rng.randint(0, 5)) for a, b in sorted({(rng.randint(-3, 3), rng.choice([b"", b"x", b"zz" * 30])) for _ in range(rng.randint(1, 12))})]
+            parts.append(Partition(k, us, (1002, NOW) if rng.random() < 0.1 else None))
+        return Builder(s, (1000 - t, 0, 0), column_index_size=512).build(parts)
+    tables = [table(t) for t in range(3)]
+    for g, t in enumerate(tables): t.generation = g
+    outcomes = {"ok": 0, "rejected": 0}
+    for trial in range(trials):
+        victim = tables[trial % len(tables)]
+        good_image, good_offs = victim.data, list(victim.compression.chunk_offsets)
+        raw = bytearray(victim.uncompressed)
+        for _ in range(rng.randint(1, 4)):
+            k = rng.randrange(len(raw)); raw[k] = rng.choice([0, 0xFF, raw[k] ^ (1 << rng.randrange(8)), rng.getrandbits(8)])
+        image = bytearray(); offs = []
+        for i in range(0, len(raw), 16384):
+            c = O.chunk_compress(O.COMP_LZ4, bytes(raw[i:i + 16384])); offs.append(len(image)); image += c + struct.pack(">I", O.crc32(c))
+        victim.data = bytes(image); victim.compression.chunk_offsets = offs
+        try:
+            task = CompactionTask(tables, CompactionController(NOW, 10**9), column_index_size=512)
+            m = task.build_manifest()
+            total = sum(t.compression.data_length for t in tables); ucap = total * 2 + 4096; icap = sum(len(t.index) for t in tables) * 2 + 4096
+            u = np.zeros(ucap, dtype=np.uint8); ix = np.zeros(icap, dtype=np.uint8); ul = C.c_uint64(); il = C.c_uint64(); st = (C.c_uint64 * 3)(); err = C.create_string_buffer(256)
+            rc = L.k4host_compact(C.byref(m), u.ctypes.data, ucap, C.byref(ul), ix.ctypes.data, icap, C.byref(il), st, err, 256)
+            outcomes["ok" if rc == 0 else "rejected"] += 1
+        finally:
+            victim.data = good_image; victim.compression.chunk_offsets = good_offs
+    print("k4 corruption fuzz done", outcomes)
+
+def test_k4_source_survives_damaged_data_under_asan(k4lib, tmp_path):
+    import subprocess, sys
+    libasan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(libasan) or not os.path.exists(libasan): pytest.skip("no libasan")
+    out = str(tmp_path / "libk4host_asan.so")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address", "-fno-omit-frame-pointer", "-fno-strict-aliasing", "-I/usr/local/cuda/include",
+                        "-Wno-attributes", "-Wno-unknown-pragmas", "-o", out, os.path.join(ROOT, "tests", "native", "k4_host.cc"), os.path.join(ROOT, "oracle", "codec.cc")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    code = "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.'); import test_k4_host_build as T; T._corruption_fuzz(%r, 150)" % out
+    c = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:abort_on_error=0"))
+    assert c.returncode == 0 and "k4 corruption fuzz done" in c.stdout, (c.stdout + c.stderr)[-4000:]

@@ -90,7 +90,7 @@ def build_manifest(tabs, schema, device_copies=None):
     from cassandra_b200 import native
     from cassandra_b200.io import sstable as sst
     from cassandra_b200.db.compaction import merged_encoding_stats, INT64_MIN, INT64_MAX
-    m = native.Manifest(); m.abi_version = 1; m.ninputs = len(tabs)
+    m = native.Manifest(); m.abi_version = native.ABI_VERSION; m.ninputs = len(tabs)
     arr = (native.Input * len(tabs))()
     for k, t in enumerate(tabs):
         d, ix, of = t.hold

@@ -45,7 +45,7 @@ enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pi
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_K1SEG_UNUSED, WS_K1SEG,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG,
        WS_SCANA = 60, WS_CODEC = 70 };
 
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
@@ -248,8 +248,10 @@ __global__ void __launch_bounds__(256) k_index_emit(const CParams* __restrict__ 
         const uint8_t* key = IDX + in.ibase + o + 2;
         // Index.db <-> Data.db consistency is checked by K4 when it parses the partition header: key length + 8-byte prefix, and for
         // longer keys the token (so this kernel needs Index.db only and can run before Data.db is on the device)
-        tok[g] = murmur3_token(key, kl);
         uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0);
+        // ByteOrderedPartitioner: the order is the key bytes themselves; the sign-flipped 8-byte prefix is an order-preserving token and
+        // the tie path of the merge (cmp_keys) finishes the comparison on the remaining bytes / the length
+        tok[g] = P.partitioner ? (int64_t)(pre ^ 0x8000000000000000ull) : murmur3_token(key, kl);
         kp[g] = pre; klen[g] = (uint16_t)kl; upos[g] = in.ubase + dpos;
         o += len;
     }
@@ -269,17 +271,22 @@ __global__ void k_input_ranges(const CParams* __restrict__ Pp, const uint64_t* _
     range[2 * i] = lo; range[2 * i + 1] = hi;
 }
 
-// an SSTable is ordered by (token, key) and its partitions do not overlap: tokens must not decrease and Data.db positions must
-// increase along Index.db (everything downstream binary-searches these arrays). Files of up to 256 partitions are exempt from the
-// token test: they merge in one bucket in file order, which is what lets the reference's golden fixtures — written by its unit tests
-// under ByteOrderedPartitioner — serve as identity-compaction vectors although the engine itself only implements Murmur3 order.
+// an SSTable is ordered by (token, key) and its partitions do not overlap: tokens must not decrease, equal tokens must come with
+// increasing (8-byte key prefix, length) and Data.db positions must increase along Index.db — everything downstream binary-searches
+// these arrays, so a file in another partitioner's order (or a damaged one) is rejected here whatever its size
+// (SortedTableWriter.verifyPartition S/io/sstable/format/SortedTableWriter.java:165-178 enforces the same order when files are written).
 __global__ void __launch_bounds__(256) k_check_order(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ pcount,
-                                                     const int64_t* __restrict__ tok, const uint64_t* __restrict__ upos, DevErr* __restrict__ err) {
+                                                     const int64_t* __restrict__ tok, const uint64_t* __restrict__ kp, const uint16_t* __restrict__ klen,
+                                                     const uint64_t* __restrict__ upos, DevErr* __restrict__ err) {
     const CParams& P = *Pp;
     for (int i = 0; i < P.ninputs; i++) {
         const uint64_t n = pcount[i], b = pbase[i];
-        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g + 1 < n; g += (uint64_t)gridDim.x * blockDim.x)
-            if ((n > 256 && tok[b + g + 1] < tok[b + g]) || upos[b + g + 1] <= upos[b + g]) report_err(err, 3, i, upos[b + g] - P.in[i].ubase);
+        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g + 1 < n; g += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t x = b + g, y = x + 1;
+            bool bad = tok[y] < tok[x] || upos[y] <= upos[x];
+            if (!bad && tok[y] == tok[x]) bad = kp[y] < kp[x] || (kp[y] == kp[x] && klen[x] <= 8 && klen[y] <= klen[x]);
+            if (bad) report_err(err, 3, i, upos[x] - P.in[i].ubase);
+        }
     }
 }
 
@@ -632,14 +639,18 @@ __global__ void __launch_bounds__(256) k_index_sizes(uint64_t nparts, const uint
 __global__ void k_find_cut(const uint64_t* __restrict__ dpos, uint64_t jlo, uint64_t nparts, uint64_t start_b, const uint64_t* __restrict__ woffs,
                            uint64_t nwin, uint32_t L, uint64_t limit, uint64_t* __restrict__ out /*[0]=j, [1]=status 0 found / 1 end / 2 need a longer window*/) {
     uint64_t a = jlo + 1, b = nparts;
+    // chunks already FLUSHED when the writer stands at byte x of the file: the buffer is flushed lazily, when the next byte needs room
+    // (BufferedDataOutputStreamPlus.write S/io/util/BufferedDataOutputStreamPlus.java:87-139), so a chunk that is exactly full is still
+    // in memory and does not count towards getEstimatedOnDiskBytesWritten (CompressedSequentialWriter.java:128-131)
+    auto flushed = [&](uint64_t x) -> uint64_t { return x ? (x - 1) / L : 0; };
     while (a < b) {
-        uint64_t mid = (a + b) / 2; uint64_t full = (dpos[mid] - start_b) / L;
+        uint64_t mid = (a + b) / 2; uint64_t full = flushed(dpos[mid] - start_b);
         bool cond = full > nwin || woffs[full] > limit;
         if (cond) b = mid; else a = mid + 1;
     }
     out[0] = a;
     if (a >= nparts) { out[1] = 1; return; }
-    uint64_t full = (dpos[a] - start_b) / L;
+    uint64_t full = flushed(dpos[a] - start_b);
     out[1] = full > nwin ? 2 : 0;
 }
 __global__ void __launch_bounds__(256) k_rel_pos(const uint64_t* __restrict__ dpos, uint64_t jlo, uint64_t jhi, uint64_t start_b, uint64_t* __restrict__ dposf) {
@@ -656,8 +667,13 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (!c || !m || !res) return B200C_EINVAL;
     auto t_start = std::chrono::steady_clock::now();
     cudaSetDevice(c->device);
-    c->cancel.store(0); c->prog_stage.store(0);
+    c->prog_stage.store(0);
     if (m->abi_version != B200C_ABI_VERSION || m->ninputs <= 0) { c->err = "bad manifest"; return B200C_EINVAL; }
+    if (m->partitioner != B200C_PARTITIONER_MURMUR3 && m->partitioner != B200C_PARTITIONER_BYTE_ORDERED) { c->err = "partitioner not supported (Murmur3Partitioner and ByteOrderedPartitioner are)"; return B200C_EUNSUPPORTED; }
+    if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) { c->err = "ByteOrderedPartitioner: token sub-ranges are not expressible"; return B200C_EUNSUPPORTED; }
+    if (m->npurge_ranges < 0 || (m->npurge_ranges && (!m->purge_range_hi || !m->purge_range_max_ts))) { c->err = "purge table"; return B200C_EINVAL; }
+    for (int k = 1; k < m->npurge_ranges; k++) if (m->purge_range_hi[k] <= m->purge_range_hi[k - 1]) { c->err = "purge_range_hi must ascend"; return B200C_EINVAL; }
+    if (c->cancel.exchange(0)) { c->err = "cancelled"; return B200C_ECANCELLED; }        // stop requested before the task got here
     if (m->ninputs > MAXK) { c->err = "more than 64 inputs per call"; return B200C_EUNSUPPORTED; }
     if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) { c->err = "static rows / tombstone_option / strict liveness"; return B200C_EUNSUPPORTED; }
     if (m->nclustering > MAXCLUST || m->ncolumns >= 64 || m->ncolumns < 0) { c->err = "schema outside the supported envelope"; return B200C_EUNSUPPORTED; }
@@ -700,6 +716,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     for (int k = 0; k < m->ncolumns; k++) hp.vfix[k] = m->columns[k].fixed_len;
     hp.o_min_ts = m->out_stats.min_timestamp; hp.o_min_ldt = m->out_stats.min_local_deletion_time; hp.o_min_ttl = m->out_stats.min_ttl;
     hp.now = m->now_in_sec; hp.gc_before = m->gc_before; hp.purge_max_ts = m->purge_max_timestamp;
+    hp.partitioner = m->partitioner;
 
     // Token-range streaming (host buffers, one output file): Index.db goes to the device first; once K2 has turned it into tokens and
     // positions the token space is cut into `want_ranges` pieces, the Data.db chunks each piece needs are copied piece by piece on the
@@ -737,6 +754,12 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     { uint8_t* p; B200C_TRY(ws_typed(c, WS_ERR2, 4096, &p)); d_err = (DevErr*)p; d_cerr = (ChunkErr*)(p + 64); d_stats = (RunStats*)(p + 128); d_hist = (unsigned long long*)(p + 256); }
     hp.U = U;
     cudaStream_t st = c->stream;
+    if (m->npurge_ranges) {
+        int64_t* d_pt; B200C_TRY(ws_typed(c, WS_PURGE, 2 * (size_t)m->npurge_ranges, &d_pt));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pt, m->purge_range_hi, 8 * (size_t)m->npurge_ranges, cudaMemcpyHostToDevice, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pt + m->npurge_ranges, m->purge_range_max_ts, 8 * (size_t)m->npurge_ranges, cudaMemcpyHostToDevice, st));
+        hp.purge_hi = d_pt; hp.purge_ts = d_pt + m->npurge_ranges; hp.npurge = m->npurge_ranges;
+    }
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_err, 0xFF, 64, st));
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_cerr, 0xFF, 64, st));
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_stats, 0, 128 + MAXK * 8 + 128, st));
@@ -771,6 +794,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (deferred && want_ranges > 1)         // keep the link busy while K2 finishes: the head of every Data.db is needed by the first piece
         for (int i = 0; i < K; i++) { uint64_t pre = (uint64_t)(m->inputs[i].nchunks * cuts[0]); B200C_TRY(copy_chunks(i, 0, pre)); h2d_next[i] = pre; }
     c->prog_total.store(bytes_read); c->prog_scanned.store(0);
+    for (int i = 0; i < K; i++) c->prog_input_pos[i].store(0);
+    c->prog_ninputs.store(K);
     timing_begin(c);
 
     // stage clock: marks on the main stream; the time between two marks is charged to the stage of the first
@@ -852,7 +877,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
     }
     uint64_t* h = (uint64_t*)c->h_pinned;
-    auto check_cancel = [&]() -> int { if (c->cancel.load()) { c->err = "cancelled"; cudaStreamSynchronize(st); return B200C_ECANCELLED; } return B200C_OK; };
+    // the request is consumed by the call that reports it (b200c.h: sticky until then, so one that lands before the call is not lost)
+    auto check_cancel = [&]() -> int { if (c->cancel.exchange(0)) { c->err = "cancelled"; cudaStreamSynchronize(st); timing_end(c); return B200C_ECANCELLED; } return B200C_OK; };
     auto chunk_error = [&](uint64_t word) -> int {                  // word = d_cerr: (input << 48 | chunk << 8 | kind)
         int which = (int)(word >> 48), kindc = (int)(word & 0xff); uint64_t chunk = (word >> 8) & 0xFFFFFFFFFFull;
         res->corruption.input = which; res->corruption.kind = kindc; res->corruption.chunk = chunk; res->corruption.offset = 0;
@@ -903,7 +929,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pcount, pcount.data(), K * 8, cudaMemcpyHostToDevice, st));
     if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
                               d_tok, d_kp, d_klen, d_upos, d_err);
-    if (total_parts > (uint64_t)K) B200C_LAUNCH(c, k_check_order, 1184, 256, 0, dP, d_pbase, d_pcount, d_tok, d_upos, d_err);
+    if (total_parts > (uint64_t)K) B200C_LAUNCH(c, k_check_order, 1184, 256, 0, dP, d_pbase, d_pcount, d_tok, d_kp, d_klen, d_upos, d_err);
     B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range);
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
@@ -937,6 +963,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     struct Need { uint64_t h2d_a, h2d_b, k1_a, k1_b; };
     std::vector<Need> need((size_t)nr * K, Need{0, 0, 0, 0});
     std::vector<uint64_t> range_bytes(nr, bytes_read);
+    std::vector<uint64_t> range_end((size_t)nr * K, 0);          // per piece and input: Data.db position behind the piece (scanner accounting)
+    for (int i = 0; i < K; i++) range_end[(size_t)(nr - 1) * K + i] = m->inputs[i].data_length;
     if (deferred) {
         int64_t* d_T; uint64_t* d_plan;
         B200C_TRY(ws_typed(c, WS_PLAN, (size_t)nr + 2 + 2 * (size_t)nr * K, &d_T)); d_plan = (uint64_t*)(d_T + nr + 2);
@@ -952,6 +980,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 uint64_t a = hplan[2 * ((size_t)r * K + i)], b = hplan[2 * ((size_t)r * K + i) + 1];
                 if (a < ubase[i] || b < a || b > ubase[i] + in.data_length) return index_data_mismatch(((uint64_t)i << 48));
                 a -= ubase[i]; b -= ubase[i]; tot += b - a;
+                range_end[(size_t)r * K + i] = b;
                 Need& nd = need[(size_t)r * K + i];
                 if (b > a) {
                     uint64_t ca = a / in.chunk_len, cb = std::min<uint64_t>(in.nchunks, (b + in.chunk_len - 1) / in.chunk_len);
@@ -1163,6 +1192,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             }
         }
         c->prog_scanned.store(bytes_read * (4 * (uint64_t)r + 3) / (4 * (uint64_t)nr));
+        if (deferred || r == nr - 1) for (int i = 0; i < K; i++) c->prog_input_pos[i].store(range_end[(size_t)r * K + i]);
 
         // ---- K5 of this piece (one output file in host memory): whole chunks go out now, the rest waits for the next piece -------------
         mark(5);
@@ -1338,6 +1368,13 @@ int b200c_poll(b200c_ctx* c, b200c_progress* p) {
     p->bytes_scanned = c->prog_scanned.load(); p->bytes_total = c->prog_total.load(); p->stage = c->prog_stage.load(); p->_pad = 0;
     return B200C_OK;
 }
+int b200c_poll_inputs(b200c_ctx* c, uint64_t* positions, int n) {
+    if (!c || !positions || n < 0) return B200C_EINVAL;
+    int k = c->prog_ninputs.load(); if (k > n) k = n;
+    for (int i = 0; i < k; i++) positions[i] = c->prog_input_pos[i].load();
+    return k;
+}
 void b200c_cancel(b200c_ctx* c) { if (c) c->cancel.store(1); }
+void b200c_cancel_reset(b200c_ctx* c) { if (c) c->cancel.store(0); }
 
 } // extern "C"

@@ -11,7 +11,7 @@
 
 namespace b200c {
 
-enum { WS_SLOTS = 96 };
+enum { WS_SLOTS = 160 };
 
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
 
@@ -30,6 +30,8 @@ struct b200c_ctx {
     std::atomic<int> cancel{0};
     std::atomic<uint64_t> prog_scanned{0}, prog_total{0};
     std::atomic<int> prog_stage{0};
+    std::atomic<int> prog_ninputs{0};
+    std::atomic<uint64_t> prog_input_pos[B200C_MAX_INPUTS];   // uncompressed bytes of each input consumed so far (b200c_poll_inputs)
     bool timing = false;
     cudaEvent_t ev_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -37,8 +37,11 @@ struct CParams {
     const uint8_t* U;              // all inputs' uncompressed Data streams, back to back (16-byte aligned bases)
     int32_t ninputs, nclust, ncols, column_index_size;
     int32_t ctype[MAXCLUST], cfix[MAXCLUST], vfix[MAXCOLS];
-    int64_t o_min_ts, o_min_ldt; int32_t o_min_ttl, _pad;
+    int64_t o_min_ts, o_min_ldt; int32_t o_min_ttl;
+    int32_t partitioner;           // 0 Murmur3Partitioner, 1 ByteOrderedPartitioner (tok[] then holds the sign-flipped 8-byte key prefix)
     int64_t now, gc_before, purge_max_ts;
+    // optional purge table (b200c_manifest.purge_range_*): ascending token bounds and the threshold that applies up to each of them
+    const int64_t* purge_hi; const int64_t* purge_ts; int64_t npurge;
     InDesc in[MAXK];
 };
 
@@ -492,6 +495,18 @@ __device__ __forceinline__ void read_marker_dts(const CParams& P, const Cur& c, 
     if (r.err) err = r.err;
 }
 
+// the purge evaluator's threshold for one output partition: per-key in the reference (CompactionController.getPurgeEvaluator
+// S/db/compaction/CompactionController.java:247-286), here bucketed by token — first table bound >= the partition's token
+__device__ __forceinline__ int64_t purge_threshold(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0,
+                                                   const uint64_t* __restrict__ pbase, const int64_t* __restrict__ part_tok) {
+    if (!P.npurge) return P.purge_max_ts;
+    const uint64_t e = contrib[c0];
+    const int64_t t0 = part_tok[pbase[(int)((e >> 56) & 0x7F)] + (e & 0xFFFFFFFFFFull)];
+    int64_t a = 0, b = P.npurge;
+    while (a < b) { int64_t mid = (a + b) >> 1; if (P.purge_hi[mid] < t0) a = mid + 1; else b = mid; }
+    return a < P.npurge ? P.purge_ts[a] : P.purge_max_ts;
+}
+
 struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; };
 
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
@@ -506,7 +521,7 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
                                   uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
                                   Cur* cur, DT* open_dt, MCell* merged,
                                   PartOut& out, PartStats& st, int& err) {
-    Purger pg{P.now, P.gc_before, P.purge_max_ts};
+    Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
     if (m > MAXK) { err = PERR_UNSUPPORTED; return; }
@@ -536,7 +551,7 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         DT pd = read_partition_dt(r);
         if (r.err) { err = r.err; return; }
         // keys longer than the 8-byte prefix: the token K2 computed from the Index.db key must be the token of the Data.db key
-        if (kl > 8 && murmur3_token(P.U + pos + 2, kl) != (int64_t)c.next) { err = PERR_CORRUPT; return; }
+        if (kl > 8 && !P.partitioner && murmur3_token(P.U + pos + 2, kl) != (int64_t)c.next) { err = PERR_CORRUPT; return; }
         if (v == 0) { key_off = pos + 2; klen = kl; }
         if (!dt_supersedes(pdel, pd)) pdel = pd;                  // collectPartitionLevelDeletion :465-482
         c.pos = r.p; c.next = r.p;

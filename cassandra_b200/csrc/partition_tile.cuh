@@ -64,7 +64,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
                                        MCell* s_cells, PartOut& out, PartStats& st, int& err) {
     const int lane = tile.thread_rank();
     const bool multi = m > 1;
-    Purger pg{P.now, P.gc_before, P.purge_max_ts};
+    Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
     Cur cur[S]; bool have[S]; DT my_pd[S];
     int lerr = 0;
     uint64_t my_key_off = 0; uint32_t my_klen = 0;
@@ -87,7 +87,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
             r.skip(kl);
             my_pd[s] = read_partition_dt(r);
             if (r.err) lerr = r.err;
-            else if (kl > 8 && murmur3_token(P.U + pos + 2, kl) != part_tok[g]) lerr = PERR_CORRUPT;      // see process_partition
+            else if (kl > 8 && !P.partitioner && murmur3_token(P.U + pos + 2, kl) != part_tok[g]) lerr = PERR_CORRUPT;      // see process_partition
             if (v == 0) { my_key_off = pos + 2; my_klen = kl; }
             cur[s].src = (uint8_t)src; cur[s].pos = r.p; cur[s].end = end; cur[s].next = r.p; cur[s].done = false;
         }

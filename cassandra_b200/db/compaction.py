@@ -20,10 +20,13 @@ INT64_MIN, INT64_MAX = -(1 << 63), (1 << 63) - 1
 class CompactionController:
     """gcBefore and the purge evaluator. overlapping_min_timestamp = min timestamp over live sstables/memtables outside the
     compaction that may contain the keys (None = no overlaps: every tombstone older than gcBefore is purgeable)."""
-    def __init__(self, now_in_sec, gc_grace_seconds=864000, overlapping_min_timestamp=None):
+    def __init__(self, now_in_sec, gc_grace_seconds=864000, overlapping_min_timestamp=None, purge_ranges=None):
         self.now_in_sec = now_in_sec
         self.gc_before = now_in_sec - gc_grace_seconds
         self.purge_max_timestamp = INT64_MAX if overlapping_min_timestamp is None else overlapping_min_timestamp
+        # optional [(token_hi, min timestamp of the overlapping sstables that may hold keys up to token_hi)], ascending: the per-key
+        # evaluator of getPurgeEvaluator bucketed by token range
+        self.purge_ranges = list(purge_ranges or [])
 
 class CompactionResult:
     def __init__(self): self.outputs = []; self.stats = {}
@@ -66,7 +69,7 @@ class CompactionTask:
         for i in sorted(ins, key=lambda s: s.generation):            # newest generation's metadata wins (:91-99)
             for name, t in i.regular_columns: union[name] = t
         out_cols = sorted(union.items(), key=lambda kv: _name_key(kv[0]))
-        m = native.Manifest(); m.abi_version = 1; m.ninputs = len(ins)
+        m = native.Manifest(); m.abi_version = native.ABI_VERSION; m.ninputs = len(ins)
         arr = (native.Input * len(ins))(); self._keep.append(arr)
         for k, s in enumerate(ins):
             a = arr[k]
@@ -103,6 +106,14 @@ class CompactionTask:
         m.now_in_sec = self.controller.now_in_sec; m.gc_before = self.controller.gc_before
         m.purge_max_timestamp = self.controller.purge_max_timestamp
         m.tombstone_option = 0; m.enforce_strict_liveness = 0
+        parts = {i.partitioner for i in ins}
+        if len(parts) != 1 or next(iter(parts)) not in sst.PARTITIONER_IDS:
+            raise native.UnsupportedError(native.EUNSUPPORTED, "partitioner " + ", ".join(sorted(parts)))
+        m.partitioner = sst.PARTITIONER_IDS[next(iter(parts))]
+        pr = self.controller.purge_ranges
+        if pr:
+            hi = np.asarray([a for a, _ in pr], dtype=np.int64); ts = np.asarray([b for _, b in pr], dtype=np.int64); self._keep += [hi, ts]
+            m.npurge_ranges = len(pr); m.purge_range_hi = hi.ctypes.data; m.purge_range_max_ts = ts.ctypes.data
         m.token_lo, m.token_hi = self.token_range; m.max_sstable_bytes = self.max_sstable_bytes
         self.out_columns = out_cols
         return m

@@ -30,13 +30,19 @@ def type_class(type_string: str):
     """AbstractType -> (B200C_TYPE_*, valueLengthIfFixed) for the comparison/layout classes the engine implements."""
     t = type_string
     if t.startswith(MARSHAL): t = t[len(MARSHAL):]
-    fixed_signed = {"LongType": 8, "TimestampType": 8, "DateType": 8, "Int32Type": 4}
-    fixed_bytes = {"DoubleType": 8, "FloatType": 4, "BooleanType": 1, "UUIDType": 16, "TimeUUIDType": 16, "LexicalUUIDType": 16}
+    # LongType / TimestampType / Int32Type compare as signed integers (LongType.compareLongs, S/db/marshal/LongType.java). DateType is the
+    # pre-2.0 timestamp type: ComparisonType.BYTE_ORDER, i.e. UNSIGNED lexicographic (S/db/marshal/DateType.java) — pre-1970 values
+    # sort after post-1970 ones — so it is a fixed-length bytes class, not a signed one.
+    fixed_signed = {"LongType": 8, "TimestampType": 8, "Int32Type": 4}
+    fixed_bytes = {"DateType": 8, "DoubleType": 8, "FloatType": 4, "BooleanType": 1, "UUIDType": 16, "TimeUUIDType": 16, "LexicalUUIDType": 16}
     if t in fixed_signed: return native.TYPE_FIXED_SIGNED, fixed_signed[t]
     if t in fixed_bytes: return native.TYPE_FIXED_BYTES, fixed_bytes[t]
     if t in ("ShortType", "ByteType"): return native.TYPE_VAR_SIGNED, 0
     if t in ("UTF8Type", "AsciiType", "BytesType"): return native.TYPE_BYTES, 0
     raise native.UnsupportedError(native.EUNSUPPORTED, "type outside the supported envelope: " + type_string)
+
+PARTITIONER_IDS = {"org.apache.cassandra.dht.Murmur3Partitioner": native.PARTITIONER_MURMUR3,
+                   "org.apache.cassandra.dht.ByteOrderedPartitioner": native.PARTITIONER_BYTE_ORDERED}
 
 CLUSTERING_OK = {"LongType", "TimestampType", "DateType", "Int32Type", "ShortType", "ByteType", "UTF8Type", "AsciiType", "BytesType"}
 
@@ -47,6 +53,10 @@ def parse_statistics(b: bytes):
     for _ in range(n):
         t, pos = struct.unpack_from(">ii", b, p); p += 8; toc[t] = pos
     out = {}
+    # VALIDATION (0): UTF partitioner class name | double bloomFilterFPChance (S/io/sstable/metadata/ValidationMetadata.java:64-78)
+    if 0 in toc:
+        p = toc[0]; (n,) = struct.unpack_from(">H", b, p); out["partitioner"] = b[p + 2:p + 2 + n].decode()
+        (out["bloom_filter_fp_chance"],) = struct.unpack_from(">d", b, p + 2 + n)
     # STATS (2)
     p = toc[2]
     for _ in range(2):                                 # two EstimatedHistograms
@@ -88,6 +98,7 @@ class SSTable:
         self.static_columns = list(static_columns)
         self.key_type = key_type; self.level = level; self.generation = generation
         self.summary_positions = None                      # Index.db offsets of the Summary.db samples (numpy uint64) when known
+        self.partitioner = "org.apache.cassandra.dht.Murmur3Partitioner"
 
     @classmethod
     def open(cls, base_path: str, generation=0):
@@ -98,6 +109,7 @@ class SSTable:
                    (st["min_timestamp"], st["min_local_deletion_time"], st["min_ttl"]), st["clustering_types"],
                    st["regular_columns"], st["static_columns"], st["key_type"], generation=generation)
         if os.path.exists(base_path + "Summary.db"): t.summary_positions = parse_summary_positions(rd("Summary.db"))
+        t.partitioner = st.get("partitioner", t.partitioner); t.bloom_filter_fp_chance = st.get("bloom_filter_fp_chance", 0.01)
         return t
 
 def parse_summary_positions(buf: bytes):

@@ -8,7 +8,10 @@ OK, EINVAL, ECUDA, ECORRUPT, ECANCELLED, EUNSUPPORTED, ENOMEM, ETOOSMALL = 0, -1
 COMP_NONE, COMP_LZ4, COMP_SNAPPY = 0, 1, 2
 FLAG_DEVICE_PTRS = 1
 INT32_MAX = 0x7FFFFFFF
-MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS = 8, 64, 128
+MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS = 8, 64, 64
+ABI_VERSION = 2
+PARTITIONER_MURMUR3, PARTITIONER_BYTE_ORDERED = 0, 1
+PSIZE_BUCKETS, CELLS_BUCKETS, HLL_P, TDROP_CAP = 151, 115, 13, 512
 TYPE_BYTES, TYPE_FIXED_SIGNED, TYPE_FIXED_BYTES, TYPE_VAR_SIGNED = 0, 1, 2, 3
 
 class B200CError(RuntimeError):
@@ -38,13 +41,29 @@ class Manifest(C.Structure):
                 ("out_max_compressed_len", C.c_int32), ("column_index_size", C.c_int32),
                 ("now_in_sec", C.c_int64), ("gc_before", C.c_int64), ("purge_max_timestamp", C.c_int64),
                 ("tombstone_option", C.c_int32), ("enforce_strict_liveness", C.c_int32),
-                ("token_lo", C.c_int64), ("token_hi", C.c_int64), ("max_sstable_bytes", C.c_uint64)]
+                ("token_lo", C.c_int64), ("token_hi", C.c_int64), ("max_sstable_bytes", C.c_uint64),
+                ("partitioner", C.c_int32), ("npurge_ranges", C.c_int32), ("purge_range_hi", C.c_void_p), ("purge_range_max_ts", C.c_void_p),
+                ("bloom_hash_count", C.c_int32), ("min_index_interval", C.c_int32), ("bloom_words", C.c_uint64)]
+class SSTableStats(C.Structure):
+    _fields_ = [("min_timestamp", C.c_int64), ("max_timestamp", C.c_int64),
+                ("min_local_deletion_time", C.c_int64), ("max_local_deletion_time", C.c_int64),
+                ("min_ttl", C.c_int32), ("max_ttl", C.c_int32),
+                ("total_rows", C.c_uint64), ("total_columns_set", C.c_uint64), ("total_cells", C.c_uint64), ("total_tombstones", C.c_uint64),
+                ("has_partition_level_deletions", C.c_int32), ("tdrop_overflow", C.c_int32),
+                ("partition_size_hist", C.c_uint64 * PSIZE_BUCKETS), ("cells_per_partition_hist", C.c_uint64 * CELLS_BUCKETS),
+                ("ntdrop", C.c_uint32), ("_pad", C.c_uint32),
+                ("tdrop_point", C.c_int64 * TDROP_CAP), ("tdrop_count", C.c_uint64 * TDROP_CAP),
+                ("hll_registers", C.c_uint8 * (1 << HLL_P))]
 class Output(C.Structure):
     _fields_ = [("data", C.c_void_p), ("data_cap", C.c_uint64), ("data_len", C.c_uint64),
                 ("index", C.c_void_p), ("index_cap", C.c_uint64), ("index_len", C.c_uint64),
                 ("chunk_offsets", C.c_void_p), ("chunk_cap", C.c_uint64), ("nchunks", C.c_uint64),
                 ("data_length", C.c_uint64), ("digest", C.c_uint32), ("_pad", C.c_uint32),
-                ("partitions", C.c_uint64), ("rows", C.c_uint64)]
+                ("partitions", C.c_uint64), ("rows", C.c_uint64),
+                ("key_buf", C.c_void_p), ("key_cap", C.c_uint64), ("first_key_len", C.c_uint32), ("last_key_len", C.c_uint32),
+                ("filter", C.c_void_p), ("filter_cap", C.c_uint64), ("filter_len", C.c_uint64),
+                ("summary", C.c_void_p), ("summary_cap", C.c_uint64), ("summary_len", C.c_uint64),
+                ("stats", C.POINTER(SSTableStats))]
 class Result(C.Structure):
     _fields_ = [("noutputs_cap", C.c_int32), ("noutputs", C.c_int32), ("outputs", C.POINTER(Output)),
                 ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64), ("total_source_rows", C.c_uint64),
@@ -83,7 +102,9 @@ SYMBOLS = {
     "b200c_uncompress": (C.c_int, [_vp, _i, _u8p, _i, _u8p, _i]),
     "b200c_compact": (C.c_int, [_vp, C.POINTER(Manifest), C.POINTER(Result), _i]),
     "b200c_poll": (C.c_int, [_vp, C.POINTER(Progress)]),
+    "b200c_poll_inputs": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
     "b200c_cancel": (None, [_vp]),
+    "b200c_cancel_reset": (None, [_vp]),
 }
 
 _LIB = None
@@ -97,7 +118,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             f = getattr(L, name); f.restype = res; f.argtypes = args
-        if L.b200c_abi_version() != 1:
+        if L.b200c_abi_version() != ABI_VERSION:
             raise ImportError("libb200compact.so ABI mismatch")
         _LIB = L
     return _LIB

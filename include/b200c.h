@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200C_ABI_VERSION 1
+#define B200C_ABI_VERSION 2
 
 /* return codes (0 = success). The shim maps them to the reference's exceptions:
  * ECORRUPT -> CorruptSSTableException + markSuspect, ECANCELLED -> CompactionInterruptedException,
@@ -46,6 +46,14 @@ enum {
 };
 
 enum { B200C_COMP_NONE = 0, B200C_COMP_LZ4 = 1, B200C_COMP_SNAPPY = 2 };
+/* IPartitioner of the table (ValidationMetadata.partitioner, S/io/sstable/metadata/ValidationMetadata.java): decides the partition
+ * order every input must already be in and the output is written in (DecoratedKey.compareTo, S/db/DecoratedKey.java:79-91).
+ *   MURMUR3       S/dht/Murmur3Partitioner.java:256-296 — signed 64-bit token, ties by unsigned key bytes
+ *   BYTE_ORDERED  S/dht/ByteOrderedPartitioner.java — the token IS the key: unsigned lexicographic key order. token_lo / token_hi
+ *                 must span the whole ring (sub-ranges of a byte-ordered ring are not expressible as int64 and are refused).
+ * Anything else (RandomPartitioner, LocalPartitioner, OrderPreservingPartitioner) -> B200C_EUNSUPPORTED. An input whose Index.db is
+ * not in the stated order is B200C_ECORRUPT whatever its size. */
+enum { B200C_PARTITIONER_MURMUR3 = 0, B200C_PARTITIONER_BYTE_ORDERED = 1 };
 
 typedef struct b200c_ctx b200c_ctx;
 
@@ -86,7 +94,11 @@ int          b200c_last_stage_ms(b200c_ctx*, double* out, int n);
  * 4-byte big-endian CRC32 of the bytes as written; chunk_offsets[i] = file offset of chunk i (CompressionInfo.db payload);
  * *digest = CRC32 of the whole image (Digest.crc32). If compressed_len >= max_compressed_len the chunk is stored raw
  * (padded with zeroes up to max_compressed_len when shorter) exactly as flushData does; pass INT32_MAX for the default
- * min_compress_ratio = 0. `out_cap` must be >= b200c_compress_bound(...). `flags` bit0: in/out/chunk_offsets are DEVICE pointers. */
+ * min_compress_ratio = 0. `out_cap` must be >= b200c_compress_bound(...). `flags` bit0: in/out/chunk_offsets are DEVICE pointers.
+ * DEVICE pointers (B200C_FLAG_DEVICE_PTRS, here and in every other entry point): the kernels read whole aligned 16-byte words, so
+ * every caller-owned device buffer must be 16-byte aligned and keep >= B200C_DEVICE_SLACK readable (for outputs: writable) bytes
+ * behind its last used byte. b200c_dev_alloc adds that slack itself; plain cudaMalloc'ed buffers must be sized accordingly. */
+#define B200C_DEVICE_SLACK 256
 uint64_t     b200c_compress_bound(int compressor, uint64_t n, int chunk_len);
 uint64_t     b200c_chunk_count(uint64_t n, int chunk_len);
 int          b200c_compress_chunks(b200c_ctx*, int compressor, const uint8_t* in, uint64_t n, int chunk_len,
@@ -130,7 +142,7 @@ typedef struct b200c_encoding_stats {   /* S/db/rows/EncodingStats.java: base va
 
 #define B200C_MAX_CLUSTERING 8
 #define B200C_MAX_COLUMNS    64
-#define B200C_MAX_INPUTS     128
+#define B200C_MAX_INPUTS     64      /* fan-in of one call (one or two sources per lane of the merge warp) */
 
 typedef struct b200c_input {
     const uint8_t*  data;               /* Data.db image (compressed chunks + inline CRCs) */
@@ -184,7 +196,50 @@ typedef struct b200c_manifest {
     int64_t         token_hi;
     /* LCS: switch output file when on-disk bytes exceed this (MaxSSTableSizeWriter.java:76-79); 0 = single output */
     uint64_t        max_sstable_bytes;
+    int32_t         partitioner;        /* B200C_PARTITIONER_* */
+    /* optional purge table (CompactionController.getPurgeEvaluator is per partition key, S/db/compaction/CompactionController.java:
+       247-286: the minimum timestamp over the overlapping sstables that may contain the key). The host buckets the ring: partitions
+       with token <= purge_range_hi[k] (first such k, the array ascending) use purge_range_max_ts[k] instead of purge_max_timestamp;
+       tokens above the last bound use purge_max_timestamp. npurge_ranges = 0: one threshold for the whole call. HOST pointers always. */
+    int32_t         npurge_ranges;
+    const int64_t*  purge_range_hi;
+    const int64_t*  purge_range_max_ts;
+    /* Filter.db geometry, decided by the host as FilterFactory.getFilter(estimatedKeys, fpChance) does (S/utils/FilterFactory.java:
+       60-75, BloomCalculations): K hash functions over bloom_words 64-bit words, per output file. 0 words = no filter (fpChance 1.0). */
+    int32_t         bloom_hash_count;
+    int32_t         min_index_interval; /* Summary.db sampling (128 default, S/schema/TableParams.java); 0 = 128 */
+    uint64_t        bloom_words;
 } b200c_manifest;
+
+/* What MetadataCollector gathers while an output is written (S/io/sstable/metadata/MetadataCollector.java:107-147,208-270; called
+ * from SortedTableWriter.startPartition/addRow/addRangeTomstoneMarker/endPartition, S/io/sstable/format/SortedTableWriter.java:
+ * 183-258, and Rows.collectStats S/db/rows/Rows.java:102-113): the per-cell / per-row / per-partition reductions the Java side
+ * needs to finish Statistics.db (StatsMetadata + CompactionMetadata) WITHOUT re-reading the output. Trackers that saw no value
+ * hold MetadataCollector's defaults (timestamps: INT64_MIN / INT64_MAX; local deletion times: INT64_MAX both; TTLs: 0 both). */
+#define B200C_PSIZE_BUCKETS 151     /* EstimatedHistogram(150): 150 bucket offsets + overflow (S/utils/EstimatedHistogram.java:48-87) */
+#define B200C_CELLS_BUCKETS 115     /* EstimatedHistogram(114) */
+#define B200C_HLL_P 13              /* HyperLogLogPlus(13, 25), MetadataCollector.java:139-145 */
+#define B200C_TDROP_CAP 512
+typedef struct b200c_sstable_stats {
+    int64_t  min_timestamp, max_timestamp;                        /* timestampTracker */
+    int64_t  min_local_deletion_time, max_local_deletion_time;    /* localDeletionTimeTracker */
+    int32_t  min_ttl, max_ttl;                                    /* ttlTracker */
+    uint64_t total_rows, total_columns_set;                       /* updateColumnSetPerRow */
+    uint64_t total_cells;                                         /* sum of currentPartitionCells */
+    uint64_t total_tombstones;                                    /* updateTombstoneCount over the whole file */
+    int32_t  has_partition_level_deletions;
+    int32_t  tdrop_overflow;                                      /* more than B200C_TDROP_CAP distinct rounded drop times: tdrop_* hold the first CAP */
+    uint64_t partition_size_hist[B200C_PSIZE_BUCKETS];            /* estimatedPartitionSize.add(rowSize) per partition */
+    uint64_t cells_per_partition_hist[B200C_CELLS_BUCKETS];       /* estimatedCellPerPartitionCount */
+    /* estimatedTombstoneDropTime input: exact multiset of local deletion times rounded UP to TOMBSTONE_HISTOGRAM_TTL_ROUND_SECONDS
+       (60 s, StreamingTombstoneHistogramBuilder.update), ascending; the shim replays them into the stock builder */
+    uint32_t ntdrop, _pad;
+    int64_t  tdrop_point[B200C_TDROP_CAP];
+    uint64_t tdrop_count[B200C_TDROP_CAP];
+    /* HyperLogLog++ dense registers (p = 13: 8192 six-bit registers, one per byte here) over MurmurHash.hash2_64(key, seed 0)
+       (MetadataCollector.addKey :160-166): register[h >>> 51] = max(1 + numberOfLeadingZeros((h << 13) | (1 << 12))) */
+    uint8_t  hll_registers[1 << B200C_HLL_P];
+} b200c_sstable_stats;
 
 typedef struct b200c_output {           /* one output sstable; caller provides the buffers */
     uint8_t*  data;        uint64_t data_cap;     uint64_t data_len;      /* Data.db image */
@@ -195,6 +250,20 @@ typedef struct b200c_output {           /* one output sstable; caller provides t
     uint32_t  _pad;
     uint64_t  partitions;                                                 /* partitions written */
     uint64_t  rows;                                                       /* rows + markers written */
+    /* ---- the rest of the sstable, all optional: a NULL pointer skips that component. HOST pointers always. ---- */
+    /* first / last partition key written (SortedTableWriter.endPartition :247-250; StatsMetadata.firstKey/lastKey, Summary.db tail):
+       key_buf receives first key then last key back to back; lengths below. Needs key_cap >= first_key_len + last_key_len
+       (2 * 65535 always suffices). */
+    uint8_t*  key_buf;     uint64_t key_cap;      uint32_t first_key_len; uint32_t last_key_len;
+    /* Filter.db image: i32 hashCount | i32 wordCount | bitset bytes (BloomFilterSerializer.serialize S/utils/BloomFilterSerializer.java:
+       50-55, OffHeapBitSet.serialize S/utils/obs/OffHeapBitSet.java:115-119), every written key added as BloomFilter.add does
+       (S/utils/BloomFilter.java:79-122). Geometry comes from the manifest (bloom_hash_count, bloom_words). */
+    uint8_t*  filter;      uint64_t filter_cap;   uint64_t filter_len;
+    /* Summary.db image (IndexSummary.IndexSummarySerializer.serialize S/io/sstable/indexsummary/IndexSummary.java:401-423 followed by
+       first and last key with int length, SSTableReader/IndexSummaryComponent): one sample every manifest.min_index_interval
+       Index.db entries (IndexSummaryBuilder.maybeAddEntry S/io/sstable/indexsummary/IndexSummaryBuilder.java:200-228) */
+    uint8_t*  summary;     uint64_t summary_cap;  uint64_t summary_len;
+    b200c_sstable_stats* stats;
 } b200c_output;
 
 typedef struct b200c_result {
@@ -225,7 +294,16 @@ int          b200c_compact(b200c_ctx*, const b200c_manifest*, b200c_result*, int
 
 typedef struct b200c_progress { uint64_t bytes_scanned; uint64_t bytes_total; int32_t stage; int32_t _pad; } b200c_progress;
 int          b200c_poll(b200c_ctx*, b200c_progress*);   /* callable from another thread */
-void         b200c_cancel(b200c_ctx*);                  /* callable from another thread; the running call returns B200C_ECANCELLED */
+/* ISSTableScanner.getCurrentPosition per input (S/io/sstable/ISSTableScanner.java:34-41, consumed by CompactionIterator.java:289-295):
+ * positions[i] = uncompressed Data.db bytes of input i the merge has consumed so far (it advances token range by token range).
+ * Writes min(n, ninputs of the running / last call) entries and returns that count. Callable from another thread. */
+int          b200c_poll_inputs(b200c_ctx*, uint64_t* positions, int n);
+/* callable from another thread; the running b200c_compact returns B200C_ECANCELLED at its next stage boundary with nothing in
+ * flight. The request is STICKY: a cancel that lands just before the call starts cancels that call (isStopRequested() can turn true
+ * any time after the task was registered, S/db/compaction/CompactionIterator.java:709-742). It is consumed by the call that reports
+ * it; the shim calls b200c_cancel_reset when it binds a NEW task to the context, before that task can be stopped. */
+void         b200c_cancel(b200c_ctx*);
+void         b200c_cancel_reset(b200c_ctx*);
 
 #ifdef __cplusplus
 }

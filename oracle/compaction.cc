@@ -119,6 +119,7 @@ struct Source {
     // current partition
     bool has = false;
     const uint8_t* key = nullptr; int keylen = 0; int64_t token = 0;
+    bool has_prev = false; int64_t prev_token = 0;
     DT pdel; uint64_t upos = 0;     // cursor inside the partition (next unfiltered)
     uint64_t part_start = 0;
 };
@@ -278,6 +279,15 @@ static void load_source(Source& src) {
 
 // advance to the next partition via Index.db (key, position, promoted index skipped): BigTableScanner.java:135-184,
 // RowIndexEntry.Serializer.deserialize S/io/sstable/format/big/RowIndexEntry.java:340-377
+// the order-defining token: Murmur3Partitioner.getToken (S/dht/Murmur3Partitioner.java:256-296), or for ByteOrderedPartitioner
+// (S/dht/ByteOrderedPartitioner.java: the token is the key) the sign-flipped big-endian 8-byte key prefix — an order-preserving stand-in
+// whose ties compare_key() resolves on the full key bytes, i.e. exactly unsigned lexicographic key order
+static thread_local int g_partitioner = B200C_PARTITIONER_MURMUR3;
+static int64_t order_token(const uint8_t* key, int kl) {
+    if (g_partitioner == B200C_PARTITIONER_MURMUR3) return murmur3_token(key, kl);
+    uint64_t pre = 0; for (int q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0);
+    return (int64_t)(pre ^ 0x8000000000000000ull);
+}
 static void next_partition(Source& src, int64_t tok_lo, int64_t tok_hi) {
     const b200c_input& in = *src.in;
     for (;;) {
@@ -289,7 +299,9 @@ static void next_partition(Source& src, int64_t tok_lo, int64_t tok_hi) {
             if (psize < 0) throw Corrupt{src.idx, 3, 0, src.ipos, "promoted index size"};
             ir.bytes(psize);
             src.ipos = ir.p - in.index;
-            int64_t tok = murmur3_token(key, kl);
+            int64_t tok = order_token(key, kl);
+            if (src.has_prev && (tok < src.prev_token)) throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db is not in partitioner order"};
+            src.has_prev = true; src.prev_token = tok;
             if (!((tok_lo == INT64_MIN || tok > tok_lo) && tok <= tok_hi)) continue;
             if (pos + 2 + kl > src.data.size() || ((src.data[pos] << 8) | src.data[pos + 1]) != kl || memcmp(src.data.data() + pos + 2, key, kl) != 0)
                 throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db entry does not match Data.db"};
@@ -480,11 +492,11 @@ struct Writer {
         chunk.clear();
     }
     void write(const uint8_t* p, size_t n) {             // BufferedDataOutputStreamPlus fill-then-flush :87-139
-        while (n) {
+        while (n) {                                      // lazy: a full buffer is flushed only when the next byte needs room (doFlush(count))
+            if (chunk.size() == (size_t)m->out_chunk_len) flush_chunk();
             size_t room = (size_t)m->out_chunk_len - chunk.size();
             size_t k = std::min(room, n);
             chunk.insert(chunk.end(), p, p + k); p += k; n -= k; position += k;
-            if (chunk.size() == (size_t)m->out_chunk_len) flush_chunk();
         }
     }
     void finish_output() { flush_chunk(); Sst& o = outs.back(); o.digest = crc32_ieee(0, o.data.data(), o.data.size()); }
@@ -615,9 +627,12 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
     if (m->nclustering > B200C_MAX_CLUSTERING || m->ncolumns > B200C_MAX_COLUMNS || m->ncolumns >= 64) return B200C_EUNSUPPORTED;
     Schema sc; sc.nclust = m->nclustering; sc.ncols = m->ncolumns;
     memcpy(sc.clust, m->clustering, sizeof(sc.clust)); memcpy(sc.cols, m->columns, sizeof(sc.cols));
+    g_partitioner = m->partitioner;
     std::vector<Source> srcs(m->ninputs);
     uint64_t bytes_read = 0;
     for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; load_source(srcs[i]); bytes_read += srcs[i].data.size(); next_partition(srcs[i], m->token_lo, m->token_hi); }
+    if (m->partitioner != B200C_PARTITIONER_MURMUR3 && m->partitioner != B200C_PARTITIONER_BYTE_ORDERED) return B200C_EUNSUPPORTED;
+    if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) return B200C_EUNSUPPORTED;
     Purger pg{m->now_in_sec, m->gc_before, m->purge_max_timestamp};
     Writer w; w.m = m; w.sc = sc; w.start_output();
     memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
@@ -638,6 +653,9 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
         // partition deletion: collectPartitionLevelDeletion S/db/rows/UnfilteredRowIterators.java:465-482
         DT pdel;
         for (int i : group) if (!pdel.supersedes(srcs[i].pdel)) pdel = srcs[i].pdel;
+        // purge evaluator of this key (CompactionController.getPurgeEvaluator :247-286), bucketed by token in the manifest
+        pg.max_ts = m->purge_max_timestamp;
+        for (int k = 0; k < m->npurge_ranges; k++) if (m->purge_range_hi[k] >= srcs[best].token) { pg.max_ts = m->purge_range_max_ts[k]; break; }
         DT out_pdel = pg.should_purge(pdel) ? DT() : pdel;     // PurgeFunction.applyToDeletion :95-99
         std::string keycopy((const char*)srcs[group[0]].key, srcs[group[0]].keylen);
         bool started = false; uint64_t written = 0;

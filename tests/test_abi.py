@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(L, s), "missing export: " + s
     assert declared == set(native.SYMBOLS), (declared ^ set(native.SYMBOLS))
-    assert L.b200c_abi_version() == 1
+    assert L.b200c_abi_version() == native.ABI_VERSION == 2
 
 def test_struct_sizes_match_header():
     # compile a tiny C program against the header and compare sizeof with the ctypes mirror
@@ -25,14 +25,14 @@ def test_struct_sizes_match_header():
     src = r'''
 #include <stdio.h>
 #include "b200c.h"
-int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200c_corruption), sizeof(b200c_column), sizeof(b200c_encoding_stats),
- sizeof(b200c_input), sizeof(b200c_manifest), sizeof(b200c_output), sizeof(b200c_result), sizeof(b200c_progress));return 0;}'''
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200c_corruption), sizeof(b200c_column), sizeof(b200c_encoding_stats),
+ sizeof(b200c_input), sizeof(b200c_manifest), sizeof(b200c_output), sizeof(b200c_result), sizeof(b200c_progress), sizeof(b200c_sstable_stats));return 0;}'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
     want = [C.sizeof(x) for x in (native.Corruption, native.Column, native.EncodingStats, native.Input, native.Manifest,
-                                  native.Output, native.Result, native.Progress)]
+                                  native.Output, native.Result, native.Progress, native.SSTableStats)]
     assert got == want
 
 def test_no_cpu_fallback_without_device():

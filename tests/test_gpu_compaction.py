@@ -375,3 +375,141 @@ def test_alternate_codec_kernels_match(env):
                         "-k", "(test_gpu_codec or golden or synthetic_configs or lcs_wide or streaming_matches) and not alternate"], cwd=root,
                        env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+# ---- round 2 --------------------------------------------------------------------------------------------------------------------------
+def test_wrong_partition_order_is_rejected_whatever_the_file_size(ctx, golden_dir):
+    """no small-file exemption: 5 byte-ordered keys declared as a Murmur3 file are out of token order -> ECORRUPT (markSuspect), as the oracle"""
+    from cassandra_b200 import native
+    s = SSTable.open(_golden(golden_dir, "legacy_oa_simple"))
+    s.partitioner = "org.apache.cassandra.dht.Murmur3Partitioner"
+    for eng in (GpuEngine(ctx), O.OracleEngine()):
+        with pytest.raises(native.CorruptSSTableError):
+            CompactionTask([s], CompactionController(NOW), column_index_size=4096).execute(eng)
+    # a Murmur3 table fed as ByteOrdered is refused as well
+    t = synth_tables(0, 1, 77, 300)[0]; t.partitioner = "org.apache.cassandra.dht.ByteOrderedPartitioner"
+    with pytest.raises(native.CorruptSSTableError):
+        CompactionTask([t], CompactionController(NOW)).execute(GpuEngine(ctx))
+
+def test_byte_ordered_long_keys_and_ties(ctx):
+    """ByteOrderedPartitioner: keys sharing their first 8 bytes are ordered (and merged) on the remaining bytes and the length"""
+    S1 = Schema(["Int32Type"], [("val", "UTF8Type")]); b = Builder(S1, (0, 0, 0))
+    keys = sorted([b"prefix00", b"prefix00\x00", b"prefix00a", b"prefix00ab", b"prefix0", b"a", b"", b"zzzzzzzzzzzzzzzzzzzz", b"prefix01"])
+    def table(sel, ts):
+        parts = [Partition(k, [Row((I32(1),), [Cell(0, ts, b"v%d" % ts)], ts=ts)]) for k in keys if k in sel]
+        t = b.build(parts)                      # the builder orders by token: rebuild in byte order
+        return t
+    import sstable_builder as sb
+    saved = O.token
+    try:
+        O.token = lambda k: 0                   # Builder.build sorts by (token, key): constant token = pure byte order
+        sb.O.token = O.token
+        t1 = table(set(keys[::2]) | {b"prefix00a"}, 5); t2 = table(set(keys[1::2]) | {b"prefix00a", b""}, 6)
+    finally:
+        O.token = saved; sb.O.token = saved
+    for t in (t1, t2): t.partitioner = "org.apache.cassandra.dht.ByteOrderedPartitioner"
+    got, want = both(ctx, [t1, t2], CompactionController(NOW))
+    assert got.stats["merged_row_counts"][:2] == [len(keys) - 2, 2]
+
+def test_datetype_clustering_is_unsigned_byte_order(ctx):
+    from test_oracle_compaction import datetype_tables
+    sc, tabs, want = datetype_tables()
+    got, _ = both(ctx, tabs, CompactionController(0, 0))
+    parts = decode_stream(sc, decompress_output(got.outputs[0]), (0, 0, 0))
+    assert [u.ck[0] for u in parts[0].unfiltereds] == want
+
+def test_lcs_switch_counts_only_flushed_chunks(ctx):
+    from test_oracle_compaction import lcs_boundary_tables
+    sc, t = lcs_boundary_tables(256)
+    kw = dict(max_sstable_bytes=1000)
+    want = CompactionTask([t], CompactionController(0, 0), **kw).execute(O.OracleEngine(), max_outputs=64)
+    got = CompactionTask([t], CompactionController(0, 0), **kw).execute(GpuEngine(ctx), max_outputs=64)
+    assert [o.partitions for o in got.outputs] == [o.partitions for o in want.outputs] and len(want.outputs) > 3
+    for g, w in zip(got.outputs, want.outputs):
+        assert g.data == w.data and g.index == w.index and g.digest == w.digest and g.compression.chunk_offsets == w.compression.chunk_offsets
+
+def test_purge_table_per_token_range(ctx):
+    tabs = synth_tables(0, 4, 0xCA551234, 3000)
+    cuts = [-(1 << 62), 0, 1 << 62]; base = 1600000000000000
+    thr = [base + 500000000, base + 2500000000, (1 << 63) - 1]
+    ctl = CompactionController(NOW, overlapping_min_timestamp=base + 1500000000, purge_ranges=list(zip(cuts, thr)))
+    got, want = both(ctx, tabs, ctl)
+    flat, _ = both(ctx, tabs, CompactionController(NOW, overlapping_min_timestamp=base + 1500000000))
+    assert flat.outputs[0].data != got.outputs[0].data
+
+def _big_host_task(n=8, universe=400000):
+    tabs = synth_tables(0, n, 0xCA55CA, universe)
+    return tabs, CompactionTask(tabs, CompactionController(NOW))
+
+def test_cancel_before_and_during_the_call(ctx):
+    """b200c_cancel from another thread: the running call returns ECANCELLED with nothing in flight; a request that lands before the
+    call starts is not lost (sticky), and b200c_cancel_reset clears a stale one. The context stays usable."""
+    import ctypes as C, threading, time
+    from cassandra_b200 import native
+    L = native.lib()
+    tabs, task = _big_host_task()
+    # (1) sticky: cancel first, then call
+    L.b200c_cancel(ctx.handle)
+    with pytest.raises(native.CompactionInterruptedError):
+        task.execute(GpuEngine(ctx))
+    # (2) consumed by the call that reported it: the next call runs
+    ok = task.execute(GpuEngine(ctx)); want = ok.outputs[0]
+    # (3) reset clears a stale request
+    L.b200c_cancel(ctx.handle); L.b200c_cancel_reset(ctx.handle)
+    again = task.execute(GpuEngine(ctx)); assert again.outputs[0].data == want.data
+    # (4) mid-run, from a second thread, at several delays; at least one must land while the call is running
+    os.environ["B200C_RANGES"] = "16"
+    try:
+        interrupted = 0
+        for delay in (0.002, 0.01, 0.03, 0.08):
+            err = []
+            def run():
+                try: task.execute(GpuEngine(ctx)); err.append(None)
+                except native.CompactionInterruptedError as e: err.append(e)
+            th = threading.Thread(target=run); th.start(); time.sleep(delay); L.b200c_cancel(ctx.handle); th.join()
+            if err[0] is not None:
+                interrupted += 1
+                assert err[0].code == native.ECANCELLED
+            L.b200c_cancel_reset(ctx.handle)
+        assert interrupted >= 1
+    finally:
+        del os.environ["B200C_RANGES"]
+    final = task.execute(GpuEngine(ctx)); assert final.outputs[0].data == want.data and final.outputs[0].digest == want.digest
+
+def test_poll_while_running(ctx):
+    """b200c_poll / b200c_poll_inputs from another thread during the call: bytes never decrease, stages advance, per-input positions
+    (ISSTableScanner.getCurrentPosition) end at each input's uncompressed length"""
+    import ctypes as C, threading, time
+    from cassandra_b200 import native
+    L = native.lib()
+    tabs, task = _big_host_task()
+    os.environ["B200C_RANGES"] = "8"
+    try:
+        seen = []; done = threading.Event()
+        def poller():
+            p = native.Progress(); pos = (C.c_uint64 * 64)()
+            while not done.is_set():
+                L.b200c_poll(ctx.handle, C.byref(p)); k = L.b200c_poll_inputs(ctx.handle, pos, 64)
+                seen.append((p.bytes_scanned, p.bytes_total, p.stage, tuple(pos[i] for i in range(k))))
+                time.sleep(0.001)
+        th = threading.Thread(target=poller); th.start()
+        task.execute(GpuEngine(ctx)); done.set(); th.join()
+    finally:
+        del os.environ["B200C_RANGES"]
+    total = sum(t.compression.data_length for t in tabs)
+    run = [s for s in seen if s[1] == total]
+    assert len(run) >= 3
+    assert all(a[0] <= b[0] for a, b in zip(run, run[1:]))
+    assert len({s[2] for s in run}) >= 2                       # saw more than one stage
+    pos = (C.c_uint64 * 64)(); k = L.b200c_poll_inputs(ctx.handle, pos, 64)
+    assert k == len(tabs) and [pos[i] for i in range(k)] == [t.compression.data_length for t in tabs]
+    mids = [s[3] for s in run if len(s[3]) == len(tabs) and any(0 < v < t.compression.data_length for v, t in zip(s[3], tabs))]
+    assert mids, "never observed an input mid-file"
+    for a, b in zip(mids, mids[1:]): assert all(x <= y for x, y in zip(a, b))
+
+def test_more_than_32768_chunks_default_switches(ctx):
+    """the thread-per-chunk K1 (k_decompress_multi_thr) engages from 32768 chunks per launch: a byte-for-byte comparison at that
+    size with no environment override (6 x 96 MiB = 36864 chunks in the device-resident one-launch path, and the streamed host path)"""
+    import synth
+    tabs = synth_tables(0, 6, 0xCA55B16, synth.universe_for(0, 96 << 20, 0.5))
+    assert sum(len(t.compression.chunk_offsets) for t in tabs) >= 32768
+    got, want = both(ctx, tabs, CompactionController(NOW))

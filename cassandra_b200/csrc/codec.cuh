@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(32) k_compress_chunks(const DevTables* __restr
     int clen;
     if (comp == COMP_LZ4) {
         if (lane == 0) { slot[0] = (uint8_t)ulen; slot[1] = (uint8_t)(ulen >> 8); slot[2] = (uint8_t)(ulen >> 16); slot[3] = (uint8_t)(ulen >> 24); }
-        clen = 4 + lz4_compress_warp(s_in, ulen, s_tab, slot + 4, lane);
+        clen = 4 + lz4_compress_warp<false>(s_in, ulen, s_tab, slot + 4, lane);
     } else if (comp == COMP_SNAPPY) {
         clen = snappy_compress_warp(s_in, ulen, s_tab, slot, lane);
     } else {
@@ -69,6 +69,38 @@ __global__ void __launch_bounds__(32) k_compress_chunks(const DevTables* __restr
         slot[clen] = (uint8_t)(crc >> 24); slot[clen + 1] = (uint8_t)(crc >> 16); slot[clen + 2] = (uint8_t)(crc >> 8); slot[clen + 3] = (uint8_t)crc;
         file_len[chunk] = (uint32_t)clen + 4;
         // zero-init register of (chunk bytes || 4 CRC bytes): advance (raw ^ LE word of the CRC bytes) by 4 bytes
+        uint32_t x = raw ^ __byte_perm(crc, 0, 0x0123);
+        seg_raw[chunk] = T->crc_t[3][x & 0xff] ^ T->crc_t[2][(x >> 8) & 0xff] ^ T->crc_t[1][(x >> 16) & 0xff] ^ T->crc_t[0][x >> 24];
+    }
+}
+
+// LZ4 with only the 16 KiB hash table in shared memory: the chunk is read where it lies (L1 read-only path), 13 blocks of one warp per
+// SM instead of 7. Needs a 4-byte aligned stream start and chunk length (every caller's buffers are).
+__global__ void __launch_bounds__(32) k_compress_chunks_lz4_direct(const DevTables* __restrict__ T,
+        const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen,
+        uint8_t* __restrict__ slots, int slot_stride, uint32_t* __restrict__ file_len, uint32_t* __restrict__ seg_raw) {
+    __shared__ __align__(16) uint16_t s_tab[LZ4_TABLE_ENTRIES];
+    const int lane = threadIdx.x;
+    const uint64_t chunk = blockIdx.x;
+    const uint64_t start = chunk * (uint64_t)chunk_len;
+    const int ulen = (int)min((uint64_t)chunk_len, n - start);
+    const uint8_t* src = in + start;
+    uint8_t* slot = slots + chunk * (uint64_t)slot_stride;
+    if (lane == 0) { slot[0] = (uint8_t)ulen; slot[1] = (uint8_t)(ulen >> 8); slot[2] = (uint8_t)(ulen >> 16); slot[3] = (uint8_t)(ulen >> 24); }
+    int clen = 4 + lz4_compress_warp<true>(src, ulen, s_tab, slot + 4, lane);
+    if (clen >= max_clen) {                            // flushData :158-177 — store raw when compression did not help enough
+        for (int i = lane; i < ulen; i += 32) slot[i] = src[i];
+        clen = ulen;
+        if (ulen < max_clen) { for (int i = ulen + lane; i < max_clen; i += 32) slot[i] = 0; clen = max_clen; }
+    }
+    __syncwarp();
+    __threadfence_block();
+    uint32_t raw = warp_crc32_raw(T, T->crc_adv128, slot, clen, lane);
+    uint32_t init = gf2_mulmod(0xFFFFFFFFu, warp_xpow8n(T, (uint32_t)clen, lane));
+    uint32_t crc = ~(raw ^ init);
+    if (lane == 0) {
+        slot[clen] = (uint8_t)(crc >> 24); slot[clen + 1] = (uint8_t)(crc >> 16); slot[clen + 2] = (uint8_t)(crc >> 8); slot[clen + 3] = (uint8_t)crc;
+        file_len[chunk] = (uint32_t)clen + 4;
         uint32_t x = raw ^ __byte_perm(crc, 0, 0x0123);
         seg_raw[chunk] = T->crc_t[3][x & 0xff] ^ T->crc_t[2][(x >> 8) & 0xff] ^ T->crc_t[1][(x >> 16) & 0xff] ^ T->crc_t[0][x >> 24];
     }

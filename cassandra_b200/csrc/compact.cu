@@ -45,9 +45,10 @@ enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pi
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG, WS_INSZ, WS_BIG, WS_INPOS, WS_TMARK, WS_TSCAN, WS_TSTART,
        WS_SCANA = 60, WS_CODEC = 70 };
 
+static_assert(WS_ERR2 < WS_SCANA && WS_SCANA + 6 <= WS_CODEC && WS_CODEC + 12 <= WS_LCS0 && WS_TSTART < WS_SLOTS, "workspace slot map");
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
 
 __device__ __forceinline__ void report_err(DevErr* e, int kind, int input, uint64_t off) {
@@ -259,7 +260,8 @@ __global__ void __launch_bounds__(256) k_index_emit(const CParams* __restrict__ 
 
 // per input: sentinel position, token-range bounds [plo, phi) (inputs are token sorted), and a sortedness check
 __global__ void k_input_ranges(const CParams* __restrict__ Pp, const uint64_t* __restrict__ pbase, const uint64_t* __restrict__ pcount,
-                               const int64_t* __restrict__ tok, uint64_t* __restrict__ upos, int64_t tlo, int64_t thi, uint64_t* __restrict__ range /*[2*K]*/) {
+                               const int64_t* __restrict__ tok, uint64_t* __restrict__ upos, int64_t tlo, int64_t thi, uint64_t* __restrict__ range /*[2*K]*/,
+                               unsigned long long* __restrict__ range_bytes /* optional: += uncompressed bytes of the partitions in range */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const CParams& P = *Pp;
     if (i >= P.ninputs) return;
@@ -269,6 +271,7 @@ __global__ void k_input_ranges(const CParams* __restrict__ Pp, const uint64_t* _
     if (tlo != I64_MIN) { uint64_t a = 0, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= tlo) a = m + 1; else b = m; } lo = a; }   // first > tlo
     { uint64_t a = lo, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= thi) a = m + 1; else b = m; } hi = a; }                     // first > thi
     range[2 * i] = lo; range[2 * i + 1] = hi;
+    if (range_bytes && hi > lo) atomicAdd(range_bytes, (unsigned long long)(upos[pbase[i] + hi] - upos[pbase[i] + lo]));
 }
 
 // an SSTable is ordered by (token, key) and its partitions do not overlap: tokens must not decrease, equal tokens must come with
@@ -489,12 +492,14 @@ struct K4Args {
     // mode 1: promoted-index slots (IXS_* layout in partition.cuh) of the partitions that can exceed one column-index block
     const uint64_t* ioff; const uint32_t* icapv; uint8_t* iscr;
     int m3_nblk;                     // mode 3 also re-emits partitions with a promoted index (two-pass A/B mode: there are no slots)
+    const uint8_t* only_big;         // mode 1: when set, only partitions flagged here (the staged kernel took the others)
 };
 
 template <bool EMIT> __device__ __forceinline__ bool k4_prologue(const K4Args& a, uint64_t j, uint8_t*& dout, uint64_t& dcap, uint64_t& dposv, uint8_t*& iout, uint32_t& nbf, uint32_t& ipf, uint32_t& ixs_cap) {
     dout = nullptr; dcap = ~0ull; dposv = 0; iout = nullptr; nbf = 0; ipf = 0; ixs_cap = 0;
     if (!EMIT) return true;
     if (a.mode == 1) {
+        if (a.only_big && !a.only_big[j]) return false;
         dout = a.dbase + a.doff[j]; dcap = a.dcapv[j];
         uint32_t slot = a.icapv[j];
         if (slot) { iout = a.iscr + a.ioff[j]; nbf = (slot - IXS_HEAD) / IXS_BLOCK_STRIDE; ixs_cap = nbf * IXS_PER_BLOCK; }
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
     if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
-    else process_partition<EMIT>(*a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e);
+    else process_partition<EMIT>(*a.P, XlateGlobal(), a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e);
     k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
@@ -553,18 +558,114 @@ __global__ void __launch_bounds__(128) k_partition_warp(const K4Args a, uint64_t
     if (tile.thread_rank() == 0) k4_epilogue<EMIT>(a, j, c0, out, st, e);
 }
 
+// ---- K4, staged mapping (the default for partitions of up to ST_MAXP input bytes and fan-in <= ST_MAXM) ------------------------------
+// The thread-per-partition kernels above parse Data.db straight from global memory: every field is a dependent load of a 32-byte
+// sector from L2 or HBM. Here a block owns a TILE = a token-contiguous run of output partitions. Because every input is sorted by
+// token, the input partitions of a tile are ONE contiguous byte range per source; those <= K ranges are copied into shared memory
+// by the TMA unit (cp.async.bulk + an mbarrier counting the bytes), each byte crossing L2 -> SM exactly once in full 16-byte
+// words, and the threads then run the same process_partition() on the copy: P.U points at the tile, cursors shrink to 32 bytes
+// (32-bit positions, 16-bit header offsets). Tiles are cut where the running input bytes pass a multiple of ST_BYTES, the running
+// contributor count a multiple of ST_CM, or the partition count a multiple of ST_MAXPART, so that the tile, its cursors and the
+// per-thread merged rows fit ~70 KB and three blocks share an SM.
+enum { ST_THREADS = 64, ST_MAXPART = 128, ST_BYTES = 32768, ST_MAXP = 8192, ST_CM = 448, ST_MAXM = 16,
+       ST_STAGE_CAP = ST_BYTES + ST_MAXP + 32 * MAXK + 64, ST_CUR_CAP = ST_CM + ST_MAXM + 48,
+       ST_HEAD = (16 + ((sizeof(CParams) + 15) & ~15) + MAXK * 8 * 3 + MAXK * 4 * 2 + 127) & ~127 };
+static_assert(ST_STAGE_CAP < 65536 - 64, "staged tiles are addressed with 16-bit header offsets");
+
+__global__ void __launch_bounds__(256) k_tile_marks(uint64_t nparts, const uint64_t* __restrict__ inpos, const uint64_t* __restrict__ op_first,
+                                                    const uint8_t* __restrict__ big, uint32_t* __restrict__ mark, unsigned long long* __restrict__ nbig) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nparts) return;
+    bool m = j == 0 || (j % ST_MAXPART) == 0 || big[j];
+    if (!m) m = big[j - 1] || inpos[j] / ST_BYTES != inpos[j - 1] / ST_BYTES || op_first[j] / ST_CM != op_first[j - 1] / ST_CM;
+    mark[j] = m ? 1u : 0u;
+    if (big[j]) atomicAdd(nbig, 1ull);
+}
+__global__ void __launch_bounds__(256) k_tile_starts(uint64_t nparts, const uint32_t* __restrict__ mark, const uint64_t* __restrict__ tscan, uint32_t* __restrict__ tile_start) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nparts && mark[j]) tile_start[tscan[j]] = (uint32_t)j;
+    if (j == nparts) tile_start[tscan[nparts]] = (uint32_t)nparts;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(ST_THREADS) k_partition_staged(const K4Args a, const uint32_t* __restrict__ tile_start, const uint8_t* __restrict__ big) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* s_bar = (uint64_t*)smem;
+    CParams* sP = (CParams*)(smem + 16);
+    unsigned long long* s_lo = (unsigned long long*)(smem + 16 + ((sizeof(CParams) + 15) & ~15));
+    unsigned long long* s_hi = s_lo + MAXK;
+    uint64_t* s_g0 = (uint64_t*)(s_hi + MAXK);
+    uint32_t* s_sbase = (uint32_t*)(s_g0 + MAXK);
+    uint32_t* s_len = s_sbase + MAXK;
+    uint8_t* stage = smem + ST_HEAD;
+    CurS* curs = (CurS*)(stage + ST_STAGE_CAP);
+    MCell* cells = (MCell*)(curs + ST_CUR_CAP);
+    const int tid = threadIdx.x;
+    const uint32_t j0 = tile_start[blockIdx.x], j1 = tile_start[blockIdx.x + 1];
+    if (j0 >= j1 || big[j0]) return;                                  // a big partition is a tile of its own: the global-memory kernels take it
+    const CParams& GP = *a.P;
+    const int K = GP.ninputs;
+    {   // header of the parameters -> shared memory, with U redirected to the tile
+        const uint32_t* g = (const uint32_t*)a.P; uint32_t* d = (uint32_t*)sP;
+        for (int i = tid; i < (int)(sizeof(CParams) / 4); i += ST_THREADS) d[i] = g[i];
+        for (int i = tid; i < MAXK; i += ST_THREADS) { s_lo[i] = ~0ull; s_hi[i] = 0; s_len[i] = 0; }
+        if (tid == 0) mbar_init(s_bar, 1);
+    }
+    __syncthreads();
+    if (tid == 0) sP->U = stage;
+    const uint64_t c0 = a.op_first[j0], c1 = a.op_first[j1];
+    for (uint64_t c = c0 + tid; c < c1; c += ST_THREADS) {            // first and last partition of every source in this tile
+        const uint64_t e = a.contrib[c]; const int src = (int)((e >> 56) & 0x7F); const unsigned long long idx = e & 0xFFFFFFFFFFull;
+        atomicMin(&s_lo[src], idx); atomicMax(&s_hi[src], idx);
+    }
+    __syncthreads();
+    if (tid < K && s_lo[tid] != ~0ull) {
+        const uint64_t b0 = a.upos[a.pbase[tid] + s_lo[tid]] & ~15ull, b1 = (a.upos[a.pbase[tid] + s_hi[tid] + 1] + 15) & ~15ull;
+        s_g0[tid] = b0; s_len[tid] = (uint32_t)min(b1 - b0, (uint64_t)0x7FFFFFF0u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int i = 0; i < K; i++) { s_sbase[i] = tot; tot += s_len[i]; if (tot > (uint32_t)ST_STAGE_CAP) break; }
+        if (tot > (uint32_t)ST_STAGE_CAP - 64) { s_len[0] = 0xFFFFFFFFu; report_err(a.err, 8, 0, j0); }      // cannot happen: the tile plan bounds it
+        else {
+            mbar_arrive_expect_tx(s_bar, tot);
+            for (int i = 0; i < K; i++) if (s_len[i]) bulk_copy_g2s(stage + s_sbase[i], GP.U + s_g0[i], s_len[i], s_bar);
+        }
+    }
+    __syncthreads();
+    if (s_len[0] == 0xFFFFFFFFu) return;
+    mbar_wait(s_bar, 0);
+    const XlateStaged xl{s_sbase, s_g0};
+    const int ncols_s = WIDE ? 0 : sP->ncols;
+    MCell merged_local[WIDE ? MAXCOLS : 1];
+    MCell* merged = WIDE ? merged_local : cells + (size_t)tid * ncols_s;
+    DT open_dt[ST_MAXM];
+    for (uint32_t j = j0 + tid; j < j1; j += ST_THREADS) {
+        uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf, ixs_cap;
+        if (!k4_prologue<true>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) continue;
+        const uint64_t cj = a.op_first[j]; const uint32_t m = (uint32_t)(a.op_first[j + 1] - cj);
+        PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+        if (m > (uint32_t)ST_MAXM || cj - c0 + m > (uint64_t)ST_CUR_CAP) e = PERR_UNSUPPORTED;
+        else process_partition<true>(*sP, xl, a.contrib, cj, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, curs + (cj - c0), open_dt, merged, out, st, e);
+        k4_epilogue<true>(a, j, cj, out, st, e);
+    }
+}
+
 // upper bound of an output partition's size: the sum of its input partitions plus 25 % + 32 bytes (re-based deltas can lengthen
 // vints by a byte or two per field; a partition that still does not fit is caught by the overflow flag and re-emitted by mode 3)
 // icap[j]: bytes of promoted-index slot (0 when the partition cannot reach a second column-index block)
 __global__ void __launch_bounds__(256) k_bounds(const uint64_t* __restrict__ contrib, const uint64_t* __restrict__ op_first, uint64_t nparts,
                                                 const uint64_t* __restrict__ upos, const uint64_t* __restrict__ pbase, uint64_t* __restrict__ bound,
-                                                uint32_t column_index_size, uint32_t* __restrict__ icap) {
+                                                uint32_t column_index_size, uint32_t* __restrict__ icap, uint32_t* __restrict__ insz, uint8_t* __restrict__ big) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nparts) return;
     uint64_t sum = 0;
     for (uint64_t c = op_first[j]; c < op_first[j + 1]; c++) { uint64_t e = contrib[c]; uint64_t g = pbase[(e >> 56) & 0x7F] + (e & 0xFFFFFFFFFFull); sum += upos[g + 1] - upos[g]; }
     uint64_t b = (sum + (sum >> 2) + 32 + 15) & ~15ull;
     bound[j] = b;
+    insz[j] = (uint32_t)min(sum, (uint64_t)0xFFFFFFFFull);
+    big[j] = (sum > (uint64_t)ST_MAXP || op_first[j + 1] - op_first[j] > (uint64_t)ST_MAXM) ? 1 : 0;      // not for the staged kernel
     uint64_t nb_max = b / column_index_size + 2;          // a block closes once it holds >= column_index_size bytes
     icap[j] = (b > column_index_size && nb_max < (1u << 23)) ? (uint32_t)(IXS_HEAD + nb_max * IXS_BLOCK_STRIDE) : 0u;
 }
@@ -688,6 +789,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // ---- layout of the concatenated device buffers -------------------------------------------------------------------------------
     std::vector<uint64_t> ubase(K + 1), ibase(K + 1), cbase(K + 1), obase(K + 1), bbase(K + 1);
     CParams hp; memset(&hp, 0, sizeof(hp));
+    std::vector<InDesc> hin(K); memset(hin.data(), 0, sizeof(InDesc) * K);
     uint64_t uo = 0, io = 0, co = 0, oo = 0, bo = 0;
     for (int i = 0; i < K; i++) {
         const b200c_input& in = m->inputs[i];
@@ -700,7 +802,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         cbase[i] = co; co += (in.data_len + 64 + 255) & ~255ull;
         obase[i] = oo; oo += in.nchunks + 1;
         bbase[i] = bo; bo += (in.index_len + IB - 1) / IB;
-        InDesc& d = hp.in[i];
+        InDesc& d = hin[i];
         d.ubase = ubase[i]; d.ulen = in.data_length; d.ibase = ibase[i]; d.ilen = in.index_len;
         d.min_ts = in.header_stats.min_timestamp; d.min_ldt = in.header_stats.min_local_deletion_time; d.min_ttl = in.header_stats.min_ttl;
         d.ncols = in.ncolumns;
@@ -749,7 +851,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     std::vector<uint64_t> sbase(K + 1, 0);
     for (int i = 0; i < K; i++) sbase[i + 1] = sbase[i] + (have_summaries ? m->inputs[i].nsummary : 0);
     uint64_t* d_summ; B200C_TRY(ws_typed(c, WS_SUMM, sbase[K] + 1, &d_summ));
-    B200C_TRY(ws_typed(c, WS_PARAMS, 1, &dP));
+    { uint8_t* pp; B200C_TRY(ws_typed(c, WS_PARAMS, sizeof(CParams) + sizeof(InDesc) * (size_t)K, &pp)); dP = (CParams*)pp; hp.in = (const InDesc*)(pp + sizeof(CParams)); }
     B200C_TRY(ws_typed(c, WS_BBASE, (size_t)K + 1, &d_bbase));
     { uint8_t* p; B200C_TRY(ws_typed(c, WS_ERR2, 4096, &p)); d_err = (DevErr*)p; d_cerr = (ChunkErr*)(p + 64); d_stats = (RunStats*)(p + 128); d_hist = (unsigned long long*)(p + 256); }
     hp.U = U;
@@ -763,6 +865,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_err, 0xFF, 64, st));
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_cerr, 0xFF, 64, st));
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_stats, 0, 128 + MAXK * 8 + 128, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync((void*)hp.in, hin.data(), sizeof(InDesc) * (size_t)K, cudaMemcpyHostToDevice, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(dP, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(d_bbase, bbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
     cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -930,8 +1033,10 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
                               d_tok, d_kp, d_klen, d_upos, d_err);
     if (total_parts > (uint64_t)K) B200C_LAUNCH(c, k_check_order, 1184, 256, 0, dP, d_pbase, d_pcount, d_tok, d_kp, d_klen, d_upos, d_err);
-    B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range);
+    unsigned long long* d_rbytes = (unsigned long long*)(d_stats + 1) + 1;      // (zeroed with the stats block)
+    B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range, d_rbytes);
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
+    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 201, d_rbytes, 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
     B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
     auto index_data_mismatch = [&](uint64_t word) -> int {
@@ -942,6 +1047,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     };
     if (h[200] != ~0ull) return index_data_mismatch(h[200]);
     for (int i = 0; i < K; i++) if (h[2 * i] > h[2 * i + 1] || h[2 * i + 1] > pcount[i]) return index_data_mismatch((uint64_t)i << 48);
+    const uint64_t bytes_in_range = h[201];
 
     // ---- token ranges --------------------------------------------------------------------------------------------------------------
     // T[0] < T[1] < ... < T[nr]: piece r merges the partitions with token in (T[r], T[r+1]] (T[0] = I64_MIN: from the first one)
@@ -1029,7 +1135,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         // ---- K3: partition merge -------------------------------------------------------------------------------------------------------
         mark(2);
         c->prog_stage.store(3);
-        B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, T[r], T[r + 1], d_range);
+        B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, T[r], T[r + 1], d_range, (unsigned long long*)nullptr);
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_cerr, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
@@ -1057,6 +1163,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         nparts_total += nparts;
         B200C_TRY(ws_typed(c, WS_OPFIRST, nparts + 2, &d_opfirst));
         uint32_t* d_list; unsigned long long* d_cursor = nullptr; uint64_t *d_bound = nullptr, *d_bpos = nullptr;
+        uint32_t* d_insz = nullptr; uint8_t* d_big = nullptr;
         B200C_TRY(ws_typed(c, WS_LIST, nparts + 1, &d_list));
         B200C_TRY(ws_typed(c, WS_BOUND, nparts + 1, &d_bound));
         B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
@@ -1066,8 +1173,10 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (ncontrib) {
             B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
             // counting sort of the output partitions by (fan-in, size bucket)
+            B200C_TRY(ws_typed(c, WS_INSZ, nparts + 1, &d_insz));
+            B200C_TRY(ws_typed(c, WS_BIG, nparts + 2, &d_big));
             B200C_LAUNCH(c, k_bounds, (unsigned)((nparts + 255) / 256), 256, 0, d_contrib, d_opfirst, nparts, d_upos, d_pbase, d_bound,
-                         (uint32_t)std::min<uint64_t>(std::max<int64_t>(1, m->column_index_size), 0x7fffffff), d_icap);
+                         (uint32_t)std::min<uint64_t>(std::max<int64_t>(1, m->column_index_size), 0x7fffffff), d_icap, d_insz, d_big);
             // tile = token-contiguous run of output partitions whose inputs total ~32 MiB
             uint64_t per_part = std::max<uint64_t>(1, range_bytes[r] / std::max<uint64_t>(1, nparts));
             uint32_t tile_shift = 12; while (tile_shift < 24 && ((1ull << (tile_shift + 1)) * per_part) <= (32ull << 20)) tile_shift++;
@@ -1151,7 +1260,35 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
                 B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
                 ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
-                B200C_TRY(launch_k4(1));
+                static const bool staged = []() { const char* e = getenv("B200C_K4_STAGED"); return !e || atoi(e) != 0; }();      // A/B switch
+                if (staged) {
+                    // tile plan: exclusive scan of the input bytes, cut marks, scan of the marks, tile starts
+                    uint64_t *d_inpos, *d_tscan; uint32_t *d_mark, *d_tstart; unsigned long long* d_nbig = (unsigned long long*)(d_stats + 1);
+                    B200C_TRY(ws_typed(c, WS_INPOS, nparts + 2, &d_inpos));
+                    B200C_TRY(ws_typed(c, WS_TMARK, nparts + 2, &d_mark));
+                    B200C_TRY(ws_typed(c, WS_TSCAN, nparts + 2, &d_tscan));
+                    B200C_TRY(ws_typed(c, WS_TSTART, nparts + 2, &d_tstart));
+                    B200C_TRY(exclusive_scan<uint32_t>(c, d_insz, nparts, d_inpos, WS_SCANA, 0));
+                    B200C_CUDA_TRY(c, cudaMemsetAsync(d_nbig, 0, 8, st));
+                    B200C_LAUNCH(c, k_tile_marks, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_inpos, d_opfirst, d_big, d_mark, d_nbig);
+                    B200C_TRY(exclusive_scan<uint32_t>(c, d_mark, nparts, d_tscan, WS_SCANA, 0));
+                    B200C_LAUNCH(c, k_tile_starts, (unsigned)((nparts + 1 + 255) / 256), 256, 0, nparts, d_mark, d_tscan, d_tstart);
+                    B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_tscan + nparts, 8, cudaMemcpyDeviceToHost, st));
+                    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_nbig, 8, cudaMemcpyDeviceToHost, st));
+                    B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                    const uint64_t ntiles = h[0], nbig = h[1];
+                    const bool wide = m->ncolumns > K4_SMEM_COLS;
+                    const size_t smem_st = (size_t)ST_HEAD + ST_STAGE_CAP + (size_t)ST_CUR_CAP * sizeof(CurS) + (wide ? 0 : (size_t)ST_THREADS * m->ncolumns * sizeof(MCell)) + 16;
+                    if (c->k4s_attr_set != (int)smem_st) {
+                        cudaFuncSetAttribute(k_partition_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);
+                        cudaFuncSetAttribute(k_partition_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);
+                        c->k4s_attr_set = (int)smem_st;
+                    }
+                    ka.mode = 1; ka.only_big = nullptr;
+                    if (wide) B200C_LAUNCH(c, k_partition_staged<true>, (unsigned)ntiles, ST_THREADS, smem_st, ka, d_tstart, d_big);
+                    else B200C_LAUNCH(c, k_partition_staged<false>, (unsigned)ntiles, ST_THREADS, smem_st, ka, d_tstart, d_big);
+                    if (nbig) { ka.only_big = d_big; B200C_TRY(launch_k4(1)); ka.only_big = nullptr; }
+                } else B200C_TRY(launch_k4(1));
             }
             B200C_LAUNCH(c, k_sum_stats, 1184, 256, 0, nparts, d_dsize, d_stmunf, d_strows, d_stats);
             B200C_TRY(exclusive_scan<uint64_t>(c, d_dsize, nparts, d_dpos, WS_SCANA, 0));
@@ -1231,7 +1368,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         memcpy(&rs, h + 8, sizeof(rs));
         memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
         for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
-        res->bytes_read = bytes_read; res->bytes_written = ubase_total; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib_total;
+        res->bytes_read = bytes_read; res->bytes_in_range = bytes_in_range; res->bytes_written = ubase_total; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib_total;
         res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
         return B200C_OK;
     };

@@ -34,9 +34,20 @@ __device__ __forceinline__ int lz4_emit_len_ext(uint8_t* out, int rem, int lane)
     return nff + 1;
 }
 
-// s_in: chunk bytes in shared memory (4-byte aligned, >= n + 8 bytes, tail zeroed); s_tab: 8192 x u16 (zeroed here);
+// s_in: chunk bytes (4-byte aligned, >= n + 8 readable bytes); s_tab: 8192 x u16 in shared memory (zeroed here);
 // out: destination (global), capacity >= lz4_compress_bound(n). Returns the compressed size (warp-uniform).
-__device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, uint8_t* out, int lane) {
+// GLOBAL = false: s_in is a shared-memory copy of the chunk. GLOBAL = true: s_in is the chunk where it lies in global memory, read
+// through the read-only L1 path (ld.global.nc): only the hash table occupies shared memory then, which doubles the chunks an SM holds
+// — and this kernel is a chain of dependent instructions per chunk, so chunks in flight are what buys throughput. No byte beyond
+// position n - 1 influences the result (searches stop at n - 12, matches at n - 5), so what follows the chunk in memory is irrelevant.
+template <bool GLOBAL> __device__ __forceinline__ uint32_t lz4_rd32(const uint32_t* in32, int p) {
+    if (!GLOBAL) return rd32_at(in32, p);
+    uint32_t lo = __ldg(in32 + (p >> 2)), hi = __ldg(in32 + (p >> 2) + 1);
+    return __funnelshift_r(lo, hi, (p & 3) * 8);
+}
+template <bool GLOBAL> __device__ __forceinline__ uint32_t lz4_rd8(const uint8_t* in, int p) { return GLOBAL ? (uint32_t)__ldg(in + p) : (uint32_t)in[p]; }
+
+template <bool GLOBAL> __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, uint8_t* out, int lane) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     {   // zero the hash table: 16 KiB, 16 bytes per lane per step
         uint4* t4 = (uint4*)s_tab;
@@ -69,7 +80,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                     int pn = fwd + lz4_attempt_offset(a + 1);
                     valid = pn <= mfl1;
                 }
-                uint32_t seq = valid ? rd32_at(in32, p) : 0u;
+                uint32_t seq = valid ? lz4_rd32<GLOBAL>(in32, p) : 0u;
                 uint32_t h = lz4_hash_u16(seq);
                 int cand = valid ? (int)s_tab[h] : 0;
                 // lanes with the same hash. match.any costs several hundred cycles here (one pass per distinct value); 13 ballots, one
@@ -82,7 +93,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                 int src = prev ? (31 - __clz(prev)) : lane;
                 int pc = __shfl_sync(FULL_MASK, p, src);
                 if (prev) cand = pc;
-                bool hit = valid && !putonly && (rd32_at(in32, cand) == seq);
+                bool hit = valid && !putonly && (lz4_rd32<GLOBAL>(in32, cand) == seq);
                 uint32_t hits = __ballot_sync(FULL_MASK, hit);
                 uint32_t inval = __ballot_sync(FULL_MASK, !valid);
                 int first_hit = hits ? (__ffs(hits) - 1) : 32;
@@ -112,7 +123,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                 // ---- catch up: extend the match backwards -----------------------------------------------------------
                 for (;;) {
                     int j = lane + 1;
-                    bool ok = (ip - j >= anchor) && (match - j >= 0) && (s_in[ip - j] == s_in[match - j]);
+                    bool ok = (ip - j >= anchor) && (match - j >= 0) && (lz4_rd8<GLOBAL>(s_in, ip - j) == lz4_rd8<GLOBAL>(s_in, match - j));
                     uint32_t b = __ballot_sync(FULL_MASK, ok);
                     int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
                     ip -= steps; match -= steps;
@@ -122,7 +133,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                 int lit = ip - anchor;
                 token_pos = op++;
                 if (lit >= 15) op += lz4_emit_len_ext(out + op, lit - 15, lane);
-                for (int i = lane; i < lit; i += 32) out[op + i] = s_in[anchor + i];
+                for (int i = lane; i < lit; i += 32) out[op + i] = (uint8_t)lz4_rd8<GLOBAL>(s_in, anchor + i);
                 op += lit;
                 lit_nibble = lit < 15 ? lit : 15;
             } else token_pos = op++;                      // immediate match: token with literal length 0
@@ -135,7 +146,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
                 int pi = ip + LZ4_MINMATCH, pm = match + LZ4_MINMATCH;
                 for (;;) {
                     int i = mc + lane;
-                    bool eq = (pi + i < matchlimit) && (s_in[pi + i] == s_in[pm + i]);
+                    bool eq = (pi + i < matchlimit) && (lz4_rd8<GLOBAL>(s_in, pi + i) == lz4_rd8<GLOBAL>(s_in, pm + i));
                     uint32_t b = __ballot_sync(FULL_MASK, eq);
                     if (b == FULL_MASK) { mc += 32; continue; }
                     mc += __ffs(~b) - 1;
@@ -156,7 +167,7 @@ __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, ui
         if (lane == 0) out[op] = (uint8_t)((last < 15 ? last : 15) << 4);
         op++;
         if (last >= 15) op += lz4_emit_len_ext(out + op, last - 15, lane);
-        for (int i = lane; i < last; i += 32) out[op + i] = s_in[anchor + i];
+        for (int i = lane; i < last; i += 32) out[op + i] = (uint8_t)lz4_rd8<GLOBAL>(s_in, anchor + i);
         op += last;
     }
     return op;

@@ -42,7 +42,7 @@ struct CParams {
     int64_t now, gc_before, purge_max_ts;
     // optional purge table (b200c_manifest.purge_range_*): ascending token bounds and the threshold that applies up to each of them
     const int64_t* purge_hi; const int64_t* purge_ts; int64_t npurge;
-    InDesc in[MAXK];
+    const InDesc* in;              // ninputs descriptors (device memory; the header above is small enough to be copied into shared memory)
 };
 
 struct DT { int64_t mfda, ldt; };
@@ -140,17 +140,24 @@ template <bool EMIT> struct Sink {
 
 struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialised clustering values (header vint + values) in U
 
-struct Cur {                       // cursor of one contributing input partition (48 bytes: it lives in shared memory)
-    uint64_t pos, next, end;       // current unfiltered, the one after it, end of the partition
+// cursor of one contributing input partition; it lives in shared memory, so its size decides how many partitions an SM can hold.
+// OFF: type of the stream positions (offsets from P.U), REL: type of the offsets inside one unfiltered header.
+//   Cur   = CurT<uint64_t, uint32_t> (48 bytes): P.U is the whole decompressed input in global memory
+//   CurS  = CurT<uint32_t, uint16_t> (32 bytes): P.U is a tile of < 64 KiB staged in shared memory (k_partition_staged)
+template <typename OFF, typename REL> struct CurT {
     uint64_t k0;                   // order-preserving 64-bit prefix of the first clustering component (see cur_load)
-    uint32_t ckend_rel, body_rel;  // offsets from pos: end of the clustering values, start of the body
+    OFF pos, next, end;            // current unfiltered, the one after it, end of the partition
+    REL ckend_rel, body_rel;       // offsets from pos: end of the clustering values, start of the body
     uint8_t ck_rel;                // offset from pos of the clustering values (1..4)
     uint8_t flags, ext, kind, n, src; bool done;
     uint8_t fast;                  // 0: no prefix key; 1: k0 orders unequal prefixes, ties need cmp_clust; 2: k0 is the whole clustering
+    typedef REL rel_t;
 };
+typedef CurT<uint64_t, uint32_t> Cur;
+typedef CurT<uint32_t, uint16_t> CurS;
 
 // parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
-__device__ __noinline__ int cur_load_impl(const CParams& P, Cur& c) {
+template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P, CUR& c) {
     int err = 0;
     for (;;) {
         Rd r{P.U, c.pos, c.end, 0};
@@ -186,13 +193,14 @@ __device__ __noinline__ int cur_load_impl(const CParams& P, Cur& c) {
                 r.skip(len);
             }
         }
-        c.ckend_rel = (uint32_t)(r.p - c.pos);
+        c.ckend_rel = (typename CUR::rel_t)(r.p - c.pos);
         uint64_t sz = r.vint();
         uint64_t after = r.p;
         r.vint();                                   // previous unfiltered size
-        c.body_rel = (uint32_t)(r.p - c.pos);
-        c.next = after + sz;
-        if (r.err || c.next > c.end || c.next < r.p) { c.done = true; return PERR_CORRUPT; }
+        c.body_rel = (typename CUR::rel_t)(r.p - c.pos);
+        const uint64_t nx = after + sz;                  // (64-bit: a damaged size must not wrap a narrow cursor)
+        if (r.err || nx > c.end || nx < r.p || r.p - c.pos > (uint64_t)(typename CUR::rel_t)~0ull) { c.done = true; return PERR_CORRUPT; }
+        c.next = (decltype(c.next))nx;
         if (!(flags & 0x02) && !(flags & 0x14)) {   // maybe an empty row: no liveness, no deletion — any cells?
             int ncin = P.in[c.src].ncols; bool any;
             if (flags & 0x20) any = ncin > 0;
@@ -202,7 +210,7 @@ __device__ __noinline__ int cur_load_impl(const CParams& P, Cur& c) {
         return err;
     }
 }
-__device__ __forceinline__ void cur_load(const CParams& P, Cur& c, int& err) { int e = cur_load_impl(P, c); if (e) err = e; }
+template <class CUR> __device__ __forceinline__ void cur_load(const CParams& P, CUR& c, int& err) { int e = cur_load_impl(P, c); if (e) err = e; }
 
 __device__ __forceinline__ int cmp_bytes(const uint8_t* a, int la, const uint8_t* b, int lb) {
     int n = la < lb ? la : lb;
@@ -225,7 +233,7 @@ __device__ __forceinline__ int cmp_value(int type, const uint8_t* a, int la, con
 }
 
 // ClusteringComparator.compare: S/db/ClusteringComparator.java:140-157
-__device__ __noinline__ int cmp_clust(const CParams& P, const Cur& a, const Cur& b) {
+template <class CUR> __device__ __noinline__ int cmp_clust(const CParams& P, const CUR& a, const CUR& b) {
     const uint8_t* pa = P.U + a.pos + a.ck_rel; const uint8_t* pb = P.U + b.pos + b.ck_rel;
     const uint8_t* ea = P.U + a.pos + a.ckend_rel; const uint8_t* eb = P.U + b.pos + b.ckend_rel;
     int m = a.n < b.n ? a.n : b.n;
@@ -247,7 +255,7 @@ __device__ __noinline__ int cmp_clust(const CParams& P, const Cur& a, const Cur&
 }
 
 // cmp_clust with the cached prefix keys in front: unequal prefixes decide, equal "whole" keys only need the kind comparison
-__device__ __forceinline__ int cmp_heads(const CParams& P, const Cur& a, const Cur& b) {
+template <class CUR> __device__ __forceinline__ int cmp_heads(const CParams& P, const CUR& a, const CUR& b) {
     if (a.fast && b.fast) {
         if (a.k0 != b.k0) return a.k0 < b.k0 ? -1 : 1;
         if (a.fast == 2 && b.fast == 2) { int d = kind_comparison(a.kind) - kind_comparison(b.kind); return d < 0 ? -1 : (d > 0 ? 1 : 0); }
@@ -376,7 +384,7 @@ template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const
 struct PartStats { uint64_t merged_unfiltereds; uint64_t rows_out; };
 
 // decodes the row at cursor `c` : liveness + deletion; returns a reader positioned at the columns subset / cells
-__device__ __forceinline__ Rd row_header(const CParams& P, const Cur& c, Live& info, DT& del) {
+template <class CUR> __device__ __forceinline__ Rd row_header(const CParams& P, const CUR& c, Live& info, DT& del) {
     const InDesc& in = P.in[c.src];
     Rd r{P.U, c.pos + c.body_rel, c.next, 0};
     info = live_empty(); del = dt_live();
@@ -387,7 +395,7 @@ __device__ __forceinline__ Rd row_header(const CParams& P, const Cur& c, Live& i
 }
 
 // folds the cells of the row at cursor `c` into merged[] (ColumnDataReducer.getReduced :838-849)
-__device__ __noinline__ int fold_cells_impl(const CParams& P, const Cur& c, Rd r, Live info, bool apply_deletion, DT active, MCell* merged) {
+template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& P, const CUR& c, Rd r, Live info, bool apply_deletion, DT active, MCell* merged) {
     const InDesc& in = P.in[c.src];
     uint64_t missing = 0;
     if (!(c.flags & 0x20)) missing = r.vint();
@@ -414,7 +422,7 @@ __device__ __noinline__ int fold_cells_impl(const CParams& P, const Cur& c, Rd r
     }
     return r.err;
 }
-__device__ __forceinline__ void fold_cells(const CParams& P, const Cur& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
+template <class CUR> __device__ __forceinline__ void fold_cells(const CParams& P, const CUR& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
     int e = fold_cells_impl(P, c, r, info, apply_deletion, active, merged); if (e) err = e;
 }
 
@@ -485,7 +493,7 @@ __device__ __forceinline__ bool purge_marker(const Purger& pg, uint8_t& kind, DT
     return !pg.dt(kind_is_start(kind) ? m_open : m_close);
 }
 
-__device__ __forceinline__ void read_marker_dts(const CParams& P, const Cur& c, DT& m_close, DT& m_open, int& err) {
+template <class CUR> __device__ __forceinline__ void read_marker_dts(const CParams& P, const CUR& c, DT& m_close, DT& m_open, int& err) {
     const InDesc& in = P.in[c.src];
     Rd r{P.U, c.pos + c.body_rel, c.next, 0};
     m_close = dt_live(); m_open = dt_live();
@@ -514,12 +522,20 @@ struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; };
 // merged[0..ncols): scratch for the merged row.
 __device__ int64_t murmur3_token(const uint8_t* key, uint32_t len);     // compact.cu
 
-template <bool EMIT>
-__device__ void process_partition(const CParams& P, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
+// where an input partition's bytes are, as an offset from P.U: the decompressed stream itself (XlateGlobal), or a tile of it that
+// k_partition_staged copied into shared memory (XlateStaged: P.U then points at the tile)
+struct XlateGlobal { __device__ __forceinline__ uint64_t operator()(int, uint64_t u) const { return u; } };
+struct XlateStaged {
+    const uint32_t* sbase; const uint64_t* g0;       // per source: offset of its staged range in the tile, stream offset that range starts at
+    __device__ __forceinline__ uint64_t operator()(int src, uint64_t u) const { return sbase[src] + (u - g0[src]); }
+};
+
+template <bool EMIT, class CUR, class XL>
+__device__ void process_partition(const CParams& P, const XL& xl, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                   const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
                                   const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen, const int64_t* __restrict__ part_tok,
                                   uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
-                                  Cur* cur, DT* open_dt, MCell* merged,
+                                  CUR* cur, DT* open_dt, MCell* merged,
                                   PartOut& out, PartStats& st, int& err) {
     Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
     DT pdel = dt_live();
@@ -530,15 +546,14 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
     for (uint32_t v = 0; v < m; v++) {
         uint64_t e = contrib[c0 + v];
         int src = (int)((e >> 56) & 0x7F); uint64_t g = pbase[src] + (e & 0xFFFFFFFFFFull);
-        Cur& c = cur[v]; c.src = (uint8_t)src; c.pos = part_upos[g]; c.end = part_upos[g + 1]; c.done = false;
+        CUR& c = cur[v]; c.src = (uint8_t)src; c.pos = (decltype(c.pos))xl(src, part_upos[g]); c.end = (decltype(c.end))xl(src, part_upos[g + 1]); c.done = false;
         c.k0 = part_kp[g]; c.ckend_rel = part_klen[g];           // what Index.db said about this partition's key (checked below)
-        c.next = (uint64_t)part_tok[g];                          // (parked here until the header is parsed)
     }
 #ifdef __CUDA_ARCH__
-    for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
+    if (sizeof(cur[0].pos) == 8) for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
 #endif
     for (uint32_t v = 0; v < m; v++) {
-        Cur& c = cur[v];
+        CUR& c = cur[v];
         uint64_t pos = c.pos;
         Rd r{P.U, pos, c.end, 0};
         uint32_t kl = r.be16();
@@ -551,10 +566,13 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
         DT pd = read_partition_dt(r);
         if (r.err) { err = r.err; return; }
         // keys longer than the 8-byte prefix: the token K2 computed from the Index.db key must be the token of the Data.db key
-        if (kl > 8 && !P.partitioner && murmur3_token(P.U + pos + 2, kl) != (int64_t)c.next) { err = PERR_CORRUPT; return; }
+        if (kl > 8 && !P.partitioner) {
+            const uint64_t e = contrib[c0 + v];
+            if (murmur3_token(P.U + pos + 2, kl) != part_tok[pbase[(int)((e >> 56) & 0x7F)] + (e & 0xFFFFFFFFFFull)]) { err = PERR_CORRUPT; return; }
+        }
         if (v == 0) { key_off = pos + 2; klen = kl; }
         if (!dt_supersedes(pdel, pd)) pdel = pd;                  // collectPartitionLevelDeletion :465-482
-        c.pos = r.p; c.next = r.p;
+        c.pos = (decltype(c.pos))r.p; c.next = c.pos;
     }
     DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;                 // PurgeFunction.applyToDeletion :95-99
 
@@ -614,14 +632,14 @@ __device__ void process_partition(const CParams& P, const uint64_t* __restrict__
             int npresent = 0; for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;
             if (!(live_is_empty(info) && dt_is_live(del) && npresent == 0)) {
                 st.merged_unfiltereds++;
-                Cur& f = cur[b];
-                CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, K_CLUSTERING, f.n};
+                CUR& f = cur[b];
+                CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), K_CLUSTERING, f.n};
                 int present = purge_row(P, pg, info, del, merged);
                 if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
             }
         } else {
-            Cur& f = cur[last];                                       // `bound` = clustering of the last marker added (:99-103)
-            CkRef ck{f.pos + f.ck_rel, f.ckend_rel - f.ck_rel, f.kind, f.n};
+            CUR& f = cur[last];                                       // `bound` = clustering of the last marker added (:99-103)
+            CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), f.kind, f.n};
             DT mc = dt_live(), mo = dt_live(); bool emit = false;
             if (!multi) { read_marker_dts(P, f, mc, mo, err); emit = true; }
             else {

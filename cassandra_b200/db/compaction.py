@@ -142,7 +142,7 @@ class CompactionTask:
             meta = CompressionMetadata(self.compression.compressor_name, cl, self.compression.max_compressed_length, int(o.data_length),
                                        [int(x) for x in co[:o.nchunks]], self.compression.options)
             r.outputs.append(OutputSSTable(d[:o.data_len].tobytes(), ix[:o.index_len].tobytes(), meta, int(o.digest), int(o.partitions), int(o.rows)))
-        r.stats = dict(bytes_read=int(res.bytes_read), bytes_written=int(res.bytes_written), total_source_rows=int(res.total_source_rows),
+        r.stats = dict(bytes_read=int(res.bytes_read), bytes_in_range=int(res.bytes_in_range), bytes_written=int(res.bytes_written), total_source_rows=int(res.total_source_rows),
                        input_partitions=int(res.input_partitions), merged_row_counts=[int(x) for x in res.merged_row_counts[:len(self.inputs)]],
                        kernel_ms=res.kernel_ms, total_ms=res.total_ms, kernel_launches=int(res.kernel_launches), index_slow_path_inputs=int(res.index_slow_path_inputs), wall_s=wall)
         return r

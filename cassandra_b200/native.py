@@ -66,7 +66,7 @@ class Output(C.Structure):
                 ("stats", C.POINTER(SSTableStats))]
 class Result(C.Structure):
     _fields_ = [("noutputs_cap", C.c_int32), ("noutputs", C.c_int32), ("outputs", C.POINTER(Output)),
-                ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64), ("total_source_rows", C.c_uint64),
+                ("bytes_read", C.c_uint64), ("bytes_in_range", C.c_uint64), ("bytes_written", C.c_uint64), ("total_source_rows", C.c_uint64),
                 ("input_partitions", C.c_uint64), ("merged_row_counts", C.c_uint64 * MAX_INPUTS),
                 ("required_data_cap", C.c_uint64), ("required_index_cap", C.c_uint64), ("required_chunk_cap", C.c_uint64),
                 ("corruption", Corruption), ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_uint64),

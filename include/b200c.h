@@ -270,7 +270,9 @@ typedef struct b200c_result {
     int32_t   noutputs_cap;             /* in: entries in outputs[] */
     int32_t   noutputs;                 /* out */
     b200c_output* outputs;
-    uint64_t  bytes_read;               /* uncompressed input bytes (metric numerator, CompactionTask.java:258) */
+    uint64_t  bytes_read;               /* uncompressed length of every input (metric numerator of a whole-ring task, CompactionTask.java:258) */
+    uint64_t  bytes_in_range;           /* uncompressed bytes of the input partitions inside (token_lo, token_hi] = what ranged scanners
+                                           report as getLengthInBytes (S/io/sstable/format/SSTableScanner.java); = bytes_read for the whole ring */
     uint64_t  bytes_written;            /* uncompressed output bytes */
     uint64_t  total_source_rows;        /* rows + markers read, CompactionIterator.totalSourceCQLRows :368 */
     uint64_t  input_partitions;

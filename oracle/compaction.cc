@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <memory>
 
 namespace oracle {
 
@@ -112,7 +113,13 @@ static int compare_clust(const Schema& s, const Clust& a, const Clust& b) {
 struct Source {
     int idx;
     const b200c_input* in;
-    std::vector<uint8_t> data;      // uncompressed Data stream
+    // uncompressed Data stream: allocated uninitialised and decompressed chunk by chunk on first touch (CompressedChunkReader reads
+    // chunks on demand too, S/io/util/CompressedChunkReader.java:103-173), so a token sub-range only pays for the chunks it crosses
+    std::unique_ptr<uint8_t[]> buf; uint64_t dlen = 0;
+    std::vector<bool> have_chunk;
+    const uint8_t* dptr() const { return buf.get(); }
+    uint64_t dsize() const { return dlen; }
+    void need(uint64_t lo, uint64_t hi);      // make bytes [lo, hi) of the stream available
     uint64_t pos = 0;               // cursor: start of the current partition
     // Index.db cursor (BigTableScanner walks Index.db: S/io/sstable/format/big/BigTableScanner.java:135-184)
     uint64_t ipos = 0;
@@ -121,7 +128,8 @@ struct Source {
     const uint8_t* key = nullptr; int keylen = 0; int64_t token = 0;
     bool has_prev = false; int64_t prev_token = 0;
     DT pdel; uint64_t upos = 0;     // cursor inside the partition (next unfiltered)
-    uint64_t part_start = 0;
+    uint64_t part_start = 0, part_end = 0;
+    uint64_t range_bytes = 0;       // uncompressed bytes of the partitions inside the token range (scanner accounting)
 };
 
 struct Reader {
@@ -190,9 +198,9 @@ static bool read_unfiltered(Source& src, const Schema& s, Unf& u) {
 }
 static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u) {
     const b200c_input& in = *src.in;
-    Reader r{src.data.data() + src.upos, src.data.data() + src.data.size(), src.idx};
+    Reader r{src.dptr() + src.upos, src.dptr() + src.part_end, src.idx};
     uint8_t flags = r.u8();
-    if (flags & 0x01) { src.upos = r.p - src.data.data(); return false; }
+    if (flags & 0x01) { src.upos = r.p - src.dptr(); return false; }
     const b200c_encoding_stats& hs = in.header_stats;
     if (flags & 0x02) {
         u.is_row = false; u.cells.clear();
@@ -246,39 +254,48 @@ static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u) {
         }
         std::sort(u.cells.begin(), u.cells.end(), [](const CellV& a, const CellV& b) { return a.col < b.col; });
     }
-    src.upos = r.p - src.data.data();
+    src.upos = r.p - src.dptr();
     return true;
 }
 
-// CompressedChunkReader.readChunk for every chunk: S/io/util/CompressedChunkReader.java:103-173
-static void load_source(Source& src) {
+// CompressedChunkReader.readChunk: S/io/util/CompressedChunkReader.java:103-173
+static void load_chunk(Source& src, uint64_t i) {
     const b200c_input& in = *src.in;
-    src.data.resize(in.data_length + 16);
+    const uint64_t nch = in.nchunks;
+    uint64_t off = in.chunk_offsets[i];
+    uint64_t next = (i + 1 < nch) ? in.chunk_offsets[i + 1] : in.data_len;
+    if (off + 4 > next || next > in.data_len) throw Corrupt{src.idx, 2, i, off, "chunk bounds"};
+    uint32_t clen = (uint32_t)(next - off - 4);
+    const uint8_t* c = in.data + off;
+    uint32_t stored = ((uint32_t)c[clen] << 24) | ((uint32_t)c[clen + 1] << 16) | ((uint32_t)c[clen + 2] << 8) | c[clen + 3];
+    if (crc32_ieee(0, c, clen) != stored) throw Corrupt{src.idx, 1, i, off, "chunk CRC mismatch"};
+    uint64_t ustart = i * (uint64_t)in.chunk_len;
+    int ulen = (int)std::min<uint64_t>(in.chunk_len, in.data_length - ustart);
+    if ((int64_t)clen >= (int64_t)in.max_compressed_len) {              // raw chunk (:116,219)
+        if ((int)clen < ulen) throw Corrupt{src.idx, 2, i, off, "short raw chunk"};
+        memcpy(src.buf.get() + ustart, c, ulen);
+    } else {
+        int got = chunk_decompress(in.compressor, c, (int)clen, src.buf.get() + ustart, ulen);
+        if (got != ulen) throw Corrupt{src.idx, 2, i, off, "malformed compressed chunk"};
+    }
+    src.have_chunk[i] = true;
+}
+void Source::need(uint64_t lo, uint64_t hi) {
+    if (hi > dlen) hi = dlen;
+    if (lo >= hi) return;
+    const uint64_t L = (uint64_t)in->chunk_len;
+    for (uint64_t i = lo / L; i <= (hi - 1) / L; i++) if (!have_chunk[i]) load_chunk(*this, i);
+}
+static void open_source(Source& src, bool whole) {
+    const b200c_input& in = *src.in;
     uint64_t nch = in.nchunks;
     if (nch != (in.data_length + in.chunk_len - 1) / (uint64_t)in.chunk_len) throw Corrupt{src.idx, 2, 0, 0, "chunk count"};
-    for (uint64_t i = 0; i < nch; i++) {
-        uint64_t off = in.chunk_offsets[i];
-        uint64_t next = (i + 1 < nch) ? in.chunk_offsets[i + 1] : in.data_len;
-        if (off + 4 > next || next > in.data_len) throw Corrupt{src.idx, 2, i, off, "chunk bounds"};
-        uint32_t clen = (uint32_t)(next - off - 4);
-        const uint8_t* c = in.data + off;
-        uint32_t stored = ((uint32_t)c[clen] << 24) | ((uint32_t)c[clen + 1] << 16) | ((uint32_t)c[clen + 2] << 8) | c[clen + 3];
-        if (crc32_ieee(0, c, clen) != stored) throw Corrupt{src.idx, 1, i, off, "chunk CRC mismatch"};
-        uint64_t ustart = i * (uint64_t)in.chunk_len;
-        int ulen = (int)std::min<uint64_t>(in.chunk_len, in.data_length - ustart);
-        if ((int64_t)clen >= (int64_t)in.max_compressed_len) {              // raw chunk (:116,219)
-            if ((int)clen < ulen) throw Corrupt{src.idx, 2, i, off, "short raw chunk"};
-            memcpy(src.data.data() + ustart, c, ulen);
-        } else {
-            int got = chunk_decompress(in.compressor, c, (int)clen, src.data.data() + ustart, ulen);
-            if (got != ulen) throw Corrupt{src.idx, 2, i, off, "malformed compressed chunk"};
-        }
-    }
-    src.data.resize(in.data_length);
+    src.buf.reset(new uint8_t[in.data_length + 64]);                    // uninitialised on purpose: nothing is read before its chunk was decoded
+    memset(src.buf.get() + in.data_length, 0, 64);
+    src.dlen = in.data_length; src.have_chunk.assign(nch, false);
+    if (whole) src.need(0, in.data_length);                             // a whole-ring compaction reads (and checksums) every chunk, as the reference does
 }
 
-// advance to the next partition via Index.db (key, position, promoted index skipped): BigTableScanner.java:135-184,
-// RowIndexEntry.Serializer.deserialize S/io/sstable/format/big/RowIndexEntry.java:340-377
 // the order-defining token: Murmur3Partitioner.getToken (S/dht/Murmur3Partitioner.java:256-296), or for ByteOrderedPartitioner
 // (S/dht/ByteOrderedPartitioner.java: the token is the key) the sign-flipped big-endian 8-byte key prefix — an order-preserving stand-in
 // whose ties compare_key() resolves on the full key bytes, i.e. exactly unsigned lexicographic key order
@@ -303,12 +320,22 @@ static void next_partition(Source& src, int64_t tok_lo, int64_t tok_hi) {
             if (src.has_prev && (tok < src.prev_token)) throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db is not in partitioner order"};
             src.has_prev = true; src.prev_token = tok;
             if (!((tok_lo == INT64_MIN || tok > tok_lo) && tok <= tok_hi)) continue;
-            if (pos + 2 + kl > src.data.size() || ((src.data[pos] << 8) | src.data[pos + 1]) != kl || memcmp(src.data.data() + pos + 2, key, kl) != 0)
+            // the partition ends where the next Index.db entry says the next one starts (or at the end of the stream)
+            uint64_t end = src.dsize();
+            if (src.ipos < in.index_len) {
+                Reader nr{in.index + src.ipos, in.index + in.index_len, src.idx};
+                int nkl = nr.u16(); nr.bytes(nkl); end = nr.vint();
+            }
+            if (end > src.dsize() || end <= pos || pos + 2 + kl > end) throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db positions"};
+            src.need(pos, end);
+            const uint8_t* d = src.dptr();
+            if (((d[pos] << 8) | d[pos + 1]) != kl || memcmp(d + pos + 2, key, kl) != 0)
                 throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db entry does not match Data.db"};
-            Reader r{src.data.data() + pos + 2 + kl, src.data.data() + src.data.size(), src.idx};
+            Reader r{d + pos + 2 + kl, d + end, src.idx};
             src.pdel = read_partition_dt(r);                               // SSTableIdentityIterator.create :62-78
-            src.key = src.data.data() + pos + 2; src.keylen = kl; src.token = tok; src.part_start = pos;
-            src.upos = r.p - src.data.data();
+            src.key = d + pos + 2; src.keylen = kl; src.token = tok; src.part_start = pos; src.part_end = end;
+            src.range_bytes += end - pos;
+            src.upos = r.p - d;
             src.has = true;
             return;
         } catch (Corrupt& c) { if (c.kind == 4) { c.kind = 3; c.offset = src.ipos; } throw; }
@@ -630,7 +657,8 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
     g_partitioner = m->partitioner;
     std::vector<Source> srcs(m->ninputs);
     uint64_t bytes_read = 0;
-    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; load_source(srcs[i]); bytes_read += srcs[i].data.size(); next_partition(srcs[i], m->token_lo, m->token_hi); }
+    const bool whole_ring = m->token_lo == INT64_MIN && m->token_hi == INT64_MAX;
+    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; open_source(srcs[i], whole_ring); bytes_read += srcs[i].dsize(); next_partition(srcs[i], m->token_lo, m->token_hi); }
     if (m->partitioner != B200C_PARTITIONER_MURMUR3 && m->partitioner != B200C_PARTITIONER_BYTE_ORDERED) return B200C_EUNSUPPORTED;
     if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) return B200C_EUNSUPPORTED;
     Purger pg{m->now_in_sec, m->gc_before, m->purge_max_timestamp};
@@ -701,6 +729,7 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
     if (w.outs.size() > 1 && w.outs.back().parts == 0) w.outs.pop_back();
     res->noutputs = (int)w.outs.size();
     res->bytes_read = bytes_read; res->total_source_rows = total_source_rows; res->input_partitions = input_partitions;
+    res->bytes_in_range = 0; for (auto& sr : srcs) res->bytes_in_range += sr.range_bytes;
     uint64_t bw = 0; int rc = B200C_OK;
     res->required_data_cap = res->required_index_cap = res->required_chunk_cap = 0;
     for (size_t i = 0; i < w.outs.size(); i++) {

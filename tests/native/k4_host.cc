@@ -68,8 +68,8 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
             const uint8_t* key = in.index + o + 2; uint64_t p = o + 2 + kl;
             uint64_t pos, ps; int r = oracle::vint_read(in.index + p, in.index + in.index_len, &pos); if (r <= 0) return fail(err, errcap, "index"); p += r;
             r = oracle::vint_read(in.index + p, in.index + in.index_len, &ps); if (r <= 0) return fail(err, errcap, "index"); p += r;
-            int64_t t = oracle::murmur3_token(key, kl);
             uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0);
+            int64_t t = m->partitioner ? (int64_t)(pre ^ 0x8000000000000000ull) : oracle::murmur3_token(key, kl);     // k_index_emit
             tok.push_back(t); kp.push_back(pre); klen.push_back((uint16_t)kl); upos.push_back(ubase[i] + pos); keyp.push_back(key);
             if ((m->token_lo == INT64_MIN || t > m->token_lo) && t <= m->token_hi) parts.push_back(Part{t, key, kl, i, n});
             o = p + ps; n++;
@@ -78,8 +78,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     }
     pbase[K] = tok.size();
     // ---- "K3": partition merge: order by (token, unsigned key bytes), sources in input order ------------------------------------------
-    // (a single input keeps its file order: the reference's golden fixtures were written under ByteOrderedPartitioner)
-    if (K > 1) std::stable_sort(parts.begin(), parts.end(), [](const Part& a, const Part& b) {
+    std::stable_sort(parts.begin(), parts.end(), [](const Part& a, const Part& b) {
         if (a.tok != b.tok) return a.tok < b.tok;
         int c = memcmp(a.key, b.key, std::min(a.klen, b.klen)); if (c) return c < 0;
         if (a.klen != b.klen) return a.klen < b.klen;
@@ -100,8 +99,10 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     for (int k = 0; k < m->ncolumns; k++) P.vfix[k] = m->columns[k].fixed_len;
     P.o_min_ts = m->out_stats.min_timestamp; P.o_min_ldt = m->out_stats.min_local_deletion_time; P.o_min_ttl = m->out_stats.min_ttl;
     P.now = m->now_in_sec; P.gc_before = m->gc_before; P.purge_max_ts = m->purge_max_timestamp;
+    P.partitioner = m->partitioner;
+    std::vector<InDesc> hin(K); memset(hin.data(), 0, sizeof(InDesc) * K); P.in = hin.data();
     for (int i = 0; i < K; i++) {
-        const b200c_input& in = m->inputs[i]; InDesc& d = P.in[i];
+        const b200c_input& in = m->inputs[i]; InDesc& d = hin[i];
         d.ubase = ubase[i]; d.ulen = in.data_length; d.min_ts = in.header_stats.min_timestamp; d.min_ldt = in.header_stats.min_local_deletion_time; d.min_ttl = in.header_stats.min_ttl;
         d.ncols = in.ncolumns; for (int k = 0; k < in.ncolumns; k++) d.colmap[k] = in.column_map[k];
     }
@@ -110,7 +111,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     std::vector<PartOut> po(nparts); PartStats st{0, 0};
     for (uint64_t j = 0; j < nparts; j++) {
         int e = 0; PartOut out{0, 0, 0, 0, 0};
-        process_partition<false>(P, contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
+        process_partition<false>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
                                  nullptr, ~0ull, 0, nullptr, 0, 0, 0, cur.data(), open_dt.data(), merged.data(), out, st, e);
         if (e) return fail(err, errcap, e == PERR_UNSUPPORTED ? "unsupported" : "corrupt data");
         po[j] = out;
@@ -127,10 +128,56 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     for (uint64_t j = 0; j < nparts; j++) {
         if (!po[j].dsize) continue;
         int e = 0; PartOut out{0, 0, 0, 0, 0};
-        process_partition<true>(P, contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
+        process_partition<true>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
                                 uout + dpos[j], ~0ull, dpos[j], iout + ipos[j], po[j].nblk, po[j].ipay, 0, cur.data(), open_dt.data(), merged.data(), out, st2, e);
         if (e || out.dsize != po[j].dsize) return fail(err, errcap, "size pass and emit pass disagree at partition " + std::to_string(j));
         written++;
+    }
+    // ---- the staged path (k_partition_staged): token-contiguous tiles of output partitions whose input byte ranges (one contiguous
+    //      range per source) are copied into a small buffer, P.U pointing at the copy, 32-byte cursors with 32/16-bit offsets -----------
+    {
+        std::vector<uint8_t> u2(dpos[nparts] + 64, 0), i2(ipos[nparts] + 64, 0);
+        std::vector<CurS> curs(MAXK); PartStats st3{0, 0};
+        const uint64_t TILE_BYTES = 40000;
+        uint64_t j0 = 0;
+        while (j0 < nparts) {
+            // grow the tile while it fits
+            uint64_t j1 = j0, bytes = 0; std::vector<uint64_t> lo(K, ~0ull), hi(K, 0);
+            while (j1 < nparts && j1 - j0 < 128) {
+                uint64_t add = 0;
+                for (uint64_t c = op_first[j1]; c < op_first[j1 + 1]; c++) { uint64_t e = contrib[c]; uint64_t g = pbase[(e >> 56) & 0x7F] + (e & 0xFFFFFFFFFFull); add += upos[g + 1] - upos[g]; }
+                if (j1 > j0 && bytes + add > TILE_BYTES) break;
+                bytes += add; j1++;
+            }
+            for (uint64_t c = op_first[j0]; c < op_first[j1]; c++) { uint64_t e = contrib[c]; int src = (int)((e >> 56) & 0x7F); uint64_t l = e & 0xFFFFFFFFFFull; lo[src] = std::min(lo[src], l); hi[src] = std::max(hi[src], l); }
+            std::vector<uint32_t> sbase(K, 0); std::vector<uint64_t> g0(K, 0); uint64_t tot = 0;
+            for (int i = 0; i < K; i++) if (lo[i] != ~0ull) {
+                uint64_t a = upos[pbase[i] + lo[i]] & ~15ull, b = (upos[pbase[i] + hi[i] + 1] + 15) & ~15ull;
+                sbase[i] = (uint32_t)tot; g0[i] = a; tot += b - a;
+            }
+            if (tot + 64 > 65535 || bytes > 60000) {          // too big to stage: the global path handles it (as the kernel does)
+                for (uint64_t j = j0; j < j1; j++) if (po[j].dsize) {
+                    int e = 0; PartOut out{0, 0, 0, 0, 0};
+                    process_partition<true>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
+                                            u2.data() + dpos[j], ~0ull, dpos[j], i2.data() + ipos[j], po[j].nblk, po[j].ipay, 0, cur.data(), open_dt.data(), merged.data(), out, st3, e);
+                    if (e) return fail(err, errcap, "staged pass (global fallback) failed");
+                }
+                j0 = j1; continue;
+            }
+            std::vector<uint8_t> tile(tot + 64, 0xEE);
+            for (int i = 0; i < K; i++) if (lo[i] != ~0ull) memcpy(tile.data() + sbase[i], U + g0[i], ((upos[pbase[i] + hi[i] + 1] + 15) & ~15ull) - g0[i]);
+            CParams PS = P; PS.U = tile.data();
+            XlateStaged xl{sbase.data(), g0.data()};
+            for (uint64_t j = j0; j < j1; j++) if (po[j].dsize) {
+                int e = 0; PartOut out{0, 0, 0, 0, 0};
+                process_partition<true>(PS, xl, contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
+                                        u2.data() + dpos[j], ~0ull, dpos[j], i2.data() + ipos[j], po[j].nblk, po[j].ipay, 0, curs.data(), open_dt.data(), merged.data(), out, st3, e);
+                if (e || out.dsize != po[j].dsize) return fail(err, errcap, "staged pass disagrees at partition " + std::to_string(j));
+            }
+            j0 = j1;
+        }
+        if (memcmp(u2.data(), uout, dpos[nparts]) || memcmp(i2.data(), iout, ipos[nparts])) return fail(err, errcap, "staged pass produced different bytes");
+        if (st3.merged_unfiltereds != st2.merged_unfiltereds || st3.rows_out != st2.rows_out) return fail(err, errcap, "staged pass counters differ");
     }
     if (stats) { stats[0] = st.merged_unfiltereds; stats[1] = st.rows_out; stats[2] = written; }
     return 0;

@@ -33,7 +33,7 @@ def both(ctx, tables, controller, **kw):
     assert g.compression.chunk_offsets == w.compression.chunk_offsets and g.compression.data_length == w.compression.data_length
     assert g.digest == w.digest == zlib.crc32(g.data)
     assert (g.partitions, g.rows) == (w.partitions, w.rows)
-    for k in ("bytes_read", "bytes_written", "total_source_rows", "input_partitions", "merged_row_counts"):
+    for k in ("bytes_read", "bytes_in_range", "bytes_written", "total_source_rows", "input_partitions", "merged_row_counts"):
         assert got.stats[k] == want.stats[k], k
     assert got.stats["kernel_launches"] > 0
     assert got.stats["index_slow_path_inputs"] == 0, "Index.db speculation fell back to the sequential walk"

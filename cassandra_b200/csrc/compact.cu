@@ -56,9 +56,9 @@ __device__ __forceinline__ void report_err(DevErr* e, int kind, int input, uint6
 }
 
 // ---- Murmur3 (Cassandra variant): S/utils/MurmurHash.java:178-260, token = Murmur3Partitioner.getToken :256-296 ---------------
-__device__ __forceinline__ uint64_t rotl64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
-__device__ __forceinline__ uint64_t fmix64(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k; }
-__device__ int64_t murmur3_token(const uint8_t* key, uint32_t len) {
+__host__ __device__ __forceinline__ uint64_t rotl64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k; }
+__host__ __device__ int64_t murmur3_token(const uint8_t* key, uint32_t len) {
     if (len == 0) return I64_MIN;
     const uint32_t nblocks = len >> 4;
     uint64_t h1 = 0, h2 = 0;
@@ -1260,7 +1260,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
                 B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
                 ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
-                static const bool staged = []() { const char* e = getenv("B200C_K4_STAGED"); return !e || atoi(e) != 0; }();      // A/B switch
+                const bool staged = []() { const char* e = getenv("B200C_K4_STAGED"); return !e || atoi(e) != 0; }();      // A/B switch (read per call)
                 if (staged) {
                     // tile plan: exclusive scan of the input bytes, cut marks, scan of the marks, tile starts
                     uint64_t *d_inpos, *d_tscan; uint32_t *d_mark, *d_tstart; unsigned long long* d_nbig = (unsigned long long*)(d_stats + 1);
@@ -1498,6 +1498,11 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     c->prog_scanned.store(bytes_read); c->prog_stage.store(6);
     res->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     return rc;
+}
+
+int64_t b200c_token(int partitioner, const uint8_t* key, uint32_t len) {
+    if (partitioner == B200C_PARTITIONER_BYTE_ORDERED) { uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < len ? key[q] : 0); return (int64_t)(pre ^ 0x8000000000000000ull); }
+    return murmur3_token(key, len);
 }
 
 int b200c_poll(b200c_ctx* c, b200c_progress* p) {

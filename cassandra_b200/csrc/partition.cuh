@@ -520,7 +520,7 @@ struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; };
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
 // cur[0..m) / open_dt[0..m): per-source cursor state owned by this thread (the caller places it in shared memory);
 // merged[0..ncols): scratch for the merged row.
-__device__ int64_t murmur3_token(const uint8_t* key, uint32_t len);     // compact.cu
+__host__ __device__ int64_t murmur3_token(const uint8_t* key, uint32_t len);     // compact.cu
 
 // where an input partition's bytes are, as an offset from P.U: the decompressed stream itself (XlateGlobal), or a tile of it that
 // k_partition_staged copied into shared memory (XlateStaged: P.U then points at the tile)

@@ -101,6 +101,7 @@ SYMBOLS = {
     "b200c_compress": (C.c_int, [_vp, _i, _u8p, _i, _u8p, _i]),
     "b200c_uncompress": (C.c_int, [_vp, _i, _u8p, _i, _u8p, _i]),
     "b200c_compact": (C.c_int, [_vp, C.POINTER(Manifest), C.POINTER(Result), _i]),
+    "b200c_token": (C.c_int64, [C.c_int, _u8p, C.c_uint32]),
     "b200c_poll": (C.c_int, [_vp, C.POINTER(Progress)]),
     "b200c_poll_inputs": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
     "b200c_cancel": (None, [_vp]),

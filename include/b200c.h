@@ -294,6 +294,11 @@ typedef struct b200c_result {
    in the one-piece run. Buffers must stay valid until the call returns; nothing is in flight afterwards, whatever the return code. */
 int          b200c_compact(b200c_ctx*, const b200c_manifest*, b200c_result*, int flags);
 
+/* the order token the engine derives from a partition key (host function, no device needed): Murmur3Partitioner.getToken
+ * (S/dht/Murmur3Partitioner.java:256-296) or, for ByteOrderedPartitioner, the sign-flipped big-endian 8-byte key prefix. For hosts that
+ * pick token-range splitters from Summary.db sample keys (one compaction sharded over several GPUs: token_lo / token_hi per shard). */
+int64_t      b200c_token(int partitioner, const uint8_t* key, uint32_t len);
+
 typedef struct b200c_progress { uint64_t bytes_scanned; uint64_t bytes_total; int32_t stage; int32_t _pad; } b200c_progress;
 int          b200c_poll(b200c_ctx*, b200c_progress*);   /* callable from another thread */
 /* ISSTableScanner.getCurrentPosition per input (S/io/sstable/ISSTableScanner.java:34-41, consumed by CompactionIterator.java:289-295):

@@ -9,6 +9,7 @@
 // (rowProcessingNeeded() == false), forward order. Anything else returns B200C_EUNSUPPORTED — same envelope as the GPU engine.
 #include "codec.h"
 #include "../include/b200c.h"
+#include "parallel.h"
 #include <cstring>
 #include <vector>
 #include <string>
@@ -22,9 +23,6 @@ namespace oracle {
 static const int64_t NO_TS = INT64_MIN;          // LivenessInfo.NO_TIMESTAMP
 static const int64_t NO_DEL = INT64_MAX;         // Cell.NO_DELETION_TIME / LivenessInfo.NO_EXPIRATION_TIME
 static const int32_t EXPIRED_TTL = INT32_MAX;    // LivenessInfo.EXPIRED_LIVENESS_TTL
-
-struct Unsupported { std::string what; };
-struct Corrupt { int input; int kind; uint64_t chunk; uint64_t offset; std::string what; };
 
 // ---- DeletionTime: S/db/DeletionTime.java:46 (LIVE), :158-176 (supersedes/deletes) -------------------------------
 struct DT {
@@ -126,7 +124,7 @@ struct Source {
     // current partition
     bool has = false;
     const uint8_t* key = nullptr; int keylen = 0; int64_t token = 0;
-    bool has_prev = false; int64_t prev_token = 0;
+    bool has_prev = false; int64_t prev_token = 0; const uint8_t* prev_key = nullptr; int prev_klen = 0;
     DT pdel; uint64_t upos = 0;     // cursor inside the partition (next unfiltered)
     uint64_t part_start = 0, part_end = 0;
     uint64_t range_bytes = 0;       // uncompressed bytes of the partitions inside the token range (scanner accounting)
@@ -295,6 +293,22 @@ static void open_source(Source& src, bool whole) {
     src.dlen = in.data_length; src.have_chunk.assign(nch, false);
     if (whole) src.need(0, in.data_length);                             // a whole-ring compaction reads (and checksums) every chunk, as the reference does
 }
+static int64_t order_token(const uint8_t* key, int kl);
+// ranged scanner: start the Index.db walk at the last Summary.db sample whose token is <= token_lo instead of at the file start
+// (BigTableScanner seeks with the index summary too, S/io/sstable/format/big/BigTableScanner.java:105-132)
+static void seek_source(Source& src, int64_t tok_lo) {
+    const b200c_input& in = *src.in;
+    if (tok_lo == INT64_MIN || !in.summary_positions || !in.nsummary) return;
+    uint64_t a = 0, b = in.nsummary;                                     // first sample with token > tok_lo
+    while (a < b) {
+        uint64_t mid = (a + b) / 2, off = in.summary_positions[mid];
+        if (off + 2 > in.index_len) { b = mid; continue; }
+        int kl = (in.index[off] << 8) | in.index[off + 1];
+        if (off + 2 + kl > in.index_len) { b = mid; continue; }
+        if (order_token(in.index + off + 2, kl) <= tok_lo) a = mid + 1; else b = mid;
+    }
+    if (a > 0) src.ipos = in.summary_positions[a - 1];
+}
 
 // the order-defining token: Murmur3Partitioner.getToken (S/dht/Murmur3Partitioner.java:256-296), or for ByteOrderedPartitioner
 // (S/dht/ByteOrderedPartitioner.java: the token is the key) the sign-flipped big-endian 8-byte key prefix — an order-preserving stand-in
@@ -317,9 +331,14 @@ static void next_partition(Source& src, int64_t tok_lo, int64_t tok_hi) {
             ir.bytes(psize);
             src.ipos = ir.p - in.index;
             int64_t tok = order_token(key, kl);
-            if (src.has_prev && (tok < src.prev_token)) throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db is not in partitioner order"};
-            src.has_prev = true; src.prev_token = tok;
-            if (!((tok_lo == INT64_MIN || tok > tok_lo) && tok <= tok_hi)) continue;
+            if (src.has_prev) {                        // SortedTableWriter.verifyPartition :165-178: keys strictly increase in (token, key bytes) order
+                bool bad = tok < src.prev_token;
+                if (!bad && tok == src.prev_token) { int n = std::min(kl, src.prev_klen); int c = n ? memcmp(src.prev_key, key, n) : 0; bad = c > 0 || (c == 0 && src.prev_klen >= kl); }
+                if (bad) throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db is not in partitioner order"};
+            }
+            src.has_prev = true; src.prev_token = tok; src.prev_key = key; src.prev_klen = kl;
+            if (tok > tok_hi) { src.has = false; src.ipos = in.index_len; return; }     // sorted input: nothing further can be in range
+            if (!(tok_lo == INT64_MIN || tok > tok_lo)) continue;
             // the partition ends where the next Index.db entry says the next one starts (or at the end of the stream)
             uint64_t end = src.dsize();
             if (src.ipos < in.index_len) {
@@ -496,10 +515,12 @@ struct Writer {
     std::vector<std::vector<uint8_t>> index_infos;
     OutBuf body, tmp;
 
+    bool raw = false;                   // parallel driver (parallel.cc): keep the uncompressed stream, compression happens after stitching
     void start_output() { outs.emplace_back(); position = 0; chunk_offset = 0; chunk.clear(); }
     void flush_chunk() {                // flushData :140-206
         if (chunk.empty()) return;
         Sst& o = outs.back();
+        if (raw) { o.data.insert(o.data.end(), chunk.begin(), chunk.end()); o.ulen += chunk.size(); chunk.clear(); return; }
         comp.resize(chunk_max_compressed(m->out_compressor, m->out_chunk_len) + 64);
         int clen = chunk_compress(m->out_compressor, chunk.data(), (int)chunk.size(), comp.data());
         const uint8_t* w = comp.data(); int wlen = clen;
@@ -647,7 +668,9 @@ struct Writer {
     }
 };
 
-static int compact_impl(const b200c_manifest* m, b200c_result* res) {
+// ro != nullptr: raw mode for the parallel driver — the uncompressed stream and the (range-relative) Index.db of output 0 are moved
+// into *ro instead of being compressed and copied into the caller's buffers
+int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
     auto t0 = std::chrono::steady_clock::now();
     if (m->abi_version != B200C_ABI_VERSION || m->ninputs <= 0 || m->ninputs > B200C_MAX_INPUTS) return B200C_EINVAL;
     if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) return B200C_EUNSUPPORTED;
@@ -658,11 +681,12 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
     std::vector<Source> srcs(m->ninputs);
     uint64_t bytes_read = 0;
     const bool whole_ring = m->token_lo == INT64_MIN && m->token_hi == INT64_MAX;
-    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; open_source(srcs[i], whole_ring); bytes_read += srcs[i].dsize(); next_partition(srcs[i], m->token_lo, m->token_hi); }
+    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; open_source(srcs[i], whole_ring); seek_source(srcs[i], m->token_lo); bytes_read += srcs[i].dsize(); next_partition(srcs[i], m->token_lo, m->token_hi); }
     if (m->partitioner != B200C_PARTITIONER_MURMUR3 && m->partitioner != B200C_PARTITIONER_BYTE_ORDERED) return B200C_EUNSUPPORTED;
     if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) return B200C_EUNSUPPORTED;
     Purger pg{m->now_in_sec, m->gc_before, m->purge_max_timestamp};
-    Writer w; w.m = m; w.sc = sc; w.start_output();
+    Writer w; w.m = m; w.sc = sc; w.raw = ro != nullptr; w.start_output();
+    if (ro && m->max_sstable_bytes) return B200C_EUNSUPPORTED;
     memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
     uint64_t total_source_rows = 0, input_partitions = 0;
     std::vector<Unf> heads(m->ninputs);
@@ -730,6 +754,11 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
     res->noutputs = (int)w.outs.size();
     res->bytes_read = bytes_read; res->total_source_rows = total_source_rows; res->input_partitions = input_partitions;
     res->bytes_in_range = 0; for (auto& sr : srcs) res->bytes_in_range += sr.range_bytes;
+    if (ro) {
+        ro->ustream = std::move(w.outs[0].data); ro->index = std::move(w.outs[0].index); ro->partitions = w.outs[0].parts; ro->rows = w.outs[0].rows;
+        res->bytes_written = ro->ustream.size(); res->noutputs = 1;
+        return B200C_OK;
+    }
     uint64_t bw = 0; int rc = B200C_OK;
     res->required_data_cap = res->required_index_cap = res->required_chunk_cap = 0;
     for (size_t i = 0; i < w.outs.size(); i++) {
@@ -754,7 +783,7 @@ static int compact_impl(const b200c_manifest* m, b200c_result* res) {
 } // namespace oracle
 
 extern "C" int orc_compact(const b200c_manifest* m, b200c_result* res, char* errbuf, int errcap) {
-    try { return oracle::compact_impl(m, res); }
+    try { return oracle::compact_impl(m, res, nullptr); }
     catch (oracle::Unsupported& u) { if (errbuf) snprintf(errbuf, errcap, "unsupported: %s", u.what.c_str()); return B200C_EUNSUPPORTED; }
     catch (oracle::Corrupt& c) {
         res->corruption.input = c.input; res->corruption.kind = c.kind; res->corruption.chunk = c.chunk; res->corruption.offset = c.offset;

@@ -124,7 +124,7 @@ def test_mixed_types_variable_keys(ctx):
     rng = random.Random(5)
     s = Schema(["LongType", "UTF8Type"], [("a", "LongType"), ("b", "UTF8Type"), ("c", "Int32Type"), ("d", "DoubleType")])
     tables = []
-    keys = [bytes(rng.getrandbits(8) for _ in range(rng.choice([1, 3, 8, 9, 17, 40]))) for _ in range(300)] + [b""]
+    keys = sorted({bytes(rng.getrandbits(8) for _ in range(rng.choice([1, 3, 8, 9, 17, 40]))) for _ in range(300)} | {b""})     # a key occurs once per sstable
     for t in range(5):
         parts = []
         for k in keys:

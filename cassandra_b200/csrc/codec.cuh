@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(32) k_compress_chunks(const DevTables* __restr
     if (comp == COMP_LZ4) {
         if (lane == 0) { slot[0] = (uint8_t)ulen; slot[1] = (uint8_t)(ulen >> 8); slot[2] = (uint8_t)(ulen >> 16); slot[3] = (uint8_t)(ulen >> 24); }
         clen = 4 + lz4_compress_warp<false>(s_in, ulen, s_tab, slot + 4, lane);
-    } else if (comp == COMP_SNAPPY) {
-        clen = snappy_compress_warp(s_in, ulen, s_tab, slot, lane);
+    } else if (comp_is_snappy(comp)) {
+        clen = snappy_compress_warp(s_in, ulen, s_tab, comp == COMP_SNAPPY15 ? 15 : 14, slot, lane);
     } else {
         clen = ulen;
         for (int i = lane; i < ulen; i += 32) slot[i] = s_in[i];
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(64) k_decompress_chunks(const DevTables* __res
     } else if (comp == COMP_LZ4) {
         int plen = (clen >= 4) ? (int)((uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24)) : -1;
         got = (plen == ulen) ? lz4_decompress_warp(src + 4, clen - 4, dst, ulen, lane) : -1;
-    } else if (comp == COMP_SNAPPY) {
+    } else if (comp_is_snappy(comp)) {
         got = snappy_decompress_warp(src, clen, dst, ulen, lane);
     } else {
         got = (clen == ulen) ? ulen : -1;

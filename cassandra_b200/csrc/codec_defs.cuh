@@ -4,11 +4,12 @@
 
 namespace b200c {
 
-enum { COMP_NONE = 0, COMP_LZ4 = 1, COMP_SNAPPY = 2 };
+enum { COMP_NONE = 0, COMP_LZ4 = 1, COMP_SNAPPY = 2, COMP_SNAPPY15 = 3 };      // SNAPPY15: hash table of up to 2^15 entries (snappy >= 1.2.0)
+__host__ __device__ __forceinline__ bool comp_is_snappy(int c) { return c == COMP_SNAPPY || c == COMP_SNAPPY15; }
 
 __host__ __device__ __forceinline__ int chunk_max_compressed(int comp, int chunk_len) {
     if (comp == COMP_LZ4) return 4 + (chunk_len + chunk_len / 255 + 16);
-    if (comp == COMP_SNAPPY) return (32 + chunk_len + chunk_len / 6);
+    if (comp_is_snappy(comp)) return (32 + chunk_len + chunk_len / 6);
     return chunk_len;
 }
 __host__ __device__ __forceinline__ int chunk_slot_stride(int comp, int chunk_len) {

@@ -796,7 +796,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (in.chunk_len <= 0 || in.chunk_len > 65536 || (in.chunk_len & (in.chunk_len - 1))) { c->err = "input chunk_len"; return B200C_EUNSUPPORTED; }
         if (in.ncolumns < 0 || in.ncolumns >= 64) { c->err = "input columns"; return B200C_EUNSUPPORTED; }
         if (in.nchunks != (in.data_length + in.chunk_len - 1) / (uint64_t)in.chunk_len) { c->err = "chunk count does not match data_length"; return B200C_EINVAL; }
-        if (in.compressor != COMP_LZ4 && in.compressor != COMP_SNAPPY && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
+        if (in.compressor != COMP_LZ4 && !comp_is_snappy(in.compressor) && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
         ubase[i] = uo; uo += (in.data_length + 64 + 65535) & ~65535ull;
         ibase[i] = io; io += (in.index_len + 64 + 255) & ~255ull;
         cbase[i] = co; co += (in.data_len + 64 + 255) & ~255ull;

@@ -60,7 +60,7 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
         B200C_LAUNCH(c, k_compress_chunks_lz4_direct, (unsigned)nchunks, 32, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
         return B200C_OK;
     }
-    int tab_bytes = comp == COMP_SNAPPY ? 32768 : 16384;
+    int tab_bytes = comp == COMP_SNAPPY15 ? 65536 : (comp == COMP_SNAPPY ? 32768 : 16384);
     size_t smem = (size_t)tab_bytes + chunk_len + 16;
     B200C_LAUNCH(c, k_compress_chunks, (unsigned)nchunks, 32, smem, c->d_tables, comp, tab_bytes, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
     return B200C_OK;
@@ -258,7 +258,7 @@ b200c_ctx* b200c_create(int device, size_t workspace_bytes) {
     delete h;
     c->h_pinned_cap = 1 << 16;
     if (cudaMallocHost(&c->h_pinned, c->h_pinned_cap) != cudaSuccess) { cudaFree(c->d_tables); delete c; return nullptr; }
-    cudaFuncSetAttribute(k_compress_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 65536 + 16);
+    cudaFuncSetAttribute(k_compress_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 65536 + 16);
     (void)workspace_bytes;
     return c;
 }
@@ -324,7 +324,7 @@ int b200c_initial_compressed_buffer_length(int comp, int chunk_len) { return chu
 
 static int check_codec_args(b200c_ctx* c, int comp, int chunk_len) {
     if (!c) return B200C_EINVAL;
-    if (comp != COMP_LZ4 && comp != COMP_SNAPPY && comp != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
+    if (comp != COMP_LZ4 && !comp_is_snappy(comp) && comp != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
     if (chunk_len <= 0 || chunk_len > 65536 || (chunk_len & (chunk_len - 1))) { c->err = "chunk_len must be a power of two <= 64 KiB"; return B200C_EUNSUPPORTED; }
     return B200C_OK;
 }
@@ -402,7 +402,7 @@ int b200c_compress(b200c_ctx* c, int comp, const uint8_t* in, int n, uint8_t* ou
     int chunk_len = 1; while (chunk_len < n) chunk_len <<= 1;
     if (n == 0) {   // degenerate: LZ4 of nothing = length prefix + one empty-literal token; Snappy = varint 0
         if (comp == COMP_LZ4) { if (out_cap < 5) return B200C_ETOOSMALL; memset(out, 0, 5); return 5; }
-        if (comp == COMP_SNAPPY) { if (out_cap < 1) return B200C_ETOOSMALL; out[0] = 0; return 1; }
+        if (comp_is_snappy(comp)) { if (out_cap < 1) return B200C_ETOOSMALL; out[0] = 0; return 1; }
         return 0;
     }
     std::vector<uint8_t> tmp(b200c_compress_bound(comp, n, chunk_len));
@@ -420,7 +420,7 @@ int b200c_uncompress(b200c_ctx* c, int comp, const uint8_t* in, int n, uint8_t* 
     if (!c || !in || n <= 0 || out_cap < 0) return B200C_EINVAL;
     int ulen;
     if (comp == COMP_LZ4) { if (n < 4) { c->err = "truncated"; return B200C_ECORRUPT; } ulen = (int)((uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 24)); }
-    else if (comp == COMP_SNAPPY) { uint32_t v = 0; int sh = 0, i = 0; bool ok = false; for (; i < n && i < 5; i++) { v |= (uint32_t)(in[i] & 0x7f) << sh; if (!(in[i] & 0x80)) { ok = true; break; } sh += 7; } if (!ok) { c->err = "bad varint"; return B200C_ECORRUPT; } ulen = (int)v; }
+    else if (comp_is_snappy(comp)) { uint32_t v = 0; int sh = 0, i = 0; bool ok = false; for (; i < n && i < 5; i++) { v |= (uint32_t)(in[i] & 0x7f) << sh; if (!(in[i] & 0x80)) { ok = true; break; } sh += 7; } if (!ok) { c->err = "bad varint"; return B200C_ECORRUPT; } ulen = (int)v; }
     else ulen = n;
     if (ulen < 0 || ulen > 65536) { c->err = "single-buffer uncompress is limited to 64 KiB"; return B200C_ECORRUPT; }
     if (ulen > out_cap) { c->err = "output buffer too small"; return B200C_ETOOSMALL; }

@@ -1,6 +1,7 @@
 // snappy.cuh — Snappy raw-format codec for one chunk per warp (S/io/compress/SnappyCompressor.java:77-105).
-// Third-party algorithm: snappy 1.1.10 (snappy-java 1.1.10.4), portable multiply hash. PARITY UNPINNED against the
-// reference (no Snappy-compressed fixture exists); parity is against oracle/codec.cc's restatement.
+// Third-party algorithm: Google snappy (snappy-java 1.1.10.4 bundles 1.1.10), portable multiply hash. The reference holds no
+// Snappy-compressed fixture; byte parity is pinned against the library itself in its >= 1.2.0 generation (max_bits = 15,
+// tests/golden/snappy), the 1.1.x generation (max_bits = 14) differing only in kMaxHashTableBits.
 // Round-1 implementation: the greedy matcher runs on lane 0 (sequential), copies and decompression use the whole warp.
 #pragma once
 #include "common.cuh"
@@ -9,7 +10,7 @@ namespace b200c {
 
 __host__ __device__ __forceinline__ int snappy_max_compressed_length(int n) { return 32 + n + n / 6; }
 
-__device__ __forceinline__ uint32_t snappy_tidx(uint32_t bytes, uint32_t tmask) { return ((0x1e35a7bdu * bytes) >> (32 - 14)) & tmask; }
+__device__ __forceinline__ uint32_t snappy_tidx(uint32_t bytes, uint32_t tmask, int max_bits) { return ((0x1e35a7bdu * bytes) >> (32 - max_bits)) & tmask; }
 
 __device__ __forceinline__ int snappy_emit_literal(uint8_t* out, int op, const uint8_t* lit, int len) {
     int n = len - 1;
@@ -41,7 +42,7 @@ __device__ __forceinline__ int snappy_emit_copy(uint8_t* out, int op, int offset
 }
 
 // one fragment (<= 64 KiB). s_in 4-byte aligned with >= 8 bytes of zeroed slack. Sequential; call from a single lane.
-__device__ int snappy_compress_fragment_seq(const uint8_t* s_in, int base, int input_size, uint16_t* s_tab, int table_size, uint8_t* out, int op) {
+__device__ int snappy_compress_fragment_seq(const uint8_t* s_in, int base, int input_size, uint16_t* s_tab, int table_size, int max_bits, uint8_t* out, int op) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     const uint32_t tmask = (uint32_t)table_size - 1;
     int ip = base; const int ip_end = base + input_size;
@@ -55,7 +56,7 @@ __device__ int snappy_compress_fragment_seq(const uint8_t* s_in, int base, int i
                 int delta = ip - base;
                 for (int i = 0; i < 16; i++) {
                     uint32_t dword = rd32_at(in32, ip + i);
-                    uint32_t e = snappy_tidx(dword, tmask);
+                    uint32_t e = snappy_tidx(dword, tmask, max_bits);
                     candidate = base + s_tab[e];
                     s_tab[e] = (uint16_t)(delta + i);
                     if (rd32_at(in32, candidate) == dword) {
@@ -69,7 +70,7 @@ __device__ int snappy_compress_fragment_seq(const uint8_t* s_in, int base, int i
             if (!found) {
                 for (;;) {
                     uint32_t data = rd32_at(in32, ip);
-                    uint32_t e = snappy_tidx(data, tmask);
+                    uint32_t e = snappy_tidx(data, tmask, max_bits);
                     uint32_t between = skip >> 5; skip += between;
                     int next_ip = ip + (int)between;
                     if (next_ip > ip_limit) { ip = next_emit; goto emit_remainder; }
@@ -87,8 +88,8 @@ __device__ int snappy_compress_fragment_seq(const uint8_t* s_in, int base, int i
                 ip += matched;
                 op = snappy_emit_copy(out, op, b0 - candidate, matched, lt12);
                 if (ip >= ip_limit) goto emit_remainder;
-                s_tab[snappy_tidx(rd32_at(in32, ip - 1), tmask)] = (uint16_t)(ip - base - 1);
-                uint32_t e = snappy_tidx(rd32_at(in32, ip), tmask);
+                s_tab[snappy_tidx(rd32_at(in32, ip - 1), tmask, max_bits)] = (uint16_t)(ip - base - 1);
+                uint32_t e = snappy_tidx(rd32_at(in32, ip), tmask, max_bits);
                 candidate = base + s_tab[e];
                 s_tab[e] = (uint16_t)(ip - base);
             } while (rd32_at(in32, ip) == rd32_at(in32, candidate));
@@ -99,8 +100,8 @@ emit_remainder:
     return op;
 }
 
-// s_tab: 16384 x u16. Returns compressed size (warp-uniform).
-__device__ int snappy_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, uint8_t* out, int lane) {
+// s_tab: (1 << max_bits) x u16. Returns compressed size (warp-uniform).
+__device__ int snappy_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, int max_bits, uint8_t* out, int lane) {
     int op = 0;
     {   uint32_t v = (uint32_t)n; uint8_t pre[5]; int k = 0;
         while (v >= 0x80) { pre[k++] = (uint8_t)(v | 0x80); v >>= 7; } pre[k++] = (uint8_t)v;
@@ -108,10 +109,10 @@ __device__ int snappy_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab,
         op = k; }
     for (int pos = 0; pos < n; pos += 65536) {
         int frag = min(n - pos, 65536);
-        int table_size = frag > 16384 ? 16384 : (frag < 256 ? 256 : (2 << (31 - __clz(frag - 1))));
+        int table_size = frag > (1 << max_bits) ? (1 << max_bits) : (frag < 256 ? 256 : (2 << (31 - __clz(frag - 1))));
         for (int i = lane; i < table_size / 2; i += 32) ((uint32_t*)s_tab)[i] = 0;
         __syncwarp();
-        if (lane == 0) op = snappy_compress_fragment_seq(s_in, pos, frag, s_tab, table_size, out, op);
+        if (lane == 0) op = snappy_compress_fragment_seq(s_in, pos, frag, s_tab, table_size, max_bits, out, op);
         op = __shfl_sync(FULL_MASK, op, 0);
         __syncwarp();
     }

@@ -5,7 +5,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200compact.so")
 
 OK, EINVAL, ECUDA, ECORRUPT, ECANCELLED, EUNSUPPORTED, ENOMEM, ETOOSMALL = 0, -1, -2, -3, -4, -5, -6, -7
-COMP_NONE, COMP_LZ4, COMP_SNAPPY = 0, 1, 2
+COMP_NONE, COMP_LZ4, COMP_SNAPPY, COMP_SNAPPY15 = 0, 1, 2, 3
 FLAG_DEVICE_PTRS = 1
 INT32_MAX = 0x7FFFFFFF
 MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS = 8, 64, 64

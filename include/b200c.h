@@ -45,7 +45,10 @@ enum {
     B200C_ETOOSMALL = -7      /* a caller-provided output buffer is too small; required sizes are reported */
 };
 
-enum { B200C_COMP_NONE = 0, B200C_COMP_LZ4 = 1, B200C_COMP_SNAPPY = 2 };
+/* SNAPPY: raw snappy as snappy-java 1.1.10.4 / Google snappy 1.1.x writes it (hash table of at most 2^14 entries). SNAPPY15: the same format
+ * written by Google snappy >= 1.2.0 (hash table of at most 2^15 entries: different, equally valid bytes; what newer snappy-java bundles, and the
+ * generation tests/golden/snappy pins against the real library). Decompression is identical for both. */
+enum { B200C_COMP_NONE = 0, B200C_COMP_LZ4 = 1, B200C_COMP_SNAPPY = 2, B200C_COMP_SNAPPY15 = 3 };
 /* IPartitioner of the table (ValidationMetadata.partitioner, S/io/sstable/metadata/ValidationMetadata.java): decides the partition
  * order every input must already be in and the output is written in (DecoratedKey.compareTo, S/db/DecoratedKey.java:79-91).
  *   MURMUR3       S/dht/Murmur3Partitioner.java:256-296 — signed 64-bit token, ties by unsigned key bytes

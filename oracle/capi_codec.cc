@@ -13,7 +13,7 @@ int      orc_lz4_compress_bound(int n) { return lz4_compress_bound(n); }
 int      orc_lz4_compress_block(const uint8_t* s, int n, uint8_t* d, int cap) { return lz4_compress_block(s, n, d, cap); }
 int      orc_lz4_decompress_block(const uint8_t* s, int n, uint8_t* d, int cap) { return lz4_decompress_block(s, n, d, cap); }
 int      orc_snappy_max_compressed_length(int n) { return snappy_max_compressed_length(n); }
-int      orc_snappy_compress(const uint8_t* s, int n, uint8_t* d) { return snappy_compress(s, n, d); }
+int      orc_snappy_compress(const uint8_t* s, int n, uint8_t* d) { return snappy_compress(s, n, d, 14); }
 int      orc_snappy_decompress(const uint8_t* s, int n, uint8_t* d, int cap) { return snappy_decompress(s, n, d, cap); }
 int      orc_chunk_max_compressed(int c, int n) { return chunk_max_compressed(c, n); }
 int      orc_chunk_compress(int c, const uint8_t* s, int n, uint8_t* d) { return chunk_compress(c, s, n, d); }

@@ -304,9 +304,11 @@ int lz4_decompress_block(const uint8_t* src, int n, uint8_t* dst, int cap) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Snappy raw format. Third-party arithmetic: snappy-java 1.1.10.4 → snappy 1.1.10 (portable multiply hash).
-// PARITY UNPINNED: the reference holds no Snappy-compressed fixture and this image has no libsnappy; this is a
-// restatement of the published CompressFragment/EmitLiteral/EmitCopy algorithm. Format round-trip is tested.
+// Snappy raw format. Third-party arithmetic: snappy-java 1.1.10.4 → snappy 1.1.10 (portable multiply hash); a restatement of the
+// published CompressFragment / EmitLiteral / EmitCopy / FindMatchLength algorithm. The reference holds no Snappy-compressed fixture
+// (SURVEY §8c), so parity is pinned against Google's library itself: with kMaxHashTableBits = 15 (snappy >= 1.2.0, the generation
+// bundled in this image's pyarrow) this code reproduces the library byte for byte on tests/golden/snappy/vectors.json and in a live
+// differential test (tests/test_snappy_golden.py); the 1.1.10 generation differs only in that constant (14, snappy.h of 1.1.10).
 // Call site S/io/compress/SnappyCompressor.java:77-105.
 // ------------------------------------------------------------------------------------------------
 int snappy_max_compressed_length(int n) { return 32 + n + n / 6; }
@@ -339,9 +341,12 @@ static inline uint8_t* snappy_emit_copy(uint8_t* op, size_t offset, size_t len, 
     if (len > 64) { op = snappy_emit_copy_upto64(op, offset, 60, false); len -= 60; }
     return snappy_emit_copy_upto64(op, offset, len, len < 12);
 }
+// HashBytes: ((kMagic * bytes) >> (32 - kMaxHashTableBits)) & mask. kMaxHashTableBits is 14 in snappy 1.1.x (what snappy-java 1.1.10.4
+// bundles: COMP_SNAPPY) and 15 from snappy 1.2.0 on (COMP_SNAPPY15) — the only difference between the two generations' compressors.
+static thread_local int t_snappy_max_bits = 14;
 static inline uint32_t snappy_table_index(uint32_t bytes, uint32_t tmask) {
     const uint32_t kMagic = 0x1e35a7bd;
-    return ((kMagic * bytes) >> (32 - 14)) & tmask;      // kMaxHashTableBits = 14
+    return ((kMagic * bytes) >> (32 - t_snappy_max_bits)) & tmask;
 }
 static uint8_t* snappy_compress_fragment(const uint8_t* input, size_t input_size, uint8_t* op, uint16_t* table, int table_size) {
     const uint8_t* ip = input;
@@ -411,17 +416,18 @@ emit_remainder:
     if (ip < ip_end) op = snappy_emit_literal(op, ip, ip_end - ip);
     return op;
 }
-int snappy_compress(const uint8_t* src, int n, uint8_t* dst) {
+int snappy_compress(const uint8_t* src, int n, uint8_t* dst, int max_table_bits) {
+    t_snappy_max_bits = max_table_bits;
     uint8_t* op = dst;
     uint32_t v = (uint32_t)n;                                   // varint32 preamble (little-endian base-128)
     while (v >= 0x80) { *op++ = (uint8_t)(v | 0x80); v >>= 7; }
     *op++ = (uint8_t)v;
-    static thread_local uint16_t table[1 << 14];
+    static thread_local uint16_t table[1 << 15];
     size_t pos = 0;
     while (pos < (size_t)n) {
         size_t frag = (size_t)n - pos; if (frag > 65536) frag = 65536;
         int table_size;
-        if (frag > (1u << 14)) table_size = 1 << 14;
+        if (frag > (1u << max_table_bits)) table_size = 1 << max_table_bits;
         else if (frag < (1u << 8)) table_size = 1 << 8;
         else table_size = 2 << (31 - __builtin_clz((uint32_t)(frag - 1)));
         memset(table, 0, table_size * sizeof(uint16_t));
@@ -471,7 +477,7 @@ int snappy_decompress(const uint8_t* src, int n, uint8_t* dst, int cap) {
 // ------------------------------------------------------------------------------------------------
 int chunk_max_compressed(int compressor, int chunk_len) {
     if (compressor == COMP_LZ4) return 4 + lz4_compress_bound(chunk_len);       // initialCompressedBufferLength :108-111
-    if (compressor == COMP_SNAPPY) return snappy_max_compressed_length(chunk_len);
+    if (compressor == COMP_SNAPPY || compressor == COMP_SNAPPY15) return snappy_max_compressed_length(chunk_len);
     return chunk_len;
 }
 int chunk_compress(int compressor, const uint8_t* src, int n, uint8_t* dst) {
@@ -480,7 +486,8 @@ int chunk_compress(int compressor, const uint8_t* src, int n, uint8_t* dst) {
         int c = lz4_compress_block(src, n, dst + 4, lz4_compress_bound(n));
         return c <= 0 ? -1 : 4 + c;
     }
-    if (compressor == COMP_SNAPPY) return snappy_compress(src, n, dst);
+    if (compressor == COMP_SNAPPY) return snappy_compress(src, n, dst, 14);
+    if (compressor == COMP_SNAPPY15) return snappy_compress(src, n, dst, 15);
     memcpy(dst, src, n); return n;
 }
 int chunk_decompress(int compressor, const uint8_t* src, int n, uint8_t* dst, int cap) {
@@ -491,7 +498,7 @@ int chunk_decompress(int compressor, const uint8_t* src, int n, uint8_t* dst, in
         int w = lz4_decompress_block(src + 4, n - 4, dst, ulen);
         return (w == ulen) ? ulen : -1;                                          // "Decompressed lengths mismatch" :161-164
     }
-    if (compressor == COMP_SNAPPY) return snappy_decompress(src, n, dst, cap);
+    if (compressor == COMP_SNAPPY || compressor == COMP_SNAPPY15) return snappy_decompress(src, n, dst, cap);
     if (n > cap) return -1;
     memcpy(dst, src, n); return n;
 }

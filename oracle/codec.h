@@ -37,12 +37,12 @@ int      lz4_decompress_block(const uint8_t* src, int n, uint8_t* dst, int cap);
 
 // ---- Snappy raw format (third-party: org.xerial.snappy:snappy-java 1.1.10.4 → snappy 1.1.10). PARITY UNPINNED (no golden, no lib).
 int      snappy_max_compressed_length(int n);
-int      snappy_compress(const uint8_t* src, int n, uint8_t* dst);
+int      snappy_compress(const uint8_t* src, int n, uint8_t* dst, int max_table_bits = 14);
 int      snappy_uncompressed_length(const uint8_t* src, int n);
 int      snappy_decompress(const uint8_t* src, int n, uint8_t* dst, int cap);
 
 // ---- chunk codec as ICompressor sees it: S/io/compress/LZ4Compressor.java:113-190, SnappyCompressor.java:77-105
-enum Compressor { COMP_LZ4 = 1, COMP_SNAPPY = 2, COMP_NONE = 0 };
+enum Compressor { COMP_LZ4 = 1, COMP_SNAPPY = 2, COMP_SNAPPY15 = 3, COMP_NONE = 0 };
 int      chunk_max_compressed(int compressor, int chunk_len);
 int      chunk_compress(int compressor, const uint8_t* src, int n, uint8_t* dst);
 int      chunk_decompress(int compressor, const uint8_t* src, int n, uint8_t* dst, int cap);

@@ -35,7 +35,7 @@ def lib():
         _LIB = L
     return _LIB
 
-COMP_LZ4, COMP_SNAPPY = 1, 2
+COMP_LZ4, COMP_SNAPPY, COMP_SNAPPY15 = 1, 2, 3
 
 def lz4_compress(b: bytes) -> bytes:
     L = lib(); cap = L.orc_lz4_compress_bound(len(b)); out = C.create_string_buffer(cap)

@@ -120,3 +120,19 @@ def test_large_stream_properties(ctx):
         assert struct.unpack(">I", image[end - 4:end])[0] == zlib.crc32(image[offs[i]:end - 4])
         assert image[offs[i]:end - 4] == O.chunk_compress(O.COMP_LZ4, stream[i * 16384:(i + 1) * 16384])
     assert ctx.decompress_chunks(native.COMP_LZ4, image, offs, len(stream), 16384) == stream
+
+def test_snappy_equals_googles_library_on_the_golden_vectors(ctx):
+    """tests/golden/snappy/vectors.json holds what Google's snappy library (>= 1.2.0 generation) produced; the GPU compressor in that
+    generation (B200C_COMP_SNAPPY15) must give the same bytes, and both generations must round-trip through the GPU decompressor"""
+    from cassandra_b200 import native
+    from test_snappy_golden import vectors
+    for name, data, want in vectors():
+        if not data: continue
+        cl = 1
+        while cl < len(data): cl <<= 1
+        image, offs, digest = ctx.compress_chunks(native.COMP_SNAPPY15, data, cl)
+        assert image[:-4] == want, name
+        assert ctx.decompress_chunks(native.COMP_SNAPPY15, image, offs, len(data), cl) == data, name
+        img14, offs14, _ = ctx.compress_chunks(native.COMP_SNAPPY, data, cl)
+        assert img14[:-4] == O.chunk_compress(O.COMP_SNAPPY, data), name
+        assert ctx.decompress_chunks(native.COMP_SNAPPY, img14, offs14, len(data), cl) == data, name

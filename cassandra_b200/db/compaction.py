@@ -35,9 +35,23 @@ class OutputSSTable:
     def __init__(self, data, index, compression, digest, partitions, rows):
         self.data = data; self.index = index; self.compression = compression; self.digest = digest
         self.partitions = partitions; self.rows = rows
+        self.filter = self.summary = self.first_key = self.last_key = None; self.stats = None
     def components(self):
-        return {"Data.db": self.data, "Index.db": self.index, "CompressionInfo.db": self.compression.serialize(),
-                "Digest.crc32": str(self.digest).encode()}
+        c = {"Data.db": self.data, "Index.db": self.index, "CompressionInfo.db": self.compression.serialize(),
+             "Digest.crc32": str(self.digest).encode()}
+        if self.filter is not None: c["Filter.db"] = self.filter
+        if self.summary is not None: c["Summary.db"] = self.summary
+        return c
+
+STATS_SCALARS = ("min_timestamp", "max_timestamp", "min_local_deletion_time", "max_local_deletion_time", "min_ttl", "max_ttl", "total_rows",
+                 "total_columns_set", "total_cells", "total_tombstones", "has_partition_level_deletions", "tdrop_overflow")
+def stats_dict(st):
+    """b200c_sstable_stats -> plain dict (the MetadataCollector reductions, S/io/sstable/metadata/MetadataCollector.java:107-147)"""
+    d = {k: int(getattr(st, k)) for k in STATS_SCALARS}
+    d["partition_size_hist"] = [int(x) for x in st.partition_size_hist]; d["cells_per_partition_hist"] = [int(x) for x in st.cells_per_partition_hist]
+    d["tombstone_drop_times"] = [(int(st.tdrop_point[i]), int(st.tdrop_count[i])) for i in range(st.ntdrop)]
+    d["hll_registers"] = bytes(st.hll_registers)
+    return d
 
 def merged_encoding_stats(inputs):
     """SerializationHeader.make: EncodingStats.Collector over the inputs' StatsMetadata minima (S/db/rows/EncodingStats.java:150-236)."""
@@ -52,11 +66,14 @@ def _name_key(name: bytes): return name                              # ColumnMet
 
 class CompactionTask:
     def __init__(self, inputs, controller: CompactionController, compression=None, column_index_size=65536,
-                 max_sstable_bytes=0, token_range=(INT64_MIN, INT64_MAX)):
+                 max_sstable_bytes=0, token_range=(INT64_MIN, INT64_MAX), bloom=None, min_index_interval=128, with_metadata=False):
         self.inputs = list(inputs); self.controller = controller
         c0 = self.inputs[0].compression
         self.compression = compression or CompressionMetadata(c0.compressor_name, c0.chunk_length, c0.max_compressed_length, 0, [])
         self.column_index_size = column_index_size; self.max_sstable_bytes = max_sstable_bytes; self.token_range = token_range
+        # with_metadata: also produce Filter.db, Summary.db, first/last key and the Statistics.db side band. bloom = (hash count,
+        # 64-bit words) as FilterFactory would size the filter (io.sstable.bloom_geometry(estimated keys, fp chance)); None = 0.01 over the input keys
+        self.with_metadata = with_metadata or bloom is not None; self.bloom = bloom; self.min_index_interval = min_index_interval
         self._keep = []
 
     def build_manifest(self):
@@ -115,6 +132,9 @@ class CompactionTask:
             hi = np.asarray([a for a, _ in pr], dtype=np.int64); ts = np.asarray([b for _, b in pr], dtype=np.int64); self._keep += [hi, ts]
             m.npurge_ranges = len(pr); m.purge_range_hi = hi.ctypes.data; m.purge_range_max_ts = ts.ctypes.data
         m.token_lo, m.token_hi = self.token_range; m.max_sstable_bytes = self.max_sstable_bytes
+        if self.with_metadata:
+            k, words = self.bloom if self.bloom is not None else sst.bloom_geometry(max(1, sum(getattr(i, "partitions", 0) or 1 for i in ins)), 0.01)
+            m.bloom_hash_count, m.bloom_words, m.min_index_interval = k, words, self.min_index_interval
         self.out_columns = out_cols
         return m
 
@@ -127,11 +147,16 @@ class CompactionTask:
         data_cap = native.lib().b200c_compress_bound(self.compression.compressor_id, total_in + 1024, cl) if engine.needs_lib_bound else total_in * 2 + (1 << 20)
         index_cap = sum(len(i.index) for i in self.inputs) * 2 + (1 << 16)
         chunk_cap = total_in // cl + 16
-        res = native.Result(); outs = (native.Output * nout)(); bufs = []
+        res = native.Result(); outs = (native.Output * nout)(); bufs = []; extra = []
         for o in outs:
             d = np.empty(data_cap, dtype=np.uint8); ix = np.empty(index_cap, dtype=np.uint8); co = np.zeros(chunk_cap, dtype=np.uint64)
             bufs.append((d, ix, co))
             o.data, o.data_cap, o.index, o.index_cap, o.chunk_offsets, o.chunk_cap = d.ctypes.data, data_cap, ix.ctypes.data, index_cap, co.ctypes.data, chunk_cap
+            if self.with_metadata:
+                kb = np.zeros(2 * 65535, dtype=np.uint8); fl = np.zeros(8 + 8 * int(m.bloom_words), dtype=np.uint8); sm = np.zeros(index_cap // 8 + (1 << 16), dtype=np.uint8)
+                st = native.SSTableStats(); extra.append((kb, fl, sm, st))
+                o.key_buf, o.key_cap, o.filter, o.filter_cap, o.summary, o.summary_cap = kb.ctypes.data, len(kb), fl.ctypes.data, len(fl), sm.ctypes.data, len(sm)
+                o.stats = C.pointer(st)
         res.noutputs_cap = nout; res.outputs = outs
         t0 = time.perf_counter()
         engine(m, res)
@@ -141,7 +166,12 @@ class CompactionTask:
             o = outs[k]; d, ix, co = bufs[k]
             meta = CompressionMetadata(self.compression.compressor_name, cl, self.compression.max_compressed_length, int(o.data_length),
                                        [int(x) for x in co[:o.nchunks]], self.compression.options)
-            r.outputs.append(OutputSSTable(d[:o.data_len].tobytes(), ix[:o.index_len].tobytes(), meta, int(o.digest), int(o.partitions), int(o.rows)))
+            out = OutputSSTable(d[:o.data_len].tobytes(), ix[:o.index_len].tobytes(), meta, int(o.digest), int(o.partitions), int(o.rows))
+            if self.with_metadata:
+                kb, fl, sm, st = extra[k]
+                out.first_key = kb[:o.first_key_len].tobytes(); out.last_key = kb[o.first_key_len:o.first_key_len + o.last_key_len].tobytes()
+                out.filter = fl[:o.filter_len].tobytes(); out.summary = sm[:o.summary_len].tobytes(); out.stats = stats_dict(st)
+            r.outputs.append(out)
         r.stats = dict(bytes_read=int(res.bytes_read), bytes_in_range=int(res.bytes_in_range), bytes_written=int(res.bytes_written), total_source_rows=int(res.total_source_rows),
                        input_partitions=int(res.input_partitions), merged_row_counts=[int(x) for x in res.merged_row_counts[:len(self.inputs)]],
                        kernel_ms=res.kernel_ms, total_ms=res.total_ms, kernel_launches=int(res.kernel_launches), index_slow_path_inputs=int(res.index_slow_path_inputs), wall_s=wall)

@@ -46,6 +46,41 @@ PARTITIONER_IDS = {"org.apache.cassandra.dht.Murmur3Partitioner": native.PARTITI
 
 CLUSTERING_OK = {"LongType", "TimestampType", "DateType", "Int32Type", "ShortType", "ByteType", "UTF8Type", "AsciiType", "BytesType"}
 
+# ---- Filter.db geometry: FilterFactory.getFilter(numElements, fpChance) (S/utils/FilterFactory.java:60-75) over BloomCalculations
+# (S/utils/BloomCalculations.java:38-160). PROBS[buckets per element][K] = false-positive probability (published table, Cao et al.).
+BLOOM_PROBS = [
+    [1.0], [1.0, 1.0], [1.0, 0.393, 0.400], [1.0, 0.283, 0.237, 0.253], [1.0, 0.221, 0.155, 0.147, 0.160],
+    [1.0, 0.181, 0.109, 0.092, 0.092, 0.101], [1.0, 0.154, 0.0804, 0.0609, 0.0561, 0.0578, 0.0638],
+    [1.0, 0.133, 0.0618, 0.0423, 0.0359, 0.0347, 0.0364], [1.0, 0.118, 0.0489, 0.0306, 0.024, 0.0217, 0.0216, 0.0229],
+    [1.0, 0.105, 0.0397, 0.0228, 0.0166, 0.0141, 0.0133, 0.0135, 0.0145], [1.0, 0.0952, 0.0329, 0.0174, 0.0118, 0.00943, 0.00844, 0.00819, 0.00846],
+    [1.0, 0.0869, 0.0276, 0.0136, 0.00864, 0.0065, 0.00552, 0.00513, 0.00509], [1.0, 0.08, 0.0236, 0.0108, 0.00646, 0.00459, 0.00371, 0.00329, 0.00314],
+    [1.0, 0.074, 0.0203, 0.00875, 0.00492, 0.00332, 0.00255, 0.00217, 0.00199, 0.00194],
+    [1.0, 0.0689, 0.0177, 0.00718, 0.00381, 0.00244, 0.00179, 0.00146, 0.00129, 0.00121, 0.0012],
+    [1.0, 0.0645, 0.0156, 0.00596, 0.003, 0.00183, 0.00128, 0.001, 0.000852, 0.000775, 0.000744],
+    [1.0, 0.0606, 0.0138, 0.005, 0.00239, 0.00139, 0.000935, 0.000702, 0.000574, 0.000505, 0.00047, 0.000459],
+    [1.0, 0.0571, 0.0123, 0.00423, 0.00193, 0.00107, 0.000692, 0.000499, 0.000394, 0.000335, 0.000302, 0.000287, 0.000284],
+    [1.0, 0.054, 0.0111, 0.00362, 0.00158, 0.000839, 0.000519, 0.00036, 0.000275, 0.000226, 0.000198, 0.000183, 0.000176],
+    [1.0, 0.0513, 0.00998, 0.00312, 0.0013, 0.000663, 0.000394, 0.000264, 0.000194, 0.000155, 0.000132, 0.000118, 0.000111, 0.000109],
+    [1.0, 0.0488, 0.00906, 0.0027, 0.00108, 0.00053, 0.000303, 0.000196, 0.00014, 0.000108, 8.89e-05, 7.77e-05, 7.12e-05, 6.79e-05, 6.71e-05]]
+
+def bloom_geometry(num_elements: int, fp_chance: float):
+    """-> (hash_count, words): K hash functions over an OffHeapBitSet of `words` 64-bit words, or (0, 0) for fpChance 1.0 (AlwaysPresent)."""
+    if fp_chance >= 1.0: return 0, 0
+    probs = BLOOM_PROBS
+    optk = []
+    for row in probs:
+        best = min(range(len(row)), key=lambda j: (row[j], j)); optk.append(max(1, best))
+    max_buckets = min(len(probs) - 1, int(((1 << 63) - 1 - 20) / max(1, num_elements)))
+    max_k = len(probs[max_buckets]) - 1
+    if fp_chance >= probs[2][1]: k, buckets = 2, optk[2]                      # (the reference returns BloomSpecification(2, optK[2]) here, as is)
+    else:
+        if fp_chance < probs[max_buckets][max_k]: raise ValueError("fp chance not satisfiable")
+        buckets = 2; k = optk[2]
+        while probs[buckets][k] > fp_chance: buckets += 1; k = optk[buckets]
+        while probs[buckets][k - 1] <= fp_chance: k -= 1
+    num_bits = num_elements * buckets + 20                                     # FilterFactory.createFilter: BITSET_EXCESS
+    return k, ((num_bits - 1) >> 6) + 1                                        # OffHeapBitSet(numBits): words
+
 def parse_statistics(b: bytes):
     (n,) = struct.unpack_from(">i", b, 0)
     toc = {}
@@ -61,11 +96,30 @@ def parse_statistics(b: bytes):
     p = toc[2]
     for _ in range(2):                                 # two EstimatedHistograms
         (sz,) = struct.unpack_from(">i", b, p); p += 4 + 16 * sz
+    hists = []
+    q = toc[2]
+    for _ in range(2):                                 # EstimatedHistogram.serializer: i32 n | (i64 offset, i64 count) x n  (offset of bucket i = offsets[i-1], first = offsets[0])
+        (sz,) = struct.unpack_from(">i", b, q); q += 4
+        hists.append([struct.unpack_from(">qq", b, q + 16 * i)[1] for i in range(sz)]); q += 16 * sz
+    out["partition_size_hist"], out["cells_per_partition_hist"] = hists
     p += 12                                            # CommitLogPosition
     mn_ts, mx_ts, mn_ldt, mx_ldt, mn_ttl, mx_ttl = struct.unpack_from(">qqIIii", b, p)
     out["min_timestamp"] = mn_ts; out["max_timestamp"] = mx_ts
     out["min_local_deletion_time"] = NO_DELETION_TIME if mn_ldt == 0xFFFFFFFF else mn_ldt
-    out["min_ttl"] = mn_ttl
+    out["max_local_deletion_time"] = NO_DELETION_TIME if mx_ldt == 0xFFFFFFFF else mx_ldt
+    out["min_ttl"] = mn_ttl; out["max_ttl"] = mx_ttl
+    q = p + 32
+    (out["compression_ratio"],) = struct.unpack_from(">d", b, q); q += 8
+    # TombstoneHistogram (oa: long points): i32 maxBinSize | i32 n | (i64 point, i32 count) x n ... versions differ; parsed defensively
+    try:
+        (_maxbin, n) = struct.unpack_from(">ii", b, q); q += 8
+        td = []
+        for _ in range(n):
+            pt, cnt = struct.unpack_from(">qi", b, q); q += 12; td.append((pt, cnt))
+        out["tombstone_drop_times"] = td
+        (out["sstable_level"], out["repaired_at"]) = struct.unpack_from(">iq", b, q); q += 12
+    except struct.error:
+        pass
     # HEADER (3)
     p = toc[3]
     v, p = _vint(b, p); hts = v + TIMESTAMP_EPOCH

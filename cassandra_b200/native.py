@@ -11,7 +11,7 @@ INT32_MAX = 0x7FFFFFFF
 MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS = 8, 64, 64
 ABI_VERSION = 2
 PARTITIONER_MURMUR3, PARTITIONER_BYTE_ORDERED = 0, 1
-PSIZE_BUCKETS, CELLS_BUCKETS, HLL_P, TDROP_CAP = 151, 115, 13, 512
+PSIZE_BUCKETS, CELLS_BUCKETS, HLL_P, TDROP_CAP = 156, 119, 13, 512
 TYPE_BYTES, TYPE_FIXED_SIGNED, TYPE_FIXED_BYTES, TYPE_VAR_SIGNED = 0, 1, 2, 3
 
 class B200CError(RuntimeError):

@@ -219,8 +219,8 @@ typedef struct b200c_manifest {
  * 183-258, and Rows.collectStats S/db/rows/Rows.java:102-113): the per-cell / per-row / per-partition reductions the Java side
  * needs to finish Statistics.db (StatsMetadata + CompactionMetadata) WITHOUT re-reading the output. Trackers that saw no value
  * hold MetadataCollector's defaults (timestamps: INT64_MIN / INT64_MAX; local deletion times: INT64_MAX both; TTLs: 0 both). */
-#define B200C_PSIZE_BUCKETS 151     /* EstimatedHistogram(150): 150 bucket offsets + overflow (S/utils/EstimatedHistogram.java:48-87) */
-#define B200C_CELLS_BUCKETS 115     /* EstimatedHistogram(114) */
+#define B200C_PSIZE_BUCKETS 156     /* EstimatedHistogram(155): 155 bucket offsets + overflow (MetadataCollector.defaultPartitionSizeHistogram :68-72) */
+#define B200C_CELLS_BUCKETS 119     /* EstimatedHistogram(118) (defaultCellPerPartitionCountHistogram :62-66) */
 #define B200C_HLL_P 13              /* HyperLogLogPlus(13, 25), MetadataCollector.java:139-145 */
 #define B200C_TDROP_CAP 512
 typedef struct b200c_sstable_stats {

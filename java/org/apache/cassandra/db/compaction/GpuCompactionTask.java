@@ -374,10 +374,10 @@ public class GpuCompactionTask extends CompactionTask
     private void writeStatistics(Descriptor d, TableMetadata table, SerializationHeader header, ByteBuffer s, ByteBuffer keys, ByteBuffer out, double ratio,
                                  Collection<SSTableReader> inputs, double fpChance) throws IOException
     {
-        long[] psizeOffsets = EstimatedHistogram.newOffsets(150, false), cellOffsets = EstimatedHistogram.newOffsets(114, false);
-        long[] psize = new long[151], cells = new long[115];
-        for (int i = 0; i < 151; i++) psize[i] = s.getLong(S_PARTITION_SIZE_HIST + 8 * i);
-        for (int i = 0; i < 115; i++) cells[i] = s.getLong(S_CELLS_HIST + 8 * i);
+        long[] psizeOffsets = EstimatedHistogram.newOffsets(155, false), cellOffsets = EstimatedHistogram.newOffsets(118, false);
+        long[] psize = new long[156], cells = new long[119];
+        for (int i = 0; i < 156; i++) psize[i] = s.getLong(S_PARTITION_SIZE_HIST + 8 * i);
+        for (int i = 0; i < 119; i++) cells[i] = s.getLong(S_CELLS_HIST + 8 * i);
         StreamingTombstoneHistogramBuilder th = new StreamingTombstoneHistogramBuilder(org.apache.cassandra.io.sstable.SSTable.TOMBSTONE_HISTOGRAM_BIN_SIZE,
                                                                                        org.apache.cassandra.io.sstable.SSTable.TOMBSTONE_HISTOGRAM_SPOOL_SIZE, 1);
         for (int i = 0; i < s.getInt(S_NTDROP); i++)                                   // points are already rounded to 60 s; replay them with their counts

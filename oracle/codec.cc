@@ -311,6 +311,23 @@ int lz4_decompress_block(const uint8_t* src, int n, uint8_t* dst, int cap) {
 // differential test (tests/test_snappy_golden.py); the 1.1.10 generation differs only in that constant (14, snappy.h of 1.1.10).
 // Call site S/io/compress/SnappyCompressor.java:77-105.
 // ------------------------------------------------------------------------------------------------
+// MurmurHash.hash2_64 (S/utils/MurmurHash.java:94-152): MurmurHash2 64-bit; the tail bytes are SIGN-extended (Java bytes), the block bytes are not
+uint64_t murmur2_64(const uint8_t* key, int length, uint64_t seed) {
+    const uint64_t m64 = 0xc6a4a7935bd1e995ull; const int r64 = 47;
+    uint64_t h64 = (seed & 0xffffffffull) ^ (m64 * (uint64_t)length);
+    int lenLongs = length >> 3;
+    for (int i = 0; i < lenLongs; i++) {
+        uint64_t k64 = 0; for (int b = 0; b < 8; b++) k64 += (uint64_t)key[i * 8 + b] << (8 * b);
+        k64 *= m64; k64 ^= k64 >> r64; k64 *= m64;
+        h64 ^= k64; h64 *= m64;
+    }
+    int rem = length & 7; const uint8_t* t = key + length - rem;
+    for (int i = rem - 1; i >= 1; i--) h64 ^= (uint64_t)(int64_t)(int8_t)t[i] << (8 * i);
+    if (rem >= 1) { h64 ^= (uint64_t)(int64_t)(int8_t)t[0]; h64 *= m64; }
+    h64 ^= h64 >> r64; h64 *= m64; h64 ^= h64 >> r64;
+    return h64;
+}
+
 int snappy_max_compressed_length(int n) { return 32 + n + n / 6; }
 
 static inline uint8_t* snappy_emit_literal(uint8_t* op, const uint8_t* lit, size_t len) {

@@ -37,6 +37,7 @@ int      lz4_decompress_block(const uint8_t* src, int n, uint8_t* dst, int cap);
 
 // ---- Snappy raw format (third-party: org.xerial.snappy:snappy-java 1.1.10.4 → snappy 1.1.10). PARITY UNPINNED (no golden, no lib).
 int      snappy_max_compressed_length(int n);
+uint64_t murmur2_64(const uint8_t* key, int length, uint64_t seed);
 int      snappy_compress(const uint8_t* src, int n, uint8_t* dst, int max_table_bits = 14);
 int      snappy_uncompressed_length(const uint8_t* src, int n);
 int      snappy_decompress(const uint8_t* src, int n, uint8_t* dst, int cap);

@@ -17,6 +17,8 @@
 #include <chrono>
 #include <climits>
 #include <memory>
+#include <map>
+#include <cmath>
 
 namespace oracle {
 
@@ -500,10 +502,116 @@ struct OutBuf { std::vector<uint8_t> b; void u8(uint8_t v) { b.push_back(v); } v
 static void write_partition_dt(OutBuf& o, const DT& d) { if (d.live()) o.u8(0x80); else { o.be64((uint64_t)d.mfda); o.be32((uint32_t)d.ldt); } }
 static int partition_dt_size(const DT& d) { return d.live() ? 1 : 12; }
 
+
+// ---- the rest of the sstable: what MetadataCollector, the bloom filter and the index summary builder gather while the
+// writer appends (S/io/sstable/format/SortedTableWriter.java:183-258). One Meta per output file. ---------------------------------------------
+static std::vector<int64_t> histogram_offsets(int size) {                 // EstimatedHistogram.newOffsets(size, false) S/utils/EstimatedHistogram.java:91-109
+    std::vector<int64_t> r(size); int64_t last = 1; r[0] = 1;
+    for (int i = 1; i < size; i++) { int64_t next = (int64_t)std::llround((double)last * 1.2); if (next == last) next++; r[i] = next; last = next; }
+    return r;
+}
+static int histogram_index(const std::vector<int64_t>& offs, int64_t n) {     // findIndex: first offset >= n, else the overflow bucket
+    return (int)(std::lower_bound(offs.begin(), offs.end(), n) - offs.begin());
+}
+struct Meta {
+    bool ts_set = false, ldt_set = false, ttl_set = false;
+    int64_t min_ts = 0, max_ts = 0, min_ldt = 0, max_ldt = 0; int32_t min_ttl = 0, max_ttl = 0;
+    uint64_t total_rows = 0, total_columns_set = 0, total_cells = 0, total_tombstones = 0, cur_cells = 0;
+    bool has_partition_deletions = false;
+    std::vector<uint64_t> psize, cells;
+    std::map<int64_t, uint64_t> tdrop;
+    std::vector<uint8_t> hll;
+    std::vector<uint8_t> bloom; int bloom_k = 0;
+    std::vector<uint32_t> sum_offsets; std::vector<uint8_t> sum_entries; uint64_t keys_written = 0; int interval = 128;
+    std::string first, last;
+    int64_t now = 0;
+    void init(const b200c_manifest* m) {
+        psize.assign(B200C_PSIZE_BUCKETS, 0); cells.assign(B200C_CELLS_BUCKETS, 0); hll.assign(1 << B200C_HLL_P, 0);
+        bloom.assign(m->bloom_words * 8, 0); bloom_k = m->bloom_hash_count; interval = m->min_index_interval > 0 ? m->min_index_interval : 128; now = m->now_in_sec;
+    }
+    // MetadataCollector.MinMax*Tracker :402-447
+    void ts(int64_t v) { if (!ts_set) { min_ts = max_ts = v; ts_set = true; } else { min_ts = std::min(min_ts, v); max_ts = std::max(max_ts, v); } }
+    void ttl(int32_t v) { if (!ttl_set) { min_ttl = max_ttl = v; ttl_set = true; } else { min_ttl = std::min(min_ttl, v); max_ttl = std::max(max_ttl, v); } }
+    void ldt(int64_t v) {                                                  // updateLocalDeletionTime :263-268
+        if (!ldt_set) { min_ldt = max_ldt = v; ldt_set = true; } else { min_ldt = std::min(min_ldt, v); max_ldt = std::max(max_ldt, v); }
+        if (v != NO_DEL) { int64_t d = v % 60; tdrop[d == 0 ? v : v + (60 - d)]++; }      // StreamingTombstoneHistogramBuilder.ceilKey, TOMBSTONE_HISTOGRAM_TTL_ROUND_SECONDS = 60
+    }
+    void update(const Live& l) { if (l.empty()) return; ts(l.ts); ttl(l.ttl); ldt(l.ldt); if (!l.is_live(now)) total_tombstones++; }     // :208-218
+    void update(const DT& d) { if (d.live()) return; ts(d.mfda); ldt(d.ldt); total_tombstones++; }                                        // :237-245
+    void update(const CellV& c) { cur_cells++; total_cells++; ts(c.ts); ttl(c.ttl); ldt(c.ldt); if (!c.is_live(now)) total_tombstones++; } // :220-228
+    void partition_deletion(const DT& d) { if (!d.live()) has_partition_deletions = true; update(d); }                                    // :230-235
+    void row(const Unf& u) {                                                // Rows.collectStats S/db/rows/Rows.java:102-113
+        update(u.info); update(u.del);
+        for (const CellV& c : u.cells) update(c);
+        total_columns_set += u.cells.size(); total_rows++;
+    }
+    void marker(const Unf& u) {                                             // SortedTableWriter.addRangeTomstoneMarker :222-238
+        if (kind_is_boundary(u.c.kind)) { update(u.m_close); update(u.m_open); }
+        else update(kind_is_start(u.c.kind) ? u.m_open : u.m_close);
+    }
+    void end_partition(const uint8_t* key, int kl, uint64_t size, uint64_t index_start) {      // endPartition :240-258 + IndexWriter.append
+        static const std::vector<int64_t> po = histogram_offsets(B200C_PSIZE_BUCKETS - 1), co = histogram_offsets(B200C_CELLS_BUCKETS - 1);
+        psize[histogram_index(po, (int64_t)size)]++;
+        cells[histogram_index(co, (int64_t)cur_cells)]++; cur_cells = 0;
+        {   // addKey :160-166 -> HyperLogLogPlus.offerHashed (dense form): register[h >>> (64 - p)] = max(rho of the remaining bits)
+            uint64_t h = murmur2_64(key, kl, 0); uint32_t idx = (uint32_t)(h >> (64 - B200C_HLL_P));
+            uint64_t w = (h << B200C_HLL_P) | (1ull << (B200C_HLL_P - 1)); uint8_t rho = (uint8_t)(__builtin_clzll(w) + 1);
+            if (rho > hll[idx]) hll[idx] = rho;
+        }
+        if (!bloom.empty()) {                                               // BloomFilter.add S/utils/BloomFilter.java:104-122
+            uint64_t hh[2]; murmur3_x64_128(key, kl, 0, hh);
+            int64_t base = (int64_t)hh[1], inc = (int64_t)hh[0]; const int64_t cap = (int64_t)bloom.size() * 8;
+            for (int i = 0; i < bloom_k; i++) { int64_t r = base % cap; uint64_t idx = (uint64_t)(r < 0 ? -r : r); bloom[idx >> 3] |= (uint8_t)(1u << (idx & 7)); base = (int64_t)((uint64_t)base + (uint64_t)inc); }
+        }
+        if (keys_written % (uint64_t)interval == 0) {                       // IndexSummaryBuilder.maybeAddEntry :200-228 at full sampling
+            sum_offsets.push_back((uint32_t)sum_entries.size());
+            sum_entries.insert(sum_entries.end(), key, key + kl);
+            for (int b = 0; b < 8; b++) sum_entries.push_back((uint8_t)(index_start >> (8 * b)));     // native (little-endian) long
+        }
+        if (keys_written == 0) first.assign((const char*)key, kl);
+        last.assign((const char*)key, kl);
+        keys_written++;
+    }
+    std::vector<uint8_t> filter_image() const {                             // BloomFilterSerializer.serialize :50-55 + OffHeapBitSet.serialize :115-119
+        std::vector<uint8_t> f; if (bloom.empty()) return f;
+        uint32_t words = (uint32_t)(bloom.size() / 8);
+        for (int b = 3; b >= 0; b--) f.push_back((uint8_t)(bloom_k >> (8 * b)));
+        for (int b = 3; b >= 0; b--) f.push_back((uint8_t)(words >> (8 * b)));
+        f.insert(f.end(), bloom.begin(), bloom.end());
+        return f;
+    }
+    std::vector<uint8_t> summary_image() const {                            // IndexSummarySerializer.serialize :401-423, then first / last key (int length + bytes)
+        std::vector<uint8_t> o; if (!keys_written) return o;
+        auto be32 = [&](uint32_t v) { for (int b = 3; b >= 0; b--) o.push_back((uint8_t)(v >> (8 * b))); };
+        auto be64 = [&](uint64_t v) { for (int b = 7; b >= 0; b--) o.push_back((uint8_t)(v >> (8 * b))); };
+        uint32_t n = (uint32_t)sum_offsets.size();
+        be32((uint32_t)interval); be32(n); be64((uint64_t)n * 4 + sum_entries.size()); be32(128); be32((uint32_t)((keys_written + interval - 1) / interval));
+        for (uint32_t off : sum_offsets) { uint32_t v = off + n * 4; for (int b = 0; b < 4; b++) o.push_back((uint8_t)(v >> (8 * b))); }
+        o.insert(o.end(), sum_entries.begin(), sum_entries.end());
+        be32((uint32_t)first.size()); o.insert(o.end(), first.begin(), first.end());
+        be32((uint32_t)last.size()); o.insert(o.end(), last.begin(), last.end());
+        return o;
+    }
+    void fill(b200c_sstable_stats* st) const {
+        memset(st, 0, sizeof(*st));
+        st->min_timestamp = ts_set ? min_ts : INT64_MIN; st->max_timestamp = ts_set ? max_ts : INT64_MAX;            // MinMaxLongTracker defaults
+        st->min_local_deletion_time = ldt_set ? min_ldt : NO_DEL; st->max_local_deletion_time = ldt_set ? max_ldt : NO_DEL;
+        st->min_ttl = ttl_set ? min_ttl : 0; st->max_ttl = ttl_set ? max_ttl : 0;
+        st->total_rows = total_rows; st->total_columns_set = total_columns_set; st->total_cells = total_cells; st->total_tombstones = total_tombstones;
+        st->has_partition_level_deletions = has_partition_deletions ? 1 : 0;
+        for (int i = 0; i < B200C_PSIZE_BUCKETS; i++) st->partition_size_hist[i] = psize[i];
+        for (int i = 0; i < B200C_CELLS_BUCKETS; i++) st->cells_per_partition_hist[i] = cells[i];
+        uint32_t k = 0;
+        for (auto& kv : tdrop) { if (k >= B200C_TDROP_CAP) { st->tdrop_overflow = 1; break; } st->tdrop_point[k] = kv.first; st->tdrop_count[k] = kv.second; k++; }
+        st->ntdrop = k;
+        memcpy(st->hll_registers, hll.data(), hll.size());
+    }
+};
+
 struct Writer {
     const b200c_manifest* m; Schema sc;
     // one output sstable
-    struct Sst { std::vector<uint8_t> data; std::vector<uint8_t> index; std::vector<uint64_t> offs; uint64_t ulen = 0; uint32_t digest = 0; uint64_t parts = 0, rows = 0; };
+    struct Sst { std::vector<uint8_t> data; std::vector<uint8_t> index; std::vector<uint64_t> offs; uint64_t ulen = 0; uint32_t digest = 0; uint64_t parts = 0, rows = 0; Meta meta; };
     std::vector<Sst> outs;
     std::vector<uint8_t> chunk;         // CompressedSequentialWriter buffer (S/io/compress/CompressedSequentialWriter.java:140-206)
     std::vector<uint8_t> comp;
@@ -516,7 +624,7 @@ struct Writer {
     OutBuf body, tmp;
 
     bool raw = false;                   // parallel driver (parallel.cc): keep the uncompressed stream, compression happens after stitching
-    void start_output() { outs.emplace_back(); position = 0; chunk_offset = 0; chunk.clear(); }
+    void start_output() { outs.emplace_back(); outs.back().meta.init(m); position = 0; chunk_offset = 0; chunk.clear(); }
     void flush_chunk() {                // flushData :140-206
         if (chunk.empty()) return;
         Sst& o = outs.back();
@@ -582,6 +690,7 @@ struct Writer {
         write(tmp.b.data(), tmp.b.size());
         header_len = position - part_start;
         prev_row_start = 0; have_first = false; open_marker = DT(); index_infos.clear(); block_start = 0;
+        outs.back().meta.partition_deletion(pdel);                          // startPartition :183-189
     }
     uint64_t cur_pos() const { return position - part_start; }
 
@@ -645,6 +754,7 @@ struct Writer {
         write(tmp.b.data(), tmp.b.size());
         write(body.b.data(), body.b.size());
         last_c = u.c; prev_row_start = pos;
+        if (u.is_row) outs.back().meta.row(u); else outs.back().meta.marker(u);
         if (!u.is_row) open_marker = (kind_is_boundary(u.c.kind) || kind_is_start(u.c.kind)) ? u.m_open : DT();
         outs.back().rows++;
         if (cur_pos() - block_start >= (uint64_t)m->column_index_size) add_index_block();     // BigFormatPartitionWriter.addUnfiltered :208-215
@@ -663,6 +773,7 @@ struct Writer {
             for (auto& ii : index_infos) e.put(ii.data(), ii.size());
             uint32_t off = 0; for (auto& ii : index_infos) { e.be32(off); off += (uint32_t)ii.size(); }
         } else e.vint(0);
+        o.meta.end_partition(key, keylen, position - part_start, o.index.size());
         o.index.insert(o.index.end(), e.b.begin(), e.b.end());
         o.parts++;
     }
@@ -773,6 +884,12 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
         memcpy(out.index, o.index.data(), o.index.size()); out.index_len = o.index.size();
         memcpy(out.chunk_offsets, o.offs.data(), o.offs.size() * 8); out.nchunks = o.offs.size();
         out.data_length = o.ulen; out.digest = o.digest; out.partitions = o.parts; out.rows = o.rows;
+        // optional components (b200c_output: NULL pointer = skip)
+        out.first_key_len = (uint32_t)o.meta.first.size(); out.last_key_len = (uint32_t)o.meta.last.size();
+        if (out.key_buf) { if (out.key_cap < o.meta.first.size() + o.meta.last.size()) rc = B200C_ETOOSMALL; else { memcpy(out.key_buf, o.meta.first.data(), o.meta.first.size()); memcpy(out.key_buf + o.meta.first.size(), o.meta.last.data(), o.meta.last.size()); } }
+        if (out.filter) { auto f = o.meta.filter_image(); out.filter_len = f.size(); if (f.size() > out.filter_cap) rc = B200C_ETOOSMALL; else if (!f.empty()) memcpy(out.filter, f.data(), f.size()); }
+        if (out.summary) { auto sm = o.meta.summary_image(); out.summary_len = sm.size(); if (sm.size() > out.summary_cap) rc = B200C_ETOOSMALL; else if (!sm.empty()) memcpy(out.summary, sm.data(), sm.size()); }
+        if (out.stats) o.meta.fill(out.stats);
     }
     res->bytes_written = bw;
     res->kernel_ms = 0; res->kernel_launches = 0; res->index_slow_path_inputs = 0;

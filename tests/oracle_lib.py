@@ -6,7 +6,7 @@ _LIB = None
 def build():
     d = os.path.join(ROOT, "oracle")
     out = os.path.join(d, "_build", "liboracle.so")
-    srcs = glob.glob(os.path.join(d, "*.cc")) + glob.glob(os.path.join(d, "*.h"))
+    srcs = glob.glob(os.path.join(d, "*.cc")) + glob.glob(os.path.join(d, "*.h")) + [os.path.join(ROOT, "include", "b200c.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["make", "-C", d, "-s"])
     return out

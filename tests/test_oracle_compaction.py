@@ -126,3 +126,53 @@ def test_purge_table_equals_per_range_compactions():
     assert decompress_output(whole.outputs[0]) == b"".join(pieces)
     flat = CompactionTask(tabs, CompactionController(NOW, overlapping_min_timestamp=1600000000000000 + 1500000000)).execute(O.OracleEngine())
     assert decompress_output(flat.outputs[0]) != decompress_output(whole.outputs[0])
+
+# ---- Filter.db, Summary.db and the Statistics.db reductions, pinned by the golden components ----------------------------------
+import struct as _st
+from cassandra_b200.io.sstable import parse_statistics, bloom_geometry
+
+def golden_meta_task(golden_dir, name):
+    base = _golden(golden_dir, name)
+    s = SSTable.open(base)
+    hc, words = _st.unpack_from(">ii", open(base + "Filter.db", "rb").read(), 0)
+    return base, s, CompactionTask([s], CompactionController(NOW), column_index_size=4096, bloom=(hc, words))
+
+@pytest.mark.parametrize("name", ["legacy_oa_simple", "legacy_oa_clust"])
+def test_identity_compaction_reproduces_filter_summary_and_statistics(golden_dir, name):
+    """identity compaction of a table written by a real Cassandra release: Filter.db (BloomFilter.add over hash3_x64_128) and Summary.db
+    (IndexSummaryBuilder) byte for byte; the MetadataCollector reductions equal to what the golden Statistics.db holds"""
+    base, s, task = golden_meta_task(golden_dir, name)
+    o = task.execute(O.OracleEngine()).outputs[0]
+    assert o.filter == open(base + "Filter.db", "rb").read()
+    assert o.summary == open(base + "Summary.db", "rb").read()
+    st = parse_statistics(open(base + "Statistics.db", "rb").read())
+    for k in ("min_timestamp", "max_timestamp", "min_local_deletion_time", "max_local_deletion_time", "min_ttl", "max_ttl"):
+        assert o.stats[k] == st[k], k
+    assert o.stats["partition_size_hist"] == st["partition_size_hist"] and o.stats["cells_per_partition_hist"] == st["cells_per_partition_hist"]
+    assert o.stats["tombstone_drop_times"] == st["tombstone_drop_times"] == []
+    assert (o.first_key, o.last_key) == (b"0", b"4")
+    assert o.stats["total_rows"] == o.rows and o.stats["has_partition_level_deletions"] == 0
+
+def test_bloom_geometry_is_filterfactorys():
+    assert bloom_geometry(5, 0.01) == (5, 2)                       # the golden Filter.db: 5 keys at fp 0.01
+    assert bloom_geometry(1000000, 0.01) == (5, (1000000 * 10 + 20 - 1) // 64 + 1)
+    assert bloom_geometry(1000, 0.1) == (3, (1000 * 5 + 20 - 1) // 64 + 1)
+    assert bloom_geometry(10, 1.0) == (0, 0)
+
+def test_metadata_of_a_synthetic_compaction_is_consistent():
+    from synth_util import synth_tables, decompress_output
+    tabs = synth_tables(0, 4, 0x57A7, 3000)
+    r = CompactionTask(tabs, CompactionController(NOW), with_metadata=True, min_index_interval=16).execute(O.OracleEngine())
+    o = r.outputs[0]; st = o.stats
+    assert sum(st["partition_size_hist"]) == o.partitions == sum(st["cells_per_partition_hist"])
+    assert st["total_cells"] == st["total_columns_set"] > 0 and st["total_rows"] == o.rows - sum(1 for _ in []) >= st["total_rows"] > 0 and st["total_tombstones"] > 0
+    assert st["min_timestamp"] <= st["max_timestamp"] and st["min_ttl"] == 0 < st["max_ttl"]
+    assert sum(c for _, c in st["tombstone_drop_times"]) > 0 and all(p % 60 == 0 for p, _ in st["tombstone_drop_times"])
+    # Summary.db: every 16th Index.db entry; the filter holds every key
+    from test_golden_murmur3 import index_keys, bloom_bytes
+    keys = index_keys(o.index)
+    assert (o.first_key, o.last_key) == (keys[0], keys[-1])
+    n = _st.unpack_from(">i", o.summary, 4)[0]; assert n == (len(keys) + 15) // 16
+    hc, words = _st.unpack_from(">ii", o.filter, 0)
+    assert o.filter[8:] == bloom_bytes(keys, hc, words)
+    regs = st["hll_registers"]; assert len(regs) == 8192 and sum(1 for x in regs if x) > 0.2 * min(len(keys), 8192)

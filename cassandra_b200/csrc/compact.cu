@@ -17,6 +17,7 @@
 #include "codec_defs.cuh"
 #include "partition.cuh"
 #include "partition_tile.cuh"
+#include "meta.cuh"
 #include <climits>
 #include <vector>
 #include <algorithm>
@@ -45,10 +46,10 @@ enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pi
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG, WS_INSZ, WS_BIG, WS_INPOS, WS_TMARK, WS_TSCAN, WS_TSTART,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG, WS_INSZ, WS_BIG, WS_INPOS, WS_TMARK, WS_TSCAN, WS_TSTART, WS_META_SG, WS_META_TD, WS_META_BLOOM, WS_META_KEYS, WS_META_SUMENT, WS_META_SUMOFF, WS_META_FLAG, WS_META_WRANK, WS_META_SAMPLE, WS_META_ESIZE, WS_META_EPOS, WS_CCOUNT,
        WS_SCANA = 60, WS_CODEC = 70 };
 
-static_assert(WS_ERR2 < WS_SCANA && WS_SCANA + 6 <= WS_CODEC && WS_CODEC + 12 <= WS_LCS0 && WS_TSTART < WS_SLOTS, "workspace slot map");
+static_assert(WS_ERR2 < WS_SCANA && WS_SCANA + 6 <= WS_CODEC && WS_CODEC + 12 <= WS_LCS0 && WS_CCOUNT < WS_SLOTS, "workspace slot map");
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
 
 __device__ __forceinline__ void report_err(DevErr* e, int kind, int input, uint64_t off) {
@@ -493,6 +494,8 @@ struct K4Args {
     const uint64_t* ioff; const uint32_t* icapv; uint8_t* iscr;
     int m3_nblk;                     // mode 3 also re-emits partitions with a promoted index (two-pass A/B mode: there are no slots)
     const uint8_t* only_big;         // mode 1: when set, only partitions flagged here (the staged kernel took the others)
+    // statistics side band (meta.cuh), gathered in the pass that visits every partition exactly once (mode 1); null otherwise
+    StatGlobal* sg; TdropTable* td; uint32_t* ccount;
 };
 
 template <bool EMIT> __device__ __forceinline__ bool k4_prologue(const K4Args& a, uint64_t j, uint8_t*& dout, uint64_t& dcap, uint64_t& dposv, uint8_t*& iout, uint32_t& nbf, uint32_t& ipf, uint32_t& ixs_cap) {
@@ -514,6 +517,7 @@ template <bool EMIT> __device__ __forceinline__ void k4_epilogue(const K4Args& a
     if (EMIT && a.mode >= 2) { if (e || out.dsize != a.dsize[j]) report_err(a.err, 8, 0, j); return; }
     if (e) { uint64_t en = a.contrib[c0]; int src = (int)((en >> 56) & 0x7F); report_err(a.err, e == PERR_UNSUPPORTED ? 9 : 4, src, a.upos[a.pbase[src] + (en & 0xFFFFFFFFFFull)] - a.P->in[src].ubase); out = PartOut{0, 0, 0, 0, 0}; st = PartStats{0, 0}; }
     a.dsize[j] = out.dsize; a.ipay[j] = out.ipay; a.nblk[j] = out.nblk; a.ihead[j] = out.ihead; a.ovf[j] = (uint8_t)out.ovf;
+    if (a.ccount) a.ccount[j] = out.cells;
     a.st_munf[j] = (uint32_t)st.merged_unfiltereds; a.st_rows[j] = (uint32_t)st.rows_out;
 }
 
@@ -535,9 +539,12 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) return;
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
+    StatAcc acc; const bool stats = a.sg != nullptr && a.mode == 1;
+    if (stats) acc.init(a.P->now, a.td);
     if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
-    else process_partition<EMIT>(*a.P, XlateGlobal(), a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e);
+    else process_partition<EMIT>(*a.P, XlateGlobal(), a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e, stats ? &acc : nullptr);
     k4_epilogue<EMIT>(a, j, c0, out, st, e);
+    if (stats && !e) stat_flush(a.sg, acc);
 }
 
 // fan-in above 16: a whole warp per partition, cursors in registers (partition_tile.cuh)
@@ -554,8 +561,10 @@ __global__ void __launch_bounds__(128) k_partition_warp(const K4Args a, uint64_t
     if (!k4_prologue<EMIT>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) return;
     uint64_t c0 = a.op_first[j]; uint32_t m = (uint32_t)(a.op_first[j + 1] - c0);
     PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
-    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, s_cells, out, st, e);
-    if (tile.thread_rank() == 0) k4_epilogue<EMIT>(a, j, c0, out, st, e);
+    StatAcc acc; const bool stats = a.sg != nullptr && a.mode == 1;
+    if (stats) acc.init(a.P->now, a.td);
+    process_partition_tile<32, S, EMIT>(tile, *a.P, a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, s_cells, out, st, e, stats ? &acc : nullptr);
+    if (tile.thread_rank() == 0) { k4_epilogue<EMIT>(a, j, c0, out, st, e); if (stats && !e) stat_flush(a.sg, acc); }
 }
 
 // ---- K4, staged mapping (the default for partitions of up to ST_MAXP input bytes and fan-in <= ST_MAXM) ------------------------------
@@ -641,15 +650,18 @@ __global__ void __launch_bounds__(ST_THREADS) k_partition_staged(const K4Args a,
     MCell merged_local[WIDE ? MAXCOLS : 1];
     MCell* merged = WIDE ? merged_local : cells + (size_t)tid * ncols_s;
     DT open_dt[ST_MAXM];
+    StatAcc acc; acc.init(sP->now, a.td);
     for (uint32_t j = j0 + tid; j < j1; j += ST_THREADS) {
         uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf, ixs_cap;
         if (!k4_prologue<true>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) continue;
         const uint64_t cj = a.op_first[j]; const uint32_t m = (uint32_t)(a.op_first[j + 1] - cj);
         PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
         if (m > (uint32_t)ST_MAXM || cj - c0 + m > (uint64_t)ST_CUR_CAP) e = PERR_UNSUPPORTED;
-        else process_partition<true>(*sP, xl, a.contrib, cj, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, curs + (cj - c0), open_dt, merged, out, st, e);
+        else process_partition<true>(*sP, xl, a.contrib, cj, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, curs + (cj - c0), open_dt, merged, out, st, e,
+                                     a.sg ? &acc : nullptr);
         k4_epilogue<true>(a, j, cj, out, st, e);
     }
+    if (a.sg) stat_flush_warp(a.sg, acc);               // (no thread returns after the barrier wait: every lane gets here)
 }
 
 // upper bound of an output partition's size: the sum of its input partitions plus 25 % + 32 bytes (re-based deltas can lengthen
@@ -775,6 +787,11 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (m->npurge_ranges < 0 || (m->npurge_ranges && (!m->purge_range_hi || !m->purge_range_max_ts))) { c->err = "purge table"; return B200C_EINVAL; }
     for (int k = 1; k < m->npurge_ranges; k++) if (m->purge_range_hi[k] <= m->purge_range_hi[k - 1]) { c->err = "purge_range_hi must ascend"; return B200C_EINVAL; }
     if (c->cancel.exchange(0)) { c->err = "cancelled"; return B200C_ECANCELLED; }        // stop requested before the task got here
+    // the rest of the sstable (Filter.db / Summary.db / Statistics.db side band / first+last key): single-output compactions
+    const b200c_output& o0 = res->outputs[0];
+    const bool want_meta = o0.key_buf || o0.filter || o0.summary || o0.stats;
+    if (want_meta && (m->max_sstable_bytes != 0 || getenv("B200C_K4_TWO_PASS"))) { c->err = "metadata side band with multi-file output"; return B200C_EUNSUPPORTED; }
+    if (want_meta && o0.filter && m->bloom_words && (m->bloom_hash_count <= 0 || m->bloom_words > (1ull << 31))) { c->err = "bloom geometry"; return B200C_EINVAL; }
     if (m->ninputs > MAXK) { c->err = "more than 64 inputs per call"; return B200C_EUNSUPPORTED; }
     if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) { c->err = "static rows / tombstone_option / strict liveness"; return B200C_EUNSUPPORTED; }
     if (m->nclustering > MAXCLUST || m->ncolumns >= 64 || m->ncolumns < 0) { c->err = "schema outside the supported envelope"; return B200C_EUNSUPPORTED; }
@@ -861,6 +878,26 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pt, m->purge_range_hi, 8 * (size_t)m->npurge_ranges, cudaMemcpyHostToDevice, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pt + m->npurge_ranges, m->purge_range_max_ts, 8 * (size_t)m->npurge_ranges, cudaMemcpyHostToDevice, st));
         hp.purge_hi = d_pt; hp.purge_ts = d_pt + m->npurge_ranges; hp.npurge = m->npurge_ranges;
+    }
+    // metadata state (meta.cuh), device resident across the pieces of the call
+    StatGlobal* d_sg = nullptr; TdropTable* d_td = nullptr; uint32_t* d_bloom = nullptr; uint8_t* d_mkeys = nullptr;
+    uint64_t written_total = 0, samples_total = 0; uint8_t* d_sument = nullptr; uint64_t* d_sumoff = nullptr; uint64_t sument_bound = 0;
+    const uint32_t meta_interval = m->min_index_interval > 0 ? (uint32_t)m->min_index_interval : 128u;
+    const uint64_t bloom_words = (want_meta && o0.filter) ? m->bloom_words : 0;
+    if (want_meta) {
+        B200C_TRY(ws_typed(c, WS_META_SG, 1, &d_sg));
+        B200C_TRY(ws_typed(c, WS_META_TD, 1, &d_td));
+        B200C_TRY(ws_typed(c, WS_META_BLOOM, bloom_words * 2 + 16, &d_bloom));
+        B200C_TRY(ws_typed(c, WS_META_KEYS, (size_t)2 * 65536, &d_mkeys));
+        std::vector<uint8_t> init(sizeof(StatGlobal), 0); StatGlobal* g0 = (StatGlobal*)init.data();
+        g0->min_ts = I64_MAX; g0->max_ts = I64_MIN; g0->min_ldt = I64_MAX; g0->max_ldt = I64_MIN; g0->min_ttl = INT_MAX; g0->max_ttl = INT_MIN;
+        auto offsets = [](long long* o, int n) { long long last = 1; o[0] = 1; for (int i = 1; i < n; i++) { long long next = llround((double)last * 1.2); if (next == last) next++; o[i] = next; last = next; } };
+        offsets(g0->psize_off, META_PSIZE - 1); offsets(g0->cells_off, META_CELLS - 1);       // EstimatedHistogram.newOffsets (S/utils/EstimatedHistogram.java:91-109)
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_sg, init.data(), sizeof(StatGlobal), cudaMemcpyHostToDevice, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));                                            // (init is a stack vector)
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_td, 0, sizeof(TdropTable), st));
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_td->key, 0xFF, sizeof(d_td->key), st));
+        if (bloom_words) B200C_CUDA_TRY(c, cudaMemsetAsync(d_bloom, 0, bloom_words * 8, st));
     }
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_err, 0xFF, 64, st));
     B200C_CUDA_TRY(c, cudaMemsetAsync(d_cerr, 0xFF, 64, st));
@@ -1211,6 +1248,13 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen; ka.tok = d_tok;
         ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
         ka.dpos = d_dpos; ka.ipos = d_ipos; ka.err = d_err; ka.jlo = 0; ka.jhi = nparts; ka.m3_nblk = two_pass ? 1 : 0;
+        uint32_t* d_ccount = nullptr; uint32_t* d_wflag = nullptr; uint64_t* d_wrank = nullptr;
+        if (want_meta) {
+            B200C_TRY(ws_typed(c, WS_CCOUNT, nparts + 1, &d_ccount));
+            B200C_TRY(ws_typed(c, WS_META_FLAG, nparts + 1, &d_wflag));
+            B200C_TRY(ws_typed(c, WS_META_WRANK, nparts + 2, &d_wrank));
+            ka.sg = d_sg; ka.td = d_td; ka.ccount = d_ccount;
+        }
         // one launch per fan-in class over its slice of the sorted list
         const uint64_t np_ = nparts;
         launch_k4 = [&, n_le8, n_le16, n_le32, np_, smem8, smem16, cell_smem32](int mode) -> int {
@@ -1298,6 +1342,11 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_dpos + nparts, 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_ipos + nparts, 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 2, d_err, 8, cudaMemcpyDeviceToHost, st));
+            if (want_meta) {
+                B200C_LAUNCH(c, k_written_flags, (unsigned)((nparts + 255) / 256), 256, 0, nparts, d_dsize, d_wflag);
+                B200C_TRY(exclusive_scan<uint32_t>(c, d_wflag, nparts, d_wrank, WS_SCANA, 0));
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 3, d_wrank + nparts, 8, cudaMemcpyDeviceToHost, st));
+            }
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
             if (h[2] != ~0ull) {
                 int kinde = (int)(h[2] >> 56);
@@ -1327,6 +1376,33 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                              d_ioff, d_icap, ISCR, IOUT);
                 B200C_TRY(launch_k4(3));
             }
+        }
+        if (want_meta && nparts && ulen_out) {
+            // per key / per partition metadata of this piece: bloom bits, HLL registers, histograms, index-summary samples, first / last key
+            const uint64_t nwritten = h[3];
+            const uint64_t ns = (written_total + nwritten + meta_interval - 1) / meta_interval - (written_total + meta_interval - 1) / meta_interval;
+            uint32_t *d_samplej, *d_esize; uint64_t* d_epos;
+            B200C_TRY(ws_typed(c, WS_META_SAMPLE, ns + 1, &d_samplej));
+            B200C_TRY(ws_typed(c, WS_META_ESIZE, ns + 1, &d_esize));
+            B200C_TRY(ws_typed(c, WS_META_EPOS, ns + 2, &d_epos));
+            MetaArgs ma; memset(&ma, 0, sizeof(ma));
+            ma.P = dP; ma.contrib = d_contrib; ma.op_first = d_opfirst; ma.upos = d_upos; ma.pbase = d_pbase; ma.dsize = d_dsize; ma.ipos = d_ipos; ma.ihead = d_ihead;
+            ma.ccount = d_ccount; ma.wrank = d_wrank; ma.nparts = nparts; ma.index_base = ilen_total; ma.written_base = written_total; ma.sg = d_sg;
+            ma.bloom = d_bloom; ma.bloom_bits = bloom_words * 64; ma.bloom_k = m->bloom_hash_count; ma.interval = meta_interval; ma.sample_j = d_samplej;
+            ma.first_key = d_mkeys; ma.last_key = d_mkeys + 65536;
+            B200C_LAUNCH(c, k_meta_keys, (unsigned)((nparts + 255) / 256), 256, 0, ma);
+            if (ns && o0.summary) {
+                B200C_LAUNCH(c, k_summary_sizes, (unsigned)((ns + 255) / 256), 256, 0, ma, ns, d_esize);
+                B200C_TRY(exclusive_scan<uint32_t>(c, d_esize, ns, d_epos, WS_SCANA, 0));
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 4, d_epos + ns, 8, cudaMemcpyDeviceToHost, st));
+                B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                B200C_TRY(ws_grow_keep<uint8_t>(c, WS_META_SUMENT, sument_bound + h[4] + 64, sument_bound, &d_sument));
+                B200C_TRY(ws_grow_keep<uint64_t>(c, WS_META_SUMOFF, samples_total + ns + 2, samples_total, &d_sumoff));
+                B200C_LAUNCH(c, k_summary_emit, (unsigned)((ns + 255) / 256), 256, 0, ma, ns, d_epos, d_sument, d_sumoff);
+                B200C_LAUNCH(c, k_meta_advance, 1, 1, 0, d_sg, ns, d_epos);
+                sument_bound += h[4]; samples_total += ns;
+            }
+            written_total += nwritten;
         }
         c->prog_scanned.store(bytes_read * (4 * (uint64_t)r + 3) / (4 * (uint64_t)nr));
         if (deferred || r == nr - 1) for (int i = 0; i < K; i++) c->prog_input_pos[i].store(range_end[(size_t)r * K + i]);
@@ -1372,6 +1448,67 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
         return B200C_OK;
     };
+    // Filter.db / Summary.db / first+last key / statistics side band of the single output -> the caller's (host) buffers
+    auto finish_meta = [&](b200c_output& out) -> int {
+        if (!want_meta) return B200C_OK;
+        B200C_LAUNCH(c, k_tdrop_final, 4, 1024, 0, d_td, d_sg);
+        std::vector<uint8_t> hb(sizeof(StatGlobal)); StatGlobal* g = (StatGlobal*)hb.data();
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(g, d_sg, sizeof(StatGlobal), cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        out.first_key_len = written_total ? g->first_len : 0; out.last_key_len = written_total ? g->last_len : 0;
+        if (out.key_buf) {
+            if (out.key_cap < (uint64_t)out.first_key_len + out.last_key_len) { c->err = "key buffer too small"; return B200C_ETOOSMALL; }
+            if (out.first_key_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.key_buf, d_mkeys, out.first_key_len, cudaMemcpyDeviceToHost, st));
+            if (out.last_key_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.key_buf + out.first_key_len, d_mkeys + 65536, out.last_key_len, cudaMemcpyDeviceToHost, st));
+        }
+        if (out.filter) {                                   // BloomFilterSerializer.serialize: i32 hashCount | i32 words | bitset bytes
+            out.filter_len = bloom_words ? 8 + bloom_words * 8 : 0;
+            if (out.filter_len > out.filter_cap) { c->err = "filter buffer too small"; return B200C_ETOOSMALL; }
+            if (bloom_words) {
+                const uint32_t k = (uint32_t)m->bloom_hash_count, w = (uint32_t)bloom_words;
+                uint8_t hd[8] = {(uint8_t)(k >> 24), (uint8_t)(k >> 16), (uint8_t)(k >> 8), (uint8_t)k, (uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w};
+                memcpy(out.filter, hd, 8);
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(out.filter + 8, d_bloom, bloom_words * 8, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (out.summary) {                                  // IndexSummarySerializer.serialize + first / last key (S/io/sstable/indexsummary/IndexSummary.java:401-423)
+            const uint64_t n = samples_total, eb = sument_bound, fl = out.first_key_len, ll = out.last_key_len;
+            out.summary_len = written_total ? 24 + 4 * n + eb + 4 + fl + 4 + ll : 0;
+            if (out.summary_len > out.summary_cap) { c->err = "summary buffer too small"; return B200C_ETOOSMALL; }
+            if (written_total) {
+                uint8_t* p = out.summary;
+                auto be32 = [&](uint32_t v) { *p++ = (uint8_t)(v >> 24); *p++ = (uint8_t)(v >> 16); *p++ = (uint8_t)(v >> 8); *p++ = (uint8_t)v; };
+                auto be64 = [&](uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); };
+                be32(meta_interval); be32((uint32_t)n); be64(4 * n + eb); be32(128); be32((uint32_t)((written_total + meta_interval - 1) / meta_interval));
+                std::vector<uint64_t> offs(n);
+                if (n) B200C_CUDA_TRY(c, cudaMemcpyAsync(offs.data(), d_sumoff, n * 8, cudaMemcpyDeviceToHost, st));
+                if (eb) B200C_CUDA_TRY(c, cudaMemcpyAsync(p + 4 * n, d_sument, eb, cudaMemcpyDeviceToHost, st));
+                B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                for (uint64_t i = 0; i < n; i++) { uint32_t v = (uint32_t)(offs[i] + 4 * n); *p++ = (uint8_t)v; *p++ = (uint8_t)(v >> 8); *p++ = (uint8_t)(v >> 16); *p++ = (uint8_t)(v >> 24); }
+                p += eb;
+                std::vector<uint8_t> kb(fl + ll + 1);
+                if (fl) B200C_CUDA_TRY(c, cudaMemcpyAsync(kb.data(), d_mkeys, fl, cudaMemcpyDeviceToHost, st));
+                if (ll) B200C_CUDA_TRY(c, cudaMemcpyAsync(kb.data() + fl, d_mkeys + 65536, ll, cudaMemcpyDeviceToHost, st));
+                B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+                be32((uint32_t)fl); memcpy(p, kb.data(), fl); p += fl; be32((uint32_t)ll); memcpy(p, kb.data() + fl, ll); p += ll;
+            }
+        }
+        if (out.stats) {
+            b200c_sstable_stats* s = out.stats; memset(s, 0, sizeof(*s));
+            s->min_timestamp = (g->seen & 1) ? g->min_ts : I64_MIN; s->max_timestamp = (g->seen & 1) ? g->max_ts : I64_MAX;     // MinMaxLongTracker defaults
+            s->min_local_deletion_time = (g->seen & 2) ? g->min_ldt : I64_MAX; s->max_local_deletion_time = (g->seen & 2) ? g->max_ldt : I64_MAX;
+            s->min_ttl = (g->seen & 4) ? g->min_ttl : 0; s->max_ttl = (g->seen & 4) ? g->max_ttl : 0;
+            s->total_rows = g->rows; s->total_columns_set = g->cols; s->total_cells = g->cells; s->total_tombstones = g->tombs;
+            s->has_partition_level_deletions = g->pdel ? 1 : 0; s->tdrop_overflow = g->tdrop_overflow ? 1 : 0;
+            for (int i = 0; i < META_PSIZE; i++) s->partition_size_hist[i] = g->psize[i];
+            for (int i = 0; i < META_CELLS; i++) s->cells_per_partition_hist[i] = g->cells_hist[i];
+            s->ntdrop = (uint32_t)std::min<uint64_t>(g->tdrop_n, B200C_TDROP_CAP);
+            for (uint32_t i = 0; i < s->ntdrop; i++) { s->tdrop_point[i] = g->tdrop_point[i]; s->tdrop_count[i] = g->tdrop_count[i]; }
+            for (int i = 0; i < META_HLL; i++) s->hll_registers[i] = (uint8_t)g->hll[i];
+        }
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        return B200C_OK;
+    };
     if (to_host_stream) {
         b200c_output& out = out0;
         uint64_t out_len = 0; uint32_t digest = 0; uint64_t* d_ooffs = nullptr;
@@ -1382,6 +1519,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         res->required_data_cap = std::max<uint64_t>(out_len, 1); res->required_index_cap = ilen_total; res->required_chunk_cap = nchunks_out;
         out.data_len = out_len; out.index_len = ilen_total; out.nchunks = nchunks_out; out.data_length = ubase_total; out.digest = digest;
         out.partitions = rs.partitions_out; out.rows = rs.rows_out;
+        { int mrc = finish_meta(out); if (mrc != B200C_OK) rc = mrc; }
         if (!os.fits || !index_fits || out_len > out.data_cap || ilen_total > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
         else {
             if (nchunks_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.chunk_offsets, d_ooffs, nchunks_out * 8, cudaMemcpyDeviceToHost, st));
@@ -1402,6 +1540,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         res->noutputs = 1;
         out.data_len = out_len; out.index_len = ilen_out; out.nchunks = nchunks_out; out.data_length = ulen_out; out.digest = digest;
         out.partitions = rs.partitions_out; out.rows = rs.rows_out;
+        { int mrc = finish_meta(out); if (mrc != B200C_OK) rc = mrc; }
         if (out_len > out.data_cap || ilen_out > out.index_cap || nchunks_out > out.chunk_cap) { c->err = "output buffers too small"; rc = B200C_ETOOSMALL; }
         else {
             if (ilen_out) B200C_CUDA_TRY(c, cudaMemcpyAsync(out.index, IOUT, ilen_out, cudaMemcpyDeviceToDevice, st));

@@ -106,23 +106,6 @@ __global__ void __launch_bounds__(256) k_offs_add_base(const uint64_t* __restric
     if (i == count) bases[1] = b + rel[count];
 }
 
-// workspace slot that keeps its first `used` bytes when it has to grow (whole-file arrays of an OutStream)
-template <typename T> static int ws_grow_keep(b200c_ctx* c, int slot, size_t count, size_t used, T** out) {
-    WsBuf& b = c->ws[slot];
-    size_t need = count * sizeof(T) + 256;
-    if (b.cap < need) {
-        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_out);
-        void* np = nullptr; size_t cap = need * 2;
-        cudaError_t e = cudaMalloc(&np, cap);
-        if (e != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(" + std::to_string(cap) + "): " + cudaGetErrorString(e); return B200C_ENOMEM; }
-        if (b.p && used) cudaMemcpy(np, b.p, std::min(used * sizeof(T), b.cap), cudaMemcpyDeviceToDevice);
-        if (b.p) cudaFree(b.p);
-        b.p = np; b.cap = cap;
-    }
-    *out = (T*)b.p;
-    return B200C_OK;
-}
-
 // ---- OutStream: K5 for one output file whose uncompressed stream is handed over in pieces -------------------------------------------
 // Every piece is compressed into slots, its chunk sizes are scanned and re-based onto the running file offset (a device scalar, so
 // no host round trip sits between the kernels), packed into one of two image buffers and copied to the caller's host buffer on the

@@ -75,6 +75,23 @@ template <typename T> inline int ws_typed(b200c_ctx* c, int slot, size_t count, 
     void* p; int rc = ws_get(c, slot, count * sizeof(T), &p); *out = (T*)p; return rc;
 }
 
+// workspace slot that keeps its first `used` bytes when it has to grow (whole-file arrays of an OutStream)
+template <typename T> inline int ws_grow_keep(b200c_ctx* c, int slot, size_t count, size_t used, T** out) {
+    WsBuf& b = c->ws[slot];
+    size_t need = count * sizeof(T) + 256;
+    if (b.cap < need) {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_out);
+        void* np = nullptr; size_t cap = need * 2;
+        cudaError_t e = cudaMalloc(&np, cap);
+        if (e != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(" + std::to_string(cap) + "): " + cudaGetErrorString(e); return B200C_ENOMEM; }
+        if (b.p && used) cudaMemcpy(np, b.p, std::min(used * sizeof(T), b.cap), cudaMemcpyDeviceToDevice);
+        if (b.p) cudaFree(b.p);
+        b.p = np; b.cap = cap;
+    }
+    *out = (T*)b.p;
+    return B200C_OK;
+}
+
 inline void timing_begin(b200c_ctx* c) { c->launches_call = 0; cudaEventRecord(c->ev0, c->stream); c->timing = true; }
 inline int timing_end(b200c_ctx* c) {
     cudaEventRecord(c->ev1, c->stream);

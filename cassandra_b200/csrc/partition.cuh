@@ -144,7 +144,9 @@ struct CkRef { uint64_t off; uint32_t len; uint8_t kind, n; };      // serialise
 // OFF: type of the stream positions (offsets from P.U), REL: type of the offsets inside one unfiltered header.
 //   Cur   = CurT<uint64_t, uint32_t> (48 bytes): P.U is the whole decompressed input in global memory
 //   CurS  = CurT<uint32_t, uint16_t> (32 bytes): P.U is a tile of < 64 KiB staged in shared memory (k_partition_staged)
-template <typename OFF, typename REL> struct CurT {
+template <int PAD> struct CurPad { uint8_t pad_[PAD]; };
+template <> struct CurPad<0> {};
+template <typename OFF, typename REL, int PAD = 0> struct CurT : CurPad<PAD> {
     uint64_t k0;                   // order-preserving 64-bit prefix of the first clustering component (see cur_load)
     OFF pos, next, end;            // current unfiltered, the one after it, end of the partition
     REL ckend_rel, body_rel;       // offsets from pos: end of the clustering values, start of the body
@@ -154,7 +156,9 @@ template <typename OFF, typename REL> struct CurT {
     typedef REL rel_t;
 };
 typedef CurT<uint64_t, uint32_t> Cur;
-typedef CurT<uint32_t, uint16_t> CurS;
+// 40-byte stride: 32-byte cursors of different threads would all start in one of four bank groups (8-way conflicts on every field)
+typedef CurT<uint32_t, uint16_t, 8> CurS;
+static_assert(sizeof(Cur) == 48 && sizeof(CurS) == 40, "cursor layouts");
 
 // parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
 template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P, CUR& c) {
@@ -304,6 +308,39 @@ __device__ bool reconcile_keep_left(const CParams& P, const MCell& l, const MCel
 // promoted-index slot of the scratch pass: [16 B partition deletion (mfda, ldt)][i32 offsets x nb_max][IndexInfo bytes, IXS_PER_BLOCK budget per block]
 enum { IXS_HEAD = 16, IXS_PER_BLOCK = 204, IXS_BLOCK_STRIDE = 4 + IXS_PER_BLOCK };
 
+// ---- MetadataCollector's reductions, gathered where the rows are written (S/io/sstable/metadata/MetadataCollector.java:208-270; called from
+// SortedTableWriter.startPartition / addRow / addRangeTomstoneMarker S/io/sstable/format/SortedTableWriter.java:183-238 and Rows.collectStats
+// S/db/rows/Rows.java:102-113). One accumulator per thread, in registers; the kernels fold them into a StatGlobal at the end of the block.
+struct TdropTable { unsigned long long key[4096]; unsigned long long cnt[4096]; unsigned int overflow; unsigned int _pad; };   // rounded drop time -> count
+struct StatAcc {
+    int64_t min_ts, max_ts, min_ldt, max_ldt; int32_t min_ttl, max_ttl; uint32_t seen;     // seen: bit0 ts, bit1 ldt, bit2 ttl
+    unsigned long long rows, cols, cells, tombs; uint32_t pdel, part_cells;
+    int64_t now; TdropTable* td;
+    __device__ __forceinline__ void init(int64_t now_, TdropTable* td_) { min_ts = max_ts = min_ldt = max_ldt = 0; min_ttl = max_ttl = 0; seen = 0; rows = cols = cells = tombs = 0; pdel = part_cells = 0; now = now_; td = td_; }
+    __device__ __forceinline__ void ts(int64_t v) { if (!(seen & 1)) { min_ts = max_ts = v; seen |= 1; } else { min_ts = v < min_ts ? v : min_ts; max_ts = v > max_ts ? v : max_ts; } }
+    __device__ __forceinline__ void ttl(int32_t v) { if (!(seen & 4)) { min_ttl = max_ttl = v; seen |= 4; } else { min_ttl = v < min_ttl ? v : min_ttl; max_ttl = v > max_ttl ? v : max_ttl; } }
+    __device__ __noinline__ void tdrop(int64_t v) {                        // StreamingTombstoneHistogramBuilder.ceilKey with roundSeconds = 60, exact counts
+#ifdef __CUDA_ARCH__
+        if (!td) return;
+        const int64_t d = v % 60; const unsigned long long pt = (unsigned long long)(d == 0 ? v : v + (60 - d));
+        uint32_t h = (uint32_t)((pt / 60) * 2654435761ull) & 4095u;
+        for (int probe = 0; probe < 4096; probe++, h = (h + 1) & 4095u) {
+            unsigned long long k = td->key[h];
+            if (k != pt) { if (k != ~0ull) continue; k = atomicCAS(&td->key[h], ~0ull, pt); if (k != ~0ull && k != pt) continue; }
+            atomicAdd(&td->cnt[h], 1ull); return;
+        }
+        td->overflow = 1;
+#endif
+    }
+    __device__ __forceinline__ void ldt(int64_t v) {
+        if (!(seen & 2)) { min_ldt = max_ldt = v; seen |= 2; } else { min_ldt = v < min_ldt ? v : min_ldt; max_ldt = v > max_ldt ? v : max_ldt; }
+        if (v != I64_MAX) tdrop(v);
+    }
+    __device__ __forceinline__ void live(const Live& l) { if (live_is_empty(l)) return; ts(l.ts); ttl(l.ttl); ldt(l.ldt); if (!live_is_live(l, now)) tombs++; }
+    __device__ __forceinline__ void dt(const DT& d) { if (dt_is_live(d)) return; ts(d.mfda); ldt(d.ldt); tombs++; }
+    __device__ __forceinline__ void cell(const MCell& m) { cells++; part_cells++; ts(m.ts); ttl(m.ttl); ldt(m.ldt); if (!(m.ldt == I64_MAX || (m.ttl != 0 && now < m.ldt))) tombs++; }
+};
+
 // ---- partition writer (SortedTablePartitionWriter + BigFormatPartitionWriter state) ------------------------------------------
 template <bool EMIT> struct PWriter {
     Sink<EMIT> d;                 // Data stream, positioned at the partition start
@@ -315,6 +352,7 @@ template <bool EMIT> struct PWriter {
     CkRef first, last;
     DT open_marker;
     uint64_t rows_out;
+    StatAcc* acc;                 // statistics side band (nullptr: not gathered in this pass)
 };
 
 template <bool EMIT> __device__ __forceinline__ void write_partition_dt(Sink<EMIT>& s, const DT& d) {
@@ -450,6 +488,7 @@ __device__ __forceinline__ int purge_row(const CParams& P, const Purger& pg, Liv
 template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, const CParams& P, uint64_t key_off, uint32_t klen, const DT& out_pdel) {
     w.d.be16(klen); w.d.copy(P.U + key_off, klen); write_partition_dt(w.d, out_pdel);      // SortedTablePartitionWriter.start :97-115
     w.header_len = w.d.pos - w.start; w.started = true;
+    if (w.acc) { w.acc->part_cells = 0; if (!dt_is_live(out_pdel)) { w.acc->pdel = 1; w.acc->dt(out_pdel); } }     // updatePartitionDeletion
 }
 
 template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
@@ -466,6 +505,11 @@ template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w,
     w.d.vint(body + vint_size(prev)); w.d.vint(prev);
     w.d.pos = put_row_body(w.d, P, flags, info, del, cells);
     pw_end_unf(w, P, ck, pos);
+    if (w.acc) {                                               // Rows.collectStats
+        w.acc->live(info); w.acc->dt(del);
+        for (int c = 0; c < P.ncols; c++) if (cells[c].present) w.acc->cell(cells[c]);
+        w.acc->cols += (unsigned long long)present; w.acc->rows++;
+    }
 }
 
 // UnfilteredSerializer.serialize(RangeTombstoneMarker) :282-305
@@ -480,6 +524,7 @@ template <bool EMIT> __device__ __forceinline__ void write_marker(PWriter<EMIT>&
     if (boundary) { write_delta_dt(w.d, P, m_close); write_delta_dt(w.d, P, m_open); } else write_delta_dt(w.d, P, start ? m_open : m_close);
     w.open_marker = (boundary || start) ? m_open : dt_live();
     pw_end_unf(w, P, ck, pos);
+    if (w.acc) { if (boundary) { w.acc->dt(m_close); w.acc->dt(m_open); } else w.acc->dt(start ? m_open : m_close); }
 }
 
 // PurgeFunction.applyToMarker :116-143. Returns false when the marker disappears; may turn a boundary into a bound.
@@ -515,7 +560,7 @@ __device__ __forceinline__ int64_t purge_threshold(const CParams& P, const uint6
     return a < P.npurge ? P.purge_ts[a] : P.purge_max_ts;
 }
 
-struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; };
+struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; uint32_t cells; };
 
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
 // cur[0..m) / open_dt[0..m): per-source cursor state owned by this thread (the caller places it in shared memory);
@@ -536,7 +581,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
                                   const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen, const int64_t* __restrict__ part_tok,
                                   uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
                                   CUR* cur, DT* open_dt, MCell* merged,
-                                  PartOut& out, PartStats& st, int& err) {
+                                  PartOut& out, PartStats& st, int& err, StatAcc* acc = nullptr) {
     Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
@@ -581,7 +626,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     const bool ixs = EMIT && ixs_cap != 0;
     w.d.base = dout; w.d.pos = 0; w.d.on = true; w.d.cap = dcap; w.ix.on = EMIT && iout && (ixs || nblocks_final > 1); w.ix.cap = ixs ? (uint64_t)ixs_cap : ~0ull; w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
-    w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
+    w.first = CkRef{0, 0, 0, 0}; w.last = w.first; w.acc = acc;
     // index entry layout (EMIT): [u16 kl][key][vint dpos][vint ipay]{[vint headerLen][DT][vint nblocks][IndexInfo..][i32 offsets..]}
     uint32_t hdr_len_known = 2 + klen + (dt_is_live(out_pdel) ? 1 : 12);
     uint32_t fixed = 2 + klen + vint_size(dpos) + vint_size(ipay_final);
@@ -672,8 +717,9 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     if (err) return;
     // partition.isEmpty() (UnfilteredRowIterator.java:63-68) / SortedTableWriter.append :134
     if (!w.started && !dt_is_live(out_pdel)) pw_start(w, P, key_off, klen, out_pdel);
-    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen; out.ovf = 0;
+    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen; out.ovf = 0; out.cells = 0;
     if (w.started) {
+        if (acc) out.cells = acc->part_cells;
         w.d.u8(0x01);                                                        // end of partition, then the trailing index block (finish() :217-243)
         if (w.rows_out && w.have_first) pw_add_index_block(w, P);
         out.dsize = w.d.pos; out.nblk = w.nblocks;

@@ -61,7 +61,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
                                        const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
                                        const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen, const int64_t* __restrict__ part_tok,
                                        uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
-                                       MCell* s_cells, PartOut& out, PartStats& st, int& err) {
+                                       MCell* s_cells, PartOut& out, PartStats& st, int& err, StatAcc* acc = nullptr) {
     const int lane = tile.thread_rank();
     const bool multi = m > 1;
     Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
@@ -107,7 +107,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
     w.d.base = dout; w.d.pos = 0; w.d.on = (lane == 0); w.d.cap = dcap; w.ix.on = (lane == 0) && EMIT && iout && (ixs || nblocks_final > 1); w.ix.cap = ixs ? (uint64_t)ixs_cap : ~0ull;
     w.start = 0; w.header_len = 0; w.prev_row_start = 0; w.block_start = 0;
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
-    w.first = CkRef{0, 0, 0, 0}; w.last = w.first;
+    w.first = CkRef{0, 0, 0, 0}; w.last = w.first; w.acc = (lane == 0) ? acc : nullptr;      // every lane runs the writer, lane 0 stores and counts
     {
         uint32_t hdr_len_known = 2 + klen + (dt_is_live(out_pdel) ? 1 : 12);
         uint32_t fixed = 2 + klen + vint_size(dpos) + vint_size(ipay_final);
@@ -290,9 +290,10 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
     }
     if (tile.any(lerr != 0)) { err = tile.any(lerr == PERR_UNSUPPORTED) ? PERR_UNSUPPORTED : PERR_CORRUPT; return; }
     if (!w.started && !dt_is_live(out_pdel)) pw_start(w, P, key_off, klen, out_pdel);
-    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen; out.ovf = 0;
+    out.dsize = 0; out.ipay = 0; out.nblk = 0; out.ihead = 2 + klen; out.ovf = 0; out.cells = 0;
     st.merged_unfiltereds += merged_unf;
     if (w.started) {
+        if (w.acc) out.cells = w.acc->part_cells;
         w.d.u8(0x01);
         if (w.rows_out && w.have_first) pw_add_index_block(w, P);
         out.dsize = w.d.pos; out.nblk = w.nblocks;

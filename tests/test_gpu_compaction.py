@@ -33,6 +33,9 @@ def both(ctx, tables, controller, **kw):
     assert g.compression.chunk_offsets == w.compression.chunk_offsets and g.compression.data_length == w.compression.data_length
     assert g.digest == w.digest == zlib.crc32(g.data)
     assert (g.partitions, g.rows) == (w.partitions, w.rows)
+    if w.filter is not None:                  # with_metadata: Filter.db, Summary.db, first/last key and every MetadataCollector reduction
+        assert g.filter == w.filter and g.summary == w.summary and (g.first_key, g.last_key) == (w.first_key, w.last_key)
+        for k in w.stats: assert g.stats[k] == w.stats[k], k
     for k in ("bytes_read", "bytes_in_range", "bytes_written", "total_source_rows", "input_partitions", "merged_row_counts"):
         assert got.stats[k] == want.stats[k], k
     assert got.stats["kernel_launches"] > 0
@@ -189,6 +192,9 @@ def test_lcs_output_switching_matches_oracle(ctx, limit, n, universe):
         assert g.data == w.data and g.index == w.index and g.digest == w.digest
         assert g.compression.chunk_offsets == w.compression.chunk_offsets and g.compression.data_length == w.compression.data_length
         assert (g.partitions, g.rows) == (w.partitions, w.rows)
+    if w.filter is not None:                  # with_metadata: Filter.db, Summary.db, first/last key and every MetadataCollector reduction
+        assert g.filter == w.filter and g.summary == w.summary and (g.first_key, g.last_key) == (w.first_key, w.last_key)
+        for k in w.stats: assert g.stats[k] == w.stats[k], k
     for k in ("bytes_read", "bytes_written", "total_source_rows", "merged_row_counts"): assert got.stats[k] == want.stats[k]
 
 def test_lcs_wide_partitions(ctx):
@@ -513,3 +519,28 @@ def test_more_than_32768_chunks_default_switches(ctx):
     tabs = synth_tables(0, 6, 0xCA55B16, synth.universe_for(0, 96 << 20, 0.5))
     assert sum(len(t.compression.chunk_offsets) for t in tabs) >= 32768
     got, want = both(ctx, tabs, CompactionController(NOW))
+
+
+# ---- the rest of the sstable on the GPU ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["legacy_oa_simple", "legacy_oa_clust"])
+def test_golden_filter_summary_statistics(ctx, golden_dir, name):
+    """identity compaction on the GPU: Filter.db and Summary.db byte for byte as the Cassandra release wrote them, statistics = the oracle's
+    (which tests/test_oracle_compaction.py pins against the golden Statistics.db)"""
+    from test_oracle_compaction import golden_meta_task
+    base, s, task = golden_meta_task(golden_dir, name)
+    got, want = both(ctx, [s], CompactionController(NOW), column_index_size=4096, bloom=task.bloom)
+    o = got.outputs[0]
+    assert o.filter == open(base + "Filter.db", "rb").read()
+    assert o.summary == open(base + "Summary.db", "rb").read()
+    assert (o.first_key, o.last_key) == (b"0", b"4")
+
+@pytest.mark.parametrize("ranges", [0, 5])
+def test_metadata_matches_oracle_on_synthetic_tables(ctx, ranges, monkeypatch):
+    if ranges: monkeypatch.setenv("B200C_RANGES", str(ranges))
+    tabs = synth_tables(0, 6, 0x3E7A + ranges, 20000)
+    got, want = both(ctx, tabs, CompactionController(NOW), with_metadata=True, min_index_interval=16)
+    st = got.outputs[0].stats
+    assert st["total_tombstones"] > 0 and len(st["tombstone_drop_times"]) > 0 and st["max_ttl"] > 0
+    wide = synth_tables(1, 3, 0x3E7B + ranges, 60, rows_per_partition=400, column_index_size=4096)
+    both(ctx, wide, CompactionController(NOW), column_index_size=4096, with_metadata=True)
+    both(ctx, tabs, CompactionController(0, 0), with_metadata=True)               # nothing purged: other tombstone / TTL paths

@@ -46,10 +46,10 @@ enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pi
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG, WS_INSZ, WS_BIG, WS_INPOS, WS_TMARK, WS_TSCAN, WS_TSTART, WS_META_SG, WS_META_TD, WS_META_BLOOM, WS_META_KEYS, WS_META_SUMENT, WS_META_SUMOFF, WS_META_FLAG, WS_META_WRANK, WS_META_SAMPLE, WS_META_ESIZE, WS_META_EPOS, WS_CCOUNT,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG, WS_INSZ, WS_BIG, WS_INPOS, WS_TMARK, WS_TSCAN, WS_TSTART, WS_META_SG, WS_META_TD, WS_META_BLOOM, WS_META_KEYS, WS_META_SUMENT, WS_META_SUMOFF, WS_META_FLAG, WS_META_WRANK, WS_META_SAMPLE, WS_META_ESIZE, WS_META_EPOS, WS_CCOUNT, WS_SLICE,
        WS_SCANA = 60, WS_CODEC = 70 };
 
-static_assert(WS_ERR2 < WS_SCANA && WS_SCANA + 6 <= WS_CODEC && WS_CODEC + 12 <= WS_LCS0 && WS_CCOUNT < WS_SLOTS, "workspace slot map");
+static_assert(WS_ERR2 < WS_SCANA && WS_SCANA + 6 <= WS_CODEC && WS_CODEC + 12 <= WS_LCS0 && WS_SLICE < WS_SLOTS, "workspace slot map");
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
 
 __device__ __forceinline__ void report_err(DevErr* e, int kind, int input, uint64_t off) {
@@ -83,6 +83,52 @@ __host__ __device__ int64_t murmur3_token(const uint8_t* key, uint32_t len) {
     h1 += h2; h2 += h1; h1 = fmix64(h1); h2 = fmix64(h2); h1 += h2;
     int64_t v = (int64_t)h1;
     return v == I64_MIN ? I64_MAX : v;
+}
+
+// ---- Index.db slices for token sub-ranges -------------------------------------------------------------------------------------------
+// A call for (token_lo, token_hi] needs only the Index.db entries between the last Summary.db sample whose token is <= token_lo and the
+// first sample whose token is > token_hi — what a ranged scanner seeks to (BigTableScanner.java:105-132, SSTableReader.getPositionsForRanges
+// S/io/sstable/format/SSTableReader.java:724). Binary search over the samples, hashing the ~2 x 17 keys it visits; runs on the host for host
+// buffers (so the rest of Index.db never crosses PCIe) and in a one-thread-per-input kernel for device-resident inputs.
+struct IdxSlice { uint64_t lo, hi, uend, s_first, s_count; };
+__host__ __device__ inline int64_t order_token_of(int partitioner, const uint8_t* key, uint32_t kl) {
+    if (partitioner == B200C_PARTITIONER_BYTE_ORDERED) { uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0); return (int64_t)(pre ^ 0x8000000000000000ull); }
+    return murmur3_token(key, kl);
+}
+__host__ __device__ inline bool sample_token(const uint8_t* index, uint64_t ilen, uint64_t off, int partitioner, int64_t* tok) {
+    if (off + 2 > ilen) return false;
+    const uint32_t kl = ((uint32_t)index[off] << 8) | index[off + 1];
+    if (off + 2 + kl > ilen) return false;
+    *tok = order_token_of(partitioner, index + off + 2, kl);
+    return true;
+}
+__host__ __device__ inline bool compute_index_slice(const uint8_t* index, uint64_t ilen, const uint64_t* summ, uint64_t ns, uint64_t data_length, int partitioner,
+                                                    int64_t tlo, int64_t thi, IdxSlice* out) {
+    uint64_t a = 0, b = ns; int64_t t = 0;
+    if (tlo != I64_MIN) while (a < b) { uint64_t mid = (a + b) / 2; if (!sample_token(index, ilen, summ[mid], partitioner, &t)) return false; if (t <= tlo) a = mid + 1; else b = mid; }
+    const uint64_t first = a ? a - 1 : 0;                      // the last sample with token <= token_lo: entries in range may follow it inside its interval
+    a = first; b = ns;
+    while (a < b) { uint64_t mid = (a + b) / 2; if (!sample_token(index, ilen, summ[mid], partitioner, &t)) return false; if (t <= thi) a = mid + 1; else b = mid; }
+    const uint64_t last = a;                                   // first sample with token > token_hi (ns: none)
+    out->lo = summ[first]; out->hi = last < ns ? summ[last] : ilen; out->s_first = first; out->s_count = last - first; out->uend = data_length;
+    if (out->lo > out->hi || out->hi > ilen) return false;
+    if (last < ns) {                                           // the slice's last partition ends where the entry at that sample says the next one starts
+        uint64_t off = summ[last]; if (off + 2 > ilen) return false;
+        const uint32_t kl = ((uint32_t)index[off] << 8) | index[off + 1]; off += 2 + kl;
+        uint64_t pos = 0; if (off >= ilen) return false;
+        const uint32_t f = index[off];
+        if (f < 0x80) pos = f;
+        else { int extra = 0; for (uint32_t x = f; x & 0x80; x <<= 1) extra++; if (extra > 8) extra = 8; if (off + extra >= ilen) return false; pos = extra == 8 ? 0 : (f & (0xFFu >> extra)); for (int k = 1; k <= extra; k++) pos = (pos << 8) | index[off + k]; }
+        if (pos > data_length) return false;
+        out->uend = pos;
+    }
+    return true;
+}
+__global__ void k_index_slices(const uint8_t* const* __restrict__ index, const uint64_t* __restrict__ ilen, const uint64_t* const* __restrict__ summ, const uint64_t* __restrict__ ns,
+                               const uint64_t* __restrict__ dlen, int K, int partitioner, int64_t tlo, int64_t thi, IdxSlice* __restrict__ out, uint32_t* __restrict__ ok) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    ok[i] = compute_index_slice(index[i], ilen[i], summ[i], ns[i], dlen[i], partitioner, tlo, thi, &out[i]) ? 1u : 0u;
 }
 
 // ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
@@ -267,7 +313,7 @@ __global__ void k_input_ranges(const CParams* __restrict__ Pp, const uint64_t* _
     const CParams& P = *Pp;
     if (i >= P.ninputs) return;
     uint64_t n = pcount[i]; const int64_t* t = tok + pbase[i];
-    upos[pbase[i] + n] = P.in[i].ubase + P.in[i].ulen;
+    upos[pbase[i] + n] = P.in[i].ubase + P.in[i].uend;
     uint64_t lo = 0, hi = n;
     if (tlo != I64_MIN) { uint64_t a = 0, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= tlo) a = m + 1; else b = m; } lo = a; }   // first > tlo
     { uint64_t a = lo, b = n; while (a < b) { uint64_t m = (a + b) / 2; if (t[m] <= thi) a = m + 1; else b = m; } hi = a; }                     // first > thi
@@ -803,6 +849,33 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // whatever way this call ends, nothing may still be copying from or into the caller's buffers
     struct CopyGuard { b200c_ctx* c; ~CopyGuard() { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->copy_out); } } copy_guard{c};
 
+    // ---- Index.db slices: a token sub-range with Summary.db samples touches only its part of every Index.db ------------------------------
+    bool have_summaries = true;
+    for (int i = 0; i < K; i++) if (m->inputs[i].index_len && !(m->inputs[i].summary_positions && m->inputs[i].nsummary)) have_summaries = false;
+    const bool sliced = have_summaries && !lcs && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX) && !getenv("B200C_NO_INDEX_SLICES");
+    std::vector<IdxSlice> isl(K);
+    for (int i = 0; i < K; i++) isl[i] = IdxSlice{0, m->inputs[i].index_len, m->inputs[i].data_length, 0, have_summaries ? m->inputs[i].nsummary : 0};
+    if (sliced) {
+        if (!dev) {
+            for (int i = 0; i < K; i++) { const b200c_input& in = m->inputs[i];
+                if (in.index_len && !compute_index_slice(in.index, in.index_len, in.summary_positions, in.nsummary, in.data_length, m->partitioner, m->token_lo, m->token_hi, &isl[i])) {
+                    c->err = "Summary.db positions of input " + std::to_string(i) + " do not point at Index.db entries"; res->corruption.input = i; res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = 0; return B200C_ECORRUPT; } }
+        } else {
+            uint8_t* w; B200C_TRY(ws_typed(c, WS_SLICE, (size_t)K * (8 * 5 + sizeof(IdxSlice) + 4) + 64, &w));
+            std::vector<uint64_t> hv((size_t)K * 5);
+            for (int i = 0; i < K; i++) { const b200c_input& in = m->inputs[i]; hv[i] = (uint64_t)(uintptr_t)in.index; hv[K + i] = in.index_len; hv[2 * K + i] = (uint64_t)(uintptr_t)in.summary_positions; hv[3 * K + i] = in.nsummary; hv[4 * K + i] = in.data_length; }
+            uint64_t* dv = (uint64_t*)w; IdxSlice* dsl = (IdxSlice*)(dv + 5 * K); uint32_t* dok = (uint32_t*)(dsl + K);
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(dv, hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            k_index_slices<<<(K + 63) / 64, 64, 0, c->stream>>>((const uint8_t* const*)dv, dv + K, (const uint64_t* const*)(dv + 2 * K), dv + 3 * K, dv + 4 * K, K, m->partitioner, m->token_lo, m->token_hi, dsl, dok);
+            std::vector<uint32_t> ok(K);
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(isl.data(), dsl, sizeof(IdxSlice) * K, cudaMemcpyDeviceToHost, c->stream));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(ok.data(), dok, 4 * K, cudaMemcpyDeviceToHost, c->stream));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < K; i++) if (m->inputs[i].index_len && !ok[i]) { c->err = "Summary.db positions of input " + std::to_string(i) + " do not point at Index.db entries"; res->corruption.input = i; res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = 0; return B200C_ECORRUPT; }
+                         else if (!m->inputs[i].index_len) isl[i] = IdxSlice{0, 0, m->inputs[i].data_length, 0, 0};
+        }
+    }
+
     // ---- layout of the concatenated device buffers -------------------------------------------------------------------------------
     std::vector<uint64_t> ubase(K + 1), ibase(K + 1), cbase(K + 1), obase(K + 1), bbase(K + 1);
     CParams hp; memset(&hp, 0, sizeof(hp));
@@ -815,12 +888,13 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (in.nchunks != (in.data_length + in.chunk_len - 1) / (uint64_t)in.chunk_len) { c->err = "chunk count does not match data_length"; return B200C_EINVAL; }
         if (in.compressor != COMP_LZ4 && !comp_is_snappy(in.compressor) && in.compressor != COMP_NONE) { c->err = "unknown compressor"; return B200C_EINVAL; }
         ubase[i] = uo; uo += (in.data_length + 64 + 65535) & ~65535ull;
-        ibase[i] = io; io += (in.index_len + 64 + 255) & ~255ull;
+        const uint64_t ilen_i = isl[i].hi - isl[i].lo;               // Index.db bytes this call reads from input i
+        ibase[i] = io; io += (ilen_i + 64 + 255) & ~255ull;
         cbase[i] = co; co += (in.data_len + 64 + 255) & ~255ull;
         obase[i] = oo; oo += in.nchunks + 1;
-        bbase[i] = bo; bo += (in.index_len + IB - 1) / IB;
+        bbase[i] = bo; bo += (ilen_i + IB - 1) / IB;
         InDesc& d = hin[i];
-        d.ubase = ubase[i]; d.ulen = in.data_length; d.ibase = ibase[i]; d.ilen = in.index_len;
+        d.ubase = ubase[i]; d.ulen = in.data_length; d.ibase = ibase[i]; d.ilen = ilen_i; d.uend = isl[i].uend;
         d.min_ts = in.header_stats.min_timestamp; d.min_ldt = in.header_stats.min_local_deletion_time; d.min_ttl = in.header_stats.min_ttl;
         d.ncols = in.ncolumns;
         for (int k = 0; k < in.ncolumns; k++) {
@@ -854,10 +928,9 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
     }
     int want_ranges = (int)cuts.size() + 1;
-    // with Summary.db positions for every input the Index.db walk does not need Data.db: its copies are then scheduled after K2
-    bool have_summaries = true;
-    for (int i = 0; i < K; i++) if (m->inputs[i].index_len && !(m->inputs[i].summary_positions && m->inputs[i].nsummary)) have_summaries = false;
-    const bool deferred = !dev && !lcs && have_summaries;
+    // with Summary.db positions for every input the Index.db walk does not need Data.db: its copies are then scheduled after K2.
+    // Device-resident inputs take the same route when the call is a token sub-range: K2 first, then only the chunks the range crosses are decoded.
+    const bool deferred = !lcs && have_summaries && (!dev || sliced);
     if (!deferred) { want_ranges = 1; cuts.clear(); }
 
     uint8_t *U, *CD, *IDX; uint64_t* CO; CParams* dP; uint64_t* d_bbase; DevErr* d_err; ChunkErr* d_cerr; RunStats* d_stats; unsigned long long* d_hist;
@@ -866,7 +939,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_CO, oo + 1, &CO));
     B200C_TRY(ws_typed(c, WS_IDX, io + 64, &IDX));
     std::vector<uint64_t> sbase(K + 1, 0);
-    for (int i = 0; i < K; i++) sbase[i + 1] = sbase[i] + (have_summaries ? m->inputs[i].nsummary : 0);
+    for (int i = 0; i < K; i++) sbase[i + 1] = sbase[i] + isl[i].s_count;
     uint64_t* d_summ; B200C_TRY(ws_typed(c, WS_SUMM, sbase[K] + 1, &d_summ));
     { uint8_t* pp; B200C_TRY(ws_typed(c, WS_PARAMS, sizeof(CParams) + sizeof(InDesc) * (size_t)K, &pp)); dP = (CParams*)pp; hp.in = (const InDesc*)(pp + sizeof(CParams)); }
     B200C_TRY(ws_typed(c, WS_BBASE, (size_t)K + 1, &d_bbase));
@@ -919,7 +992,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (a >= b) return B200C_OK;
         uint64_t lo = chunk_off(i, a), hi = chunk_off(i, b);
         if (lo > hi || hi > in.data_len) { c->err = "chunk offsets of input " + std::to_string(i) + " are not increasing"; res->corruption.input = i; res->corruption.kind = 2; res->corruption.chunk = a; res->corruption.offset = 0; return B200C_ECORRUPT; }
-        if (hi > lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i] + lo, in.data + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+        if (hi > lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i] + lo, in.data + lo, hi - lo, kind, cs));
         return B200C_OK;
     };
     for (int i = 0; i < K; i++) {
@@ -927,11 +1000,14 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         bytes_read += in.data_length;
         if (!deferred && in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, cs));
         if (in.nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(CO + obase[i], in.chunk_offsets, in.nchunks * 8, kind, cs));
-        if (in.index_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index, in.index_len, kind, cs));
-        if (have_summaries && in.nsummary) B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + sbase[i], in.summary_positions, in.nsummary * 8, kind, cs));
+        if (isl[i].hi > isl[i].lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index + isl[i].lo, isl[i].hi - isl[i].lo, kind, cs));
+        if (isl[i].s_count) {
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + sbase[i], in.summary_positions + isl[i].s_first, isl[i].s_count * 8, kind, cs));
+            if (isl[i].lo) { k_add_u64<<<(unsigned)((isl[i].s_count + 255) / 256), 256, 0, cs>>>(d_summ + sbase[i], isl[i].s_count, (uint64_t)0 - isl[i].lo); c->launches_call++; c->launches_total++; }   // positions relative to the slice
+        }
         B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[i], cs));
     }
-    if (deferred && want_ranges > 1)         // keep the link busy while K2 finishes: the head of every Data.db is needed by the first piece
+    if (deferred && want_ranges > 1 && !sliced)         // keep the link busy while K2 finishes: the head of every Data.db is needed by the first piece
         for (int i = 0; i < K; i++) { uint64_t pre = (uint64_t)(m->inputs[i].nchunks * cuts[0]); B200C_TRY(copy_chunks(i, 0, pre)); h2d_next[i] = pre; }
     c->prog_total.store(bytes_read); c->prog_scanned.store(0);
     for (int i = 0; i < K; i++) c->prog_input_pos[i].store(0);
@@ -995,7 +1071,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         return B200C_OK;
     };
-    if (dev && k1_batching) {                       // device-resident inputs: the staging copies are device-to-device, wait for all and decode in one launch
+    if (dev && k1_batching && !deferred) {          // device-resident inputs: the staging copies are device-to-device, wait for all and decode in one launch
         std::vector<uint64_t> z(K, 0), e(K);
         for (int i = 0; i < K; i++) { B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0)); e[i] = m->inputs[i].nchunks; }
         B200C_TRY(k1_many(z, e));

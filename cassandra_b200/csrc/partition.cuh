@@ -29,7 +29,8 @@ enum { PERR_NONE = 0, PERR_CORRUPT = 1, PERR_UNSUPPORTED = 2 };
 
 struct InDesc {
     uint64_t ubase, ulen;          // this input's uncompressed stream inside U
-    uint64_t ibase, ilen;          // this input's Index.db inside IDX
+    uint64_t ibase, ilen;          // this input's Index.db (or the slice of it a token sub-range needs) inside IDX
+    uint64_t uend;                 // end of the last partition the Index.db slice describes, as an offset in this input's stream (= ulen for the whole file)
     int64_t min_ts, min_ldt; int32_t min_ttl; int32_t ncols;
     int32_t colmap[MAXCOLS];
 };

@@ -544,3 +544,72 @@ def test_metadata_matches_oracle_on_synthetic_tables(ctx, ranges, monkeypatch):
     wide = synth_tables(1, 3, 0x3E7B + ranges, 60, rows_per_partition=400, column_index_size=4096)
     both(ctx, wide, CompactionController(NOW), column_index_size=4096, with_metadata=True)
     both(ctx, tabs, CompactionController(0, 0), with_metadata=True)               # nothing purged: other tombstone / TTL paths
+
+class DeviceEngine:
+    """b200c_compact with B200C_FLAG_DEVICE_PTRS: inputs uploaded to HBM first, outputs produced there and read back (the path bench.py's `value` times)"""
+    needs_lib_bound = True
+    def __init__(self, ctx): self.ctx = ctx
+    def __call__(self, manifest, result):
+        import ctypes as C
+        from cassandra_b200 import native
+        L = native.lib(); ctx = self.ctx; allocs = []
+        def up(ptr, n):
+            d = C.c_void_p(); ctx.check(L.b200c_dev_alloc(ctx.handle, max(n, 1), C.byref(d))); allocs.append(d)
+            if n: ctx.check(L.b200c_memcpy_h2d(ctx.handle, d, ptr, n))
+            return d.value
+        try:
+            host_in = []
+            for k in range(manifest.ninputs):
+                a = manifest.inputs[k]; host_in.append((a.data, a.index, a.chunk_offsets, a.summary_positions))
+                a.data = up(a.data, a.data_len); a.index = up(a.index, a.index_len); a.chunk_offsets = up(a.chunk_offsets, a.nchunks * 8)
+                if a.nsummary: a.summary_positions = up(a.summary_positions, a.nsummary * 8)
+            host_out = []
+            for k in range(result.noutputs_cap):
+                o = result.outputs[k]; host_out.append((o.data, o.index, o.chunk_offsets))
+                o.data = up(None, o.data_cap); o.index = up(None, o.index_cap); o.chunk_offsets = up(None, o.chunk_cap * 8)
+            rc = L.b200c_compact(ctx.handle, C.byref(manifest), C.byref(result), native.FLAG_DEVICE_PTRS)
+            for k in range(result.noutputs_cap):
+                o = result.outputs[k]; hd, hi, hc = host_out[k]
+                if rc == 0 and k < result.noutputs:
+                    if o.data_len: ctx.check(L.b200c_memcpy_d2h(ctx.handle, hd, o.data, o.data_len))
+                    if o.index_len: ctx.check(L.b200c_memcpy_d2h(ctx.handle, hi, o.index, o.index_len))
+                    if o.nchunks: ctx.check(L.b200c_memcpy_d2h(ctx.handle, hc, o.chunk_offsets, o.nchunks * 8))
+                o.data, o.index, o.chunk_offsets = hd, hi, hc
+            for k in range(manifest.ninputs):
+                a = manifest.inputs[k]; a.data, a.index, a.chunk_offsets, a.summary_positions = host_in[k]
+            ctx.check(rc, result.corruption)
+        finally:
+            for d in allocs: L.b200c_dev_free(ctx.handle, d)
+
+def test_device_resident_inputs_whole_ring_and_token_shards(ctx):
+    """B200C_FLAG_DEVICE_PTRS (what bench.py's `value` and the sharded multi-GPU run use): the whole ring, and token sub-ranges, for which
+    only the Index.db slice between the bracketing Summary.db samples is walked and only the chunks the range crosses are decoded.
+    Shards must equal the oracle's and concatenate to the whole-ring output."""
+    tabs = synth_tables(0, 5, 0xD37, 30000)
+    for g, t in enumerate(tabs): t.generation = g
+    want = CompactionTask(tabs, CompactionController(NOW)).execute(O.OracleEngine()).outputs[0]
+    got = CompactionTask(tabs, CompactionController(NOW)).execute(DeviceEngine(ctx)).outputs[0]
+    assert got.data == want.data and got.index == want.index and got.digest == want.digest and got.compression.chunk_offsets == want.compression.chunk_offsets
+    cuts = [-(1 << 63), -(1 << 62) - 12345, -7, (1 << 62) + 99, (1 << 63) - 1]
+    stream = b""
+    for lo, hi in zip(cuts, cuts[1:]):
+        w = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine())
+        for eng in (DeviceEngine(ctx), GpuEngine(ctx)):
+            g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(eng)
+            assert g.outputs[0].data == w.outputs[0].data and g.outputs[0].index == w.outputs[0].index and g.outputs[0].digest == w.outputs[0].digest
+            assert g.stats["bytes_in_range"] == w.stats["bytes_in_range"] and g.stats["merged_row_counts"] == w.stats["merged_row_counts"]
+        stream += decompress_output(w.outputs[0])
+    assert stream == decompress_output(want)
+    # the same without the slices (A/B switch): identical bytes
+    os.environ["B200C_NO_INDEX_SLICES"] = "1"
+    try:
+        g = CompactionTask(tabs, CompactionController(NOW), token_range=(cuts[1], cuts[2])).execute(GpuEngine(ctx))
+        w = CompactionTask(tabs, CompactionController(NOW), token_range=(cuts[1], cuts[2])).execute(O.OracleEngine())
+        assert g.outputs[0].data == w.outputs[0].data and g.outputs[0].index == w.outputs[0].index
+    finally:
+        del os.environ["B200C_NO_INDEX_SLICES"]
+    # a range that holds nothing, and one that ends before the first / starts after the last key
+    for lo, hi in ((5, 6), (-(1 << 63), -(1 << 63) + 5), ((1 << 63) - 7, (1 << 63) - 1)):
+        w = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine())
+        g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(GpuEngine(ctx))
+        assert g.outputs[0].data == w.outputs[0].data and g.outputs[0].partitions == w.outputs[0].partitions

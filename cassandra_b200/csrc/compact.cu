@@ -663,19 +663,24 @@ __global__ void __launch_bounds__(ST_THREADS) k_partition_staged(const K4Args a,
     {   // header of the parameters -> shared memory, with U redirected to the tile
         const uint32_t* g = (const uint32_t*)a.P; uint32_t* d = (uint32_t*)sP;
         for (int i = tid; i < (int)(sizeof(CParams) / 4); i += ST_THREADS) d[i] = g[i];
-        for (int i = tid; i < MAXK; i += ST_THREADS) { s_lo[i] = ~0ull; s_hi[i] = 0; s_len[i] = 0; }
+        for (int i = tid; i < MAXK; i += ST_THREADS) { ((uint32_t*)s_lo)[i] = 0xFFFFFFFFu; ((uint32_t*)s_lo)[MAXK + i] = 0; s_len[i] = 0; }
         if (tid == 0) mbar_init(s_bar, 1);
     }
     __syncthreads();
     if (tid == 0) sP->U = stage;
     const uint64_t c0 = a.op_first[j0], c1 = a.op_first[j1];
-    for (uint64_t c = c0 + tid; c < c1; c += ST_THREADS) {            // first and last partition of every source in this tile
-        const uint64_t e = a.contrib[c]; const int src = (int)((e >> 56) & 0x7F); const unsigned long long idx = e & 0xFFFFFFFFFFull;
-        atomicMin(&s_lo[src], idx); atomicMax(&s_hi[src], idx);
+    // first and last contribution of every source in this tile. A source's partitions appear in increasing order along the contributor list,
+    // so the first / last POSITION of a source gives its lowest / highest partition: native 32-bit shared-memory min / max atomics on the
+    // position (64-bit ones on the partition index would be compare-and-swap loops, 32 lanes deep on the same address)
+    uint32_t* s_first = (uint32_t*)s_lo; uint32_t* s_last = s_first + MAXK;
+    for (uint64_t c = c0 + tid; c < c1; c += ST_THREADS) {
+        const int src = (int)((a.contrib[c] >> 56) & 0x7F);
+        atomicMin(&s_first[src], (uint32_t)(c - c0)); atomicMax(&s_last[src], (uint32_t)(c - c0));
     }
     __syncthreads();
-    if (tid < K && s_lo[tid] != ~0ull) {
-        const uint64_t b0 = a.upos[a.pbase[tid] + s_lo[tid]] & ~15ull, b1 = (a.upos[a.pbase[tid] + s_hi[tid] + 1] + 15) & ~15ull;
+    if (tid < K && s_first[tid] != 0xFFFFFFFFu) {
+        const uint64_t ilo = a.contrib[c0 + s_first[tid]] & 0xFFFFFFFFFFull, ihi = a.contrib[c0 + s_last[tid]] & 0xFFFFFFFFFFull;
+        const uint64_t b0 = a.upos[a.pbase[tid] + ilo] & ~15ull, b1 = (a.upos[a.pbase[tid] + ihi + 1] + 15) & ~15ull;
         s_g0[tid] = b0; s_len[tid] = (uint32_t)min(b1 - b0, (uint64_t)0x7FFFFFF0u);
     }
     __syncthreads();

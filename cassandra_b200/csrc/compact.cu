@@ -38,6 +38,9 @@ int decompress_stream_device(b200c_ctx* c, int comp, const uint8_t* d_data, uint
 int decompress_multi_device(b200c_ctx* c, K1Seg* segs, int nseg, int verify, ChunkErr* d_err, int ws_slot);
 
 enum { IB = 256 };                       // Index.db speculation block
+#ifndef B200C_K4_STAGED_DEFAULT
+#define B200C_K4_STAGED_DEFAULT 0          // flipped to 1 once the staged mapping has beaten the global one on the B200 (profiles/)
+#endif
 #ifndef B200C_K1_BATCH_DEFAULT
 #define B200C_K1_BATCH_DEFAULT true
 #endif
@@ -1385,7 +1388,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
                 B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
                 ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
-                const bool staged = []() { const char* e = getenv("B200C_K4_STAGED"); return !e || atoi(e) != 0; }();      // A/B switch (read per call)
+                const bool staged = []() { const char* e = getenv("B200C_K4_STAGED"); return e ? atoi(e) != 0 : (B200C_K4_STAGED_DEFAULT != 0); }();      // A/B switch (read per call)
                 if (staged) {
                     // tile plan: exclusive scan of the input bytes, cut marks, scan of the marks, tile starts
                     uint64_t *d_inpos, *d_tscan; uint32_t *d_mark, *d_tstart; unsigned long long* d_nbig = (unsigned long long*)(d_stats + 1);

@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 ( nvidia-smi --query-gpu=name,memory.total --format=csv; nproc; free -g | head -2; lscpu | grep -E "Model name|Socket|NUMA|Thread|Core"; which java javac ) > gpurun_out/r2_box.txt 2>&1
 B200C_K4_STAGED=1 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2_gputest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_gputest.log; tail -12 gpurun_out/r2_gputest.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2_gputest_default.log 2>&1; echo "pytest(default switches) rc=$?"; tail -3 gpurun_out/r2_gputest_default.log
 echo "== default (K4 global)"; python tools/one_compaction.py --mib 256 --repeat 3 2>/dev/null | tail -1
 echo "== K4 staged"; B200C_K4_STAGED=1 python tools/one_compaction.py --mib 256 --repeat 3 2>/dev/null | tail -1
 echo "== K5 L1"; B200C_K5=1 python tools/one_compaction.py --mib 256 --repeat 3 2>/dev/null | tail -1

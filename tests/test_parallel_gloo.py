@@ -15,9 +15,22 @@ def _worker(rank, world, port, outdir):
     from cassandra_b200.db.compaction import CompactionTask, CompactionController
     manifest = parallel.broadcast_manifest(dict(seed=0xCA550004, nsst=4, universe=6000, now=1700000000) if rank == 0 else None)
     tabs = synth_tables(0, manifest["nsst"], manifest["seed"], manifest["universe"])
-    lo, hi = parallel.shard_token_ranges(world)[rank]
+    # splitters as bench.py --gpus N picks them: rank 0 hashes evenly spaced Summary.db sample keys (b200c_token, host function of the
+    # product library) and balances the sampled partitions; one broadcast
+    cuts = None
+    if rank == 0:
+        from cassandra_b200 import native
+        L = native.lib(); toks = []
+        for t in tabs:
+            ix = t.index
+            for off in [int(x) for x in t.summary_positions[::7]]:
+                kl = (ix[off] << 8) | ix[off + 1]; key = bytes(ix[off + 2:off + 2 + kl])
+                toks.append(L.b200c_token(native.PARTITIONER_MURMUR3, key, kl))
+        cuts = parallel.weighted_token_ranges(toks, world)
+    cuts = parallel.broadcast_manifest(cuts)
+    lo, hi = cuts[rank]
     r = CompactionTask(tabs, CompactionController(manifest["now"]), token_range=(lo, hi)).execute(O.OracleEngine())
-    counters = dict(rank=rank, partitions=r.outputs[0].partitions, rows=r.outputs[0].rows, bytes_written=r.stats["bytes_written"])
+    counters = dict(rank=rank, in_range=r.stats["bytes_in_range"], partitions=r.outputs[0].partitions, rows=r.outputs[0].rows, bytes_written=r.stats["bytes_written"])
     gathered = parallel.all_gather_counters(counters)
     tmax = parallel.max_over_ranks(1.0 + rank)
     pickle.dump(dict(stream=decompress_output(r.outputs[0]), gathered=gathered, tmax=tmax, manifest=manifest), open(os.path.join(outdir, "r%d.pkl" % rank), "wb"))
@@ -41,6 +54,8 @@ def test_two_rank_token_range_sharding():
     assert res[0]["stream"] + res[1]["stream"] == decompress_output(full.outputs[0])
     assert sum(g["partitions"] for g in res[0]["gathered"]) == full.outputs[0].partitions
     assert sum(g["rows"] for g in res[0]["gathered"]) == full.outputs[0].rows
+    shares = [g["in_range"] for g in res[0]["gathered"]]
+    assert sum(shares) == full.stats["bytes_read"] and min(shares) > 0.4 * sum(shares)        # the sample-weighted splitter balances the shards
 
 def test_range_helpers():
     from cassandra_b200 import parallel

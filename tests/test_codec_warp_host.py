@@ -1,0 +1,48 @@
+"""The warp-per-chunk compressors of K5 (cassandra_b200/csrc/lz4.cuh, snappy.cuh) on the CPU: tests/native/codec_warp_host.cc compiles the very
+device source with g++ and runs it on a 32-fiber warp emulator (tests/native/warp_emu.h: every warp intrinsic is a lockstep rendezvous, a
+collective that not all lanes reach aborts). Output must equal the oracle's / liblz4's / Google snappy's byte for byte — the GPU tests prove the
+same for the CUDA build; this one needs no GPU and lets the speculation logic be developed here."""
+import ctypes as C, os, random, shutil, subprocess, pytest
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+@pytest.fixture(scope="module")
+def warp():
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"): pytest.skip("needs g++ and the CUDA headers")
+    out = os.path.join(ROOT, "tests", "native", "_build", "libcodecwarp.so")
+    srcs = [os.path.join(ROOT, "tests", "native", "codec_warp_host.cc")]
+    deps = srcs + [os.path.join(ROOT, "tests", "native", "warp_emu.h")] + [os.path.join(ROOT, "cassandra_b200", "csrc", f) for f in ("lz4.cuh", "snappy.cuh", "common.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        r = subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fno-strict-aliasing", "-I/usr/local/cuda/include", "-Wno-attributes", "-Wno-unknown-pragmas",
+                            "-o", out] + srcs, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(out); L.warp_compress.restype = C.c_int; L.warp_compress.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_void_p]
+    return L
+
+def run(L, mode, data):
+    out = C.create_string_buffer(len(data) + len(data) // 6 + 64)
+    n = L.warp_compress(mode, data, len(data), out); assert n > 0
+    return out.raw[:n]
+
+def corpus():
+    from test_oracle_codec import _corpus
+    rng = random.Random(0xC0DEC)
+    words = [bytes(rng.getrandbits(8) for _ in range(rng.randint(2, 12))) for _ in range(100)]
+    extra = [b"".join(rng.choice(words) for _ in range(3000))[:16384], bytes(16384), bytes(rng.getrandbits(8) for _ in range(5000)), b"ab" * 4000, b"x" * 13, b"y" * 12, b"0123456789abcdef" * 700]
+    return list(_corpus(random.Random(7)))[:12] + extra
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_lz4_warp_source_equals_the_oracle(warp, mode):
+    for k, d in enumerate(corpus()):
+        d = d[:16384]
+        if not d: continue
+        assert run(warp, mode, d) == O.lz4_compress(d), (k, len(d))
+
+def test_snappy_warp_source_equals_googles_library(warp):
+    from test_snappy_golden import vectors
+    for name, data, want in vectors():
+        if not data: continue
+        assert run(warp, 3, data) == want, name
+        assert run(warp, 2, data) == O.chunk_compress(O.COMP_SNAPPY, data), name

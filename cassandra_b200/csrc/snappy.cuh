@@ -2,7 +2,6 @@
 // Third-party algorithm: Google snappy (snappy-java 1.1.10.4 bundles 1.1.10), portable multiply hash. The reference holds no
 // Snappy-compressed fixture; byte parity is pinned against the library itself in its >= 1.2.0 generation (max_bits = 15,
 // tests/golden/snappy), the 1.1.x generation (max_bits = 14) differing only in kMaxHashTableBits.
-// Round-1 implementation: the greedy matcher runs on lane 0 (sequential), copies and decompression use the whole warp.
 #pragma once
 #include "common.cuh"
 
@@ -41,62 +40,114 @@ __device__ __forceinline__ int snappy_emit_copy(uint8_t* out, int op, int offset
     return snappy_emit_copy64(out, op, offset, len, len < 12);
 }
 
-// one fragment (<= 64 KiB). s_in 4-byte aligned with >= 8 bytes of zeroed slack. Sequential; call from a single lane.
-__device__ int snappy_compress_fragment_seq(const uint8_t* s_in, int base, int input_size, uint16_t* s_tab, int table_size, int max_bits, uint8_t* out, int op) {
+// EmitLiteral, warp wide: tag (+ length bytes) by lane 0, the bytes 32 per step. Returns the new output position (warp-uniform).
+__device__ __forceinline__ int snappy_emit_literal_warp(uint8_t* out, int op, const uint8_t* lit, int len, int lane) {
+    const int n = len - 1;
+    int hdr = 1;
+    if (n < 60) { if (lane == 0) out[op] = (uint8_t)(n << 2); }
+    else {
+        const int count = ((31 - __clz(n)) >> 3) + 1; hdr = 1 + count;
+        if (lane == 0) { out[op] = (uint8_t)((59 + count) << 2); for (int i = 0; i < count; i++) out[op + 1 + i] = (uint8_t)(n >> (8 * i)); }
+    }
+    for (int i = lane; i < len; i += 32) out[op + hdr + i] = lit[i];
+    return op + hdr + len;
+}
+// EmitCopy: 64-byte copies while len >= 68 (3 bytes each, one per lane), then one or two short ones by lane 0
+__device__ __forceinline__ int snappy_emit_copy_warp(uint8_t* out, int op, int offset, int len, bool lt12, int lane) {
+    if (lt12) { if (lane == 0) snappy_emit_copy64(out, op, offset, len, true); return op + ((offset < 2048) ? 2 : 3); }
+    int nfull = 0;
+    if (len >= 68) { nfull = (len - 68) / 64 + 1; for (int i = lane; i < nfull; i += 32) snappy_emit_copy64(out, op + 3 * i, offset, 64, false); op += 3 * nfull; len -= 64 * nfull; }
+    int end = op;
+    if (len > 64) { if (lane == 0) snappy_emit_copy64(out, end, offset, 60, false); end += 3; len -= 60; }
+    const bool l12 = len < 12;
+    if (lane == 0) snappy_emit_copy64(out, end, offset, len, l12);
+    return end + ((l12 && offset < 2048) ? 2 : 3);
+}
+
+// One fragment (<= 64 KiB), whole warp. CompressFragment's greedy matcher is sequential by definition (what position i finds in the hash table
+// depends on every earlier lookup-and-insert); as in lz4.cuh the warp SPECULATES 32 consecutive search attempts at once — hash, table probe and
+// 4-byte compare in parallel, lanes with equal hashes resolved in attempt order with per-bit ballots — and takes the first hit, which is what
+// the sequential loop would have found. After a match the library (1) inserts position ip - 1, (2) tests position ip (lookup + insert: a hit is
+// an immediate copy with no literal), (3) resumes the search at ip + 1: those three ride in the first window as lane 0 (insert only), lane 1
+// (the test) and lanes 2.. (search attempts 0..29), lane order being the sequential order.
+// Attempt k of a search looks at q_k with q_0 = start, q_(k+1) = q_k + (skip_k >> 5), skip_(k+1) = skip_k + (skip_k >> 5), skip_0 = 32; the first 16
+// attempts are unconditional when at least 16 bytes remain before ip_limit (the library's unrolled prologue), every other attempt ends the
+// fragment when its successor would pass ip_limit.
+__device__ int snappy_compress_fragment_warp(const uint8_t* s_in, int base, int input_size, uint16_t* s_tab, int table_size, int max_bits, uint8_t* out, int op, int lane) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     const uint32_t tmask = (uint32_t)table_size - 1;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     int ip = base; const int ip_end = base + input_size;
     if (input_size >= 15) {
         const int ip_limit = base + input_size - 15;
+        bool have_prefix = false;
         for (;;) {
-            int next_emit = ip++;
-            uint32_t skip = 32;
-            int candidate = 0; bool found = false;
-            if (ip_limit - ip >= 16) {
-                int delta = ip - base;
-                for (int i = 0; i < 16; i++) {
-                    uint32_t dword = rd32_at(in32, ip + i);
-                    uint32_t e = snappy_tidx(dword, tmask, max_bits);
-                    candidate = base + s_tab[e];
-                    s_tab[e] = (uint16_t)(delta + i);
-                    if (rd32_at(in32, candidate) == dword) {
-                        out[op] = (uint8_t)(i << 2);
-                        for (int k = 0; k <= i; k++) out[op + 1 + k] = s_in[next_emit + k];
-                        ip += i; op += i + 2; found = true; break;
-                    }
+            const int next_emit = ip;
+            const int start = ip + 1;                                   // `next_emit = ip++`
+            const bool unrolled = ip_limit - start >= 16;
+            int hit_ip = 0, candidate = 0; bool ended = false, immediate = false;
+            int q0 = start; uint32_t skip0 = 32; int a0 = 0;            // state of the first attempt of the current window
+            for (bool first = true;; first = false) {
+                const bool prefixed = first && have_prefix;
+                int q; bool valid, putonly = false; int qn = 0; uint32_t skn = 0;
+                if (prefixed && lane < 2) { q = lane == 0 ? ip - 1 : ip; valid = true; putonly = lane == 0; }
+                else {
+                    const int l = lane - (prefixed ? 2 : 0);
+                    q = q0; uint32_t sk = skip0;
+                    for (int t = 0; t < l; t++) { const uint32_t st = sk >> 5; q += (int)st; sk += st; }       // (one add per earlier attempt; 31 at most)
+                    const uint32_t st = sk >> 5; qn = q + (int)st; skn = sk + st;
+                    valid = (unrolled && a0 + l < 16) || qn <= ip_limit;
                 }
-                if (!found) { ip += 16; skip += 16; }
-            }
-            if (!found) {
-                for (;;) {
-                    uint32_t data = rd32_at(in32, ip);
-                    uint32_t e = snappy_tidx(data, tmask, max_bits);
-                    uint32_t between = skip >> 5; skip += between;
-                    int next_ip = ip + (int)between;
-                    if (next_ip > ip_limit) { ip = next_emit; goto emit_remainder; }
-                    candidate = base + s_tab[e];
-                    s_tab[e] = (uint16_t)(ip - base);
-                    if (data == rd32_at(in32, candidate)) break;
-                    ip = next_ip;
+                const uint32_t dword = valid ? rd32_at(in32, q) : 0u;
+                const uint32_t h = snappy_tidx(dword, tmask, max_bits);
+                int cand = valid ? base + (int)s_tab[h] : 0;
+                uint32_t same = FULL_MASK;
+                for (int b = 0; b < max_bits; b++) { const uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
+                const uint32_t prev = same & lt_mask;
+                const int src = prev ? (31 - __clz(prev)) : lane;
+                const int pq = __shfl_sync(FULL_MASK, q, src);
+                if (prev) cand = pq;
+                const bool hit = valid && !putonly && rd32_at(in32, cand) == dword;
+                const uint32_t hits = __ballot_sync(FULL_MASK, hit);
+                const uint32_t inval = __ballot_sync(FULL_MASK, !valid);
+                const int first_hit = hits ? (__ffs(hits) - 1) : 32;
+                const int first_inv = inval ? (__ffs(inval) - 1) : 32;
+                if (first_hit < first_inv) {
+                    const uint32_t le = (first_hit == 31) ? FULL_MASK : ((2u << first_hit) - 1u);
+                    const uint32_t later_same = same & le & ~lt_mask & ~(1u << lane);
+                    if (lane <= first_hit && !later_same) s_tab[h] = (uint16_t)(q - base);
+                    hit_ip = __shfl_sync(FULL_MASK, q, first_hit);
+                    candidate = __shfl_sync(FULL_MASK, cand, first_hit);
+                    immediate = prefixed && first_hit == 1;
+                    break;
                 }
-                op = snappy_emit_literal(out, op, s_in + next_emit, ip - next_emit);
+                if (first_inv < 32) { ended = true; break; }
+                { const uint32_t later_same = same & ~lt_mask & ~(1u << lane); if (!later_same) s_tab[h] = (uint16_t)(q - base); }
+                __syncwarp();
+                q0 = __shfl_sync(FULL_MASK, qn, 31); skip0 = __shfl_sync(FULL_MASK, skn, 31);                   // the attempt after lane 31's
+                a0 += prefixed ? 30 : 32;
             }
-            do {
-                int b0 = ip; int matched = 4;
-                while (ip + matched < ip_end && s_in[candidate + matched] == s_in[ip + matched]) matched++;
-                bool lt12 = (matched - 4) < 8;
-                ip += matched;
-                op = snappy_emit_copy(out, op, b0 - candidate, matched, lt12);
-                if (ip >= ip_limit) goto emit_remainder;
-                s_tab[snappy_tidx(rd32_at(in32, ip - 1), tmask, max_bits)] = (uint16_t)(ip - base - 1);
-                uint32_t e = snappy_tidx(rd32_at(in32, ip), tmask, max_bits);
-                candidate = base + s_tab[e];
-                s_tab[e] = (uint16_t)(ip - base);
-            } while (rd32_at(in32, ip) == rd32_at(in32, candidate));
+            if (ended) { ip = next_emit; break; }
+            __syncwarp();
+            ip = hit_ip;
+            if (!immediate) op = snappy_emit_literal_warp(out, op, s_in + next_emit, ip - next_emit, lane);
+            // FindMatchLength(candidate + 4, ip + 4, ip_end): 32 bytes per step
+            int matched = 4;
+            for (;;) {
+                const int i = matched + lane;
+                const bool eq = (ip + i < ip_end) && (s_in[candidate + i] == s_in[ip + i]);
+                const uint32_t b = __ballot_sync(FULL_MASK, eq);
+                if (b == FULL_MASK) { matched += 32; continue; }
+                matched += __ffs(~b) - 1;
+                break;
+            }
+            op = snappy_emit_copy_warp(out, op, ip - candidate, matched, (matched - 4) < 8, lane);
+            ip += matched;
+            if (ip >= ip_limit) break;                                  // emit_remainder from here
+            have_prefix = true;
         }
     }
-emit_remainder:
-    if (ip < ip_end) op = snappy_emit_literal(out, op, s_in + ip, ip_end - ip);
+    if (ip < ip_end) op = snappy_emit_literal_warp(out, op, s_in + ip, ip_end - ip, lane);
     return op;
 }
 
@@ -112,8 +163,7 @@ __device__ int snappy_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab,
         int table_size = frag > (1 << max_bits) ? (1 << max_bits) : (frag < 256 ? 256 : (2 << (31 - __clz(frag - 1))));
         for (int i = lane; i < table_size / 2; i += 32) ((uint32_t*)s_tab)[i] = 0;
         __syncwarp();
-        if (lane == 0) op = snappy_compress_fragment_seq(s_in, pos, frag, s_tab, table_size, max_bits, out, op);
-        op = __shfl_sync(FULL_MASK, op, 0);
+        op = snappy_compress_fragment_warp(s_in, pos, frag, s_tab, table_size, max_bits, out, op, lane);
         __syncwarp();
     }
     return op;

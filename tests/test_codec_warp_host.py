@@ -46,3 +46,17 @@ def test_snappy_warp_source_equals_googles_library(warp):
         if not data: continue
         assert run(warp, 3, data) == want, name
         assert run(warp, 2, data) == O.chunk_compress(O.COMP_SNAPPY, data), name
+
+def test_snappy_warp_source_random_differential(warp):
+    """more shapes than the golden vectors: sizes around the 15-byte margin, the 16-attempt prologue, table-size steps and the 64 KiB fragment"""
+    rng = random.Random(0x5A9)
+    alphabet = [bytes(rng.getrandbits(8) for _ in range(rng.randint(1, 9))) for _ in range(30)]
+    for it in range(60):
+        n = rng.choice([1, 2, 14, 15, 16, 17, 30, 31, 32, 33, 100, 255, 256, 257, 1000, 4096, 4097, 16384, 20000, 65536])
+        kind = rng.random()
+        if kind < 0.25: d = bytes(rng.getrandbits(8) for _ in range(n))
+        elif kind < 0.6: d = b"".join(rng.choice(alphabet) for _ in range(n))[:n]
+        elif kind < 0.8: d = bytes(rng.choice(b"ab\x00") for _ in range(n))
+        else: d = (bytes(rng.getrandbits(8) for _ in range(rng.randint(1, 40))) * n)[:n]
+        assert run(warp, 2, d) == O.chunk_compress(O.COMP_SNAPPY, d), (it, n, "2^14")
+        assert run(warp, 3, d) == O.chunk_compress(O.COMP_SNAPPY15, d), (it, n, "2^15")

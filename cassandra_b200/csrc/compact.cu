@@ -49,10 +49,10 @@ enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pi
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
        WS_TOK, WS_KP, WS_KLEN, WS_UPOS, WS_PBASE, WS_RANGE, WS_BSTART, WS_CONTRIB, WS_HEAD, WS_OPIDX, WS_OPFIRST,
-       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG, WS_INSZ, WS_BIG, WS_INPOS, WS_TMARK, WS_TSCAN, WS_TSTART, WS_META_SG, WS_META_TD, WS_META_BLOOM, WS_META_KEYS, WS_META_SUMENT, WS_META_SUMOFF, WS_META_FLAG, WS_META_WRANK, WS_META_SAMPLE, WS_META_ESIZE, WS_META_EPOS, WS_CCOUNT, WS_SLICE,
+       WS_LIST, WS_CURSOR, WS_STMUNF, WS_STROWS, WS_OVF, WS_BOUND, WS_BPOS, WS_SCRATCH, WS_DSIZE, WS_IPAY, WS_NBLK, WS_IHEAD, WS_DPOS, WS_ISIZE, WS_IPOS, WS_UOUT, WS_IOUT, WS_DOUT, WS_OOFFS, WS_STATS, WS_ERR2, WS_LCS0 = 82, WS_LCS1, WS_LCS2, WS_LCS3, WS_LCS4, WS_ICAP, WS_IOFF, WS_ISCR, WS_PLAN, WS_UOUT2, WS_SUMM, WS_PURGE, WS_K1SEG, WS_INSZ, WS_BIG, WS_INPOS, WS_TMARK, WS_TSCAN, WS_TSTART, WS_META_SG, WS_META_TD, WS_META_BLOOM, WS_META_KEYS, WS_META_SUMENT, WS_META_SUMOFF, WS_META_FLAG, WS_META_WRANK, WS_META_SAMPLE, WS_META_ESIZE, WS_META_EPOS, WS_CCOUNT, WS_SLICE, WS_META_TDD,
        WS_SCANA = 60, WS_CODEC = 70 };
 
-static_assert(WS_ERR2 < WS_SCANA && WS_SCANA + 6 <= WS_CODEC && WS_CODEC + 12 <= WS_LCS0 && WS_SLICE < WS_SLOTS, "workspace slot map");
+static_assert(WS_ERR2 < WS_SCANA && WS_SCANA + 6 <= WS_CODEC && WS_CODEC + 12 <= WS_LCS0 && WS_META_TDD < WS_SLOTS, "workspace slot map");
 struct DevErr { unsigned long long code; };       // min over (kind << 56 | input << 48 | offset); ~0 = none
 
 __device__ __forceinline__ void report_err(DevErr* e, int kind, int input, uint64_t off) {
@@ -699,13 +699,30 @@ __global__ void __launch_bounds__(ST_THREADS) k_partition_staged(const K4Args a,
     __syncthreads();
     if (s_len[0] == 0xFFFFFFFFu) return;
     mbar_wait(s_bar, 0);
+    // The lanes leave the wait loop one by one, and threads that were apart when a convergence barrier (BSSY) was set up do not re-join at its
+    // BSYNC: without this barrier every lane ran the whole partition code ALONE (ncu: 1.0 active threads per instruction, 10 x slower than
+    // the round-1 kernel — profiles/r2_k4_staged_divergence.txt). A block-wide barrier re-converges the warps before the per-partition work.
+    __syncthreads();
+    // partitions of the tile in fan-in order (counting sort in shared memory): the lanes of a warp then walk similar numbers of cursors
+    uint8_t* s_order = (uint8_t*)s_lo;                               // (the first/last arrays are dead now) 128 entries + 20 counters behind them
+    uint32_t* s_cnt = (uint32_t*)(s_order + ST_MAXPART);
+    const uint32_t np = j1 - j0;
+    if (tid < ST_MAXM + 2) s_cnt[tid] = 0;
+    __syncthreads();
+    for (uint32_t p = tid; p < np; p += ST_THREADS) { const uint32_t m = (uint32_t)(a.op_first[j0 + p + 1] - a.op_first[j0 + p]); atomicAdd(&s_cnt[min(m, (uint32_t)ST_MAXM + 1)], 1u); }
+    __syncthreads();
+    if (tid == 0) { uint32_t acc = 0; for (int k = 0; k <= ST_MAXM + 1; k++) { const uint32_t n = s_cnt[k]; s_cnt[k] = acc; acc += n; } }
+    __syncthreads();
+    for (uint32_t p = tid; p < np; p += ST_THREADS) { const uint32_t m = (uint32_t)(a.op_first[j0 + p + 1] - a.op_first[j0 + p]); s_order[atomicAdd(&s_cnt[min(m, (uint32_t)ST_MAXM + 1)], 1u)] = (uint8_t)p; }
+    __syncthreads();
     const XlateStaged xl{s_sbase, s_g0};
     const int ncols_s = WIDE ? 0 : sP->ncols;
     MCell merged_local[WIDE ? MAXCOLS : 1];
     MCell* merged = WIDE ? merged_local : cells + (size_t)tid * ncols_s;
     DT open_dt[ST_MAXM];
     StatAcc acc; acc.init(sP->now, a.td);
-    for (uint32_t j = j0 + tid; j < j1; j += ST_THREADS) {
+    for (uint32_t t = tid; t < np; t += ST_THREADS) {
+        const uint32_t j = j0 + s_order[t];
         uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf, ixs_cap;
         if (!k4_prologue<true>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) continue;
         const uint64_t cj = a.op_first[j]; const uint32_t m = (uint32_t)(a.op_first[j + 1] - cj);
@@ -1535,7 +1552,10 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // Filter.db / Summary.db / first+last key / statistics side band of the single output -> the caller's (host) buffers
     auto finish_meta = [&](b200c_output& out) -> int {
         if (!want_meta) return B200C_OK;
-        B200C_LAUNCH(c, k_tdrop_final, 4, 1024, 0, d_td, d_sg);
+        TdropDense* d_tdd; B200C_TRY(ws_typed(c, WS_META_TDD, 1, &d_tdd));
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_tdd, 0, 8, st));
+        B200C_LAUNCH(c, k_tdrop_compact, TDROP_SLOTS / 1024, 1024, 0, d_td, d_tdd);
+        B200C_LAUNCH(c, k_tdrop_final, TDROP_SLOTS / 1024, 1024, 0, d_td, d_tdd, d_sg);
         std::vector<uint8_t> hb(sizeof(StatGlobal)); StatGlobal* g = (StatGlobal*)hb.data();
         B200C_CUDA_TRY(c, cudaMemcpyAsync(g, d_sg, sizeof(StatGlobal), cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));

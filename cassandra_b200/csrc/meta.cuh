@@ -170,17 +170,24 @@ __global__ void __launch_bounds__(256) k_summary_emit(const MetaArgs a, uint64_t
 __global__ void k_meta_advance(StatGlobal* g, uint64_t nsamples, const uint64_t* __restrict__ epos) {
     g->nsamples += nsamples; g->sum_bytes += nsamples ? epos[nsamples] : 0;
 }
-// exact tombstone drop-time histogram: hash table -> the B200C_TDROP_CAP smallest points, ascending (rank by counting; the table is tiny)
-__global__ void __launch_bounds__(1024) k_tdrop_final(const TdropTable* __restrict__ td, StatGlobal* g) {
+// exact tombstone drop-time histogram: hash table -> dense list -> the B200C_TDROP_CAP smallest points, ascending (rank by counting)
+struct TdropDense { unsigned long long n; unsigned long long key[TDROP_SLOTS], cnt[TDROP_SLOTS]; };
+__global__ void __launch_bounds__(1024) k_tdrop_compact(const TdropTable* __restrict__ td, TdropDense* __restrict__ d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 4096) return;
+    if (i >= TDROP_SLOTS) return;
     const unsigned long long k = td->key[i];
     if (k == ~0ull) return;
+    const unsigned long long at = atomicAdd(&d->n, 1ull);
+    d->key[at] = k; d->cnt[at] = td->cnt[i];
+}
+__global__ void __launch_bounds__(1024) k_tdrop_final(const TdropTable* __restrict__ td, const TdropDense* __restrict__ d, StatGlobal* g) {
+    const unsigned long long n = d->n; const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { g->tdrop_n = n; if (td->overflow || n > B200C_TDROP_CAP) g->tdrop_overflow = 1; }
+    if (i >= n) return;
+    const unsigned long long k = d->key[i];
     unsigned int rank = 0;
-    for (int q = 0; q < 4096; q++) { unsigned long long o = td->key[q]; if (o != ~0ull && o < k) rank++; }
-    atomicAdd(&g->tdrop_n, 1ull);
-    if (rank < B200C_TDROP_CAP) { g->tdrop_point[rank] = (long long)k; g->tdrop_count[rank] = td->cnt[i]; } else g->tdrop_overflow = 1;
-    if (td->overflow) g->tdrop_overflow = 1;
+    for (unsigned long long q = 0; q < n; q++) rank += d->key[q] < k ? 1u : 0u;
+    if (rank < B200C_TDROP_CAP) { g->tdrop_point[rank] = (long long)k; g->tdrop_count[rank] = d->cnt[i]; }
 }
 
 } // namespace b200c

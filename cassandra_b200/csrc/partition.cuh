@@ -312,7 +312,8 @@ enum { IXS_HEAD = 16, IXS_PER_BLOCK = 204, IXS_BLOCK_STRIDE = 4 + IXS_PER_BLOCK 
 // ---- MetadataCollector's reductions, gathered where the rows are written (S/io/sstable/metadata/MetadataCollector.java:208-270; called from
 // SortedTableWriter.startPartition / addRow / addRangeTomstoneMarker S/io/sstable/format/SortedTableWriter.java:183-238 and Rows.collectStats
 // S/db/rows/Rows.java:102-113). One accumulator per thread, in registers; the kernels fold them into a StatGlobal at the end of the block.
-struct TdropTable { unsigned long long key[4096]; unsigned long long cnt[4096]; unsigned int overflow; unsigned int _pad; };   // rounded drop time -> count
+enum { TDROP_SLOTS = 65536 };             // distinct 60 s-rounded drop times the table can hold (45 days of minutes); beyond: overflow flag
+struct TdropTable { unsigned long long key[TDROP_SLOTS]; unsigned long long cnt[TDROP_SLOTS]; unsigned int overflow; unsigned int _pad; };   // rounded drop time -> count
 struct StatAcc {
     int64_t min_ts, max_ts, min_ldt, max_ldt; int32_t min_ttl, max_ttl; uint32_t seen;     // seen: bit0 ts, bit1 ldt, bit2 ttl
     unsigned long long rows, cols, cells, tombs; uint32_t pdel, part_cells;
@@ -324,8 +325,8 @@ struct StatAcc {
 #ifdef __CUDA_ARCH__
         if (!td) return;
         const int64_t d = v % 60; const unsigned long long pt = (unsigned long long)(d == 0 ? v : v + (60 - d));
-        uint32_t h = (uint32_t)((pt / 60) * 2654435761ull) & 4095u;
-        for (int probe = 0; probe < 4096; probe++, h = (h + 1) & 4095u) {
+        uint32_t h = (uint32_t)(((pt / 60) * 2654435761ull) >> 8) & (TDROP_SLOTS - 1);
+        for (int probe = 0; probe < 1024; probe++, h = (h + 1) & (TDROP_SLOTS - 1)) {
             unsigned long long k = td->key[h];
             if (k != pt) { if (k != ~0ull) continue; k = atomicCAS(&td->key[h], ~0ull, pt); if (k != ~0ull && k != pt) continue; }
             atomicAdd(&td->cnt[h], 1ull); return;

@@ -115,9 +115,12 @@ struct Source {
     const b200c_input* in;
     // uncompressed Data stream: allocated uninitialised and decompressed chunk by chunk on first touch (CompressedChunkReader reads
     // chunks on demand too, S/io/util/CompressedChunkReader.java:103-173), so a token sub-range only pays for the chunks it crosses
-    std::unique_ptr<uint8_t[]> buf; uint64_t dlen = 0;
+    // A token sub-range allocates only the span of the stream it can touch (span0 .. span0 + span bytes, chunk aligned): thousands of range
+    // tasks each mapping a whole-file buffer would serialise on the kernel's address-space lock.
+    std::unique_ptr<uint8_t[]> buf; uint64_t dlen = 0, span0 = 0, span1 = 0;
     std::vector<bool> have_chunk;
-    const uint8_t* dptr() const { return buf.get(); }
+    const uint8_t* dptr() const { return buf.get() - span0; }       // biased: dptr() + stream offset, valid for offsets in [span0, span1)
+    uint8_t* wptr() { return buf.get() - span0; }
     uint64_t dsize() const { return dlen; }
     void need(uint64_t lo, uint64_t hi);      // make bytes [lo, hi) of the stream available
     uint64_t pos = 0;               // cursor: start of the current partition
@@ -273,9 +276,9 @@ static void load_chunk(Source& src, uint64_t i) {
     int ulen = (int)std::min<uint64_t>(in.chunk_len, in.data_length - ustart);
     if ((int64_t)clen >= (int64_t)in.max_compressed_len) {              // raw chunk (:116,219)
         if ((int)clen < ulen) throw Corrupt{src.idx, 2, i, off, "short raw chunk"};
-        memcpy(src.buf.get() + ustart, c, ulen);
+        memcpy(src.wptr() + ustart, c, ulen);
     } else {
-        int got = chunk_decompress(in.compressor, c, (int)clen, src.buf.get() + ustart, ulen);
+        int got = chunk_decompress(in.compressor, c, (int)clen, src.wptr() + ustart, ulen);
         if (got != ulen) throw Corrupt{src.idx, 2, i, off, "malformed compressed chunk"};
     }
     src.have_chunk[i] = true;
@@ -284,32 +287,44 @@ void Source::need(uint64_t lo, uint64_t hi) {
     if (hi > dlen) hi = dlen;
     if (lo >= hi) return;
     const uint64_t L = (uint64_t)in->chunk_len;
+    if (lo < span0 || hi > span1) throw Corrupt{idx, 3, 0, lo, "Index.db position outside the range the Summary.db samples bracket"};
     for (uint64_t i = lo / L; i <= (hi - 1) / L; i++) if (!have_chunk[i]) load_chunk(*this, i);
 }
-static void open_source(Source& src, bool whole) {
-    const b200c_input& in = *src.in;
-    uint64_t nch = in.nchunks;
-    if (nch != (in.data_length + in.chunk_len - 1) / (uint64_t)in.chunk_len) throw Corrupt{src.idx, 2, 0, 0, "chunk count"};
-    src.buf.reset(new uint8_t[in.data_length + 64]);                    // uninitialised on purpose: nothing is read before its chunk was decoded
-    memset(src.buf.get() + in.data_length, 0, 64);
-    src.dlen = in.data_length; src.have_chunk.assign(nch, false);
-    if (whole) src.need(0, in.data_length);                             // a whole-ring compaction reads (and checksums) every chunk, as the reference does
-}
 static int64_t order_token(const uint8_t* key, int kl);
-// ranged scanner: start the Index.db walk at the last Summary.db sample whose token is <= token_lo instead of at the file start
-// (BigTableScanner seeks with the index summary too, S/io/sstable/format/big/BigTableScanner.java:105-132)
-static void seek_source(Source& src, int64_t tok_lo) {
+// data position stored in the Index.db entry at `off` (u16 keyLen | key | vint position | ...)
+static uint64_t entry_position(const b200c_input& in, uint64_t off, int idx) {
+    Reader r{in.index + off, in.index + in.index_len, idx};
+    int kl = r.u16(); r.bytes(kl); return r.vint();
+}
+// Opens the stream for (tok_lo, tok_hi]. Ranged scanner: the Index.db walk starts at the last Summary.db sample whose token is <= tok_lo
+// instead of at the file start and cannot pass the first sample whose token is > tok_hi (BigTableScanner seeks with the index summary too,
+// S/io/sstable/format/big/BigTableScanner.java:105-132); the stream buffer covers exactly the chunks between those two samples.
+static void open_source(Source& src, int64_t tok_lo, int64_t tok_hi) {
     const b200c_input& in = *src.in;
-    if (tok_lo == INT64_MIN || !in.summary_positions || !in.nsummary) return;
-    uint64_t a = 0, b = in.nsummary;                                     // first sample with token > tok_lo
-    while (a < b) {
-        uint64_t mid = (a + b) / 2, off = in.summary_positions[mid];
-        if (off + 2 > in.index_len) { b = mid; continue; }
-        int kl = (in.index[off] << 8) | in.index[off + 1];
-        if (off + 2 + kl > in.index_len) { b = mid; continue; }
-        if (order_token(in.index + off + 2, kl) <= tok_lo) a = mid + 1; else b = mid;
+    uint64_t nch = in.nchunks; const uint64_t L = (uint64_t)in.chunk_len;
+    if (nch != (in.data_length + in.chunk_len - 1) / L) throw Corrupt{src.idx, 2, 0, 0, "chunk count"};
+    src.dlen = in.data_length; src.have_chunk.assign(nch, false);
+    uint64_t lo = 0, hi = in.data_length;
+    const bool whole = tok_lo == INT64_MIN && tok_hi == INT64_MAX;
+    if (!whole && in.summary_positions && in.nsummary && in.index_len) {
+        auto tok_at = [&](uint64_t k) { uint64_t off = in.summary_positions[k]; if (off + 2 > in.index_len) throw Corrupt{src.idx, 3, 0, off, "summary position"};
+                                        int kl = (in.index[off] << 8) | in.index[off + 1]; if (off + 2 + kl > in.index_len) throw Corrupt{src.idx, 3, 0, off, "summary position"};
+                                        return order_token(in.index + off + 2, kl); };
+        uint64_t a = 0, b = in.nsummary;                                   // first sample with token > tok_lo
+        if (tok_lo != INT64_MIN) while (a < b) { uint64_t mid = (a + b) / 2; if (tok_at(mid) <= tok_lo) a = mid + 1; else b = mid; }
+        const uint64_t first = a ? a - 1 : 0;
+        a = first; b = in.nsummary;                                        // first sample with token > tok_hi
+        while (a < b) { uint64_t mid = (a + b) / 2; if (tok_at(mid) <= tok_hi) a = mid + 1; else b = mid; }
+        src.ipos = in.summary_positions[first];
+        lo = entry_position(in, in.summary_positions[first], src.idx);
+        if (a < in.nsummary) hi = entry_position(in, in.summary_positions[a], src.idx);
+        if (lo > hi || hi > in.data_length) throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db positions"};
     }
-    if (a > 0) src.ipos = in.summary_positions[a - 1];
+    src.span0 = lo / L * L; src.span1 = std::min<uint64_t>(in.data_length, (hi + L - 1) / L * L);
+    if (src.span1 < src.span0) src.span1 = src.span0;
+    src.buf.reset(new uint8_t[src.span1 - src.span0 + 64]);               // uninitialised on purpose: nothing is read before its chunk was decoded
+    memset(src.buf.get() + (src.span1 - src.span0), 0, 64);
+    if (whole) src.need(0, in.data_length);                               // a whole-ring compaction reads (and checksums) every chunk, as the reference does
 }
 
 // the order-defining token: Murmur3Partitioner.getToken (S/dht/Murmur3Partitioner.java:256-296), or for ByteOrderedPartitioner
@@ -602,7 +617,7 @@ struct Meta {
         for (int i = 0; i < B200C_PSIZE_BUCKETS; i++) st->partition_size_hist[i] = psize[i];
         for (int i = 0; i < B200C_CELLS_BUCKETS; i++) st->cells_per_partition_hist[i] = cells[i];
         uint32_t k = 0;
-        for (auto& kv : tdrop) { if (k >= B200C_TDROP_CAP) { st->tdrop_overflow = 1; break; } st->tdrop_point[k] = kv.first; st->tdrop_count[k] = kv.second; k++; }
+        for (auto& kv : tdrop) { if (k >= B200C_TDROP_CAP) { st->tdrop_overflow = 1; break; } st->tdrop_point[k] = kv.first; st->tdrop_count[k] = kv.second; k++; }      // the CAP smallest points
         st->ntdrop = k;
         memcpy(st->hll_registers, hll.data(), hll.size());
     }
@@ -791,8 +806,7 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
     g_partitioner = m->partitioner;
     std::vector<Source> srcs(m->ninputs);
     uint64_t bytes_read = 0;
-    const bool whole_ring = m->token_lo == INT64_MIN && m->token_hi == INT64_MAX;
-    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; open_source(srcs[i], whole_ring); seek_source(srcs[i], m->token_lo); bytes_read += srcs[i].dsize(); next_partition(srcs[i], m->token_lo, m->token_hi); }
+    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; open_source(srcs[i], m->token_lo, m->token_hi); bytes_read += srcs[i].dsize(); next_partition(srcs[i], m->token_lo, m->token_hi); }
     if (m->partitioner != B200C_PARTITIONER_MURMUR3 && m->partitioner != B200C_PARTITIONER_BYTE_ORDERED) return B200C_EUNSUPPORTED;
     if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) return B200C_EUNSUPPORTED;
     Purger pg{m->now_in_sec, m->gc_before, m->purge_max_timestamp};

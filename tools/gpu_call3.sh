@@ -20,7 +20,7 @@ timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r
 B200C_K4_STAGED=1 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r3_traffic_cfg1_staged.csv python tools/one_compaction.py --mib 1024 --repeat 1 > /dev/null 2>&1; echo "traffic staged rc=$?"
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r3_traffic_cfg1_global.csv python tools/one_compaction.py --mib 1024 --repeat 1 > /dev/null 2>&1; echo "traffic global rc=$?"
 B200C_K4_STAGED=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_partition_staged -c 1 -o gpurun_out/r3_prof_staged python tools/one_compaction.py --mib 256 --repeat 1 > /dev/null 2>&1; echo "ncu staged rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_compress_chunks_lz4_direct -s 20 -c 1 -o gpurun_out/r3_prof_k5 python tools/one_compaction.py --mib 256 --repeat 1 > /dev/null 2>&1; echo "ncu k5 rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_compress_chunks_lz4_direct -s 16 -c 1 -o gpurun_out/r3_prof_k5 python tools/one_compaction.py --mib 256 --repeat 1 > /dev/null 2>&1; echo "ncu k5 rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_decompress_multi_thr -c 1 -o gpurun_out/r3_prof_k1 python tools/one_compaction.py --mib 256 --repeat 1 > /dev/null 2>&1; echo "ncu k1 rc=$?"
 B200C_K4_STAGED=1 timeout 900 python bench.py --workload cfg2 --steps 3 --warmup 3 > gpurun_out/r3_bench_cfg2.json 2> gpurun_out/r3_bench_cfg2.err; echo "cfg2 rc=$?"; tail -2 gpurun_out/r3_bench_cfg2.err; cut -c1-900 gpurun_out/r3_bench_cfg2.json
 B200C_K4_STAGED=1 timeout 900 python bench.py --workload cfg4 --steps 3 --warmup 3 > gpurun_out/r3_bench_cfg4.json 2> gpurun_out/r3_bench_cfg4.err; echo "cfg4 rc=$?"; tail -2 gpurun_out/r3_bench_cfg4.err; cut -c1-900 gpurun_out/r3_bench_cfg4.json

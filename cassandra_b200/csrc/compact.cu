@@ -503,23 +503,25 @@ struct RunStats { unsigned long long merged_unfiltereds, rows_out, partitions_ou
 //            class streams through U once instead of once per (m, size) bin,
 //   m, size bucket: threads of a warp run the same number of cursors over similarly sized partitions (less divergence).
 enum { SORT_BUCKETS = 16, SORT_BINS = MAXK * SORT_BUCKETS };
-__device__ __forceinline__ uint32_t fanin_class(uint32_t m) { return m <= 8 ? 0u : (m <= 16 ? 1u : (m <= 32 ? 2u : 3u)); }
-__device__ __forceinline__ uint64_t sort_key(uint32_t m, uint64_t bound, uint64_t j, uint32_t tile_shift, uint64_t ntiles) {
+// wide_bound: partitions whose inputs exceed it go to the warp-per-partition kernel whatever their fan-in (one lane per source parses in
+// parallel, the tournament runs on shuffles): a single thread walking hundreds of KB is the slowest thing the GPU can do (schema W)
+__device__ __forceinline__ uint32_t fanin_class(uint32_t m, uint64_t bound, uint64_t wide_bound) { return (bound > wide_bound && m <= 32) ? 2u : (m <= 8 ? 0u : (m <= 16 ? 1u : (m <= 32 ? 2u : 3u))); }
+__device__ __forceinline__ uint64_t sort_key(uint32_t m, uint64_t bound, uint64_t j, uint32_t tile_shift, uint64_t ntiles, uint64_t wide_bound) {
     uint64_t avg = bound / (m ? m : 1);
     uint32_t bucket = (uint32_t)min((uint64_t)(SORT_BUCKETS - 1), avg >> 5);
-    return ((uint64_t)fanin_class(m) * ntiles + (j >> tile_shift)) * SORT_BINS + (m - 1) * SORT_BUCKETS + bucket;
+    return ((uint64_t)fanin_class(m, bound, wide_bound) * ntiles + (j >> tile_shift)) * SORT_BINS + (m - 1) * SORT_BUCKETS + bucket;
 }
 __global__ void __launch_bounds__(256) k_class_hist(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts,
-                                                    uint32_t tile_shift, uint64_t ntiles, unsigned long long* __restrict__ hist) {
+                                                    uint32_t tile_shift, uint64_t ntiles, uint64_t wide_bound, unsigned long long* __restrict__ hist) {
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nparts; j += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&hist[sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j], j, tile_shift, ntiles)], 1ull);
+        atomicAdd(&hist[sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j], j, tile_shift, ntiles, wide_bound)], 1ull);
 }
 // warp-aggregated counting-sort scatter: list[cursor[key]++] = j
 __global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restrict__ op_first, const uint64_t* __restrict__ bound, uint64_t nparts,
-                                                       uint32_t tile_shift, uint64_t ntiles, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
+                                                       uint32_t tile_shift, uint64_t ntiles, uint64_t wide_bound, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ list) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = j < nparts;
-    uint64_t key = valid ? sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j], j, tile_shift, ntiles) : ~0ull;
+    uint64_t key = valid ? sort_key((uint32_t)(op_first[j + 1] - op_first[j]), bound[j], j, tile_shift, ntiles, wide_bound) : ~0ull;
     uint32_t peers = __match_any_sync(FULL_MASK, key);
     int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
     unsigned long long base = 0;
@@ -1319,14 +1321,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             uint64_t per_part = std::max<uint64_t>(1, range_bytes[r] / std::max<uint64_t>(1, nparts));
             uint32_t tile_shift = 12; while (tile_shift < 24 && ((1ull << (tile_shift + 1)) * per_part) <= (32ull << 20)) tile_shift++;
             const uint64_t ntiles = (nparts >> tile_shift) + 1, nkeys = 4 * ntiles * SORT_BINS;
+            const uint64_t wide_bound = []() -> uint64_t { const char* e = getenv("B200C_K4_WIDE_WARP"); return e ? strtoull(e, nullptr, 10) : 0; }() ?: ~0ull;    // bytes; unset / 0 = off (A/B)
             B200C_TRY(ws_typed(c, WS_CURSOR, nkeys + 2, &d_cursor));
             B200C_CUDA_TRY(c, cudaMemsetAsync(d_cursor, 0, (nkeys + 2) * 8, st));
-            B200C_LAUNCH(c, k_class_hist, 1184, 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor);
+            B200C_LAUNCH(c, k_class_hist, 1184, 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, wide_bound, d_cursor);
             B200C_TRY(exclusive_scan<uint64_t>(c, (const uint64_t*)d_cursor, nkeys, (uint64_t*)d_cursor, WS_SCANA, 0));
             for (int k = 1; k <= 3; k++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512 + k, (uint64_t*)d_cursor + (uint64_t)k * ntiles * SORT_BINS, 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
             n_le8 = h[513]; n_le16 = h[514]; n_le32 = h[515];
-            B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, d_cursor, d_list);
+            B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, wide_bound, d_cursor, d_list);
         }
         B200C_TRY(check_cancel());
 

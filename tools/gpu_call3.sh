@@ -25,3 +25,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_de
 B200C_K4_STAGED=1 timeout 900 python bench.py --workload cfg2 --steps 3 --warmup 3 > gpurun_out/r3_bench_cfg2.json 2> gpurun_out/r3_bench_cfg2.err; echo "cfg2 rc=$?"; tail -2 gpurun_out/r3_bench_cfg2.err; cut -c1-900 gpurun_out/r3_bench_cfg2.json
 B200C_K4_STAGED=1 timeout 900 python bench.py --workload cfg4 --steps 3 --warmup 3 > gpurun_out/r3_bench_cfg4.json 2> gpurun_out/r3_bench_cfg4.err; echo "cfg4 rc=$?"; tail -2 gpurun_out/r3_bench_cfg4.err; cut -c1-900 gpurun_out/r3_bench_cfg4.json
 ls -la gpurun_out/r3_* | head -20
+echo "== schema W 8x256MiB default"; python tools/one_compaction.py --workload cfg4 --mib 256 --repeat 2 2>/dev/null | tail -1
+echo "== schema W 8x256MiB wide->warp (32 KiB)"; B200C_K4_WIDE_WARP=32768 python tools/one_compaction.py --workload cfg4 --mib 256 --repeat 2 2>/dev/null | tail -1
+B200C_K4_WIDE_WARP=32768 timeout 600 python -m pytest tests/test_gpu_compaction.py -m gpu -q -k "wide or synthetic_configs or streaming_matches or lcs_wide" > gpurun_out/r3_gputest_widewarp.log 2>&1; echo "pytest(wide->warp) rc=$?"; tail -3 gpurun_out/r3_gputest_widewarp.log

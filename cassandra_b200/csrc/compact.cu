@@ -1548,7 +1548,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         memcpy(&rs, h + 8, sizeof(rs));
         memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
         for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
-        res->bytes_read = bytes_read; res->bytes_in_range = bytes_in_range; res->bytes_written = ubase_total; res->total_source_rows = rs.merged_unfiltereds; res->input_partitions = ncontrib_total;
+        res->bytes_read = bytes_read; res->bytes_in_range = bytes_in_range; res->bytes_written = ubase_total; res->total_source_rows = rs.merged_unfiltereds + nparts_total /* one applyToStatic -> updateProgress per merged partition */; res->input_partitions = ncontrib_total;
         res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
         return B200C_OK;
     };

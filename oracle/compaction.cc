@@ -824,6 +824,8 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
         std::vector<int> group;
         for (int i = 0; i < m->ninputs; i++) if (srcs[i].has && compare_key(srcs[i], srcs[best]) == 0) group.push_back(i);
         res->merged_row_counts[group.size() - 1]++;       // CompactionIterator.updateCounterFor :220-232
+        total_source_rows++;                               // Purger.applyToStatic -> updateProgress(): BaseRows applies it to every partition's static row, the empty one included
+                                                           // (S/db/transform/BaseRows.java:106-110, S/db/partitions/PurgeFunction.java:101-106, CompactionIterator.java:365-371)
         input_partitions += group.size();
         // LCS: CompactionAwareWriter.maybeSwitchWriter / MaxSSTableSizeWriter.shouldSwitchWriterInCurrentLocation :76-79 (before each partition)
         if (m->max_sstable_bytes && w.chunk_offset > m->max_sstable_bytes) { w.finish_output(); w.start_output(); }

@@ -179,6 +179,6 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
         if (memcmp(u2.data(), uout, dpos[nparts]) || memcmp(i2.data(), iout, ipos[nparts])) return fail(err, errcap, "staged pass produced different bytes");
         if (st3.merged_unfiltereds != st2.merged_unfiltereds || st3.rows_out != st2.rows_out) return fail(err, errcap, "staged pass counters differ");
     }
-    if (stats) { stats[0] = st.merged_unfiltereds; stats[1] = st.rows_out; stats[2] = written; }
+    if (stats) { stats[0] = st.merged_unfiltereds + nparts; stats[1] = st.rows_out; stats[2] = written; }
     return 0;
 }

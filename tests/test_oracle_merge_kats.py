@@ -212,7 +212,7 @@ def test_dsl_merge_examples():
     # markers vanish (RangeTombstoneMarker.Merger emits only on change); the exclusive end at 30 sorts before row 30
     assert kinds == [(K_INCL_START, 5, None, 140), (K_INCL_END_EXCL_START, 7, 140, 160), ("row", 15, 180), (K_EXCL_END, 30, 160, None),
                      ("row", 30, 150), ("row", 40, 120)]
-    assert r.stats["total_source_rows"] == 6          # merged, non-null unfiltereds entering the purger (Purger.updateProgress)
+    assert r.stats["total_source_rows"] == 6 + 1      # merged, non-null unfiltereds entering the purger plus the partition's static-row step (Purger.applyToStatic/applyToRow/applyToMarker -> updateProgress)
 
 def test_builder_output_is_identity_under_oracle():
     """independent writer vs oracle writer: compacting a single table with nothing purgeable reproduces its bytes"""
@@ -236,4 +236,4 @@ def test_empty_rows_are_skipped_at_read_time():
     b = Builder(S1, (0, 0, 0))
     t = b.build([Partition(b"k", [Row((I32(1),), []), Row((I32(2),), [Cell(0, 5, b"v")])])])
     parts, r = compact([t], gc_grace=10**9)
-    assert [u.ck for u in parts[0].unfiltereds] == [(I32(2),)] and r.stats["total_source_rows"] == 1
+    assert [u.ck for u in parts[0].unfiltereds] == [(I32(2),)] and r.stats["total_source_rows"] == 1 + 1

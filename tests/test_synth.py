@@ -16,7 +16,7 @@ def test_generated_tables_are_identity_stable(schema, universe, rpp, cis):
         assert decompress_output(o) == t.uncompressed
         assert o.index == t.index
         assert o.data == t.data and o.compression.chunk_offsets == t.compression.chunk_offsets
-        assert o.partitions == t.partitions and o.rows == t.rows == r.stats["total_source_rows"]
+        assert o.partitions == t.partitions and o.rows == t.rows == r.stats["total_source_rows"] - t.partitions
 
 def test_wide_schema_has_promoted_index_and_range_tombstones():
     (t,) = synth_tables(1, 1, 77, 60, p=1.0, rows_per_partition=1000)

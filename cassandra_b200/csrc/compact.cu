@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     extern __shared__ __align__(16) uint8_t s_raw[];
     // per thread in shared memory: M_CAP cursors, then (for tables with <= K4_SMEM_COLS columns) the merged-row scratch; +8 bytes
     // so that consecutive threads start in different banks. Wider tables keep the merged row in local memory.
-    const int ncols_s = a.P->ncols <= K4_SMEM_COLS ? a.P->ncols : 0;
+    const int ncols_s = a.P->mcols <= K4_SMEM_COLS ? a.P->mcols : 0;
     const int stride = M_CAP * SLOT_BYTES + ncols_s * (int)sizeof(MCell) + 8;
     Cur* cur = (Cur*)(s_raw + (size_t)threadIdx.x * stride);
     MCell merged_local[MAXCOLS];
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(128) k_partition_warp(const K4Args a, uint64_t
     extern __shared__ __align__(16) uint8_t s_raw[];
     auto tile = cg::tiled_partition<32>(cg::this_thread_block());
     const int tid = threadIdx.x / 32;
-    MCell* s_cells = (MCell*)s_raw + (size_t)tid * a.P->ncols;
+    MCell* s_cells = (MCell*)s_raw + (size_t)tid * a.P->mcols;
     uint64_t t = lo + (uint64_t)blockIdx.x * 4 + tid;
     if (t >= hi) return;
     uint64_t j = a.list[t];
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_partition_staged(const K4Args a,
     for (uint32_t p = tid; p < np; p += ST_THREADS) { const uint32_t m = (uint32_t)(a.op_first[j0 + p + 1] - a.op_first[j0 + p]); s_order[atomicAdd(&s_cnt[min(m, (uint32_t)ST_MAXM + 1)], 1u)] = (uint8_t)p; }
     __syncthreads();
     const XlateStaged xl{s_sbase, s_g0};
-    const int ncols_s = WIDE ? 0 : sP->ncols;
+    const int ncols_s = WIDE ? 0 : sP->mcols;
     MCell merged_local[WIDE ? MAXCOLS : 1];
     MCell* merged = WIDE ? merged_local : cells + (size_t)tid * ncols_s;
     DT open_dt[ST_MAXM];
@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(128) k_index_promoted(const CParams* __restric
     const uint8_t* slot = iscr + ioff[j];
     const uint32_t nb_max = (icap[j] - IXS_HEAD) / IXS_BLOCK_STRIDE, nb = nblk[j], n = ihead[j];
     DT pd; pd.mfda = ((const int64_t*)slot)[0]; pd.ldt = ((const int64_t*)slot)[1];
-    const uint32_t pdsz = dt_is_live(pd) ? 1u : 12u, hdr_len = n + pdsz;
+    const uint32_t pdsz = dt_is_live(pd) ? 1u : 12u, hdr_len = (uint32_t)((const int64_t*)slot)[2];     // key + partition deletion + static row
     const uint32_t infos = ipay[j] - vint_size(hdr_len) - pdsz - vint_size(nb) - 4 * nb;
     Sink<true> s{iout + ipos[j], 0, true, ~0ull};
     s.copy(k, n); s.vint(dpos[j]); s.vint(ipay[j]);
@@ -866,7 +866,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (want_meta && (m->max_sstable_bytes != 0 || getenv("B200C_K4_TWO_PASS"))) { c->err = "metadata side band with multi-file output"; return B200C_EUNSUPPORTED; }
     if (want_meta && o0.filter && m->bloom_words && (m->bloom_hash_count <= 0 || m->bloom_words > (1ull << 31))) { c->err = "bloom geometry"; return B200C_EINVAL; }
     if (m->ninputs > MAXK) { c->err = "more than 64 inputs per call"; return B200C_EUNSUPPORTED; }
-    if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) { c->err = "static rows / tombstone_option / strict liveness"; return B200C_EUNSUPPORTED; }
+    if (m->tombstone_option != 0 || m->enforce_strict_liveness) { c->err = "tombstone_option / strict liveness"; return B200C_EUNSUPPORTED; }
+    if (m->nstatic_columns < 0 || m->nstatic_columns > MAXSTAT) { c->err = "more than 16 static columns"; return B200C_EUNSUPPORTED; }
     if (m->nclustering > MAXCLUST || m->ncolumns >= 64 || m->ncolumns < 0) { c->err = "schema outside the supported envelope"; return B200C_EUNSUPPORTED; }
     if (res->noutputs_cap < 1 || !res->outputs) { c->err = "no output slot"; return B200C_EINVAL; }
     if (m->out_chunk_len <= 0 || m->out_chunk_len > 65536 || (m->out_chunk_len & (m->out_chunk_len - 1))) { c->err = "output chunk_len"; return B200C_EUNSUPPORTED; }
@@ -928,12 +929,20 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             if (in.column_map[k] < 0 || in.column_map[k] >= m->ncolumns || (k && in.column_map[k] <= in.column_map[k - 1])) { c->err = "column_map must be strictly increasing (both headers are name ordered)"; return B200C_EINVAL; }
             d.colmap[k] = in.column_map[k];
         }
+        d.nstat = in.nstatic_columns; d._pad = 0;
+        if (in.nstatic_columns < 0 || in.nstatic_columns > m->nstatic_columns) { c->err = "input static columns"; return B200C_EINVAL; }
+        for (int k = 0; k < in.nstatic_columns; k++) {
+            if (in.static_column_map[k] < 0 || in.static_column_map[k] >= m->nstatic_columns || (k && in.static_column_map[k] <= in.static_column_map[k - 1])) { c->err = "static_column_map must be strictly increasing"; return B200C_EINVAL; }
+            d.smap[k] = in.static_column_map[k];
+        }
     }
     ubase[K] = uo; ibase[K] = io; cbase[K] = co; obase[K] = oo; bbase[K] = bo;
     const uint64_t nblocks = bo;
     hp.ninputs = K; hp.nclust = m->nclustering; hp.ncols = m->ncolumns; hp.column_index_size = m->column_index_size > 0 ? m->column_index_size : 65536;
     for (int k = 0; k < m->nclustering; k++) { hp.ctype[k] = m->clustering[k].type; hp.cfix[k] = m->clustering[k].fixed_len; }
     for (int k = 0; k < m->ncolumns; k++) hp.vfix[k] = m->columns[k].fixed_len;
+    hp.nstat = m->nstatic_columns; hp.mcols = std::max(m->ncolumns, m->nstatic_columns);
+    for (int k = 0; k < m->nstatic_columns; k++) hp.sfix[k] = m->static_columns[k].fixed_len;
     hp.o_min_ts = m->out_stats.min_timestamp; hp.o_min_ldt = m->out_stats.min_local_deletion_time; hp.o_min_ttl = m->out_stats.min_ttl;
     hp.now = m->now_in_sec; hp.gc_before = m->gc_before; hp.purge_max_ts = m->purge_max_timestamp;
     hp.partitioner = m->partitioner;
@@ -1346,8 +1355,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_TRY(ws_typed(c, WS_STMUNF, nparts + 1, &d_stmunf));
         B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
         B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
-        const size_t cols_s = m->ncolumns <= K4_SMEM_COLS ? (size_t)m->ncolumns * sizeof(MCell) : 0;
-        const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * m->ncolumns * sizeof(MCell);
+        const size_t cols_s = hp.mcols <= K4_SMEM_COLS ? (size_t)hp.mcols * sizeof(MCell) : 0;
+        const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * hp.mcols * sizeof(MCell);
         memset(&ka, 0, sizeof(ka));
         ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen; ka.tok = d_tok;
         ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
@@ -1426,7 +1435,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                     B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
                     const uint64_t ntiles = h[0], nbig = h[1];
                     const bool wide = m->ncolumns > K4_SMEM_COLS;
-                    const size_t smem_st = (size_t)ST_HEAD + ST_STAGE_CAP + (size_t)ST_CUR_CAP * sizeof(CurS) + (wide ? 0 : (size_t)ST_THREADS * m->ncolumns * sizeof(MCell)) + 16;
+                    const size_t smem_st = (size_t)ST_HEAD + ST_STAGE_CAP + (size_t)ST_CUR_CAP * sizeof(CurS) + (wide ? 0 : (size_t)ST_THREADS * hp.mcols * sizeof(MCell)) + 16;
                     if (c->k4s_attr_set != (int)smem_st) {
                         cudaFuncSetAttribute(k_partition_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);
                         cudaFuncSetAttribute(k_partition_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);

@@ -13,13 +13,13 @@
 //                                                       S/db/rows/UnfilteredSerializer.java:151-305, S/db/rows/Cell.java:268-305
 //   BigFormatPartitionWriter / IndexInfo / RowIndexEntry S/io/sstable/format/big/BigFormatPartitionWriter.java:128-251,
 //                                                       S/io/sstable/IndexInfo.java:107-117, .../big/RowIndexEntry.java:625-642
-// Envelope: simple regular columns (< 64), <= 8 clustering columns, no static rows / complex columns / counters.
+// Envelope: simple regular columns (< 64), simple static columns (<= 16), <= 8 clustering columns, no complex columns / counters.
 #pragma once
 #include "common.cuh"
 
 namespace b200c {
 
-enum { MAXK = 64, MAXCOLS = 64, MAXCLUST = 8 };
+enum { MAXK = 64, MAXCOLS = 64, MAXCLUST = 8, MAXSTAT = 16 };
 enum { TYPE_BYTES = 0, TYPE_FIXED_SIGNED = 1, TYPE_FIXED_BYTES = 2, TYPE_VAR_SIGNED = 3 };
 enum { K_EXCL_END = 0, K_INCL_START = 1, K_EXCL_END_INCL_START = 2, K_STATIC = 3, K_CLUSTERING = 4, K_INCL_END_EXCL_START = 5, K_INCL_END = 6, K_EXCL_START = 7 };
 enum { PERR_NONE = 0, PERR_CORRUPT = 1, PERR_UNSUPPORTED = 2 };
@@ -33,12 +33,15 @@ struct InDesc {
     uint64_t uend;                 // end of the last partition the Index.db slice describes, as an offset in this input's stream (= ulen for the whole file)
     int64_t min_ts, min_ldt; int32_t min_ttl; int32_t ncols;
     int32_t colmap[MAXCOLS];
+    int32_t nstat, _pad; int32_t smap[MAXSTAT];      // static columns of this input's header -> output static columns
 };
 struct CParams {
     const uint8_t* U;              // all inputs' uncompressed Data streams, back to back (16-byte aligned bases)
     int32_t ninputs, nclust, ncols, column_index_size;
     int32_t ctype[MAXCLUST], cfix[MAXCLUST], vfix[MAXCOLS];
     int64_t o_min_ts, o_min_ldt; int32_t o_min_ttl;
+    int32_t nstat, sfix[MAXSTAT];  // static columns of the output header (0: the table has none, no static rows anywhere)
+    int32_t mcols;                 // max(ncols, nstat): cells of scratch a merged row needs
     int32_t partitioner;           // 0 Murmur3Partitioner, 1 ByteOrderedPartitioner (tok[] then holds the sign-flipped 8-byte key prefix)
     int64_t now, gc_before, purge_max_ts;
     // optional purge table (b200c_manifest.purge_range_*): ascending token bounds and the threshold that applies up to each of them
@@ -175,7 +178,8 @@ template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P,
             if (c.kind > 7 || c.kind == K_STATIC || c.kind == K_CLUSTERING || c.n > P.nclust) { c.done = true; return PERR_CORRUPT; }
         } else {
             if (flags & 0x80) c.ext = (uint8_t)r.u8();
-            if ((c.ext & 0x03) || (flags & 0x40)) { c.done = true; return PERR_UNSUPPORTED; }
+            if (c.ext & 0x01) { c.done = true; return PERR_CORRUPT; }       // a static row among the clustered ones (UnfilteredSerializer.deserialize :477-479)
+            if ((c.ext & 0x02) || (flags & 0x40)) { c.done = true; return PERR_UNSUPPORTED; }
             c.kind = K_CLUSTERING; c.n = (uint8_t)P.nclust;
         }
         c.ck_rel = (uint8_t)(r.p - c.pos);
@@ -216,6 +220,31 @@ template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P,
     }
 }
 template <class CUR> __device__ __forceinline__ void cur_load(const CParams& P, CUR& c, int& err) { int e = cur_load_impl(P, c); if (e) err = e; }
+
+// The static row at c.pos, right after the partition deletion (SSTableSimpleIterator.readStaticRow -> UnfilteredSerializer.deserializeStaticRow
+// :538-552): parsed INTO the cursor (flags, body_rel, next) so that row_header / fold_cells read it like any other row. *nonempty: it
+// has liveness, a deletion or at least one cell.
+template <class CUR> __device__ __noinline__ int static_load(const CParams& P, CUR& c, bool* nonempty) {
+    Rd r{P.U, c.pos, c.end, 0};
+    uint32_t flags = r.u8(), ext = r.u8();
+    if (r.err || (flags & 0x03) || !(flags & 0x80) || !(ext & 0x01)) return PERR_CORRUPT;
+    if ((ext & 0x02) || (flags & 0x40)) return PERR_UNSUPPORTED;
+    c.flags = (uint8_t)flags; c.ext = (uint8_t)ext; c.kind = K_STATIC; c.n = 0; c.ck_rel = 2; c.ckend_rel = 2; c.fast = 0;
+    uint64_t sz = r.vint();
+    uint64_t after = r.p;
+    r.vint();                                       // previous unfiltered size (0)
+    c.body_rel = (typename CUR::rel_t)(r.p - c.pos);
+    const uint64_t nx = after + sz;
+    if (r.err || nx > c.end || nx < r.p) return PERR_CORRUPT;
+    c.next = (decltype(c.next))nx;
+    *nonempty = true;
+    if (!(flags & 0x14)) {
+        int ncin = P.in[c.src].nstat;
+        if (flags & 0x20) *nonempty = ncin > 0;
+        else { Rd b{P.U, c.pos + c.body_rel, c.next, 0}; uint64_t missing = b.vint(); *nonempty = ((~missing) & ((1ull << ncin) - 1)) != 0; }
+    }
+    return 0;
+}
 
 __device__ __forceinline__ int cmp_bytes(const uint8_t* a, int la, const uint8_t* b, int lb) {
     int n = la < lb ? la : lb;
@@ -306,8 +335,8 @@ __device__ bool reconcile_keep_left(const CParams& P, const MCell& l, const MCel
     return cmp_bytes(P.U + l.voff, l.vlen, P.U + r.voff, r.vlen) >= 0;
 }
 
-// promoted-index slot of the scratch pass: [16 B partition deletion (mfda, ldt)][i32 offsets x nb_max][IndexInfo bytes, IXS_PER_BLOCK budget per block]
-enum { IXS_HEAD = 16, IXS_PER_BLOCK = 204, IXS_BLOCK_STRIDE = 4 + IXS_PER_BLOCK };
+// promoted-index slot of the scratch pass: [partition deletion (mfda, ldt), headerLength: 3 x int64][i32 offsets x nb_max][IndexInfo bytes, IXS_PER_BLOCK budget per block]
+enum { IXS_HEAD = 24, IXS_PER_BLOCK = 204, IXS_BLOCK_STRIDE = 4 + IXS_PER_BLOCK };
 
 // ---- MetadataCollector's reductions, gathered where the rows are written (S/io/sstable/metadata/MetadataCollector.java:208-270; called from
 // SortedTableWriter.startPartition / addRow / addRangeTomstoneMarker S/io/sstable/format/SortedTableWriter.java:183-238 and Rows.collectStats
@@ -355,6 +384,7 @@ template <bool EMIT> struct PWriter {
     DT open_marker;
     uint64_t rows_out;
     StatAcc* acc;                 // statistics side band (nullptr: not gathered in this pass)
+    uint8_t* ix_entry; uint32_t ix_fixed;   // final emit into the Index.db entry itself: ix.base = ix_entry + ix_fixed + vint_size(header_len), set by pw_start
 };
 
 template <bool EMIT> __device__ __forceinline__ void write_partition_dt(Sink<EMIT>& s, const DT& d) {
@@ -397,16 +427,16 @@ template <bool EMIT> __device__ __forceinline__ void pw_end_unf(PWriter<EMIT>& w
 }
 
 // row body: UnfilteredSerializer.serializeRowBody :213-269 + Cell.Serializer.serialize S/db/rows/Cell.java:268-305
-template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const CParams& P, int flags, Live info, DT del, const MCell* cells) {
+template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const CParams& P, int flags, Live info, DT del, const MCell* cells, int ncols, const int32_t* vfix) {
     if (flags & 0x04) s.vint((uint64_t)info.ts - (uint64_t)P.o_min_ts);
     if (flags & 0x08) { s.vint((uint64_t)(int64_t)(info.ttl - P.o_min_ttl)); s.vint((uint64_t)(int64_t)(int32_t)(info.ldt - P.o_min_ldt)); }
     if (flags & 0x10) write_delta_dt(s, P, del);
     if (!(flags & 0x20)) {
         uint64_t missing = 0;
-        for (int c = 0; c < P.ncols; c++) if (!cells[c].present) missing |= 1ull << c;
+        for (int c = 0; c < ncols; c++) if (!cells[c].present) missing |= 1ull << c;
         s.vint(missing);
     }
-    for (int c = 0; c < P.ncols; c++) {
+    for (int c = 0; c < ncols; c++) {
         const MCell& m = cells[c]; if (!m.present) continue;
         bool has_value = m.vlen > 0, deleted = m.ldt != I64_MAX && m.ttl == 0, expiring = m.ttl != 0;
         bool use_ts = !live_is_empty(info) && m.ts == info.ts;
@@ -416,7 +446,7 @@ template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const
         if (!use_ts) s.vint((uint64_t)m.ts - (uint64_t)P.o_min_ts);
         if ((deleted || expiring) && !use_ttl) s.vint((uint64_t)(int64_t)(int32_t)(m.ldt - P.o_min_ldt));
         if (expiring && !use_ttl) s.vint((uint64_t)(int64_t)(m.ttl - P.o_min_ttl));
-        if (has_value) { if (P.vfix[c] <= 0) s.vint((uint64_t)m.vlen); s.copy(P.U + m.voff, (uint32_t)m.vlen); }
+        if (has_value) { if (vfix[c] <= 0) s.vint((uint64_t)m.vlen); s.copy(P.U + m.voff, (uint32_t)m.vlen); }
     }
     return s.pos;
 }
@@ -435,13 +465,14 @@ template <class CUR> __device__ __forceinline__ Rd row_header(const CParams& P, 
 }
 
 // folds the cells of the row at cursor `c` into merged[] (ColumnDataReducer.getReduced :838-849)
-template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& P, const CUR& c, Rd r, Live info, bool apply_deletion, DT active, MCell* merged) {
+template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& P, const CUR& c, Rd r, Live info, bool apply_deletion, DT active, MCell* merged, bool stat) {
     const InDesc& in = P.in[c.src];
+    const int nin = stat ? in.nstat : in.ncols; const int32_t* const map = stat ? in.smap : in.colmap; const int32_t* const vfix = stat ? P.sfix : P.vfix;
     uint64_t missing = 0;
     if (!(c.flags & 0x20)) missing = r.vint();
-    for (int i = 0; i < in.ncols; i++) {
+    for (int i = 0; i < nin; i++) {
         if ((missing >> i) & 1) continue;
-        int oc = in.colmap[i];
+        int oc = map[i];
         uint32_t cf = r.u8();
         bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
         MCell m; m.present = true;
@@ -450,7 +481,7 @@ template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& 
         m.ttl = use_ttl ? info.ttl : (expiring ? r.vint32() + in.min_ttl : 0);
         m.voff = r.p; m.vlen = 0;
         if (has_value) {
-            int64_t len = P.vfix[oc] > 0 ? P.vfix[oc] : (int64_t)r.vint32();
+            int64_t len = vfix[oc] > 0 ? vfix[oc] : (int64_t)r.vint32();
             if (len < 0) { r.err = PERR_CORRUPT; len = 0; }
             m.voff = r.p; m.vlen = (int32_t)len; r.skip((uint64_t)len);
         }
@@ -462,16 +493,16 @@ template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& 
     }
     return r.err;
 }
-template <class CUR> __device__ __forceinline__ void fold_cells(const CParams& P, const CUR& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err) {
-    int e = fold_cells_impl(P, c, r, info, apply_deletion, active, merged); if (e) err = e;
+template <class CUR> __device__ __forceinline__ void fold_cells(const CParams& P, const CUR& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err, bool stat = false) {
+    int e = fold_cells_impl(P, c, r, info, apply_deletion, active, merged, stat); if (e) err = e;
 }
 
 // BTreeRow.purge :457-499 + AbstractCell.purge :78-99. Returns the number of surviving cells, or -1 when the row disappears.
-__device__ __forceinline__ int purge_row(const CParams& P, const Purger& pg, Live& info, DT& del, MCell* cells) {
+__device__ __forceinline__ int purge_row(const Purger& pg, Live& info, DT& del, MCell* cells, int ncols) {
     if (pg.live(info)) info = live_empty();
     if (pg.dt(del)) del = dt_live();
     int present = 0;
-    for (int c = 0; c < P.ncols; c++) {
+    for (int c = 0; c < ncols; c++) {
         MCell& m = cells[c]; if (!m.present) continue;
         bool is_live = m.ldt == I64_MAX || (m.ttl != 0 && pg.now < m.ldt);
         if (!is_live) {
@@ -487,10 +518,40 @@ __device__ __forceinline__ int purge_row(const CParams& P, const Purger& pg, Liv
     return present;
 }
 
-template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, const CParams& P, uint64_t key_off, uint32_t klen, const DT& out_pdel) {
+// Tables with static columns carry a static row in every partition, the empty one included (SortedTableWriter.append :144-146,
+// SortedTablePartitionWriter.addStaticRow :117-126, UnfilteredSerializer.serializeStaticRow :144-149): flags | EXTENSION, extended flags
+// IS_STATIC, no clustering, previous size 0. scells == nullptr: the (merged, purged) static row is empty.
+template <bool EMIT> __device__ __noinline__ void write_static(PWriter<EMIT>& w, const CParams& P, const Live info, const DT del, const MCell* scells, int present) {
+    if (!scells) {                                   // no liveness, no deletion, every column missing
+        const uint64_t mask = (1ull << P.nstat) - 1;
+        w.d.u8(0x80); w.d.u8(0x01); w.d.vint(vint_size(mask) + 1); w.d.vint(0); w.d.vint(mask);
+        return;
+    }
+    int flags = 0x80;
+    if (!live_is_empty(info)) flags |= 0x04;
+    if (info.ttl != 0) flags |= 0x08;
+    if (!dt_is_live(del)) flags |= 0x10;
+    if (present == P.nstat) flags |= 0x20;
+    Sink<EMIT> cs{nullptr, 0, false, 0};
+    uint64_t body = put_row_body(cs, P, flags, info, del, scells, P.nstat, P.sfix);
+    w.d.u8(flags); w.d.u8(0x01);
+    w.d.vint(body + 1); w.d.vint(0);
+    w.d.pos = put_row_body(w.d, P, flags, info, del, scells, P.nstat, P.sfix);
+    if (w.acc) {                                     // SortedTableWriter.addStaticRow :188-197: Rows.collectStats unless the row is empty
+        w.acc->live(info); w.acc->dt(del);
+        for (int c = 0; c < P.nstat; c++) if (scells[c].present) w.acc->cell(scells[c]);
+        w.acc->cols += (unsigned long long)present; w.acc->rows++;
+    }
+}
+template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, const CParams& P, uint64_t key_off, uint32_t klen, const DT& out_pdel,
+                                                              const MCell* scells = nullptr, const Live& sinfo = Live{I64_MIN, I64_MAX, 0}, const DT& sdel = DT{I64_MIN, I64_MAX}, int spresent = 0) {
     w.d.be16(klen); w.d.copy(P.U + key_off, klen); write_partition_dt(w.d, out_pdel);      // SortedTablePartitionWriter.start :97-115
-    w.header_len = w.d.pos - w.start; w.started = true;
+    w.started = true;
     if (w.acc) { w.acc->part_cells = 0; if (!dt_is_live(out_pdel)) { w.acc->pdel = 1; w.acc->dt(out_pdel); } }     // updatePartitionDeletion
+    if (P.nstat > 0) write_static(w, P, sinfo, sdel, scells, spresent);
+    w.header_len = w.d.pos - w.start;
+    // final emit with an Index.db slot: the IndexInfos start behind the entry's fixed part, whose size depends on headerLength
+    if (EMIT && w.ix_entry) w.ix.base = w.ix_entry + w.ix_fixed + vint_size(w.header_len);
 }
 
 template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
@@ -502,10 +563,10 @@ template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w,
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
     Sink<EMIT> cs{nullptr, 0, false, 0};                       // same instantiation as the real sink, stores off: counts the body
-    uint64_t body = put_row_body(cs, P, flags, info, del, cells);
+    uint64_t body = put_row_body(cs, P, flags, info, del, cells, P.ncols, P.vfix);
     w.d.u8(flags); w.d.copy(P.U + ck.off, ck.len);
     w.d.vint(body + vint_size(prev)); w.d.vint(prev);
-    w.d.pos = put_row_body(w.d, P, flags, info, del, cells);
+    w.d.pos = put_row_body(w.d, P, flags, info, del, cells, P.ncols, P.vfix);
     pw_end_unf(w, P, ck, pos);
     if (w.acc) {                                               // Rows.collectStats
         w.acc->live(info); w.acc->dt(del);
@@ -564,6 +625,34 @@ __device__ __forceinline__ int64_t purge_threshold(const CParams& P, const uint6
 
 struct PartOut { uint64_t dsize; uint32_t ipay, nblk, ihead; uint32_t ovf; uint32_t cells; };
 
+// The merged static row of one output partition: cursors cur[v], v in sgrp, stand on their non-empty static rows (static_load).
+// mergeStaticRows S/db/rows/UnfilteredRowIterators.java:484-505 -> Row.Merger.merge(partitionDeletion) S/db/rows/Row.java:730-781: runs for
+// every fan-in (the merge iterator's constructor calls it), and its single-row shortcut counts every iterator, the ones with an empty
+// static row too (merger.add(i, ...) for all i). Returns the number of merged cells, or -1 when nothing is left.
+template <class CUR> __device__ __noinline__ int merge_static(const CParams& P, CUR* cur, uint64_t sgrp, uint32_t m, DT pdel, MCell* merged, Live* info_out, DT* del_out, int* err) {
+    Live info = live_empty(); DT del = dt_live(); DT active = pdel;
+    for (int k = 0; k < P.nstat; k++) merged[k].present = false;
+    const bool as_is = m == 1 && dt_is_live(pdel);
+    for (uint64_t bits = sgrp; bits; bits &= bits - 1) {
+        int v = __ffsll((long long)bits) - 1;
+        Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) *err = r.err;
+        if (live_supersedes(vi, info)) info = vi;
+        if (dt_supersedes(vd, del)) del = vd;
+    }
+    if (!as_is) {
+        if (dt_supersedes(del, active)) active = del; else del = dt_live();
+        if (dt_deletes(active, info.ts)) info = live_empty();
+    }
+    for (uint64_t bits = sgrp; bits && !*err; bits &= bits - 1) {
+        int v = __ffsll((long long)bits) - 1;
+        Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd);
+        fold_cells(P, cur[v], r, vi, !as_is, active, merged, *err, true);
+    }
+    *info_out = info; *del_out = del;
+    int n = 0; for (int k = 0; k < P.nstat; k++) n += merged[k].present;
+    return (live_is_empty(info) && dt_is_live(del) && n == 0) ? -1 : n;
+}
+
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
 // cur[0..m) / open_dt[0..m): per-source cursor state owned by this thread (the caller places it in shared memory);
 // merged[0..ncols): scratch for the merged row.
@@ -587,6 +676,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
+    uint64_t sgrp = 0;                                // contributors with a non-empty static row
     if (m > MAXK) { err = PERR_UNSUPPORTED; return; }
     // prologue in three sweeps so that the m dependent chains (contrib -> upos -> Data bytes) overlap instead of serialising:
     // (1) resolve the input partitions, (2) prefetch their first lines, (3) parse the partition headers
@@ -620,6 +710,11 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
         if (v == 0) { key_off = pos + 2; klen = kl; }
         if (!dt_supersedes(pdel, pd)) pdel = pd;                  // collectPartitionLevelDeletion :465-482
         c.pos = (decltype(c.pos))r.p; c.next = c.pos;
+        if (P.in[c.src].nstat > 0) {                              // header.hasStatic(): this input's partitions carry a static row
+            bool ne = false; int e = static_load(P, c, &ne);
+            if (e) { err = e; return; }
+            if (ne) sgrp |= 1ull << v;
+        }
     }
     DT out_pdel = pg.dt(pdel) ? dt_live() : pdel;                 // PurgeFunction.applyToDeletion :95-99
 
@@ -630,12 +725,20 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
     w.first = CkRef{0, 0, 0, 0}; w.last = w.first; w.acc = acc;
     // index entry layout (EMIT): [u16 kl][key][vint dpos][vint ipay]{[vint headerLen][DT][vint nblocks][IndexInfo..][i32 offsets..]}
-    uint32_t hdr_len_known = 2 + klen + (dt_is_live(out_pdel) ? 1 : 12);
     uint32_t fixed = 2 + klen + vint_size(dpos) + vint_size(ipay_final);
-    uint32_t pre = fixed + vint_size(hdr_len_known) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
-    w.ix.base = (EMIT && iout) ? iout + pre : nullptr; w.ix.pos = 0;
+    w.ix.base = nullptr; w.ix.pos = 0;
+    w.ix_entry = (EMIT && iout && !ixs) ? iout : nullptr; w.ix_fixed = fixed + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
     w.ix_offs = (EMIT && iout) ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
     if (ixs) { w.ix_offs = iout + IXS_HEAD; w.ix.base = iout + IXS_HEAD + 4 * (size_t)nblocks_final; }
+    // static row: merged and purged before anything else (the merge iterator's constructor does it); a non-empty one makes the partition
+    // non-empty (UnfilteredRowIterator.isEmpty :63-68), so the partition starts here and now while merged[] still holds its cells
+    if (P.nstat > 0 && sgrp) {
+        Live sinfo; DT sdel;
+        int n = merge_static(P, cur, sgrp, m, pdel, merged, &sinfo, &sdel, &err);
+        if (err) return;
+        if (n >= 0) { n = purge_row(pg, sinfo, sdel, merged, P.nstat); if (n >= 0) pw_start(w, P, key_off, klen, out_pdel, merged, sinfo, sdel, n); }
+    }
+    if (P.nstat > 0) for (uint32_t v = 0; v < m; v++) if (P.in[cur[v].src].nstat > 0) cur[v].pos = cur[v].next;      // step over the static rows
 
     // One code path for every fan-in. m == 1 is the reference's TrivialOneToOne case (UnfilteredRowIterators.java:552-556): rows
     // and markers pass through untouched (no Row.Merger, no marker merger) and only the purge transformation applies.
@@ -681,7 +784,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
                 st.merged_unfiltereds++;
                 CUR& f = cur[b];
                 CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), K_CLUSTERING, f.n};
-                int present = purge_row(P, pg, info, del, merged);
+                int present = purge_row(pg, info, del, merged, P.ncols);
                 if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
             }
         } else {
@@ -731,7 +834,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
         if (ixs) {                                                           // the entry itself is assembled by k_index_promoted once positions are known
             if (w.nblocks > 1) {
                 if (w.ix.pos > w.ix.cap || w.nblocks > nblocks_final) out.ovf = 1;
-                ((int64_t*)iout)[0] = out_pdel.mfda; ((int64_t*)iout)[1] = out_pdel.ldt;
+                ((int64_t*)iout)[0] = out_pdel.mfda; ((int64_t*)iout)[1] = out_pdel.ldt; ((int64_t*)iout)[2] = (int64_t)w.header_len;
             }
         } else if (EMIT && !iout && w.nblocks > 1) out.ovf = 1;              // scratch pass without a slot: re-emit in mode 3
         else if (EMIT && iout) {                                             // RowIndexEntry.serialize :468-473, IndexedEntry.serialize :625-642

@@ -38,7 +38,7 @@ __device__ __forceinline__ MCell purge_cell(const Purger& pg, MCell m) {
 }
 
 // decodes the next cell of input column `icol` at reader r (Cell.Serializer.deserialize, S/db/rows/Cell.java:307-349)
-__device__ __forceinline__ MCell read_cell(const CParams& P, const InDesc& in, Rd& r, const Live& info, int oc) {
+__device__ __forceinline__ MCell read_cell(const InDesc& in, Rd& r, const Live& info, int oc, const int32_t* vfix) {
     uint32_t cf = r.u8();
     bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
     MCell m; m.present = true;
@@ -47,13 +47,83 @@ __device__ __forceinline__ MCell read_cell(const CParams& P, const InDesc& in, R
     m.ttl = use_ttl ? info.ttl : (expiring ? r.vint32() + in.min_ttl : 0);
     m.voff = r.p; m.vlen = 0;
     if (has_value) {
-        int64_t len = P.vfix[oc] > 0 ? P.vfix[oc] : (int64_t)r.vint32();
+        int64_t len = vfix[oc] > 0 ? vfix[oc] : (int64_t)r.vint32();
         if (len < 0) { r.err = PERR_CORRUPT; len = 0; }
         m.voff = r.p; m.vlen = (int32_t)len; r.skip((uint64_t)len);
     }
     if (m.ttl < 0) r.err = PERR_CORRUPT;
     if (m.ldt != I64_MAX) m.ldt = decode_ldt(m.ldt, m.ttl);
     return m;
+}
+
+// One merged row out of the versions the lanes in grp[] stand on (Row.Merger.merge S/db/rows/Row.java:730-781; ColumnDataReducer :838-849):
+// row headers and cells are decoded side by side, one lane per source, and folded in source order by broadcast. s_cells[0..columns) receives
+// the merged AND purged cells (lane 0 stores). stat: the static column set (mergeStaticRows) instead of the regular one.
+template <int G, int S> __device__ __forceinline__ void tile_merge_rows(const cg::thread_block_tile<G>& tile, const CParams& P, const Purger& pg, Cur (&cur)[S], const unsigned (&grp)[S],
+                                                                        bool as_is, DT active, bool stat, MCell* s_cells, Live& info, DT& del, int& npresent_merged, int& npresent, int& lerr) {
+    const int lane = tile.thread_rank();
+    const int nout = stat ? P.nstat : P.ncols; const int32_t* const vfix = stat ? P.sfix : P.vfix;
+    bool ing[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) ing[s] = (grp[s] >> lane) & 1;
+    Live myinfo[S]; DT mydel[S]; Rd rd[S]; uint64_t missing[S]; int icol[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        myinfo[s] = live_empty(); mydel[s] = dt_live(); rd[s] = Rd{P.U, 0, 0, 0}; missing[s] = 0; icol[s] = 0;
+        if (ing[s]) {
+            rd[s] = row_header(P, cur[s], myinfo[s], mydel[s]);
+            if (!(cur[s].flags & 0x20)) missing[s] = rd[s].vint();
+            if (rd[s].err) lerr = rd[s].err;
+        }
+    }
+    info = live_empty(); del = dt_live();
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        for (unsigned bits = grp[s]; bits; bits &= bits - 1) {
+            int l = __ffs(bits) - 1;
+            Live vi; vi.ts = tshfl64<G>(tile, myinfo[s].ts, l); vi.ldt = tshfl64<G>(tile, myinfo[s].ldt, l); vi.ttl = tile.shfl(myinfo[s].ttl, l);
+            DT vd = tshfl_dt<G>(tile, mydel[s], l);
+            if (live_supersedes(vi, info)) info = vi;
+            if (dt_supersedes(vd, del)) del = vd;
+        }
+    }
+    if (!as_is) {
+        if (dt_supersedes(del, active)) active = del; else del = dt_live();
+        if (dt_deletes(active, info.ts)) info = live_empty();
+    }
+    npresent_merged = 0; npresent = 0;
+    for (int c = 0; c < nout; c++) {
+        MCell mine[S]; bool hasc[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            hasc[s] = false; mine[s].present = false; mine[s].ts = 0; mine[s].ldt = 0; mine[s].voff = 0; mine[s].ttl = 0; mine[s].vlen = 0;
+            if (ing[s]) {
+                const InDesc& in = P.in[cur[s].src];
+                const int nin = stat ? in.nstat : in.ncols; const int32_t* const map = stat ? in.smap : in.colmap;
+                while (icol[s] < nin && ((missing[s] >> icol[s]) & 1)) icol[s]++;
+                if (icol[s] < nin && map[icol[s]] == c) {
+                    mine[s] = read_cell(in, rd[s], myinfo[s], c, vfix); hasc[s] = true; icol[s]++;
+                    if (rd[s].err) lerr = rd[s].err;
+                }
+            }
+        }
+        MCell mc; mc.present = false; mc.ts = 0; mc.ldt = I64_MAX; mc.voff = 0; mc.ttl = 0; mc.vlen = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            for (unsigned bits = tile.ballot(hasc[s]); bits; bits &= bits - 1) {
+                int l = __ffs(bits) - 1;
+                MCell x; x.present = true;
+                x.ts = tshfl64<G>(tile, mine[s].ts, l); x.ldt = tshfl64<G>(tile, mine[s].ldt, l); x.voff = tshflu64<G>(tile, mine[s].voff, l);
+                x.ttl = tile.shfl(mine[s].ttl, l); x.vlen = tile.shfl(mine[s].vlen, l);
+                if (!as_is && dt_deletes(active, x.ts)) continue;
+                if (!mc.present || !reconcile_keep_left(P, mc, x)) mc = x;
+            }
+        }
+        npresent_merged += mc.present;
+        MCell pc = purge_cell(pg, mc);
+        npresent += pc.present;
+        if (lane == 0) s_cells[c] = pc;
+    }
 }
 
 template <int G, int S, bool EMIT>
@@ -109,12 +179,37 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
     w.nblocks = 0; w.nblocks_final = nblocks_final; w.started = false; w.have_first = false; w.open_marker = dt_live(); w.rows_out = 0;
     w.first = CkRef{0, 0, 0, 0}; w.last = w.first; w.acc = (lane == 0) ? acc : nullptr;      // every lane runs the writer, lane 0 stores and counts
     {
-        uint32_t hdr_len_known = 2 + klen + (dt_is_live(out_pdel) ? 1 : 12);
         uint32_t fixed = 2 + klen + vint_size(dpos) + vint_size(ipay_final);
-        uint32_t pre = fixed + vint_size(hdr_len_known) + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
-        w.ix.base = (EMIT && iout) ? iout + pre : nullptr; w.ix.pos = 0;
+        w.ix.base = nullptr; w.ix.pos = 0;
+        w.ix_entry = (EMIT && iout && !ixs) ? iout : nullptr; w.ix_fixed = fixed + (dt_is_live(out_pdel) ? 1 : 12) + vint_size(nblocks_final);
         w.ix_offs = (EMIT && iout) ? iout + fixed + ipay_final - 4 * nblocks_final : nullptr;
         if (ixs) { w.ix_offs = iout + IXS_HEAD; w.ix.base = iout + IXS_HEAD + 4 * (size_t)nblocks_final; }
+    }
+    // ---- static rows: merged and purged before the clustered rows (see process_partition) -----------------------------------------------
+    if (P.nstat > 0) {
+        bool sne[S]; unsigned sg[S]; unsigned anys = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            sne[s] = false;
+            if (have[s] && P.in[cur[s].src].nstat > 0) { int e = static_load(P, cur[s], &sne[s]); if (e) { lerr = e; sne[s] = false; } }
+        }
+        if (tile.any(lerr != 0)) { err = tile.any(lerr == PERR_UNSUPPORTED) ? PERR_UNSUPPORTED : PERR_CORRUPT; return; }
+#pragma unroll
+        for (int s = 0; s < S; s++) { sg[s] = tile.ballot(sne[s]); anys |= sg[s]; }
+        if (anys) {
+            Live sinfo; DT sdel; int npm, np;
+            tile_merge_rows<G, S>(tile, P, pg, cur, sg, m == 1 && dt_is_live(pdel), pdel, true, s_cells, sinfo, sdel, npm, np, lerr);
+            tile.sync();
+            if (tile.any(lerr != 0)) { err = tile.any(lerr == PERR_UNSUPPORTED) ? PERR_UNSUPPORTED : PERR_CORRUPT; return; }
+            if (!(live_is_empty(sinfo) && dt_is_live(sdel) && npm == 0)) {
+                if (pg.live(sinfo)) sinfo = live_empty();
+                if (pg.dt(sdel)) sdel = dt_live();
+                if (!(live_is_empty(sinfo) && dt_is_live(sdel) && np == 0)) pw_start(w, P, key_off, klen, out_pdel, s_cells, sinfo, sdel, np);
+            }
+            tile.sync();
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) if (have[s] && P.in[cur[s].src].nstat > 0) cur[s].pos = cur[s].next;      // step over the static rows
     }
 
 #pragma unroll
@@ -165,63 +260,8 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
             // ---- rows: Row.Merger.merge (multi source) or pass-through (single source, TrivialOneToOne) -----------------------------
             DT active = multi ? (dt_is_live(cur_open) ? pdel : cur_open) : dt_live();
             const bool as_is = !multi || (gcount == 1 && dt_is_live(active));
-            Live myinfo[S]; DT mydel[S]; Rd rd[S]; uint64_t missing[S]; int icol[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                myinfo[s] = live_empty(); mydel[s] = dt_live(); rd[s] = Rd{P.U, 0, 0, 0}; missing[s] = 0; icol[s] = 0;
-                if (ing[s]) {
-                    rd[s] = row_header(P, cur[s], myinfo[s], mydel[s]);
-                    if (!(cur[s].flags & 0x20)) missing[s] = rd[s].vint();
-                    if (rd[s].err) lerr = rd[s].err;
-                }
-            }
-            Live info = live_empty(); DT del = dt_live();
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                for (unsigned bits = grp[s]; bits; bits &= bits - 1) {
-                    int l = __ffs(bits) - 1;
-                    Live vi; vi.ts = tshfl64<G>(tile, myinfo[s].ts, l); vi.ldt = tshfl64<G>(tile, myinfo[s].ldt, l); vi.ttl = tile.shfl(myinfo[s].ttl, l);
-                    DT vd = tshfl_dt<G>(tile, mydel[s], l);
-                    if (live_supersedes(vi, info)) info = vi;
-                    if (dt_supersedes(vd, del)) del = vd;
-                }
-            }
-            if (!as_is) {
-                if (dt_supersedes(del, active)) active = del; else del = dt_live();
-                if (dt_deletes(active, info.ts)) info = live_empty();
-            }
-            int npresent_merged = 0, npresent = 0;
-            for (int c = 0; c < P.ncols; c++) {
-                MCell mine[S]; bool hasc[S];
-#pragma unroll
-                for (int s = 0; s < S; s++) {
-                    hasc[s] = false; mine[s].present = false; mine[s].ts = 0; mine[s].ldt = 0; mine[s].voff = 0; mine[s].ttl = 0; mine[s].vlen = 0;
-                    if (ing[s]) {
-                        const InDesc& in = P.in[cur[s].src];
-                        while (icol[s] < in.ncols && ((missing[s] >> icol[s]) & 1)) icol[s]++;
-                        if (icol[s] < in.ncols && in.colmap[icol[s]] == c) {
-                            mine[s] = read_cell(P, in, rd[s], myinfo[s], c); hasc[s] = true; icol[s]++;
-                            if (rd[s].err) lerr = rd[s].err;
-                        }
-                    }
-                }
-                MCell mc; mc.present = false; mc.ts = 0; mc.ldt = I64_MAX; mc.voff = 0; mc.ttl = 0; mc.vlen = 0;
-#pragma unroll
-                for (int s = 0; s < S; s++) {
-                    for (unsigned bits = tile.ballot(hasc[s]); bits; bits &= bits - 1) {
-                        int l = __ffs(bits) - 1;
-                        MCell x; x.present = true;
-                        x.ts = tshfl64<G>(tile, mine[s].ts, l); x.ldt = tshfl64<G>(tile, mine[s].ldt, l); x.voff = tshflu64<G>(tile, mine[s].voff, l);
-                        x.ttl = tile.shfl(mine[s].ttl, l); x.vlen = tile.shfl(mine[s].vlen, l);
-                        if (!as_is && dt_deletes(active, x.ts)) continue;
-                        if (!mc.present || !reconcile_keep_left(P, mc, x)) mc = x;
-                    }
-                }
-                npresent_merged += mc.present;
-                MCell pc = purge_cell(pg, mc);
-                npresent += pc.present;
-                if (lane == 0) s_cells[c] = pc;
-            }
+            Live info; DT del; int npresent_merged, npresent;
+            tile_merge_rows<G, S>(tile, P, pg, cur, grp, as_is, active, false, s_cells, info, del, npresent_merged, npresent, lerr);
             tile.sync();
             bool haverow = !(live_is_empty(info) && dt_is_live(del) && npresent_merged == 0);
             if (haverow && !tile.any(lerr != 0)) {
@@ -303,7 +343,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
         if (ixs) {
             if (w.nblocks > 1) {
                 if (w.ix.pos > w.ix.cap || w.nblocks > nblocks_final) out.ovf = 1;
-                if (lane == 0) { ((int64_t*)iout)[0] = out_pdel.mfda; ((int64_t*)iout)[1] = out_pdel.ldt; }
+                if (lane == 0) { ((int64_t*)iout)[0] = out_pdel.mfda; ((int64_t*)iout)[1] = out_pdel.ldt; ((int64_t*)iout)[2] = (int64_t)w.header_len; }
             }
         } else if (EMIT && !iout && w.nblocks > 1) out.ovf = 1;
         else if (EMIT && iout && lane == 0) {

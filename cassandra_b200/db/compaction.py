@@ -78,14 +78,17 @@ class CompactionTask:
 
     def build_manifest(self):
         ins = self.inputs
-        if any(i.static_columns for i in ins):
-            raise native.UnsupportedError(native.EUNSUPPORTED, "static columns")
         ct = ins[0].clustering_types
         if any(i.clustering_types != ct for i in ins): raise native.UnsupportedError(native.EUNSUPPORTED, "clustering types differ")
         union = {}
         for i in sorted(ins, key=lambda s: s.generation):            # newest generation's metadata wins (:91-99)
             for name, t in i.regular_columns: union[name] = t
         out_cols = sorted(union.items(), key=lambda kv: _name_key(kv[0]))
+        sunion = {}
+        for i in sorted(ins, key=lambda s: s.generation):
+            for name, t in i.static_columns: sunion[name] = t
+        out_static = sorted(sunion.items(), key=lambda kv: _name_key(kv[0]))
+        if len(out_static) > native.MAX_STATIC_COLUMNS: raise native.UnsupportedError(native.EUNSUPPORTED, "more than %d static columns" % native.MAX_STATIC_COLUMNS)
         m = native.Manifest(); m.abi_version = native.ABI_VERSION; m.ninputs = len(ins)
         arr = (native.Input * len(ins))(); self._keep.append(arr)
         for k, s in enumerate(ins):
@@ -101,6 +104,9 @@ class CompactionTask:
             a.ncolumns = len(s.regular_columns)
             names = [n for n, _ in out_cols]
             for ci, (name, _) in enumerate(s.regular_columns): a.column_map[ci] = names.index(name)
+            a.nstatic_columns = len(s.static_columns)
+            snames = [n for n, _ in out_static]
+            for ci, (name, _) in enumerate(s.static_columns): a.static_column_map[ci] = snames.index(name)
             a.header_stats.min_timestamp, a.header_stats.min_local_deletion_time, a.header_stats.min_ttl = s.header_stats
             a.level = s.level
             sp = getattr(s, "summary_positions", None)
@@ -116,7 +122,8 @@ class CompactionTask:
             m.clustering[k].type, m.clustering[k].fixed_len = sst.type_class(t)
         m.ncolumns = len(out_cols)
         for k, (_, t) in enumerate(out_cols): m.columns[k].type, m.columns[k].fixed_len = sst.type_class(t)
-        m.has_static = 0
+        m.nstatic_columns = len(out_static)
+        for k, (_, t) in enumerate(out_static): m.static_columns[k].type, m.static_columns[k].fixed_len = sst.type_class(t)
         m.out_stats.min_timestamp, m.out_stats.min_local_deletion_time, m.out_stats.min_ttl = merged_encoding_stats(ins)
         m.out_compressor = self.compression.compressor_id; m.out_chunk_len = self.compression.chunk_length
         m.out_max_compressed_len = self.compression.max_compressed_length; m.column_index_size = self.column_index_size

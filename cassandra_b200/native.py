@@ -8,7 +8,7 @@ OK, EINVAL, ECUDA, ECORRUPT, ECANCELLED, EUNSUPPORTED, ENOMEM, ETOOSMALL = 0, -1
 COMP_NONE, COMP_LZ4, COMP_SNAPPY, COMP_SNAPPY15 = 0, 1, 2, 3
 FLAG_DEVICE_PTRS = 1
 INT32_MAX = 0x7FFFFFFF
-MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS = 8, 64, 64
+MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS, MAX_STATIC_COLUMNS = 8, 64, 64, 16
 ABI_VERSION = 2
 PARTITIONER_MURMUR3, PARTITIONER_BYTE_ORDERED = 0, 1
 PSIZE_BUCKETS, CELLS_BUCKETS, HLL_P, TDROP_CAP = 156, 119, 13, 512
@@ -32,18 +32,20 @@ class Input(C.Structure):
                 ("chunk_offsets", C.c_void_p), ("nchunks", C.c_uint64), ("data_length", C.c_uint64),
                 ("compressor", C.c_int32), ("chunk_len", C.c_int32), ("max_compressed_len", C.c_int32), ("ncolumns", C.c_int32),
                 ("column_map", C.c_int32 * MAX_COLUMNS), ("header_stats", EncodingStats), ("_pad", C.c_int32), ("level", C.c_int32),
-                ("summary_positions", C.c_void_p), ("nsummary", C.c_uint64)]
+                ("summary_positions", C.c_void_p), ("nsummary", C.c_uint64),
+                ("nstatic_columns", C.c_int32), ("static_column_map", C.c_int32 * MAX_STATIC_COLUMNS), ("_pad2", C.c_int32)]
 class Manifest(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("ninputs", C.c_int32), ("inputs", C.POINTER(Input)),
                 ("nclustering", C.c_int32), ("clustering", Column * MAX_CLUSTERING),
-                ("ncolumns", C.c_int32), ("columns", Column * MAX_COLUMNS), ("has_static", C.c_int32),
+                ("ncolumns", C.c_int32), ("columns", Column * MAX_COLUMNS), ("nstatic_columns", C.c_int32),
                 ("out_stats", EncodingStats), ("out_compressor", C.c_int32), ("out_chunk_len", C.c_int32),
                 ("out_max_compressed_len", C.c_int32), ("column_index_size", C.c_int32),
                 ("now_in_sec", C.c_int64), ("gc_before", C.c_int64), ("purge_max_timestamp", C.c_int64),
                 ("tombstone_option", C.c_int32), ("enforce_strict_liveness", C.c_int32),
                 ("token_lo", C.c_int64), ("token_hi", C.c_int64), ("max_sstable_bytes", C.c_uint64),
                 ("partitioner", C.c_int32), ("npurge_ranges", C.c_int32), ("purge_range_hi", C.c_void_p), ("purge_range_max_ts", C.c_void_p),
-                ("bloom_hash_count", C.c_int32), ("min_index_interval", C.c_int32), ("bloom_words", C.c_uint64)]
+                ("bloom_hash_count", C.c_int32), ("min_index_interval", C.c_int32), ("bloom_words", C.c_uint64),
+                ("static_columns", Column * MAX_STATIC_COLUMNS)]
 class SSTableStats(C.Structure):
     _fields_ = [("min_timestamp", C.c_int64), ("max_timestamp", C.c_int64),
                 ("min_local_deletion_time", C.c_int64), ("max_local_deletion_time", C.c_int64),

@@ -146,6 +146,7 @@ typedef struct b200c_encoding_stats {   /* S/db/rows/EncodingStats.java: base va
 #define B200C_MAX_CLUSTERING 8
 #define B200C_MAX_COLUMNS    64
 #define B200C_MAX_INPUTS     64      /* fan-in of one call (one or two sources per lane of the merge warp) */
+#define B200C_MAX_STATIC_COLUMNS 16
 
 typedef struct b200c_input {
     const uint8_t*  data;               /* Data.db image (compressed chunks + inline CRCs) */
@@ -170,6 +171,11 @@ typedef struct b200c_input {
        cannot overlap their Data.db copies with the kernels (no token-range streaming). */
     const uint64_t* summary_positions;
     uint64_t        nsummary;
+    /* static columns in this sstable's SerializationHeader (header.hasStatic() <=> nstatic_columns > 0: every partition then carries a
+       static row right after its partition deletion, S/io/sstable/format/SortedTablePartitionWriter.java:97-126), header order */
+    int32_t         nstatic_columns;
+    int32_t         static_column_map[B200C_MAX_STATIC_COLUMNS]; /* header static column i -> index in manifest.static_columns */
+    int32_t         _pad2;
 } b200c_input;
 
 typedef struct b200c_manifest {
@@ -181,7 +187,7 @@ typedef struct b200c_manifest {
     b200c_column    clustering[B200C_MAX_CLUSTERING];
     int32_t         ncolumns;           /* regular simple columns of the OUTPUT header (union of inputs), header order */
     b200c_column    columns[B200C_MAX_COLUMNS];
-    int32_t         has_static;         /* must be 0 (B200C_EUNSUPPORTED otherwise) */
+    int32_t         nstatic_columns;    /* static simple columns of the OUTPUT header (0: the table has none and no static rows are written) */
     /* output encoding: SerializationHeader.make (S/db/SerializationHeader.java:77-100) = min over inputs' StatsMetadata */
     b200c_encoding_stats out_stats;
     int32_t         out_compressor;
@@ -212,6 +218,7 @@ typedef struct b200c_manifest {
     int32_t         bloom_hash_count;
     int32_t         min_index_interval; /* Summary.db sampling (128 default, S/schema/TableParams.java); 0 = 128 */
     uint64_t        bloom_words;
+    b200c_column    static_columns[B200C_MAX_STATIC_COLUMNS];
 } b200c_manifest;
 
 /* What MetadataCollector gathers while an output is written (S/io/sstable/metadata/MetadataCollector.java:107-147,208-270; called

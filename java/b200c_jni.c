@@ -51,13 +51,14 @@ static const jint LAYOUT[] = {
     OFF(b200c_input, data), OFF(b200c_input, data_len), OFF(b200c_input, index), OFF(b200c_input, index_len), OFF(b200c_input, chunk_offsets), OFF(b200c_input, nchunks),
     OFF(b200c_input, data_length), OFF(b200c_input, compressor), OFF(b200c_input, chunk_len), OFF(b200c_input, max_compressed_len), OFF(b200c_input, ncolumns),
     OFF(b200c_input, column_map), OFF(b200c_input, header_stats), OFF(b200c_input, level), OFF(b200c_input, summary_positions), OFF(b200c_input, nsummary),
+    OFF(b200c_input, nstatic_columns), OFF(b200c_input, static_column_map),
     OFF(b200c_manifest, abi_version), OFF(b200c_manifest, ninputs), OFF(b200c_manifest, inputs), OFF(b200c_manifest, nclustering), OFF(b200c_manifest, clustering),
-    OFF(b200c_manifest, ncolumns), OFF(b200c_manifest, columns), OFF(b200c_manifest, has_static), OFF(b200c_manifest, out_stats), OFF(b200c_manifest, out_compressor),
+    OFF(b200c_manifest, ncolumns), OFF(b200c_manifest, columns), OFF(b200c_manifest, nstatic_columns), OFF(b200c_manifest, out_stats), OFF(b200c_manifest, out_compressor),
     OFF(b200c_manifest, out_chunk_len), OFF(b200c_manifest, out_max_compressed_len), OFF(b200c_manifest, column_index_size), OFF(b200c_manifest, now_in_sec),
     OFF(b200c_manifest, gc_before), OFF(b200c_manifest, purge_max_timestamp), OFF(b200c_manifest, tombstone_option), OFF(b200c_manifest, enforce_strict_liveness),
     OFF(b200c_manifest, token_lo), OFF(b200c_manifest, token_hi), OFF(b200c_manifest, max_sstable_bytes), OFF(b200c_manifest, partitioner), OFF(b200c_manifest, npurge_ranges),
     OFF(b200c_manifest, purge_range_hi), OFF(b200c_manifest, purge_range_max_ts), OFF(b200c_manifest, bloom_hash_count), OFF(b200c_manifest, min_index_interval),
-    OFF(b200c_manifest, bloom_words),
+    OFF(b200c_manifest, bloom_words), OFF(b200c_manifest, static_columns),
     OFF(b200c_output, data), OFF(b200c_output, data_cap), OFF(b200c_output, data_len), OFF(b200c_output, index), OFF(b200c_output, index_cap), OFF(b200c_output, index_len),
     OFF(b200c_output, chunk_offsets), OFF(b200c_output, chunk_cap), OFF(b200c_output, nchunks), OFF(b200c_output, data_length), OFF(b200c_output, digest),
     OFF(b200c_output, partitions), OFF(b200c_output, rows), OFF(b200c_output, key_buf), OFF(b200c_output, key_cap), OFF(b200c_output, first_key_len),

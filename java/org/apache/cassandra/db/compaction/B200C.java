@@ -25,7 +25,7 @@ public final class B200C
     public static final int PARTITIONER_MURMUR3 = 0, PARTITIONER_BYTE_ORDERED = 1;
     public static final int TYPE_BYTES = 0, TYPE_FIXED_SIGNED = 1, TYPE_FIXED_BYTES = 2, TYPE_VAR_SIGNED = 3;
     public static final int ABI_VERSION = 2;
-    public static final int MAX_CLUSTERING = 8, MAX_COLUMNS = 64, MAX_INPUTS = 64;
+    public static final int MAX_CLUSTERING = 8, MAX_COLUMNS = 64, MAX_INPUTS = 64, MAX_STATIC_COLUMNS = 16;
 
     // ---- lifecycle ----------------------------------------------------------------------------------------------------------
     public static native int    abiVersion();                                       // b200c_abi_version
@@ -98,14 +98,15 @@ public final class B200C
         // b200c_input
         public static final int IN_DATA = next(), IN_DATA_LEN = next(), IN_INDEX = next(), IN_INDEX_LEN = next(), IN_CHUNK_OFFSETS = next(), IN_NCHUNKS = next(),
                                 IN_DATA_LENGTH = next(), IN_COMPRESSOR = next(), IN_CHUNK_LEN = next(), IN_MAX_COMPRESSED_LEN = next(), IN_NCOLUMNS = next(),
-                                IN_COLUMN_MAP = next(), IN_HEADER_STATS = next(), IN_LEVEL = next(), IN_SUMMARY_POSITIONS = next(), IN_NSUMMARY = next();
+                                IN_COLUMN_MAP = next(), IN_HEADER_STATS = next(), IN_LEVEL = next(), IN_SUMMARY_POSITIONS = next(), IN_NSUMMARY = next(),
+                                IN_NSTATIC_COLUMNS = next(), IN_STATIC_COLUMN_MAP = next();
         // b200c_manifest
         public static final int M_ABI_VERSION = next(), M_NINPUTS = next(), M_INPUTS = next(), M_NCLUSTERING = next(), M_CLUSTERING = next(), M_NCOLUMNS = next(),
-                                M_COLUMNS = next(), M_HAS_STATIC = next(), M_OUT_STATS = next(), M_OUT_COMPRESSOR = next(), M_OUT_CHUNK_LEN = next(),
+                                M_COLUMNS = next(), M_NSTATIC_COLUMNS = next(), M_OUT_STATS = next(), M_OUT_COMPRESSOR = next(), M_OUT_CHUNK_LEN = next(),
                                 M_OUT_MAX_COMPRESSED_LEN = next(), M_COLUMN_INDEX_SIZE = next(), M_NOW_IN_SEC = next(), M_GC_BEFORE = next(),
                                 M_PURGE_MAX_TIMESTAMP = next(), M_TOMBSTONE_OPTION = next(), M_ENFORCE_STRICT_LIVENESS = next(), M_TOKEN_LO = next(),
                                 M_TOKEN_HI = next(), M_MAX_SSTABLE_BYTES = next(), M_PARTITIONER = next(), M_NPURGE_RANGES = next(), M_PURGE_RANGE_HI = next(),
-                                M_PURGE_RANGE_MAX_TS = next(), M_BLOOM_HASH_COUNT = next(), M_MIN_INDEX_INTERVAL = next(), M_BLOOM_WORDS = next();
+                                M_PURGE_RANGE_MAX_TS = next(), M_BLOOM_HASH_COUNT = next(), M_MIN_INDEX_INTERVAL = next(), M_BLOOM_WORDS = next(), M_STATIC_COLUMNS = next();
         // b200c_output
         public static final int O_DATA = next(), O_DATA_CAP = next(), O_DATA_LEN = next(), O_INDEX = next(), O_INDEX_CAP = next(), O_INDEX_LEN = next(),
                                 O_CHUNK_OFFSETS = next(), O_CHUNK_CAP = next(), O_NCHUNKS = next(), O_DATA_LENGTH = next(), O_DIGEST = next(), O_PARTITIONS = next(),

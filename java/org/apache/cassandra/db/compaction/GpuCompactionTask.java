@@ -77,7 +77,9 @@ public class GpuCompactionTask extends CompactionTask
         TableMetadata t = cfs.metadata();
         if (inputs.isEmpty() || inputs.size() > B200C.MAX_INPUTS) return false;
         if (!(t.partitioner instanceof Murmur3Partitioner) && !(t.partitioner instanceof ByteOrderedPartitioner)) return false;
-        if (t.isCounter() || t.isIndex() || !t.staticColumns().isEmpty()) return false;
+        if (t.isCounter() || t.isIndex() || t.staticColumns().size() > B200C.MAX_STATIC_COLUMNS) return false;
+        for (ColumnMetadata c : t.staticColumns())
+            if (c.isComplex() || typeClass(c.type) < 0) return false;
         if (t.clusteringColumns().size() > B200C.MAX_CLUSTERING || t.regularColumns().size() >= B200C.MAX_COLUMNS) return false;
         for (ColumnMetadata c : t.regularColumns())
             if (c.isComplex() || typeClass(c.type) < 0) return false;
@@ -196,6 +198,8 @@ public class GpuCompactionTask extends CompactionTask
             final EncodingStats outStats = header.stats();
             final List<ColumnMetadata> outColumns = new ArrayList<>();
             header.columns().regulars.forEach(outColumns::add);
+            final List<ColumnMetadata> outStatics = new ArrayList<>();
+            header.columns().statics.forEach(outStatics::add);
 
             List<Input> inputs = new ArrayList<>();
             try
@@ -218,6 +222,10 @@ public class GpuCompactionTask extends CompactionTask
                     s.reader.header.columns().regulars.forEach(have::add);
                     in.putInt(o + IN_NCOLUMNS, have.size());
                     for (int c = 0; c < have.size(); c++) in.putInt(o + IN_COLUMN_MAP + 4 * c, outColumns.indexOf(have.get(c)));
+                    List<ColumnMetadata> haveStatic = new ArrayList<>();
+                    s.reader.header.columns().statics.forEach(haveStatic::add);
+                    in.putInt(o + IN_NSTATIC_COLUMNS, haveStatic.size());
+                    for (int c = 0; c < haveStatic.size(); c++) in.putInt(o + IN_STATIC_COLUMN_MAP + 4 * c, outStatics.indexOf(haveStatic.get(c)));
                     EncodingStats hs = s.reader.header.stats();
                     in.putLong(o + IN_HEADER_STATS, hs.minTimestamp).putLong(o + IN_HEADER_STATS + 8, hs.minLocalDeletionTime).putInt(o + IN_HEADER_STATS + 16, hs.minTTL);
                     in.putInt(o + IN_LEVEL, s.reader.getSSTableLevel());
@@ -237,6 +245,9 @@ public class GpuCompactionTask extends CompactionTask
                 m.putInt(M_NCOLUMNS, outColumns.size());
                 for (int k = 0; k < outColumns.size(); k++)
                     m.putInt(M_COLUMNS + 8 * k, typeClass(outColumns.get(k).type)).putInt(M_COLUMNS + 8 * k + 4, Math.max(0, outColumns.get(k).type.valueLengthIfFixed()));
+                m.putInt(M_NSTATIC_COLUMNS, outStatics.size());
+                for (int k = 0; k < outStatics.size(); k++)
+                    m.putInt(M_STATIC_COLUMNS + 8 * k, typeClass(outStatics.get(k).type)).putInt(M_STATIC_COLUMNS + 8 * k + 4, Math.max(0, outStatics.get(k).type.valueLengthIfFixed()));
                 m.putLong(M_OUT_STATS, outStats.minTimestamp).putLong(M_OUT_STATS + 8, outStats.minLocalDeletionTime).putInt(M_OUT_STATS + 16, outStats.minTTL);
                 m.putInt(M_OUT_COMPRESSOR, outComp).putInt(M_OUT_CHUNK_LEN, cp.chunkLength()).putInt(M_OUT_MAX_COMPRESSED_LEN, cp.maxCompressedLength());
                 m.putInt(M_COLUMN_INDEX_SIZE, DatabaseDescriptor.getColumnIndexSize(BigFormat.getInstance().getDefaultColumnIndexSize()));

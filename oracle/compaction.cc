@@ -5,7 +5,7 @@
 // One call = one CompactionTask.runMayThrow hot loop (S/db/compaction/CompactionTask.java:184-236), single threaded as the
 // reference is. S/ = /root/reference/src/java/org/apache/cassandra/. Each block cites the file:line it follows.
 //
-// Scope restated: simple regular columns, no static rows, no complex columns/counters, tombstoneOption NONE, no 2i
+// Scope restated: simple regular and static columns, no complex columns/counters, tombstoneOption NONE, no 2i
 // (rowProcessingNeeded() == false), forward order. Anything else returns B200C_EUNSUPPORTED — same envelope as the GPU engine.
 #include "codec.h"
 #include "../include/b200c.h"
@@ -76,6 +76,7 @@ static inline bool kind_is_start(int k) { return k == K_INCL_START || k == K_EXC
 struct Schema {
     int nclust; b200c_column clust[B200C_MAX_CLUSTERING];
     int ncols; b200c_column cols[B200C_MAX_COLUMNS];
+    int nstat; b200c_column stat[B200C_MAX_STATIC_COLUMNS];      // static columns (SerializationHeader.columns(true))
 };
 
 // AbstractType.compare for the supported comparison classes (S/db/marshal/AbstractType.java:212-215; LongType.compareLongs:
@@ -131,6 +132,8 @@ struct Source {
     const uint8_t* key = nullptr; int keylen = 0; int64_t token = 0;
     bool has_prev = false; int64_t prev_token = 0; const uint8_t* prev_key = nullptr; int prev_klen = 0;
     DT pdel; uint64_t upos = 0;     // cursor inside the partition (next unfiltered)
+    Unf stat; bool has_stat = false;     // the partition's static row (non-empty)
+    const struct Schema* schema = nullptr;
     uint64_t part_start = 0, part_end = 0;
     uint64_t range_bytes = 0;       // uncompressed bytes of the partitions inside the token range (scanner accounting)
 };
@@ -190,6 +193,42 @@ static int64_t decode_ldt(int64_t ldt, int32_t ttl) {
 }
 
 // UnfilteredSerializer.deserialize: S/db/rows/UnfilteredSerializer.java:433-645. Returns false at end of partition.
+// UnfilteredSerializer.deserializeRowBody :574-650 (sizes, liveness, deletion, columns subset, cells) for the regular or the static column set
+static void read_row_body(Reader& r, Source& src, uint8_t flags, int ncols_in, const int32_t* colmap, const b200c_column* types, Unf& u) {
+    const b200c_encoding_stats& hs = src.in->header_stats;
+    r.vint(); r.vint();                                   // row size, previous unfiltered size
+    u.info = Live(); u.del = DT();
+    if (flags & 0x04) u.info.ts = (int64_t)(r.vint() + (uint64_t)hs.min_timestamp);
+    if (flags & 0x08) { u.info.ttl = r.vint32() + hs.min_ttl; u.info.ldt = (int64_t)r.vint32() + hs.min_local_deletion_time; }
+    if (flags & 0x10) u.del = read_delta_dt(r, hs);
+    uint64_t missing = 0;
+    if (!(flags & 0x20)) {                                // Columns.deserializeSubset: S/db/Columns.java:533-560
+        if (ncols_in >= 64) throw Unsupported{">= 64 columns"};
+        missing = r.vint();
+    }
+    u.cells.clear();
+    for (int i = 0; i < ncols_in; i++) {
+        if ((missing >> i) & 1) continue;
+        int oc = colmap[i];
+        const b200c_column& t = types[oc];
+        uint8_t cf = r.u8();                              // Cell.Serializer.deserialize: S/db/rows/Cell.java:307-349
+        bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
+        CellV c; c.col = oc;
+        c.ts = use_ts ? u.info.ts : (int64_t)(r.vint() + (uint64_t)hs.min_timestamp);
+        c.ldt = use_ttl ? u.info.ldt : ((deleted || expiring) ? (int64_t)r.vint32() + hs.min_local_deletion_time : NO_DEL);
+        c.ttl = use_ttl ? u.info.ttl : (expiring ? r.vint32() + hs.min_ttl : 0);
+        c.val = r.p; c.vlen = 0;
+        if (has_value) {
+            int len = t.fixed_len > 0 ? t.fixed_len : (int)r.vint32();
+            if (len < 0) throw Corrupt{src.idx, 4, 0, 0, "negative value length"};
+            c.val = r.bytes(len); c.vlen = len;
+        }
+        if (c.ttl < 0) throw Corrupt{src.idx, 4, 0, 0, "Invalid TTL"};
+        if (c.ldt != NO_DEL) c.ldt = decode_ldt(c.ldt, c.ttl);
+        u.cells.push_back(c);
+    }
+    std::sort(u.cells.begin(), u.cells.end(), [](const CellV& a, const CellV& b) { return a.col < b.col; });
+}
 static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u);
 static bool read_unfiltered(Source& src, const Schema& s, Unf& u) {
     // UnfilteredSerializer.deserialize :433-447: empty rows (e.g. all columns dropped) are skipped at read time
@@ -219,43 +258,12 @@ static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u) {
     } else {
         u.is_row = true;
         uint8_t ext = (flags & 0x80) ? r.u8() : 0;
-        if (ext & 0x01) throw Unsupported{"static row"};
+        if (ext & 0x01) throw Corrupt{src.idx, 4, 0, 0, "static flag on a clustered row"};      // UnfilteredSerializer.deserialize :477-479
         if (ext & 0x02) throw Unsupported{"shadowable deletion"};
         if (flags & 0x40) throw Unsupported{"complex deletion"};
         u.c.kind = K_CLUSTERING;
         read_clust_values(r, s, s.nclust, u.c);
-        r.vint(); r.vint();                                   // row size, previous unfiltered size
-        u.info = Live(); u.del = DT();
-        if (flags & 0x04) u.info.ts = (int64_t)(r.vint() + (uint64_t)hs.min_timestamp);
-        if (flags & 0x08) { u.info.ttl = r.vint32() + hs.min_ttl; u.info.ldt = (int64_t)r.vint32() + hs.min_local_deletion_time; }
-        if (flags & 0x10) u.del = read_delta_dt(r, hs);
-        uint64_t missing = 0;
-        if (!(flags & 0x20)) {                                // Columns.deserializeSubset: S/db/Columns.java:533-560
-            if (in.ncolumns >= 64) throw Unsupported{">= 64 columns"};
-            missing = r.vint();
-        }
-        u.cells.clear();
-        for (int i = 0; i < in.ncolumns; i++) {
-            if ((missing >> i) & 1) continue;
-            int oc = in.column_map[i];
-            const b200c_column& t = s.cols[oc];
-            uint8_t cf = r.u8();                              // Cell.Serializer.deserialize: S/db/rows/Cell.java:307-349
-            bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
-            CellV c; c.col = oc;
-            c.ts = use_ts ? u.info.ts : (int64_t)(r.vint() + (uint64_t)hs.min_timestamp);
-            c.ldt = use_ttl ? u.info.ldt : ((deleted || expiring) ? (int64_t)r.vint32() + hs.min_local_deletion_time : NO_DEL);
-            c.ttl = use_ttl ? u.info.ttl : (expiring ? r.vint32() + hs.min_ttl : 0);
-            c.val = r.p; c.vlen = 0;
-            if (has_value) {
-                int len = t.fixed_len > 0 ? t.fixed_len : (int)r.vint32();
-                if (len < 0) throw Corrupt{src.idx, 4, 0, 0, "negative value length"};
-                c.val = r.bytes(len); c.vlen = len;
-            }
-            if (c.ttl < 0) throw Corrupt{src.idx, 4, 0, 0, "Invalid TTL"};
-            if (c.ldt != NO_DEL) c.ldt = decode_ldt(c.ldt, c.ttl);
-            u.cells.push_back(c);
-        }
-        std::sort(u.cells.begin(), u.cells.end(), [](const CellV& a, const CellV& b) { return a.col < b.col; });
+        read_row_body(r, src, flags, in.ncolumns, in.column_map, s.cols, u);
     }
     src.upos = r.p - src.dptr();
     return true;
@@ -369,6 +377,17 @@ static void next_partition(Source& src, int64_t tok_lo, int64_t tok_hi) {
                 throw Corrupt{src.idx, 3, 0, src.ipos, "Index.db entry does not match Data.db"};
             Reader r{d + pos + 2 + kl, d + end, src.idx};
             src.pdel = read_partition_dt(r);                               // SSTableIdentityIterator.create :62-78
+            src.has_stat = false;
+            if (in.nstatic_columns > 0) {                                  // SSTableSimpleIterator.readStaticRow -> UnfilteredSerializer.deserializeStaticRow :538-552
+                uint8_t flags = r.u8();
+                if ((flags & 0x01) || (flags & 0x02) || !(flags & 0x80)) throw Corrupt{src.idx, 4, 0, 0, "static row flags"};
+                uint8_t ext = r.u8();
+                if (!(ext & 0x01)) throw Corrupt{src.idx, 4, 0, 0, "static row flags"};
+                if ((ext & 0x02) || (flags & 0x40)) throw Unsupported{"shadowable / complex deletion"};
+                src.stat.is_row = true; src.stat.c = Clust(); src.stat.c.kind = K_STATIC;
+                read_row_body(r, src, flags, in.nstatic_columns, in.static_column_map, src.schema->stat, src.stat);
+                src.has_stat = !(src.stat.info.empty() && src.stat.del.live() && src.stat.cells.empty());
+            }
             src.key = d + pos + 2; src.keylen = kl; src.token = tok; src.part_start = pos; src.part_end = end;
             src.range_bytes += end - pos;
             src.upos = r.p - d;
@@ -699,10 +718,59 @@ struct Writer {
         o.vint((uint64_t)(int64_t)(int32_t)(d.ldt - m->out_stats.min_local_deletion_time));
     }
 
-    void start_partition(const uint8_t* key, int keylen, const DT& pdel) {     // SortedTablePartitionWriter.start :97-115
+    static int row_flags(const Unf& u, int ncols) {          // UnfilteredSerializer.serialize(Row) :151-186
+        int flags = 0;
+        if (!u.info.empty()) flags |= 0x04;
+        if (u.info.expiring()) flags |= 0x08;
+        if (!u.del.live()) flags |= 0x10;
+        if ((int)u.cells.size() == ncols) flags |= 0x20;
+        return flags;
+    }
+    void write_row_body(OutBuf& body, const Unf& u, int flags, int ncols, const b200c_column* types) {      // serializeRowBody :213-269
+        if (flags & 0x04) body.vint((uint64_t)u.info.ts - (uint64_t)m->out_stats.min_timestamp);
+        if (flags & 0x08) { body.vint((uint64_t)(int64_t)(u.info.ttl - m->out_stats.min_ttl));
+                            body.vint((uint64_t)(int64_t)(int32_t)(u.info.ldt - m->out_stats.min_local_deletion_time)); }
+        if (flags & 0x10) write_delta_dt(body, u.del);
+        if (!(flags & 0x20)) {                            // Columns.serializeSubset :503-531, encodeBitmap :586-608
+            if (ncols >= 64) throw Unsupported{">= 64 columns"};
+            uint64_t missing = (1ull << ncols) - 1;
+            for (const CellV& c : u.cells) missing &= ~(1ull << c.col);
+            body.vint(missing);
+        }
+        for (const CellV& c : u.cells) {                  // Cell.Serializer.serialize: S/db/rows/Cell.java:268-305
+            bool has_value = c.vlen > 0, deleted = c.tombstone(), expiring = c.expiring();
+            bool use_ts = !u.info.empty() && c.ts == u.info.ts;
+            bool use_ttl = expiring && u.info.expiring() && c.ttl == u.info.ttl && c.ldt == u.info.ldt;
+            int cf = 0;
+            if (!has_value) cf |= 0x04;
+            if (deleted) cf |= 0x01; else if (expiring) cf |= 0x02;
+            if (use_ts) cf |= 0x08;
+            if (use_ttl) cf |= 0x10;
+            body.u8((uint8_t)cf);
+            if (!use_ts) body.vint((uint64_t)c.ts - (uint64_t)m->out_stats.min_timestamp);
+            if ((deleted || expiring) && !use_ttl) body.vint((uint64_t)(int64_t)(int32_t)(c.ldt - m->out_stats.min_local_deletion_time));
+            if (expiring && !use_ttl) body.vint((uint64_t)(int64_t)(c.ttl - m->out_stats.min_ttl));
+            if (has_value) { if (types[c.col].fixed_len <= 0) body.vint((uint64_t)c.vlen); body.put(c.val, c.vlen); }
+        }
+    }
+
+    // stat: the merged, purged static row, or nullptr when it is empty. Tables with static columns always carry one per partition
+    // (SortedTableWriter.append :144-146, SortedTablePartitionWriter.addStaticRow :117-126, UnfilteredSerializer.serializeStaticRow :144-149)
+    void start_partition(const uint8_t* key, int keylen, const DT& pdel, const Unf* stat = nullptr) {     // SortedTablePartitionWriter.start :97-115
         part_start = position;
         tmp.b.clear(); tmp.be16((uint16_t)keylen); tmp.put(key, keylen); write_partition_dt(tmp, pdel);
         write(tmp.b.data(), tmp.b.size());
+        if (sc.nstat > 0) {
+            static const Unf empty_static;
+            const Unf& u = stat ? *stat : empty_static;
+            tmp.b.clear(); body.b.clear();
+            int flags = row_flags(u, sc.nstat) | 0x80;                         // hasExtendedFlags(row) = row.isStatic() || shadowable :755-758
+            tmp.u8((uint8_t)flags); tmp.u8(0x01);                             // extended flags: IS_STATIC
+            write_row_body(body, u, flags, sc.nstat, sc.stat);
+            tmp.vint(body.size() + vint_size(0)); tmp.vint(0);
+            write(tmp.b.data(), tmp.b.size()); write(body.b.data(), body.b.size());
+            if (stat) outs.back().meta.row(u);                                // SortedTableWriter.addStaticRow :188-197: collectStats unless empty
+        }
         header_len = position - part_start;
         prev_row_start = 0; have_first = false; open_marker = DT(); index_infos.clear(); block_start = 0;
         outs.back().meta.partition_deletion(pdel);                          // startPartition :183-189
@@ -731,39 +799,10 @@ struct Writer {
             else write_delta_dt(body, kind_is_start(u.c.kind) ? u.m_open : u.m_close);
             tmp.vint(body.size() + vint_size(prev_size)); tmp.vint(prev_size);
         } else {
-            int flags = 0;
-            if (!u.info.empty()) flags |= 0x04;
-            if (u.info.expiring()) flags |= 0x08;
-            if (!u.del.live()) flags |= 0x10;
-            bool all = (int)u.cells.size() == sc.ncols;
-            if (all) flags |= 0x20;
+            int flags = row_flags(u, sc.ncols);
             tmp.u8((uint8_t)flags);
             write_clust_values(tmp, u.c);
-            if (flags & 0x04) body.vint((uint64_t)u.info.ts - (uint64_t)m->out_stats.min_timestamp);
-            if (flags & 0x08) { body.vint((uint64_t)(int64_t)(u.info.ttl - m->out_stats.min_ttl));
-                                body.vint((uint64_t)(int64_t)(int32_t)(u.info.ldt - m->out_stats.min_local_deletion_time)); }
-            if (flags & 0x10) write_delta_dt(body, u.del);
-            if (!all) {                                   // Columns.serializeSubset :503-531, encodeBitmap :586-608
-                if (sc.ncols >= 64) throw Unsupported{">= 64 columns"};
-                uint64_t missing = (sc.ncols == 64 ? ~0ull : ((1ull << sc.ncols) - 1));
-                for (const CellV& c : u.cells) missing &= ~(1ull << c.col);
-                body.vint(missing);
-            }
-            for (const CellV& c : u.cells) {              // Cell.Serializer.serialize: S/db/rows/Cell.java:268-305
-                bool has_value = c.vlen > 0, deleted = c.tombstone(), expiring = c.expiring();
-                bool use_ts = !u.info.empty() && c.ts == u.info.ts;
-                bool use_ttl = expiring && u.info.expiring() && c.ttl == u.info.ttl && c.ldt == u.info.ldt;
-                int cf = 0;
-                if (!has_value) cf |= 0x04;
-                if (deleted) cf |= 0x01; else if (expiring) cf |= 0x02;
-                if (use_ts) cf |= 0x08;
-                if (use_ttl) cf |= 0x10;
-                body.u8((uint8_t)cf);
-                if (!use_ts) body.vint((uint64_t)c.ts - (uint64_t)m->out_stats.min_timestamp);
-                if ((deleted || expiring) && !use_ttl) body.vint((uint64_t)(int64_t)(int32_t)(c.ldt - m->out_stats.min_local_deletion_time));
-                if (expiring && !use_ttl) body.vint((uint64_t)(int64_t)(c.ttl - m->out_stats.min_ttl));
-                if (has_value) { if (sc.cols[c.col].fixed_len <= 0) body.vint((uint64_t)c.vlen); body.put(c.val, c.vlen); }
-            }
+            write_row_body(body, u, flags, sc.ncols, sc.cols);
             tmp.vint(body.size() + vint_size(prev_size)); tmp.vint(prev_size);
         }
         write(tmp.b.data(), tmp.b.size());
@@ -799,14 +838,20 @@ struct Writer {
 int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
     auto t0 = std::chrono::steady_clock::now();
     if (m->abi_version != B200C_ABI_VERSION || m->ninputs <= 0 || m->ninputs > B200C_MAX_INPUTS) return B200C_EINVAL;
-    if (m->has_static || m->tombstone_option != 0 || m->enforce_strict_liveness) return B200C_EUNSUPPORTED;
+    if (m->tombstone_option != 0 || m->enforce_strict_liveness) return B200C_EUNSUPPORTED;
     if (m->nclustering > B200C_MAX_CLUSTERING || m->ncolumns > B200C_MAX_COLUMNS || m->ncolumns >= 64) return B200C_EUNSUPPORTED;
-    Schema sc; sc.nclust = m->nclustering; sc.ncols = m->ncolumns;
-    memcpy(sc.clust, m->clustering, sizeof(sc.clust)); memcpy(sc.cols, m->columns, sizeof(sc.cols));
+    if (m->nstatic_columns < 0 || m->nstatic_columns > B200C_MAX_STATIC_COLUMNS) return B200C_EUNSUPPORTED;
+    for (int i = 0; i < m->ninputs; i++) {
+        const b200c_input& in = m->inputs[i];
+        if (in.nstatic_columns < 0 || in.nstatic_columns > m->nstatic_columns) return B200C_EINVAL;
+        for (int k = 0; k < in.nstatic_columns; k++) if (in.static_column_map[k] < 0 || in.static_column_map[k] >= m->nstatic_columns) return B200C_EINVAL;
+    }
+    Schema sc; sc.nclust = m->nclustering; sc.ncols = m->ncolumns; sc.nstat = m->nstatic_columns;
+    memcpy(sc.clust, m->clustering, sizeof(sc.clust)); memcpy(sc.cols, m->columns, sizeof(sc.cols)); memcpy(sc.stat, m->static_columns, sizeof(sc.stat));
     g_partitioner = m->partitioner;
     std::vector<Source> srcs(m->ninputs);
     uint64_t bytes_read = 0;
-    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; open_source(srcs[i], m->token_lo, m->token_hi); bytes_read += srcs[i].dsize(); next_partition(srcs[i], m->token_lo, m->token_hi); }
+    for (int i = 0; i < m->ninputs; i++) { srcs[i].idx = i; srcs[i].in = &m->inputs[i]; srcs[i].schema = &sc; open_source(srcs[i], m->token_lo, m->token_hi); bytes_read += srcs[i].dsize(); next_partition(srcs[i], m->token_lo, m->token_hi); }
     if (m->partitioner != B200C_PARTITIONER_MURMUR3 && m->partitioner != B200C_PARTITIONER_BYTE_ORDERED) return B200C_EUNSUPPORTED;
     if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) return B200C_EUNSUPPORTED;
     Purger pg{m->now_in_sec, m->gc_before, m->purge_max_timestamp};
@@ -838,11 +883,18 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
         DT out_pdel = pg.should_purge(pdel) ? DT() : pdel;     // PurgeFunction.applyToDeletion :95-99
         std::string keycopy((const char*)srcs[group[0]].key, srcs[group[0]].keylen);
         bool started = false; uint64_t written = 0;
+        // static row: UnfilteredRowMergeIterator's constructor merges them eagerly, whatever the fan-in, with the partition deletion as the
+        // active deletion (mergeStaticRows S/db/rows/UnfilteredRowIterators.java:484-505); then PurgeFunction.applyToStatic :101-106
+        Unf stat_out; bool have_static = false;
+        if (sc.nstat > 0) {
+            std::vector<Unf*> vs; for (int i : group) if (srcs[i].has_stat) vs.push_back(&srcs[i].stat);
+            if (!vs.empty()) have_static = merge_rows(vs, pdel, stat_out) && purge_row(stat_out, pg);
+        }
         auto emit = [&](Unf& u) {
             total_source_rows++;                               // Purger.updateProgress :366-371
             bool keep = u.is_row ? purge_row(u, pg) : purge_marker(u, pg);
             if (!keep) return;
-            if (!started) { w.start_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel); started = true; }
+            if (!started) { w.start_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel, have_static ? &stat_out : nullptr); started = true; }
             w.add_unfiltered(u); written++;
         };
         if (group.size() == 1) {
@@ -872,7 +924,7 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
             }
         }
         // partition.isEmpty(): S/db/rows/UnfilteredRowIterator.java:63-68; SortedTableWriter.append :134
-        if (!started && !out_pdel.live()) { w.start_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel); started = true; }
+        if (!started && (!out_pdel.live() || have_static)) { w.start_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel, have_static ? &stat_out : nullptr); started = true; }
         if (started) w.end_partition((const uint8_t*)keycopy.data(), (int)keycopy.size(), out_pdel, written);
         for (int i : group) next_partition(srcs[i], m->token_lo, m->token_hi);
     }

@@ -97,6 +97,8 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     P.U = U; P.ninputs = K; P.nclust = m->nclustering; P.ncols = m->ncolumns; P.column_index_size = m->column_index_size > 0 ? m->column_index_size : 65536;
     for (int k = 0; k < m->nclustering; k++) { P.ctype[k] = m->clustering[k].type; P.cfix[k] = m->clustering[k].fixed_len; }
     for (int k = 0; k < m->ncolumns; k++) P.vfix[k] = m->columns[k].fixed_len;
+    P.nstat = m->nstatic_columns; P.mcols = std::max(m->ncolumns, m->nstatic_columns);
+    for (int k = 0; k < m->nstatic_columns; k++) P.sfix[k] = m->static_columns[k].fixed_len;
     P.o_min_ts = m->out_stats.min_timestamp; P.o_min_ldt = m->out_stats.min_local_deletion_time; P.o_min_ttl = m->out_stats.min_ttl;
     P.now = m->now_in_sec; P.gc_before = m->gc_before; P.purge_max_ts = m->purge_max_timestamp;
     P.partitioner = m->partitioner;
@@ -105,6 +107,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
         const b200c_input& in = m->inputs[i]; InDesc& d = hin[i];
         d.ubase = ubase[i]; d.ulen = in.data_length; d.min_ts = in.header_stats.min_timestamp; d.min_ldt = in.header_stats.min_local_deletion_time; d.min_ttl = in.header_stats.min_ttl;
         d.ncols = in.ncolumns; for (int k = 0; k < in.ncolumns; k++) d.colmap[k] = in.column_map[k];
+        d.nstat = in.nstatic_columns; for (int k = 0; k < in.nstatic_columns; k++) d.smap[k] = in.static_column_map[k];
     }
     // ---- K4, the code under test: size pass, host-side scans, emit pass ---------------------------------------------------------------
     std::vector<Cur> cur(MAXK); std::vector<DT> open_dt(MAXK); std::vector<MCell> merged(MAXCOLS);

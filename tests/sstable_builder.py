@@ -29,15 +29,18 @@ class Marker:
     def __init__(self, kind, values, close=None, open=None):
         self.kind = kind; self.ck = tuple(values); self.close = close; self.open = open
 class Partition:
-    def __init__(self, key, unfiltereds=(), deletion=LIVE):
-        self.key = key; self.unfiltereds = list(unfiltereds); self.deletion = deletion
+    """static: Row with ck == () holding cells of the static columns (col = index in Schema.static_columns), or None"""
+    def __init__(self, key, unfiltereds=(), deletion=LIVE, static=None):
+        self.key = key; self.unfiltereds = list(unfiltereds); self.deletion = deletion; self.static = static
 
 class Schema:
-    def __init__(self, clustering_types, columns):
+    def __init__(self, clustering_types, columns, static_columns=()):
         self.clustering_types = [t if "." in t else MARSHAL + t for t in clustering_types]
         self.columns = sorted([(n if isinstance(n, bytes) else n.encode(), t if "." in t else MARSHAL + t) for n, t in columns])
+        self.static_columns = sorted([(n if isinstance(n, bytes) else n.encode(), t if "." in t else MARSHAL + t) for n, t in static_columns])
         self.cfixed = [type_class(t)[1] for t in self.clustering_types]
         self.vfixed = [type_class(t)[1] for _, t in self.columns]
+        self.sfixed = [type_class(t)[1] for _, t in self.static_columns]
     def col_index(self, name):
         name = name if isinstance(name, bytes) else name.encode()
         return [n for n, _ in self.columns].index(name)
@@ -76,18 +79,21 @@ class Builder:
             elif u.kind in (K_INCL_START, K_EXCL_START): body = self.delta_dt(u.open)
             else: body = self.delta_dt(u.close)
             return head + vint(len(body) + len(vint(prev_size))) + vint(prev_size) + body
-        flags = 0
+        return self.row(u, prev_size, self.s.columns, self.s.vfixed, False)
+
+    def row(self, u, prev_size, columns, vfixed, static):
+        flags = 0x80 if static else 0            # static rows carry the extension byte (IS_STATIC), UnfilteredSerializer.java:109-114,755-758
         if u.ts != NO_TS: flags |= 0x04
         if u.ttl: flags |= 0x08
         if u.deletion is not None: flags |= 0x10
         cells = sorted(u.cells, key=lambda c: c.col)
-        if len(cells) == len(self.s.columns): flags |= 0x20
+        if len(cells) == len(columns): flags |= 0x20
         body = bytearray()
         if flags & 0x04: body += vint(u.ts - self.min_ts)
         if flags & 0x08: body += i32s(u.ttl - self.min_ttl) + i32s(u.ldt - self.min_ldt)
         if flags & 0x10: body += self.delta_dt(u.deletion)
         if not flags & 0x20:
-            missing = (1 << len(self.s.columns)) - 1
+            missing = (1 << len(columns)) - 1
             for c in cells: missing &= ~(1 << c.col)
             body += vint(missing)
         for c in cells:
@@ -100,9 +106,9 @@ class Builder:
             if (deleted or expiring) and not use_ttl: body += i32s(c.ldt - self.min_ldt)
             if expiring and not use_ttl: body += i32s(c.ttl - self.min_ttl)
             if c.value:
-                if not self.s.vfixed[c.col]: body += vint(len(c.value))
+                if not vfixed[c.col]: body += vint(len(c.value))
                 body += c.value
-        head = bytes([flags]) + self.clust_values(u.ck)
+        head = bytes([flags, 0x01]) if static else bytes([flags]) + self.clust_values(u.ck)
         return head + vint(len(body) + len(vint(prev_size))) + vint(prev_size) + bytes(body)
 
     def build(self, partitions, chunk_length=16384, compressor=O.COMP_LZ4, generation=0):
@@ -112,6 +118,8 @@ class Builder:
             start = len(data)
             if pi % getattr(self, 'summary_interval', 3) == 0: summary.append(len(index))      # Summary.db sample (tiny interval: many anchors even in small tables)
             data += struct.pack(">H", len(p.key)) + p.key + _part_dt(p.deletion)
+            if self.s.static_columns:              # SortedTablePartitionWriter.addStaticRow :117-126: always present when the header has static columns
+                data += self.row(p.static if p.static is not None else Row(()), 0, self.s.static_columns, self.s.sfixed, True)
             header_len = len(data) - start
             prev_start = 0; infos = []; first = None; block_start = 0; open_marker = None; last = None
             for u in p.unfiltereds:
@@ -140,7 +148,7 @@ class Builder:
         name = {O.COMP_LZ4: "LZ4Compressor", O.COMP_SNAPPY: "SnappyCompressor"}[compressor]
         meta = CompressionMetadata(name, chunk_length, 0x7FFFFFFF, len(data), offs)
         stats = (self.min_ts, self.min_ldt, self.min_ttl)
-        t = SSTable(bytes(image), bytes(index), meta, stats, stats, self.s.clustering_types, self.s.columns, generation=generation)
+        t = SSTable(bytes(image), bytes(index), meta, stats, stats, self.s.clustering_types, self.s.columns, self.s.static_columns, generation=generation)
         t.uncompressed = data
         import numpy as _np
         t.summary_positions = _np.asarray(summary, dtype=_np.uint64)
@@ -176,10 +184,35 @@ def decode_stream(schema: Schema, data: bytes, stats):
             off = limit
         return tuple(out)
     def rdt(): return (rv() + min_ts, ri32() + min_ldt)
+    def rrow(flags, ck, columns, vfixed):
+        nonlocal p
+        rv(); rv()
+        r = Row(ck)
+        if flags & 0x04: r.ts = rv() + min_ts
+        if flags & 0x08: r.ttl = ri32() + min_ttl; r.ldt = ri32() + min_ldt
+        if flags & 0x10: r.deletion = rdt()
+        missing = 0 if flags & 0x20 else rv()
+        for ci in range(len(columns)):
+            if (missing >> ci) & 1: continue
+            cf = data[p]; p += 1
+            ts = r.ts if cf & 0x08 else rv() + min_ts
+            ldt = r.ldt if cf & 0x10 else ((ri32() + min_ldt) if cf & 0x03 else NO_DELETION_TIME)
+            ttl = r.ttl if cf & 0x10 else ((ri32() + min_ttl) if cf & 0x02 else 0)
+            val = b""
+            if not cf & 0x04:
+                ln = vfixed[ci] or rv(); val = data[p:p + ln]; p += ln
+            r.cells.append(Cell(ci, ts, val, ttl, ldt))
+        return r
     while p < len(data):
         (kl,) = struct.unpack_from(">H", data, p); p += 2; key = data[p:p + kl]; p += kl
         if data[p] == 0x80: pdel = None; p += 1
         else: pdel = struct.unpack_from(">qI", data, p); p += 12
+        static = None
+        if schema.static_columns:
+            flags, ext = data[p], data[p + 1]; p += 2
+            assert flags & 0x80 and ext == 0x01 and not flags & 0x03, "static row flags"
+            static = rrow(flags, (), schema.static_columns, schema.sfixed)
+            if static.ts == NO_TS and static.deletion is None and not static.cells: static = None
         us = []
         while True:
             flags = data[p]; p += 1
@@ -190,22 +223,7 @@ def decode_stream(schema: Schema, data: bytes, stats):
                 elif kind in (K_INCL_START, K_EXCL_START): us.append(Marker(kind, ck, None, rdt()))
                 else: us.append(Marker(kind, ck, rdt(), None))
                 continue
-            ck = rclust(len(schema.clustering_types)); rv(); rv()
-            r = Row(ck)
-            if flags & 0x04: r.ts = rv() + min_ts
-            if flags & 0x08: r.ttl = ri32() + min_ttl; r.ldt = ri32() + min_ldt
-            if flags & 0x10: r.deletion = rdt()
-            missing = 0 if flags & 0x20 else rv()
-            for ci in range(len(schema.columns)):
-                if (missing >> ci) & 1: continue
-                cf = data[p]; p += 1
-                ts = r.ts if cf & 0x08 else rv() + min_ts
-                ldt = r.ldt if cf & 0x10 else ((ri32() + min_ldt) if cf & 0x03 else NO_DELETION_TIME)
-                ttl = r.ttl if cf & 0x10 else ((ri32() + min_ttl) if cf & 0x02 else 0)
-                val = b""
-                if not cf & 0x04:
-                    ln = schema.vfixed[ci] or rv(); val = data[p:p + ln]; p += ln
-                r.cells.append(Cell(ci, ts, val, ttl, ldt))
-            us.append(r)
-        parts.append(Partition(key, us, pdel))
+            ck = rclust(len(schema.clustering_types))
+            us.append(rrow(flags, ck, schema.columns, schema.vfixed))
+        parts.append(Partition(key, us, pdel, static))
     return parts

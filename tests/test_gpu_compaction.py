@@ -173,10 +173,18 @@ def test_corrupt_index_is_rejected(ctx):
 
 def test_unsupported_is_refused_not_faked(ctx):
     from cassandra_b200 import native
-    s_static = Schema(["Int32Type"], [("val", "UTF8Type")])
-    t = Builder(s_static, (0, 0, 0)).build([Partition(b"k", [Row((I32(1),), [Cell(0, 5, b"v")], ts=5)])])
-    t.static_columns = [(b"s", "org.apache.cassandra.db.marshal.UTF8Type")]
+    class ComplexDeletion(Builder):                  # HAS_COMPLEX_DELETION (0x40): complex columns are outside the envelope
+        def row(self, u, prev_size, columns, vfixed, static):
+            b = bytearray(super().row(u, prev_size, columns, vfixed, static)); b[0] |= 0x40; return bytes(b)
+    t = ComplexDeletion(Schema(["Int32Type"], [("val", "UTF8Type")]), (0, 0, 0)).build([Partition(b"k", [Row((I32(1),), [Cell(0, 5, b"v")], ts=5)])])
     with pytest.raises(native.UnsupportedError):
+        CompactionTask([t], CompactionController(NOW)).execute(GpuEngine(ctx))
+    with pytest.raises(native.UnsupportedError):
+        CompactionTask([t], CompactionController(NOW)).execute(O.OracleEngine())
+    # a header that promises static columns over a stream without static rows is corruption, not something to guess around
+    t = Builder(Schema(["Int32Type"], [("val", "UTF8Type")]), (0, 0, 0)).build([Partition(b"k", [Row((I32(1),), [Cell(0, 5, b"v")], ts=5)])])
+    t.static_columns = [(b"s", "org.apache.cassandra.db.marshal.UTF8Type")]
+    with pytest.raises(native.CorruptSSTableError):
         CompactionTask([t], CompactionController(NOW)).execute(GpuEngine(ctx))
 
 @pytest.mark.parametrize("limit,n,universe", [(200_000, 6, 30000), (1 << 20, 8, 60000), (50_000, 3, 8000)])
@@ -614,3 +622,34 @@ def test_device_resident_inputs_whole_ring_and_token_shards(ctx):
         w = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine())
         g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(GpuEngine(ctx))
         assert g.outputs[0].data == w.outputs[0].data and g.outputs[0].partitions == w.outputs[0].partitions
+
+
+# ---- static rows ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,wide,cis", [(1, False, 2048), (2, False, 65536), (3, True, 1024)])
+def test_static_rows_match_oracle(ctx, seed, wide, cis):
+    from static_tables import static_tables
+    tabs = static_tables(seed, ntables=5, nkeys=400, wide=wide, cis=cis)
+    both(ctx, tabs, CompactionController(NOW, 864000), column_index_size=cis, with_metadata=True)
+    both(ctx, tabs, CompactionController(NOW, 10**9), column_index_size=cis)
+    both(ctx, tabs, CompactionController(NOW, 864000, overlapping_min_timestamp=1015), column_index_size=cis)
+    both(ctx, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)     # one source: the partition deletion still shadows static cells
+    both(ctx, tabs[2:3], CompactionController(NOW, 864000), column_index_size=cis)    # no static columns in the only input
+
+def test_static_rows_every_kernel_variant(ctx, monkeypatch):
+    from static_tables import static_tables
+    many = static_tables(7, ntables=20, nkeys=300, cis=2048)                          # fan-in above 16: the warp-per-partition kernel
+    both(ctx, many, CompactionController(NOW, 864000), column_index_size=2048, with_metadata=True)
+    tabs = static_tables(8, ntables=6, nkeys=2000, cis=2048)
+    for env in ({"B200C_K4_STAGED": "1"}, {"B200C_K4_STAGED": "0"}, {"B200C_RANGES": "5"}, {"B200C_K4_WIDE_WARP": "2048"}):
+        for k, v in env.items(): monkeypatch.setenv(k, v)
+        both(ctx, tabs, CompactionController(NOW, 864000), column_index_size=2048, with_metadata=True)
+        for k in env: monkeypatch.delenv(k)
+    # LCS output switching and a token sub-range with static rows
+    want = CompactionTask(tabs, CompactionController(NOW), column_index_size=2048, max_sstable_bytes=60000).execute(O.OracleEngine())
+    got = CompactionTask(tabs, CompactionController(NOW), column_index_size=2048, max_sstable_bytes=60000).execute(GpuEngine(ctx))
+    assert len(got.outputs) == len(want.outputs) > 1
+    for g, w in zip(got.outputs, want.outputs): assert g.data == w.data and g.index == w.index and g.digest == w.digest
+    lo, hi = -(1 << 62), (1 << 61)
+    w = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine()).outputs[0]
+    g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(GpuEngine(ctx)).outputs[0]
+    assert g.data == w.data and g.index == w.index and g.digest == w.digest

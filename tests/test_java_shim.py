@@ -36,11 +36,11 @@ def test_layout_table_matches_the_ctypes_mirror(jni):
     def offs(cls, fields): return [getattr(cls, f).offset for f in fields]
     want = [C.sizeof(x) for x in (native.Input, native.Manifest, native.Output, native.Result, native.Progress, native.SSTableStats, native.Corruption)]
     want += offs(native.Input, ["data", "data_len", "index", "index_len", "chunk_offsets", "nchunks", "data_length", "compressor", "chunk_len", "max_compressed_len",
-                                "ncolumns", "column_map", "header_stats", "level", "summary_positions", "nsummary"])
-    want += offs(native.Manifest, ["abi_version", "ninputs", "inputs", "nclustering", "clustering", "ncolumns", "columns", "has_static", "out_stats", "out_compressor",
+                                "ncolumns", "column_map", "header_stats", "level", "summary_positions", "nsummary", "nstatic_columns", "static_column_map"])
+    want += offs(native.Manifest, ["abi_version", "ninputs", "inputs", "nclustering", "clustering", "ncolumns", "columns", "nstatic_columns", "out_stats", "out_compressor",
                                    "out_chunk_len", "out_max_compressed_len", "column_index_size", "now_in_sec", "gc_before", "purge_max_timestamp", "tombstone_option",
                                    "enforce_strict_liveness", "token_lo", "token_hi", "max_sstable_bytes", "partitioner", "npurge_ranges", "purge_range_hi",
-                                   "purge_range_max_ts", "bloom_hash_count", "min_index_interval", "bloom_words"])
+                                   "purge_range_max_ts", "bloom_hash_count", "min_index_interval", "bloom_words", "static_columns"])
     want += offs(native.Output, ["data", "data_cap", "data_len", "index", "index_cap", "index_len", "chunk_offsets", "chunk_cap", "nchunks", "data_length", "digest",
                                  "partitions", "rows", "key_buf", "key_cap", "first_key_len", "last_key_len", "filter", "filter_cap", "filter_len", "summary",
                                  "summary_cap", "summary_len", "stats"])

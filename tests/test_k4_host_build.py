@@ -136,3 +136,13 @@ def test_k4_source_survives_damaged_data_under_asan(k4lib, tmp_path):
     c = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:abort_on_error=0"))
     assert c.returncode == 0 and "k4 corruption fuzz done" in c.stdout, (c.stdout + c.stderr)[-4000:]
+
+@pytest.mark.parametrize("seed,wide,cis", [(1, False, 2048), (2, False, 65536), (3, True, 1024)])
+def test_k4_source_static_rows(k4lib, seed, wide, cis):
+    from static_tables import static_tables
+    tabs = static_tables(seed, ntables=5, wide=wide, cis=cis)
+    check(k4lib, tabs, CompactionController(NOW, 864000), column_index_size=cis)                 # old tombstones purge
+    check(k4lib, tabs, CompactionController(NOW, 10**9), column_index_size=cis)                  # nothing purges
+    check(k4lib, tabs, CompactionController(NOW, 864000, overlapping_min_timestamp=1015), column_index_size=cis)
+    check(k4lib, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)             # single source: partition deletion still shadows the static row
+    check(k4lib, tabs[2:3], CompactionController(NOW, 864000), column_index_size=cis)            # input without static columns

@@ -237,3 +237,73 @@ def test_empty_rows_are_skipped_at_read_time():
     t = b.build([Partition(b"k", [Row((I32(1),), []), Row((I32(2),), [Cell(0, 5, b"v")])])])
     parts, r = compact([t], gc_grace=10**9)
     assert [u.ck for u in parts[0].unfiltereds] == [(I32(2),)] and r.stats["total_source_rows"] == 1 + 1
+
+# ---- static rows ----------------------------------------------------------------------------------------------------
+# No `oa` fixture under the reference's test data carries static columns, so these pin the oracle against the reference's rules restated:
+# mergeStaticRows (UnfilteredRowIterators.java:484-505), PurgeFunction.applyToStatic (:101-106), SortedTableWriter.append/addStaticRow
+# (:134-146,188-197), SortedTablePartitionWriter.addStaticRow (:117-126), UnfilteredSerializer.serializeStaticRow (:144-149).
+S_ST = Schema(["Int32Type"], [("val", "UTF8Type")], static_columns=[("s1", "UTF8Type"), ("s2", "LongType")])
+I64 = lambda v: struct.pack(">q", v)
+
+def test_static_rows_merge_newest_cell_wins_per_column():
+    b = Builder(S_ST, (0, 0, 0))
+    a = b.build([Partition(b"p", [Row((I32(1),), [Cell(0, 10, b"r")], ts=10)], static=Row((), [Cell(0, 100, b"old"), Cell(1, 300, I64(7))]))])
+    c = b.build([Partition(b"p", [Row((I32(2),), [Cell(0, 11, b"q")], ts=11)], static=Row((), [Cell(0, 200, b"new")]))])
+    parts, r = compact([a, c], schema=S_ST, gc_grace=10**9)
+    st = parts[0].static
+    assert [(x.col, x.ts, x.value) for x in st.cells] == [(0, 200, b"new"), (1, 300, I64(7))]
+    assert [u.ck for u in parts[0].unfiltereds] == [(I32(1),), (I32(2),)]
+    assert r.stats["total_source_rows"] == 2 + 1                      # two rows + the static-row step
+
+def test_static_row_identity_with_promoted_index_and_empty_static_rows():
+    rng = random.Random(11); parts = []
+    for k in range(40):
+        rows = [Row((I32(i),), [Cell(0, 1000 + i, b"v" * rng.randint(0, 200))], ts=1000 + i) for i in range(rng.randint(0, 60))]
+        st = None
+        if rng.random() < 0.6: st = Row((), [Cell(ci, 900 + rng.randint(0, 50), v) for ci, v in ((0, b"s" * rng.randint(0, 40)), (1, I64(k))) if rng.random() < 0.7])
+        if st is not None and not st.cells: st = None
+        if not rows and st is None: rows = [Row((I32(0),), [Cell(0, 1000, b"x")], ts=1000)]
+        parts.append(Partition(b"key%03d" % k, rows, None, st))
+    t = Builder(S_ST, (900, 0, 0), column_index_size=1024).build(parts)
+    r = CompactionTask([t], CompactionController(NOW, 10**9), column_index_size=1024).execute(O.OracleEngine())
+    o = r.outputs[0]
+    assert o.data == t.data and o.index == t.index           # headerLength of the promoted index includes the static row
+
+def test_partition_deletion_shadows_static_cells_even_from_a_single_source():
+    b = Builder(S_ST, (0, 0, 0))
+    # Row.Merger.merge(partitionDeletion) runs for the static row whatever the fan-in, while the clustered rows of a lone source pass through
+    t = b.build([Partition(b"p", [Row((I32(1),), [Cell(0, 50, b"kept: TrivialOneToOne")], ts=50)], deletion=(100, NOW), static=Row((), [Cell(0, 50, b"shadowed"), Cell(1, 150, I64(1))]))])
+    parts, _ = compact([t], schema=S_ST, gc_grace=10**9)
+    assert [(x.col, x.ts) for x in parts[0].static.cells] == [(1, 150)]
+    assert len(parts[0].unfiltereds) == 1 and parts[0].deletion == (100, NOW)
+
+def test_static_only_partition_is_written_and_purged_static_only_partition_is_dropped():
+    b = Builder(S_ST, (0, 0, 0))
+    live = Partition(b"live", [], static=Row((), [Cell(0, 5, b"x")]))
+    dead = Partition(b"dead", [], static=Row((), [Cell.tombstone(0, 5, NOW - 10**6)]))
+    t = b.build([live, dead])
+    parts, r = compact([t], schema=S_ST, gc_grace=1000)
+    assert [p.key for p in parts] == [b"live"] and parts[0].static.cells[0].value == b"x"
+    assert r.outputs[0].partitions == 1 and r.outputs[0].rows == 0
+    parts, _ = compact([t], schema=S_ST, gc_grace=10**9)               # not yet purgeable: both stay
+    assert sorted(p.key for p in parts) == [b"dead", b"live"]
+
+def test_static_columns_missing_in_one_input_and_header_union():
+    s_a = Schema(["Int32Type"], [("val", "UTF8Type")], static_columns=[("s2", "LongType")])
+    s_none = Schema(["Int32Type"], [("val", "UTF8Type")])
+    a = Builder(s_a, (0, 0, 0)).build([Partition(b"p", [Row((I32(1),), [Cell(0, 1, b"a")], ts=1)], static=Row((), [Cell(0, 9, I64(42))]))])
+    n = Builder(s_none, (0, 0, 0)).build([Partition(b"p", [Row((I32(1),), [Cell(0, 2, b"b")], ts=2)]), Partition(b"q", [Row((I32(1),), [Cell(0, 2, b"c")], ts=2)])])
+    c = Builder(S_ST, (0, 0, 0)).build([Partition(b"p", [], static=Row((), [Cell(0, 3, b"s1")]))])
+    parts, _ = compact([a, n, c], schema=S_ST, gc_grace=10**9)
+    by = {p.key: p for p in parts}
+    assert [(x.col, x.value) for x in by[b"p"].static.cells] == [(0, b"s1"), (1, I64(42))] and by[b"q"].static is None
+    assert by[b"p"].unfiltereds[0].cells[0].value == b"b"
+
+def test_static_row_counts_in_statistics():
+    b = Builder(S_ST, (0, 0, 0))
+    t = b.build([Partition(b"p", [Row((I32(1),), [Cell(0, 10, b"r")], ts=10)], static=Row((), [Cell(0, 100, b"x"), Cell(1, 300, I64(7))])),
+                 Partition(b"q", [Row((I32(1),), [Cell(0, 10, b"r")], ts=10)])])
+    r = CompactionTask([t], CompactionController(NOW, 10**9), with_metadata=True).execute(O.OracleEngine())
+    st = r.outputs[0].stats
+    # Rows.collectStats runs for the non-empty static row: one more row, two more cells / columns set (SortedTableWriter.addStaticRow :188-197)
+    assert st["total_rows"] == 3 and st["total_cells"] == 4 and st["total_columns_set"] == 4 and st["max_timestamp"] == 300

@@ -234,7 +234,7 @@ def cpu_compact(L, m, res, threads, ranges=0, max_ranges=0):
     if m.max_sstable_bytes or threads <= 1 and not max_ranges:
         rc = L.orc_compact(C.byref(m), C.byref(res), err, 256)
     else:
-        rc = L.orc_compact_parallel(C.byref(m), C.byref(res), threads, ranges or max(threads * 4, 16), max_ranges, tm, C.byref(hi), err, 256)
+        rc = L.orc_compact_parallel(C.byref(m), C.byref(res), threads, ranges or max(threads * 8, 16), max_ranges, tm, C.byref(hi), err, 256)
     dt = time.perf_counter() - t0
     if rc != 0: raise RuntimeError("CPU oracle failed rc=%d: %s" % (rc, err.value.decode()))
     return dt, hi.value, [tm[0], tm[1], tm[2]]

@@ -725,13 +725,15 @@ __global__ void __launch_bounds__(ST_THREADS) k_partition_staged(const K4Args a,
     StatAcc acc; acc.init(sP->now, a.td);
     for (uint32_t t = tid; t < np; t += ST_THREADS) {
         const uint32_t j = j0 + s_order[t];
+        const uint64_t cj = a.op_first[j]; const uint32_t m = (uint32_t)(a.op_first[j + 1] - cj);
+        // the largest fan-in among the lanes that walk this round together (a subset of the warp is fine: it is only a loop bound)
+        const uint32_t m_uni = min((uint32_t)ST_MAXM, __reduce_max_sync(__activemask(), m));
         uint8_t *dout, *iout; uint64_t dcap, dposv; uint32_t nbf, ipf, ixs_cap;
         if (!k4_prologue<true>(a, j, dout, dcap, dposv, iout, nbf, ipf, ixs_cap)) continue;
-        const uint64_t cj = a.op_first[j]; const uint32_t m = (uint32_t)(a.op_first[j + 1] - cj);
         PartOut out{0, 0, 0, 0, 0}; PartStats st{0, 0}; int e = 0;
         if (m > (uint32_t)ST_MAXM || cj - c0 + m > (uint64_t)ST_CUR_CAP) e = PERR_UNSUPPORTED;
         else process_partition<true>(*sP, xl, a.contrib, cj, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, curs + (cj - c0), open_dt, merged, out, st, e,
-                                     a.sg ? &acc : nullptr);
+                                     a.sg ? &acc : nullptr, m_uni);
         k4_epilogue<true>(a, j, cj, out, st, e);
     }
     if (a.sg) stat_flush_warp(a.sg, acc);               // (no thread returns after the barrier wait: every lane gets here)
@@ -1022,8 +1024,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_CUDA_TRY(c, cudaEventRecord(c->ev0, st));
     B200C_CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev0, 0));
     std::vector<uint64_t> h2d_next(K, 0), k1_next(K, 0);      // deferred mode: first chunk of input i not yet copied / not yet decompressed
-    auto chunk_off = [&](int i, uint64_t ch) -> uint64_t { const b200c_input& in = m->inputs[i]; return ch >= in.nchunks ? in.data_len : in.chunk_offsets[ch]; };
-    auto copy_chunks = [&](int i, uint64_t a, uint64_t b) -> int {      // compressed bytes of chunks [a, b) of input i -> CD (host pointers only)
+    // device-resident inputs taking the piece route (a token sub-range): the host schedules the chunk-range copies, so it needs the offsets too
+    std::vector<std::vector<uint64_t>> co_host(dev && deferred ? K : 0);
+    for (size_t i = 0; i < co_host.size(); i++) {
+        co_host[i].resize(m->inputs[i].nchunks);
+        if (m->inputs[i].nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(co_host[i].data(), m->inputs[i].chunk_offsets, m->inputs[i].nchunks * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    if (!co_host.empty()) B200C_CUDA_TRY(c, cudaStreamSynchronize(cs));
+    auto chunk_off = [&](int i, uint64_t ch) -> uint64_t { const b200c_input& in = m->inputs[i]; return ch >= in.nchunks ? in.data_len : (co_host.empty() ? in.chunk_offsets[ch] : co_host[i][ch]); };
+    auto copy_chunks = [&](int i, uint64_t a, uint64_t b) -> int {      // compressed bytes of chunks [a, b) of input i -> CD
         const b200c_input& in = m->inputs[i];
         if (a >= b) return B200C_OK;
         uint64_t lo = chunk_off(i, a), hi = chunk_off(i, b);

@@ -116,11 +116,19 @@ struct Rd {
     const uint8_t* U; uint64_t p, end; int err;
     __device__ __forceinline__ uint32_t u8() { if (p >= end) { err = PERR_CORRUPT; return 1; } return U[p++]; }
     __device__ __forceinline__ uint32_t be16() { uint32_t a = u8(); return (a << 8) | u8(); }
+    // VIntCoding.readUnsignedVInt (S/utils/vint/VIntCoding.java:66-98), inline: one unaligned 8-byte fetch (every buffer the reader walks has
+    // >= 16 bytes of slack behind it), the 1-byte case — most sizes, flags-like fields and small deltas — leaves after three instructions
     __device__ __forceinline__ uint64_t vint() {
-        uint64_t left = end - p;
-        VintR r = vint_decode(U + p, p < end ? (uint32_t)(left < 9 ? left : 9) : 0u);
-        if (!r.n) { err = PERR_CORRUPT; p = end; return 0; }
-        p += r.n; return r.v;
+        if (p >= end) { err = PERR_CORRUPT; p = end; return 0; }
+        const uint64_t x = load_be64(U + p);
+        const uint32_t first = (uint32_t)(x >> 56);
+        if (first < 0x80) { p++; return first; }
+        const uint32_t extra = __clz((int)(~(first << 24)));                       // leading one bits = extra bytes (8 for 0xFF)
+        if (end - p < 1 + (uint64_t)extra) { err = PERR_CORRUPT; p = end; return 0; }
+        uint64_t v;
+        if (extra == 8) v = (x << 8) | U[p + 8];
+        else v = (x >> (8 * (7 - extra))) & ((1ull << (8 + 7 * extra)) - 1ull);
+        p += 1 + extra; return v;
     }
     __device__ __forceinline__ int32_t vint32() { uint64_t v = vint(); int32_t r = (int32_t)v; if ((int64_t)r != (int64_t)v) err = PERR_CORRUPT; return r; }
     __device__ __forceinline__ void skip(uint64_t n) { if (end - p < n) { err = PERR_CORRUPT; p = end; } else p += n; }
@@ -672,7 +680,12 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
                                   const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen, const int64_t* __restrict__ part_tok,
                                   uint8_t* dout, uint64_t dcap, uint64_t dpos, uint8_t* iout, uint32_t nblocks_final, uint32_t ipay_final, uint32_t ixs_cap,
                                   CUR* cur, DT* open_dt, MCell* merged,
-                                  PartOut& out, PartStats& st, int& err, StatAcc* acc = nullptr) {
+                                  PartOut& out, PartStats& st, int& err, StatAcc* acc = nullptr, uint32_t m_uni = 0) {
+    // m_uni: a bound >= m that is the same for every lane of the warp (0: m itself). Loops over the cursors run to it with the lanes' own
+    // m as a guard inside: lanes of different fan-in then leave those loops together. ptxas reconverges lanes that left a loop at different
+    // trip counts only at the end of the enclosing region, i.e. after the whole partition — the staged kernel, whose warps mix fan-ins, ran
+    // two lanes at a time that way (profiles/r2_k4_staged_divergence.txt).
+    const uint32_t mu = m_uni > m ? m_uni : m;
     Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
@@ -680,7 +693,8 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     if (m > MAXK) { err = PERR_UNSUPPORTED; return; }
     // prologue in three sweeps so that the m dependent chains (contrib -> upos -> Data bytes) overlap instead of serialising:
     // (1) resolve the input partitions, (2) prefetch their first lines, (3) parse the partition headers
-    for (uint32_t v = 0; v < m; v++) {
+    for (uint32_t v = 0; v < mu; v++) {
+        if (v >= m) continue;
         uint64_t e = contrib[c0 + v];
         int src = (int)((e >> 56) & 0x7F); uint64_t g = pbase[src] + (e & 0xFFFFFFFFFFull);
         CUR& c = cur[v]; c.src = (uint8_t)src; c.pos = (decltype(c.pos))xl(src, part_upos[g]); c.end = (decltype(c.end))xl(src, part_upos[g + 1]); c.done = false;
@@ -689,7 +703,8 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
 #ifdef __CUDA_ARCH__
     if (sizeof(cur[0].pos) == 8) for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
 #endif
-    for (uint32_t v = 0; v < m; v++) {
+    for (uint32_t v = 0; v < mu; v++) {
+        if (v >= m) continue;
         CUR& c = cur[v];
         uint64_t pos = c.pos;
         Rd r{P.U, pos, c.end, 0};
@@ -745,38 +760,36 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     const bool multi = m > 1;
     uint64_t has_open = 0; int biggest = -1;
     DT cur_open = dt_live();                       // open deletion in the merged stream
-    for (uint32_t v = 0; v < m; v++) cur_load(P, cur[v], err);
+    for (uint32_t v = 0; v < mu; v++) if (v < m) cur_load(P, cur[v], err);
     while (!err) {
-        int b = -1;
-        for (uint32_t v = 0; v < m; v++) if (!cur[v].done && (b < 0 || cmp_heads(P, cur[v], cur[b]) < 0)) b = (int)v;
+        // smallest head and the heads equal to it in one sweep (MergeIterator: equal items reduce together, in source order)
+        int b = -1; uint64_t grp = 0;
+        for (uint32_t v = 0; v < mu; v++) {
+            if (v >= m || cur[v].done) continue;
+            const int c = b < 0 ? -1 : cmp_heads(P, cur[v], cur[b]);
+            if (c < 0) { b = (int)v; grp = 1ull << v; } else if (c == 0) grp |= 1ull << v;
+        }
         if (b < 0) break;
-        uint64_t grp = 1ull << b; int gcount = 1, last = b;
-        for (uint32_t v = b + 1; v < m; v++) if (!cur[v].done && cmp_heads(P, cur[v], cur[b]) == 0) { grp |= 1ull << v; gcount++; last = (int)v; }
+        const int gcount = __popcll(grp), last = 63 - __clzll((long long)grp);
         if (!(cur[b].flags & 0x02)) {
             DT active = multi ? (dt_is_live(cur_open) ? pdel : cur_open) : dt_live();      // activeDeletion() :191-197
             const bool as_is = !multi || ((gcount == 1) && dt_is_live(active));            // Row.Merger.merge :734-739
             Live info = live_empty(); DT del = dt_live();
             for (int k = 0; k < P.ncols; k++) merged[k].present = false;
-            if (gcount > 1) {
-                for (uint64_t bits = grp; bits; bits &= bits - 1) {
-                    int v = __ffsll((long long)bits) - 1;
-                    Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) err = r.err;
-                    if (live_supersedes(vi, info)) info = vi;
-                    if (dt_supersedes(vd, del)) del = vd;
-                }
+            // one sweep over the versions: row headers and cells together. Cells are reconciled first and the active deletion is applied to
+            // the winners afterwards — the same result as ColumnDataReducer's skip-then-reconcile (:838-849), because Cells.reconcile orders by
+            // timestamp first: a winner the deletion covers means every version was covered, a winner above it beat only lower timestamps.
+            for (uint64_t bits = grp; bits && !err; bits &= bits - 1) {
+                int v = __ffsll((long long)bits) - 1;
+                Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) err = r.err;
+                if (gcount == 1) { info = vi; del = vd; }
+                else { if (live_supersedes(vi, info)) info = vi; if (dt_supersedes(vd, del)) del = vd; }
+                fold_cells(P, cur[v], r, vi, false, active, merged, err);
             }
             if (!as_is) {
                 if (dt_supersedes(del, active)) active = del; else del = dt_live();
                 if (dt_deletes(active, info.ts)) info = live_empty();
-            }
-            for (uint64_t bits = grp; bits && !err; bits &= bits - 1) {
-                int v = __ffsll((long long)bits) - 1;
-                Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd);
-                if (gcount == 1) { if (as_is) { info = vi; del = vd; } else { /* single version under an active deletion */
-                        info = vi; del = vd;
-                        if (dt_supersedes(del, active)) active = del; else del = dt_live();
-                        if (dt_deletes(active, info.ts)) info = live_empty(); } }
-                fold_cells(P, cur[v], r, vi, !as_is, active, merged, err); if (r.err) err = r.err;
+                for (int k = 0; k < P.ncols; k++) if (merged[k].present && dt_deletes(active, merged[k].ts)) merged[k].present = false;
             }
             if (err) break;
             int npresent = 0; for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;

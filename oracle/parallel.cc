@@ -16,6 +16,8 @@
 #include <climits>
 #include <cstring>
 #include <thread>
+#include <mutex>
+#include <malloc.h>
 #include <memory>
 
 namespace oracle {
@@ -176,10 +178,19 @@ static int compact_parallel_impl(const b200c_manifest* m, b200c_result* res, int
 // nranges: token ranges the ring is cut into (>= threads for balance); max_ranges > 0: only the first max_ranges of them (bounded
 // sample: the result is then the compaction of the token range (token_lo, cut[max_ranges]]). times_ms (optional): merge / stitch / compress.
 // *sample_token_hi (optional) = upper token bound of what was compacted (token_hi unless max_ranges cut the ring short).
+// Range tasks allocate and free a few MiB per source and per output piece. With glibc's defaults every such buffer is its own mmap: first-touch
+// page faults for each task and an munmap (TLB shoot-down to every core of the process) when it ends — on the 128-thread GPU host that made 64
+// threads slower than 16. Serving these sizes from the per-thread arenas and never trimming them lets a thread reuse its warm pages.
+static void tune_allocator_once() {
+    static std::once_flag once;
+    std::call_once(once, [] { mallopt(M_MMAP_THRESHOLD, 32 << 20); mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20); });
+}
+
 extern "C" int orc_compact_parallel(const b200c_manifest* m, b200c_result* res, int nthreads, int nranges, int max_ranges, double* times_ms, int64_t* sample_token_hi,
                                     char* errbuf, int errcap) {
     try {
         oracle::ParallelTimes tm{0, 0, 0};
+        tune_allocator_once();
         int rc = oracle::compact_parallel_impl(m, res, nthreads, nranges, max_ranges, &tm, sample_token_hi);
         if (times_ms) { times_ms[0] = tm.merge_ms; times_ms[1] = tm.stitch_ms; times_ms[2] = tm.compress_ms; }
         return rc;

@@ -229,7 +229,7 @@ def oracle_api():
 def cpu_compact(L, m, res, threads, ranges=0, max_ranges=0):
     """one CPU-oracle compaction of manifest m into res. threads > 1 (single-output workloads): token-range parallel oracle.
     Returns (seconds, sample_token_hi, [merge, stitch, compress] ms)."""
-    err = C.create_string_buffer(256); tm = (C.c_double * 3)(); hi = C.c_int64(INT64_MAX)
+    err = C.create_string_buffer(256); tm = (C.c_double * 6)(); hi = C.c_int64(INT64_MAX)
     t0 = time.perf_counter()
     if m.max_sstable_bytes or threads <= 1 and not max_ranges:
         rc = L.orc_compact(C.byref(m), C.byref(res), err, 256)
@@ -237,7 +237,7 @@ def cpu_compact(L, m, res, threads, ranges=0, max_ranges=0):
         rc = L.orc_compact_parallel(C.byref(m), C.byref(res), threads, ranges or max(threads * 8, 16), max_ranges, tm, C.byref(hi), err, 256)
     dt = time.perf_counter() - t0
     if rc != 0: raise RuntimeError("CPU oracle failed rc=%d: %s" % (rc, err.value.decode()))
-    return dt, hi.value, [tm[0], tm[1], tm[2]]
+    return dt, hi.value, [round(tm[k], 1) for k in range(6)]
 
 def host_out_bufs_numpy(nout, cap_d, cap_i, cap_c):
     import numpy as np
@@ -436,7 +436,7 @@ def cpu_leg_and_verify(args, wl, line, tabs, m_host, caps, ctx, L, do, ho, last,
     cb = {"value": round(covered / sec / 1e6, 1), "unit": "MB/s", "cores": thr, "kind": "port",
           "sample": ("the whole workload" if hi == INT64_MAX else "token range (MIN, %d] of the same workload = %.1f %% of its bytes" % (hi, 100.0 * covered / u_in)) +
                     (", one compaction cut into %d token ranges, one oracle thread per range (oracle/parallel.cc)" % ranges if thr > 1 else ", single-threaded oracle (= one reference compaction task)"),
-          "seconds": round(sec, 2), "phase_ms": [round(x, 1) for x in tm], "rows_merged_per_s": round(int(res.total_source_rows) / sec, 0)}
+          "seconds": round(sec, 2), "phase_ms": [round(x, 1) for x in tm[:3]], "range_tasks_ms": {"wall_sum": tm[3], "thread_cpu_sum": tm[4], "longest": tm[5]}, "rows_merged_per_s": round(int(res.total_source_rows) / sec, 0)}
     if thr > 1:                                  # what ONE reference compaction task achieves: a single thread, on a small prefix
         r1, _ = host_out_bufs_numpy(1, cap_d // 16 + (1 << 20), cap_i // 16 + (1 << 20), cap_c // 16 + 1024)
         s1, _, _ = cpu_compact(OL, m_host, r1, 1, ranges, max(1, ranges // 128))
@@ -488,7 +488,7 @@ def run_reference(args, wl):
         thr = threads; max_ranges, _ = estimate_max_ranges(u_in, threads, ranges, args.cpu_budget_s)
     res, files = host_out_bufs_numpy(nout, cap_d, cap_i, cap_c)
     for _ in range(args.warmup): cpu_compact(OL, m, res, thr, ranges, max_ranges)
-    total = 0.0; covered = 0; rows = 0; tms = [0.0, 0.0, 0.0]; hi = INT64_MAX
+    total = 0.0; covered = 0; rows = 0; tms = [0.0] * 6; hi = INT64_MAX
     for _ in range(args.steps):
         sec, hi, tm = cpu_compact(OL, m, res, thr, ranges, max_ranges)
         total += sec; covered += int(res.bytes_in_range); rows += int(res.total_source_rows); tms = [a + b for a, b in zip(tms, tm)]
@@ -507,7 +507,8 @@ def run_reference(args, wl):
     cb = {"value": round(value, 1), "unit": "MB/s", "cores": thr, "kind": "port",
           "sample": ("the whole workload" if hi == INT64_MAX else "token range (MIN, %d] = %.1f %% of the workload's bytes per step" % (hi, 100.0 * covered / args.steps / u_in)) +
                     (", ONE compaction cut into %d token ranges, one oracle thread per range" % ranges if thr > 1 else ", single-threaded oracle"),
-          "phase_ms": [round(x / args.steps, 1) for x in tms], "scaling": curve or None, "host_threads": threads}
+          "phase_ms": [round(x / args.steps, 1) for x in tms[:3]], "range_tasks_ms": {"wall_sum": round(tms[3] / args.steps, 1), "thread_cpu_sum": round(tms[4] / args.steps, 1), "longest": round(tms[5] / args.steps, 1)},
+          "scaling": curve or None, "host_threads": threads}
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"] + ", chunk 16 KiB, schema %s, seed %#x" % (wl["schema"], wl["seed"]), "uncompressed_in_bytes": u_in,

@@ -76,10 +76,12 @@ __global__ void __launch_bounds__(32) k_compress_chunks(const DevTables* __restr
 
 // LZ4 with only the 16 KiB hash table in shared memory: the chunk is read where it lies (L1 read-only path), 13 blocks of one warp per
 // SM instead of 7. Needs a 4-byte aligned stream start and chunk length (every caller's buffers are).
+template <bool DUP>
 __global__ void __launch_bounds__(32) k_compress_chunks_lz4_direct(const DevTables* __restrict__ T,
         const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen,
         uint8_t* __restrict__ slots, int slot_stride, uint32_t* __restrict__ file_len, uint32_t* __restrict__ seg_raw) {
     __shared__ __align__(16) uint16_t s_tab[LZ4_TABLE_ENTRIES];
+    __shared__ uint8_t s_dup[DUP ? LZ4_DUP_ENTRIES : 1];
     const int lane = threadIdx.x;
     const uint64_t chunk = blockIdx.x;
     const uint64_t start = chunk * (uint64_t)chunk_len;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(32) k_compress_chunks_lz4_direct(const DevTabl
     const uint8_t* src = in + start;
     uint8_t* slot = slots + chunk * (uint64_t)slot_stride;
     if (lane == 0) { slot[0] = (uint8_t)ulen; slot[1] = (uint8_t)(ulen >> 8); slot[2] = (uint8_t)(ulen >> 16); slot[3] = (uint8_t)(ulen >> 24); }
-    int clen = 4 + lz4_compress_warp<true>(src, ulen, s_tab, slot + 4, lane);
+    int clen = 4 + lz4_compress_warp<true>(src, ulen, s_tab, slot + 4, lane, DUP ? s_dup : nullptr);
     if (clen >= max_clen) {                            // flushData :158-177 — store raw when compression did not help enough
         for (int i = lane; i < ulen; i += 32) slot[i] = src[i];
         clen = ulen;

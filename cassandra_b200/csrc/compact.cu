@@ -855,7 +855,9 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (!c || !m || !res) return B200C_EINVAL;
     auto t_start = std::chrono::steady_clock::now();
     cudaSetDevice(c->device);
-    c->prog_stage.store(0);
+    c->prog_stage.store(0); c->prog_scanned.store(0);
+    for (int i = 0; i < B200C_MAX_INPUTS; i++) c->prog_input_pos[i].store(0);
+    c->prog_seq.fetch_add(1);              // after the resets: figures read behind a new call_seq belong to this call
     if (m->abi_version != B200C_ABI_VERSION || m->ninputs <= 0) { c->err = "bad manifest"; return B200C_EINVAL; }
     if (m->partitioner != B200C_PARTITIONER_MURMUR3 && m->partitioner != B200C_PARTITIONER_BYTE_ORDERED) { c->err = "partitioner not supported (Murmur3Partitioner and ByteOrderedPartitioner are)"; return B200C_EUNSUPPORTED; }
     if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) { c->err = "ByteOrderedPartitioner: token sub-ranges are not expressible"; return B200C_EUNSUPPORTED; }
@@ -1771,7 +1773,7 @@ int64_t b200c_token(int partitioner, const uint8_t* key, uint32_t len) {
 
 int b200c_poll(b200c_ctx* c, b200c_progress* p) {
     if (!c || !p) return B200C_EINVAL;
-    p->bytes_scanned = c->prog_scanned.load(); p->bytes_total = c->prog_total.load(); p->stage = c->prog_stage.load(); p->_pad = 0;
+    p->call_seq = c->prog_seq.load(); p->bytes_scanned = c->prog_scanned.load(); p->bytes_total = c->prog_total.load(); p->stage = c->prog_stage.load();
     return B200C_OK;
 }
 int b200c_poll_inputs(b200c_ctx* c, uint64_t* positions, int n) {

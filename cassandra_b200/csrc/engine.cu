@@ -56,8 +56,9 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
     uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
     if (!nchunks) return B200C_OK;
     const int k5_mode = []() { const char* e = getenv("B200C_K5"); return e ? atoi(e) : 1; }();      // 1 (default): LZ4 reads the chunk through L1, 13 chunks per SM: 48.0 -> 34.7 ms at 16 x 256 MiB; 0: chunk copy in shared memory (A/B)
-    if (k5_mode == 1 && comp == COMP_LZ4 && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0) {
-        B200C_LAUNCH(c, k_compress_chunks_lz4_direct, (unsigned)nchunks, 32, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
+    if ((k5_mode == 1 || k5_mode == 2) && comp == COMP_LZ4 && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0) {
+        if (k5_mode == 2) B200C_LAUNCH(c, k_compress_chunks_lz4_direct<true>, (unsigned)nchunks, 32, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);   // + distinct-hash fast path (A/B)
+        else B200C_LAUNCH(c, k_compress_chunks_lz4_direct<false>, (unsigned)nchunks, 32, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
         return B200C_OK;
     }
     int tab_bytes = comp == COMP_SNAPPY15 ? 65536 : (comp == COMP_SNAPPY ? 32768 : 16384);

@@ -29,7 +29,7 @@ struct b200c_ctx {
     double last_ms = 0.0;
     std::atomic<int> cancel{0};
     std::atomic<uint64_t> prog_scanned{0}, prog_total{0};
-    std::atomic<int> prog_stage{0};
+    std::atomic<int> prog_stage{0}; std::atomic<int> prog_seq{0};
     std::atomic<int> prog_ninputs{0};
     std::atomic<uint64_t> prog_input_pos[B200C_MAX_INPUTS];   // uncompressed bytes of each input consumed so far (b200c_poll_inputs)
     bool timing = false;

@@ -47,7 +47,10 @@ template <bool GLOBAL> __device__ __forceinline__ uint32_t lz4_rd32(const uint32
 }
 template <bool GLOBAL> __device__ __forceinline__ uint32_t lz4_rd8(const uint8_t* in, int p) { return GLOBAL ? (uint32_t)__ldg(in + p) : (uint32_t)in[p]; }
 
-template <bool GLOBAL> __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, uint8_t* out, int lane) {
+// s_dup (optional, LZ4_DUP_ENTRIES bytes of shared memory, any content): lets a search window prove in five instructions that no two of its
+// attempts share a hash — the usual case — instead of building the same-hash masks with 13 ballots.
+enum { LZ4_DUP_ENTRIES = 2048 };
+template <bool GLOBAL> __device__ int lz4_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, uint8_t* out, int lane, uint8_t* s_dup = nullptr) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     {   // zero the hash table: 16 KiB, 16 bytes per lane per step
         uint4* t4 = (uint4*)s_tab;
@@ -87,8 +90,21 @@ template <bool GLOBAL> __device__ int lz4_compress_warp(const uint8_t* s_in, int
                 // per hash bit, are independent of each other and give the same mask. Invalid lanes form a suffix that neither
                 // `prev` (lower lanes only) nor the masked `later_same` tests below can reach, so they need no special key.
                 uint32_t same = FULL_MASK;
+                bool unique = false;
+                if (s_dup) {
+                    // every valid lane writes its number into the slot of its hash (one of the writers of a slot wins): a lane that reads back
+                    // another number shares the slot, i.e. possibly the hash, with someone; no such lane = all hashes distinct
+                    const uint32_t dh = h & (LZ4_DUP_ENTRIES - 1);
+                    if (valid) s_dup[dh] = (uint8_t)lane;
+                    __syncwarp();
+                    const bool shared = valid && s_dup[dh] != (uint8_t)lane;
+                    unique = !__any_sync(FULL_MASK, shared);
+                }
+                if (unique) same = 1u << lane;
+                else {
 #pragma unroll
-                for (int b = 0; b < LZ4_HASHLOG_U16; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
+                    for (int b = 0; b < LZ4_HASHLOG_U16; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
+                }
                 uint32_t prev = same & lt_mask;
                 int src = prev ? (31 - __clz(prev)) : lane;
                 int pc = __shfl_sync(FULL_MASK, p, src);

@@ -74,7 +74,7 @@ class Result(C.Structure):
                 ("corruption", Corruption), ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_uint64),
                 ("index_slow_path_inputs", C.c_uint64)]
 class Progress(C.Structure):
-    _fields_ = [("bytes_scanned", C.c_uint64), ("bytes_total", C.c_uint64), ("stage", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("bytes_scanned", C.c_uint64), ("bytes_total", C.c_uint64), ("stage", C.c_int32), ("call_seq", C.c_int32)]
 
 # every symbol include/b200c.h declares: (restype, argtypes)
 _vp, _u64, _i, _u8p = C.c_void_p, C.c_uint64, C.c_int, C.c_void_p

@@ -309,7 +309,9 @@ int          b200c_compact(b200c_ctx*, const b200c_manifest*, b200c_result*, int
  * pick token-range splitters from Summary.db sample keys (one compaction sharded over several GPUs: token_lo / token_hi per shard). */
 int64_t      b200c_token(int partitioner, const uint8_t* key, uint32_t len);
 
-typedef struct b200c_progress { uint64_t bytes_scanned; uint64_t bytes_total; int32_t stage; int32_t _pad; } b200c_progress;
+/* call_seq: number of b200c_compact calls this context has started; it changes after the counters were reset for the new call, so a poller that
+   remembers it can tell the running call's figures from the final state of the previous one */
+typedef struct b200c_progress { uint64_t bytes_scanned; uint64_t bytes_total; int32_t stage; int32_t call_seq; } b200c_progress;
 int          b200c_poll(b200c_ctx*, b200c_progress*);   /* callable from another thread */
 /* ISSTableScanner.getCurrentPosition per input (S/io/sstable/ISSTableScanner.java:34-41, consumed by CompactionIterator.java:289-295):
  * positions[i] = uncompressed Data.db bytes of input i the merge has consumed so far (it advances token range by token range).

@@ -16,6 +16,7 @@
 #include <climits>
 #include <cstring>
 #include <thread>
+#include <ctime>
 #include <mutex>
 #include <malloc.h>
 #include <memory>
@@ -73,7 +74,7 @@ template <typename F> static void parallel_for(int nthreads, uint64_t n, F f) {
     for (auto& x : th) x.join();
 }
 
-struct ParallelTimes { double merge_ms, stitch_ms, compress_ms; };
+struct ParallelTimes { double merge_ms, stitch_ms, compress_ms; double task_wall_ms, task_cpu_ms, task_max_ms; };      // task_*: summed over the range tasks of the merge phase
 
 static int compact_parallel_impl(const b200c_manifest* m, b200c_result* res, int nthreads, int nranges, int max_ranges, ParallelTimes* tm, int64_t* sample_hi) {
     auto t0 = std::chrono::steady_clock::now();
@@ -87,13 +88,18 @@ static int compact_parallel_impl(const b200c_manifest* m, b200c_result* res, int
     if (sample_hi) *sample_hi = T[R];
     std::vector<RangeOut> ro(R); std::vector<b200c_result> rr(R);
     std::vector<int> rc(R, B200C_OK); std::vector<Corrupt> cerr(R); std::vector<std::string> uerr(R);
+    std::vector<double> twall(R, 0), tcpu(R, 0);
+    auto thread_cpu_ms = []() { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     parallel_for(nthreads, (uint64_t)R, [&](uint64_t r) {
+        auto w0 = std::chrono::steady_clock::now(); const double c0 = thread_cpu_ms();
         b200c_manifest mm = *m; mm.token_lo = T[r]; mm.token_hi = T[r + 1];
         memset(&rr[r], 0, sizeof(b200c_result)); rr[r].noutputs_cap = 1; rr[r].outputs = res->outputs;   // (outputs untouched in raw mode)
         try { rc[r] = compact_impl(&mm, &rr[r], &ro[r]); }
         catch (Corrupt& c) { rc[r] = B200C_ECORRUPT; cerr[r] = c; }
         catch (Unsupported& u) { rc[r] = B200C_EUNSUPPORTED; uerr[r] = u.what; }
+        twall[r] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); tcpu[r] = thread_cpu_ms() - c0;
     });
+    if (tm) { tm->task_wall_ms = tm->task_cpu_ms = tm->task_max_ms = 0; for (int r = 0; r < R; r++) { tm->task_wall_ms += twall[r]; tm->task_cpu_ms += tcpu[r]; tm->task_max_ms = std::max(tm->task_max_ms, twall[r]); } }
     for (int r = 0; r < R; r++) {
         if (rc[r] == B200C_ECORRUPT) throw cerr[r];
         if (rc[r] == B200C_EUNSUPPORTED) throw Unsupported{uerr[r]};
@@ -176,7 +182,7 @@ static int compact_parallel_impl(const b200c_manifest* m, b200c_result* res, int
 } // namespace oracle
 
 // nranges: token ranges the ring is cut into (>= threads for balance); max_ranges > 0: only the first max_ranges of them (bounded
-// sample: the result is then the compaction of the token range (token_lo, cut[max_ranges]]). times_ms (optional): merge / stitch / compress.
+// sample: the result is then the compaction of the token range (token_lo, cut[max_ranges]]). times_ms (optional, 6 doubles): merge / stitch / compress phase, then the range tasks' summed wall time, summed thread CPU time and the longest task.
 // *sample_token_hi (optional) = upper token bound of what was compacted (token_hi unless max_ranges cut the ring short).
 // Range tasks allocate and free a few MiB per source and per output piece. With glibc's defaults every such buffer is its own mmap: first-touch
 // page faults for each task and an munmap (TLB shoot-down to every core of the process) when it ends — on the 128-thread GPU host that made 64
@@ -189,10 +195,10 @@ static void tune_allocator_once() {
 extern "C" int orc_compact_parallel(const b200c_manifest* m, b200c_result* res, int nthreads, int nranges, int max_ranges, double* times_ms, int64_t* sample_token_hi,
                                     char* errbuf, int errcap) {
     try {
-        oracle::ParallelTimes tm{0, 0, 0};
+        oracle::ParallelTimes tm{0, 0, 0, 0, 0, 0};
         tune_allocator_once();
         int rc = oracle::compact_parallel_impl(m, res, nthreads, nranges, max_ranges, &tm, sample_token_hi);
-        if (times_ms) { times_ms[0] = tm.merge_ms; times_ms[1] = tm.stitch_ms; times_ms[2] = tm.compress_ms; }
+        if (times_ms) { times_ms[0] = tm.merge_ms; times_ms[1] = tm.stitch_ms; times_ms[2] = tm.compress_ms; times_ms[3] = tm.task_wall_ms; times_ms[4] = tm.task_cpu_ms; times_ms[5] = tm.task_max_ms; }
         return rc;
     }
     catch (oracle::Unsupported& u) { if (errbuf) snprintf(errbuf, errcap, "unsupported: %s", u.what.c_str()); return B200C_EUNSUPPORTED; }

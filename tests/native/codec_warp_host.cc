@@ -25,16 +25,19 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 
 using namespace b200c;
 
-// mode 0: LZ4, chunk copy in "shared memory"; 1: LZ4 reading the chunk in place (the L1 variant); 2 / 3: Snappy with max_bits 14 / 15
+// mode 0: LZ4, chunk copy in "shared memory"; 1: LZ4 reading the chunk in place (the L1 variant); 2 / 3: Snappy with max_bits 14 / 15;
+// 4: LZ4 in place with the distinct-hash fast path
 extern "C" int warp_compress(int mode, const uint8_t* in, int n, uint8_t* out) {
     std::vector<uint8_t> s_in((size_t)n + 64, 0); memcpy(s_in.data(), in, n);
     std::vector<uint16_t> tab(1 << 15, 0xDEAD);                       // the kernels zero what they use
+    std::vector<uint8_t> dup(LZ4_DUP_ENTRIES, 0xEE);
     int result = -1;
     // 4-byte aligned base as the kernel guarantees
     warp_emu::run([&](int lane) {
         int r;
         if (mode == 0) r = lz4_compress_warp<false>(s_in.data(), n, tab.data(), out, lane);
         else if (mode == 1) r = lz4_compress_warp<true>(s_in.data(), n, tab.data(), out, lane);
+        else if (mode == 4) r = lz4_compress_warp<true>(s_in.data(), n, tab.data(), out, lane, dup.data());
         else r = snappy_compress_warp(s_in.data(), n, tab.data(), mode == 3 ? 15 : 14, out, lane);
         if (lane == 0) result = r;
     });

@@ -33,7 +33,7 @@ def corpus():
     extra = [b"".join(rng.choice(words) for _ in range(3000))[:16384], bytes(16384), bytes(rng.getrandbits(8) for _ in range(5000)), b"ab" * 4000, b"x" * 13, b"y" * 12, b"0123456789abcdef" * 700]
     return list(_corpus(random.Random(7)))[:12] + extra
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 4])
 def test_lz4_warp_source_equals_the_oracle(warp, mode):
     for k, d in enumerate(corpus()):
         d = d[:16384]

@@ -503,15 +503,15 @@ def test_poll_while_running(ctx):
             p = native.Progress(); pos = (C.c_uint64 * 64)()
             while not done.is_set():
                 L.b200c_poll(ctx.handle, C.byref(p)); k = L.b200c_poll_inputs(ctx.handle, pos, 64)
-                seen.append((p.bytes_scanned, p.bytes_total, p.stage, tuple(pos[i] for i in range(k))))
+                seen.append((p.bytes_scanned, p.bytes_total, p.stage, tuple(pos[i] for i in range(k)), p.call_seq))
                 time.sleep(0.001)
+        p0 = native.Progress(); L.b200c_poll(ctx.handle, C.byref(p0))
         th = threading.Thread(target=poller); th.start()
         task.execute(GpuEngine(ctx)); done.set(); th.join()
     finally:
         del os.environ["B200C_RANGES"]
     total = sum(t.compression.data_length for t in tabs)
-    first_live = next(k for k, s in enumerate(seen) if s[1] == total and s[2] < 6)      # (samples before the call still show the previous, finished call)
-    run = [s for s in seen[first_live:] if s[1] == total]
+    run = [s for s in seen if s[4] == p0.call_seq + 1 and s[1] == total]               # (samples before the call still show the previous call: other call_seq)
     assert len(run) >= 3
     assert all(a[0] <= b[0] for a, b in zip(run, run[1:]))
     assert len({s[2] for s in run}) >= 2                       # saw more than one stage

@@ -19,7 +19,7 @@ def run_parallel(task, threads, ranges, max_ranges=0):
     res.noutputs_cap = 1; res.outputs = outs
     L = O.lib(); L.orc_compact_parallel.restype = C.c_int
     L.orc_compact_parallel.argtypes = [C.POINTER(native.Manifest), C.POINTER(native.Result), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_char_p, C.c_int]
-    err = C.create_string_buffer(256); tm = (C.c_double * 3)(); hi = C.c_int64()
+    err = C.create_string_buffer(256); tm = (C.c_double * 6)(); hi = C.c_int64()
     rc = L.orc_compact_parallel(C.byref(m), C.byref(res), threads, ranges, max_ranges, tm, C.byref(hi), err, 256)
     assert rc == 0, err.value
     return (bytes(d[:o.data_len]), bytes(ix[:o.index_len]), [int(x) for x in co[:o.nchunks]], int(o.digest), int(o.partitions), int(o.rows),

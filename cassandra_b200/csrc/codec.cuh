@@ -108,6 +108,38 @@ __global__ void __launch_bounds__(32) k_compress_chunks_lz4_direct(const DevTabl
     }
 }
 
+// Snappy the same way: only the hash table (32 KiB for 16 KiB chunks, 64 KiB for the 15-bit generation) in shared memory, 6 chunks per SM
+// instead of 4. dynamic smem = tab_bytes.
+__global__ void __launch_bounds__(32) k_compress_chunks_snappy_direct(const DevTables* __restrict__ T, int max_bits,
+        const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen,
+        uint8_t* __restrict__ slots, int slot_stride, uint32_t* __restrict__ file_len, uint32_t* __restrict__ seg_raw) {
+    extern __shared__ __align__(16) uint8_t smem_tab[];
+    uint16_t* s_tab = (uint16_t*)smem_tab;
+    const int lane = threadIdx.x;
+    const uint64_t chunk = blockIdx.x;
+    const uint64_t start = chunk * (uint64_t)chunk_len;
+    const int ulen = (int)min((uint64_t)chunk_len, n - start);
+    const uint8_t* src = in + start;
+    uint8_t* slot = slots + chunk * (uint64_t)slot_stride;
+    int clen = snappy_compress_warp<true>(src, ulen, s_tab, max_bits, slot, lane);
+    if (clen >= max_clen) {
+        for (int i = lane; i < ulen; i += 32) slot[i] = src[i];
+        clen = ulen;
+        if (ulen < max_clen) { for (int i = ulen + lane; i < max_clen; i += 32) slot[i] = 0; clen = max_clen; }
+    }
+    __syncwarp();
+    __threadfence_block();
+    uint32_t raw = warp_crc32_raw(T, T->crc_adv128, slot, clen, lane);
+    uint32_t init = gf2_mulmod(0xFFFFFFFFu, warp_xpow8n(T, (uint32_t)clen, lane));
+    uint32_t crc = ~(raw ^ init);
+    if (lane == 0) {
+        slot[clen] = (uint8_t)(crc >> 24); slot[clen + 1] = (uint8_t)(crc >> 16); slot[clen + 2] = (uint8_t)(crc >> 8); slot[clen + 3] = (uint8_t)crc;
+        file_len[chunk] = (uint32_t)clen + 4;
+        uint32_t x = raw ^ __byte_perm(crc, 0, 0x0123);
+        seg_raw[chunk] = T->crc_t[3][x & 0xff] ^ T->crc_t[2][(x >> 8) & 0xff] ^ T->crc_t[1][(x >> 16) & 0xff] ^ T->crc_t[0][x >> 24];
+    }
+}
+
 // ---- pack: slots -> dense Data.db image --------------------------------------------------------------------------
 // one warp per chunk; offs = exclusive scan of file_len
 // out_base (optional): device scalar subtracted from the offsets, for an image buffer that holds only a window of the file

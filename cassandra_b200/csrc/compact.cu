@@ -530,7 +530,8 @@ __global__ void __launch_bounds__(256) k_fanin_scatter(const uint64_t* __restric
     if (valid) list[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)j;
 }
 
-enum { SLOT_BYTES = sizeof(Cur), K4_SMEM_COLS = 8 };          // per-source cursor in shared memory
+typedef Cur32 K4Cur;                                           // cursor of the thread-per-partition kernels (partition.cuh)
+enum { SLOT_BYTES = sizeof(K4Cur), K4_SMEM_COLS = 8 };        // per-source cursor in shared memory
 
 // mode 0: size pass only (EMIT = false). mode 1: the single serialisation pass — bytes go to scratch at dbase + doff[j] (capacity
 // dcapv[j]), sizes/stats are recorded, no Index.db. mode 2: final emit of every written partition at dbase + dpos[j] with its Index.db
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     // so that consecutive threads start in different banks. Wider tables keep the merged row in local memory.
     const int ncols_s = a.P->mcols <= K4_SMEM_COLS ? a.P->mcols : 0;
     const int stride = M_CAP * SLOT_BYTES + ncols_s * (int)sizeof(MCell) + 8;
-    Cur* cur = (Cur*)(s_raw + (size_t)threadIdx.x * stride);
+    K4Cur* cur = (K4Cur*)(s_raw + (size_t)threadIdx.x * stride);
     MCell merged_local[MAXCOLS];
     MCell* merged = ncols_s ? (MCell*)(cur + M_CAP) : merged_local;
     DT open_dt[M_CAP];                                   // only touched when the partition holds range tombstone markers
@@ -941,6 +942,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
     }
     ubase[K] = uo; ibase[K] = io; cbase[K] = co; obase[K] = oo; bbase[K] = bo;
+    if (uo >= (1ull << 40)) { c->err = "decompressed inputs of 1 TiB or more per call"; return B200C_EUNSUPPORTED; }      // stream offsets are 40-bit in the K4 cursors
     const uint64_t nblocks = bo;
     hp.ninputs = K; hp.nclust = m->nclustering; hp.ncols = m->ncolumns; hp.column_index_size = m->column_index_size > 0 ? m->column_index_size : 65536;
     for (int k = 0; k < m->nclustering; k++) { hp.ctype[k] = m->clustering[k].type; hp.cfix[k] = m->clustering[k].fixed_len; }
@@ -1552,7 +1554,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         ubase_total += ulen_out; ilen_total += ilen_out;
     }
-    c->prog_scanned.store(bytes_read * 3 / 4);
+    // (progress: the last piece left bytes_scanned at (4 nr - 1) / (4 nr) of the input; the wrap-up below takes it to the total)
 
     // ---- K5 wrap-up / remaining writers ------------------------------------------------------------------------------------------------
     int rc = B200C_OK;
@@ -1693,10 +1695,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_TRY(ws_typed(c, WS_DOUT, file_bound + 64, &d_dout));
         res->required_data_cap = res->required_index_cap = res->required_chunk_cap = 0;
         uint64_t jlo = 0, start_b = 0; int f = 0;
+        // how much of the stream to compress before looking for the file boundary: the file holds max_sstable_bytes of COMPRESSED chunks, so the
+        // window is that divided by the ratio seen so far (the inputs' own ratio for the first file, then the previous file's) plus 8 %; a window
+        // that turns out too short is extended below (doubling), nothing is compressed twice
+        double est_ratio = 0.5;
+        { uint64_t ci = 0, ui = 0; for (int i = 0; i < K; i++) { ci += m->inputs[i].data_len; ui += m->inputs[i].data_length; } if (ui) est_ratio = std::min(1.0, std::max(0.05, (double)ci / (double)ui)); }
         while (jlo < nparts && start_b < ulen_out) {
             B200C_TRY(check_cancel());
             const uint64_t remaining = ulen_out - start_b, rem_chunks = (remaining + L - 1) / L;
-            uint64_t want = std::max<uint64_t>(64, 2 * m->max_sstable_bytes / L + 8), done = 0, jhi = nparts, status = 2;
+            uint64_t want = std::max<uint64_t>(64, (uint64_t)((double)m->max_sstable_bytes / est_ratio * 1.08) / L + 8), done = 0, jhi = nparts, status = 2;
             while (status == 2) {
                 uint64_t W = std::min(rem_chunks, want);
                 if (W > done) B200C_TRY(compress_slots_device(c, comp, UOUT + start_b + done * L, std::min(remaining - done * L, (W - done) * (uint64_t)L), (int)L,
@@ -1736,6 +1743,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_fstats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
             const uint64_t filen = h[0]; RunStats fs; memcpy(&fs, h + 8, sizeof(fs));
+            if (flen && out_len) est_ratio = std::min(1.0, std::max(0.05, (double)out_len / (double)flen));
             res->required_data_cap = std::max<uint64_t>(res->required_data_cap, out_len);
             res->required_index_cap = std::max<uint64_t>(res->required_index_cap, filen);
             res->required_chunk_cap = std::max<uint64_t>(res->required_chunk_cap, fchunks);

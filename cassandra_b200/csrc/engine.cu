@@ -62,6 +62,12 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
         return B200C_OK;
     }
     int tab_bytes = comp == COMP_SNAPPY15 ? 65536 : (comp == COMP_SNAPPY ? 32768 : 16384);
+    if (k5_mode != 0 && comp_is_snappy(comp) && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0 && chunk_len <= 65536) {
+        // the table a chunk of this length needs (snappy_compress_warp: next power of two >= chunk length, capped by the generation's maximum)
+        int need = 512; while (need < 2 * chunk_len && need < tab_bytes) need <<= 1;
+        B200C_LAUNCH(c, k_compress_chunks_snappy_direct, (unsigned)nchunks, 32, (size_t)need, c->d_tables, comp == COMP_SNAPPY15 ? 15 : 14, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
+        return B200C_OK;
+    }
     size_t smem = (size_t)tab_bytes + chunk_len + 16;
     B200C_LAUNCH(c, k_compress_chunks, (unsigned)nchunks, 32, smem, c->d_tables, comp, tab_bytes, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);
     return B200C_OK;
@@ -243,6 +249,7 @@ b200c_ctx* b200c_create(int device, size_t workspace_bytes) {
     c->h_pinned_cap = 1 << 16;
     if (cudaMallocHost(&c->h_pinned, c->h_pinned_cap) != cudaSuccess) { cudaFree(c->d_tables); delete c; return nullptr; }
     cudaFuncSetAttribute(k_compress_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 65536 + 16);
+    cudaFuncSetAttribute(k_compress_chunks_snappy_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     (void)workspace_bytes;
     return c;
 }

@@ -166,8 +166,22 @@ template <typename OFF, typename REL, int PAD = 0> struct CurT : CurPad<PAD> {
     uint8_t flags, ext, kind, n, src; bool done;
     uint8_t fast;                  // 0: no prefix key; 1: k0 orders unequal prefixes, ties need cmp_clust; 2: k0 is the whole clustering
     typedef REL rel_t;
+    __host__ __device__ static constexpr uint64_t rel_max() { return (uint64_t)(REL)~(REL)0; }
 };
 typedef CurT<uint64_t, uint32_t> Cur;
+// The same cursor in 32 bytes, for the thread-per-partition kernels whose residency is set by shared memory (16 cursors per thread): stream
+// offsets in 40 bits (the engine refuses inputs whose decompressed streams add up to 2^40 bytes), header-relative offsets in 20 bits (a
+// clustering prefix is at most 8 values of < 64 KiB each), the small fields in what is left. Bit-fields keep the field syntax, so the
+// code above and below is the same for every cursor type; the extra shifts and masks ride in issue slots this latency-bound kernel leaves idle.
+struct Cur32 {
+    uint64_t k0;
+    uint64_t pos : 40, ckend_rel : 20, n : 4;
+    uint64_t next : 40, body_rel : 20, kind : 3, done : 1;
+    uint64_t end : 40, flags : 8, src : 6, ck_rel : 3, ext : 2, fast : 2;
+    typedef uint32_t rel_t;
+    __host__ __device__ static constexpr uint64_t rel_max() { return (1ull << 20) - 1; }
+};
+static_assert(sizeof(Cur32) == 32, "packed cursor layout");
 // 40-byte stride: 32-byte cursors of different threads would all start in one of four bank groups (8-way conflicts on every field)
 typedef CurT<uint32_t, uint16_t, 8> CurS;
 static_assert(sizeof(Cur) == 48 && sizeof(CurS) == 40, "cursor layouts");
@@ -182,10 +196,11 @@ template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P,
         if (flags & 0x01) { c.done = true; c.next = r.p; return 0; }
         c.flags = (uint8_t)flags; c.ext = 0;
         if (flags & 0x02) {
-            c.kind = (uint8_t)r.u8(); c.n = (uint8_t)r.be16();
-            if (c.kind > 7 || c.kind == K_STATIC || c.kind == K_CLUSTERING || c.n > P.nclust) { c.done = true; return PERR_CORRUPT; }
+            const uint32_t kind = r.u8(), nv = r.be16();           // (checked before they go into the cursor: its fields may be narrower)
+            if (kind > 7 || kind == K_STATIC || kind == K_CLUSTERING || nv > (uint32_t)P.nclust) { c.done = true; return PERR_CORRUPT; }
+            c.kind = (uint8_t)kind; c.n = (uint8_t)nv;
         } else {
-            if (flags & 0x80) c.ext = (uint8_t)r.u8();
+            if (flags & 0x80) c.ext = (uint8_t)(r.u8() & 0x03);
             if (c.ext & 0x01) { c.done = true; return PERR_CORRUPT; }       // a static row among the clustered ones (UnfilteredSerializer.deserialize :477-479)
             if ((c.ext & 0x02) || (flags & 0x40)) { c.done = true; return PERR_UNSUPPORTED; }
             c.kind = K_CLUSTERING; c.n = (uint8_t)P.nclust;
@@ -216,7 +231,7 @@ template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P,
         r.vint();                                   // previous unfiltered size
         c.body_rel = (typename CUR::rel_t)(r.p - c.pos);
         const uint64_t nx = after + sz;                  // (64-bit: a damaged size must not wrap a narrow cursor)
-        if (r.err || nx > c.end || nx < r.p || r.p - c.pos > (uint64_t)(typename CUR::rel_t)~0ull) { c.done = true; return PERR_CORRUPT; }
+        if (r.err || nx > c.end || nx < r.p || r.p - c.pos > CUR::rel_max()) { c.done = true; return PERR_CORRUPT; }
         c.next = (decltype(c.next))nx;
         if (!(flags & 0x02) && !(flags & 0x14)) {   // maybe an empty row: no liveness, no deletion — any cells?
             int ncin = P.in[c.src].ncols; bool any;
@@ -237,7 +252,7 @@ template <class CUR> __device__ __noinline__ int static_load(const CParams& P, C
     uint32_t flags = r.u8(), ext = r.u8();
     if (r.err || (flags & 0x03) || !(flags & 0x80) || !(ext & 0x01)) return PERR_CORRUPT;
     if ((ext & 0x02) || (flags & 0x40)) return PERR_UNSUPPORTED;
-    c.flags = (uint8_t)flags; c.ext = (uint8_t)ext; c.kind = K_STATIC; c.n = 0; c.ck_rel = 2; c.ckend_rel = 2; c.fast = 0;
+    c.flags = (uint8_t)flags; c.ext = (uint8_t)(ext & 0x03); c.kind = K_STATIC; c.n = 0; c.ck_rel = 2; c.ckend_rel = 2; c.fast = 0;
     uint64_t sz = r.vint();
     uint64_t after = r.p;
     r.vint();                                       // previous unfiltered size (0)
@@ -701,7 +716,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
         c.k0 = part_kp[g]; c.ckend_rel = part_klen[g];           // what Index.db said about this partition's key (checked below)
     }
 #ifdef __CUDA_ARCH__
-    if (sizeof(cur[0].pos) == 8) for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
+    if (sizeof(typename CUR::rel_t) == 4) for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
 #endif
     for (uint32_t v = 0; v < mu; v++) {
         if (v >= m) continue;
@@ -796,13 +811,13 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
             if (!(live_is_empty(info) && dt_is_live(del) && npresent == 0)) {
                 st.merged_unfiltereds++;
                 CUR& f = cur[b];
-                CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), K_CLUSTERING, f.n};
+                CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), K_CLUSTERING, (uint8_t)f.n};
                 int present = purge_row(pg, info, del, merged, P.ncols);
                 if (present >= 0) { if (!w.started) pw_start(w, P, key_off, klen, out_pdel); write_row(w, P, ck, info, del, merged, present); }
             }
         } else {
             CUR& f = cur[last];                                       // `bound` = clustering of the last marker added (:99-103)
-            CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), f.kind, f.n};
+            CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), (uint8_t)f.kind, (uint8_t)f.n};
             DT mc = dt_live(), mo = dt_live(); bool emit = false;
             if (!multi) { read_marker_dts(P, f, mc, mo, err); emit = true; }
             else {

@@ -4,6 +4,7 @@
 // tests/golden/snappy), the 1.1.x generation (max_bits = 14) differing only in kMaxHashTableBits.
 #pragma once
 #include "common.cuh"
+#include "lz4.cuh"          // lz4_rd32 / lz4_rd8: chunk bytes from a shared-memory copy or, GLOBAL, through the read-only L1 path
 
 namespace b200c {
 
@@ -41,7 +42,7 @@ __device__ __forceinline__ int snappy_emit_copy(uint8_t* out, int op, int offset
 }
 
 // EmitLiteral, warp wide: tag (+ length bytes) by lane 0, the bytes 32 per step. Returns the new output position (warp-uniform).
-__device__ __forceinline__ int snappy_emit_literal_warp(uint8_t* out, int op, const uint8_t* lit, int len, int lane) {
+template <bool GLOBAL = false> __device__ __forceinline__ int snappy_emit_literal_warp(uint8_t* out, int op, const uint8_t* lit, int len, int lane) {
     const int n = len - 1;
     int hdr = 1;
     if (n < 60) { if (lane == 0) out[op] = (uint8_t)(n << 2); }
@@ -49,7 +50,7 @@ __device__ __forceinline__ int snappy_emit_literal_warp(uint8_t* out, int op, co
         const int count = ((31 - __clz(n)) >> 3) + 1; hdr = 1 + count;
         if (lane == 0) { out[op] = (uint8_t)((59 + count) << 2); for (int i = 0; i < count; i++) out[op + 1 + i] = (uint8_t)(n >> (8 * i)); }
     }
-    for (int i = lane; i < len; i += 32) out[op + hdr + i] = lit[i];
+    for (int i = lane; i < len; i += 32) out[op + hdr + i] = (uint8_t)lz4_rd8<GLOBAL>(lit, i);
     return op + hdr + len;
 }
 // EmitCopy: 64-byte copies while len >= 68 (3 bytes each, one per lane), then one or two short ones by lane 0
@@ -73,7 +74,7 @@ __device__ __forceinline__ int snappy_emit_copy_warp(uint8_t* out, int op, int o
 // Attempt k of a search looks at q_k with q_0 = start, q_(k+1) = q_k + (skip_k >> 5), skip_(k+1) = skip_k + (skip_k >> 5), skip_0 = 32; the first 16
 // attempts are unconditional when at least 16 bytes remain before ip_limit (the library's unrolled prologue), every other attempt ends the
 // fragment when its successor would pass ip_limit.
-__device__ int snappy_compress_fragment_warp(const uint8_t* s_in, int base, int input_size, uint16_t* s_tab, int table_size, int max_bits, uint8_t* out, int op, int lane) {
+template <bool GLOBAL = false> __device__ int snappy_compress_fragment_warp(const uint8_t* s_in, int base, int input_size, uint16_t* s_tab, int table_size, int max_bits, uint8_t* out, int op, int lane) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     const uint32_t tmask = (uint32_t)table_size - 1;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -98,7 +99,7 @@ __device__ int snappy_compress_fragment_warp(const uint8_t* s_in, int base, int 
                     const uint32_t st = sk >> 5; qn = q + (int)st; skn = sk + st;
                     valid = (unrolled && a0 + l < 16) || qn <= ip_limit;
                 }
-                const uint32_t dword = valid ? rd32_at(in32, q) : 0u;
+                const uint32_t dword = valid ? lz4_rd32<GLOBAL>(in32, q) : 0u;
                 const uint32_t h = snappy_tidx(dword, tmask, max_bits);
                 int cand = valid ? base + (int)s_tab[h] : 0;
                 uint32_t same = FULL_MASK;
@@ -107,7 +108,7 @@ __device__ int snappy_compress_fragment_warp(const uint8_t* s_in, int base, int 
                 const int src = prev ? (31 - __clz(prev)) : lane;
                 const int pq = __shfl_sync(FULL_MASK, q, src);
                 if (prev) cand = pq;
-                const bool hit = valid && !putonly && rd32_at(in32, cand) == dword;
+                const bool hit = valid && !putonly && lz4_rd32<GLOBAL>(in32, cand) == dword;
                 const uint32_t hits = __ballot_sync(FULL_MASK, hit);
                 const uint32_t inval = __ballot_sync(FULL_MASK, !valid);
                 const int first_hit = hits ? (__ffs(hits) - 1) : 32;
@@ -130,12 +131,12 @@ __device__ int snappy_compress_fragment_warp(const uint8_t* s_in, int base, int 
             if (ended) { ip = next_emit; break; }
             __syncwarp();
             ip = hit_ip;
-            if (!immediate) op = snappy_emit_literal_warp(out, op, s_in + next_emit, ip - next_emit, lane);
+            if (!immediate) op = snappy_emit_literal_warp<GLOBAL>(out, op, s_in + next_emit, ip - next_emit, lane);
             // FindMatchLength(candidate + 4, ip + 4, ip_end): 32 bytes per step
             int matched = 4;
             for (;;) {
                 const int i = matched + lane;
-                const bool eq = (ip + i < ip_end) && (s_in[candidate + i] == s_in[ip + i]);
+                const bool eq = (ip + i < ip_end) && (lz4_rd8<GLOBAL>(s_in, candidate + i) == lz4_rd8<GLOBAL>(s_in, ip + i));
                 const uint32_t b = __ballot_sync(FULL_MASK, eq);
                 if (b == FULL_MASK) { matched += 32; continue; }
                 matched += __ffs(~b) - 1;
@@ -147,12 +148,13 @@ __device__ int snappy_compress_fragment_warp(const uint8_t* s_in, int base, int 
             have_prefix = true;
         }
     }
-    if (ip < ip_end) op = snappy_emit_literal_warp(out, op, s_in + ip, ip_end - ip, lane);
+    if (ip < ip_end) op = snappy_emit_literal_warp<GLOBAL>(out, op, s_in + ip, ip_end - ip, lane);
     return op;
 }
 
 // s_tab: (1 << max_bits) x u16. Returns compressed size (warp-uniform).
-__device__ int snappy_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, int max_bits, uint8_t* out, int lane) {
+// GLOBAL: s_in is the chunk where it lies in global memory (4-byte aligned, >= 8 readable bytes behind it), see lz4_compress_warp
+template <bool GLOBAL = false> __device__ int snappy_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab, int max_bits, uint8_t* out, int lane) {
     int op = 0;
     {   uint32_t v = (uint32_t)n; uint8_t pre[5]; int k = 0;
         while (v >= 0x80) { pre[k++] = (uint8_t)(v | 0x80); v >>= 7; } pre[k++] = (uint8_t)v;
@@ -163,7 +165,7 @@ __device__ int snappy_compress_warp(const uint8_t* s_in, int n, uint16_t* s_tab,
         int table_size = frag > (1 << max_bits) ? (1 << max_bits) : (frag < 256 ? 256 : (2 << (31 - __clz(frag - 1))));
         for (int i = lane; i < table_size / 2; i += 32) ((uint32_t*)s_tab)[i] = 0;
         __syncwarp();
-        op = snappy_compress_fragment_warp(s_in, pos, frag, s_tab, table_size, max_bits, out, op, lane);
+        op = snappy_compress_fragment_warp<GLOBAL>(s_in, pos, frag, s_tab, table_size, max_bits, out, op, lane);
         __syncwarp();
     }
     return op;

@@ -118,10 +118,12 @@ struct Source {
     // chunks on demand too, S/io/util/CompressedChunkReader.java:103-173), so a token sub-range only pays for the chunks it crosses
     // A token sub-range allocates only the span of the stream it can touch (span0 .. span0 + span bytes, chunk aligned): thousands of range
     // tasks each mapping a whole-file buffer would serialise on the kernel's address-space lock.
-    std::unique_ptr<uint8_t[]> buf; uint64_t dlen = 0, span0 = 0, span1 = 0;
+    // The buffer comes from a per-thread pool that only grows (one slot per input): the range tasks of the parallel driver (parallel.cc) would
+    // otherwise mmap / munmap a few MiB per input and task, and on a 128-thread host those address-space operations serialise all the threads.
+    uint8_t* buf = nullptr; uint64_t dlen = 0, span0 = 0, span1 = 0;
     std::vector<bool> have_chunk;
-    const uint8_t* dptr() const { return buf.get() - span0; }       // biased: dptr() + stream offset, valid for offsets in [span0, span1)
-    uint8_t* wptr() { return buf.get() - span0; }
+    const uint8_t* dptr() const { return buf - span0; }       // biased: dptr() + stream offset, valid for offsets in [span0, span1)
+    uint8_t* wptr() { return buf - span0; }
     uint64_t dsize() const { return dlen; }
     void need(uint64_t lo, uint64_t hi);      // make bytes [lo, hi) of the stream available
     uint64_t pos = 0;               // cursor: start of the current partition
@@ -330,8 +332,15 @@ static void open_source(Source& src, int64_t tok_lo, int64_t tok_hi) {
     }
     src.span0 = lo / L * L; src.span1 = std::min<uint64_t>(in.data_length, (hi + L - 1) / L * L);
     if (src.span1 < src.span0) src.span1 = src.span0;
-    src.buf.reset(new uint8_t[src.span1 - src.span0 + 64]);               // uninitialised on purpose: nothing is read before its chunk was decoded
-    memset(src.buf.get() + (src.span1 - src.span0), 0, 64);
+    {
+        struct Slot { std::unique_ptr<uint8_t[]> p; uint64_t cap = 0; };
+        static thread_local std::vector<Slot> pool;
+        if (pool.size() <= (size_t)src.idx) pool.resize((size_t)src.idx + 1);
+        Slot& sl = pool[src.idx]; const uint64_t need = src.span1 - src.span0 + 64;
+        if (sl.cap < need) { sl.p.reset(); sl.cap = need + need / 4; sl.p.reset(new uint8_t[sl.cap]); }      // uninitialised on purpose: nothing is read before its chunk was decoded
+        src.buf = sl.p.get();
+    }
+    memset(src.buf + (src.span1 - src.span0), 0, 64);
     if (whole) src.need(0, in.data_length);                               // a whole-ring compaction reads (and checksums) every chunk, as the reference does
 }
 
@@ -856,6 +865,11 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
     if (m->partitioner == B200C_PARTITIONER_BYTE_ORDERED && (m->token_lo != INT64_MIN || m->token_hi != INT64_MAX || m->npurge_ranges)) return B200C_EUNSUPPORTED;
     Purger pg{m->now_in_sec, m->gc_before, m->purge_max_timestamp};
     Writer w; w.m = m; w.sc = sc; w.raw = ro != nullptr; w.start_output();
+    if (ro) {                                              // a range task: one allocation for the piece of the stream it can produce, none while it grows
+        uint64_t span = 0, ispan = 0;
+        for (auto& sr : srcs) { span += sr.span1 - sr.span0; ispan += sr.in->index_len ? (uint64_t)((double)sr.in->index_len * (double)(sr.span1 - sr.span0) / (double)std::max<uint64_t>(1, sr.in->data_length)) : 0; }
+        w.outs.back().data.reserve(span + (span >> 3) + 4096); w.outs.back().index.reserve(ispan + (ispan >> 2) + 4096);
+    }
     if (ro && m->max_sstable_bytes) return B200C_EUNSUPPORTED;
     memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
     uint64_t total_source_rows = 0, input_partitions = 0;

@@ -38,6 +38,7 @@ extern "C" int warp_compress(int mode, const uint8_t* in, int n, uint8_t* out) {
         if (mode == 0) r = lz4_compress_warp<false>(s_in.data(), n, tab.data(), out, lane);
         else if (mode == 1) r = lz4_compress_warp<true>(s_in.data(), n, tab.data(), out, lane);
         else if (mode == 4) r = lz4_compress_warp<true>(s_in.data(), n, tab.data(), out, lane, dup.data());
+        else if (mode == 5 || mode == 6) r = snappy_compress_warp<true>(s_in.data(), n, tab.data(), mode == 6 ? 15 : 14, out, lane);     // Snappy reading the chunk in place
         else r = snappy_compress_warp(s_in.data(), n, tab.data(), mode == 3 ? 15 : 14, out, lane);
         if (lane == 0) result = r;
     });

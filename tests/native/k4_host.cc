@@ -111,7 +111,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
         d.nstat = in.nstatic_columns; for (int k = 0; k < in.nstatic_columns; k++) d.smap[k] = in.static_column_map[k];
     }
     // ---- K4, the code under test: size pass, host-side scans, emit pass ---------------------------------------------------------------
-    std::vector<Cur> cur(MAXK); std::vector<DT> open_dt(MAXK); std::vector<MCell> merged(MAXCOLS);
+    std::vector<Cur32> cur(MAXK); /* the cursor type of k_partition_thr */ std::vector<DT> open_dt(MAXK); std::vector<MCell> merged(MAXCOLS);
     std::vector<PartOut> po(nparts); PartStats st{0, 0};
     for (uint64_t j = 0; j < nparts; j++) {
         int e = 0; PartOut out{0, 0, 0, 0, 0};

@@ -45,6 +45,7 @@ def test_snappy_warp_source_equals_googles_library(warp):
     for name, data, want in vectors():
         if not data: continue
         assert run(warp, 3, data) == want, name
+        assert run(warp, 6, data) == want, name                                                  # chunk read in place (the L1 variant K5 launches)
         assert run(warp, 2, data) == O.chunk_compress(O.COMP_SNAPPY, data), name
 
 def test_snappy_warp_source_random_differential(warp):
@@ -60,3 +61,4 @@ def test_snappy_warp_source_random_differential(warp):
         else: d = (bytes(rng.getrandbits(8) for _ in range(rng.randint(1, 40))) * n)[:n]
         assert run(warp, 2, d) == O.chunk_compress(O.COMP_SNAPPY, d), (it, n, "2^14")
         assert run(warp, 3, d) == O.chunk_compress(O.COMP_SNAPPY15, d), (it, n, "2^15")
+        assert run(warp, 5, d) == O.chunk_compress(O.COMP_SNAPPY, d), (it, n, "2^14 in place")

@@ -226,6 +226,22 @@ def oracle_api():
     L.orc_compact.argtypes = [C.POINTER(native.Manifest), C.POINTER(native.Result), C.c_char_p, C.c_int]
     return L
 
+def usable_cpus():
+    """(threads worth starting, note): the CPUs this process may run on, capped by the container's CPU-time quota (cgroup cpu.max /
+    cfs_quota): with a quota of q CPUs, more than q busy threads are only throttled — on the round-2 GPU box 128 logical CPUs were visible,
+    the pod got 16 CPUs' worth of time, and 64 / 128 oracle threads ran SLOWER than 16 (profiles/r2_cpu_arm_scaling.txt)."""
+    n = len(os.sched_getaffinity(0)); quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max": quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0: quota = q / per
+        except Exception: pass
+    if quota is not None and quota < n: return max(1, int(quota + 0.5)), {"visible_cpus": n, "cgroup_cpu_quota": round(quota, 2)}
+    return n, {"visible_cpus": n, "cgroup_cpu_quota": quota}
+
 def cpu_compact(L, m, res, threads, ranges=0, max_ranges=0):
     """one CPU-oracle compaction of manifest m into res. threads > 1 (single-output workloads): token-range parallel oracle.
     Returns (seconds, sample_token_hi, [merge, stitch, compress] ms)."""
@@ -424,7 +440,7 @@ def cpu_leg_and_verify(args, wl, line, tabs, m_host, caps, ctx, L, do, ho, last,
     from cassandra_b200 import native
     cap_d, cap_i, cap_c, nout = caps
     OL = oracle_api()
-    threads = len(os.sched_getaffinity(0)); u_in = sum(t.compression.data_length for t in tabs)
+    threads, cpu_note = usable_cpus(); u_in = sum(t.compression.data_length for t in tabs)
     ranges = max(64, threads * 4)
     if wl["lcs"]:
         max_ranges = 0; thr = 1                 # multi-file output: the single-threaded oracle (= one reference compaction task)
@@ -436,7 +452,7 @@ def cpu_leg_and_verify(args, wl, line, tabs, m_host, caps, ctx, L, do, ho, last,
     cb = {"value": round(covered / sec / 1e6, 1), "unit": "MB/s", "cores": thr, "kind": "port",
           "sample": ("the whole workload" if hi == INT64_MAX else "token range (MIN, %d] of the same workload = %.1f %% of its bytes" % (hi, 100.0 * covered / u_in)) +
                     (", one compaction cut into %d token ranges, one oracle thread per range (oracle/parallel.cc)" % ranges if thr > 1 else ", single-threaded oracle (= one reference compaction task)"),
-          "seconds": round(sec, 2), "phase_ms": [round(x, 1) for x in tm[:3]], "range_tasks_ms": {"wall_sum": tm[3], "thread_cpu_sum": tm[4], "longest": tm[5]}, "rows_merged_per_s": round(int(res.total_source_rows) / sec, 0)}
+          "seconds": round(sec, 2), "phase_ms": [round(x, 1) for x in tm[:3]], "range_tasks_ms": {"wall_sum": tm[3], "thread_cpu_sum": tm[4], "longest": tm[5]}, "host": cpu_note, "rows_merged_per_s": round(int(res.total_source_rows) / sec, 0)}
     if thr > 1:                                  # what ONE reference compaction task achieves: a single thread, on a small prefix
         r1, _ = host_out_bufs_numpy(1, cap_d // 16 + (1 << 20), cap_i // 16 + (1 << 20), cap_c // 16 + 1024)
         s1, _, _ = cpu_compact(OL, m_host, r1, 1, ranges, max(1, ranges // 128))
@@ -471,7 +487,8 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0: return
     import numpy as np
-    threads = args.ref_threads or len(os.sched_getaffinity(0))
+    threads, cpu_note = usable_cpus()
+    if args.ref_threads: threads = args.ref_threads
     t0 = time.time()
     tabs = make_inputs(wl, oracle_compressor(wl), threads, pinned=False)
     log("reference arm: inputs ready in %.1fs" % (time.time() - t0))
@@ -496,8 +513,7 @@ def run_reference(args, wl):
     # scaling curve: constant work per thread (4 of 1024 token ranges each), so the points are comparable
     curve = {}
     if not wl["lcs"]:
-        for t in sorted({1, 16, 64, threads}):
-            if t > threads: continue
+        for t in sorted({1, 4, 16, 64, threads, cpu_note["visible_cpus"]}):          # beyond the quota: shows the throttling
             r1, _ = host_out_bufs_numpy(1, cap_d, cap_i, cap_c) if t * 4 >= 512 else host_out_bufs_numpy(1, cap_d // 4 + (8 << 20), cap_i // 4 + (8 << 20), cap_c // 4 + 1024)
             s1, _, _ = cpu_compact(OL, m, r1, t, 1024, min(1024, 4 * t))
             curve[str(t)] = {"MB/s": round(int(r1.bytes_in_range) / s1 / 1e6, 1), "seconds": round(s1, 2)}
@@ -508,12 +524,12 @@ def run_reference(args, wl):
           "sample": ("the whole workload" if hi == INT64_MAX else "token range (MIN, %d] = %.1f %% of the workload's bytes per step" % (hi, 100.0 * covered / args.steps / u_in)) +
                     (", ONE compaction cut into %d token ranges, one oracle thread per range" % ranges if thr > 1 else ", single-threaded oracle"),
           "phase_ms": [round(x / args.steps, 1) for x in tms[:3]], "range_tasks_ms": {"wall_sum": round(tms[3] / args.steps, 1), "thread_cpu_sum": round(tms[4] / args.steps, 1), "longest": round(tms[5] / args.steps, 1)},
-          "scaling": curve or None, "host_threads": threads}
+          "scaling": curve or None, "host_threads": threads, "host": cpu_note}
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"] + ", chunk 16 KiB, schema %s, seed %#x" % (wl["schema"], wl["seed"]), "uncompressed_in_bytes": u_in,
                        "reference_arm": "C++ restatement of the reference algorithm (oracle/; the JVM cannot run in this image: no JDK), same inputs as the b200 arm, "
-                                        "all host threads via token-range parallelism; the reference itself runs one such compaction on ONE thread (cpu_baseline.scaling['1'])"},
+                                        "as many threads as the container's CPU quota allows (cpu_baseline.host) via token-range parallelism; the reference itself runs one such compaction on ONE thread (cpu_baseline.scaling['1'])"},
             "rows_merged_per_s": round(rows / total, 0), "cpu_baseline": cb,
             "e2e": {"value": round(value, 1), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)

@@ -257,6 +257,19 @@ __device__ __forceinline__ void decompress_chunk_thread(const uint32_t (*s_crc)[
     const uint8_t* src = data + off;
     if (verify) {
         uint32_t crc = 0xFFFFFFFFu; int i = 0;
+        // a thread's chunk is its private stream: fetching it 8 bytes at a time asks for every 32-byte sector four times, with a few thousand
+        // other threads' sectors in between (ncu: 8 x the compressed bytes read from DRAM). The body therefore takes whole sectors — two
+        // aligned 16-byte loads per step — after a byte-wise run-up to the first 16-byte boundary.
+        {
+            int head = (int)((16u - (uint32_t)((uintptr_t)src & 15u)) & 15u); if (head > clen) head = clen;
+            for (; i < head; i++) crc = s_crc[0][(crc ^ src[i]) & 0xff] ^ (crc >> 8);
+            for (; i + 32 <= clen; i += 32) {
+                const uint4 a = __ldg((const uint4*)(src + i)), b4 = __ldg((const uint4*)(src + i + 16));
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const uint32_t x = crc ^ w[k]; crc = s_crc[3][x & 0xff] ^ s_crc[2][(x >> 8) & 0xff] ^ s_crc[1][(x >> 16) & 0xff] ^ s_crc[0][x >> 24]; }
+            }
+        }
         for (; i + 8 <= clen; i += 8) {
             uint64_t v = ld_le64(src + i);
             uint32_t x = crc ^ (uint32_t)v;

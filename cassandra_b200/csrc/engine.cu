@@ -214,7 +214,11 @@ int decompress_multi_device(b200c_ctx* c, K1Seg* segs, int nseg, int verify, Chu
     if (!total) return B200C_OK;
     K1Seg* d; B200C_TRY(ws_typed(c, ws_slot, (size_t)nseg, &d));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(d, segs, sizeof(K1Seg) * nseg, cudaMemcpyHostToDevice, c->stream));
-    B200C_LAUNCH(c, k_decompress_multi_thr, (unsigned)((total + 127) / 128), 128, 0, c->d_tables, d, nseg, total, verify, d_err);
+    // B200C_K1_PAD=bytes of unused dynamic shared memory per block: caps the blocks resident per SM (A/B: fewer private streams in flight =
+    // a smaller L2 working set for a kernel whose DRAM traffic is several times its algorithmic bytes)
+    const int k1_pad = []() { const char* e = getenv("B200C_K1_PAD"); return e ? atoi(e) : 0; }();
+    if (k1_pad > 48 * 1024 - 4096) { static bool once = false; if (!once) { cudaFuncSetAttribute(k_decompress_multi_thr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); once = true; } }
+    B200C_LAUNCH(c, k_decompress_multi_thr, (unsigned)((total + 127) / 128), 128, (size_t)k1_pad, c->d_tables, d, nseg, total, verify, d_err);
     return B200C_OK;
 }
 

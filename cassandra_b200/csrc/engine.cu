@@ -56,6 +56,15 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
     uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
     if (!nchunks) return B200C_OK;
     const int k5_mode = []() { const char* e = getenv("B200C_K5"); return e ? atoi(e) : 1; }();      // 1 (default): LZ4 reads the chunk through L1, 13 chunks per SM: 48.0 -> 34.7 ms at 16 x 256 MiB; 0: chunk copy in shared memory (A/B)
+    if (k5_mode == 3 && comp == COMP_LZ4 && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0 && chunk_len <= LZ4C_MAX_CHUNK) {
+        // two passes (lz4_chain.cuh): same-hash predecessor links for every position, then the parse with one bit per position in shared memory
+        uint32_t* ent; B200C_TRY(ws_typed(c, WS_K5_ENT, (size_t)n + 16384, &ent));
+        B200C_LAUNCH(c, k_lz4_chain_build, (unsigned)nchunks, 32, 0, d_in, n, chunk_len, ent);
+        const size_t smem = (size_t)K5B_WARPS * ((chunk_len + 31) >> 5) * 4;
+        B200C_LAUNCH(c, k_compress_chunks_lz4_chain, (unsigned)((nchunks + K5B_WARPS - 1) / K5B_WARPS), 32 * K5B_WARPS, smem, c->d_tables, d_in, n, chunk_len, max_clen, (const uint32_t*)ent,
+                     slots, stride, file_len, seg_raw, nchunks);
+        return B200C_OK;
+    }
     if ((k5_mode == 1 || k5_mode == 2) && comp == COMP_LZ4 && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0) {
         if (k5_mode == 2) B200C_LAUNCH(c, k_compress_chunks_lz4_direct<true>, (unsigned)nchunks, 32, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);   // + distinct-hash fast path (A/B)
         else B200C_LAUNCH(c, k_compress_chunks_lz4_direct<false>, (unsigned)nchunks, 32, 0, c->d_tables, d_in, n, chunk_len, max_clen, slots, stride, file_len, seg_raw);

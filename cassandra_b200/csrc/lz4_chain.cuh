@@ -1,0 +1,237 @@
+// lz4_chain.cuh — LZ4 block compression in two kernels, bit-exact with liblz4's LZ4_compress_default like lz4.cuh, built so that the
+// SEQUENTIAL part of the format no longer owns 16 KiB of shared memory per chunk.
+//
+// lz4.cuh keeps liblz4's hash table (8192 x u16) in shared memory for the whole life of a chunk: 14 chunks per SM, each of them one long
+// chain of dependent instructions — that is what bounds K5 (ncu: 14 warps per SM, 40 % issue utilisation). What the table answers is
+// "the most recent INSERTED position with this hash"; which positions get inserted depends on the parse, but "the most recent EARLIER
+// positions with this hash" do not. So:
+//
+//   pass A (lz4_chain_build_warp, one warp per chunk, table in shared memory, no parse — 512 independent-looking steps per chunk):
+//       for every position p the two nearest earlier positions with the same hash, q1 > q2, and whether their 4 bytes equal p's:
+//       ent[p] = q1 | eq1 << 15 | q2 << 16 | eq2 << 31        (no earlier position: 0 — the zero-initialised table entry liblz4 reads)
+//   pass B (lz4_compress_warp_chain, the parse): the candidate of a search attempt at p is the first INSERTED position along
+//       q1, q2, ent[q2].q1, ...; "inserted" is one bit per position (2 KiB of shared memory per chunk instead of 16). Nine lookups in ten
+//       end at q1 (measured on the benchmark's data), and the hit test is the precomputed bit: the search window reads no chunk bytes.
+//
+// Equivalence with the table: positions are inserted in increasing order (search attempts move forward; after a match liblz4 inserts ip-2,
+// which lies behind every earlier insertion, then tests and inserts ip), so table[h] is always the LARGEST inserted position with hash h,
+// or 0 while none was inserted — and the chain from p visits exactly the earlier positions with p's hash in decreasing order.
+// Chunk lengths up to 32 KiB (15-bit positions); longer chunks keep the lz4.cuh kernel.
+#pragma once
+#include "lz4.cuh"
+
+namespace b200c {
+
+enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF };
+
+#if defined(__CUDA_ARCH__)
+#define LZ4C_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
+#else
+#define LZ4C_PREFETCH(p) ((void)0)
+#endif
+
+// number of positions that can ever be looked up or inserted: search attempts and the post-match test stay below mflimitPlusOne = n - 11
+__host__ __device__ __forceinline__ int lz4c_positions(int n) { return n >= LZ4_MINLENGTH ? n - LZ4_MFLIMIT + 1 : 0; }
+
+// ---- pass A ---------------------------------------------------------------------------------------------------------------------------
+// s_in: the chunk where it lies in global memory (4-byte aligned, >= n + 8 readable bytes); s_t1 / s_t2: 8192 x u16 each (last and
+// second-to-last position per hash); s_dup: LZ4_DUP_ENTRIES bytes; ent: lz4c_positions(n) words.
+__device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint16_t* s_t2, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+    const uint32_t* in32 = (const uint32_t*)s_in;
+    {
+        uint4* a = (uint4*)s_t1; uint4* b = (uint4*)s_t2;
+        for (int i = lane; i < (LZ4_TABLE_ENTRIES * 2) / 16; i += 32) { a[i] = make_uint4(~0u, ~0u, ~0u, ~0u); b[i] = make_uint4(~0u, ~0u, ~0u, ~0u); }
+    }
+    __syncwarp();
+    const int npos = lz4c_positions(n);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int p0 = 0; p0 < npos; p0 += 32) {
+        const int p = p0 + lane; const bool valid = p < npos;
+        const uint32_t seq = valid ? lz4_rd32<true>(in32, p) : 0u;
+        const uint32_t h = lz4_hash_u16(seq);
+        const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
+        // do two positions of this step share a hash? (see lz4.cuh: one byte per hash slot, the lanes that read back another lane's number share)
+        const uint32_t dh = h & (LZ4_DUP_ENTRIES - 1);
+        if (valid) s_dup[dh] = (uint8_t)lane;
+        __syncwarp();
+        const bool shared = valid && s_dup[dh] != (uint8_t)lane;
+        const bool unique = !__any_sync(FULL_MASK, shared);
+        uint32_t q1 = LZ4C_NONE, q2 = LZ4C_NONE;
+        if (unique) {
+            if (valid) { q1 = s_t1[h]; q2 = s_t2[h]; s_t2[h] = (uint16_t)q1; s_t1[h] = (uint16_t)p; }
+        } else {
+            uint32_t same = FULL_MASK;
+#pragma unroll
+            for (int b = 0; b < LZ4_HASHLOG_U16; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
+            same &= vmask;
+            const uint32_t lower = same & lt_mask;
+            const int c = __popc(lower);
+            const uint32_t t1 = valid ? s_t1[h] : LZ4C_NONE, t2 = valid ? s_t2[h] : LZ4C_NONE;
+            if (c >= 1) {
+                const int l1 = 31 - __clz(lower);
+                q1 = (uint32_t)(p0 + l1);
+                const uint32_t rest = lower & ~(1u << l1);
+                q2 = rest ? (uint32_t)(p0 + 31 - __clz(rest)) : t1;
+            } else { q1 = t1; q2 = t2; }
+            __syncwarp();                                          // every lane has read the tables
+            const uint32_t higher = same & ~lt_mask & ~(1u << lane);
+            if (valid && !higher) { s_t1[h] = (uint16_t)p; s_t2[h] = (uint16_t)q1; }
+        }
+        __syncwarp();
+        const uint32_t a1 = q1 == LZ4C_NONE ? 0u : q1, a2 = q2 == LZ4C_NONE ? 0u : q2;
+        if (valid) {
+            const uint32_t e1 = lz4_rd32<true>(in32, (int)a1) == seq, e2 = lz4_rd32<true>(in32, (int)a2) == seq;
+            ent[p] = a1 | (e1 << 15) | (a2 << 16) | (e2 << 31);
+        }
+    }
+}
+
+// bits [lo, hi) that fall into 32-bit word w of a bitmap
+__device__ __forceinline__ uint32_t lz4c_range_bits(int lo, int hi, int w) {
+    const int a = lo > w * 32 ? lo - w * 32 : 0, b = hi < w * 32 + 32 ? hi - w * 32 : 32;
+    if (b <= a) return 0u;
+    const uint32_t upto_b = b >= 32 ? FULL_MASK : ((1u << b) - 1u);
+    return upto_b & ~((1u << a) - 1u);
+}
+
+// ---- pass B ---------------------------------------------------------------------------------------------------------------------------
+// s_in as above; ent: pass A's output for this chunk; s_bm: (n + 31) / 32 words of shared memory (zeroed here); out: capacity >=
+// lz4_compress_bound(n). Returns the compressed size (warp-uniform). The control flow is lz4_compress_warp's (32 speculated attempts per
+// step, the post-match insert / test folded into the first window as lanes 0 and 1); only the candidate lookup and the hit test differ.
+__device__ int lz4_compress_warp_chain(const uint8_t* s_in, int n, const uint32_t* __restrict__ ent, uint32_t* s_bm, uint8_t* out, int lane) {
+    const uint32_t* in32 = (const uint32_t*)s_in;
+    for (int i = lane; i < ((n + 31) >> 5); i += 32) s_bm[i] = (i == 0) ? 1u : 0u;       // "first byte": position 0 is inserted
+    __syncwarp();
+    int anchor = 0, op = 0;
+    const int mfl1 = n - LZ4_MFLIMIT + 1;
+    const int matchlimit = n - LZ4_LASTLITERALS;
+
+    if (n >= LZ4_MINLENGTH) {
+        int fwd = 1; bool have_prefix = false; int pre_ip = 0;
+        for (;;) {
+            int ip = 0, match = 0, token_pos; bool ended = false, immediate = false;
+            if (lane < 4) LZ4C_PREFETCH(ent + fwd + 64 + 32 * lane);
+            int a0 = 0;
+            for (bool first = true;; first = false) {
+                const bool prefixed = first && have_prefix;
+                int p; bool valid, putonly = false;
+                if (prefixed && lane < 2) { p = lane == 0 ? pre_ip - 2 : pre_ip; valid = true; putonly = lane == 0; }
+                else {
+                    const int a = a0 + lane - (prefixed ? 2 : 0);
+                    p = fwd + lz4_attempt_offset(a);
+                    const int pn = fwd + lz4_attempt_offset(a + 1);
+                    valid = pn <= mfl1;
+                }
+                const uint32_t inval = __ballot_sync(FULL_MASK, !valid);
+                const int first_inv = inval ? (__ffs(inval) - 1) : 32;
+                // the window's own positions count as inserted for the lanes behind them (they are, unless an earlier lane hits — and then
+                // the later lanes' answers are dropped). Contiguous windows (every attempt within the first 65: step 1) know them by
+                // arithmetic; windows in the accelerated regime mark them in the bitmap first and take the unused marks back afterwards.
+                const bool contiguous = a0 + 32 <= 66;
+                const int w_lo = prefixed ? pre_ip - 2 : fwd + a0;               // first position of a contiguous window
+                const int hole = prefixed ? pre_ip - 1 : -1;                      // the one position between lane 0 and lane 1 of a prefixed window
+                if (!contiguous) { if (valid) atomicOr(&s_bm[p >> 5], 1u << (p & 31)); __syncwarp(); }
+                const uint32_t e = valid ? ent[p] : 0u;
+                const int q1 = (int)(e & 0x7FFFu), q2 = (int)((e >> 16) & 0x7FFFu);
+                const bool in1 = contiguous ? (q1 >= w_lo && q1 != hole) : false, in2 = contiguous ? (q2 >= w_lo && q2 != hole) : false;
+                const bool ins1 = in1 || ((s_bm[q1 >> 5] >> (q1 & 31)) & 1u), ins2 = in2 || ((s_bm[q2 >> 5] >> (q2 & 31)) & 1u);
+                int cand = ins1 ? q1 : q2;
+                bool hit = valid && !putonly && (ins1 ? ((e >> 15) & 1u) : (e >> 31));
+                bool deeper = valid && !ins1 && !ins2;
+                if (__any_sync(FULL_MASK, deeper)) {
+                    // further down the chain (one lookup in forty): follow the first-level links, then compare the bytes
+                    int q = q2;
+                    for (;;) {
+                        const bool go = deeper && !((contiguous && q >= w_lo && q != hole) || ((s_bm[q >> 5] >> (q & 31)) & 1u));
+                        if (!__any_sync(FULL_MASK, go)) break;
+                        if (go) q = (int)(ent[q] & 0x7FFFu);
+                    }
+                    if (deeper) { cand = q; hit = !putonly && (lz4_rd32<true>(in32, q) == lz4_rd32<true>(in32, p)); }
+                }
+                const uint32_t hits = __ballot_sync(FULL_MASK, hit);
+                const int first_hit = hits ? (__ffs(hits) - 1) : 32;
+                const bool found = first_hit < first_inv;
+                // insertions: lanes up to the hit (all valid lanes when there is none)
+                const int last_ins = found ? first_hit : (first_inv - 1);        // -1: no valid lane at all
+                if (contiguous) {
+                    if (last_ins >= 0) {
+                        const int p_last = __shfl_sync(FULL_MASK, p, last_ins);
+                        if (lane < 3) {
+                            const int w = (w_lo >> 5) + lane;
+                            uint32_t mbits = lz4c_range_bits(w_lo, p_last + 1, w);
+                            if (hole >= 0 && (hole >> 5) == w) mbits &= ~(1u << (hole & 31));
+                            if (mbits) s_bm[w] |= mbits;
+                        }
+                    }
+                } else {
+                    __syncwarp();
+                    if (valid && lane > last_ins) atomicAnd(&s_bm[p >> 5], ~(1u << (p & 31)));
+                }
+                __syncwarp();
+                if (found) {
+                    ip = __shfl_sync(FULL_MASK, p, first_hit);
+                    match = __shfl_sync(FULL_MASK, cand, first_hit);
+                    immediate = prefixed && first_hit == 1;
+                    break;
+                }
+                if (first_inv < 32) { ended = true; break; }
+                a0 += prefixed ? 30 : 32;
+            }
+            if (ended) break;
+
+            int lit_nibble = 0;
+            if (!immediate) {
+                // ---- catch up: extend the match backwards -----------------------------------------------------------
+                for (;;) {
+                    int j = lane + 1;
+                    bool ok = (ip - j >= anchor) && (match - j >= 0) && (lz4_rd8<true>(s_in, ip - j) == lz4_rd8<true>(s_in, match - j));
+                    uint32_t b = __ballot_sync(FULL_MASK, ok);
+                    int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
+                    ip -= steps; match -= steps;
+                    if (steps < 32) break;
+                }
+                // ---- literals ---------------------------------------------------------------------------------------
+                int lit = ip - anchor;
+                token_pos = op++;
+                if (lit >= 15) op += lz4_emit_len_ext(out + op, lit - 15, lane);
+                for (int i = lane; i < lit; i += 32) out[op + i] = (uint8_t)lz4_rd8<true>(s_in, anchor + i);
+                op += lit;
+                lit_nibble = lit < 15 ? lit : 15;
+            } else token_pos = op++;                      // immediate match: token with literal length 0
+
+            // ---- the match: offset, length beyond MINMATCH limited by matchlimit (LZ4_count) --------------------------
+            if (lane == 0) { int off = ip - match; out[op] = (uint8_t)off; out[op + 1] = (uint8_t)(off >> 8); }
+            op += 2;
+            int mc = 0;
+            {
+                int pi = ip + LZ4_MINMATCH, pm = match + LZ4_MINMATCH;
+                for (;;) {
+                    int i = mc + lane;
+                    bool eq = (pi + i < matchlimit) && (lz4_rd8<true>(s_in, pi + i) == lz4_rd8<true>(s_in, pm + i));
+                    uint32_t b = __ballot_sync(FULL_MASK, eq);
+                    if (b == FULL_MASK) { mc += 32; continue; }
+                    mc += __ffs(~b) - 1;
+                    break;
+                }
+            }
+            ip += mc + LZ4_MINMATCH;
+            if (lane == 0) out[token_pos] = (uint8_t)((lit_nibble << 4) | (mc < 15 ? mc : 15));
+            if (mc >= 15) op += lz4_emit_len_ext(out + op, mc - 15, lane);
+            anchor = ip;
+            if (ip >= mfl1) break;
+            have_prefix = true; pre_ip = ip; fwd = ip + 1;
+        }
+    }
+    // ---- last literals ------------------------------------------------------------------------------------------
+    {
+        int last = n - anchor;
+        if (lane == 0) out[op] = (uint8_t)((last < 15 ? last : 15) << 4);
+        op++;
+        if (last >= 15) op += lz4_emit_len_ext(out + op, last - 15, lane);
+        for (int i = lane; i < last; i += 32) out[op + i] = (uint8_t)lz4_rd8<true>(s_in, anchor + i);
+        op += last;
+    }
+    return op;
+}
+
+} // namespace b200c

@@ -14,6 +14,7 @@
 #include "snappy.cuh"
 #include "codec_defs.cuh"
 #include "lz4_thread.cuh"
+#include "lz4_batch.cuh"
 
 namespace b200c {
 
@@ -369,6 +370,61 @@ __global__ void __launch_bounds__(128) k_decompress_multi_thr(const DevTables* _
     const uint64_t chunk = g.chunk0 + (t - g.first);
     if (chunk >= g.nchunks) return;
     decompress_chunk_thread(s_crc, COMP_LZ4, g.data, g.data_len, g.offs, g.nchunks, g.chunk_len, g.max_clen, g.data_length, g.out, verify, err, chunk, g.tag);
+}
+
+// ---- K1 in two passes (lz4_batch.cuh): walk (thread per chunk: validate, record the sequence starts) then copy (warp per chunk, 32 sequences
+// per step). Record slots: a block of n bytes has at most (n - 1) / 3 + 1 sequences, so chunk c of a segment owns the u16 slots from
+// rec0 + (offs[c] - offs[chunk0]) / 3 + 2 (c - chunk0) on — no scan, no second walk.
+enum : uint32_t { K1_SKIP = 0xFFFFFFFFu, K1_BAD = 0xFFFFFFFEu, K1_BAD_OFFS = 0xFFFFFFFDu, K1_RAW = 0xFFFFFFFCu };
+struct K1Chunk { const uint8_t* src; uint8_t* dst; int clen, ulen; uint64_t slot, ctag; };
+// which chunk thread/warp t of a multi-segment launch owns and where its bytes are; false: nothing to do (K1_SKIP) or bad offsets (reported)
+__device__ __forceinline__ uint32_t k1_locate(const K1Seg* __restrict__ segs, int nseg, uint64_t t, K1Chunk& k) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (segs[mid].first <= t) lo = mid; else hi = mid - 1; }
+    const K1Seg& g = segs[lo];
+    const uint64_t chunk = g.chunk0 + (t - g.first);
+    if (chunk >= g.nchunks) return K1_SKIP;
+    const uint64_t off = g.offs[chunk], next = (chunk + 1 < g.nchunks) ? g.offs[chunk + 1] : g.data_len, off0 = g.offs[g.chunk0];
+    const uint64_t ustart = chunk * (uint64_t)g.chunk_len;
+    k.ctag = ((uint64_t)g.tag << 40) | chunk;
+    if (off + 4 > next || next > g.data_len || ustart >= g.data_length || next - off - 4 > (uint64_t)(chunk_max_compressed(COMP_LZ4, g.chunk_len) + g.chunk_len) ||
+        off < off0 || next - off0 > g.rec_span) return K1_BAD_OFFS;
+    k.clen = (int)(next - off - 4); k.ulen = (int)min((uint64_t)g.chunk_len, g.data_length - ustart);
+    k.src = g.data + off; k.dst = g.out + ustart;
+    k.slot = g.rec0 + (off - off0) / 3 + 2 * (chunk - g.chunk0);
+    return k.clen >= g.max_clen ? K1_RAW : 0u;
+}
+__global__ void __launch_bounds__(128) k_lz4_walk_multi(const K1Seg* __restrict__ segs, int nseg, uint64_t total, uint16_t* __restrict__ rec,
+                                                        uint32_t* __restrict__ nseq, ChunkErr* __restrict__ err) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    K1Chunk k; const uint32_t st = k1_locate(segs, nseg, t, k);
+    if (st == K1_SKIP) { nseq[t] = K1_SKIP; return; }
+    if (st == K1_BAD_OFFS) { report_chunk_err(err, k.ctag, 2); nseq[t] = K1_BAD_OFFS; return; }
+    if (st == K1_RAW) { if (k.clen < k.ulen) { report_chunk_err(err, k.ctag, 2); nseq[t] = K1_BAD; } else nseq[t] = K1_RAW; return; }
+    const uint8_t* src = k.src;
+    const int plen = (k.clen >= 4) ? (int)((uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24)) : -1;
+    const int r = (plen == k.ulen) ? lz4_walk_thread(src + 4, k.clen - 4, k.ulen, rec + k.slot, (k.clen + 4) / 3 + 1) : -1;
+    if (r < 0) { report_chunk_err(err, k.ctag, 2); nseq[t] = K1_BAD; } else nseq[t] = (uint32_t)r;
+}
+enum { K1C_WARPS = 4 };
+__global__ void __launch_bounds__(32 * K1C_WARPS) k_lz4_copy_multi(const DevTables* __restrict__ T, const K1Seg* __restrict__ segs, int nseg, uint64_t total,
+                                                                   const uint16_t* __restrict__ rec, const uint32_t* __restrict__ nseq, int verify, ChunkErr* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t t = (uint64_t)blockIdx.x * K1C_WARPS + (threadIdx.x >> 5);
+    if (t >= total) return;
+    const uint32_t ns = nseq[t];
+    if (ns == K1_SKIP || ns == K1_BAD_OFFS) return;
+    K1Chunk k; (void)k1_locate(segs, nseg, t, k);
+    if (verify) {                                      // (a chunk the walk refused still has its CRC looked at: a CRC mismatch is the error reported first)
+        const uint32_t crc = warp_crc32(T, T->crc_adv128, k.src, k.clen, lane);
+        const uint8_t* s = k.src + k.clen;
+        const uint32_t stored = ((uint32_t)s[0] << 24) | ((uint32_t)s[1] << 16) | ((uint32_t)s[2] << 8) | s[3];
+        if (crc != stored) { if (lane == 0) report_chunk_err(err, k.ctag, 1); return; }
+    }
+    if (ns == K1_BAD) return;
+    if (ns == K1_RAW) { for (int i = lane; i < k.ulen; i += 32) k.dst[i] = k.src[i]; return; }
+    (void)lz4_copy_warp(k.src + 4, k.clen - 4, rec + k.slot, (int)ns, k.dst, lane);
 }
 
 } // namespace b200c

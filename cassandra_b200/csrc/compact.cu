@@ -1109,6 +1109,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             K1Seg g; memset(&g, 0, sizeof(g));
             g.data = CD + cbase[i]; g.data_len = in.data_len; g.offs = CO + obase[i]; g.nchunks = in.nchunks; g.data_length = in.data_length; g.out = U + ubase[i];
             g.chunk0 = from[i]; g.count = to[i] - from[i]; g.chunk_len = in.chunk_len; g.max_clen = in.max_compressed_len; g.tag = i;
+            if (!dev || !co_host.empty()) { const uint64_t a = chunk_off(i, from[i]), b = chunk_off(i, to[i]); g.rec_span = b > a ? b - a : 0; }      // (0 / unknown: the whole file)
             segs.push_back(g); total += g.count;
         }
         const bool batched = total >= (k1_batch_env == 2 ? 1u : 32768u);

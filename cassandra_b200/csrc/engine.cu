@@ -221,8 +221,28 @@ int decompress_multi_device(b200c_ctx* c, K1Seg* segs, int nseg, int verify, Chu
     uint64_t total = 0;
     for (int i = 0; i < nseg; i++) { segs[i].first = total; segs[i].count = segs[i].nchunks > segs[i].chunk0 ? std::min(segs[i].count, segs[i].nchunks - segs[i].chunk0) : 0; total += segs[i].count; }
     if (!total) return B200C_OK;
+    // B200C_K1=2: two passes (lz4_batch.cuh) — walk: one thread per chunk validates the block and records where its sequences start;
+    // copy: one warp per chunk, 32 sequences per step. rec_span (when the caller knows the range's compressed size) sizes the record slots.
+    static const int k1_mode = []() { const char* e = getenv("B200C_K1"); return e ? atoi(e) : 1; }();
+    uint64_t rec_total = 0;
+    for (int i = 0; i < nseg; i++) {
+        if (!segs[i].rec_span || segs[i].rec_span > segs[i].data_len) segs[i].rec_span = segs[i].data_len;
+        segs[i].rec0 = rec_total; rec_total += segs[i].rec_span / 3 + 2 * segs[i].count + 8;
+    }
     K1Seg* d; B200C_TRY(ws_typed(c, ws_slot, (size_t)nseg, &d));
     B200C_CUDA_TRY(c, cudaMemcpyAsync(d, segs, sizeof(K1Seg) * nseg, cudaMemcpyHostToDevice, c->stream));
+    if (k1_mode == 2) {
+        uint16_t* rec; uint32_t* nseq;
+        B200C_TRY(ws_typed(c, WS_K1_REC, (size_t)rec_total + 64, &rec));
+        B200C_TRY(ws_typed(c, WS_K1_NSEQ, (size_t)total + 64, &nseq));
+        B200C_LAUNCH(c, k_lz4_walk_multi, (unsigned)((total + 127) / 128), 128, 0, d, nseg, total, rec, nseq, d_err);
+        // blocks of the copy kernel resident per SM (B200C_K1_COPY_BLOCKS, 4 warps each): every chunk in flight keeps ~30 KB of L2 busy
+        static const int copy_blocks = []() { const char* e = getenv("B200C_K1_COPY_BLOCKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+        static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_lz4_copy_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+        const size_t pad = copy_blocks >= 16 ? 0 : (size_t)(220 * 1024) / copy_blocks;
+        B200C_LAUNCH(c, k_lz4_copy_multi, (unsigned)((total + K1C_WARPS - 1) / K1C_WARPS), 32 * K1C_WARPS, pad, c->d_tables, (const K1Seg*)d, nseg, total, (const uint16_t*)rec, (const uint32_t*)nseq, verify, d_err);
+        return B200C_OK;
+    }
     // B200C_K1_PAD=bytes of unused dynamic shared memory per block: caps the blocks resident per SM (A/B: fewer private streams in flight =
     // a smaller L2 working set for a kernel whose DRAM traffic is several times its algorithmic bytes)
     const int k1_pad = []() { const char* e = getenv("B200C_K1_PAD"); return e ? atoi(e) : 0; }();

@@ -11,7 +11,7 @@
 
 namespace b200c {
 
-enum { WS_SLOTS = 160, WS_K5_ENT = 150 };      // (slots 0..15: codec calls, 16..: compact.cu's map, 150: K5's hash-chain entries)
+enum { WS_SLOTS = 160, WS_K5_ENT = 150, WS_K1_REC = 151, WS_K1_NSEQ = 152 };      // (slots 0..15: codec calls, 16..: compact.cu's map, 150: K5's hash-chain entries, 151-152: K1's sequence records)
 
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
 

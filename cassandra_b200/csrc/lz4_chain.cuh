@@ -114,54 +114,60 @@ __device__ int lz4_compress_warp_chain(const uint8_t* s_in, int n, const uint32_
             int a0 = 0;
             for (bool first = true;; first = false) {
                 const bool prefixed = first && have_prefix;
+                // The window's own positions count as inserted for the lanes behind them (they are, unless an earlier lane hits — and then
+                // the later lanes' answers are dropped). Contiguous windows (every attempt within the first 65: step 1) know their positions
+                // and that membership by arithmetic; windows in the accelerated regime mark them in the bitmap first and take the unused
+                // marks back afterwards.
+                const bool contiguous = a0 + 32 <= 66;
+                const int w_lo = prefixed ? pre_ip - 2 : fwd + a0;               // first position of a contiguous window
+                const int hole = prefixed ? pre_ip - 1 : -1;                      // the one position lanes 0 and 1 of a prefixed window leave out
                 int p; bool valid, putonly = false;
-                if (prefixed && lane < 2) { p = lane == 0 ? pre_ip - 2 : pre_ip; valid = true; putonly = lane == 0; }
-                else {
-                    const int a = a0 + lane - (prefixed ? 2 : 0);
+                if (contiguous) {
+                    p = w_lo + lane + ((prefixed && lane >= 1) ? 1 : 0);
+                    putonly = prefixed && lane == 0;
+                    valid = (prefixed && lane < 2) || p + 1 <= mfl1;
+                } else {
+                    const int a = a0 + lane;
                     p = fwd + lz4_attempt_offset(a);
-                    const int pn = fwd + lz4_attempt_offset(a + 1);
-                    valid = pn <= mfl1;
+                    valid = fwd + lz4_attempt_offset(a + 1) <= mfl1;
                 }
                 const uint32_t inval = __ballot_sync(FULL_MASK, !valid);
                 const int first_inv = inval ? (__ffs(inval) - 1) : 32;
-                // the window's own positions count as inserted for the lanes behind them (they are, unless an earlier lane hits — and then
-                // the later lanes' answers are dropped). Contiguous windows (every attempt within the first 65: step 1) know them by
-                // arithmetic; windows in the accelerated regime mark them in the bitmap first and take the unused marks back afterwards.
-                const bool contiguous = a0 + 32 <= 66;
-                const int w_lo = prefixed ? pre_ip - 2 : fwd + a0;               // first position of a contiguous window
-                const int hole = prefixed ? pre_ip - 1 : -1;                      // the one position between lane 0 and lane 1 of a prefixed window
                 if (!contiguous) { if (valid) atomicOr(&s_bm[p >> 5], 1u << (p & 31)); __syncwarp(); }
                 const uint32_t e = valid ? ent[p] : 0u;
                 const int q1 = (int)(e & 0x7FFFu), q2 = (int)((e >> 16) & 0x7FFFu);
-                const bool in1 = contiguous ? (q1 >= w_lo && q1 != hole) : false, in2 = contiguous ? (q2 >= w_lo && q2 != hole) : false;
+                const bool in1 = contiguous && q1 >= w_lo && q1 != hole, in2 = contiguous && q2 >= w_lo && q2 != hole;
                 const bool ins1 = in1 || ((s_bm[q1 >> 5] >> (q1 & 31)) & 1u), ins2 = in2 || ((s_bm[q2 >> 5] >> (q2 & 31)) & 1u);
                 int cand = ins1 ? q1 : q2;
-                bool hit = valid && !putonly && (ins1 ? ((e >> 15) & 1u) : (e >> 31));
-                bool deeper = valid && !ins1 && !ins2;
-                if (__any_sync(FULL_MASK, deeper)) {
-                    // further down the chain (one lookup in forty): follow the first-level links, then compare the bytes
-                    int q = q2;
-                    for (;;) {
-                        const bool go = deeper && !((contiguous && q >= w_lo && q != hole) || ((s_bm[q >> 5] >> (q & 31)) & 1u));
-                        if (!__any_sync(FULL_MASK, go)) break;
-                        if (go) q = (int)(ent[q] & 0x7FFFu);
+                bool hit = valid && !putonly && (ins1 ? ((e >> 15) & 1u) : (ins2 ? (e >> 31) : 0u));
+                const bool deeper = valid && !ins1 && !ins2;
+                uint32_t hits = __ballot_sync(FULL_MASK, hit);
+                const uint32_t dmask = __ballot_sync(FULL_MASK, deeper);
+                if (dmask) {
+                    const int first_deep = __ffs(dmask) - 1, sure = hits ? (__ffs(hits) - 1) : 32;
+                    if (first_deep < sure && first_deep < first_inv) {
+                        // further down the chain decides (one lookup in forty goes this deep): follow the first-level links, then compare the bytes
+                        int q = q2;
+                        for (;;) {
+                            const bool go = deeper && !((contiguous && q >= w_lo && q != hole) || ((s_bm[q >> 5] >> (q & 31)) & 1u));
+                            if (!__any_sync(FULL_MASK, go)) break;
+                            if (go) q = (int)(ent[q] & 0x7FFFu);
+                        }
+                        if (deeper) { cand = q; hit = !putonly && (lz4_rd32<true>(in32, q) == lz4_rd32<true>(in32, p)); }
+                        hits = __ballot_sync(FULL_MASK, hit);
                     }
-                    if (deeper) { cand = q; hit = !putonly && (lz4_rd32<true>(in32, q) == lz4_rd32<true>(in32, p)); }
                 }
-                const uint32_t hits = __ballot_sync(FULL_MASK, hit);
                 const int first_hit = hits ? (__ffs(hits) - 1) : 32;
                 const bool found = first_hit < first_inv;
                 // insertions: lanes up to the hit (all valid lanes when there is none)
                 const int last_ins = found ? first_hit : (first_inv - 1);        // -1: no valid lane at all
                 if (contiguous) {
-                    if (last_ins >= 0) {
-                        const int p_last = __shfl_sync(FULL_MASK, p, last_ins);
-                        if (lane < 3) {
-                            const int w = (w_lo >> 5) + lane;
-                            uint32_t mbits = lz4c_range_bits(w_lo, p_last + 1, w);
-                            if (hole >= 0 && (hole >> 5) == w) mbits &= ~(1u << (hole & 31));
-                            if (mbits) s_bm[w] |= mbits;
-                        }
+                    if (last_ins >= 0 && lane < 2) {
+                        const int p_last = w_lo + last_ins + ((prefixed && last_ins >= 1) ? 1 : 0);
+                        const int w = (w_lo >> 5) + lane;
+                        uint32_t mbits = lz4c_range_bits(w_lo, p_last + 1, w);
+                        if (hole >= 0 && (hole >> 5) == w) mbits &= ~(1u << (hole & 31));
+                        if (mbits) s_bm[w] |= mbits;
                     }
                 } else {
                     __syncwarp();
@@ -169,7 +175,7 @@ __device__ int lz4_compress_warp_chain(const uint8_t* s_in, int n, const uint32_
                 }
                 __syncwarp();
                 if (found) {
-                    ip = __shfl_sync(FULL_MASK, p, first_hit);
+                    ip = contiguous ? (w_lo + first_hit + ((prefixed && first_hit >= 1) ? 1 : 0)) : __shfl_sync(FULL_MASK, p, first_hit);
                     match = __shfl_sync(FULL_MASK, cand, first_hit);
                     immediate = prefixed && first_hit == 1;
                     break;
@@ -179,17 +185,39 @@ __device__ int lz4_compress_warp_chain(const uint8_t* s_in, int n, const uint32_
             }
             if (ended) break;
 
-            int lit_nibble = 0;
-            if (!immediate) {
-                // ---- catch up: extend the match backwards -----------------------------------------------------------
-                for (;;) {
-                    int j = lane + 1;
-                    bool ok = (ip - j >= anchor) && (match - j >= 0) && (lz4_rd8<true>(s_in, ip - j) == lz4_rd8<true>(s_in, match - j));
-                    uint32_t b = __ballot_sync(FULL_MASK, ok);
-                    int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
-                    ip -= steps; match -= steps;
+            // ---- catch up (backwards, not after an immediate match) and match length (forwards from ip + 4, up to matchlimit: LZ4_count):
+            //      both first steps are loaded together — one memory latency; the total is back + forward because the bytes in between are
+            //      the match itself
+            int back = 0, mc = 0;
+            {
+                const int j = lane + 1;
+                const bool okb = !immediate && (ip - j >= anchor) && (match - j >= 0) && (lz4_rd8<true>(s_in, ip - j) == lz4_rd8<true>(s_in, match - j));
+                const bool eqf = (ip + LZ4_MINMATCH + lane < matchlimit) && (lz4_rd8<true>(s_in, ip + LZ4_MINMATCH + lane) == lz4_rd8<true>(s_in, match + LZ4_MINMATCH + lane));
+                const uint32_t bb = __ballot_sync(FULL_MASK, okb), bf = __ballot_sync(FULL_MASK, eqf);
+                back = (bb == FULL_MASK) ? 32 : (__ffs(~bb) - 1);
+                mc = (bf == FULL_MASK) ? 32 : (__ffs(~bf) - 1);
+                while (back && !(back & 31)) {                   // every lane matched: keep going, 32 bytes per step
+                    const int jj = back + lane + 1;
+                    const bool ok = (ip - jj >= anchor) && (match - jj >= 0) && (lz4_rd8<true>(s_in, ip - jj) == lz4_rd8<true>(s_in, match - jj));
+                    const uint32_t b = __ballot_sync(FULL_MASK, ok);
+                    const int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
+                    back += steps;
                     if (steps < 32) break;
                 }
+                while (mc && !(mc & 31)) {
+                    const int i = mc + lane;
+                    const bool eq = (ip + LZ4_MINMATCH + i < matchlimit) && (lz4_rd8<true>(s_in, ip + LZ4_MINMATCH + i) == lz4_rd8<true>(s_in, match + LZ4_MINMATCH + i));
+                    const uint32_t b = __ballot_sync(FULL_MASK, eq);
+                    const int steps = (b == FULL_MASK) ? 32 : (__ffs(~b) - 1);
+                    mc += steps;
+                    if (steps < 32) break;
+                }
+            }
+            const int ip_end = ip + LZ4_MINMATCH + mc;         // first byte behind the match
+            ip -= back; match -= back; mc += back;
+
+            int lit_nibble = 0;
+            if (!immediate) {
                 // ---- literals ---------------------------------------------------------------------------------------
                 int lit = ip - anchor;
                 token_pos = op++;
@@ -199,24 +227,14 @@ __device__ int lz4_compress_warp_chain(const uint8_t* s_in, int n, const uint32_
                 lit_nibble = lit < 15 ? lit : 15;
             } else token_pos = op++;                      // immediate match: token with literal length 0
 
-            // ---- the match: offset, length beyond MINMATCH limited by matchlimit (LZ4_count) --------------------------
-            if (lane == 0) { int off = ip - match; out[op] = (uint8_t)off; out[op + 1] = (uint8_t)(off >> 8); }
-            op += 2;
-            int mc = 0;
-            {
-                int pi = ip + LZ4_MINMATCH, pm = match + LZ4_MINMATCH;
-                for (;;) {
-                    int i = mc + lane;
-                    bool eq = (pi + i < matchlimit) && (lz4_rd8<true>(s_in, pi + i) == lz4_rd8<true>(s_in, pm + i));
-                    uint32_t b = __ballot_sync(FULL_MASK, eq);
-                    if (b == FULL_MASK) { mc += 32; continue; }
-                    mc += __ffs(~b) - 1;
-                    break;
-                }
+            // ---- the match: offset, length beyond MINMATCH ------------------------------------------------------------
+            if (lane == 0) {
+                const int off = ip - match; out[op] = (uint8_t)off; out[op + 1] = (uint8_t)(off >> 8);
+                out[token_pos] = (uint8_t)((lit_nibble << 4) | (mc < 15 ? mc : 15));
             }
-            ip += mc + LZ4_MINMATCH;
-            if (lane == 0) out[token_pos] = (uint8_t)((lit_nibble << 4) | (mc < 15 ? mc : 15));
+            op += 2;
             if (mc >= 15) op += lz4_emit_len_ext(out + op, mc - 15, lane);
+            ip = ip_end;
             anchor = ip;
             if (ip >= mfl1) break;
             have_prefix = true; pre_ip = ip; fwd = ip + 1;

@@ -9,6 +9,7 @@
 #include <vector>
 #include <random>
 #include "../../cassandra_b200/csrc/lz4_thread.cuh"
+#include "../../cassandra_b200/csrc/lz4_batch.cuh"      // the walk of the two-pass decoder: same acceptance set, exact-size record buffer
 #include "../../oracle/codec.h"
 
 static std::vector<uint8_t> make_data(std::mt19937_64& rng, int n, int kind) {
@@ -41,6 +42,8 @@ int main(int argc, char** argv) {
             uint8_t* sraw = (uint8_t*)malloc(align + c + 16); uint8_t* src = sraw + align; memcpy(src, comp.data(), c); memset(src + c, 0xEE, 16);
             uint8_t* dst = nullptr; if (posix_memalign((void**)&dst, 8, n + 16 + 8)) return 3;
             memset(dst, 0xCD, n + 16);
+            { const int rc = (c - 1) / 3 + 1; uint16_t* rec = (uint16_t*)malloc(sizeof(uint16_t) * rc); int ns = b200c::lz4_walk_thread(src, c, n, rec, rc);
+              if (ns < 1 || ns > rc) { fprintf(stderr, "WALK refused a valid block it=%d n=%d ns=%d\n", it, n, ns); return 7; } free(rec); }
             int got = b200c::lz4_decompress_thread(src, c, dst, n);
             if (got != n || memcmp(dst, data.data(), n)) { fprintf(stderr, "MISMATCH it=%d n=%d align=%d got=%d\n", it, n, align, got); return 1; }
             ok++;
@@ -53,6 +56,8 @@ int main(int argc, char** argv) {
                 if (m & 1) cc = (int)(rng() % c); else for (int k = 0; k < 1 + (int)(rng() % 3); k++) bad[rng() % c] ^= (uint8_t)(1u << (rng() % 8));
                 uint8_t* braw = (uint8_t*)malloc(align + cc + 16); uint8_t* b = braw + align; if (cc) memcpy(b, bad.data(), cc); memset(b + cc, 0x11, 16);
                 int g3 = b200c::lz4_decompress_thread(b, cc, dst, n);
+                { const int rc = cc > 0 ? (cc - 1) / 3 + 1 : 1; uint16_t* rec = (uint16_t*)malloc(sizeof(uint16_t) * rc); int ns = b200c::lz4_walk_thread(b, cc, n, rec, rc); free(rec);
+                  if ((ns >= 0) != (g3 == n)) { fprintf(stderr, "WALK and decoder disagree it=%d m=%d ns=%d g3=%d n=%d\n", it, m, ns, g3, n); return 8; } }
                 if (g3 > n) { fprintf(stderr, "OVERRUN reported it=%d\n", it); return 5; }
                 if (g3 < 0) rejected++; else survived++;
                 free(braw);

@@ -1,7 +1,8 @@
 """The per-thread LZ4 decoder that K1's thread-per-chunk kernels run (cassandra_b200/csrc/lz4_thread.cuh) is plain C++ compiled for
 host and device. Here the same source is built with g++ -fsanitize=address,undefined and fuzzed against the oracle on the CPU: valid
 blocks at every source alignment must decode exactly; flipped and truncated blocks must fail or stay inside the buffers (+16 bytes of
-slack, as every engine buffer has)."""
+slack, as every engine buffer has). The walk of the two-pass decoder (lz4_batch.cuh) rides along: it must accept exactly the blocks the
+decoder decodes to the expected size, with a record buffer of exactly (n - 1) / 3 + 1 entries."""
 import os, shutil, subprocess, pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

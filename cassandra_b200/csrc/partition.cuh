@@ -187,7 +187,7 @@ typedef CurT<uint32_t, uint16_t, 8> CurS;
 static_assert(sizeof(Cur) == 48 && sizeof(CurS) == 40, "cursor layouts");
 
 // parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
-template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P, CUR& c) {
+template <class CUR> __device__ __forceinline__ int cur_load_body(const CParams& P, CUR& c) {
     int err = 0;
     for (;;) {
         Rd r{P.U, c.pos, c.end, 0};
@@ -242,6 +242,9 @@ template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P,
         return err;
     }
 }
+// The cursor lives in shared memory and most of its fields are bit-fields: parsed into a register copy and written back once (a dozen
+// read-modify-write cycles through a generic pointer otherwise).
+template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P, CUR& cref) { CUR c = cref; const int e = cur_load_body(P, c); cref = c; return e; }
 template <class CUR> __device__ __forceinline__ void cur_load(const CParams& P, CUR& c, int& err) { int e = cur_load_impl(P, c); if (e) err = e; }
 
 // The static row at c.pos, right after the partition deletion (SSTableSimpleIterator.readStaticRow -> UnfilteredSerializer.deserializeStaticRow
@@ -555,11 +558,15 @@ template <bool EMIT> __device__ __noinline__ void write_static(PWriter<EMIT>& w,
     if (info.ttl != 0) flags |= 0x08;
     if (!dt_is_live(del)) flags |= 0x10;
     if (present == P.nstat) flags |= 0x20;
-    Sink<EMIT> cs{nullptr, 0, false, 0};
-    uint64_t body = put_row_body(cs, P, flags, info, del, scells, P.nstat, P.sfix);
+    const uint64_t p0 = w.d.pos;                     // (size field guessed at one byte, see write_row)
+    Sink<EMIT> b = w.d; b.pos = p0 + 2 + 1 + 1;
+    uint64_t end = put_row_body(b, P, flags, info, del, scells, P.nstat, P.sfix);
+    const uint64_t body = end - b.pos;
+    const int vs = vint_size(body + 1);
+    if (vs != 1) { b.pos = p0 + 2 + vs + 1; end = put_row_body(b, P, flags, info, del, scells, P.nstat, P.sfix); }
     w.d.u8(flags); w.d.u8(0x01);
     w.d.vint(body + 1); w.d.vint(0);
-    w.d.pos = put_row_body(w.d, P, flags, info, del, scells, P.nstat, P.sfix);
+    w.d.pos = end;
     if (w.acc) {                                     // SortedTableWriter.addStaticRow :188-197: Rows.collectStats unless the row is empty
         w.acc->live(info); w.acc->dt(del);
         for (int c = 0; c < P.nstat; c++) if (scells[c].present) w.acc->cell(scells[c]);
@@ -585,11 +592,18 @@ template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w,
     if (present == P.ncols) flags |= 0x20;
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
-    Sink<EMIT> cs{nullptr, 0, false, 0};                       // same instantiation as the real sink, stores off: counts the body
-    uint64_t body = put_row_body(cs, P, flags, info, del, cells, P.ncols, P.vfix);
+    // The row size precedes the body it counts. Instead of serialising the body twice (count, then emit) it is emitted once behind a size
+    // field assumed to take one byte — bodies of up to 126 bytes, i.e. nearly all of them — and emitted again only when that guess was wrong.
+    const int vp = vint_size(prev);
+    const uint64_t p0 = w.d.pos;
+    Sink<EMIT> b = w.d; b.pos = p0 + 1 + ck.len + 1 + vp;
+    uint64_t end = put_row_body(b, P, flags, info, del, cells, P.ncols, P.vfix);
+    const uint64_t body = end - b.pos;
+    const int vs = vint_size(body + vp);
+    if (vs != 1) { b.pos = p0 + 1 + ck.len + vs + vp; end = put_row_body(b, P, flags, info, del, cells, P.ncols, P.vfix); }
     w.d.u8(flags); w.d.copy(P.U + ck.off, ck.len);
-    w.d.vint(body + vint_size(prev)); w.d.vint(prev);
-    w.d.pos = put_row_body(w.d, P, flags, info, del, cells, P.ncols, P.vfix);
+    w.d.vint(body + vp); w.d.vint(prev);
+    w.d.pos = end;
     pw_end_unf(w, P, ck, pos);
     if (w.acc) {                                               // Rows.collectStats
         w.acc->live(info); w.acc->dt(del);

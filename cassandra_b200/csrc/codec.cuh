@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "lz4.cuh"
 #include "lz4_chain.cuh"
+#include "snappy_chain.cuh"
 #include "snappy.cuh"
 #include "codec_defs.cuh"
 #include "lz4_thread.cuh"
@@ -136,6 +137,44 @@ __global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_lz4_chain(co
     if (lane == 0) { slot[0] = (uint8_t)ulen; slot[1] = (uint8_t)(ulen >> 8); slot[2] = (uint8_t)(ulen >> 16); slot[3] = (uint8_t)(ulen >> 24); }
     int clen = 4 + lz4_compress_warp_chain(src, ulen, ent + start, s_bits + (size_t)wid * ((chunk_len + 31) >> 5), slot + 4, lane);
     if (clen >= max_clen) {                            // flushData :158-177 — store raw when compression did not help enough
+        for (int i = lane; i < ulen; i += 32) slot[i] = src[i];
+        clen = ulen;
+        if (ulen < max_clen) { for (int i = ulen + lane; i < max_clen; i += 32) slot[i] = 0; clen = max_clen; }
+    }
+    __syncwarp();
+    __threadfence_block();
+    uint32_t raw = warp_crc32_raw(T, T->crc_adv128, slot, clen, lane);
+    uint32_t init = gf2_mulmod(0xFFFFFFFFu, warp_xpow8n(T, (uint32_t)clen, lane));
+    uint32_t crc = ~(raw ^ init);
+    if (lane == 0) {
+        slot[clen] = (uint8_t)(crc >> 24); slot[clen + 1] = (uint8_t)(crc >> 16); slot[clen + 2] = (uint8_t)(crc >> 8); slot[clen + 3] = (uint8_t)crc;
+        file_len[chunk] = (uint32_t)clen + 4;
+        uint32_t x = raw ^ __byte_perm(crc, 0, 0x0123);
+        seg_raw[chunk] = T->crc_t[3][x & 0xff] ^ T->crc_t[2][(x >> 8) & 0xff] ^ T->crc_t[1][(x >> 16) & 0xff] ^ T->crc_t[0][x >> 24];
+    }
+}
+
+// Snappy in two passes (snappy_chain.cuh). dynamic smem of the build pass: 2 tables of table_size u16 + LZ4_DUP_ENTRIES bytes.
+__global__ void __launch_bounds__(32) k_snappy_chain_build(int max_bits, int table_size, const uint8_t* __restrict__ in, uint64_t n, int chunk_len, uint32_t* __restrict__ ent) {
+    extern __shared__ __align__(16) uint8_t smem_sc[];
+    uint16_t* s_t1 = (uint16_t*)smem_sc; uint16_t* s_t2 = s_t1 + table_size; uint8_t* s_dup = (uint8_t*)(s_t2 + table_size);
+    const uint64_t start = (uint64_t)blockIdx.x * (uint64_t)chunk_len;
+    const int ulen = (int)min((uint64_t)chunk_len, n - start);
+    snappy_chain_build_warp(in + start, ulen, max_bits, s_t1, s_t2, s_dup, ent + start, threadIdx.x);
+}
+__global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_snappy_chain(const DevTables* __restrict__ T,
+        const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen, const uint32_t* __restrict__ ent,
+        uint8_t* __restrict__ slots, int slot_stride, uint32_t* __restrict__ file_len, uint32_t* __restrict__ seg_raw, uint64_t nchunks) {
+    extern __shared__ __align__(16) uint32_t s_bits[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t chunk = (uint64_t)blockIdx.x * K5B_WARPS + wid;
+    if (chunk >= nchunks) return;
+    const uint64_t start = chunk * (uint64_t)chunk_len;
+    const int ulen = (int)min((uint64_t)chunk_len, n - start);
+    const uint8_t* src = in + start;
+    uint8_t* slot = slots + chunk * (uint64_t)slot_stride;
+    int clen = snappy_compress_warp_chain(src, ulen, ent + start, s_bits + (size_t)wid * ((chunk_len + 31) >> 5), slot, lane);
+    if (clen >= max_clen) {
         for (int i = lane; i < ulen; i += 32) slot[i] = src[i];
         clen = ulen;
         if (ulen < max_clen) { for (int i = ulen + lane; i < max_clen; i += 32) slot[i] = 0; clen = max_clen; }

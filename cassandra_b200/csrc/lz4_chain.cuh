@@ -34,21 +34,20 @@ enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF };
 __host__ __device__ __forceinline__ int lz4c_positions(int n) { return n >= LZ4_MINLENGTH ? n - LZ4_MFLIMIT + 1 : 0; }
 
 // ---- pass A ---------------------------------------------------------------------------------------------------------------------------
-// s_in: the chunk where it lies in global memory (4-byte aligned, >= n + 8 readable bytes); s_t1 / s_t2: 8192 x u16 each (last and
-// second-to-last position per hash); s_dup: LZ4_DUP_ENTRIES bytes; ent: lz4c_positions(n) words.
-__device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint16_t* s_t2, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+// s_in: the chunk where it lies in global memory (4-byte aligned, >= npos + 7 readable bytes); s_t1 / s_t2: nent x u16 each (last and
+// second-to-last position per hash); s_dup: LZ4_DUP_ENTRIES bytes; ent: npos words. HASH: 4 bytes -> table index (< nent = 1 << hbits).
+template <class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint16_t* s_t2, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     {
         uint4* a = (uint4*)s_t1; uint4* b = (uint4*)s_t2;
-        for (int i = lane; i < (LZ4_TABLE_ENTRIES * 2) / 16; i += 32) { a[i] = make_uint4(~0u, ~0u, ~0u, ~0u); b[i] = make_uint4(~0u, ~0u, ~0u, ~0u); }
+        for (int i = lane; i < (nent * 2) / 16; i += 32) { a[i] = make_uint4(~0u, ~0u, ~0u, ~0u); b[i] = make_uint4(~0u, ~0u, ~0u, ~0u); }
     }
     __syncwarp();
-    const int npos = lz4c_positions(n);
     const uint32_t lt_mask = (1u << lane) - 1u;
     for (int p0 = 0; p0 < npos; p0 += 32) {
         const int p = p0 + lane; const bool valid = p < npos;
         const uint32_t seq = valid ? lz4_rd32<true>(in32, p) : 0u;
-        const uint32_t h = lz4_hash_u16(seq);
+        const uint32_t h = hash(seq);
         const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
         // do two positions of this step share a hash? (see lz4.cuh: one byte per hash slot, the lanes that read back another lane's number share)
         const uint32_t dh = h & (LZ4_DUP_ENTRIES - 1);
@@ -61,8 +60,7 @@ __device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n,
             if (valid) { q1 = s_t1[h]; q2 = s_t2[h]; s_t2[h] = (uint16_t)q1; s_t1[h] = (uint16_t)p; }
         } else {
             uint32_t same = FULL_MASK;
-#pragma unroll
-            for (int b = 0; b < LZ4_HASHLOG_U16; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
+            for (int b = 0; b < hbits; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
             same &= vmask;
             const uint32_t lower = same & lt_mask;
             const int c = __popc(lower);
@@ -84,6 +82,10 @@ __device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n,
             ent[p] = a1 | (e1 << 15) | (a2 << 16) | (e2 << 31);
         }
     }
+}
+struct Lz4Hash { __device__ __forceinline__ uint32_t operator()(uint32_t seq) const { return lz4_hash_u16(seq); } };
+__device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint16_t* s_t2, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+    chain_build_warp(s_in, lz4c_positions(n), LZ4_TABLE_ENTRIES, LZ4_HASHLOG_U16, Lz4Hash(), s_t1, s_t2, s_dup, ent, lane);
 }
 
 // bits [lo, hi) that fall into 32-bit word w of a bitmap

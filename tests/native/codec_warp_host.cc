@@ -25,21 +25,29 @@ static inline unsigned atomicAnd(unsigned* p, unsigned v) { unsigned o = *p; *p 
 #include "../../cassandra_b200/csrc/lz4.cuh"
 #include "../../cassandra_b200/csrc/lz4_chain.cuh"
 #include "../../cassandra_b200/csrc/snappy.cuh"
+#include "../../cassandra_b200/csrc/snappy_chain.cuh"
 
 using namespace b200c;
 
 // mode 0: LZ4, chunk copy in "shared memory"; 1: LZ4 reading the chunk in place (the L1 variant); 2 / 3: Snappy with max_bits 14 / 15;
-// 4: LZ4 in place with the distinct-hash fast path; 7: LZ4 in two passes (lz4_chain.cuh: predecessor links, then the parse over an insertion bitmap)
+// 4: LZ4 in place with the distinct-hash fast path; 7: LZ4 in two passes; 8 / 9: Snappy in two passes (max_bits 14 / 15, chunks up to 32 KiB); [7] (lz4_chain.cuh: predecessor links, then the parse over an insertion bitmap)
 extern "C" int warp_compress(int mode, const uint8_t* in, int n, uint8_t* out) {
     std::vector<uint8_t> s_in((size_t)n + 64, 0); memcpy(s_in.data(), in, n);
     std::vector<uint16_t> tab(1 << 15, 0xDEAD);                       // the kernels zero what they use
     std::vector<uint8_t> dup(LZ4_DUP_ENTRIES, 0xEE);
     std::vector<uint32_t> ent((size_t)n + 64, 0xABABABABu), bm((size_t)n / 32 + 2, 0xCDCDCDCDu);
+    std::vector<uint16_t> tab2(2 << 15, 0xDEAD);
     int result = -1;
     // 4-byte aligned base as the kernel guarantees
     warp_emu::run([&](int lane) {
         int r;
-        if (mode == 7) {
+        if (mode == 8 || mode == 9) {                                        // Snappy in two passes (snappy_chain.cuh), max_bits 14 / 15
+            const int mb = mode == 9 ? 15 : 14;
+            snappy_chain_build_warp(s_in.data(), n, mb, tab2.data(), tab2.data() + (1 << 15), dup.data(), ent.data(), lane);
+            __syncwarp();
+            r = snappy_compress_warp_chain(s_in.data(), n, ent.data(), bm.data(), out, lane);
+        }
+        else if (mode == 7) {
             lz4_chain_build_warp(s_in.data(), n, tab.data(), tab.data() + LZ4_TABLE_ENTRIES, dup.data(), ent.data(), lane);
             __syncwarp();
             r = lz4_compress_warp_chain(s_in.data(), n, ent.data(), bm.data(), out, lane);

@@ -12,7 +12,7 @@ def warp():
     if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"): pytest.skip("needs g++ and the CUDA headers")
     out = os.path.join(ROOT, "tests", "native", "_build", "libcodecwarp.so")
     srcs = [os.path.join(ROOT, "tests", "native", "codec_warp_host.cc")]
-    deps = srcs + [os.path.join(ROOT, "tests", "native", "warp_emu.h")] + [os.path.join(ROOT, "cassandra_b200", "csrc", f) for f in ("lz4.cuh", "lz4_chain.cuh", "snappy.cuh", "common.cuh")]
+    deps = srcs + [os.path.join(ROOT, "tests", "native", "warp_emu.h")] + [os.path.join(ROOT, "cassandra_b200", "csrc", f) for f in ("lz4.cuh", "lz4_chain.cuh", "snappy.cuh", "snappy_chain.cuh", "common.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         r = subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fno-strict-aliasing", "-I/usr/local/cuda/include", "-Wno-attributes", "-Wno-unknown-pragmas",
@@ -45,6 +45,7 @@ def test_snappy_warp_source_equals_googles_library(warp):
     for name, data, want in vectors():
         if not data: continue
         assert run(warp, 3, data) == want, name
+        if len(data) <= 32768: assert run(warp, 9, data) == want, name                           # two passes (snappy_chain.cuh)
         assert run(warp, 6, data) == want, name                                                  # chunk read in place (the L1 variant K5 launches)
         assert run(warp, 2, data) == O.chunk_compress(O.COMP_SNAPPY, data), name
 
@@ -62,6 +63,9 @@ def test_snappy_warp_source_random_differential(warp):
         assert run(warp, 2, d) == O.chunk_compress(O.COMP_SNAPPY, d), (it, n, "2^14")
         assert run(warp, 3, d) == O.chunk_compress(O.COMP_SNAPPY15, d), (it, n, "2^15")
         assert run(warp, 5, d) == O.chunk_compress(O.COMP_SNAPPY, d), (it, n, "2^14 in place")
+        if n <= 32768:
+            assert run(warp, 8, d) == O.chunk_compress(O.COMP_SNAPPY, d), (it, n, "2^14 two passes")
+            assert run(warp, 9, d) == O.chunk_compress(O.COMP_SNAPPY15, d), (it, n, "2^15 two passes")
 
 def test_lz4_chain_random_differential(warp):
     """lz4_chain.cuh (mode 7) against the oracle on the shapes that stress what it changed: incompressible data (accelerated, non-contiguous search

@@ -1414,6 +1414,11 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             cudaFuncSetAttribute(k_partition_thr<8, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
             cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
             cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            // B200C_K4_CARVEOUT=percent of the SM's unified L1/shared memory left to shared memory (A/B: fewer resident blocks, more L1 for the
+            // scattered reads of Data.db); unset: the driver sizes the carve-out for the most blocks that fit
+            if (const char* e = getenv("B200C_K4_CARVEOUT")) { const int pct = atoi(e);
+                cudaFuncSetAttribute(k_partition_thr<8, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+                cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
             c->k4_attr_set = (int)(smem8 + 1);
         }
         uint8_t* SCRATCH = nullptr;

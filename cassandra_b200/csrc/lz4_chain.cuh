@@ -22,7 +22,7 @@
 
 namespace b200c {
 
-enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF };
+enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF, LZ4C_DUP_ENTRIES = 8192 };      // dup table: one byte per LZ4 hash (no false sharing)
 
 #if defined(__CUDA_ARCH__)
 #define LZ4C_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
@@ -33,7 +33,7 @@ enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF };
 // number of positions that can ever be looked up or inserted: search attempts and the post-match test stay below mflimitPlusOne = n - 11
 __host__ __device__ __forceinline__ int lz4c_positions(int n) { return n >= LZ4_MINLENGTH ? n - LZ4_MFLIMIT + 1 : 0; }
 
-// ---- pass A ---------------------------------------------------------------------------------------------------------------------------
+// ---- pass A  (s_dup: LZ4C_DUP_ENTRIES bytes) ---------------------------------------------------------------------------------------------------------------------------
 // s_in: the chunk where it lies in global memory (4-byte aligned, >= npos + 7 readable bytes); s_t1 / s_t2: nent x u16 each (last and
 // second-to-last position per hash); s_dup: LZ4_DUP_ENTRIES bytes; ent: npos words. HASH: 4 bytes -> table index (< nent = 1 << hbits).
 template <class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint16_t* s_t2, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
@@ -50,7 +50,7 @@ template <class HASH> __device__ __forceinline__ void chain_build_warp(const uin
         const uint32_t h = hash(seq);
         const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
         // do two positions of this step share a hash? (see lz4.cuh: one byte per hash slot, the lanes that read back another lane's number share)
-        const uint32_t dh = h & (LZ4_DUP_ENTRIES - 1);
+        const uint32_t dh = h & (LZ4C_DUP_ENTRIES - 1);
         if (valid) s_dup[dh] = (uint8_t)lane;
         __syncwarp();
         const bool shared = valid && s_dup[dh] != (uint8_t)lane;
@@ -146,16 +146,21 @@ __device__ int lz4_compress_warp_chain(const uint8_t* s_in, int n, const uint32_
                 uint32_t hits = __ballot_sync(FULL_MASK, hit);
                 const uint32_t dmask = __ballot_sync(FULL_MASK, deeper);
                 if (dmask) {
-                    const int first_deep = __ffs(dmask) - 1, sure = hits ? (__ffs(hits) - 1) : 32;
-                    if (first_deep < sure && first_deep < first_inv) {
-                        // further down the chain decides (one lookup in forty goes this deep): follow the first-level links, then compare the bytes
-                        int q = q2;
+                    // further down the chain (one lookup in forty goes this deep): follow the first-level links, then compare the bytes. Only
+                    // lanes in front of the first hit known so far can decide the window — the speculated lanes behind a hit sit INSIDE the
+                    // match that follows, exactly the positions whose hash chains are longest (hundreds of never-inserted predecessors)
+                    int limit = hits ? (__ffs(hits) - 1) : 32; if (first_inv < limit) limit = first_inv;
+                    if ((int)(__ffs(dmask) - 1) < limit) {
+                        bool walking = deeper; int q = q2;
                         for (;;) {
-                            const bool go = deeper && !((contiguous && q >= w_lo && q != hole) || ((s_bm[q >> 5] >> (q & 31)) & 1u));
-                            if (!__any_sync(FULL_MASK, go)) break;
-                            if (go) q = (int)(ent[q] & 0x7FFFu);
+                            walking = walking && lane < limit;
+                            const bool ins = walking && ((contiguous && q >= w_lo && q != hole) || ((s_bm[q >> 5] >> (q & 31)) & 1u));
+                            if (ins) { walking = false; cand = q; hit = !putonly && (lz4_rd32<true>(in32, q) == lz4_rd32<true>(in32, p)); }
+                            const uint32_t nh = __ballot_sync(FULL_MASK, ins && hit);
+                            if (nh && (int)(__ffs(nh) - 1) < limit) limit = __ffs(nh) - 1;
+                            if (!__any_sync(FULL_MASK, walking && lane < limit)) break;
+                            if (walking && lane < limit) q = (int)(ent[q] & 0x7FFFu);
                         }
-                        if (deeper) { cand = q; hit = !putonly && (lz4_rd32<true>(in32, q) == lz4_rd32<true>(in32, p)); }
                         hits = __ballot_sync(FULL_MASK, hit);
                     }
                 }

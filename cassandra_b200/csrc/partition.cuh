@@ -82,6 +82,7 @@ __device__ __noinline__ void vint_store(uint8_t* dst, uint64_t v, int size) {
     if (size == 1) { dst[0] = (uint8_t)v; return; }
     if (size < 9) {
         uint64_t reg = (v << ((8 - size) << 3)) | ((uint64_t)(uint8_t)(~(0xffu >> (size - 1))) << 56);
+#pragma unroll 1
         for (int i = 0; i < size; i++) dst[i] = (uint8_t)(reg >> (56 - 8 * i));
         return;
     }
@@ -91,6 +92,7 @@ __device__ __noinline__ void bytes_copy(uint8_t* dst, const uint8_t* src, uint32
     for (uint32_t i = 0; i < n; i += 8) {                // one wide (unaligned) load per 8 bytes, byte stores
         uint64_t x = load_be64(src + i);
         uint32_t k = n - i < 8 ? n - i : 8;
+#pragma unroll 1
         for (uint32_t b = 0; b < k; b++) dst[i + b] = (uint8_t)(x >> (56 - 8 * b));
     }
 }
@@ -112,23 +114,32 @@ __device__ __noinline__ VintR vint_decode(const uint8_t* p, uint32_t avail) {   
     r.v = (x >> (8 * (7 - extra))) & ((1ull << nbits) - 1ull); r.n = 1 + extra;
     return r;
 }
+// value and position behind it; np == ~0: the vint runs past `end` (every buffer the reader walks has >= 16 bytes of slack behind it: one unaligned 8-byte fetch)
+struct VintP { uint64_t v, np; };
+__device__ __noinline__ VintP rd_vint_fn(const uint8_t* U, uint64_t p, uint64_t end) {
+    VintP r; r.v = 0; r.np = ~0ull;
+    if (p >= end) return r;
+    const uint64_t x = load_be64(U + p);
+    const uint32_t first = (uint32_t)(x >> 56);
+    if (first < 0x80) { r.v = first; r.np = p + 1; return r; }
+    const uint32_t extra = __clz((int)(~(first << 24)));                       // leading one bits = extra bytes (8 for 0xFF)
+    if (end - p < 1 + (uint64_t)extra) return r;
+    if (extra == 8) r.v = (x << 8) | U[p + 8];
+    else r.v = (x >> (8 * (7 - extra))) & ((1ull << (8 + 7 * extra)) - 1ull);
+    r.np = p + 1 + extra;
+    return r;
+}
 struct Rd {
     const uint8_t* U; uint64_t p, end; int err;
     __device__ __forceinline__ uint32_t u8() { if (p >= end) { err = PERR_CORRUPT; return 1; } return U[p++]; }
     __device__ __forceinline__ uint32_t be16() { uint32_t a = u8(); return (a << 8) | u8(); }
-    // VIntCoding.readUnsignedVInt (S/utils/vint/VIntCoding.java:66-98), inline: one unaligned 8-byte fetch (every buffer the reader walks has
-    // >= 16 bytes of slack behind it), the 1-byte case — most sizes, flags-like fields and small deltas — leaves after three instructions
+    // VIntCoding.readUnsignedVInt (S/utils/vint/VIntCoding.java:66-98). ONE out-of-line copy (rd_vint_fn): this reader is used at ~40 places of
+    // the per-partition code; inlined, its copies alone were a quarter of the instructions the hot loop touches, and the kernel's hot code
+    // (42 KB at 95 % of the executed instructions) did not fit the 32 KB instruction cache — ncu: "no instruction" was the top stall reason.
     __device__ __forceinline__ uint64_t vint() {
-        if (p >= end) { err = PERR_CORRUPT; p = end; return 0; }
-        const uint64_t x = load_be64(U + p);
-        const uint32_t first = (uint32_t)(x >> 56);
-        if (first < 0x80) { p++; return first; }
-        const uint32_t extra = __clz((int)(~(first << 24)));                       // leading one bits = extra bytes (8 for 0xFF)
-        if (end - p < 1 + (uint64_t)extra) { err = PERR_CORRUPT; p = end; return 0; }
-        uint64_t v;
-        if (extra == 8) v = (x << 8) | U[p + 8];
-        else v = (x >> (8 * (7 - extra))) & ((1ull << (8 + 7 * extra)) - 1ull);
-        p += 1 + extra; return v;
+        const VintP r = rd_vint_fn(U, p, end);
+        if (r.np == ~0ull) { err = PERR_CORRUPT; p = end; return 0; }
+        p = r.np; return r.v;
     }
     __device__ __forceinline__ int32_t vint32() { uint64_t v = vint(); int32_t r = (int32_t)v; if ((int64_t)r != (int64_t)v) err = PERR_CORRUPT; return r; }
     __device__ __forceinline__ void skip(uint64_t n) { if (end - p < n) { err = PERR_CORRUPT; p = end; } else p += n; }
@@ -187,7 +198,7 @@ typedef CurT<uint32_t, uint16_t, 8> CurS;
 static_assert(sizeof(Cur) == 48 && sizeof(CurS) == 40, "cursor layouts");
 
 // parses the unfiltered header at c.pos (skipping empty rows: UnfilteredSerializer.deserialize :433-447)
-template <class CUR> __device__ __forceinline__ int cur_load_body(const CParams& P, CUR& c) {
+template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P, CUR& c) {
     int err = 0;
     for (;;) {
         Rd r{P.U, c.pos, c.end, 0};
@@ -242,9 +253,6 @@ template <class CUR> __device__ __forceinline__ int cur_load_body(const CParams&
         return err;
     }
 }
-// The cursor lives in shared memory and most of its fields are bit-fields: parsed into a register copy and written back once (a dozen
-// read-modify-write cycles through a generic pointer otherwise).
-template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P, CUR& cref) { CUR c = cref; const int e = cur_load_body(P, c); cref = c; return e; }
 template <class CUR> __device__ __forceinline__ void cur_load(const CParams& P, CUR& c, int& err) { int e = cur_load_impl(P, c); if (e) err = e; }
 
 // The static row at c.pos, right after the partition deletion (SSTableSimpleIterator.readStaticRow -> UnfilteredSerializer.deserializeStaticRow

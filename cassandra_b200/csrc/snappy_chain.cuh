@@ -75,16 +75,19 @@ __device__ int snappy_compress_warp_chain(const uint8_t* s_in, int n, const uint
                 const bool deeper = valid && !ins1 && !ins2;
                 uint32_t hits = __ballot_sync(FULL_MASK, hit);
                 const uint32_t dmask = __ballot_sync(FULL_MASK, deeper);
-                if (dmask) {
-                    const int first_deep = __ffs(dmask) - 1, sure = hits ? (__ffs(hits) - 1) : 32;
-                    if (first_deep < sure && first_deep < first_inv) {
-                        int c = q2;
+                if (dmask) {                                          // (see lz4_chain.cuh: only lanes in front of the first known hit walk)
+                    int limit = hits ? (__ffs(hits) - 1) : 32; if (first_inv < limit) limit = first_inv;
+                    if ((int)(__ffs(dmask) - 1) < limit) {
+                        bool walking = deeper; int c = q2;
                         for (;;) {
-                            const bool go = deeper && !((contiguous && c >= w_lo) || ((s_bm[c >> 5] >> (c & 31)) & 1u));
-                            if (!__any_sync(FULL_MASK, go)) break;
-                            if (go) c = (int)(ent[c] & 0x7FFFu);
+                            walking = walking && lane < limit;
+                            const bool ins = walking && ((contiguous && c >= w_lo) || ((s_bm[c >> 5] >> (c & 31)) & 1u));
+                            if (ins) { walking = false; cand = c; hit = !putonly && (lz4_rd32<true>(in32, c) == lz4_rd32<true>(in32, q)); }
+                            const uint32_t nh = __ballot_sync(FULL_MASK, ins && hit);
+                            if (nh && (int)(__ffs(nh) - 1) < limit) limit = __ffs(nh) - 1;
+                            if (!__any_sync(FULL_MASK, walking && lane < limit)) break;
+                            if (walking && lane < limit) c = (int)(ent[c] & 0x7FFFu);
                         }
-                        if (deeper) { cand = c; hit = !putonly && (lz4_rd32<true>(in32, c) == lz4_rd32<true>(in32, q)); }
                         hits = __ballot_sync(FULL_MASK, hit);
                     }
                 }

@@ -34,7 +34,7 @@ using namespace b200c;
 extern "C" int warp_compress(int mode, const uint8_t* in, int n, uint8_t* out) {
     std::vector<uint8_t> s_in((size_t)n + 64, 0); memcpy(s_in.data(), in, n);
     std::vector<uint16_t> tab(1 << 15, 0xDEAD);                       // the kernels zero what they use
-    std::vector<uint8_t> dup(LZ4_DUP_ENTRIES, 0xEE);
+    std::vector<uint8_t> dup(8192, 0xEE);
     std::vector<uint32_t> ent((size_t)n + 64, 0xABABABABu), bm((size_t)n / 32 + 2, 0xCDCDCDCDu);
     std::vector<uint16_t> tab2(2 << 15, 0xDEAD);
     int result = -1;

@@ -116,11 +116,10 @@ __global__ void __launch_bounds__(32) k_compress_chunks_lz4_direct(const DevTabl
 // instead of the 16 KiB table, so residency is set by registers, not by shared memory. ent: one word per byte of the stream.
 __global__ void __launch_bounds__(32) k_lz4_chain_build(const uint8_t* __restrict__ in, uint64_t n, int chunk_len, uint32_t* __restrict__ ent) {
     __shared__ __align__(16) uint16_t s_t1[LZ4_TABLE_ENTRIES];
-    __shared__ __align__(16) uint16_t s_t2[LZ4_TABLE_ENTRIES];
     __shared__ uint8_t s_dup[LZ4C_DUP_ENTRIES];
     const uint64_t start = (uint64_t)blockIdx.x * (uint64_t)chunk_len;
     const int ulen = (int)min((uint64_t)chunk_len, n - start);
-    lz4_chain_build_warp(in + start, ulen, s_t1, s_t2, s_dup, ent + start, threadIdx.x);
+    lz4_chain_build_warp(in + start, ulen, s_t1, s_dup, ent + start, threadIdx.x);
 }
 enum { K5B_WARPS = 4 };
 __global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_lz4_chain(const DevTables* __restrict__ T,
@@ -154,13 +153,13 @@ __global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_lz4_chain(co
     }
 }
 
-// Snappy in two passes (snappy_chain.cuh). dynamic smem of the build pass: 2 tables of table_size u16 + LZ4C_DUP_ENTRIES bytes.
+// Snappy in two passes (snappy_chain.cuh). dynamic smem of the build pass: one table of table_size u16 + LZ4C_DUP_ENTRIES bytes.
 __global__ void __launch_bounds__(32) k_snappy_chain_build(int max_bits, int table_size, const uint8_t* __restrict__ in, uint64_t n, int chunk_len, uint32_t* __restrict__ ent) {
     extern __shared__ __align__(16) uint8_t smem_sc[];
-    uint16_t* s_t1 = (uint16_t*)smem_sc; uint16_t* s_t2 = s_t1 + table_size; uint8_t* s_dup = (uint8_t*)(s_t2 + table_size);
+    uint16_t* s_t1 = (uint16_t*)smem_sc; uint8_t* s_dup = (uint8_t*)(s_t1 + table_size);
     const uint64_t start = (uint64_t)blockIdx.x * (uint64_t)chunk_len;
     const int ulen = (int)min((uint64_t)chunk_len, n - start);
-    snappy_chain_build_warp(in + start, ulen, max_bits, s_t1, s_t2, s_dup, ent + start, threadIdx.x);
+    snappy_chain_build_warp(in + start, ulen, max_bits, s_t1, s_dup, ent + start, threadIdx.x);
 }
 __global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_snappy_chain(const DevTables* __restrict__ T,
         const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen, const uint32_t* __restrict__ ent,

@@ -34,58 +34,66 @@ enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF, LZ4C_DUP_ENTRIES = 8192 };   
 __host__ __device__ __forceinline__ int lz4c_positions(int n) { return n >= LZ4_MINLENGTH ? n - LZ4_MFLIMIT + 1 : 0; }
 
 // ---- pass A  (s_dup: LZ4C_DUP_ENTRIES bytes) ---------------------------------------------------------------------------------------------------------------------------
-// s_in: the chunk where it lies in global memory (4-byte aligned, >= npos + 7 readable bytes); s_t1 / s_t2: nent x u16 each (last and
-// second-to-last position per hash); s_dup: LZ4_DUP_ENTRIES bytes; ent: npos words. HASH: 4 bytes -> table index (< nent = 1 << hbits).
-template <class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint16_t* s_t2, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+// s_in: the chunk where it lies in global memory (4-byte aligned, >= npos + 7 readable bytes); s_t1: nent x u16 (last position per hash);
+// s_dup: LZ4C_DUP_ENTRIES bytes; ent: npos words. HASH: 4 bytes -> table index (< nent = 1 << hbits).
+template <class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     {
-        uint4* a = (uint4*)s_t1; uint4* b = (uint4*)s_t2;
-        for (int i = lane; i < (nent * 2) / 16; i += 32) { a[i] = make_uint4(~0u, ~0u, ~0u, ~0u); b[i] = make_uint4(~0u, ~0u, ~0u, ~0u); }
+        uint4* a = (uint4*)s_t1;
+        for (int i = lane; i < (nent * 2) / 16; i += 32) a[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
     __syncwarp();
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // ---- phase 1 (sequential in the table): nearest earlier position with the same hash. The 4 bytes of the NEXT step are fetched before this
+    //      step's table work, so the only chain between steps is the table itself.
+    uint32_t seq_next = lane < npos ? lz4_rd32<true>(in32, lane) : 0u;
     for (int p0 = 0; p0 < npos; p0 += 32) {
         const int p = p0 + lane; const bool valid = p < npos;
-        const uint32_t seq = valid ? lz4_rd32<true>(in32, p) : 0u;
+        const uint32_t seq = seq_next;
+        seq_next = (p + 32 < npos) ? lz4_rd32<true>(in32, p + 32) : 0u;
         const uint32_t h = hash(seq);
-        const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
         // do two positions of this step share a hash? (see lz4.cuh: one byte per hash slot, the lanes that read back another lane's number share)
         const uint32_t dh = h & (LZ4C_DUP_ENTRIES - 1);
         if (valid) s_dup[dh] = (uint8_t)lane;
         __syncwarp();
         const bool shared = valid && s_dup[dh] != (uint8_t)lane;
         const bool unique = !__any_sync(FULL_MASK, shared);
-        uint32_t q1 = LZ4C_NONE, q2 = LZ4C_NONE;
+        uint32_t q1 = LZ4C_NONE;
         if (unique) {
-            if (valid) { q1 = s_t1[h]; q2 = s_t2[h]; s_t2[h] = (uint16_t)q1; s_t1[h] = (uint16_t)p; }
+            if (valid) { q1 = s_t1[h]; s_t1[h] = (uint16_t)p; }
         } else {
+            const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
             uint32_t same = FULL_MASK;
             for (int b = 0; b < hbits; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
             same &= vmask;
             const uint32_t lower = same & lt_mask;
-            const int c = __popc(lower);
-            const uint32_t t1 = valid ? s_t1[h] : LZ4C_NONE, t2 = valid ? s_t2[h] : LZ4C_NONE;
-            if (c >= 1) {
-                const int l1 = 31 - __clz(lower);
-                q1 = (uint32_t)(p0 + l1);
-                const uint32_t rest = lower & ~(1u << l1);
-                q2 = rest ? (uint32_t)(p0 + 31 - __clz(rest)) : t1;
-            } else { q1 = t1; q2 = t2; }
-            __syncwarp();                                          // every lane has read the tables
+            q1 = lower ? (uint32_t)(p0 + 31 - __clz(lower)) : (valid ? (uint32_t)s_t1[h] : (uint32_t)LZ4C_NONE);
+            __syncwarp();                                          // every lane has read the table
             const uint32_t higher = same & ~lt_mask & ~(1u << lane);
-            if (valid && !higher) { s_t1[h] = (uint16_t)p; s_t2[h] = (uint16_t)q1; }
+            if (valid && !higher) s_t1[h] = (uint16_t)p;
         }
         __syncwarp();
-        const uint32_t a1 = q1 == LZ4C_NONE ? 0u : q1, a2 = q2 == LZ4C_NONE ? 0u : q2;
         if (valid) {
-            const uint32_t e1 = lz4_rd32<true>(in32, (int)a1) == seq, e2 = lz4_rd32<true>(in32, (int)a2) == seq;
-            ent[p] = a1 | (e1 << 15) | (a2 << 16) | (e2 << 31);
+            const uint32_t a1 = q1 == LZ4C_NONE ? 0u : q1;
+            const uint32_t e1 = lz4_rd32<true>(in32, (int)a1) == seq;
+            ent[p] = a1 | (e1 << 15);
+        }
+    }
+    __syncwarp();
+    // ---- phase 2 (parallel): the predecessor's predecessor and its equality bit; position 0 ends every chain (its own link is 0)
+    for (int p0 = 0; p0 < npos; p0 += 32) {
+        const int p = p0 + lane;
+        if (p < npos) {
+            const uint32_t e = ent[p];
+            const uint32_t a2 = ent[e & 0x7FFFu] & 0x7FFFu;
+            const uint32_t e2 = lz4_rd32<true>(in32, (int)a2) == lz4_rd32<true>(in32, p);
+            ent[p] = (e & 0xFFFFu) | (a2 << 16) | (e2 << 31);
         }
     }
 }
 struct Lz4Hash { __device__ __forceinline__ uint32_t operator()(uint32_t seq) const { return lz4_hash_u16(seq); } };
-__device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint16_t* s_t2, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
-    chain_build_warp(s_in, lz4c_positions(n), LZ4_TABLE_ENTRIES, LZ4_HASHLOG_U16, Lz4Hash(), s_t1, s_t2, s_dup, ent, lane);
+__device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+    chain_build_warp(s_in, lz4c_positions(n), LZ4_TABLE_ENTRIES, LZ4_HASHLOG_U16, Lz4Hash(), s_t1, s_dup, ent, lane);
 }
 
 // bits [lo, hi) that fall into 32-bit word w of a bitmap

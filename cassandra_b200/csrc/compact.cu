@@ -127,6 +127,17 @@ __host__ __device__ inline bool compute_index_slice(const uint8_t* index, uint64
     }
     return true;
 }
+// data position stored in the Index.db entry at `off` (u16 keyLen | key | vint position | ...)
+__host__ __device__ inline bool entry_data_position(const uint8_t* index, uint64_t ilen, uint64_t off, uint64_t data_length, uint64_t* pos_out) {
+    if (off + 2 > ilen) return false;
+    const uint32_t kl = ((uint32_t)index[off] << 8) | index[off + 1]; off += 2 + kl;
+    if (off >= ilen) return false;
+    const uint32_t f = index[off]; uint64_t pos;
+    if (f < 0x80) pos = f;
+    else { int extra = 0; for (uint32_t x = f; x & 0x80; x <<= 1) extra++; if (extra > 8) extra = 8; if (off + extra >= ilen) return false; pos = extra == 8 ? 0 : (f & (0xFFu >> extra)); for (int k = 1; k <= extra; k++) pos = (pos << 8) | index[off + k]; }
+    if (pos > data_length) return false;
+    *pos_out = pos; return true;
+}
 __global__ void k_index_slices(const uint8_t* const* __restrict__ index, const uint64_t* __restrict__ ilen, const uint64_t* const* __restrict__ summ, const uint64_t* __restrict__ ns,
                                const uint64_t* __restrict__ dlen, int K, int partitioner, int64_t tlo, int64_t thi, IdxSlice* __restrict__ out, uint32_t* __restrict__ ok) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -943,7 +954,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     }
     ubase[K] = uo; ibase[K] = io; cbase[K] = co; obase[K] = oo; bbase[K] = bo;
     if (uo >= (1ull << 40)) { c->err = "decompressed inputs of 1 TiB or more per call"; return B200C_EUNSUPPORTED; }      // stream offsets are 40-bit in the K4 cursors
-    const uint64_t nblocks = bo;
+    (void)bo;
     hp.ninputs = K; hp.nclust = m->nclustering; hp.ncols = m->ncolumns; hp.column_index_size = m->column_index_size > 0 ? m->column_index_size : 65536;
     for (int k = 0; k < m->nclustering; k++) { hp.ctype[k] = m->clustering[k].type; hp.cfix[k] = m->clustering[k].fixed_len; }
     for (int k = 0; k < m->ncolumns; k++) hp.vfix[k] = m->columns[k].fixed_len;
@@ -974,15 +985,63 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // Device-resident inputs take the same route when the call is a token sub-range: K2 first, then only the chunks the range crosses are decoded.
     const bool deferred = !lcs && have_summaries && (!dev || sliced);
     if (!deferred) { want_ranges = 1; cuts.clear(); }
-
+    // Index.db streaming (host buffers, several pieces): the pieces are cut on the HOST, at tokens of Summary.db samples of the input with the
+    // most samples, and every piece brings its own Index.db slices (the samples bracketing its token range, as a ranged scanner would seek),
+    // its Summary positions and its Data.db chunks. K2 runs per piece: nothing waits for the whole Index.db (4.3 GB = 80 ms of PCIe on
+    // configs[1]) any more, and the per-partition arrays are piece sized.
+    std::vector<int64_t> T{m->token_lo, m->token_hi};
+    std::vector<std::vector<IdxSlice>> psl(1, isl);                 // per piece and input: Index.db slice ...
+    std::vector<uint64_t> pustart((size_t)K, 0);                    // ... and where the Data.db bytes its entries describe start ([ustart, slice.uend))
+    bool istream = false;
+    if (deferred && !dev && want_ranges > 1) {
+        // Summary.db is a hint here as everywhere: if its positions do not parse or the slices they give do not tile the call's own
+        // slice, the call runs as one piece (K2 over the whole Index.db, as before)
+        auto plan = [&]() -> bool {
+            int imax = 0; uint64_t nmax = 0;
+            for (int i = 0; i < K; i++) if (isl[i].s_count > nmax) { nmax = isl[i].s_count; imax = i; }
+            if (nmax < (uint64_t)want_ranges * (forced_ranges ? 1 : 32)) return false;
+            const b200c_input& big = m->inputs[imax];
+            std::vector<int64_t> t2{m->token_lo};
+            for (int r = 1; r < want_ranges; r++) {
+                const uint64_t sidx = isl[imax].s_first + std::min<uint64_t>(nmax - 1, (uint64_t)(nmax * cuts[r - 1]));
+                int64_t t = 0;
+                if (!sample_token(big.index, big.index_len, big.summary_positions[sidx], m->partitioner, &t)) return false;
+                if (t > t2.back() && t < m->token_hi) t2.push_back(t);
+            }
+            t2.push_back(m->token_hi);
+            const int n2 = (int)t2.size() - 1;
+            if (n2 < 2) return false;
+            std::vector<std::vector<IdxSlice>> p2(n2, isl); std::vector<uint64_t> u2((size_t)n2 * K, 0);
+            for (int r = 0; r < n2; r++) for (int i = 0; i < K; i++) {
+                const b200c_input& in = m->inputs[i];
+                IdxSlice& sl = p2[r][i];
+                if (!in.index_len) { sl = IdxSlice{0, 0, in.data_length, 0, 0}; u2[(size_t)r * K + i] = in.data_length; continue; }
+                if (!compute_index_slice(in.index, in.index_len, in.summary_positions, in.nsummary, in.data_length, m->partitioner, t2[r], t2[r + 1], &sl)) return false;
+                // every entry must lie in some piece's slice: consecutive slices touch or overlap, the first starts and the last ends with the call's own
+                if (r == 0 && sl.lo != isl[i].lo) return false;
+                if (r == n2 - 1 && sl.hi != isl[i].hi) return false;
+                if (r > 0 && (sl.lo > p2[r - 1][i].hi || sl.lo < p2[r - 1][i].lo || sl.hi < p2[r - 1][i].hi)) return false;
+                uint64_t pos = sl.uend;
+                if (sl.hi > sl.lo && !entry_data_position(in.index, in.index_len, sl.lo, in.data_length, &pos)) return false;
+                if (pos > sl.uend) return false;
+                u2[(size_t)r * K + i] = pos;
+            }
+            T = t2; psl = p2; pustart = u2;
+            return true;
+        };
+        istream = plan();
+    }
+    const int nr = (int)T.size() - 1;
     uint8_t *U, *CD, *IDX; uint64_t* CO; CParams* dP; uint64_t* d_bbase; DevErr* d_err; ChunkErr* d_cerr; RunStats* d_stats; unsigned long long* d_hist;
     B200C_TRY(ws_typed(c, WS_U, uo + 64, &U));
     B200C_TRY(ws_typed(c, WS_CD, co + 64, &CD));
     B200C_TRY(ws_typed(c, WS_CO, oo + 1, &CO));
     B200C_TRY(ws_typed(c, WS_IDX, io + 64, &IDX));
-    std::vector<uint64_t> sbase(K + 1, 0);
-    for (int i = 0; i < K; i++) sbase[i + 1] = sbase[i] + isl[i].s_count;
-    uint64_t* d_summ; B200C_TRY(ws_typed(c, WS_SUMM, sbase[K] + 1, &d_summ));
+    // Summary.db positions on the device: one run per piece and input (slice relative)
+    std::vector<std::vector<uint64_t>> psb(nr, std::vector<uint64_t>(K + 1, 0));
+    uint64_t summ_total = 0;
+    for (int r = 0; r < nr; r++) for (int i = 0; i <= K; i++) { psb[r][i] = summ_total; if (i < K) summ_total += psl[r][i].s_count; }
+    uint64_t* d_summ; B200C_TRY(ws_typed(c, WS_SUMM, summ_total + 1, &d_summ));
     { uint8_t* pp; B200C_TRY(ws_typed(c, WS_PARAMS, sizeof(CParams) + sizeof(InDesc) * (size_t)K, &pp)); dP = (CParams*)pp; hp.in = (const InDesc*)(pp + sizeof(CParams)); }
     B200C_TRY(ws_typed(c, WS_BBASE, (size_t)K + 1, &d_bbase));
     { uint8_t* p; B200C_TRY(ws_typed(c, WS_ERR2, 4096, &p)); d_err = (DevErr*)p; d_cerr = (ChunkErr*)(p + 64); d_stats = (RunStats*)(p + 128); d_hist = (unsigned long long*)(p + 256); }
@@ -1044,20 +1103,59 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (hi > lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i] + lo, in.data + lo, hi - lo, kind, cs));
         return B200C_OK;
     };
+    // what each piece needs from each input: chunks to copy (deferred mode) and to decompress
+    struct Need { uint64_t h2d_a, h2d_b, k1_a, k1_b; };
+    std::vector<Need> need((size_t)nr * K, Need{0, 0, 0, 0});
+    std::vector<uint64_t> range_bytes(nr, 0);
+    std::vector<uint64_t> range_end((size_t)nr * K, 0);          // per piece and input: Data.db position behind the piece (scanner accounting)
+    for (int i = 0; i < K; i++) { bytes_read += m->inputs[i].data_length; range_end[(size_t)(nr - 1) * K + i] = m->inputs[i].data_length; }
+    for (int r = 0; r < nr; r++) range_bytes[r] = bytes_read;
+    auto need_of = [&](int r, int i, uint64_t a, uint64_t b) {      // piece r reads bytes [a, b) of input i's decompressed stream
+        const b200c_input& in = m->inputs[i];
+        range_end[(size_t)r * K + i] = b;
+        Need& nd = need[(size_t)r * K + i];
+        if (b > a) {
+            uint64_t ca = a / in.chunk_len, cb = std::min<uint64_t>(in.nchunks, (b + in.chunk_len - 1) / in.chunk_len);
+            nd.h2d_a = std::max(ca, h2d_next[i]); nd.h2d_b = std::max(cb, nd.h2d_a); h2d_next[i] = nd.h2d_b;
+            nd.k1_a = std::max(ca, k1_next[i]); nd.k1_b = std::max(cb, nd.k1_a); k1_next[i] = nd.k1_b;
+        }
+    };
     for (int i = 0; i < K; i++) {
         const b200c_input& in = m->inputs[i];
-        bytes_read += in.data_length;
         if (!deferred && in.data_len) B200C_CUDA_TRY(c, cudaMemcpyAsync(CD + cbase[i], in.data, in.data_len, kind, cs));
         if (in.nchunks) B200C_CUDA_TRY(c, cudaMemcpyAsync(CO + obase[i], in.chunk_offsets, in.nchunks * 8, kind, cs));
-        if (isl[i].hi > isl[i].lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index + isl[i].lo, isl[i].hi - isl[i].lo, kind, cs));
-        if (isl[i].s_count) {
-            B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + sbase[i], in.summary_positions + isl[i].s_first, isl[i].s_count * 8, kind, cs));
-            if (isl[i].lo) { k_add_u64<<<(unsigned)((isl[i].s_count + 255) / 256), 256, 0, cs>>>(d_summ + sbase[i], isl[i].s_count, (uint64_t)0 - isl[i].lo); c->launches_call++; c->launches_total++; }   // positions relative to the slice
+        if (!istream) {
+            if (isl[i].hi > isl[i].lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index + isl[i].lo, isl[i].hi - isl[i].lo, kind, cs));
+            if (isl[i].s_count) {
+                B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + psb[0][i], in.summary_positions + isl[i].s_first, isl[i].s_count * 8, kind, cs));
+                if (isl[i].lo) { k_add_u64<<<(unsigned)((isl[i].s_count + 255) / 256), 256, 0, cs>>>(d_summ + psb[0][i], isl[i].s_count, (uint64_t)0 - isl[i].lo); c->launches_call++; c->launches_total++; }   // positions relative to the slice
+            }
         }
         B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[i], cs));
     }
-    if (deferred && want_ranges > 1 && !sliced)         // keep the link busy while K2 finishes: the head of every Data.db is needed by the first piece
-        for (int i = 0; i < K; i++) { uint64_t pre = (uint64_t)(m->inputs[i].nchunks * cuts[0]); B200C_TRY(copy_chunks(i, 0, pre)); h2d_next[i] = pre; }
+    if (istream) {
+        // piece after piece: the Index.db bytes not copied yet (consecutive slices overlap by a sample interval), the piece's Summary positions,
+        // its Data.db chunks; EV_RANGE + r fires when piece r is on the device
+        std::vector<uint64_t> idx_copied(K);
+        for (int i = 0; i < K; i++) idx_copied[i] = isl[i].lo;
+        for (int r = 0; r < nr; r++) {
+            uint64_t tot = 0;
+            for (int i = 0; i < K; i++) {
+                const b200c_input& in = m->inputs[i]; const IdxSlice& sl = psl[r][i];
+                const uint64_t from = std::max(sl.lo, idx_copied[i]);
+                if (sl.hi > from) { B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i] + (from - isl[i].lo), in.index + from, sl.hi - from, kind, cs)); idx_copied[i] = sl.hi; }
+                if (sl.s_count) {
+                    B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + psb[r][i], in.summary_positions + sl.s_first, sl.s_count * 8, kind, cs));
+                    if (sl.lo) { k_add_u64<<<(unsigned)((sl.s_count + 255) / 256), 256, 0, cs>>>(d_summ + psb[r][i], sl.s_count, (uint64_t)0 - sl.lo); c->launches_call++; c->launches_total++; }
+                }
+                need_of(r, i, pustart[(size_t)r * K + i], sl.uend);
+                tot += sl.uend - pustart[(size_t)r * K + i];
+                B200C_TRY(copy_chunks(i, need[(size_t)r * K + i].h2d_a, need[(size_t)r * K + i].h2d_b));
+            }
+            range_bytes[r] = tot;
+            B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[EV_RANGE + r], cs));
+        }
+    }
     c->prog_total.store(bytes_read); c->prog_scanned.store(0);
     for (int i = 0; i < K; i++) c->prog_input_pos[i].store(0);
     c->prog_ninputs.store(K);
@@ -1079,18 +1177,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     c->nstages = 0;
     mark(0);
 
-    // ---- K1: decompress + verify, with the speculative part of K2 (find / chain / prove) per input right behind it so that both
-    //      run underneath the host->device copies of the following inputs (deferred mode: K1 runs per token range further down) ------
+    // ---- K1: decompress + verify (deferred mode: K1 runs per token range further down) ---------------------------------------------------
     c->prog_stage.store(1);
-    uint64_t *d_istart, *d_iend, *d_iscan; uint32_t *d_icnt, *d_ihit, *d_ibad;
-    B200C_TRY(ws_typed(c, WS_ISTART, nblocks + 1, &d_istart));
-    B200C_TRY(ws_typed(c, WS_IEND, nblocks + 1, &d_iend));
-    B200C_TRY(ws_typed(c, WS_ICNT, nblocks + 1, &d_icnt));
-    B200C_TRY(ws_typed(c, WS_IHIT, nblocks + 1, &d_ihit));
-    B200C_TRY(ws_typed(c, WS_IBAD, (size_t)K + 1, &d_ibad));
-    B200C_TRY(ws_typed(c, WS_ISCAN, nblocks + 2, &d_iscan));
-    if (nblocks) B200C_CUDA_TRY(c, cudaMemsetAsync(d_ihit, 0, nblocks * 4, st));
-    B200C_CUDA_TRY(c, cudaMemsetAsync(d_ibad, 0, (K + 1) * 4, st));
     auto k1 = [&](int i, uint64_t a, uint64_t b) -> int {           // chunks [a, b) of input i
         const b200c_input& in = m->inputs[i];
         if (a >= b) return B200C_OK;
@@ -1121,26 +1209,13 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         return B200C_OK;
     };
-    if (dev && k1_batching && !deferred) {          // device-resident inputs: the staging copies are device-to-device, wait for all and decode in one launch
-        std::vector<uint64_t> z(K, 0), e(K);
-        for (int i = 0; i < K; i++) { B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0)); e[i] = m->inputs[i].nchunks; }
-        B200C_TRY(k1_many(z, e));
-    }
-    for (int i = 0; i < K; i++) {
-        B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0));
-        if (!deferred && !(dev && k1_batching)) B200C_TRY(k1(i, 0, m->inputs[i].nchunks));
-        const uint64_t nb = bbase[i + 1] - bbase[i];
-        if (nb) {
-            unsigned g = (unsigned)((nb + 255) / 256);
-            if (have_summaries) {
-                B200C_CUDA_TRY(c, cudaMemsetAsync(d_istart + bbase[i], 0xFF, nb * 8, st));
-                const uint64_t ns = sbase[i + 1] - sbase[i];
-                B200C_LAUNCH(c, k_index_find_anchors, (unsigned)((ns + 127) / 128), 128, 0, dP, IDX, d_bbase, i, d_summ + sbase[i], ns, (unsigned long long*)d_istart);
-            } else B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart);
-            B200C_LAUNCH(c, k_index_chain, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart, d_icnt, d_iend);
-            B200C_LAUNCH(c, k_index_verify_a, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_iend, d_ihit, d_ibad);
-            B200C_LAUNCH(c, k_index_verify_b, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_ihit, d_ibad);
-        }
+    for (int i = 0; i < K; i++) B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_in[i], 0));      // chunk offsets (and, unless the pieces bring their own, Index.db / Data.db) are there
+    if (!deferred) {
+        if (dev && k1_batching) {          // device-resident inputs: the staging copies are device-to-device, decode in one launch
+            std::vector<uint64_t> z(K, 0), e(K);
+            for (int i = 0; i < K; i++) e[i] = m->inputs[i].nchunks;
+            B200C_TRY(k1_many(z, e));
+        } else for (int i = 0; i < K; i++) B200C_TRY(k1(i, 0, m->inputs[i].nchunks));
     }
     uint64_t* h = (uint64_t*)c->h_pinned;
     // the request is consumed by the call that reports it (b200c.h: sticky until then, so one that lands before the call is not lost)
@@ -1152,25 +1227,69 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         timing_end(c);
         return B200C_ECORRUPT;
     };
+    auto index_data_mismatch = [&](uint64_t word) -> int {
+        res->corruption.input = (int)((word >> 48) & 0xFF); res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = word & 0xFFFFFFFFFFFFull;
+        c->err = "Index.db does not match Data.db in input " + std::to_string(res->corruption.input);
+        timing_end(c);
+        return B200C_ECORRUPT;
+    };
 
-    // ---- K2: Index.db ------------------------------------------------------------------------------------------------------------
-    mark(1);
-    c->prog_stage.store(2);
+    // ---- K2: Index.db -> tokens, key prefixes, positions of the partitions the slices `sl` describe (speculate from the Summary.db samples,
+    //      prove against the sequential parse, emit), order check, and the partitions of every input inside (tlo, thi] ---------------------
     uint64_t total_parts = 0;
     std::vector<uint64_t> pcount(K, 0), pbase(K + 1, 0);
-    if (nblocks) {
-        B200C_LAUNCH(c, k_index_seq, (K + 63) / 64, 64, 0, dP, IDX, d_bbase, d_istart, d_icnt, d_ibad, d_err);
-        B200C_TRY(exclusive_scan<uint32_t>(c, d_icnt, nblocks, d_iscan, WS_SCANA, 0));
-    } else B200C_CUDA_TRY(c, cudaMemsetAsync(d_iscan, 0, 16, st));
-    // read back: chunk errors, index errors, per-input partition counts
-    {
+    int64_t* d_tok = nullptr; uint64_t *d_kp = nullptr, *d_upos = nullptr, *d_pbase = nullptr, *d_pcount = nullptr, *d_range = nullptr; uint16_t* d_klen = nullptr;
+    B200C_TRY(ws_typed(c, WS_PBASE, (size_t)2 * K + 2, &d_pbase)); d_pcount = d_pbase + K + 1;
+    B200C_TRY(ws_typed(c, WS_RANGE, (size_t)2 * K + 16, &d_range));
+    unsigned long long* d_rbytes = (unsigned long long*)(d_stats + 1) + 1;      // (zeroed with the stats block; every K2 run adds its range)
+    res->index_slow_path_inputs = 0;
+    uint64_t slow_inputs = 0;
+    auto k2_run = [&](const std::vector<IdxSlice>& sl, const std::vector<uint64_t>& sb, int64_t tlo, int64_t thi) -> int {
+        c->prog_stage.store(2);
+        uint64_t bo2 = 0;
+        for (int i = 0; i < K; i++) {
+            const uint64_t ilen_i = sl[i].hi - sl[i].lo;
+            bbase[i] = bo2; bo2 += (ilen_i + IB - 1) / IB;
+            hin[i].ibase = ibase[i] + (sl[i].lo - isl[i].lo); hin[i].ilen = ilen_i; hin[i].uend = sl[i].uend;
+        }
+        bbase[K] = bo2;
+        const uint64_t nblocks = bo2;
+        B200C_CUDA_TRY(c, cudaMemcpyAsync((void*)hp.in, hin.data(), sizeof(InDesc) * (size_t)K, cudaMemcpyHostToDevice, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_bbase, bbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
+        uint64_t *d_istart, *d_iend, *d_iscan; uint32_t *d_icnt, *d_ihit, *d_ibad;
+        B200C_TRY(ws_typed(c, WS_ISTART, nblocks + 1, &d_istart));
+        B200C_TRY(ws_typed(c, WS_IEND, nblocks + 1, &d_iend));
+        B200C_TRY(ws_typed(c, WS_ICNT, nblocks + 1, &d_icnt));
+        B200C_TRY(ws_typed(c, WS_IHIT, nblocks + 1, &d_ihit));
+        B200C_TRY(ws_typed(c, WS_IBAD, (size_t)K + 1, &d_ibad));
+        B200C_TRY(ws_typed(c, WS_ISCAN, nblocks + 2, &d_iscan));
+        if (nblocks) B200C_CUDA_TRY(c, cudaMemsetAsync(d_ihit, 0, nblocks * 4, st));
+        B200C_CUDA_TRY(c, cudaMemsetAsync(d_ibad, 0, (K + 1) * 4, st));
+        for (int i = 0; i < K; i++) {
+            const uint64_t nb = bbase[i + 1] - bbase[i];
+            if (!nb) continue;
+            unsigned g = (unsigned)((nb + 255) / 256);
+            if (have_summaries) {
+                B200C_CUDA_TRY(c, cudaMemsetAsync(d_istart + bbase[i], 0xFF, nb * 8, st));
+                const uint64_t ns = sl[i].s_count;
+                B200C_LAUNCH(c, k_index_find_anchors, (unsigned)((ns + 127) / 128), 128, 0, dP, IDX, d_bbase, i, d_summ + sb[i], ns, (unsigned long long*)d_istart);
+            } else B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart);
+            B200C_LAUNCH(c, k_index_chain, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart, d_icnt, d_iend);
+            B200C_LAUNCH(c, k_index_verify_a, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_iend, d_ihit, d_ibad);
+            B200C_LAUNCH(c, k_index_verify_b, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_ihit, d_ibad);
+        }
+        if (nblocks) {
+            B200C_LAUNCH(c, k_index_seq, (K + 63) / 64, 64, 0, dP, IDX, d_bbase, d_istart, d_icnt, d_ibad, d_err);
+            B200C_TRY(exclusive_scan<uint32_t>(c, d_icnt, nblocks, d_iscan, WS_SCANA, 0));
+        } else B200C_CUDA_TRY(c, cudaMemsetAsync(d_iscan, 0, 16, st));
+        // read back: chunk errors, index errors, per-input partition counts
         for (int i = 0; i <= K; i++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8 + i, d_iscan + bbase[i], 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cerr, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 1, d_err, 8, cudaMemcpyDeviceToHost, st));
         if (nblocks) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 300, d_ibad, (K + 1) * 4, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-        res->index_slow_path_inputs = 0;
-        if (nblocks) for (int i = 0; i < K; i++) res->index_slow_path_inputs += ((uint32_t*)(h + 300))[i] ? 1 : 0;
+        if (nblocks) for (int i = 0; i < K && i < 64; i++) if (((uint32_t*)(h + 300))[i]) slow_inputs |= 1ull << i;
+        res->index_slow_path_inputs = __builtin_popcountll(slow_inputs);
         if (h[0] != ~0ull) return chunk_error(h[0]);
         if (h[1] != ~0ull) {
             res->corruption.input = (int)((h[1] >> 48) & 0xFF); res->corruption.kind = (int)(h[1] >> 56); res->corruption.chunk = 0; res->corruption.offset = h[1] & 0xFFFFFFFFFFFFull;
@@ -1178,63 +1297,39 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             timing_end(c);
             return B200C_ECORRUPT;
         }
+        total_parts = 0;
         for (int i = 0; i < K; i++) { pcount[i] = h[8 + i + 1] - h[8 + i]; pbase[i] = total_parts; total_parts += pcount[i] + 1; }
         pbase[K] = total_parts;
-    }
-    B200C_TRY(check_cancel());
-    if (total_parts - K >= (1ull << 40)) { c->err = "too many partitions"; return B200C_EUNSUPPORTED; }
-
-    int64_t* d_tok; uint64_t *d_kp, *d_upos, *d_pbase, *d_pcount, *d_range; uint16_t* d_klen;
-    B200C_TRY(ws_typed(c, WS_TOK, total_parts + 1, &d_tok));
-    B200C_TRY(ws_typed(c, WS_KP, total_parts + 1, &d_kp));
-    B200C_TRY(ws_typed(c, WS_KLEN, total_parts + 1, &d_klen));
-    B200C_TRY(ws_typed(c, WS_UPOS, total_parts + 1, &d_upos));
-    B200C_TRY(ws_typed(c, WS_PBASE, (size_t)2 * K + 2, &d_pbase)); d_pcount = d_pbase + K + 1;
-    B200C_TRY(ws_typed(c, WS_RANGE, (size_t)2 * K + 16, &d_range));
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pbase, pbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pcount, pcount.data(), K * 8, cudaMemcpyHostToDevice, st));
-    if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
-                              d_tok, d_kp, d_klen, d_upos, d_err);
-    if (total_parts > (uint64_t)K) B200C_LAUNCH(c, k_check_order, 1184, 256, 0, dP, d_pbase, d_pcount, d_tok, d_kp, d_klen, d_upos, d_err);
-    unsigned long long* d_rbytes = (unsigned long long*)(d_stats + 1) + 1;      // (zeroed with the stats block)
-    B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, m->token_lo, m->token_hi, d_range, d_rbytes);
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 201, d_rbytes, 8, cudaMemcpyDeviceToHost, st));
-    B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
-    B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-    auto index_data_mismatch = [&](uint64_t word) -> int {
-        res->corruption.input = (int)((word >> 48) & 0xFF); res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = word & 0xFFFFFFFFFFFFull;
-        c->err = "Index.db does not match Data.db in input " + std::to_string(res->corruption.input);
-        timing_end(c);
-        return B200C_ECORRUPT;
+        B200C_TRY(check_cancel());
+        if (total_parts - K >= (1ull << 40)) { c->err = "too many partitions"; return B200C_EUNSUPPORTED; }
+        B200C_TRY(ws_typed(c, WS_TOK, total_parts + 1, &d_tok));
+        B200C_TRY(ws_typed(c, WS_KP, total_parts + 1, &d_kp));
+        B200C_TRY(ws_typed(c, WS_KLEN, total_parts + 1, &d_klen));
+        B200C_TRY(ws_typed(c, WS_UPOS, total_parts + 1, &d_upos));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pbase, pbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pcount, pcount.data(), K * 8, cudaMemcpyHostToDevice, st));
+        if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
+                                  d_tok, d_kp, d_klen, d_upos, d_err);
+        if (total_parts > (uint64_t)K) B200C_LAUNCH(c, k_check_order, 1184, 256, 0, dP, d_pbase, d_pcount, d_tok, d_kp, d_klen, d_upos, d_err);
+        B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, tlo, thi, d_range, d_rbytes);
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 200, d_err, 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+        if (h[200] != ~0ull) return index_data_mismatch(h[200]);
+        for (int i = 0; i < K; i++) if (h[2 * i] > h[2 * i + 1] || h[2 * i + 1] > pcount[i]) return index_data_mismatch((uint64_t)i << 48);
+        // a slice that does not start with the call's own slice starts at a sample at or below tlo: its first entry is not in range. One that
+        // is — the Summary.db positions lied about the tokens — could hide partitions of this range in the previous slice: refuse it.
+        for (int i = 0; i < K; i++) if (pcount[i] && sl[i].lo != isl[i].lo && h[2 * i] == 0) {
+            c->err = "Summary.db positions of input " + std::to_string(i) + " do not bracket the token range"; res->corruption.input = i; res->corruption.kind = 3; res->corruption.chunk = 0; res->corruption.offset = sl[i].lo;
+            timing_end(c); return B200C_ECORRUPT; }
+        return B200C_OK;
     };
-    if (h[200] != ~0ull) return index_data_mismatch(h[200]);
-    for (int i = 0; i < K; i++) if (h[2 * i] > h[2 * i + 1] || h[2 * i + 1] > pcount[i]) return index_data_mismatch((uint64_t)i << 48);
-    const uint64_t bytes_in_range = h[201];
+    mark(1);
+    if (!istream) B200C_TRY(k2_run(isl, psb[0], m->token_lo, m->token_hi));
 
-    // ---- token ranges --------------------------------------------------------------------------------------------------------------
-    // T[0] < T[1] < ... < T[nr]: piece r merges the partitions with token in (T[r], T[r+1]] (T[0] = I64_MIN: from the first one)
-    std::vector<int64_t> T{m->token_lo, m->token_hi};
-    if (want_ranges > 1) {
-        int imax = 0; uint64_t nmax = 0;
-        for (int i = 0; i < K; i++) { uint64_t n = h[2 * i + 1] - h[2 * i]; if (n > nmax) { nmax = n; imax = i; } }
-        if (nmax >= (uint64_t)want_ranges * (forced_ranges ? 2 : 4096)) {   // quantiles of the largest input's tokens
-            const uint64_t lo = h[2 * imax];
-            for (int r = 1; r < want_ranges; r++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 600 + r, d_tok + pbase[imax] + lo + std::min<uint64_t>(nmax - 1, (uint64_t)(nmax * cuts[r - 1])), 8, cudaMemcpyDeviceToHost, st));
-            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-            T.pop_back();
-            for (int r = 1; r < want_ranges; r++) { int64_t t = (int64_t)h[600 + r]; if (t > T.back() && t < m->token_hi) T.push_back(t); }
-            T.push_back(m->token_hi);
-        }
-    }
-    const int nr = (int)T.size() - 1;
-    // what each piece needs from each input: chunks to copy (deferred mode) and to decompress
-    struct Need { uint64_t h2d_a, h2d_b, k1_a, k1_b; };
-    std::vector<Need> need((size_t)nr * K, Need{0, 0, 0, 0});
-    std::vector<uint64_t> range_bytes(nr, bytes_read);
-    std::vector<uint64_t> range_end((size_t)nr * K, 0);          // per piece and input: Data.db position behind the piece (scanner accounting)
-    for (int i = 0; i < K; i++) range_end[(size_t)(nr - 1) * K + i] = m->inputs[i].data_length;
-    if (deferred) {
+    // ---- token ranges: T[0] < T[1] < ... < T[nr]; piece r merges the partitions with token in (T[r], T[r+1]]. Several pieces: planned on the
+    //      host above (Index.db streaming). One piece of a token sub-range over device-resident inputs: the chunks it crosses come from here.
+    if (deferred && !istream) {
         int64_t* d_T; uint64_t* d_plan;
         B200C_TRY(ws_typed(c, WS_PLAN, (size_t)nr + 2 + 2 * (size_t)nr * K, &d_T)); d_plan = (uint64_t*)(d_T + nr + 2);
         B200C_CUDA_TRY(c, cudaMemcpyAsync(d_T, T.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1249,13 +1344,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 uint64_t a = hplan[2 * ((size_t)r * K + i)], b = hplan[2 * ((size_t)r * K + i) + 1];
                 if (a < ubase[i] || b < a || b > ubase[i] + in.data_length) return index_data_mismatch(((uint64_t)i << 48));
                 a -= ubase[i]; b -= ubase[i]; tot += b - a;
-                range_end[(size_t)r * K + i] = b;
-                Need& nd = need[(size_t)r * K + i];
-                if (b > a) {
-                    uint64_t ca = a / in.chunk_len, cb = std::min<uint64_t>(in.nchunks, (b + in.chunk_len - 1) / in.chunk_len);
-                    nd.h2d_a = std::max(ca, h2d_next[i]); nd.h2d_b = std::max(cb, nd.h2d_a); h2d_next[i] = nd.h2d_b;
-                    nd.k1_a = std::max(ca, k1_next[i]); nd.k1_b = std::max(cb, nd.k1_a); k1_next[i] = nd.k1_b;
-                }
+                need_of(r, i, a, b);
             }
             range_bytes[r] = tot;
         }
@@ -1286,7 +1375,12 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
 
     for (int r = 0; r < nr; r++) {
         B200C_TRY(check_cancel());
-        // ---- K1 of this piece (deferred mode) -----------------------------------------------------------------------------------------
+        // ---- K2 of this piece (Index.db streaming), then its K1 (deferred mode) --------------------------------------------------------
+        if (istream) {
+            mark(1);
+            B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_pool[EV_RANGE + r], 0));
+            B200C_TRY(k2_run(psl[r], psb[r], T[r], T[r + 1]));
+        }
         mark(0);
         c->prog_stage.store(1);
         if (deferred) {
@@ -1568,6 +1662,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8, d_stats, sizeof(RunStats), cudaMemcpyDeviceToHost, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 16, d_hist, MAXK * 8, cudaMemcpyDeviceToHost, st));
+        B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 201, d_rbytes, 8, cudaMemcpyDeviceToHost, st));
         mark(-1);
         int trc = timing_end(c);
         if (trc != B200C_OK) return trc;
@@ -1576,7 +1671,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         memcpy(&rs, h + 8, sizeof(rs));
         memset(res->merged_row_counts, 0, sizeof(res->merged_row_counts));
         for (int k = 0; k < MAXK; k++) res->merged_row_counts[k] = h[16 + k];
-        res->bytes_read = bytes_read; res->bytes_in_range = bytes_in_range; res->bytes_written = ubase_total; res->total_source_rows = rs.merged_unfiltereds + nparts_total /* one applyToStatic -> updateProgress per merged partition */; res->input_partitions = ncontrib_total;
+        res->bytes_read = bytes_read; res->bytes_in_range = h[201]; res->bytes_written = ubase_total; res->total_source_rows = rs.merged_unfiltereds + nparts_total /* one applyToStatic -> updateProgress per merged partition */; res->input_partitions = ncontrib_total;
         res->kernel_ms = c->last_ms; res->kernel_launches = c->launches_call;
         return B200C_OK;
     };

@@ -509,14 +509,16 @@ __global__ void __launch_bounds__(256) k_op_first(const uint32_t* __restrict__ h
 struct RunStats { unsigned long long merged_unfiltereds, rows_out, partitions_out; };
 
 // Work-list order. Partitions are counting-sorted by key = (class, tile, fan-in m, size bucket):
-//   class  = which kernel handles the fan-in (<= 8, <= 16, <= 32, <= 64): each class is one contiguous slice of the list,
+//   class  = which kernel handles the fan-in (<= 8, <= 12, <= 16, <= 32, <= 64): each class is one contiguous slice of the list
+//            (12: the cursors of a thread live in shared memory, and two thirds of the fan-ins above 8 of a 16-way merge are <= 12 —
+//            8 instead of 6 blocks per SM for them),
 //   tile   = j >> tile_shift: token-contiguous groups of output partitions whose input bytes (~32 MiB) stay L2 resident, so every
 //            class streams through U once instead of once per (m, size) bin,
 //   m, size bucket: threads of a warp run the same number of cursors over similarly sized partitions (less divergence).
 enum { SORT_BUCKETS = 16, SORT_BINS = MAXK * SORT_BUCKETS };
 // wide_bound: partitions whose inputs exceed it go to the warp-per-partition kernel whatever their fan-in (one lane per source parses in
 // parallel, the tournament runs on shuffles): a single thread walking hundreds of KB is the slowest thing the GPU can do (schema W)
-__device__ __forceinline__ uint32_t fanin_class(uint32_t m, uint64_t bound, uint64_t wide_bound) { return (bound > wide_bound && m <= 32) ? 2u : (m <= 8 ? 0u : (m <= 16 ? 1u : (m <= 32 ? 2u : 3u))); }
+__device__ __forceinline__ uint32_t fanin_class(uint32_t m, uint64_t bound, uint64_t wide_bound) { return (bound > wide_bound && m <= 32) ? 3u : (m <= 8 ? 0u : (m <= 12 ? 1u : (m <= 16 ? 2u : (m <= 32 ? 3u : 4u)))); }
 __device__ __forceinline__ uint64_t sort_key(uint32_t m, uint64_t bound, uint64_t j, uint32_t tile_shift, uint64_t ntiles, uint64_t wide_bound) {
     uint64_t avg = bound / (m ? m : 1);
     uint32_t bucket = (uint32_t)min((uint64_t)(SORT_BUCKETS - 1), avg >> 5);
@@ -1426,7 +1428,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_TRY(ws_typed(c, WS_BPOS, nparts + 2, &d_bpos));
         B200C_TRY(ws_typed(c, WS_ICAP, nparts + 1, &d_icap));
         B200C_TRY(ws_typed(c, WS_IOFF, nparts + 2, &d_ioff));
-        uint64_t n_le8 = 0, n_le16 = 0, n_le32 = 0;
+        uint64_t n_le8 = 0, n_le12 = 0, n_le16 = 0, n_le32 = 0;
         if (ncontrib) {
             B200C_LAUNCH(c, k_op_first, (unsigned)((ncontrib + 1 + 255) / 256), 256, 0, d_head, d_opidx, ncontrib, d_opfirst);
             // counting sort of the output partitions by (fan-in, size bucket)
@@ -1437,15 +1439,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             // tile = token-contiguous run of output partitions whose inputs total ~32 MiB
             uint64_t per_part = std::max<uint64_t>(1, range_bytes[r] / std::max<uint64_t>(1, nparts));
             uint32_t tile_shift = 12; while (tile_shift < 24 && ((1ull << (tile_shift + 1)) * per_part) <= (32ull << 20)) tile_shift++;
-            const uint64_t ntiles = (nparts >> tile_shift) + 1, nkeys = 4 * ntiles * SORT_BINS;
+            const uint64_t ntiles = (nparts >> tile_shift) + 1, nkeys = 5 * ntiles * SORT_BINS;
             const uint64_t wide_bound = []() -> uint64_t { const char* e = getenv("B200C_K4_WIDE_WARP"); return e ? strtoull(e, nullptr, 10) : 0; }() ?: ~0ull;    // bytes; unset / 0 = off (A/B)
             B200C_TRY(ws_typed(c, WS_CURSOR, nkeys + 2, &d_cursor));
             B200C_CUDA_TRY(c, cudaMemsetAsync(d_cursor, 0, (nkeys + 2) * 8, st));
             B200C_LAUNCH(c, k_class_hist, 1184, 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, wide_bound, d_cursor);
             B200C_TRY(exclusive_scan<uint64_t>(c, (const uint64_t*)d_cursor, nkeys, (uint64_t*)d_cursor, WS_SCANA, 0));
-            for (int k = 1; k <= 3; k++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512 + k, (uint64_t*)d_cursor + (uint64_t)k * ntiles * SORT_BINS, 8, cudaMemcpyDeviceToHost, st));
+            for (int k = 1; k <= 4; k++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 512 + k, (uint64_t*)d_cursor + (uint64_t)k * ntiles * SORT_BINS, 8, cudaMemcpyDeviceToHost, st));
             B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
-            n_le8 = h[513]; n_le16 = h[514]; n_le32 = h[515];
+            n_le8 = h[513]; n_le12 = h[514]; n_le16 = h[515]; n_le32 = h[516];
             B200C_LAUNCH(c, k_fanin_scatter, (unsigned)((nparts + 255) / 256), 256, 0, d_opfirst, d_bound, nparts, tile_shift, ntiles, wide_bound, d_cursor, d_list);
         }
         B200C_TRY(check_cancel());
@@ -1464,7 +1466,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
         B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
         const size_t cols_s = hp.mcols <= K4_SMEM_COLS ? (size_t)hp.mcols * sizeof(MCell) : 0;
-        const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * hp.mcols * sizeof(MCell);
+        const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem12 = (size_t)64 * (12 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * hp.mcols * sizeof(MCell);
         memset(&ka, 0, sizeof(ka));
         ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen; ka.tok = d_tok;
         ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
@@ -1478,7 +1480,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         // one launch per fan-in class over its slice of the sorted list
         const uint64_t np_ = nparts;
-        launch_k4 = [&, n_le8, n_le16, n_le32, np_, smem8, smem16, cell_smem32](int mode) -> int {
+        launch_k4 = [&, n_le8, n_le12, n_le16, n_le32, np_, smem8, smem12, smem16, cell_smem32](int mode) -> int {
             ka.mode = mode;
             const bool emit = mode != 0;
             if (n_le8) {
@@ -1486,10 +1488,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 if (emit) B200C_LAUNCH(c, (k_partition_thr<8, 128, true>), g, 128, smem8, ka, 0ull, n_le8);
                 else B200C_LAUNCH(c, (k_partition_thr<8, 128, false>), g, 128, smem8, ka, 0ull, n_le8);
             }
-            if (n_le16 > n_le8) {
-                unsigned g = (unsigned)((n_le16 - n_le8 + 63) / 64);
-                if (emit) B200C_LAUNCH(c, (k_partition_thr<16, 64, true>), g, 64, smem16, ka, n_le8, n_le16);
-                else B200C_LAUNCH(c, (k_partition_thr<16, 64, false>), g, 64, smem16, ka, n_le8, n_le16);
+            if (n_le12 > n_le8) {
+                unsigned g = (unsigned)((n_le12 - n_le8 + 63) / 64);
+                if (emit) B200C_LAUNCH(c, (k_partition_thr<12, 64, true>), g, 64, smem12, ka, n_le8, n_le12);
+                else B200C_LAUNCH(c, (k_partition_thr<12, 64, false>), g, 64, smem12, ka, n_le8, n_le12);
+            }
+            if (n_le16 > n_le12) {
+                unsigned g = (unsigned)((n_le16 - n_le12 + 63) / 64);
+                if (emit) B200C_LAUNCH(c, (k_partition_thr<16, 64, true>), g, 64, smem16, ka, n_le12, n_le16);
+                else B200C_LAUNCH(c, (k_partition_thr<16, 64, false>), g, 64, smem16, ka, n_le12, n_le16);
             }
             if (n_le32 > n_le16) {
                 unsigned g = (unsigned)((n_le32 - n_le16 + 3) / 4);
@@ -1506,12 +1513,15 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         if (c->k4_attr_set != (int)(smem8 + 1)) {      // > 48 KiB of dynamic shared memory needs an explicit opt-in, once per context/device
             cudaFuncSetAttribute(k_partition_thr<8, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
             cudaFuncSetAttribute(k_partition_thr<8, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(k_partition_thr<12, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12);
+            cudaFuncSetAttribute(k_partition_thr<12, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12);
             cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
             cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
             // B200C_K4_CARVEOUT=percent of the SM's unified L1/shared memory left to shared memory (A/B: fewer resident blocks, more L1 for the
             // scattered reads of Data.db); unset: the driver sizes the carve-out for the most blocks that fit
             if (const char* e = getenv("B200C_K4_CARVEOUT")) { const int pct = atoi(e);
                 cudaFuncSetAttribute(k_partition_thr<8, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+                cudaFuncSetAttribute(k_partition_thr<12, 64, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
                 cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
             c->k4_attr_set = (int)(smem8 + 1);
         }

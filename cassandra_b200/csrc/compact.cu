@@ -207,12 +207,12 @@ __global__ void __launch_bounds__(256) k_index_find(const CParams* __restrict__ 
 // entries between two anchors and records, per block, the lowest entry start it meets. Nothing is taken on trust: chain / verify
 // below still prove the result against the sequential parse, a wrong anchor only costs the sequential fallback.
 __global__ void __launch_bounds__(128) k_index_find_anchors(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase, int i,
-                                                            const uint64_t* __restrict__ anchors, uint64_t n, unsigned long long* __restrict__ start) {
+                                                            const uint64_t* __restrict__ anchors, uint64_t n, uint64_t bias /* file offset the slice starts at */, unsigned long long* __restrict__ start) {
     uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     const CParams& P = *Pp;
     const uint64_t ilen = P.in[i].ilen;
-    uint64_t o = anchors[a], end = (a + 1 < n) ? anchors[a + 1] : ilen;
+    uint64_t o = anchors[a] - bias, end = (a + 1 < n) ? anchors[a + 1] - bias : ilen;
     if (o >= ilen || end > ilen || end <= o) return;
     uint64_t prev_block = NONE64;
     while (o < end) {
@@ -1039,7 +1039,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     B200C_TRY(ws_typed(c, WS_CD, co + 64, &CD));
     B200C_TRY(ws_typed(c, WS_CO, oo + 1, &CO));
     B200C_TRY(ws_typed(c, WS_IDX, io + 64, &IDX));
-    // Summary.db positions on the device: one run per piece and input (slice relative)
+    // Summary.db positions on the device: one run per piece and input (file offsets; K2 subtracts the slice start — no kernel rides on the copy stream)
     std::vector<std::vector<uint64_t>> psb(nr, std::vector<uint64_t>(K + 1, 0));
     uint64_t summ_total = 0;
     for (int r = 0; r < nr; r++) for (int i = 0; i <= K; i++) { psb[r][i] = summ_total; if (i < K) summ_total += psl[r][i].s_count; }
@@ -1130,7 +1130,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             if (isl[i].hi > isl[i].lo) B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i], in.index + isl[i].lo, isl[i].hi - isl[i].lo, kind, cs));
             if (isl[i].s_count) {
                 B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + psb[0][i], in.summary_positions + isl[i].s_first, isl[i].s_count * 8, kind, cs));
-                if (isl[i].lo) { k_add_u64<<<(unsigned)((isl[i].s_count + 255) / 256), 256, 0, cs>>>(d_summ + psb[0][i], isl[i].s_count, (uint64_t)0 - isl[i].lo); c->launches_call++; c->launches_total++; }   // positions relative to the slice
             }
         }
         B200C_CUDA_TRY(c, cudaEventRecord(c->ev_in[i], cs));
@@ -1148,7 +1147,6 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 if (sl.hi > from) { B200C_CUDA_TRY(c, cudaMemcpyAsync(IDX + ibase[i] + (from - isl[i].lo), in.index + from, sl.hi - from, kind, cs)); idx_copied[i] = sl.hi; }
                 if (sl.s_count) {
                     B200C_CUDA_TRY(c, cudaMemcpyAsync(d_summ + psb[r][i], in.summary_positions + sl.s_first, sl.s_count * 8, kind, cs));
-                    if (sl.lo) { k_add_u64<<<(unsigned)((sl.s_count + 255) / 256), 256, 0, cs>>>(d_summ + psb[r][i], sl.s_count, (uint64_t)0 - sl.lo); c->launches_call++; c->launches_total++; }
                 }
                 need_of(r, i, pustart[(size_t)r * K + i], sl.uend);
                 tot += sl.uend - pustart[(size_t)r * K + i];
@@ -1274,7 +1272,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             if (have_summaries) {
                 B200C_CUDA_TRY(c, cudaMemsetAsync(d_istart + bbase[i], 0xFF, nb * 8, st));
                 const uint64_t ns = sl[i].s_count;
-                B200C_LAUNCH(c, k_index_find_anchors, (unsigned)((ns + 127) / 128), 128, 0, dP, IDX, d_bbase, i, d_summ + sb[i], ns, (unsigned long long*)d_istart);
+                B200C_LAUNCH(c, k_index_find_anchors, (unsigned)((ns + 127) / 128), 128, 0, dP, IDX, d_bbase, i, d_summ + sb[i], ns, sl[i].lo, (unsigned long long*)d_istart);
             } else B200C_LAUNCH(c, k_index_find, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart);
             B200C_LAUNCH(c, k_index_chain, g, 256, 0, dP, IDX, d_bbase, bbase[i], bbase[i + 1], d_istart, d_icnt, d_iend);
             B200C_LAUNCH(c, k_index_verify_a, g, 256, 0, dP, d_bbase, bbase[i], bbase[i + 1], d_istart, d_iend, d_ihit, d_ibad);

@@ -34,9 +34,10 @@ enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF, LZ4C_DUP_ENTRIES = 8192 };   
 __host__ __device__ __forceinline__ int lz4c_positions(int n) { return n >= LZ4_MINLENGTH ? n - LZ4_MFLIMIT + 1 : 0; }
 
 // ---- pass A  (s_dup: LZ4C_DUP_ENTRIES bytes) ---------------------------------------------------------------------------------------------------------------------------
-// s_in: the chunk where it lies in global memory (4-byte aligned, >= npos + 7 readable bytes); s_t1: nent x u16 (last position per hash);
+// s_in: the chunk (4-byte aligned, >= npos + 7 readable bytes) — GLOBAL: where it lies in global memory, else a copy in shared memory (the build
+// pass is a chain of table updates: with the chunk's bytes a DRAM access away each of its 512 steps cost 1 350 cycles); s_t1: nent x u16 (last position per hash);
 // s_dup: LZ4C_DUP_ENTRIES bytes; ent: npos words. HASH: 4 bytes -> table index (< nent = 1 << hbits).
-template <class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+template <bool GLOBAL, class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     {
         uint4* a = (uint4*)s_t1;
@@ -46,11 +47,11 @@ template <class HASH> __device__ __forceinline__ void chain_build_warp(const uin
     const uint32_t lt_mask = (1u << lane) - 1u;
     // ---- phase 1 (sequential in the table): nearest earlier position with the same hash. The 4 bytes of the NEXT step are fetched before this
     //      step's table work, so the only chain between steps is the table itself.
-    uint32_t seq_next = lane < npos ? lz4_rd32<true>(in32, lane) : 0u;
+    uint32_t seq_next = lane < npos ? lz4_rd32<GLOBAL>(in32, lane) : 0u;
     for (int p0 = 0; p0 < npos; p0 += 32) {
         const int p = p0 + lane; const bool valid = p < npos;
         const uint32_t seq = seq_next;
-        seq_next = (p + 32 < npos) ? lz4_rd32<true>(in32, p + 32) : 0u;
+        seq_next = (p + 32 < npos) ? lz4_rd32<GLOBAL>(in32, p + 32) : 0u;
         const uint32_t h = hash(seq);
         // do two positions of this step share a hash? (see lz4.cuh: one byte per hash slot, the lanes that read back another lane's number share)
         const uint32_t dh = h & (LZ4C_DUP_ENTRIES - 1);
@@ -62,38 +63,49 @@ template <class HASH> __device__ __forceinline__ void chain_build_warp(const uin
         if (unique) {
             if (valid) { q1 = s_t1[h]; s_t1[h] = (uint16_t)p; }
         } else {
-            const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
-            uint32_t same = FULL_MASK;
-            for (int b = 0; b < hbits; b++) { uint32_t mb = __ballot_sync(FULL_MASK, (h >> b) & 1u); same &= ((h >> b) & 1u) ? mb : ~mb; }
-            same &= vmask;
-            const uint32_t lower = same & lt_mask;
-            q1 = lower ? (uint32_t)(p0 + 31 - __clz(lower)) : (valid ? (uint32_t)s_t1[h] : (uint32_t)LZ4C_NONE);
+            // some positions of this step share a hash (runs, repeated row prefixes: common in SSTable bytes). Only those groups need an order:
+            // one round per distinct shared hash — its lanes by ballot, nearest lower lane = predecessor, highest lane writes the table
+            uint32_t todo = __ballot_sync(FULL_MASK, shared);
+            uint32_t t1 = valid ? (uint32_t)s_t1[h] : (uint32_t)LZ4C_NONE;
             __syncwarp();                                          // every lane has read the table
-            const uint32_t higher = same & ~lt_mask & ~(1u << lane);
-            if (valid && !higher) s_t1[h] = (uint16_t)p;
+            q1 = t1;
+            bool writer = valid;
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                const uint32_t hh = __shfl_sync(FULL_MASK, h, l);
+                const uint32_t same = __ballot_sync(FULL_MASK, valid && h == hh);
+                if (valid && h == hh) {
+                    const uint32_t lower = same & lt_mask;
+                    if (lower) q1 = (uint32_t)(p0 + 31 - __clz(lower));
+                    writer = !(same & ~lt_mask & ~(1u << lane));
+                }
+                todo &= ~same;
+            }
+            if (writer) s_t1[h] = (uint16_t)p;
         }
         __syncwarp();
         if (valid) {
             const uint32_t a1 = q1 == LZ4C_NONE ? 0u : q1;
-            const uint32_t e1 = lz4_rd32<true>(in32, (int)a1) == seq;
+            const uint32_t e1 = lz4_rd32<GLOBAL>(in32, (int)a1) == seq;
             ent[p] = a1 | (e1 << 15);
         }
     }
     __syncwarp();
     // ---- phase 2 (parallel): the predecessor's predecessor and its equality bit; position 0 ends every chain (its own link is 0)
-    for (int p0 = 0; p0 < npos; p0 += 32) {
+#pragma unroll 4
+    for (int p0 = 0; p0 < npos; p0 += 32) {                    // (no dependency between the steps: four of them in flight hide the two dependent reads)
         const int p = p0 + lane;
         if (p < npos) {
             const uint32_t e = ent[p];
             const uint32_t a2 = ent[e & 0x7FFFu] & 0x7FFFu;
-            const uint32_t e2 = lz4_rd32<true>(in32, (int)a2) == lz4_rd32<true>(in32, p);
+            const uint32_t e2 = lz4_rd32<GLOBAL>(in32, (int)a2) == lz4_rd32<GLOBAL>(in32, p);
             ent[p] = (e & 0xFFFFu) | (a2 << 16) | (e2 << 31);
         }
     }
 }
 struct Lz4Hash { __device__ __forceinline__ uint32_t operator()(uint32_t seq) const { return lz4_hash_u16(seq); } };
-__device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
-    chain_build_warp(s_in, lz4c_positions(n), LZ4_TABLE_ENTRIES, LZ4_HASHLOG_U16, Lz4Hash(), s_t1, s_dup, ent, lane);
+template <bool GLOBAL> __device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+    chain_build_warp<GLOBAL>(s_in, lz4c_positions(n), LZ4_TABLE_ENTRIES, LZ4_HASHLOG_U16, Lz4Hash(), s_t1, s_dup, ent, lane);
 }
 
 // bits [lo, hi) that fall into 32-bit word w of a bitmap

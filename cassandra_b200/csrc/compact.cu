@@ -22,6 +22,7 @@
 #include <vector>
 #include <algorithm>
 #include <functional>
+#include <cmath>
 
 using namespace b200c;
 
@@ -978,8 +979,18 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             int n = std::max(1, std::min((int)MAX_RANGES, atoi(e))); forced_ranges = true;
             for (int r = 1; r < n; r++) cuts.push_back((double)r / n);
         } else if (co >= (1536ull << 20)) {
-            double f = std::min(0.5, std::max(1.0 / 16, (double)(512ull << 20) / (double)co));
-            for (; f < 1.0 && cuts.size() + 1 < MAX_RANGES; f *= 2) cuts.push_back(f);
+            // The kernels of a piece take longer than its copies (configs[1]: 430 ms of kernels, 320 ms of PCIe), so the pipeline is kernel
+            // bound as long as no piece waits for its own data: a small first piece (the kernels start early), then EQUAL pieces. Doubling
+            // pieces (B200C_SCHEDULE=geometric, the round-1 schedule) end with a piece of half the input that cannot start before the
+            // last byte has arrived: 84 ms of idle kernels on configs[1].
+            const double f0 = std::min(0.5, std::max(1.0 / 16, (double)(512ull << 20) / (double)co));
+            const char* sch = getenv("B200C_SCHEDULE");
+            if (sch && !strcmp(sch, "geometric")) { for (double f = f0; f < 1.0 && cuts.size() + 1 < MAX_RANGES; f *= 2) cuts.push_back(f); }
+            else {
+                const double piece = std::max((double)co / 8, (double)(768ull << 20));
+                int n = (int)std::ceil((1.0 - f0) * (double)co / piece); n = std::max(1, std::min(n, (int)MAX_RANGES - 1));
+                for (int k = 0; k < n; k++) cuts.push_back(f0 + (1.0 - f0) * k / n);
+            }
         }
     }
     int want_ranges = (int)cuts.size() + 1;

@@ -114,26 +114,11 @@ __global__ void __launch_bounds__(32) k_compress_chunks_lz4_direct(const DevTabl
 // LZ4 in two passes (lz4_chain.cuh). Pass A: the two nearest earlier same-hash positions of every position, one warp per chunk with the
 // hash tables in shared memory and no parse. Pass B: the parse, with one bit per position in shared memory — 2 KiB per 16 KiB chunk
 // instead of the 16 KiB table, so residency is set by registers, not by shared memory. ent: one word per byte of the stream.
-// the chunk is staged in shared memory by ONE bulk copy (cp.async.bulk, the TMA unit's 1-D path, completion counted by an mbarrier): from
-// the 16-byte boundary below its first byte to the one above its last + 8 (every stream buffer has >= 64 bytes of slack behind it).
-// dynamic smem: chunk_len + 64 bytes.
-__device__ __forceinline__ const uint8_t* stage_chunk_bulk(uint8_t* s_buf, uint64_t* s_bar, const uint8_t* src, int ulen, int lane) {
-    const uint32_t head = (uint32_t)((uintptr_t)src & 15u);
-    const uint32_t bytes = (head + (uint32_t)ulen + 8u + 15u) & ~15u;
-    if (lane == 0) { mbar_init(s_bar, 1); mbar_arrive_expect_tx(s_bar, bytes); bulk_copy_g2s(s_buf, src - head, bytes, s_bar); }
-    __syncwarp();
-    mbar_wait(s_bar, 0);
-    return s_buf + head;
-}
 __global__ void __launch_bounds__(32) k_lz4_chain_build(const uint8_t* __restrict__ in, uint64_t n, int chunk_len, uint32_t* __restrict__ ent) {
     __shared__ __align__(16) uint16_t s_t1[LZ4_TABLE_ENTRIES];
-    __shared__ uint8_t s_dup[LZ4C_DUP_ENTRIES];
-    __shared__ __align__(8) uint64_t s_bar;
-    extern __shared__ __align__(16) uint8_t s_stage[];
     const uint64_t start = (uint64_t)blockIdx.x * (uint64_t)chunk_len;
     const int ulen = (int)min((uint64_t)chunk_len, n - start);
-    const uint8_t* s_in = stage_chunk_bulk(s_stage, &s_bar, in + start, ulen, threadIdx.x);
-    lz4_chain_build_warp<false>(s_in, ulen, s_t1, s_dup, ent + start, threadIdx.x);
+    lz4_chain_build_warp<true>(in + start, ulen, s_t1, ent + start, threadIdx.x);
 }
 enum { K5B_WARPS = 4 };
 __global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_lz4_chain(const DevTables* __restrict__ T,
@@ -167,16 +152,12 @@ __global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_lz4_chain(co
     }
 }
 
-// Snappy in two passes (snappy_chain.cuh). dynamic smem of the build pass: one table of table_size u16 + LZ4C_DUP_ENTRIES bytes.
+// Snappy in two passes (snappy_chain.cuh). dynamic smem of the build pass: one table of table_size u16.
 __global__ void __launch_bounds__(32) k_snappy_chain_build(int max_bits, int table_size, const uint8_t* __restrict__ in, uint64_t n, int chunk_len, uint32_t* __restrict__ ent) {
-    extern __shared__ __align__(16) uint8_t smem_sc[];               // [chunk_len + 64 staged chunk][table][dup][barrier]
-    __shared__ __align__(8) uint64_t s_bar;
-    const int stage_bytes = (chunk_len + 64 + 15) & ~15;
-    uint16_t* s_t1 = (uint16_t*)(smem_sc + stage_bytes); uint8_t* s_dup = (uint8_t*)(s_t1 + table_size);
+    extern __shared__ __align__(16) uint8_t smem_sc[];               // the table: table_size x u16
     const uint64_t start = (uint64_t)blockIdx.x * (uint64_t)chunk_len;
     const int ulen = (int)min((uint64_t)chunk_len, n - start);
-    const uint8_t* s_in = stage_chunk_bulk(smem_sc, &s_bar, in + start, ulen, threadIdx.x);
-    snappy_chain_build_warp<false>(s_in, ulen, max_bits, s_t1, s_dup, ent + start, threadIdx.x);
+    snappy_chain_build_warp<true>(in + start, ulen, max_bits, (uint16_t*)smem_sc, ent + start, threadIdx.x);
 }
 __global__ void __launch_bounds__(32 * K5B_WARPS) k_compress_chunks_snappy_chain(const DevTables* __restrict__ T,
         const uint8_t* __restrict__ in, uint64_t n, int chunk_len, int max_clen, const uint32_t* __restrict__ ent,

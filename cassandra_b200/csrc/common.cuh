@@ -58,7 +58,6 @@ __device__ __forceinline__ int vint_read(const uint8_t* p, const uint8_t* end, u
     if (first == 0xFF) extra = 8;
     if (p + 1 + extra > end) return 0;
     uint64_t r = first & (0xffu >> extra);
-#pragma unroll 1
     for (int i = 0; i < extra; i++) r = (r << 8) | p[1 + i];
     *v = r;
     return 1 + extra;

@@ -59,8 +59,7 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
     if (k5_mode == 3 && comp == COMP_LZ4 && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0 && chunk_len <= LZ4C_MAX_CHUNK) {
         // two passes (lz4_chain.cuh): same-hash predecessor links for every position, then the parse with one bit per position in shared memory
         uint32_t* ent; B200C_TRY(ws_typed(c, WS_K5_ENT, (size_t)n + 16384, &ent));
-        static bool attr_l = false; if (!attr_l) { cudaFuncSetAttribute(k_lz4_chain_build, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4C_MAX_CHUNK + 64); attr_l = true; }
-        B200C_LAUNCH(c, k_lz4_chain_build, (unsigned)nchunks, 32, (size_t)chunk_len + 64, d_in, n, chunk_len, ent);
+        B200C_LAUNCH(c, k_lz4_chain_build, (unsigned)nchunks, 32, 0, d_in, n, chunk_len, ent);
         const size_t smem = (size_t)K5B_WARPS * ((chunk_len + 31) >> 5) * 4;
         B200C_LAUNCH(c, k_compress_chunks_lz4_chain, (unsigned)((nchunks + K5B_WARPS - 1) / K5B_WARPS), 32 * K5B_WARPS, smem, c->d_tables, d_in, n, chunk_len, max_clen, (const uint32_t*)ent,
                      slots, stride, file_len, seg_raw, nchunks);
@@ -74,8 +73,8 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
     if (k5_mode == 3 && comp_is_snappy(comp) && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0 && chunk_len <= LZ4C_MAX_CHUNK) {
         const int max_bits = comp == COMP_SNAPPY15 ? 15 : 14, tsz = snappy_table_size(chunk_len, max_bits);
         uint32_t* ent; B200C_TRY(ws_typed(c, WS_K5_ENT, (size_t)n + 16384, &ent));
-        static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_snappy_chain_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + LZ4C_DUP_ENTRIES + LZ4C_MAX_CHUNK + 80); attr = true; }
-        B200C_LAUNCH(c, k_snappy_chain_build, (unsigned)nchunks, 32, (size_t)2 * tsz + LZ4C_DUP_ENTRIES + (((size_t)chunk_len + 64 + 15) & ~(size_t)15), max_bits, tsz, d_in, n, chunk_len, ent);
+        static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_snappy_chain_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768); attr = true; }
+        B200C_LAUNCH(c, k_snappy_chain_build, (unsigned)nchunks, 32, (size_t)2 * tsz, max_bits, tsz, d_in, n, chunk_len, ent);
         const size_t smem = (size_t)K5B_WARPS * ((chunk_len + 31) >> 5) * 4;
         B200C_LAUNCH(c, k_compress_chunks_snappy_chain, (unsigned)((nchunks + K5B_WARPS - 1) / K5B_WARPS), 32 * K5B_WARPS, smem, c->d_tables, d_in, n, chunk_len, max_clen, (const uint32_t*)ent,
                      slots, stride, file_len, seg_raw, nchunks);

@@ -33,11 +33,11 @@ enum { LZ4C_MAX_CHUNK = 32768, LZ4C_NONE = 0xFFFF, LZ4C_DUP_ENTRIES = 8192 };   
 // number of positions that can ever be looked up or inserted: search attempts and the post-match test stay below mflimitPlusOne = n - 11
 __host__ __device__ __forceinline__ int lz4c_positions(int n) { return n >= LZ4_MINLENGTH ? n - LZ4_MFLIMIT + 1 : 0; }
 
-// ---- pass A  (s_dup: LZ4C_DUP_ENTRIES bytes) ---------------------------------------------------------------------------------------------------------------------------
+// ---- pass A ---------------------------------------------------------------------------------------------------------------------------
 // s_in: the chunk (4-byte aligned, >= npos + 7 readable bytes) — GLOBAL: where it lies in global memory, else a copy in shared memory (the build
 // pass is a chain of table updates: with the chunk's bytes a DRAM access away each of its 512 steps cost 1 350 cycles); s_t1: nent x u16 (last position per hash);
 // s_dup: LZ4C_DUP_ENTRIES bytes; ent: npos words. HASH: 4 bytes -> table index (< nent = 1 << hbits).
-template <bool GLOBAL, class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+template <bool GLOBAL, class HASH> __device__ __forceinline__ void chain_build_warp(const uint8_t* s_in, int npos, int nent, int hbits, HASH hash, uint16_t* s_t1, uint32_t* __restrict__ ent, int lane) {
     const uint32_t* in32 = (const uint32_t*)s_in;
     {
         uint4* a = (uint4*)s_t1;
@@ -45,49 +45,51 @@ template <bool GLOBAL, class HASH> __device__ __forceinline__ void chain_build_w
     }
     __syncwarp();
     const uint32_t lt_mask = (1u << lane) - 1u;
-    // ---- phase 1 (sequential in the table): nearest earlier position with the same hash. The 4 bytes of the NEXT step are fetched before this
-    //      step's table work, so the only chain between steps is the table itself.
-    uint32_t seq_next = lane < npos ? lz4_rd32<GLOBAL>(in32, lane) : 0u;
-    for (int p0 = 0; p0 < npos; p0 += 32) {
-        const int p = p0 + lane; const bool valid = p < npos;
-        const uint32_t seq = seq_next;
-        seq_next = (p + 32 < npos) ? lz4_rd32<GLOBAL>(in32, p + 32) : 0u;
-        const uint32_t h = hash(seq);
-        // do two positions of this step share a hash? (see lz4.cuh: one byte per hash slot, the lanes that read back another lane's number share)
-        const uint32_t dh = h & (LZ4C_DUP_ENTRIES - 1);
-        if (valid) s_dup[dh] = (uint8_t)lane;
-        __syncwarp();
-        const bool shared = valid && s_dup[dh] != (uint8_t)lane;
-        const bool unique = !__any_sync(FULL_MASK, shared);
-        uint32_t q1 = LZ4C_NONE;
-        if (unique) {
-            if (valid) { q1 = s_t1[h]; s_t1[h] = (uint16_t)p; }
-        } else {
-            // some positions of this step share a hash (runs, repeated row prefixes: common in SSTable bytes). Only those groups need an order:
-            // one round per distinct shared hash — its lanes by ballot, nearest lower lane = predecessor, highest lane writes the table
-            uint32_t todo = __ballot_sync(FULL_MASK, shared);
-            uint32_t t1 = valid ? (uint32_t)s_t1[h] : (uint32_t)LZ4C_NONE;
-            __syncwarp();                                          // every lane has read the table
-            q1 = t1;
-            bool writer = valid;
-            while (todo) {
-                const int l = __ffs(todo) - 1;
-                const uint32_t hh = __shfl_sync(FULL_MASK, h, l);
-                const uint32_t same = __ballot_sync(FULL_MASK, valid && h == hh);
-                if (valid && h == hh) {
-                    const uint32_t lower = same & lt_mask;
-                    if (lower) q1 = (uint32_t)(p0 + 31 - __clz(lower));
-                    writer = !(same & ~lt_mask & ~(1u << lane));
+    // ---- phase 1 (sequential in the table): nearest earlier position with the same hash. The only shared memory is the table itself (16 KiB:
+    //      14 chunks per SM — a warp alone on its scheduler runs this chain at ~11 cycles per instruction, residency is what it needs), so the
+    //      chunk is read where it lies, four steps ahead of the table work (the bytes of a step are a DRAM access away).
+    enum { AHEAD = 4 };
+    uint32_t ring[AHEAD];
+#pragma unroll
+    for (int k = 0; k < AHEAD; k++) ring[k] = (32 * k + lane < npos) ? lz4_rd32<GLOBAL>(in32, 32 * k + lane) : 0u;
+    for (int p0 = 0; p0 < npos; p0 += 32 * AHEAD) {
+#pragma unroll
+        for (int k = 0; k < AHEAD; k++) {
+            const int p = p0 + 32 * k + lane; const bool valid = p < npos;
+            if (p0 + 32 * k >= npos) break;
+            const uint32_t seq = ring[k];
+            ring[k] = (p + 32 * AHEAD < npos) ? lz4_rd32<GLOBAL>(in32, p + 32 * AHEAD) : 0u;
+            const uint32_t h = hash(seq);
+            // every lane reads its slot, then writes its position into it and reads back: a lane that reads another position shares its hash with
+            // a lane of this step (runs and repeated row prefixes make that common in SSTable bytes). One round per shared hash puts the group in
+            // order: nearest lower lane = predecessor, highest lane owns the slot.
+            uint32_t q1 = valid ? (uint32_t)s_t1[h] : (uint32_t)LZ4C_NONE;
+            __syncwarp();
+            if (valid) s_t1[h] = (uint16_t)p;
+            __syncwarp();
+            const bool lost = valid && s_t1[h] != (uint16_t)p;
+            uint32_t todo = __ballot_sync(FULL_MASK, lost);
+            if (todo) {
+                bool fix = false;
+                while (todo) {
+                    const int l = __ffs(todo) - 1;
+                    const uint32_t hh = __shfl_sync(FULL_MASK, h, l);
+                    const uint32_t same = __ballot_sync(FULL_MASK, valid && h == hh);
+                    if (valid && h == hh) {
+                        const uint32_t lower = same & lt_mask;
+                        if (lower) q1 = (uint32_t)(p0 + 32 * k + 31 - __clz(lower));
+                        fix = !(same & ~lt_mask & ~(1u << lane));                 // the group's highest lane
+                    }
+                    todo &= ~same;
                 }
-                todo &= ~same;
+                if (fix) s_t1[h] = (uint16_t)p;
+                __syncwarp();
             }
-            if (writer) s_t1[h] = (uint16_t)p;
-        }
-        __syncwarp();
-        if (valid) {
-            const uint32_t a1 = q1 == LZ4C_NONE ? 0u : q1;
-            const uint32_t e1 = lz4_rd32<GLOBAL>(in32, (int)a1) == seq;
-            ent[p] = a1 | (e1 << 15);
+            if (valid) {
+                const uint32_t a1 = q1 == LZ4C_NONE ? 0u : q1;
+                const uint32_t e1 = lz4_rd32<GLOBAL>(in32, (int)a1) == seq;
+                ent[p] = a1 | (e1 << 15);
+            }
         }
     }
     __syncwarp();
@@ -104,8 +106,8 @@ template <bool GLOBAL, class HASH> __device__ __forceinline__ void chain_build_w
     }
 }
 struct Lz4Hash { __device__ __forceinline__ uint32_t operator()(uint32_t seq) const { return lz4_hash_u16(seq); } };
-template <bool GLOBAL> __device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
-    chain_build_warp<GLOBAL>(s_in, lz4c_positions(n), LZ4_TABLE_ENTRIES, LZ4_HASHLOG_U16, Lz4Hash(), s_t1, s_dup, ent, lane);
+template <bool GLOBAL> __device__ __forceinline__ void lz4_chain_build_warp(const uint8_t* s_in, int n, uint16_t* s_t1, uint32_t* __restrict__ ent, int lane) {
+    chain_build_warp<GLOBAL>(s_in, lz4c_positions(n), LZ4_TABLE_ENTRIES, LZ4_HASHLOG_U16, Lz4Hash(), s_t1, ent, lane);
 }
 
 // bits [lo, hi) that fall into 32-bit word w of a bitmap

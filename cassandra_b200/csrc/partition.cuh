@@ -146,27 +146,17 @@ struct Rd {
 };
 
 // ---- sinks ----------------------------------------------------------------------------------------------------------------
-// big-endian store of the low `n` bytes of v / vint store, out of line: byte-wise stores inlined at every use were a tenth of the K4 kernels' code
-__device__ __noinline__ void sink_store_be(uint8_t* dst, uint64_t v, int n) {
-#pragma unroll 1
-    for (int i = 0; i < n; i++) dst[i] = (uint8_t)(v >> (8 * (n - 1 - i)));
-}
-__device__ __noinline__ int sink_store_vint(uint8_t* dst, uint64_t room, bool store, uint64_t v) {      // returns the size; stores when it fits
-    const int size = vint_size(v);
-    if (store && (uint64_t)size <= room) vint_store(dst, v, size);
-    return size;
-}
 template <bool EMIT> struct Sink {
     uint8_t* base; uint64_t pos; bool on;      // on: this lane performs the stores (tile mode: lane 0 only; every lane tracks pos)
     uint64_t cap;                              // bytes available at base: stores beyond it are dropped (the caller sees pos > cap)
     __device__ __forceinline__ void u8(uint32_t v) { if (EMIT && on && pos < cap) base[pos] = (uint8_t)v; pos++; }
-    __device__ __forceinline__ void be(uint64_t v, int n) { if (EMIT && on && pos + n <= cap) sink_store_be(base + pos, v, n); pos += n; }
-    __device__ __forceinline__ void be16(uint32_t v) { be(v, 2); }
-    __device__ __forceinline__ void be32(uint32_t v) { be(v, 4); }
-    __device__ __forceinline__ void be64(uint64_t v) { be(v, 8); }
+    __device__ __forceinline__ void be16(uint32_t v) { u8(v >> 8); u8(v); }
+    __device__ __forceinline__ void be32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
+    __device__ __forceinline__ void be64(uint64_t v) { be32((uint32_t)(v >> 32)); be32((uint32_t)v); }
     __device__ __forceinline__ void vint(uint64_t v) {
-        if (EMIT) pos += sink_store_vint(base + pos, pos <= cap ? cap - pos : 0, on, v);
-        else pos += vint_size(v);
+        int size = vint_size(v);
+        if (EMIT && on && pos + size <= cap) vint_store(base + pos, v, size);
+        pos += size;
     }
     __device__ __forceinline__ void copy(const uint8_t* src, uint32_t n) { if (EMIT && on && pos + n <= cap) bytes_copy(base + pos, src, n); pos += n; }
 };
@@ -411,9 +401,9 @@ struct StatAcc {
         if (!(seen & 2)) { min_ldt = max_ldt = v; seen |= 2; } else { min_ldt = v < min_ldt ? v : min_ldt; max_ldt = v > max_ldt ? v : max_ldt; }
         if (v != I64_MAX) tdrop(v);
     }
-    __device__ __noinline__ void live(const Live& l) { if (live_is_empty(l)) return; ts(l.ts); ttl(l.ttl); ldt(l.ldt); if (!live_is_live(l, now)) tombs++; }
-    __device__ __noinline__ void dt(const DT& d) { if (dt_is_live(d)) return; ts(d.mfda); ldt(d.ldt); tombs++; }
-    __device__ __noinline__ void cell(const MCell& m) { cells++; part_cells++; ts(m.ts); ttl(m.ttl); ldt(m.ldt); if (!(m.ldt == I64_MAX || (m.ttl != 0 && now < m.ldt))) tombs++; }
+    __device__ __forceinline__ void live(const Live& l) { if (live_is_empty(l)) return; ts(l.ts); ttl(l.ttl); ldt(l.ldt); if (!live_is_live(l, now)) tombs++; }
+    __device__ __forceinline__ void dt(const DT& d) { if (dt_is_live(d)) return; ts(d.mfda); ldt(d.ldt); tombs++; }
+    __device__ __forceinline__ void cell(const MCell& m) { cells++; part_cells++; ts(m.ts); ttl(m.ttl); ldt(m.ldt); if (!(m.ldt == I64_MAX || (m.ttl != 0 && now < m.ldt))) tombs++; }
 };
 
 // ---- partition writer (SortedTablePartitionWriter + BigFormatPartitionWriter state) ------------------------------------------
@@ -477,7 +467,6 @@ template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const
     if (flags & 0x10) write_delta_dt(s, P, del);
     if (!(flags & 0x20)) {
         uint64_t missing = 0;
-#pragma unroll 1
         for (int c = 0; c < ncols; c++) if (!cells[c].present) missing |= 1ull << c;
         s.vint(missing);
     }
@@ -705,9 +694,7 @@ template <class CUR> __device__ __noinline__ int merge_static(const CParams& P, 
         fold_cells(P, cur[v], r, vi, !as_is, active, merged, *err, true);
     }
     *info_out = info; *del_out = del;
-    int n = 0;
-#pragma unroll 1
-    for (int k = 0; k < P.nstat; k++) n += merged[k].present;
+    int n = 0; for (int k = 0; k < P.nstat; k++) n += merged[k].present;
     return (live_is_empty(info) && dt_is_live(del) && n == 0) ? -1 : n;
 }
 
@@ -751,10 +738,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
         c.k0 = part_kp[g]; c.ckend_rel = part_klen[g];           // what Index.db said about this partition's key (checked below)
     }
 #ifdef __CUDA_ARCH__
-    if (sizeof(typename CUR::rel_t) == 4) {
-#pragma unroll 1
-        for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
-    }
+    if (sizeof(typename CUR::rel_t) == 4) for (uint32_t v = 0; v < m; v++) asm volatile("prefetch.global.L1 [%0];" :: "l"(P.U + cur[v].pos));
 #endif
     for (uint32_t v = 0; v < mu; v++) {
         if (v >= m) continue;
@@ -845,9 +829,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
                 for (int k = 0; k < P.ncols; k++) if (merged[k].present && dt_deletes(active, merged[k].ts)) merged[k].present = false;
             }
             if (err) break;
-            int npresent = 0;
-#pragma unroll 1
-            for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;
+            int npresent = 0; for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;
             if (!(live_is_empty(info) && dt_is_live(del) && npresent == 0)) {
                 st.merged_unfiltereds++;
                 CUR& f = cur[b];

@@ -16,9 +16,9 @@ __host__ __device__ __forceinline__ int snappy_table_size(int frag, int max_bits
 // positions the matcher can look up or insert: everything below ip_limit = n - 15
 __host__ __device__ __forceinline__ int snappyc_positions(int n) { return n >= 15 ? n - 14 : 0; }
 
-template <bool GLOBAL> __device__ __forceinline__ void snappy_chain_build_warp(const uint8_t* s_in, int n, int max_bits, uint16_t* s_t1, uint8_t* s_dup, uint32_t* __restrict__ ent, int lane) {
+template <bool GLOBAL> __device__ __forceinline__ void snappy_chain_build_warp(const uint8_t* s_in, int n, int max_bits, uint16_t* s_t1, uint32_t* __restrict__ ent, int lane) {
     const int tsz = snappy_table_size(n, max_bits);
-    chain_build_warp<GLOBAL>(s_in, snappyc_positions(n), tsz, 31 - __clz(tsz), SnappyHash{(uint32_t)tsz - 1u, max_bits}, s_t1, s_dup, ent, lane);
+    chain_build_warp<GLOBAL>(s_in, snappyc_positions(n), tsz, 31 - __clz(tsz), SnappyHash{(uint32_t)tsz - 1u, max_bits}, s_t1, ent, lane);
 }
 
 // s_in: the chunk in global memory (4-byte aligned, >= 8 readable bytes behind it), n <= 32768; ent: pass A's output; s_bm: (n + 31) / 32 words.

@@ -43,12 +43,12 @@ extern "C" int warp_compress(int mode, const uint8_t* in, int n, uint8_t* out) {
         int r;
         if (mode == 8 || mode == 9) {                                        // Snappy in two passes (snappy_chain.cuh), max_bits 14 / 15
             const int mb = mode == 9 ? 15 : 14;
-            snappy_chain_build_warp<true>(s_in.data(), n, mb, tab2.data(), dup.data(), ent.data(), lane);
+            snappy_chain_build_warp<true>(s_in.data(), n, mb, tab2.data(), ent.data(), lane);
             __syncwarp();
             r = snappy_compress_warp_chain(s_in.data(), n, ent.data(), bm.data(), out, lane);
         }
         else if (mode == 7) {
-            lz4_chain_build_warp<true>(s_in.data(), n, tab.data(), dup.data(), ent.data(), lane);
+            lz4_chain_build_warp<true>(s_in.data(), n, tab.data(), ent.data(), lane);
             __syncwarp();
             r = lz4_compress_warp_chain(s_in.data(), n, ent.data(), bm.data(), out, lane);
         }

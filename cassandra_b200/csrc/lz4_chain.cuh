@@ -85,23 +85,22 @@ template <bool GLOBAL, class HASH> __device__ __forceinline__ void chain_build_w
                 if (fix) s_t1[h] = (uint16_t)p;
                 __syncwarp();
             }
-            if (valid) {
-                const uint32_t a1 = q1 == LZ4C_NONE ? 0u : q1;
-                const uint32_t e1 = lz4_rd32<GLOBAL>(in32, (int)a1) == seq;
-                ent[p] = a1 | (e1 << 15);
-            }
+            if (valid) ent[p] = q1 == LZ4C_NONE ? 0u : q1;      // (nothing of this phase waits for a load behind the table: a warp issues in order,
+                                                                //  the 4-byte compare of the candidate would stall the next step's table work)
         }
     }
     __syncwarp();
-    // ---- phase 2 (parallel): the predecessor's predecessor and its equality bit; position 0 ends every chain (its own link is 0)
-#pragma unroll 4
-    for (int p0 = 0; p0 < npos; p0 += 32) {                    // (no dependency between the steps: four of them in flight hide the two dependent reads)
+    // ---- phase 2 (parallel, no dependency between the steps: eight of them in flight hide the dependent reads): the predecessor's predecessor
+    //      and both equality bits; position 0 ends every chain (its own link is 0)
+#pragma unroll 8
+    for (int p0 = 0; p0 < npos; p0 += 32) {
         const int p = p0 + lane;
         if (p < npos) {
-            const uint32_t e = ent[p];
-            const uint32_t a2 = ent[e & 0x7FFFu] & 0x7FFFu;
-            const uint32_t e2 = lz4_rd32<GLOBAL>(in32, (int)a2) == lz4_rd32<GLOBAL>(in32, p);
-            ent[p] = (e & 0xFFFFu) | (a2 << 16) | (e2 << 31);
+            const uint32_t a1 = ent[p] & 0x7FFFu;
+            const uint32_t a2 = ent[a1] & 0x7FFFu;
+            const uint32_t sp = lz4_rd32<GLOBAL>(in32, p);
+            const uint32_t e1 = lz4_rd32<GLOBAL>(in32, (int)a1) == sp, e2 = lz4_rd32<GLOBAL>(in32, (int)a2) == sp;
+            ent[p] = a1 | (e1 << 15) | (a2 << 16) | (e2 << 31);
         }
     }
 }

@@ -3,9 +3,9 @@
    python tools/traffic_summary.py gpurun_out/r2_traffic_cfg1.csv cfg1 [existing.json] > profiles/r2_traffic.json
 Kernels launched before the first k_decompress* / k_index_find* (the input preparation, which compresses the synthetic inputs with K5) are skipped."""
 import collections, csv, json, re, sys
-STAGE = [("K1 decompress+verify", r"k_decompress"), ("K2 index scan", r"k_index_(find|chain|verify|seq|emit)|k_check_order|k_input_ranges|k_range_plan|k_index_slices"),
+STAGE = [("K1 decompress+verify", r"k_decompress|k_lz4_walk|k_lz4_copy"), ("K2 index scan", r"k_index_(find|chain|verify|seq|emit)|k_check_order|k_input_ranges|k_range_plan|k_index_slices"),
          ("K3 partition merge", r"k_merge_|k_bucket_bounds|k_op_first"), ("K4 merge+purge+serialise", r"k_partition_|k_bounds|k_class_hist|k_fanin_scatter|k_tile_|k_sum_stats"),
-         ("K4 gather+index", r"k_gather|k_index_simple|k_index_promoted|k_index_sizes|k_add_u64"), ("K5 compress+crc+pack", r"k_compress_chunks|k_pack_chunks|k_digest|k_offs_add_base"),
+         ("K4 gather+index", r"k_gather|k_index_simple|k_index_promoted|k_index_sizes|k_add_u64"), ("K5 compress+crc+pack", r"k_compress_chunks|k_lz4_chain_build|k_snappy_chain_build|k_pack_chunks|k_digest|k_offs_add_base"),
          ("meta", r"k_meta_|k_summary_|k_tdrop|k_written_flags"), ("scans", r"k_scan_")]
 rows = list(csv.DictReader([l for l in open(sys.argv[1]) if not l.startswith("==")]))
 per = collections.OrderedDict(); started = False; kernels = collections.OrderedDict()

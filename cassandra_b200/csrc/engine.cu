@@ -55,7 +55,11 @@ int compress_slots_device(b200c_ctx* c, int comp, const uint8_t* d_in, uint64_t 
                           uint8_t* slots, int stride, uint32_t* file_len, uint32_t* seg_raw) {
     uint64_t nchunks = (n + chunk_len - 1) / chunk_len;
     if (!nchunks) return B200C_OK;
-    const int k5_mode = []() { const char* e = getenv("B200C_K5"); return e ? atoi(e) : 1; }();      // 1 (default): LZ4 reads the chunk through L1, 13 chunks per SM: 48.0 -> 34.7 ms at 16 x 256 MiB; 0: chunk copy in shared memory (A/B)
+    // B200C_K5: 0 = chunk copy in shared memory, 1 = the chunk read through L1 (LZ4: 48.0 -> 34.7 ms at 16 x 256 MiB), 3 = two passes (lz4_chain.cuh /
+    // snappy_chain.cuh). Unset: what measured fastest — LZ4 mode 1 (two passes: 39.2 ms, the link-building pass is bound by the sector
+    // traffic of its random 4-byte reads), Snappy two passes (105.3 -> 90.7 ms on configs[2]: its table is 32 KiB, 6 chunks per SM).
+    const int k5_env = []() { const char* e = getenv("B200C_K5"); return e ? atoi(e) : -1; }();
+    const int k5_mode = k5_env >= 0 ? k5_env : (comp_is_snappy(comp) ? 3 : 1);
     if (k5_mode == 3 && comp == COMP_LZ4 && ((uintptr_t)d_in & 3) == 0 && (chunk_len & 3) == 0 && chunk_len <= LZ4C_MAX_CHUNK) {
         // two passes (lz4_chain.cuh): same-hash predecessor links for every position, then the parse with one bit per position in shared memory
         uint32_t* ent; B200C_TRY(ws_typed(c, WS_K5_ENT, (size_t)n + 16384, &ent));

@@ -172,15 +172,19 @@ __device__ int lz4_compress_warp_chain(const uint8_t* s_in, int n, const uint32_
                     // match that follows, exactly the positions whose hash chains are longest (hundreds of never-inserted predecessors)
                     int limit = hits ? (__ffs(hits) - 1) : 32; if (first_inv < limit) limit = first_inv;
                     if ((int)(__ffs(dmask) - 1) < limit) {
-                        bool walking = deeper; int q = q2;
+                        bool walking = deeper; int q = q2;                     // q: a position known not to be inserted; its entry names the next two
                         for (;;) {
                             walking = walking && lane < limit;
-                            const bool ins = walking && ((contiguous && q >= w_lo && q != hole) || ((s_bm[q >> 5] >> (q & 31)) & 1u));
-                            if (ins) { walking = false; cand = q; hit = !putonly && (lz4_rd32<true>(in32, q) == lz4_rd32<true>(in32, p)); }
+                            const uint32_t eq_ = walking ? ent[q] : 0u;
+                            const int c1 = (int)(eq_ & 0x7FFFu), c2 = (int)((eq_ >> 16) & 0x7FFFu);
+                            const bool i1 = walking && ((contiguous && c1 >= w_lo && c1 != hole) || ((s_bm[c1 >> 5] >> (c1 & 31)) & 1u));
+                            const bool i2 = walking && !i1 && ((contiguous && c2 >= w_lo && c2 != hole) || ((s_bm[c2 >> 5] >> (c2 & 31)) & 1u));
+                            const bool ins = i1 || i2;
+                            if (ins) { walking = false; cand = i1 ? c1 : c2; hit = !putonly && (lz4_rd32<true>(in32, cand) == lz4_rd32<true>(in32, p)); }
+                            else if (walking) q = c2;
                             const uint32_t nh = __ballot_sync(FULL_MASK, ins && hit);
                             if (nh && (int)(__ffs(nh) - 1) < limit) limit = __ffs(nh) - 1;
                             if (!__any_sync(FULL_MASK, walking && lane < limit)) break;
-                            if (walking && lane < limit) q = (int)(ent[q] & 0x7FFFu);
                         }
                         hits = __ballot_sync(FULL_MASK, hit);
                     }

@@ -78,15 +78,19 @@ __device__ int snappy_compress_warp_chain(const uint8_t* s_in, int n, const uint
                 if (dmask) {                                          // (see lz4_chain.cuh: only lanes in front of the first known hit walk)
                     int limit = hits ? (__ffs(hits) - 1) : 32; if (first_inv < limit) limit = first_inv;
                     if ((int)(__ffs(dmask) - 1) < limit) {
-                        bool walking = deeper; int c = q2;
+                        bool walking = deeper; int c = q2;                     // c: known not to be inserted; its entry names the next two
                         for (;;) {
                             walking = walking && lane < limit;
-                            const bool ins = walking && ((contiguous && c >= w_lo) || ((s_bm[c >> 5] >> (c & 31)) & 1u));
-                            if (ins) { walking = false; cand = c; hit = !putonly && (lz4_rd32<true>(in32, c) == lz4_rd32<true>(in32, q)); }
+                            const uint32_t eq_ = walking ? ent[c] : 0u;
+                            const int c1 = (int)(eq_ & 0x7FFFu), c2 = (int)((eq_ >> 16) & 0x7FFFu);
+                            const bool i1 = walking && ((contiguous && c1 >= w_lo) || ((s_bm[c1 >> 5] >> (c1 & 31)) & 1u));
+                            const bool i2 = walking && !i1 && ((contiguous && c2 >= w_lo) || ((s_bm[c2 >> 5] >> (c2 & 31)) & 1u));
+                            const bool ins = i1 || i2;
+                            if (ins) { walking = false; cand = i1 ? c1 : c2; hit = !putonly && (lz4_rd32<true>(in32, cand) == lz4_rd32<true>(in32, q)); }
+                            else if (walking) c = c2;
                             const uint32_t nh = __ballot_sync(FULL_MASK, ins && hit);
                             if (nh && (int)(__ffs(nh) - 1) < limit) limit = __ffs(nh) - 1;
                             if (!__any_sync(FULL_MASK, walking && lane < limit)) break;
-                            if (walking && lane < limit) c = (int)(ent[c] & 0x7FFFu);
                         }
                         hits = __ballot_sync(FULL_MASK, hit);
                     }

@@ -62,7 +62,7 @@ def merged_encoding_stats(inputs):
     if ldt == sst.NO_DELETION_TIME: ldt = sst.DELETION_TIME_EPOCH
     return ts, ldt, ttl
 
-def _name_key(name: bytes): return name                              # ColumnMetadata order for simple regular columns = name bytes
+def _name_key(name: bytes): return name                              # ColumnMetadata order within a group (simple / complex) = name bytes
 
 class CompactionTask:
     def __init__(self, inputs, controller: CompactionController, compression=None, column_index_size=65536,
@@ -83,7 +83,8 @@ class CompactionTask:
         union = {}
         for i in sorted(ins, key=lambda s: s.generation):            # newest generation's metadata wins (:91-99)
             for name, t in i.regular_columns: union[name] = t
-        out_cols = sorted(union.items(), key=lambda kv: _name_key(kv[0]))
+        # ColumnMetadata.comparisonOrder: simple columns before complex (multi-cell) ones, each group by name (S/schema/ColumnMetadata.java:139-149)
+        out_cols = sorted(union.items(), key=lambda kv: (sst.is_complex(kv[1]), _name_key(kv[0])))
         sunion = {}
         for i in sorted(ins, key=lambda s: s.generation):
             for name, t in i.static_columns: sunion[name] = t
@@ -121,7 +122,9 @@ class CompactionTask:
             if short not in sst.CLUSTERING_OK: raise native.UnsupportedError(native.EUNSUPPORTED, "clustering type " + t)
             m.clustering[k].type, m.clustering[k].fixed_len = sst.type_class(t)
         m.ncolumns = len(out_cols)
-        for k, (_, t) in enumerate(out_cols): m.columns[k].type, m.columns[k].fixed_len = sst.type_class(t)
+        for k, (_, t) in enumerate(out_cols): m.columns[k].type, m.columns[k].fixed_len = sst.column_class(t)
+        if sum(1 for _, t in out_cols if sst.is_complex(t)) > native.MAX_COMPLEX_COLUMNS: raise native.UnsupportedError(native.EUNSUPPORTED, "more than %d multi-cell columns" % native.MAX_COMPLEX_COLUMNS)
+        if any(sst.is_complex(t) for _, t in out_static): raise native.UnsupportedError(native.EUNSUPPORTED, "multi-cell static column")
         m.nstatic_columns = len(out_static)
         for k, (_, t) in enumerate(out_static): m.static_columns[k].type, m.static_columns[k].fixed_len = sst.type_class(t)
         m.out_stats.min_timestamp, m.out_stats.min_local_deletion_time, m.out_stats.min_ttl = merged_encoding_stats(ins)

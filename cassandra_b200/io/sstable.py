@@ -41,6 +41,40 @@ def type_class(type_string: str):
     if t in ("UTF8Type", "AsciiType", "BytesType"): return native.TYPE_BYTES, 0
     raise native.UnsupportedError(native.EUNSUPPORTED, "type outside the supported envelope: " + type_string)
 
+def _split_args(inner: str):
+    out, depth, cur = [], 0, ""
+    for ch in inner:
+        if ch == "(": depth += 1
+        if ch == ")": depth -= 1
+        if ch == "," and depth == 0: out.append(cur.strip()); cur = ""
+        else: cur += ch
+    if cur.strip(): out.append(cur.strip())
+    return out
+
+def is_complex(type_string: str) -> bool:
+    """multi-cell column: a non-frozen collection (ColumnMetadata.isComplex = type.isMultiCell, S/schema/ColumnMetadata.java)"""
+    t = type_string[len(MARSHAL):] if type_string.startswith(MARSHAL) else type_string
+    return t.startswith(("MapType(", "SetType(", "ListType("))
+
+def column_class(type_string: str):
+    """(type, fixed_len) of a column for the manifest: simple columns as type_class; multi-cell collections as
+    B200C_COLUMN_COMPLEX(value class, path class) / B200C_COLUMN_FIXED(value length, path length) — cell path = map key / set element /
+    list timeuuid, cell value = map value / nothing / list element (CollectionType.nameComparator / valueComparator)."""
+    t = type_string[len(MARSHAL):] if type_string.startswith(MARSHAL) else type_string
+    if t.startswith("FrozenType("): return native.TYPE_BYTES, 0                    # a frozen collection / UDT is one opaque value
+    if not is_complex(type_string):
+        if t.startswith("UserType(") or t.startswith("CounterColumnType"): raise native.UnsupportedError(native.EUNSUPPORTED, "type outside the supported envelope: " + type_string)
+        return type_class(type_string)
+    kind, inner = t.split("(", 1); args = _split_args(inner[:-1])
+    def cls(a):
+        a2 = a[len(MARSHAL):] if a.startswith(MARSHAL) else a
+        if a2.startswith("FrozenType("): return native.TYPE_BYTES, 0
+        return type_class(a)
+    if kind == "MapType": (pt, pl), (vt, vl) = cls(args[0]), cls(args[1])
+    elif kind == "SetType": (pt, pl), (vt, vl) = cls(args[0]), (native.TYPE_BYTES, 0)
+    else: (pt, pl), (vt, vl) = (native.TYPE_TIMEUUID, 16), cls(args[0])
+    return vt | ((pt + 1) << 8), vl | (pl << 16)
+
 PARTITIONER_IDS = {"org.apache.cassandra.dht.Murmur3Partitioner": native.PARTITIONER_MURMUR3,
                    "org.apache.cassandra.dht.ByteOrderedPartitioner": native.PARTITIONER_BYTE_ORDERED}
 

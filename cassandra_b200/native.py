@@ -12,7 +12,8 @@ MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS, MAX_STATIC_COLUMNS = 8, 64, 64, 16
 ABI_VERSION = 2
 PARTITIONER_MURMUR3, PARTITIONER_BYTE_ORDERED = 0, 1
 PSIZE_BUCKETS, CELLS_BUCKETS, HLL_P, TDROP_CAP = 156, 119, 13, 512
-TYPE_BYTES, TYPE_FIXED_SIGNED, TYPE_FIXED_BYTES, TYPE_VAR_SIGNED = 0, 1, 2, 3
+TYPE_BYTES, TYPE_FIXED_SIGNED, TYPE_FIXED_BYTES, TYPE_VAR_SIGNED, TYPE_TIMEUUID = 0, 1, 2, 3, 4
+MAX_COMPLEX_COLUMNS = 8
 
 class B200CError(RuntimeError):
     def __init__(self, code, msg, corruption=None):

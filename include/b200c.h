@@ -128,12 +128,22 @@ enum {
     B200C_TYPE_BYTES = 0,     /* variable length, unsigned lexicographic compare (text, ascii, blob, varchar) */
     B200C_TYPE_FIXED_SIGNED = 1, /* fixed length big-endian two's complement, signed compare (bigint 8, int 4, smallint 2, tinyint 1, timestamp 8, counter n/a) */
     B200C_TYPE_FIXED_BYTES = 2,  /* fixed length, unsigned lexicographic compare (boolean 1, and any fixed type used only as a value) */
-    B200C_TYPE_VAR_SIGNED = 3    /* variable length payload holding a fixed-width signed int: empty value sorts first (LongType with empty) */
+    B200C_TYPE_VAR_SIGNED = 3,   /* variable length payload holding a fixed-width signed int: empty value sorts first (LongType with empty) */
+    B200C_TYPE_TIMEUUID = 4      /* 16 bytes, TimeUUIDType.compareCustom (S/db/marshal/TimeUUIDType.java): timestamp fields first — cell paths of lists only */
 };
+/* A multi-cell (complex) column — non-frozen map / set / list — stores one cell per element, each with a CELL PATH (the map key, the set
+ * element, the list's timeuuid), and an optional complex deletion (S/db/rows/ComplexColumnData.java, UnfilteredSerializer.java:271-280,
+ * Cell.java:268-305). Same struct, no layout change: `type` carries the class of the cell VALUES in bits 0-7 and, for a complex column,
+ * 1 + the class of the cell PATHS in bits 8-15 (0 = simple column); `fixed_len` the values' fixed length in bits 0-15 and the paths'
+ * in bits 16-31. In a SerializationHeader the simple columns come first, then the complex ones, each group in name order
+ * (ColumnMetadata.comparisonOrder): column_map must follow that order. Complex static columns, counters and non-frozen UDTs are refused. */
+#define B200C_COLUMN_COMPLEX(value_type, path_type) ((value_type) | (((path_type) + 1) << 8))
+#define B200C_COLUMN_FIXED(value_len, path_len)     ((value_len) | ((path_len) << 16))
+enum { B200C_MAX_COMPLEX_COLUMNS = 8 };
 
 typedef struct b200c_column {
-    int32_t  type;            /* B200C_TYPE_* */
-    int32_t  fixed_len;       /* value length in bytes if fixed, else 0 (AbstractType.valueLengthIfFixed) */
+    int32_t  type;            /* B200C_TYPE_* (complex columns: B200C_COLUMN_COMPLEX) */
+    int32_t  fixed_len;       /* value length in bytes if fixed, else 0 (AbstractType.valueLengthIfFixed); complex columns: B200C_COLUMN_FIXED */
 } b200c_column;
 
 typedef struct b200c_encoding_stats {   /* S/db/rows/EncodingStats.java: base values the deltas in the files are against */
@@ -298,10 +308,14 @@ typedef struct b200c_result {
 } b200c_result;
 
 /* flags: bit0 = input/outputs buffers are DEVICE pointers (inputs resident in HBM; used for the kernel-only metric).
-   With HOST buffers, one output file (max_sstable_bytes == 0) and summary_positions on every input, the call streams: Index.db is
-   copied first, then Data.db chunk ranges token range by token range while earlier ranges are already being merged, compressed and
-   copied back (pin the buffers with b200c_host_register, pageable memory serialises the copies). Every output byte is the same as
-   in the one-piece run. Buffers must stay valid until the call returns; nothing is in flight afterwards, whatever the return code. */
+   With HOST buffers, one output file (max_sstable_bytes == 0) and summary_positions on every input, the call streams: the token range
+   is cut into pieces at tokens of Summary.db samples, and piece by piece the Index.db slice between the samples that bracket the
+   piece (what a ranged scanner seeks to, SSTableReader.getPositionsForRanges), its Summary positions and the Data.db chunks it
+   describes are copied while earlier pieces are already being parsed, merged, compressed and copied back (pin the buffers with
+   b200c_host_register, pageable memory serialises the copies). Every output byte is the same as in the one-piece run. Summary
+   positions stay hints: if they do not parse or their slices do not tile the file the call runs as one piece; a slice whose first
+   entry lies inside the piece's token range (samples that lie about their tokens) is refused with B200C_ECORRUPT.
+   Buffers must stay valid until the call returns; nothing is in flight afterwards, whatever the return code. */
 int          b200c_compact(b200c_ctx*, const b200c_manifest*, b200c_result*, int flags);
 
 /* the order token the engine derives from a partition key (host function, no device needed): Murmur3Partitioner.getToken

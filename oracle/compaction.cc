@@ -53,6 +53,7 @@ struct Val { const uint8_t* p = nullptr; int32_t len = 0; bool null = false; };
 struct Clust { uint8_t kind = 4; int n = 0; Val v[B200C_MAX_CLUSTERING]; };
 struct CellV {
     int col; int64_t ts; int32_t ttl; int64_t ldt; const uint8_t* val; int32_t vlen;
+    const uint8_t* path = nullptr; int32_t plen = 0;                   // cell path: cells of multi-cell columns only (Cell.path())
     bool tombstone() const { return ldt != NO_DEL && ttl == 0; }       // AbstractCell.java:58-61
     bool expiring() const { return ttl != 0; }
     bool is_live(int64_t now) const { return ldt == NO_DEL || (ttl != 0 && now < ldt); }   // :53-56
@@ -61,7 +62,11 @@ struct Unf {
     bool is_row = true;
     Clust c;
     // row
-    Live info; DT del; std::vector<CellV> cells;
+    Live info; DT del; std::vector<CellV> cells;        // cells in (column, path) order
+    std::vector<std::pair<int, DT>> cdel;             // multi-cell columns of this row that carry a complex deletion (non-live), by column
+    bool has_column(int col) const { for (const CellV& c : cells) if (c.col == col) return true; for (auto& d : cdel) if (d.first == col) return true; return false; }
+    DT complex_deletion(int col) const { for (auto& d : cdel) if (d.first == col) return d.second; return DT(); }
+    bool has_data() const { return !cells.empty() || !cdel.empty(); }
     // marker: bound -> dt_open or dt_close by kind; boundary -> both
     DT m_close, m_open;
 };
@@ -77,11 +82,26 @@ struct Schema {
     int nclust; b200c_column clust[B200C_MAX_CLUSTERING];
     int ncols; b200c_column cols[B200C_MAX_COLUMNS];
     int nstat; b200c_column stat[B200C_MAX_STATIC_COLUMNS];      // static columns (SerializationHeader.columns(true))
+    int ncomplex = 0;                                             // multi-cell columns among cols[] (they follow the simple ones)
 };
 
+// multi-cell columns (include/b200c.h B200C_COLUMN_COMPLEX / _FIXED): class and fixed length of the cell values / of the cell paths
+static inline bool col_complex(const b200c_column& t) { return ((t.type >> 8) & 0xFF) != 0; }
+static inline b200c_column col_value_type(const b200c_column& t) { return b200c_column{t.type & 0xFF, t.fixed_len & 0xFFFF}; }
+static inline b200c_column col_path_type(const b200c_column& t) { return b200c_column{((t.type >> 8) & 0xFF) - 1, (int32_t)((uint32_t)t.fixed_len >> 16)}; }
 // AbstractType.compare for the supported comparison classes (S/db/marshal/AbstractType.java:212-215; LongType.compareLongs:
 // empty < non-empty, first byte signed then unsigned bytes; BytesType/UTF8Type: unsigned lexicographic)
 static int compare_value(const b200c_column& t, const Val& a, const Val& b) {
+    if (t.type == B200C_TYPE_TIMEUUID) {              // AbstractTimeUUIDType.compareCustom S/db/marshal/AbstractTimeUUIDType.java:58-87,126-144
+        const bool pa = a.len == 16, pb = b.len == 16;
+        if (!(pa && pb)) return pa ? 1 : (pb ? -1 : 0);
+        auto be64 = [](const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 8; i++) v = (v << 8) | p[i]; return v; };
+        auto reorder = [](uint64_t x) { return (int64_t)((x << 48) | ((x << 16) & 0xFFFF00000000ull) | (x >> 32)); };
+        const int64_t m1 = reorder(be64(a.p)), m2 = reorder(be64(b.p));
+        if (m1 != m2) return m1 < m2 ? -1 : 1;
+        const int64_t l1 = (int64_t)(be64(a.p + 8) ^ 0x0080808080808080ull), l2 = (int64_t)(be64(b.p + 8) ^ 0x0080808080808080ull);
+        return l1 == l2 ? 0 : (l1 < l2 ? -1 : 1);
+    }
     if (t.type == B200C_TYPE_FIXED_SIGNED || t.type == B200C_TYPE_VAR_SIGNED) {
         if (a.len == 0 || b.len == 0) return a.len == 0 ? (b.len == 0 ? 0 : -1) : 1;
         int d = (int)(int8_t)a.p[0] - (int)(int8_t)b.p[0];
@@ -208,35 +228,54 @@ static void read_row_body(Reader& r, Source& src, uint8_t flags, int ncols_in, c
         if (ncols_in >= 64) throw Unsupported{">= 64 columns"};
         missing = r.vint();
     }
-    u.cells.clear();
-    for (int i = 0; i < ncols_in; i++) {
-        if ((missing >> i) & 1) continue;
-        int oc = colmap[i];
-        const b200c_column& t = types[oc];
-        uint8_t cf = r.u8();                              // Cell.Serializer.deserialize: S/db/rows/Cell.java:307-349
+    u.cells.clear(); u.cdel.clear();
+    auto read_cell = [&](int oc, const b200c_column& t, bool complex) {      // Cell.Serializer.deserialize: S/db/rows/Cell.java:307-349
+        const b200c_column vt = col_value_type(t);
+        uint8_t cf = r.u8();
         bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
         CellV c; c.col = oc;
         c.ts = use_ts ? u.info.ts : (int64_t)(r.vint() + (uint64_t)hs.min_timestamp);
         c.ldt = use_ttl ? u.info.ldt : ((deleted || expiring) ? (int64_t)r.vint32() + hs.min_local_deletion_time : NO_DEL);
         c.ttl = use_ttl ? u.info.ttl : (expiring ? r.vint32() + hs.min_ttl : 0);
+        if (complex) {                                   // :330-332 column.cellPathSerializer().deserialize: CollectionPathSerializer = vint length + bytes (fixed-length types: bare)
+            const b200c_column pt = col_path_type(t);
+            int plen = pt.fixed_len > 0 ? pt.fixed_len : (int)r.vint32();
+            if (plen < 0) throw Corrupt{src.idx, 4, 0, 0, "negative path length"};
+            c.path = r.bytes(plen); c.plen = plen;
+        }
         c.val = r.p; c.vlen = 0;
         if (has_value) {
-            int len = t.fixed_len > 0 ? t.fixed_len : (int)r.vint32();
+            int len = vt.fixed_len > 0 ? vt.fixed_len : (int)r.vint32();
             if (len < 0) throw Corrupt{src.idx, 4, 0, 0, "negative value length"};
             c.val = r.bytes(len); c.vlen = len;
         }
         if (c.ttl < 0) throw Corrupt{src.idx, 4, 0, 0, "Invalid TTL"};
         if (c.ldt != NO_DEL) c.ldt = decode_ldt(c.ldt, c.ttl);
         u.cells.push_back(c);
+    };
+    for (int i = 0; i < ncols_in; i++) {
+        if ((missing >> i) & 1) continue;
+        int oc = colmap[i];
+        const b200c_column& t = types[oc];
+        if (!col_complex(t)) { read_cell(oc, t, false); continue; }
+        // UnfilteredSerializer.readComplexColumn :652-672: [complex deletion when the row says HAS_COMPLEX_DELETION] vint count, cells.
+        // ComplexColumnData.Builder.build :350-356: a column with a live deletion and no cell does not exist.
+        DT cd;
+        if (flags & 0x40) cd = read_delta_dt(r, hs);
+        int64_t count = (int64_t)r.vint32();
+        if (count < 0) throw Corrupt{src.idx, 4, 0, 0, "negative cell count"};
+        for (int64_t k = 0; k < count; k++) read_cell(oc, t, true);
+        if (!cd.live()) u.cdel.push_back({oc, cd});
     }
-    std::sort(u.cells.begin(), u.cells.end(), [](const CellV& a, const CellV& b) { return a.col < b.col; });
+    std::stable_sort(u.cells.begin(), u.cells.end(), [](const CellV& a, const CellV& b) { return a.col < b.col; });
+    std::sort(u.cdel.begin(), u.cdel.end(), [](const std::pair<int, DT>& a, const std::pair<int, DT>& b) { return a.first < b.first; });
 }
 static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u);
 static bool read_unfiltered(Source& src, const Schema& s, Unf& u) {
     // UnfilteredSerializer.deserialize :433-447: empty rows (e.g. all columns dropped) are skipped at read time
     for (;;) {
         if (!read_unfiltered_one(src, s, u)) return false;
-        if (u.is_row && u.info.empty() && u.del.live() && u.cells.empty()) continue;
+        if (u.is_row && u.info.empty() && u.del.live() && !u.has_data()) continue;
         return true;
     }
 }
@@ -262,7 +301,7 @@ static bool read_unfiltered_one(Source& src, const Schema& s, Unf& u) {
         uint8_t ext = (flags & 0x80) ? r.u8() : 0;
         if (ext & 0x01) throw Corrupt{src.idx, 4, 0, 0, "static flag on a clustered row"};      // UnfilteredSerializer.deserialize :477-479
         if (ext & 0x02) throw Unsupported{"shadowable deletion"};
-        if (flags & 0x40) throw Unsupported{"complex deletion"};
+        if ((flags & 0x40) && !s.ncomplex) throw Unsupported{"complex deletion"};       // (a table without multi-cell columns has none)
         u.c.kind = K_CLUSTERING;
         read_clust_values(r, s, s.nclust, u.c);
         read_row_body(r, src, flags, in.ncolumns, in.column_map, s.cols, u);
@@ -442,7 +481,11 @@ static bool purge_row(Unf& r, const Purger& pg) {
     size_t w = 0;
     for (size_t i = 0; i < r.cells.size(); i++) if (purge_cell(r.cells[i], pg)) r.cells[w++] = r.cells[i];
     r.cells.resize(w);
-    return !(r.info.empty() && r.del.live() && r.cells.empty());
+    // ComplexColumnData.purge S/db/rows/ComplexColumnData.java:212-216 (+ update :229-238): a purgeable complex deletion becomes LIVE; the column goes when nothing is left
+    w = 0;
+    for (size_t i = 0; i < r.cdel.size(); i++) if (!pg.should_purge(r.cdel[i].second)) r.cdel[w++] = r.cdel[i];
+    r.cdel.resize(w);
+    return !(r.info.empty() && r.del.live() && !r.has_data());
 }
 // PurgeFunction.applyToMarker :116-143. Returns false if the marker disappears.
 static bool purge_marker(Unf& m, const Purger& pg) {
@@ -477,8 +520,8 @@ static const CellV& reconcile(const CellV& l, const CellV& r) {
     return c >= 0 ? l : r;
 }
 
-// Row.Merger.merge: S/db/rows/Row.java:730-781 (simple columns only: ColumnDataReducer :838-849). Returns false for null.
-static bool merge_rows(std::vector<Unf*>& versions, DT active, Unf& out) {
+// Row.Merger.merge: S/db/rows/Row.java:730-781; ColumnDataReducer.getReduced :838-883 (simple cell / multi-cell column). Returns false for null.
+static bool merge_rows(std::vector<Unf*>& versions, DT active, Unf& out, const Schema* sc = nullptr, bool stat = false) {
     if (versions.size() == 1 && active.live()) { out = *versions[0]; return true; }
     Live info; DT del;
     for (Unf* v : versions) {
@@ -487,22 +530,53 @@ static bool merge_rows(std::vector<Unf*>& versions, DT active, Unf& out) {
     }
     if (del.supersedes(active)) active = del; else del = DT();
     if (active.deletes(info.ts)) info = Live();          // deletes(LivenessInfo) = deletes(timestamp); EMPTY ts = MIN is always "deleted" but stays EMPTY
-    out.is_row = true; out.c = versions[0]->c; out.info = info; out.del = del; out.cells.clear();
+    out.is_row = true; out.c = versions[0]->c; out.info = info; out.del = del; out.cells.clear(); out.cdel.clear();
     size_t cur[B200C_MAX_INPUTS] = {0};
-    for (;;) {
-        int col = INT_MAX;
-        for (size_t i = 0; i < versions.size(); i++) if (cur[i] < versions[i]->cells.size()) col = std::min(col, versions[i]->cells[cur[i]].col);
-        if (col == INT_MAX) break;
-        const CellV* merged = nullptr;
-        for (size_t i = 0; i < versions.size(); i++) {
-            if (cur[i] < versions[i]->cells.size() && versions[i]->cells[cur[i]].col == col) {
-                const CellV& c = versions[i]->cells[cur[i]++];
-                if (!active.deletes(c.ts)) merged = merged ? &reconcile(*merged, c) : &c;
+    uint64_t cols_present = 0;                             // columns any version has data for (a multi-cell column may consist of its deletion only)
+    for (Unf* v : versions) { for (const CellV& c : v->cells) cols_present |= 1ull << c.col; for (auto& d : v->cdel) cols_present |= 1ull << d.first; }
+    for (int col = 0; col < 64; col++) {
+        if (!((cols_present >> col) & 1)) continue;
+        const bool complex = sc && !stat && col_complex(sc->cols[col]);
+        if (!complex) {
+            const CellV* merged = nullptr;
+            for (size_t i = 0; i < versions.size(); i++) {
+                if (cur[i] < versions[i]->cells.size() && versions[i]->cells[cur[i]].col == col) {
+                    const CellV& c = versions[i]->cells[cur[i]++];
+                    if (!active.deletes(c.ts)) merged = merged ? &reconcile(*merged, c) : &c;
+                }
             }
+            if (merged) out.cells.push_back(*merged);
+            continue;
         }
-        if (merged) out.cells.push_back(*merged);
+        // multi-cell column :851-883: the strongest complex deletion; kept (and it shadows the cells) only if it supersedes the active deletion
+        DT cd;
+        for (Unf* v : versions) { DT d = v->complex_deletion(col); if (d.supersedes(cd)) cd = d; }
+        DT cell_del = active;
+        if (cd.supersedes(active)) cell_del = cd; else cd = DT();
+        if (!cd.live()) out.cdel.push_back({col, cd});
+        // MergeIterator over the versions' cells in cell-path order (Cell.comparator = column.cellPathComparator())
+        const b200c_column pt = col_path_type(sc->cols[col]);
+        for (;;) {
+            const CellV* head = nullptr;
+            for (size_t i = 0; i < versions.size(); i++) {
+                if (cur[i] >= versions[i]->cells.size() || versions[i]->cells[cur[i]].col != col) continue;
+                const CellV& c = versions[i]->cells[cur[i]];
+                if (!head || compare_value(pt, Val{c.path, c.plen, false}, Val{head->path, head->plen, false}) < 0) head = &c;
+            }
+            if (!head) break;
+            const Val hp{head->path, head->plen, false};
+            const CellV* merged = nullptr;
+            for (size_t i = 0; i < versions.size(); i++) {                 // CellReducer :900-918, in source order
+                if (cur[i] >= versions[i]->cells.size() || versions[i]->cells[cur[i]].col != col) continue;
+                const CellV& c = versions[i]->cells[cur[i]];
+                if (compare_value(pt, Val{c.path, c.plen, false}, hp) != 0) continue;
+                cur[i]++;
+                if (!cell_del.deletes(c.ts)) merged = merged ? &reconcile(*merged, c) : &c;
+            }
+            if (merged) out.cells.push_back(*merged);
+        }
     }
-    return !(out.info.empty() && out.del.live() && out.cells.empty());
+    return !(out.info.empty() && out.del.live() && !out.has_data());
 }
 
 // RangeTombstoneMarker.Merger: S/db/rows/RangeTombstoneMarker.java:72-199 (forward order)
@@ -585,8 +659,10 @@ struct Meta {
     void partition_deletion(const DT& d) { if (!d.live()) has_partition_deletions = true; update(d); }                                    // :230-235
     void row(const Unf& u) {                                                // Rows.collectStats S/db/rows/Rows.java:102-113
         update(u.info); update(u.del);
-        for (const CellV& c : u.cells) update(c);
-        total_columns_set += u.cells.size(); total_rows++;
+        for (auto& d : u.cdel) update(d.second);                              // StatsAccumulation.accumulateOnColumnData S/db/rows/Rows.java:66-82
+        int cols_with_cells = 0, last = -1;
+        for (const CellV& c : u.cells) { update(c); if (c.col != last) { cols_with_cells++; last = c.col; } }
+        total_columns_set += cols_with_cells; total_rows++;
     }
     void marker(const Unf& u) {                                             // SortedTableWriter.addRangeTomstoneMarker :222-238
         if (kind_is_boundary(u.c.kind)) { update(u.m_close); update(u.m_open); }
@@ -732,7 +808,11 @@ struct Writer {
         if (!u.info.empty()) flags |= 0x04;
         if (u.info.expiring()) flags |= 0x08;
         if (!u.del.live()) flags |= 0x10;
-        if ((int)u.cells.size() == ncols) flags |= 0x20;
+        int present = 0, last = -1;
+        for (const CellV& c : u.cells) if (c.col != last) { present++; last = c.col; }
+        for (auto& d : u.cdel) { bool has_cell = false; for (const CellV& c : u.cells) if (c.col == d.first) has_cell = true; if (!has_cell) present++; }
+        if (present == ncols) flags |= 0x20;                  // row.columnCount() == headerColumns.size() :170-171
+        if (!u.cdel.empty()) flags |= 0x40;                   // row.hasComplexDeletion() :166-167, BTreeRow.java:400-405
         return flags;
     }
     void write_row_body(OutBuf& body, const Unf& u, int flags, int ncols, const b200c_column* types) {      // serializeRowBody :213-269
@@ -744,9 +824,34 @@ struct Writer {
             if (ncols >= 64) throw Unsupported{">= 64 columns"};
             uint64_t missing = (1ull << ncols) - 1;
             for (const CellV& c : u.cells) missing &= ~(1ull << c.col);
+            for (auto& d : u.cdel) missing &= ~(1ull << d.first);
             body.vint(missing);
         }
-        for (const CellV& c : u.cells) {                  // Cell.Serializer.serialize: S/db/rows/Cell.java:268-305
+        // multi-cell columns (writeComplexColumn :271-280): [complex deletion when the row has any] vint cell count, then the cells. A column that
+        // consists of its deletion only has no cell to hang the header on: written when the walk passes its position.
+        size_t next_cd = 0; int open_col = -1;
+        auto complex_head = [&](int col) {
+            if (flags & 0x40) write_delta_dt(body, u.complex_deletion(col));
+            uint64_t cnt = 0; for (const CellV& c : u.cells) if (c.col == col) cnt++;
+            body.vint(cnt);
+        };
+        auto flush_deletion_only = [&](int upto) {             // complex columns < upto that have a deletion but no cell
+            for (; next_cd < u.cdel.size() && u.cdel[next_cd].first < upto; next_cd++) {
+                bool has_cell = false; for (const CellV& c : u.cells) if (c.col == u.cdel[next_cd].first) has_cell = true;
+                if (!has_cell) complex_head(u.cdel[next_cd].first);
+            }
+        };
+        for (size_t ci = 0; ci <= u.cells.size(); ci++) {
+            if (ci == u.cells.size()) { flush_deletion_only(INT_MAX); break; }
+            const CellV& c = u.cells[ci];
+            const bool complex = col_complex(types[c.col]);
+            if (complex && c.col != open_col) { flush_deletion_only(c.col); complex_head(c.col); open_col = c.col; }
+            else if (!complex) flush_deletion_only(c.col);
+            write_cell(body, u, c, types);
+        }
+    }
+    void write_cell(OutBuf& body, const Unf& u, const CellV& c, const b200c_column* types) {      // Cell.Serializer.serialize: S/db/rows/Cell.java:268-305
+        {
             bool has_value = c.vlen > 0, deleted = c.tombstone(), expiring = c.expiring();
             bool use_ts = !u.info.empty() && c.ts == u.info.ts;
             bool use_ttl = expiring && u.info.expiring() && c.ttl == u.info.ttl && c.ldt == u.info.ldt;
@@ -759,7 +864,8 @@ struct Writer {
             if (!use_ts) body.vint((uint64_t)c.ts - (uint64_t)m->out_stats.min_timestamp);
             if ((deleted || expiring) && !use_ttl) body.vint((uint64_t)(int64_t)(int32_t)(c.ldt - m->out_stats.min_local_deletion_time));
             if (expiring && !use_ttl) body.vint((uint64_t)(int64_t)(c.ttl - m->out_stats.min_ttl));
-            if (has_value) { if (types[c.col].fixed_len <= 0) body.vint((uint64_t)c.vlen); body.put(c.val, c.vlen); }
+            if (col_complex(types[c.col])) { if (col_path_type(types[c.col]).fixed_len <= 0) body.vint((uint64_t)c.plen); body.put(c.path, c.plen); }      // :300-301 cellPathSerializer
+            if (has_value) { if (col_value_type(types[c.col]).fixed_len <= 0) body.vint((uint64_t)c.vlen); body.put(c.val, c.vlen); }
         }
     }
 
@@ -857,6 +963,13 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
     }
     Schema sc; sc.nclust = m->nclustering; sc.ncols = m->ncolumns; sc.nstat = m->nstatic_columns;
     memcpy(sc.clust, m->clustering, sizeof(sc.clust)); memcpy(sc.cols, m->columns, sizeof(sc.cols)); memcpy(sc.stat, m->static_columns, sizeof(sc.stat));
+    for (int k = 0; k < m->ncolumns; k++) {                                // multi-cell columns follow the simple ones (ColumnMetadata.comparisonOrder)
+        if (col_complex(sc.cols[k])) sc.ncomplex++; else if (sc.ncomplex) return B200C_EINVAL;
+        const int pt = col_path_type(sc.cols[k]).type;
+        if (col_complex(sc.cols[k]) && (pt < 0 || pt > B200C_TYPE_TIMEUUID)) return B200C_EINVAL;
+    }
+    if (sc.ncomplex > B200C_MAX_COMPLEX_COLUMNS) return B200C_EUNSUPPORTED;
+    for (int k = 0; k < m->nstatic_columns; k++) if (col_complex(sc.stat[k])) return B200C_EUNSUPPORTED;
     g_partitioner = m->partitioner;
     std::vector<Source> srcs(m->ninputs);
     uint64_t bytes_read = 0;
@@ -928,7 +1041,7 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
                 Unf out; bool have;
                 if (heads[b].is_row) {                         // MergeReducer.getReduced :575-591
                     std::vector<Unf*> vs; for (size_t g : eq) vs.push_back(&heads[g]);
-                    have = merge_rows(vs, mm.active(), out);
+                    have = merge_rows(vs, mm.active(), out, &sc);
                 } else {
                     std::vector<std::pair<int, Unf*>> vs; for (size_t g : eq) vs.push_back({(int)g, &heads[g]});
                     have = mm.merge(vs, out);

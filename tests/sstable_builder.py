@@ -3,7 +3,7 @@ Layouts follow SURVEY Appendix A: SortedTablePartitionWriter.java:97-166, Unfilt
 ClusteringPrefix.java:455-477, BigFormatPartitionWriter.java:128-251, RowIndexEntry.java:625-642, IndexInfo.java:107-117."""
 import struct
 import oracle_lib as O
-from cassandra_b200.io.sstable import SSTable, MARSHAL, type_class, TIMESTAMP_EPOCH, DELETION_TIME_EPOCH, NO_DELETION_TIME
+from cassandra_b200.io.sstable import SSTable, MARSHAL, type_class, column_class, is_complex, TIMESTAMP_EPOCH, DELETION_TIME_EPOCH, NO_DELETION_TIME
 from cassandra_b200.io.compress import CompressionMetadata
 
 LIVE = None
@@ -17,13 +17,17 @@ def i32s(v):            # writeUnsignedVInt32(int): sign-extended int
     return vint(v)
 
 class Cell:
-    def __init__(self, col, ts, value=b"", ttl=0, ldt=NO_DELETION_TIME):
-        self.col = col; self.ts = ts; self.value = value; self.ttl = ttl; self.ldt = ldt
+    """path: the cell path of a cell of a multi-cell column (map key / set element / list timeuuid), None for simple columns"""
+    def __init__(self, col, ts, value=b"", ttl=0, ldt=NO_DELETION_TIME, path=None):
+        self.col = col; self.ts = ts; self.value = value; self.ttl = ttl; self.ldt = ldt; self.path = path
     @staticmethod
-    def tombstone(col, ts, ldt): return Cell(col, ts, b"", 0, ldt)
+    def tombstone(col, ts, ldt, path=None): return Cell(col, ts, b"", 0, ldt, path)
 class Row:
-    def __init__(self, ck, cells=(), ts=NO_TS, ttl=0, ldt=NO_DELETION_TIME, deletion=LIVE):
+    """complex_deletions: {column index: (markedForDeleteAt, localDeletionTime)} of multi-cell columns. The cells of a multi-cell column must be
+    given in path order (the writer does not know the path comparator)."""
+    def __init__(self, ck, cells=(), ts=NO_TS, ttl=0, ldt=NO_DELETION_TIME, deletion=LIVE, complex_deletions=None):
         self.ck = tuple(ck); self.cells = list(cells); self.ts = ts; self.ttl = ttl; self.ldt = ldt; self.deletion = deletion
+        self.complex_deletions = dict(complex_deletions or {})
 class Marker:
     """kind: bound/boundary kind ordinal; values: clustering prefix; close/open: (markedForDeleteAt, localDeletionTime) or None"""
     def __init__(self, kind, values, close=None, open=None):
@@ -36,10 +40,12 @@ class Partition:
 class Schema:
     def __init__(self, clustering_types, columns, static_columns=()):
         self.clustering_types = [t if "." in t else MARSHAL + t for t in clustering_types]
-        self.columns = sorted([(n if isinstance(n, bytes) else n.encode(), t if "." in t else MARSHAL + t) for n, t in columns])
+        self.columns = sorted([(n if isinstance(n, bytes) else n.encode(), t if "." in t else MARSHAL + t) for n, t in columns], key=lambda nt: (is_complex(nt[1]), nt[0]))
         self.static_columns = sorted([(n if isinstance(n, bytes) else n.encode(), t if "." in t else MARSHAL + t) for n, t in static_columns])
         self.cfixed = [type_class(t)[1] for t in self.clustering_types]
-        self.vfixed = [type_class(t)[1] for _, t in self.columns]
+        self.vfixed = [column_class(t)[1] & 0xFFFF for _, t in self.columns]
+        self.pfixed = [column_class(t)[1] >> 16 for _, t in self.columns]
+        self.complex = [is_complex(t) for _, t in self.columns]
         self.sfixed = [type_class(t)[1] for _, t in self.static_columns]
     def col_index(self, name):
         name = name if isinstance(name, bytes) else name.encode()
@@ -86,17 +92,32 @@ class Builder:
         if u.ts != NO_TS: flags |= 0x04
         if u.ttl: flags |= 0x08
         if u.deletion is not None: flags |= 0x10
-        cells = sorted(u.cells, key=lambda c: c.col)
-        if len(cells) == len(columns): flags |= 0x20
+        cells = sorted(u.cells, key=lambda c: c.col)                       # (stable: the cells of a multi-cell column keep their path order)
+        cdel = {} if static else u.complex_deletions
+        present = sorted({c.col for c in cells} | set(cdel))
+        if cdel: flags |= 0x40                                              # HAS_COMPLEX_DELETION
+        if len(present) == len(columns): flags |= 0x20
         body = bytearray()
         if flags & 0x04: body += vint(u.ts - self.min_ts)
         if flags & 0x08: body += i32s(u.ttl - self.min_ttl) + i32s(u.ldt - self.min_ldt)
         if flags & 0x10: body += self.delta_dt(u.deletion)
         if not flags & 0x20:
             missing = (1 << len(columns)) - 1
-            for c in cells: missing &= ~(1 << c.col)
+            for col in present: missing &= ~(1 << col)
             body += vint(missing)
-        for c in cells:
+        cx = (lambda col: (not static) and self.s.complex[col])
+        def cx_head(col):                                                   # UnfilteredSerializer.writeComplexColumn :271-280
+            out = bytearray()
+            if flags & 0x40: out += self.delta_dt(cdel.get(col, (NO_TS, NO_DELETION_TIME)))
+            out += vint(sum(1 for c in cells if c.col == col))
+            return out
+        order = []                                                          # (column, cell or None) in serialisation order
+        for col in present:
+            mine = [c for c in cells if c.col == col]
+            if cx(col): order.append((col, None)); order += [(col, c) for c in mine]
+            else: order += [(col, c) for c in mine]
+        for col, c in order:
+            if c is None: body += cx_head(col); continue
             deleted = c.ldt != NO_DELETION_TIME and c.ttl == 0; expiring = c.ttl != 0
             use_ts = u.ts != NO_TS and c.ts == u.ts
             use_ttl = expiring and u.ttl != 0 and c.ttl == u.ttl and c.ldt == u.ldt
@@ -105,6 +126,9 @@ class Builder:
             if not use_ts: body += vint(c.ts - self.min_ts)
             if (deleted or expiring) and not use_ttl: body += i32s(c.ldt - self.min_ldt)
             if expiring and not use_ttl: body += i32s(c.ttl - self.min_ttl)
+            if cx(col):                                                     # Cell.Serializer.serialize :300-301: the path precedes the value
+                if not self.s.pfixed[col]: body += vint(len(c.path))
+                body += c.path
             if c.value:
                 if not vfixed[c.col]: body += vint(len(c.value))
                 body += c.value

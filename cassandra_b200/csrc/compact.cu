@@ -587,7 +587,7 @@ template <bool EMIT> __device__ __forceinline__ void k4_epilogue(const K4Args& a
     a.st_munf[j] = (uint32_t)st.merged_unfiltereds; a.st_rows[j] = (uint32_t)st.rows_out;
 }
 
-template <int M_CAP, int NT, bool EMIT>
+template <int M_CAP, int NT, bool EMIT, bool CX = false>
 __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t lo, uint64_t hi) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     // per thread in shared memory: M_CAP cursors, then (for tables with <= K4_SMEM_COLS columns) the merged-row scratch; +8 bytes
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(NT) k_partition_thr(const K4Args a, uint64_t l
     StatAcc acc; const bool stats = a.sg != nullptr && a.mode == 1;
     if (stats) acc.init(a.P->now, a.td);
     if (m > (uint32_t)M_CAP) e = PERR_UNSUPPORTED;
-    else process_partition<EMIT>(*a.P, XlateGlobal(), a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e, stats ? &acc : nullptr);
+    else process_partition<EMIT, K4Cur, XlateGlobal, M_CAP, CX>(*a.P, XlateGlobal(), a.contrib, c0, m, a.upos, a.pbase, a.kp, a.klen, a.tok, dout, dcap, dposv, iout, nbf, ipf, ixs_cap, cur, open_dt, merged, out, st, e, stats ? &acc : nullptr);
     k4_epilogue<EMIT>(a, j, c0, out, st, e);
     if (stats && !e) stat_flush(a.sg, acc);
 }
@@ -961,7 +961,16 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     (void)bo;
     hp.ninputs = K; hp.nclust = m->nclustering; hp.ncols = m->ncolumns; hp.column_index_size = m->column_index_size > 0 ? m->column_index_size : 65536;
     for (int k = 0; k < m->nclustering; k++) { hp.ctype[k] = m->clustering[k].type; hp.cfix[k] = m->clustering[k].fixed_len; }
-    for (int k = 0; k < m->ncolumns; k++) hp.vfix[k] = m->columns[k].fixed_len;
+    for (int k = 0; k < m->ncolumns; k++) {                 // multi-cell columns: include/b200c.h B200C_COLUMN_COMPLEX / _FIXED; they follow the simple ones
+        const int ptype = ((m->columns[k].type >> 8) & 0xFF) - 1;
+        hp.vfix[k] = m->columns[k].fixed_len & 0xFFFF;
+        if (ptype >= 0) {
+            if (ptype > TYPE_TIMEUUID) { c->err = "cell path class"; return B200C_EINVAL; }
+            if (hp.ncx >= MAXCX) { c->err = "more than 8 multi-cell columns"; return B200C_EUNSUPPORTED; }
+            if (!hp.ncx) hp.cx_first = k;
+            hp.ptype[hp.ncx] = ptype; hp.pfix[hp.ncx] = (int32_t)((uint32_t)m->columns[k].fixed_len >> 16); hp.ncx++;
+        } else if (hp.ncx) { c->err = "simple column behind a multi-cell one (ColumnMetadata order: simple columns first)"; return B200C_EINVAL; }
+    }
     hp.nstat = m->nstatic_columns; hp.mcols = std::max(m->ncolumns, m->nstatic_columns);
     for (int k = 0; k < m->nstatic_columns; k++) hp.sfix[k] = m->static_columns[k].fixed_len;
     hp.o_min_ts = m->out_stats.min_timestamp; hp.o_min_ldt = m->out_stats.min_local_deletion_time; hp.o_min_ttl = m->out_stats.min_ttl;
@@ -1476,7 +1485,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_TRY(ws_typed(c, WS_STROWS, nparts + 1, &d_strows));
         B200C_TRY(ws_typed(c, WS_OVF, nparts + 1, &d_ovf));
         const size_t cols_s = hp.mcols <= K4_SMEM_COLS ? (size_t)hp.mcols * sizeof(MCell) : 0;
-        const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem12 = (size_t)64 * (12 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * hp.mcols * sizeof(MCell);
+        const size_t smem8 = (size_t)128 * (8 * SLOT_BYTES + cols_s + 8), smem12 = (size_t)64 * (12 * SLOT_BYTES + cols_s + 8), smem16 = (size_t)64 * (16 * SLOT_BYTES + cols_s + 8), smem64 = (size_t)32 * (64 * SLOT_BYTES + cols_s + 8), cell_smem32 = (size_t)4 * hp.mcols * sizeof(MCell);
         memset(&ka, 0, sizeof(ka));
         ka.P = dP; ka.contrib = d_contrib; ka.op_first = d_opfirst; ka.list = d_list; ka.upos = d_upos; ka.pbase = d_pbase; ka.kp = d_kp; ka.klen = d_klen; ka.tok = d_tok;
         ka.dsize = d_dsize; ka.ipay = d_ipay; ka.nblk = d_nblk; ka.ihead = d_ihead; ka.st_munf = d_stmunf; ka.st_rows = d_strows; ka.ovf = d_ovf;
@@ -1490,9 +1499,19 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         }
         // one launch per fan-in class over its slice of the sorted list
         const uint64_t np_ = nparts;
-        launch_k4 = [&, n_le8, n_le12, n_le16, n_le32, np_, smem8, smem12, smem16, cell_smem32](int mode) -> int {
+        launch_k4 = [&, n_le8, n_le12, n_le16, n_le32, np_, smem8, smem12, smem16, smem64, cell_smem32](int mode) -> int {
             ka.mode = mode;
             const bool emit = mode != 0;
+            if (hp.ncx) {
+                // tables with multi-cell (complex) columns: the CX instantiations of the thread kernels, for every fan-in (64 cursors per thread above 16);
+                // single serialisation pass only (the size-pass A/B mode is refused above)
+                if (!emit) { c->err = "B200C_K4_TWO_PASS with multi-cell columns"; return B200C_EUNSUPPORTED; }
+                if (n_le8) B200C_LAUNCH(c, (k_partition_thr<8, 128, true, true>), (unsigned)((n_le8 + 127) / 128), 128, smem8, ka, 0ull, n_le8);
+                if (n_le12 > n_le8) B200C_LAUNCH(c, (k_partition_thr<12, 64, true, true>), (unsigned)((n_le12 - n_le8 + 63) / 64), 64, smem12, ka, n_le8, n_le12);
+                if (n_le16 > n_le12) B200C_LAUNCH(c, (k_partition_thr<16, 64, true, true>), (unsigned)((n_le16 - n_le12 + 63) / 64), 64, smem16, ka, n_le12, n_le16);
+                if (np_ > n_le16) B200C_LAUNCH(c, (k_partition_thr<64, 32, true, true>), (unsigned)((np_ - n_le16 + 31) / 32), 32, smem64, ka, n_le16, np_);
+                return B200C_OK;
+            }
             if (n_le8) {
                 unsigned g = (unsigned)((n_le8 + 127) / 128);
                 if (emit) B200C_LAUNCH(c, (k_partition_thr<8, 128, true>), g, 128, smem8, ka, 0ull, n_le8);
@@ -1527,6 +1546,10 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             cudaFuncSetAttribute(k_partition_thr<12, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12);
             cudaFuncSetAttribute(k_partition_thr<16, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
             cudaFuncSetAttribute(k_partition_thr<16, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            cudaFuncSetAttribute(k_partition_thr<8, 128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            cudaFuncSetAttribute(k_partition_thr<12, 64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem12);
+            cudaFuncSetAttribute(k_partition_thr<16, 64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            cudaFuncSetAttribute(k_partition_thr<64, 32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
             // B200C_K4_CARVEOUT=percent of the SM's unified L1/shared memory left to shared memory (A/B: fewer resident blocks, more L1 for the
             // scattered reads of Data.db); unset: the driver sizes the carve-out for the most blocks that fit
             if (const char* e = getenv("B200C_K4_CARVEOUT")) { const int pct = atoi(e);
@@ -1550,7 +1573,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
                 B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
                 ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
-                const bool staged = []() { const char* e = getenv("B200C_K4_STAGED"); return e ? atoi(e) != 0 : (B200C_K4_STAGED_DEFAULT != 0); }();      // A/B switch (read per call)
+                const bool staged = !hp.ncx && []() { const char* e = getenv("B200C_K4_STAGED"); return e ? atoi(e) != 0 : (B200C_K4_STAGED_DEFAULT != 0); }();      // A/B switch (read per call; tables with multi-cell columns: thread kernels)
                 if (staged) {
                     // tile plan: exclusive scan of the input bytes, cut marks, scan of the marks, tile starts
                     uint64_t *d_inpos, *d_tscan; uint32_t *d_mark, *d_tstart; unsigned long long* d_nbig = (unsigned long long*)(d_stats + 1);

@@ -19,8 +19,8 @@
 
 namespace b200c {
 
-enum { MAXK = 64, MAXCOLS = 64, MAXCLUST = 8, MAXSTAT = 16 };
-enum { TYPE_BYTES = 0, TYPE_FIXED_SIGNED = 1, TYPE_FIXED_BYTES = 2, TYPE_VAR_SIGNED = 3 };
+enum { MAXK = 64, MAXCOLS = 64, MAXCLUST = 8, MAXSTAT = 16, MAXCX = 8 };
+enum { TYPE_BYTES = 0, TYPE_FIXED_SIGNED = 1, TYPE_FIXED_BYTES = 2, TYPE_VAR_SIGNED = 3, TYPE_TIMEUUID = 4 };
 enum { K_EXCL_END = 0, K_INCL_START = 1, K_EXCL_END_INCL_START = 2, K_STATIC = 3, K_CLUSTERING = 4, K_INCL_END_EXCL_START = 5, K_INCL_END = 6, K_EXCL_START = 7 };
 enum { PERR_NONE = 0, PERR_CORRUPT = 1, PERR_UNSUPPORTED = 2 };
 
@@ -42,6 +42,10 @@ struct CParams {
     int64_t o_min_ts, o_min_ldt; int32_t o_min_ttl;
     int32_t nstat, sfix[MAXSTAT];  // static columns of the output header (0: the table has none, no static rows anywhere)
     int32_t mcols;                 // max(ncols, nstat): cells of scratch a merged row needs
+    // multi-cell (complex) columns: the LAST ncx regular columns (ColumnMetadata.comparisonOrder puts them behind the simple ones); vfix[] of
+    // those is the fixed length of their cell VALUES, ptype / pfix class and fixed length of their cell PATHS
+    int32_t ncx, cx_first;
+    int32_t ptype[MAXCX], pfix[MAXCX];
     int32_t partitioner;           // 0 Murmur3Partitioner, 1 ByteOrderedPartitioner (tok[] then holds the sign-flipped 8-byte key prefix)
     int64_t now, gc_before, purge_max_ts;
     // optional purge table (b200c_manifest.purge_range_*): ascending token bounds and the threshold that applies up to each of them
@@ -213,7 +217,7 @@ template <class CUR> __device__ __noinline__ int cur_load_impl(const CParams& P,
         } else {
             if (flags & 0x80) c.ext = (uint8_t)(r.u8() & 0x03);
             if (c.ext & 0x01) { c.done = true; return PERR_CORRUPT; }       // a static row among the clustered ones (UnfilteredSerializer.deserialize :477-479)
-            if ((c.ext & 0x02) || (flags & 0x40)) { c.done = true; return PERR_UNSUPPORTED; }
+            if ((c.ext & 0x02) || ((flags & 0x40) && !P.ncx)) { c.done = true; return PERR_UNSUPPORTED; }      // shadowable deletion; HAS_COMPLEX_DELETION without multi-cell columns
             c.kind = K_CLUSTERING; c.n = (uint8_t)P.nclust;
         }
         c.ck_rel = (uint8_t)(r.p - c.pos);
@@ -460,8 +464,13 @@ template <bool EMIT> __device__ __forceinline__ void pw_end_unf(PWriter<EMIT>& w
     if ((w.d.pos - w.start) - w.block_start >= (uint64_t)P.column_index_size) pw_add_index_block(w, P);
 }
 
+struct CxVer { uint64_t cells, end; int64_t its, ildt; int32_t ittl; uint8_t flags, src; };      // one version of the row: where its columns start (behind the row header fields), its liveness (cells may say USE_ROW_TIMESTAMP / USE_ROW_TTL)
+struct CxCol { DT cd; uint32_t ncells; uint8_t pre, post; };                                     // merged + purged complex deletion, cells after the purge; column exists before / after the purge
+struct CxEmit { const CxVer* ver; int nver; bool as_is; DT active; const CxCol* col; const Purger* pg; };
+template <bool E> __device__ int cx_merge(const CParams& P, const Purger& pg, const CxVer* ver, int nver, bool as_is, DT active, int j,
+                                         const Live info, CxCol* sum, Sink<E>* s, bool row_has_cd, const CxCol* known, StatAcc* acc);      // (multi-cell columns, below)
 // row body: UnfilteredSerializer.serializeRowBody :213-269 + Cell.Serializer.serialize S/db/rows/Cell.java:268-305
-template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const CParams& P, int flags, Live info, DT del, const MCell* cells, int ncols, const int32_t* vfix) {
+template <bool E, bool CX = false> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const CParams& P, int flags, Live info, DT del, const MCell* cells, int ncols, const int32_t* vfix, const CxEmit* cx = nullptr) {
     if (flags & 0x04) s.vint((uint64_t)info.ts - (uint64_t)P.o_min_ts);
     if (flags & 0x08) { s.vint((uint64_t)(int64_t)(info.ttl - P.o_min_ttl)); s.vint((uint64_t)(int64_t)(int32_t)(info.ldt - P.o_min_ldt)); }
     if (flags & 0x10) write_delta_dt(s, P, del);
@@ -472,6 +481,10 @@ template <bool E> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const
     }
     for (int c = 0; c < ncols; c++) {
         const MCell& m = cells[c]; if (!m.present) continue;
+        if constexpr (CX) if (c >= P.cx_first) {          // writeComplexColumn :271-280 (cells[c].present = the column exists)
+            cx_merge<E>(P, *cx->pg, cx->ver, cx->nver, cx->as_is, cx->active, c - P.cx_first, info, nullptr, &s, (flags & 0x40) != 0, &cx->col[c - P.cx_first], nullptr);
+            continue;
+        }
         bool has_value = m.vlen > 0, deleted = m.ldt != I64_MAX && m.ttl == 0, expiring = m.ttl != 0;
         bool use_ts = !live_is_empty(info) && m.ts == info.ts;
         bool use_ttl = expiring && info.ttl != 0 && m.ttl == info.ttl && m.ldt == info.ldt;
@@ -507,6 +520,7 @@ template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& 
     for (int i = 0; i < nin; i++) {
         if ((missing >> i) & 1) continue;
         int oc = map[i];
+        if (!stat && P.ncx && oc >= P.cx_first) break;        // the multi-cell columns follow the simple ones: merged by cx_merge
         uint32_t cf = r.u8();
         bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
         MCell m; m.present = true;
@@ -532,7 +546,7 @@ template <class CUR> __device__ __forceinline__ void fold_cells(const CParams& P
 }
 
 // BTreeRow.purge :457-499 + AbstractCell.purge :78-99. Returns the number of surviving cells, or -1 when the row disappears.
-__device__ __forceinline__ int purge_row(const Purger& pg, Live& info, DT& del, MCell* cells, int ncols) {
+__device__ __forceinline__ int purge_row(const Purger& pg, Live& info, DT& del, MCell* cells, int ncols, int extra_present = 0) {      // extra_present: multi-cell columns left after their own purge
     if (pg.live(info)) info = live_empty();
     if (pg.dt(del)) del = dt_live();
     int present = 0;
@@ -548,8 +562,138 @@ __device__ __forceinline__ int purge_row(const Purger& pg, Live& info, DT& del, 
         }
         present++;
     }
+    present += extra_present;
     if (live_is_empty(info) && dt_is_live(del) && present == 0) return -1;
     return present;
+}
+
+// ---- multi-cell (complex) columns: non-frozen map / set / list -------------------------------------------------------------------------
+// One cell per element, each with a cell path; an optional complex deletion per column (S/db/rows/ComplexColumnData.java). They follow the simple
+// columns in every row. Everything here is out of line and only runs for tables that have such columns (P.ncx > 0): the kernels' hot code
+// stays what it was. A merged row's complex columns are merged straight from the versions' bytes — summary first (deletion, cell counts,
+// whether the column exists before / after the purge: the row flags and the subset bitmap need them), then once more per serialisation.
+
+__device__ __forceinline__ MCell purge_cell_fn(const Purger& pg, MCell m) {                     // AbstractCell.purge S/db/rows/AbstractCell.java:78-99
+    if (!m.present) return m;
+    bool is_live = m.ldt == I64_MAX || (m.ttl != 0 && pg.now < m.ldt);
+    if (!is_live) {
+        if (pg.ts_ldt(m.ts, m.ldt)) { m.present = false; return m; }
+        if (m.ttl != 0) { m.ldt = m.ldt - m.ttl; m.ttl = 0; m.vlen = 0; if (pg.ts_ldt(m.ts, m.ldt)) m.present = false; }
+    }
+    return m;
+}
+// AbstractTimeUUIDType.compareCustom S/db/marshal/AbstractTimeUUIDType.java:58-87,126-144 (list cell paths); everything else: cmp_value
+__device__ __noinline__ int cmp_path(int type, const uint8_t* a, int la, const uint8_t* b, int lb) {
+    if (type == TYPE_TIMEUUID) {
+        const bool pa = la == 16, pb = lb == 16;
+        if (!(pa && pb)) return pa ? 1 : (pb ? -1 : 0);
+        const uint64_t ma = load_be64(a), mb = load_be64(b);
+        const int64_t ra = (int64_t)((ma << 48) | ((ma << 16) & 0xFFFF00000000ull) | (ma >> 32)), rb = (int64_t)((mb << 48) | ((mb << 16) & 0xFFFF00000000ull) | (mb >> 32));
+        if (ra != rb) return ra < rb ? -1 : 1;
+        const int64_t sa = (int64_t)(load_be64(a + 8) ^ 0x0080808080808080ull), sb = (int64_t)(load_be64(b + 8) ^ 0x0080808080808080ull);
+        return sa == sb ? 0 : (sa < sb ? -1 : 1);
+    }
+    return cmp_value(type, a, la, b, lb);
+}
+// one cell at r (Cell.Serializer.deserialize S/db/rows/Cell.java:307-349); pfix < 0: a simple column's cell (no path), else the path's fixed length (0: vint length)
+struct PCell { MCell m; uint64_t poff; int32_t plen; };
+__device__ __noinline__ void cx_read_cell(const InDesc& in, Rd& r, const CxVer& v, int vfix, int pfix, PCell* out) {
+    uint32_t cf = r.u8();
+    bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
+    MCell m; m.present = true;
+    m.ts = use_ts ? v.its : (int64_t)(r.vint() + (uint64_t)in.min_ts);
+    m.ldt = use_ttl ? v.ildt : ((deleted || expiring) ? (int64_t)r.vint32() + in.min_ldt : I64_MAX);
+    m.ttl = use_ttl ? v.ittl : (expiring ? r.vint32() + in.min_ttl : 0);
+    out->poff = r.p; out->plen = 0;
+    if (pfix >= 0) { int64_t pl = pfix > 0 ? pfix : (int64_t)r.vint32(); if (pl < 0) { r.err = PERR_CORRUPT; pl = 0; } out->poff = r.p; out->plen = (int32_t)pl; r.skip((uint64_t)pl); }
+    m.voff = r.p; m.vlen = 0;
+    if (has_value) { int64_t len = vfix > 0 ? vfix : (int64_t)r.vint32(); if (len < 0) { r.err = PERR_CORRUPT; len = 0; } m.voff = r.p; m.vlen = (int32_t)len; r.skip((uint64_t)len); }
+    if (m.ttl < 0) r.err = PERR_CORRUPT;
+    if (m.ldt != I64_MAX) m.ldt = decode_ldt(m.ldt, m.ttl);
+    out->m = m;
+}
+// positions r at the cells of complex column `oc` in version v (UnfilteredSerializer.readComplexColumn :652-672); false: the version does not have it
+__device__ __noinline__ bool cx_seek(const CParams& P, const CxVer& v, int oc, Rd& r, DT* cd, uint32_t* count) {
+    const InDesc& in = P.in[v.src];
+    r = Rd{P.U, v.cells, v.end, 0};
+    uint64_t missing = 0;
+    if (!(v.flags & 0x20)) missing = r.vint();
+    for (int i = 0; i < in.ncols && !r.err; i++) {
+        if ((missing >> i) & 1) continue;
+        const int oci = in.colmap[i];
+        PCell tmp;
+        if (oci < P.cx_first) { cx_read_cell(in, r, v, P.vfix[oci], -1, &tmp); continue; }
+        DT d = dt_live();
+        if (v.flags & 0x40) d = read_delta_dt(r, in);
+        const int32_t n = r.vint32();
+        if (n < 0) { r.err = PERR_CORRUPT; return false; }
+        if (oci == oc) { *cd = d; *count = (uint32_t)n; return true; }
+        for (int32_t k = 0; k < n && !r.err; k++) cx_read_cell(in, r, v, P.vfix[oci], P.pfix[oci - P.cx_first], &tmp);
+    }
+    return false;
+}
+template <bool E> __device__ __forceinline__ void put_cell(Sink<E>& s, const CParams& P, const Live& info, const MCell& m, int vfix, const uint8_t* path, int plen, int pfix) {      // Cell.Serializer.serialize :268-305
+    bool has_value = m.vlen > 0, deleted = m.ldt != I64_MAX && m.ttl == 0, expiring = m.ttl != 0;
+    bool use_ts = !live_is_empty(info) && m.ts == info.ts;
+    bool use_ttl = expiring && info.ttl != 0 && m.ttl == info.ttl && m.ldt == info.ldt;
+    int cf = (has_value ? 0 : 0x04) | (deleted ? 0x01 : (expiring ? 0x02 : 0)) | (use_ts ? 0x08 : 0) | (use_ttl ? 0x10 : 0);
+    s.u8(cf);
+    if (!use_ts) s.vint((uint64_t)m.ts - (uint64_t)P.o_min_ts);
+    if ((deleted || expiring) && !use_ttl) s.vint((uint64_t)(int64_t)(int32_t)(m.ldt - P.o_min_ldt));
+    if (expiring && !use_ttl) s.vint((uint64_t)(int64_t)(m.ttl - P.o_min_ttl));
+    if (pfix >= 0) { if (pfix == 0) s.vint((uint64_t)plen); s.copy(path, (uint32_t)plen); }          // :300-301: the path precedes the value
+    if (has_value) { if (vfix <= 0) s.vint((uint64_t)m.vlen); s.copy(P.U + m.voff, (uint32_t)m.vlen); }
+}
+// ColumnDataReducer.getReduced, complex branch (S/db/rows/Row.java:851-883) + ComplexColumnData.purge (:212-216), for complex column j of the row
+// whose versions are ver[0..nver). sum: fill the summary. s: serialise the column (its summary in `known`; header = [deletion when the row has
+// any] count). acc: statistics (Rows.StatsAccumulation.accumulateOnColumnData S/db/rows/Rows.java:66-82). Returns an error code.
+template <bool E> __device__ __noinline__ int cx_merge(const CParams& P, const Purger& pg, const CxVer* ver, int nver, bool as_is, DT active, int j,
+                                                        const Live info, CxCol* sum, Sink<E>* s, bool row_has_cd, const CxCol* known, StatAcc* acc) {
+    const int oc = P.cx_first + j, vfix = P.vfix[oc], pfix = P.pfix[j], ptype = P.ptype[j];
+    uint64_t pos[MAXK]; uint32_t rem[MAXK];
+    DT cd = dt_live();
+    for (int v = 0; v < nver; v++) {
+        Rd r; DT d = dt_live(); uint32_t n = 0; rem[v] = 0; pos[v] = 0;
+        if (cx_seek(P, ver[v], oc, r, &d, &n)) { pos[v] = r.p; rem[v] = n; if (dt_supersedes(d, cd)) cd = d; }
+        if (r.err) return r.err;
+    }
+    DT cell_del = dt_live();
+    if (!as_is) { if (dt_supersedes(cd, active)) cell_del = cd; else { cd = dt_live(); cell_del = active; } }      // :867-876
+    const bool cd_pre = !dt_is_live(cd);
+    if (pg.dt(cd)) cd = dt_live();
+    if (s) { if (row_has_cd) write_delta_dt(*s, P, known->cd); s->vint(known->ncells); }
+    if (acc && !dt_is_live(cd)) acc->dt(cd);
+    uint32_t npre = 0, npost = 0;
+    for (;;) {
+        // the smallest head in cell-path order (MergeIterator over Cell.comparator = column.cellPathComparator())
+        int b = -1; PCell best;
+        for (int v = 0; v < nver; v++) {
+            if (!rem[v]) continue;
+            Rd r{P.U, pos[v], ver[v].end, 0}; PCell c; cx_read_cell(P.in[ver[v].src], r, ver[v], vfix, pfix, &c);
+            if (r.err) return r.err;
+            if (b < 0 || cmp_path(ptype, P.U + c.poff, c.plen, P.U + best.poff, best.plen) < 0) { b = v; best = c; }
+        }
+        if (b < 0) break;
+        MCell mc; mc.present = false; mc.ts = 0; mc.ldt = I64_MAX; mc.voff = 0; mc.ttl = 0; mc.vlen = 0;
+        for (int v = 0; v < nver; v++) {                          // CellReducer :900-918, in source order
+            if (!rem[v]) continue;
+            Rd r{P.U, pos[v], ver[v].end, 0}; PCell c; cx_read_cell(P.in[ver[v].src], r, ver[v], vfix, pfix, &c);
+            if (v != b && cmp_path(ptype, P.U + c.poff, c.plen, P.U + best.poff, best.plen) != 0) continue;
+            pos[v] = r.p; rem[v]--;
+            if (!as_is && dt_deletes(cell_del, c.m.ts)) continue;
+            if (!mc.present || !reconcile_keep_left(P, mc, c.m)) mc = c.m;
+        }
+        if (!mc.present) continue;
+        npre++;
+        const MCell pc = purge_cell_fn(pg, mc);
+        if (!pc.present) continue;
+        npost++;
+        if (s) put_cell(*s, P, info, pc, vfix, P.U + best.poff, best.plen, pfix);
+        if (acc) acc->cell(pc);
+    }
+    if (sum) { sum->cd = cd; sum->ncells = npost; sum->pre = (cd_pre || npre) ? 1 : 0; sum->post = (!dt_is_live(cd) || npost) ? 1 : 0; }
+    if (acc && npost) acc->cols++;
+    return 0;
 }
 
 // Tables with static columns carry a static row in every partition, the empty one included (SortedTableWriter.append :144-146,
@@ -592,12 +736,13 @@ template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, 
     if (EMIT && w.ix_entry) w.ix.base = w.ix_entry + w.ix_fixed + vint_size(w.header_len);
 }
 
-template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present) {
+template <bool EMIT, bool CX = false> __device__ __forceinline__ void write_row(PWriter<EMIT>& w, const CParams& P, const CkRef& ck, const Live& info, const DT& del, const MCell* cells, int present, const CxEmit* cx = nullptr) {
     int flags = 0;
     if (!live_is_empty(info)) flags |= 0x04;
     if (info.ttl != 0) flags |= 0x08;
     if (!dt_is_live(del)) flags |= 0x10;
     if (present == P.ncols) flags |= 0x20;
+    if constexpr (CX) for (int j = 0; j < P.ncx; j++) if (!dt_is_live(cx->col[j].cd)) flags |= 0x40;      // row.hasComplexDeletion() :166-167
     uint64_t pos = pw_begin_unf(w, ck);
     uint64_t prev = pos - w.prev_row_start;
     // The row size precedes the body it counts. Instead of serialising the body twice (count, then emit) it is emitted once behind a size
@@ -605,18 +750,21 @@ template <bool EMIT> __device__ __forceinline__ void write_row(PWriter<EMIT>& w,
     const int vp = vint_size(prev);
     const uint64_t p0 = w.d.pos;
     Sink<EMIT> b = w.d; b.pos = p0 + 1 + ck.len + 1 + vp;
-    uint64_t end = put_row_body(b, P, flags, info, del, cells, P.ncols, P.vfix);
+    uint64_t end = put_row_body<EMIT, CX>(b, P, flags, info, del, cells, P.ncols, P.vfix, cx);
     const uint64_t body = end - b.pos;
     const int vs = vint_size(body + vp);
-    if (vs != 1) { b.pos = p0 + 1 + ck.len + vs + vp; end = put_row_body(b, P, flags, info, del, cells, P.ncols, P.vfix); }
+    if (vs != 1) { b.pos = p0 + 1 + ck.len + vs + vp; end = put_row_body<EMIT, CX>(b, P, flags, info, del, cells, P.ncols, P.vfix, cx); }
     w.d.u8(flags); w.d.copy(P.U + ck.off, ck.len);
     w.d.vint(body + vp); w.d.vint(prev);
     w.d.pos = end;
     pw_end_unf(w, P, ck, pos);
     if (w.acc) {                                               // Rows.collectStats
         w.acc->live(info); w.acc->dt(del);
-        for (int c = 0; c < P.ncols; c++) if (cells[c].present) w.acc->cell(cells[c]);
-        w.acc->cols += (unsigned long long)present; w.acc->rows++;
+        const int nsimple = CX ? P.cx_first : P.ncols; int simple_present = 0;
+        for (int c = 0; c < nsimple; c++) if (cells[c].present) { w.acc->cell(cells[c]); simple_present++; }
+        w.acc->cols += (unsigned long long)simple_present; w.acc->rows++;
+        if constexpr (CX) for (int j = 0; j < P.ncx; j++) if (cells[P.cx_first + j].present)
+            cx_merge<EMIT>(P, *cx->pg, cx->ver, cx->nver, cx->as_is, cx->active, j, info, nullptr, (Sink<EMIT>*)nullptr, false, nullptr, w.acc);
     }
 }
 
@@ -711,7 +859,26 @@ struct XlateStaged {
     __device__ __forceinline__ uint64_t operator()(int src, uint64_t u) const { return sbase[src] + (u - g0[src]); }
 };
 
-template <bool EMIT, class CUR, class XL>
+// the versions of a row -> CxVer[], then the summary of every multi-cell column (see cx_merge)
+template <class CUR> __device__ __noinline__ int cx_row_summary(const CParams& P, const Purger& pg, CUR* cur, uint64_t grp, bool as_is, DT active, CxVer* ver, CxCol* col,
+                                                                MCell* merged, int* pre, int* post, int* nver_out) {
+    int nv = 0;
+    for (uint64_t bits = grp; bits; bits &= bits - 1) {
+        const int v = __ffsll((long long)bits) - 1;
+        Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) return r.err;
+        ver[nv++] = CxVer{r.p, (uint64_t)cur[v].next, vi.ts, vi.ldt, vi.ttl, (uint8_t)cur[v].flags, (uint8_t)cur[v].src};
+    }
+    for (int j = 0; j < P.ncx; j++) {
+        const int e = cx_merge<false>(P, pg, ver, nv, as_is, active, j, live_empty(), &col[j], (Sink<false>*)nullptr, false, nullptr, nullptr);
+        if (e) return e;
+        merged[P.cx_first + j].present = col[j].post != 0; *pre += col[j].pre; *post += col[j].post;
+    }
+    *nver_out = nv;
+    return 0;
+}
+
+// CX: the table has multi-cell columns (a separate instantiation: the kernels of every other table compile to exactly the code they had)
+template <bool EMIT, class CUR, class XL, int MCAP = MAXK, bool CX = false>
 __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t* __restrict__ contrib, uint64_t c0, uint32_t m,
                                   const uint64_t* __restrict__ part_upos, const uint64_t* __restrict__ pbase,
                                   const uint64_t* __restrict__ part_kp, const uint16_t* __restrict__ part_klen, const int64_t* __restrict__ part_tok,
@@ -727,7 +894,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
     uint64_t sgrp = 0;                                // contributors with a non-empty static row
-    if (m > MAXK) { err = PERR_UNSUPPORTED; return; }
+    if (m > MAXK || (!CX && P.ncx)) { err = PERR_UNSUPPORTED; return; }
     // prologue in three sweeps so that the m dependent chains (contrib -> upos -> Data bytes) overlap instead of serialising:
     // (1) resolve the input partitions, (2) prefetch their first lines, (3) parse the partition headers
     for (uint32_t v = 0; v < mu; v++) {
@@ -823,14 +990,31 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
                 else { if (live_supersedes(vi, info)) info = vi; if (dt_supersedes(vd, del)) del = vd; }
                 fold_cells(P, cur[v], r, vi, false, active, merged, err);
             }
+            const int nsimple = CX ? P.cx_first : P.ncols;
             if (!as_is) {
                 if (dt_supersedes(del, active)) active = del; else del = dt_live();
                 if (dt_deletes(active, info.ts)) info = live_empty();
-                for (int k = 0; k < P.ncols; k++) if (merged[k].present && dt_deletes(active, merged[k].ts)) merged[k].present = false;
+                for (int k = 0; k < nsimple; k++) if (merged[k].present && dt_deletes(active, merged[k].ts)) merged[k].present = false;
             }
             if (err) break;
-            int npresent = 0; for (int k = 0; k < P.ncols; k++) npresent += merged[k].present;
-            if (!(live_is_empty(info) && dt_is_live(del) && npresent == 0)) {
+            int npresent = 0; for (int k = 0; k < nsimple; k++) npresent += merged[k].present;
+            if constexpr (CX) {
+                // multi-cell columns: summary (deletion, cell counts, existence before / after the purge) now, the cells when the row is written
+                CxVer cxv[MCAP]; CxCol cxc[MAXCX];
+                int cx_pre = 0, cx_post = 0, cx_nver = 0;
+                { int e = cx_row_summary(P, pg, cur, grp, as_is, active, cxv, cxc, merged, &cx_pre, &cx_post, &cx_nver); if (e) { err = e; break; } }
+                if (!(live_is_empty(info) && dt_is_live(del) && npresent + cx_pre == 0)) {
+                    st.merged_unfiltereds++;
+                    CUR& f = cur[b];
+                    CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), K_CLUSTERING, (uint8_t)f.n};
+                    int present = purge_row(pg, info, del, merged, nsimple, cx_post);
+                    if (present >= 0) {
+                        if (!w.started) pw_start(w, P, key_off, klen, out_pdel);
+                        const CxEmit cxe{cxv, cx_nver, as_is, active, cxc, &pg};
+                        write_row<EMIT, true>(w, P, ck, info, del, merged, present, &cxe);
+                    }
+                }
+            } else if (!(live_is_empty(info) && dt_is_live(del) && npresent == 0)) {
                 st.merged_unfiltereds++;
                 CUR& f = cur[b];
                 CkRef ck{(uint64_t)f.pos + f.ck_rel, (uint32_t)(f.ckend_rel - f.ck_rel), K_CLUSTERING, (uint8_t)f.n};

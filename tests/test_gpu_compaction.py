@@ -654,3 +654,26 @@ def test_static_rows_every_kernel_variant(ctx, monkeypatch):
     w = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine()).outputs[0]
     g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(GpuEngine(ctx)).outputs[0]
     assert g.data == w.data and g.index == w.index and g.digest == w.digest
+
+# ---- multi-cell (complex) columns ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,ntab,big,cis", [(1, 5, False, 65536), (2, 20, False, 65536), (3, 3, True, 2048), (4, 40, False, 65536)])
+def test_complex_columns_match_oracle(ctx, seed, ntab, big, cis):
+    """a map, a set and a list beside simple columns: complex deletions, cells merged in cell-path order (TimeUUID order for the list), purge,
+    HAS_COMPLEX_DELETION / subset bitmap, statistics; fan-ins up to 40 (the 64-cursor instantiation), wide partitions with a promoted index"""
+    from complex_tables import complex_tables
+    tabs = complex_tables(seed, ntables=ntab, nkeys=60 if not big else 6, cis=cis, big=big)
+    both(ctx, tabs, CompactionController(NOW, 864000), column_index_size=cis, with_metadata=True)
+    both(ctx, tabs, CompactionController(NOW, 10 ** 9), column_index_size=cis)          # nothing purgeable
+    both(ctx, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)       # single source: pass-through + purge
+    both(ctx, tabs, CompactionController(NOW, 0), column_index_size=cis, with_metadata=True)
+
+def test_complex_columns_streamed_and_sharded(ctx, monkeypatch):
+    from complex_tables import complex_tables
+    tabs = complex_tables(9, ntables=6, nkeys=2500)
+    monkeypatch.setenv("B200C_RANGES", "4")
+    both(ctx, tabs, CompactionController(NOW, 864000))
+    lo, hi = -(1 << 62), (1 << 61)
+    for g, t in enumerate(tabs): t.generation = g
+    want = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine()).outputs[0]
+    g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(GpuEngine(ctx)).outputs[0]
+    assert g.data == want.data and g.index == want.index and g.digest == want.digest

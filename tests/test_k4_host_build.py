@@ -146,3 +146,14 @@ def test_k4_source_static_rows(k4lib, seed, wide, cis):
     check(k4lib, tabs, CompactionController(NOW, 864000, overlapping_min_timestamp=1015), column_index_size=cis)
     check(k4lib, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)             # single source: partition deletion still shadows the static row
     check(k4lib, tabs[2:3], CompactionController(NOW, 864000), column_index_size=cis)            # input without static columns
+
+@pytest.mark.parametrize("seed,big,cis", [(1, False, 65536), (2, False, 65536), (3, True, 2048)])
+def test_k4_source_complex_columns(k4lib, seed, big, cis):
+    """multi-cell columns (map / set / list beside simple ones): complex deletions, cells merged in cell-path order (TimeUUID order for the list),
+    purge, HAS_COMPLEX_DELETION / subset bitmap, wide partitions with a promoted index — the K4 source against the oracle"""
+    from complex_tables import complex_tables
+    tabs = complex_tables(seed, ntables=5 if not big else 3, nkeys=60 if not big else 6, cis=cis, big=big)
+    check(k4lib, tabs, CompactionController(NOW, 864000), column_index_size=cis)
+    check(k4lib, tabs, CompactionController(NOW, 10 ** 9), column_index_size=cis)          # nothing purgeable
+    check(k4lib, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)       # single source: pass-through + purge
+    check(k4lib, tabs, CompactionController(NOW, 0), column_index_size=cis)

@@ -81,8 +81,12 @@ public class GpuCompactionTask extends CompactionTask
         for (ColumnMetadata c : t.staticColumns())
             if (c.isComplex() || typeClass(c.type) < 0) return false;
         if (t.clusteringColumns().size() > B200C.MAX_CLUSTERING || t.regularColumns().size() >= B200C.MAX_COLUMNS) return false;
+        int complex = 0;
         for (ColumnMetadata c : t.regularColumns())
-            if (c.isComplex() || typeClass(c.type) < 0) return false;
+        {
+            if (c.isComplex()) { if (columnClass(c.type) < 0 || ++complex > B200C.MAX_COMPLEX_COLUMNS) return false; }
+            else if (typeClass(c.type) < 0) return false;
+        }
         for (ColumnMetadata c : t.clusteringColumns())
             if (clusteringClass(c.type) < 0) return false;
         if (cfs.getCompactionStrategyManager().getCompactionParams().tombstoneOption() != org.apache.cassandra.schema.CompactionParams.TombstoneOption.NONE) return false;
@@ -117,6 +121,30 @@ public class GpuCompactionTask extends CompactionTask
             default: return -1;
         }
     }
+
+    /** b200c_column.type / .fixed_len of a regular column: simple columns as typeClass; multi-cell collections (map / set / list) as
+     *  B200C_COLUMN_COMPLEX(value class, path class) / B200C_COLUMN_FIXED(value length, path length) — include/b200c.h. The cell path is
+     *  CollectionType.nameComparator() (map key, set element, list timeuuid), the cell value CollectionType.valueComparator(). -1: refused
+     *  (non-frozen UDTs, element types outside the envelope). Frozen collections are single opaque values. */
+    static int columnClass(AbstractType<?> type)
+    {
+        if (!type.isMultiCell()) return type.isCollection() || type.isUDT() ? B200C.TYPE_BYTES : typeClass(type);
+        if (!(type instanceof org.apache.cassandra.db.marshal.CollectionType)) return -1;
+        org.apache.cassandra.db.marshal.CollectionType<?> ct = (org.apache.cassandra.db.marshal.CollectionType<?>) type;
+        int path = ct.kind == org.apache.cassandra.db.marshal.CollectionType.Kind.LIST ? B200C.TYPE_TIMEUUID : elementClass(ct.nameComparator());
+        int value = ct.kind == org.apache.cassandra.db.marshal.CollectionType.Kind.SET ? B200C.TYPE_BYTES : elementClass(ct.valueComparator());
+        return path < 0 || value < 0 ? -1 : value | ((path + 1) << 8);
+    }
+    static int columnFixedLen(AbstractType<?> type)
+    {
+        if (!type.isMultiCell()) return type.isCollection() || type.isUDT() ? 0 : Math.max(0, type.valueLengthIfFixed());
+        org.apache.cassandra.db.marshal.CollectionType<?> ct = (org.apache.cassandra.db.marshal.CollectionType<?>) type;
+        int path = ct.kind == org.apache.cassandra.db.marshal.CollectionType.Kind.LIST ? 16 : elementFixedLen(ct.nameComparator());
+        int value = ct.kind == org.apache.cassandra.db.marshal.CollectionType.Kind.SET ? 0 : elementFixedLen(ct.valueComparator());
+        return value | (path << 16);
+    }
+    private static int elementClass(AbstractType<?> t) { return t.isCollection() || t.isUDT() ? B200C.TYPE_BYTES : typeClass(t); }       // (frozen inside a collection)
+    private static int elementFixedLen(AbstractType<?> t) { return t.isCollection() || t.isUDT() ? 0 : Math.max(0, t.valueLengthIfFixed()); }
 
     /** clustering columns additionally need a comparison the engine implements: signed integers or unsigned bytes */
     static int clusteringClass(AbstractType<?> type)
@@ -244,7 +272,7 @@ public class GpuCompactionTask extends CompactionTask
                 }
                 m.putInt(M_NCOLUMNS, outColumns.size());
                 for (int k = 0; k < outColumns.size(); k++)
-                    m.putInt(M_COLUMNS + 8 * k, typeClass(outColumns.get(k).type)).putInt(M_COLUMNS + 8 * k + 4, Math.max(0, outColumns.get(k).type.valueLengthIfFixed()));
+                    m.putInt(M_COLUMNS + 8 * k, columnClass(outColumns.get(k).type)).putInt(M_COLUMNS + 8 * k + 4, columnFixedLen(outColumns.get(k).type));      // (header order: simple columns, then multi-cell ones)
                 m.putInt(M_NSTATIC_COLUMNS, outStatics.size());
                 for (int k = 0; k < outStatics.size(); k++)
                     m.putInt(M_STATIC_COLUMNS + 8 * k, typeClass(outStatics.get(k).type)).putInt(M_STATIC_COLUMNS + 8 * k + 4, Math.max(0, outStatics.get(k).type.valueLengthIfFixed()));

@@ -512,7 +512,7 @@ template <class CUR> __device__ __forceinline__ Rd row_header(const CParams& P, 
 }
 
 // folds the cells of the row at cursor `c` into merged[] (ColumnDataReducer.getReduced :838-849)
-template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& P, const CUR& c, Rd r, Live info, bool apply_deletion, DT active, MCell* merged, bool stat) {
+template <class CUR, bool CX = false> __device__ __noinline__ int fold_cells_impl(const CParams& P, const CUR& c, Rd r, Live info, bool apply_deletion, DT active, MCell* merged, bool stat) {
     const InDesc& in = P.in[c.src];
     const int nin = stat ? in.nstat : in.ncols; const int32_t* const map = stat ? in.smap : in.colmap; const int32_t* const vfix = stat ? P.sfix : P.vfix;
     uint64_t missing = 0;
@@ -520,7 +520,7 @@ template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& 
     for (int i = 0; i < nin; i++) {
         if ((missing >> i) & 1) continue;
         int oc = map[i];
-        if (!stat && P.ncx && oc >= P.cx_first) break;        // the multi-cell columns follow the simple ones: merged by cx_merge
+        if constexpr (CX) if (!stat && oc >= P.cx_first) break;      // the multi-cell columns follow the simple ones: merged by cx_merge
         uint32_t cf = r.u8();
         bool has_value = !(cf & 0x04), deleted = cf & 0x01, expiring = cf & 0x02, use_ts = cf & 0x08, use_ttl = cf & 0x10;
         MCell m; m.present = true;
@@ -541,8 +541,8 @@ template <class CUR> __device__ __noinline__ int fold_cells_impl(const CParams& 
     }
     return r.err;
 }
-template <class CUR> __device__ __forceinline__ void fold_cells(const CParams& P, const CUR& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err, bool stat = false) {
-    int e = fold_cells_impl(P, c, r, info, apply_deletion, active, merged, stat); if (e) err = e;
+template <bool CX = false, class CUR> __device__ __forceinline__ void fold_cells(const CParams& P, const CUR& c, Rd& r, const Live& info, bool apply_deletion, const DT& active, MCell* merged, int& err, bool stat = false) {
+    int e = fold_cells_impl<CUR, CX>(P, c, r, info, apply_deletion, active, merged, stat); if (e) err = e;
 }
 
 // BTreeRow.purge :457-499 + AbstractCell.purge :78-99. Returns the number of surviving cells, or -1 when the row disappears.
@@ -988,7 +988,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
                 Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) err = r.err;
                 if (gcount == 1) { info = vi; del = vd; }
                 else { if (live_supersedes(vi, info)) info = vi; if (dt_supersedes(vd, del)) del = vd; }
-                fold_cells(P, cur[v], r, vi, false, active, merged, err);
+                fold_cells<CX>(P, cur[v], r, vi, false, active, merged, err);
             }
             const int nsimple = CX ? P.cx_first : P.ncols;
             if (!as_is) {

@@ -226,6 +226,51 @@ __global__ void __launch_bounds__(128) k_index_find_anchors(const CParams* __res
     }
 }
 
+// K2 with Summary.db samples, in two walks instead of four passes: every Summary interval (the entries between two samples: 128 by default,
+// ~2 KB of Index.db) is one thread. Walk 1 counts the interval's entries and PROVES the samples: the walk from sample a must land exactly on
+// sample a + 1 (the last one on the end of the slice) and the first sample must be the slice's first byte — by induction the intervals'
+// chains are the sequential parse. Walk 2 (after a scan of the counts) parses again and emits token / key prefix / key length / position.
+// Any interval that does not land marks the input: the call then falls back to the speculate-chain-verify path below, whose sequential
+// last resort reports real damage with its offset.
+__global__ void __launch_bounds__(128) k_index_count_intervals(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, int i, const uint64_t* __restrict__ anchors, uint64_t n,
+                                                               uint64_t bias, uint32_t* __restrict__ acnt, uint32_t* __restrict__ bad) {
+    uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const CParams& P = *Pp;
+    const uint64_t ilen = P.in[i].ilen;
+    uint64_t o = anchors[a] - bias; const uint64_t end = (a + 1 < n) ? anchors[a + 1] - bias : ilen;
+    uint32_t cnt = 0;
+    if ((a == 0 && o != 0) || o >= ilen || end > ilen || end <= o) { bad[i] = 1; acnt[a] = 0; return; }
+    while (o < end) {
+        uint64_t dpos; uint32_t kl;
+        const uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
+        if (!len) break;
+        cnt++; o += len;
+    }
+    if (o != end) bad[i] = 1;
+    acnt[a] = cnt;
+}
+__global__ void __launch_bounds__(128) k_index_emit_intervals(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, int i, const uint64_t* __restrict__ anchors, uint64_t n,
+                                                              uint64_t bias, const uint64_t* __restrict__ ascan /* of this input's intervals, [n + 1] */, uint64_t g0,
+                                                              int64_t* __restrict__ tok, uint64_t* __restrict__ kp, uint16_t* __restrict__ klen, uint64_t* __restrict__ upos) {
+    uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const CParams& P = *Pp;
+    const InDesc& in = P.in[i];
+    uint64_t o = anchors[a] - bias; const uint64_t end = (a + 1 < n) ? anchors[a + 1] - bias : in.ilen;
+    uint64_t g = g0 + (ascan[a] - ascan[0]); const uint64_t gend = g0 + (ascan[a + 1] - ascan[0]);
+    for (; o < end && g < gend; g++) {
+        uint64_t dpos; uint32_t kl;
+        const uint64_t len = idx_entry(P, IDX, i, o, false, &dpos, &kl);
+        if (!len) return;                                  // (cannot happen: walk 1 parsed the same bytes)
+        const uint8_t* key = IDX + in.ibase + o + 2;
+        uint64_t pre = 0; for (uint32_t q = 0; q < 8; q++) pre = (pre << 8) | (q < kl ? key[q] : 0);
+        tok[g] = P.partitioner ? (int64_t)(pre ^ 0x8000000000000000ull) : murmur3_token(key, kl);       // (see k_index_emit)
+        kp[g] = pre; klen[g] = (uint16_t)kl; upos[g] = in.ubase + dpos;
+        o += len;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_index_chain(const CParams* __restrict__ Pp, const uint8_t* __restrict__ IDX, const uint64_t* __restrict__ bbase, uint64_t b0,
                                                      uint64_t nblocks, const uint64_t* __restrict__ start, uint32_t* __restrict__ cnt, uint64_t* __restrict__ chain_end) {
     uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1277,6 +1322,54 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         const uint64_t nblocks = bo2;
         B200C_CUDA_TRY(c, cudaMemcpyAsync((void*)hp.in, hin.data(), sizeof(InDesc) * (size_t)K, cudaMemcpyHostToDevice, st));
         B200C_CUDA_TRY(c, cudaMemcpyAsync(d_bbase, bbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
+        auto alloc_arrays = [&]() -> int {
+            B200C_TRY(check_cancel());
+            if (total_parts - K >= (1ull << 40)) { c->err = "too many partitions"; return B200C_EUNSUPPORTED; }
+            B200C_TRY(ws_typed(c, WS_TOK, total_parts + 1, &d_tok));
+            B200C_TRY(ws_typed(c, WS_KP, total_parts + 1, &d_kp));
+            B200C_TRY(ws_typed(c, WS_KLEN, total_parts + 1, &d_klen));
+            B200C_TRY(ws_typed(c, WS_UPOS, total_parts + 1, &d_upos));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pbase, pbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pcount, pcount.data(), K * 8, cudaMemcpyHostToDevice, st));
+            return B200C_OK;
+        };
+        // ---- with Summary.db samples: one thread per Summary interval, count + prove, scan, emit (B200C_K2_LEGACY=1: the four-pass path) --------
+        bool emitted = false;
+        static const bool k2_legacy = getenv("B200C_K2_LEGACY") != nullptr;
+        bool intervals_ok = have_summaries && !k2_legacy;
+        for (int i = 0; i < K && intervals_ok; i++)      // (sparse samples: an interval is one thread's serial walk — leave those to the block-parallel path)
+            if (sl[i].hi > sl[i].lo && (!sl[i].s_count || (sl[i].hi - sl[i].lo) / sl[i].s_count > (64u << 10))) intervals_ok = false;
+        if (intervals_ok) {
+            std::vector<uint64_t> abase(K + 1, 0);
+            for (int i = 0; i < K; i++) abase[i + 1] = abase[i] + sl[i].s_count;
+            const uint64_t na = abase[K];
+            uint32_t *d_acnt, *d_abad; uint64_t* d_ascan;
+            B200C_TRY(ws_typed(c, WS_ICNT, na + 1, &d_acnt));
+            B200C_TRY(ws_typed(c, WS_ISCAN, na + 2, &d_ascan));
+            B200C_TRY(ws_typed(c, WS_IBAD, (size_t)K + 1, &d_abad));
+            B200C_CUDA_TRY(c, cudaMemsetAsync(d_abad, 0, (K + 1) * 4, st));
+            for (int i = 0; i < K; i++) if (sl[i].s_count)
+                B200C_LAUNCH(c, k_index_count_intervals, (unsigned)((sl[i].s_count + 127) / 128), 128, 0, dP, IDX, i, d_summ + sb[i], sl[i].s_count, sl[i].lo, d_acnt + abase[i], d_abad);
+            if (na) B200C_TRY(exclusive_scan<uint32_t>(c, d_acnt, na, d_ascan, WS_SCANA, 0)); else B200C_CUDA_TRY(c, cudaMemsetAsync(d_ascan, 0, 16, st));
+            for (int i = 0; i <= K; i++) B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 8 + i, d_ascan + abase[i], 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_cerr, 8, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaMemcpyAsync(h + 300, d_abad, (K + 1) * 4, cudaMemcpyDeviceToHost, st));
+            B200C_CUDA_TRY(c, cudaStreamSynchronize(st));
+            if (h[0] != ~0ull) return chunk_error(h[0]);
+            bool any_bad = false;
+            for (int i = 0; i < K; i++) if (((uint32_t*)(h + 300))[i]) any_bad = true;
+            if (!any_bad) {
+                total_parts = 0;
+                for (int i = 0; i < K; i++) { pcount[i] = h[8 + i + 1] - h[8 + i]; pbase[i] = total_parts; total_parts += pcount[i] + 1; }
+                pbase[K] = total_parts;
+                B200C_TRY(alloc_arrays());
+                for (int i = 0; i < K; i++) if (sl[i].s_count)
+                    B200C_LAUNCH(c, k_index_emit_intervals, (unsigned)((sl[i].s_count + 127) / 128), 128, 0, dP, IDX, i, d_summ + sb[i], sl[i].s_count, sl[i].lo, d_ascan + abase[i], pbase[i],
+                                 d_tok, d_kp, d_klen, d_upos);
+                emitted = true;
+            }
+        }
+        if (!emitted) {
         uint64_t *d_istart, *d_iend, *d_iscan; uint32_t *d_icnt, *d_ihit, *d_ibad;
         B200C_TRY(ws_typed(c, WS_ISTART, nblocks + 1, &d_istart));
         B200C_TRY(ws_typed(c, WS_IEND, nblocks + 1, &d_iend));
@@ -1321,16 +1414,10 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         total_parts = 0;
         for (int i = 0; i < K; i++) { pcount[i] = h[8 + i + 1] - h[8 + i]; pbase[i] = total_parts; total_parts += pcount[i] + 1; }
         pbase[K] = total_parts;
-        B200C_TRY(check_cancel());
-        if (total_parts - K >= (1ull << 40)) { c->err = "too many partitions"; return B200C_EUNSUPPORTED; }
-        B200C_TRY(ws_typed(c, WS_TOK, total_parts + 1, &d_tok));
-        B200C_TRY(ws_typed(c, WS_KP, total_parts + 1, &d_kp));
-        B200C_TRY(ws_typed(c, WS_KLEN, total_parts + 1, &d_klen));
-        B200C_TRY(ws_typed(c, WS_UPOS, total_parts + 1, &d_upos));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pbase, pbase.data(), (K + 1) * 8, cudaMemcpyHostToDevice, st));
-        B200C_CUDA_TRY(c, cudaMemcpyAsync(d_pcount, pcount.data(), K * 8, cudaMemcpyHostToDevice, st));
+        B200C_TRY(alloc_arrays());
         if (nblocks) B200C_LAUNCH(c, k_index_emit, (unsigned)((nblocks + 255) / 256), 256, 0, dP, IDX, d_bbase, nblocks, d_istart, d_icnt, d_iscan, d_pbase,
                                   d_tok, d_kp, d_klen, d_upos, d_err);
+        }      // (legacy path)
         if (total_parts > (uint64_t)K) B200C_LAUNCH(c, k_check_order, 1184, 256, 0, dP, d_pbase, d_pcount, d_tok, d_kp, d_klen, d_upos, d_err);
         B200C_LAUNCH(c, k_input_ranges, (K + 63) / 64, 64, 0, dP, d_pbase, d_pcount, d_tok, d_upos, tlo, thi, d_range, d_rbytes);
         B200C_CUDA_TRY(c, cudaMemcpyAsync(h, d_range, 2 * K * 8, cudaMemcpyDeviceToHost, st));

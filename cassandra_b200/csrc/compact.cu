@@ -1336,7 +1336,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         // ---- B200C_K2_INTERVALS=1 (A/B, measured slower: 11.8 vs 7.7 ms at 16 x 256 MiB — a thread's 2 KB serial walk, twice, against the
         //      256-byte blocks of the default path): one thread per Summary interval, count + prove, scan, emit -----------------------------
         bool emitted = false;
-        static const bool k2_intervals = getenv("B200C_K2_INTERVALS") != nullptr;
+        const bool k2_intervals = getenv("B200C_K2_INTERVALS") != nullptr;
         bool intervals_ok = have_summaries && k2_intervals;
         for (int i = 0; i < K && intervals_ok; i++)      // (sparse samples: an interval is one thread's serial walk — leave those to the block-parallel path)
             if (sl[i].hi > sl[i].lo && (!sl[i].s_count || (sl[i].hi - sl[i].lo) / sl[i].s_count > (64u << 10))) intervals_ok = false;

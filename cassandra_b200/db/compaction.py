@@ -44,7 +44,7 @@ class OutputSSTable:
         return c
 
 STATS_SCALARS = ("min_timestamp", "max_timestamp", "min_local_deletion_time", "max_local_deletion_time", "min_ttl", "max_ttl", "total_rows",
-                 "total_columns_set", "total_cells", "total_tombstones", "has_partition_level_deletions", "tdrop_overflow")
+                 "total_columns_set", "total_cells", "total_tombstones", "has_partition_level_deletions", "tdrop_overflow", "has_legacy_counter_shards")
 def stats_dict(st):
     """b200c_sstable_stats -> plain dict (the MetadataCollector reductions, S/io/sstable/metadata/MetadataCollector.java:107-147)"""
     d = {k: int(getattr(st, k)) for k in STATS_SCALARS}

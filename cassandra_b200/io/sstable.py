@@ -63,7 +63,8 @@ def column_class(type_string: str):
     t = type_string[len(MARSHAL):] if type_string.startswith(MARSHAL) else type_string
     if t.startswith("FrozenType("): return native.TYPE_BYTES, 0                    # a frozen collection / UDT is one opaque value
     if not is_complex(type_string):
-        if t.startswith("UserType(") or t.startswith("CounterColumnType"): raise native.UnsupportedError(native.EUNSUPPORTED, "type outside the supported envelope: " + type_string)
+        if t.startswith("CounterColumnType"): return native.TYPE_COUNTER, 0            # counter context, merged shard by shard (S/db/context/CounterContext.java)
+        if t.startswith("UserType("): raise native.UnsupportedError(native.EUNSUPPORTED, "type outside the supported envelope: " + type_string)
         return type_class(type_string)
     kind, inner = t.split("(", 1); args = _split_args(inner[:-1])
     def cls(a):

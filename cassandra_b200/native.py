@@ -12,7 +12,7 @@ MAX_CLUSTERING, MAX_COLUMNS, MAX_INPUTS, MAX_STATIC_COLUMNS = 8, 64, 64, 16
 ABI_VERSION = 2
 PARTITIONER_MURMUR3, PARTITIONER_BYTE_ORDERED = 0, 1
 PSIZE_BUCKETS, CELLS_BUCKETS, HLL_P, TDROP_CAP = 156, 119, 13, 512
-TYPE_BYTES, TYPE_FIXED_SIGNED, TYPE_FIXED_BYTES, TYPE_VAR_SIGNED, TYPE_TIMEUUID = 0, 1, 2, 3, 4
+TYPE_BYTES, TYPE_FIXED_SIGNED, TYPE_FIXED_BYTES, TYPE_VAR_SIGNED, TYPE_TIMEUUID, TYPE_COUNTER = 0, 1, 2, 3, 4, 5
 MAX_COMPLEX_COLUMNS = 8
 
 class B200CError(RuntimeError):
@@ -54,7 +54,7 @@ class SSTableStats(C.Structure):
                 ("total_rows", C.c_uint64), ("total_columns_set", C.c_uint64), ("total_cells", C.c_uint64), ("total_tombstones", C.c_uint64),
                 ("has_partition_level_deletions", C.c_int32), ("tdrop_overflow", C.c_int32),
                 ("partition_size_hist", C.c_uint64 * PSIZE_BUCKETS), ("cells_per_partition_hist", C.c_uint64 * CELLS_BUCKETS),
-                ("ntdrop", C.c_uint32), ("_pad", C.c_uint32),
+                ("ntdrop", C.c_uint32), ("has_legacy_counter_shards", C.c_uint32),
                 ("tdrop_point", C.c_int64 * TDROP_CAP), ("tdrop_count", C.c_uint64 * TDROP_CAP),
                 ("hll_registers", C.c_uint8 * (1 << HLL_P))]
 class Output(C.Structure):

@@ -126,17 +126,20 @@ int          b200c_uncompress(b200c_ctx*, int compressor, const uint8_t* in, int
 /* comparison / layout class of a CQL type, as AbstractType exposes it (S/db/marshal/AbstractType.java:66-82,212-215,490,535-552) */
 enum {
     B200C_TYPE_BYTES = 0,     /* variable length, unsigned lexicographic compare (text, ascii, blob, varchar) */
-    B200C_TYPE_FIXED_SIGNED = 1, /* fixed length big-endian two's complement, signed compare (bigint 8, int 4, smallint 2, tinyint 1, timestamp 8, counter n/a) */
+    B200C_TYPE_FIXED_SIGNED = 1, /* fixed length big-endian two's complement, signed compare (bigint 8, int 4, smallint 2, tinyint 1, timestamp 8) */
     B200C_TYPE_FIXED_BYTES = 2,  /* fixed length, unsigned lexicographic compare (boolean 1, and any fixed type used only as a value) */
     B200C_TYPE_VAR_SIGNED = 3,   /* variable length payload holding a fixed-width signed int: empty value sorts first (LongType with empty) */
-    B200C_TYPE_TIMEUUID = 4      /* 16 bytes, TimeUUIDType.compareCustom (S/db/marshal/TimeUUIDType.java): timestamp fields first — cell paths of lists only */
+    B200C_TYPE_TIMEUUID = 4,     /* 16 bytes, TimeUUIDType.compareCustom (S/db/marshal/TimeUUIDType.java): timestamp fields first — cell paths of lists only */
+    B200C_TYPE_COUNTER = 5       /* CounterColumnType: variable length counter context (S/db/context/CounterContext.java:40-76); live cells of the same
+                                    row are MERGED shard by shard (Cells.resolveCounter S/db/rows/Cells.java:121-162) instead of picked. Regular
+                                    simple columns only; static counter columns are refused. */
 };
 /* A multi-cell (complex) column — non-frozen map / set / list — stores one cell per element, each with a CELL PATH (the map key, the set
  * element, the list's timeuuid), and an optional complex deletion (S/db/rows/ComplexColumnData.java, UnfilteredSerializer.java:271-280,
  * Cell.java:268-305). Same struct, no layout change: `type` carries the class of the cell VALUES in bits 0-7 and, for a complex column,
  * 1 + the class of the cell PATHS in bits 8-15 (0 = simple column); `fixed_len` the values' fixed length in bits 0-15 and the paths'
  * in bits 16-31. In a SerializationHeader the simple columns come first, then the complex ones, each group in name order
- * (ColumnMetadata.comparisonOrder): column_map must follow that order. Complex static columns, counters and non-frozen UDTs are refused. */
+ * (ColumnMetadata.comparisonOrder): column_map must follow that order. Complex static columns and non-frozen UDTs are refused. */
 #define B200C_COLUMN_COMPLEX(value_type, path_type) ((value_type) | (((path_type) + 1) << 8))
 #define B200C_COLUMN_FIXED(value_len, path_len)     ((value_len) | ((path_len) << 16))
 enum { B200C_MAX_COMPLEX_COLUMNS = 8 };
@@ -253,7 +256,8 @@ typedef struct b200c_sstable_stats {
     uint64_t cells_per_partition_hist[B200C_CELLS_BUCKETS];       /* estimatedCellPerPartitionCount */
     /* estimatedTombstoneDropTime input: exact multiset of local deletion times rounded UP to TOMBSTONE_HISTOGRAM_TTL_ROUND_SECONDS
        (60 s, StreamingTombstoneHistogramBuilder.update), ascending; the shim replays them into the stock builder */
-    uint32_t ntdrop, _pad;
+    uint32_t ntdrop;
+    uint32_t has_legacy_counter_shards;                           /* updateHasLegacyCounterShards :352-355: a written counter cell holds a local or remote shard */
     int64_t  tdrop_point[B200C_TDROP_CAP];
     uint64_t tdrop_count[B200C_TDROP_CAP];
     /* HyperLogLog++ dense registers (p = 13: 8192 six-bit registers, one per byte here) over MurmurHash.hash2_64(key, seed 0)

@@ -72,7 +72,7 @@ static const jint LAYOUT[] = {
     OFF(b200c_sstable_stats, max_local_deletion_time), OFF(b200c_sstable_stats, min_ttl), OFF(b200c_sstable_stats, max_ttl), OFF(b200c_sstable_stats, total_rows),
     OFF(b200c_sstable_stats, total_columns_set), OFF(b200c_sstable_stats, total_cells), OFF(b200c_sstable_stats, total_tombstones),
     OFF(b200c_sstable_stats, has_partition_level_deletions), OFF(b200c_sstable_stats, tdrop_overflow), OFF(b200c_sstable_stats, partition_size_hist),
-    OFF(b200c_sstable_stats, cells_per_partition_hist), OFF(b200c_sstable_stats, ntdrop), OFF(b200c_sstable_stats, tdrop_point), OFF(b200c_sstable_stats, tdrop_count),
+    OFF(b200c_sstable_stats, cells_per_partition_hist), OFF(b200c_sstable_stats, ntdrop), OFF(b200c_sstable_stats, has_legacy_counter_shards), OFF(b200c_sstable_stats, tdrop_point), OFF(b200c_sstable_stats, tdrop_count),
     OFF(b200c_sstable_stats, hll_registers),
 };
 JNIEXPORT jintArray JNICALL CLS(layout)(JNIEnv* e, jclass c)

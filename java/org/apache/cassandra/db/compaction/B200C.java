@@ -23,7 +23,7 @@ public final class B200C
     public static final int OK = 0, EINVAL = -1, ECUDA = -2, ECORRUPT = -3, ECANCELLED = -4, EUNSUPPORTED = -5, ENOMEM = -6, ETOOSMALL = -7;
     public static final int COMP_NONE = 0, COMP_LZ4 = 1, COMP_SNAPPY = 2;
     public static final int PARTITIONER_MURMUR3 = 0, PARTITIONER_BYTE_ORDERED = 1;
-    public static final int TYPE_BYTES = 0, TYPE_FIXED_SIGNED = 1, TYPE_FIXED_BYTES = 2, TYPE_VAR_SIGNED = 3, TYPE_TIMEUUID = 4;
+    public static final int TYPE_BYTES = 0, TYPE_FIXED_SIGNED = 1, TYPE_FIXED_BYTES = 2, TYPE_VAR_SIGNED = 3, TYPE_TIMEUUID = 4, TYPE_COUNTER = 5;
     public static final int MAX_COMPLEX_COLUMNS = 8;       // multi-cell (map / set / list) columns per table, B200C_MAX_COMPLEX_COLUMNS
     public static final int ABI_VERSION = 2;
     public static final int MAX_CLUSTERING = 8, MAX_COLUMNS = 64, MAX_INPUTS = 64, MAX_STATIC_COLUMNS = 16;
@@ -120,7 +120,7 @@ public final class B200C
         // b200c_sstable_stats
         public static final int S_MIN_TIMESTAMP = next(), S_MAX_TIMESTAMP = next(), S_MIN_LDT = next(), S_MAX_LDT = next(), S_MIN_TTL = next(), S_MAX_TTL = next(),
                                 S_TOTAL_ROWS = next(), S_TOTAL_COLUMNS_SET = next(), S_TOTAL_CELLS = next(), S_TOTAL_TOMBSTONES = next(), S_HAS_PARTITION_DELETIONS = next(),
-                                S_TDROP_OVERFLOW = next(), S_PARTITION_SIZE_HIST = next(), S_CELLS_HIST = next(), S_NTDROP = next(), S_TDROP_POINT = next(),
+                                S_TDROP_OVERFLOW = next(), S_PARTITION_SIZE_HIST = next(), S_CELLS_HIST = next(), S_NTDROP = next(), S_HAS_LEGACY_COUNTER_SHARDS = next(), S_TDROP_POINT = next(),
                                 S_TDROP_COUNT = next(), S_HLL_REGISTERS = next();
         // b200c_corruption, b200c_encoding_stats, b200c_column are {i32 input, i32 kind, u64 chunk, u64 offset} / {i64, i64, i32, pad} / {i32, i32}
         private Layout() {}

@@ -77,7 +77,7 @@ public class GpuCompactionTask extends CompactionTask
         TableMetadata t = cfs.metadata();
         if (inputs.isEmpty() || inputs.size() > B200C.MAX_INPUTS) return false;
         if (!(t.partitioner instanceof Murmur3Partitioner) && !(t.partitioner instanceof ByteOrderedPartitioner)) return false;
-        if (t.isCounter() || t.isIndex() || t.staticColumns().size() > B200C.MAX_STATIC_COLUMNS) return false;
+        if (t.isIndex() || t.staticColumns().size() > B200C.MAX_STATIC_COLUMNS) return false;      // (counter tables: regular counter columns only — typeClass refuses a static one)
         for (ColumnMetadata c : t.staticColumns())
             if (c.isComplex() || typeClass(c.type) < 0) return false;
         if (t.clusteringColumns().size() > B200C.MAX_CLUSTERING || t.regularColumns().size() >= B200C.MAX_COLUMNS) return false;
@@ -85,7 +85,7 @@ public class GpuCompactionTask extends CompactionTask
         for (ColumnMetadata c : t.regularColumns())
         {
             if (c.isComplex()) { if (columnClass(c.type) < 0 || ++complex > B200C.MAX_COMPLEX_COLUMNS) return false; }
-            else if (typeClass(c.type) < 0) return false;
+            else if (columnClass(c.type) < 0) return false;
         }
         for (ColumnMetadata c : t.clusteringColumns())
             if (clusteringClass(c.type) < 0) return false;
@@ -128,6 +128,7 @@ public class GpuCompactionTask extends CompactionTask
      *  (non-frozen UDTs, element types outside the envelope). Frozen collections are single opaque values. */
     static int columnClass(AbstractType<?> type)
     {
+        if (type.isCounter()) return B200C.TYPE_COUNTER;                 // counter context: merged shard by shard (Cells.resolveCounter), variable length
         if (!type.isMultiCell()) return type.isCollection() || type.isUDT() ? B200C.TYPE_BYTES : typeClass(type);
         if (!(type instanceof org.apache.cassandra.db.marshal.CollectionType)) return -1;
         org.apache.cassandra.db.marshal.CollectionType<?> ct = (org.apache.cassandra.db.marshal.CollectionType<?>) type;
@@ -432,7 +433,7 @@ public class GpuCompactionTask extends CompactionTask
         components.put(MetadataType.STATS, new StatsMetadata(new EstimatedHistogram(psizeOffsets, psize), new EstimatedHistogram(cellOffsets, cells), intervals.build(),
                                                              s.getLong(S_MIN_TIMESTAMP), s.getLong(S_MAX_TIMESTAMP), s.getLong(S_MIN_LDT), s.getLong(S_MAX_LDT),
                                                              s.getInt(S_MIN_TTL), s.getInt(S_MAX_TTL), ratio, th.build(), getLevel(), table.comparator.subtypes(), Slice.ALL,
-                                                             false, ActiveRepairService.UNREPAIRED_SSTABLE, s.getLong(S_TOTAL_COLUMNS_SET), s.getLong(S_TOTAL_ROWS), Double.NaN,
+                                                             s.getInt(S_HAS_LEGACY_COUNTER_SHARDS) != 0, ActiveRepairService.UNREPAIRED_SSTABLE, s.getLong(S_TOTAL_COLUMNS_SET), s.getLong(S_TOTAL_ROWS), Double.NaN,
                                                              org.apache.cassandra.service.StorageService.instance.getLocalHostUUID(), null, false,
                                                              s.getInt(S_HAS_PARTITION_DELETIONS) != 0, ByteBuffer.wrap(first), ByteBuffer.wrap(last)));
         components.put(MetadataType.COMPACTION, new CompactionMetadata(cardinality));

@@ -5,7 +5,7 @@
 // One call = one CompactionTask.runMayThrow hot loop (S/db/compaction/CompactionTask.java:184-236), single threaded as the
 // reference is. S/ = /root/reference/src/java/org/apache/cassandra/. Each block cites the file:line it follows.
 //
-// Scope restated: simple regular and static columns, no complex columns/counters, tombstoneOption NONE, no 2i
+// Scope restated: simple regular and static columns, multi-cell and counter regular columns, tombstoneOption NONE, no 2i
 // (rowProcessingNeeded() == false), forward order. Anything else returns B200C_EUNSUPPORTED — same envelope as the GPU engine.
 #include "codec.h"
 #include "../include/b200c.h"
@@ -69,6 +69,7 @@ struct Unf {
     bool has_data() const { return !cells.empty() || !cdel.empty(); }
     // marker: bound -> dt_open or dt_close by kind; boundary -> both
     DT m_close, m_open;
+    std::vector<std::shared_ptr<std::vector<uint8_t>>> owned;      // merged counter contexts this row's cells point into (they have no place in an input stream)
 };
 
 // ClusteringPrefix.Kind: S/db/ClusteringPrefix.java:65-82
@@ -504,6 +505,98 @@ static bool purge_marker(Unf& m, const Purger& pg) {
     return !pg.should_purge(d);
 }
 
+// ---- counter contexts: S/db/context/CounterContext.java ---------------------------------------------------------------
+// context = [i16 n = number of header elements][n x i16 element][shards: 16-byte counter id, i64 clock, i64 count] (:40-58); element e >= 0: the shard
+// with index e is LOCAL, e < 0: the shard with index e - Short.MIN_VALUE is GLOBAL; shards without an element are REMOTE. Shards are in id order.
+namespace ctr {
+enum { STEP = 32 };
+static inline int be16s(const uint8_t* p) { return (int16_t)(((uint16_t)p[0] << 8) | p[1]); }
+static inline int64_t be64s(const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 8; i++) v = (v << 8) | p[i]; return (int64_t)v; }
+static inline int header_length(const uint8_t* c) { int n = be16s(c); return 2 + (n < 0 ? -n : n) * 2; }      // headerLength :173-176
+struct State {                                                                // ContextState :757-914
+    const uint8_t* c; int len, hlen, hoff, boff; bool global = false, local = false;
+    State(const uint8_t* ctx, int n) : c(ctx), len(n) { hlen = boff = header_length(ctx); hoff = 2; upd(); }
+    int index() const { return (boff - hlen) / STEP; }
+    void upd() {                                                              // updateIsGlobalOrLocal :810-822
+        if (hoff >= hlen) { global = local = false; return; }
+        const int e = be16s(c + hoff);
+        global = e == index() + INT16_MIN; local = e == index();
+    }
+    bool has() const { return boff < len; }
+    void next() { boff += STEP; if (global || local) hoff += 2; upd(); }
+    void reset() { hoff = 2; boff = hlen; upd(); }
+    int64_t clock() const { return be64s(c + boff + 16); }
+    int64_t count() const { return be64s(c + boff + 24); }
+    int cmp_id(const State& o) const { return memcmp(c + boff, o.c + o.boff, 16); }      // compareId :178-181 (ByteBufferUtil.compareSubArrays, unsigned)
+};
+enum Rel { EQUAL, GREATER, LESS, DISJOINT };
+static Rel compare(const State& l, const State& r) {                          // :443-529
+    const int64_t lc = l.clock(), ln = l.count(), rc = r.clock(), rn = r.count();
+    if (l.global || r.global) {
+        if (l.global && r.global) { if (lc == rc) return ln > rn ? GREATER : (ln == rn ? EQUAL : LESS); return lc > rc ? GREATER : LESS; }
+        return l.global ? GREATER : LESS;
+    }
+    if (l.local || r.local) { if (l.local && r.local) return DISJOINT; return l.local ? GREATER : LESS; }
+    if (lc == rc) return ln > rn ? GREATER : (ln == rn ? EQUAL : LESS);
+    return lc > rc ? GREATER : LESS;
+}
+struct Out {                                                                   // ContextState.allocate :784-793 + writeElement :891-903
+    std::vector<uint8_t>& b; int hlen, hoff = 2, boff;
+    Out(std::vector<uint8_t>& buf, int g, int l, int rm) : b(buf) { hlen = 2 + (g + l) * 2; b.assign(hlen + (g + l + rm) * STEP, 0); b[0] = (uint8_t)((g + l) >> 8); b[1] = (uint8_t)(g + l); boff = hlen; }
+    void write(const uint8_t* id, int64_t clock, int64_t count, bool global, bool local) {
+        memcpy(&b[boff], id, 16);
+        for (int i = 0; i < 8; i++) { b[boff + 16 + i] = (uint8_t)((uint64_t)clock >> (56 - 8 * i)); b[boff + 24 + i] = (uint8_t)((uint64_t)count >> (56 - 8 * i)); }
+        if (global || local) { const int e = (boff - hlen) / STEP + (global ? INT16_MIN : 0); b[hoff] = (uint8_t)((uint16_t)(int16_t)e >> 8); b[hoff + 1] = (uint8_t)e; hoff += 2; }
+        boff += STEP;
+    }
+    void copy(const State& s) { write(s.c + s.boff, s.clock(), s.count(), s.global, s.local); }
+};
+// CounterContext.merge :296-447. Returns 0 = the left context is the result, 1 = the right one, 2 = `out` holds a new context.
+static int merge(const uint8_t* lp, int ll, const uint8_t* rp, int rl, std::vector<uint8_t>& out) {
+    bool lsup = true, rsup = true; int g = 0, lo = 0, rm = 0;
+    State l(lp, ll), r(rp, rl);
+    auto tally = [&](bool isg, bool isl) { if (isg) g++; else if (isl) lo++; else rm++; };
+    while (l.has() && r.has()) {
+        const int cmp = l.cmp_id(r);
+        if (cmp == 0) {
+            const Rel rel = compare(l, r);
+            if (rel == GREATER) rsup = false; else if (rel == LESS) lsup = false; else if (rel == DISJOINT) lsup = rsup = false;
+            tally(l.global || r.global, l.local || r.local);
+            l.next(); r.next();
+        } else if (cmp > 0) { lsup = false; tally(r.global, r.local); r.next(); }
+        else { rsup = false; tally(l.global, l.local); l.next(); }
+    }
+    if (l.has()) rsup = false; else if (r.has()) lsup = false;
+    if (lsup) return 0;
+    if (rsup) return 1;
+    while (l.has()) { tally(l.global, l.local); l.next(); }
+    while (r.has()) { tally(r.global, r.local); r.next(); }
+    l.reset(); r.reset();
+    Out o(out, g, lo, rm);
+    while (l.has() && r.has()) {
+        const int cmp = l.cmp_id(r);
+        if (cmp == 0) {
+            const Rel rel = compare(l, r);
+            if (rel == DISJOINT) o.write(l.c + l.boff, (int64_t)((uint64_t)l.clock() + (uint64_t)r.clock()), (int64_t)((uint64_t)l.count() + (uint64_t)r.count()), false, true);
+            else if (rel == GREATER) o.copy(l); else o.copy(r);
+            r.next(); l.next();
+        } else if (cmp > 0) { o.copy(r); r.next(); } else { o.copy(l); l.next(); }
+    }
+    while (l.has()) { o.copy(l); l.next(); }
+    while (r.has()) { o.copy(r); r.next(); }
+    return 2;
+}
+// hasLegacyShards :595-608
+static bool has_legacy_shards(const uint8_t* c, int len) {
+    const int total = (len - header_length(c)) / STEP; int n = be16s(c); if (n < 0) n = -n;
+    if (n < total) return true;
+    for (int i = 0; i < n; i++) if (be16s(c + 2 + 2 * i) >= 0) return true;
+    return false;
+}
+// what the walk of ContextState needs from stored bytes: a whole header, whole shards (anything else throws in the reference's ByteBuffer reads)
+static bool well_formed(const uint8_t* c, int len) { return len >= 2 && header_length(c) <= len && (len - header_length(c)) % STEP == 0; }
+}  // namespace ctr
+
 // ---- Cells.reconcile: S/db/rows/Cells.java:68-121 ---------------------------------------------------------------------
 static const CellV& reconcile(const CellV& l, const CellV& r) {
     if (l.ts != r.ts) return l.ts > r.ts ? l : r;
@@ -520,6 +613,26 @@ static const CellV& reconcile(const CellV& l, const CellV& r) {
     return c >= 0 ? l : r;
 }
 
+// Cells.reconcile for a counter column :73-74 -> resolveCounter :121-162 (isCounterCell = the column is a counter and the cell is no tombstone,
+// S/db/rows/AbstractCell.java:46-49). `out` owns the merged context when a new one is built.
+static CellV reconcile_counter(const CellV& l, const CellV& r, Unf& out) {
+    const bool lt = l.tombstone(), rt = r.tombstone();
+    if (lt && rt) return reconcile(l, r);                                     // neither is a counter cell: resolveRegular
+    if (lt | rt) return lt ? l : r;                                           // a tombstone always wins (CASSANDRA-7346)
+    const bool le = l.vlen == 0, re = r.vlen == 0;
+    if (le || re) { if (le != re) return le ? l : r; return l.ts > r.ts ? l : r; }      // :142-149
+    if (!ctr::well_formed(l.val, l.vlen) || !ctr::well_formed(r.val, r.vlen)) throw Corrupt{0, 4, 0, 0, "malformed counter context"};
+    auto buf = std::make_shared<std::vector<uint8_t>>();
+    const int which = ctr::merge(l.val, l.vlen, r.val, r.vlen, *buf);
+    const int64_t ts = std::max(l.ts, r.ts);
+    if (which == 0 && ts == l.ts) return l;
+    if (which == 1 && ts == r.ts) return r;
+    CellV m = l; m.ts = ts; m.ttl = 0; m.ldt = NO_DEL;                        // new BufferCell(left.column(), timestamp, NO_TTL, NO_DELETION_TIME, merged, left.path())
+    if (which == 0) { m.val = l.val; m.vlen = l.vlen; } else if (which == 1) { m.val = r.val; m.vlen = r.vlen; }
+    else { out.owned.push_back(buf); m.val = buf->data(); m.vlen = (int32_t)buf->size(); }
+    return m;
+}
+
 // Row.Merger.merge: S/db/rows/Row.java:730-781; ColumnDataReducer.getReduced :838-883 (simple cell / multi-cell column). Returns false for null.
 static bool merge_rows(std::vector<Unf*>& versions, DT active, Unf& out, const Schema* sc = nullptr, bool stat = false) {
     if (versions.size() == 1 && active.live()) { out = *versions[0]; return true; }
@@ -530,13 +643,25 @@ static bool merge_rows(std::vector<Unf*>& versions, DT active, Unf& out, const S
     }
     if (del.supersedes(active)) active = del; else del = DT();
     if (active.deletes(info.ts)) info = Live();          // deletes(LivenessInfo) = deletes(timestamp); EMPTY ts = MIN is always "deleted" but stays EMPTY
-    out.is_row = true; out.c = versions[0]->c; out.info = info; out.del = del; out.cells.clear(); out.cdel.clear();
+    out.is_row = true; out.c = versions[0]->c; out.info = info; out.del = del; out.cells.clear(); out.cdel.clear(); out.owned.clear();
     size_t cur[B200C_MAX_INPUTS] = {0};
     uint64_t cols_present = 0;                             // columns any version has data for (a multi-cell column may consist of its deletion only)
     for (Unf* v : versions) { for (const CellV& c : v->cells) cols_present |= 1ull << c.col; for (auto& d : v->cdel) cols_present |= 1ull << d.first; }
     for (int col = 0; col < 64; col++) {
         if (!((cols_present >> col) & 1)) continue;
         const bool complex = sc && !stat && col_complex(sc->cols[col]);
+        if (!complex && sc && !stat && sc->cols[col].type == B200C_TYPE_COUNTER) {
+            bool have = false; CellV merged{};
+            for (size_t i = 0; i < versions.size(); i++) {
+                if (cur[i] < versions[i]->cells.size() && versions[i]->cells[cur[i]].col == col) {
+                    const CellV& c = versions[i]->cells[cur[i]++];
+                    if (active.deletes(c.ts)) continue;
+                    if (have) merged = reconcile_counter(merged, c, out); else { merged = c; have = true; }
+                }
+            }
+            if (have) out.cells.push_back(merged);
+            continue;
+        }
         if (!complex) {
             const CellV* merged = nullptr;
             for (size_t i = 0; i < versions.size(); i++) {
@@ -657,8 +782,11 @@ struct Meta {
     void update(const DT& d) { if (d.live()) return; ts(d.mfda); ldt(d.ldt); total_tombstones++; }                                        // :237-245
     void update(const CellV& c) { cur_cells++; total_cells++; ts(c.ts); ttl(c.ttl); ldt(c.ldt); if (!c.is_live(now)) total_tombstones++; } // :220-228
     void partition_deletion(const DT& d) { if (!d.live()) has_partition_deletions = true; update(d); }                                    // :230-235
-    void row(const Unf& u) {                                                // Rows.collectStats S/db/rows/Rows.java:102-113
+    bool has_legacy_counter_shards = false;
+    void row(const Unf& u, const b200c_column* types = nullptr) {           // Rows.collectStats S/db/rows/Rows.java:102-113 (types: the regular columns' — null for a static row)
         update(u.info); update(u.del);
+        if (types) for (const CellV& c : u.cells)                             // Cells.collectStats S/db/rows/Cells.java:44-50
+            if (types[c.col].type == B200C_TYPE_COUNTER && !c.tombstone() && c.vlen >= 2 && ctr::has_legacy_shards(c.val, c.vlen)) has_legacy_counter_shards = true;
         for (auto& d : u.cdel) update(d.second);                              // StatsAccumulation.accumulateOnColumnData S/db/rows/Rows.java:66-82
         int cols_with_cells = 0, last = -1;
         for (const CellV& c : u.cells) { update(c); if (c.col != last) { cols_with_cells++; last = c.col; } }
@@ -722,7 +850,7 @@ struct Meta {
         for (int i = 0; i < B200C_CELLS_BUCKETS; i++) st->cells_per_partition_hist[i] = cells[i];
         uint32_t k = 0;
         for (auto& kv : tdrop) { if (k >= B200C_TDROP_CAP) { st->tdrop_overflow = 1; break; } st->tdrop_point[k] = kv.first; st->tdrop_count[k] = kv.second; k++; }      // the CAP smallest points
-        st->ntdrop = k;
+        st->ntdrop = k; st->has_legacy_counter_shards = has_legacy_counter_shards ? 1 : 0;
         memcpy(st->hll_registers, hll.data(), hll.size());
     }
 };
@@ -923,7 +1051,7 @@ struct Writer {
         write(tmp.b.data(), tmp.b.size());
         write(body.b.data(), body.b.size());
         last_c = u.c; prev_row_start = pos;
-        if (u.is_row) outs.back().meta.row(u); else outs.back().meta.marker(u);
+        if (u.is_row) outs.back().meta.row(u, sc.cols); else outs.back().meta.marker(u);
         if (!u.is_row) open_marker = (kind_is_boundary(u.c.kind) || kind_is_start(u.c.kind)) ? u.m_open : DT();
         outs.back().rows++;
         if (cur_pos() - block_start >= (uint64_t)m->column_index_size) add_index_block();     // BigFormatPartitionWriter.addUnfiltered :208-215
@@ -969,7 +1097,8 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
         if (col_complex(sc.cols[k]) && (pt < 0 || pt > B200C_TYPE_TIMEUUID)) return B200C_EINVAL;
     }
     if (sc.ncomplex > B200C_MAX_COMPLEX_COLUMNS) return B200C_EUNSUPPORTED;
-    for (int k = 0; k < m->nstatic_columns; k++) if (col_complex(sc.stat[k])) return B200C_EUNSUPPORTED;
+    for (int k = 0; k < m->nstatic_columns; k++) if (col_complex(sc.stat[k]) || sc.stat[k].type == B200C_TYPE_COUNTER) return B200C_EUNSUPPORTED;
+    for (int k = 0; k < m->ncolumns; k++) if (col_complex(sc.cols[k]) && col_value_type(sc.cols[k]).type == B200C_TYPE_COUNTER) return B200C_EINVAL;      // (no collections of counters)
     g_partitioner = m->partitioner;
     std::vector<Source> srcs(m->ninputs);
     uint64_t bytes_read = 0;
@@ -1103,3 +1232,16 @@ extern "C" int orc_compact(const b200c_manifest* m, b200c_result* res, char* err
         return B200C_ECORRUPT;
     }
 }
+
+// test hook: CounterContext.merge on two contexts. Returns the merged length (bytes in out), or -1 when a context is malformed / out too small.
+extern "C" int orc_counter_merge(const uint8_t* l, int ll, const uint8_t* r, int rl, uint8_t* out, int cap, int* which) {
+    if (!oracle::ctr::well_formed(l, ll) || !oracle::ctr::well_formed(r, rl)) return -1;
+    std::vector<uint8_t> buf;
+    const int w = oracle::ctr::merge(l, ll, r, rl, buf);
+    if (which) *which = w;
+    const uint8_t* p = w == 0 ? l : (w == 1 ? r : buf.data()); const int n = w == 0 ? ll : (w == 1 ? rl : (int)buf.size());
+    if (n > cap) return -1;
+    memcpy(out, p, n);
+    return n;
+}
+extern "C" int orc_counter_has_legacy_shards(const uint8_t* c, int n) { return oracle::ctr::well_formed(c, n) ? (oracle::ctr::has_legacy_shards(c, n) ? 1 : 0) : -1; }

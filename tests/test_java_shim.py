@@ -48,7 +48,7 @@ def test_layout_table_matches_the_ctypes_mirror(jni):
                                  "merged_row_counts", "required_data_cap", "required_index_cap", "required_chunk_cap", "corruption", "kernel_ms", "total_ms"])
     want += offs(native.SSTableStats, ["min_timestamp", "max_timestamp", "min_local_deletion_time", "max_local_deletion_time", "min_ttl", "max_ttl", "total_rows",
                                        "total_columns_set", "total_cells", "total_tombstones", "has_partition_level_deletions", "tdrop_overflow", "partition_size_hist",
-                                       "cells_per_partition_hist", "ntdrop", "tdrop_point", "tdrop_count", "hll_registers"])
+                                       "cells_per_partition_hist", "ntdrop", "has_legacy_counter_shards", "tdrop_point", "tdrop_count", "hll_registers"])
     assert got == want
 
 def test_java_sources_are_present_and_name_the_reference_hooks():

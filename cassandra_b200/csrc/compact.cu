@@ -1015,7 +1015,13 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             if (!hp.ncx) hp.cx_first = k;
             hp.ptype[hp.ncx] = ptype; hp.pfix[hp.ncx] = (int32_t)((uint32_t)m->columns[k].fixed_len >> 16); hp.ncx++;
         } else if (hp.ncx) { c->err = "simple column behind a multi-cell one (ColumnMetadata order: simple columns first)"; return B200C_EINVAL; }
+        if ((m->columns[k].type & 0xFF) == B200C_TYPE_COUNTER) {      // counter columns: cells merged shard by shard (partition.cuh ctr_merge), CX kernels
+            if (ptype >= 0) { c->err = "collection of counters"; return B200C_EINVAL; }
+            hp.ctr_mask |= 1ull << k;
+        }
     }
+    if (!hp.ncx) hp.cx_first = m->ncolumns;
+    for (int k = 0; k < m->nstatic_columns; k++) if ((m->static_columns[k].type & 0xFF) == B200C_TYPE_COUNTER) { c->err = "static counter column"; return B200C_EUNSUPPORTED; }
     hp.nstat = m->nstatic_columns; hp.mcols = std::max(m->ncolumns, m->nstatic_columns);
     for (int k = 0; k < m->nstatic_columns; k++) hp.sfix[k] = m->static_columns[k].fixed_len;
     hp.o_min_ts = m->out_stats.min_timestamp; hp.o_min_ldt = m->out_stats.min_local_deletion_time; hp.o_min_ttl = m->out_stats.min_ttl;
@@ -1590,8 +1596,8 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         launch_k4 = [&, n_le8, n_le12, n_le16, n_le32, np_, smem8, smem12, smem16, smem64, cell_smem32](int mode) -> int {
             ka.mode = mode;
             const bool emit = mode != 0;
-            if (hp.ncx) {
-                // tables with multi-cell (complex) columns: the CX instantiations of the thread kernels, for every fan-in (64 cursors per thread above 16);
+            if (hp.ncx || hp.ctr_mask) {
+                // tables with multi-cell (complex) or counter columns: the CX instantiations of the thread kernels, for every fan-in (64 cursors per thread above 16);
                 // single serialisation pass only (the size-pass A/B mode is refused above)
                 if (!emit) { c->err = "B200C_K4_TWO_PASS with multi-cell columns"; return B200C_EUNSUPPORTED; }
                 if (n_le8) B200C_LAUNCH(c, (k_partition_thr<8, 128, true, true>), (unsigned)((n_le8 + 127) / 128), 128, smem8, ka, 0ull, n_le8);
@@ -1661,7 +1667,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 B200C_TRY(ws_typed(c, WS_SCRATCH, h[0] + 64, &SCRATCH));
                 B200C_TRY(ws_typed(c, WS_ISCR, h[1] + 64, &ISCR));
                 ka.doff = d_bpos; ka.dcapv = d_bound; ka.dbase = SCRATCH; ka.iout = nullptr; ka.ioff = d_ioff; ka.icapv = d_icap; ka.iscr = ISCR;
-                const bool staged = !hp.ncx && []() { const char* e = getenv("B200C_K4_STAGED"); return e ? atoi(e) != 0 : (B200C_K4_STAGED_DEFAULT != 0); }();      // A/B switch (read per call; tables with multi-cell columns: thread kernels)
+                const bool staged = !hp.ncx && !hp.ctr_mask && []() { const char* e = getenv("B200C_K4_STAGED"); return e ? atoi(e) != 0 : (B200C_K4_STAGED_DEFAULT != 0); }();      // A/B switch (read per call; tables with multi-cell columns: thread kernels)
                 if (staged) {
                     // tile plan: exclusive scan of the input bytes, cut marks, scan of the marks, tile starts
                     uint64_t *d_inpos, *d_tscan; uint32_t *d_mark, *d_tstart; unsigned long long* d_nbig = (unsigned long long*)(d_stats + 1);
@@ -1860,7 +1866,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             s->min_local_deletion_time = (g->seen & 2) ? g->min_ldt : I64_MAX; s->max_local_deletion_time = (g->seen & 2) ? g->max_ldt : I64_MAX;
             s->min_ttl = (g->seen & 4) ? g->min_ttl : 0; s->max_ttl = (g->seen & 4) ? g->max_ttl : 0;
             s->total_rows = g->rows; s->total_columns_set = g->cols; s->total_cells = g->cells; s->total_tombstones = g->tombs;
-            s->has_partition_level_deletions = g->pdel ? 1 : 0; s->tdrop_overflow = g->tdrop_overflow ? 1 : 0;
+            s->has_partition_level_deletions = g->pdel ? 1 : 0; s->tdrop_overflow = g->tdrop_overflow ? 1 : 0; s->has_legacy_counter_shards = (g->seen & 8) ? 1 : 0;
             for (int i = 0; i < META_PSIZE; i++) s->partition_size_hist[i] = g->psize[i];
             for (int i = 0; i < META_CELLS; i++) s->cells_per_partition_hist[i] = g->cells_hist[i];
             s->ntdrop = (uint32_t)std::min<uint64_t>(g->tdrop_n, B200C_TDROP_CAP);

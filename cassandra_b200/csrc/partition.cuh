@@ -46,6 +46,7 @@ struct CParams {
     // those is the fixed length of their cell VALUES, ptype / pfix class and fixed length of their cell PATHS
     int32_t ncx, cx_first;
     int32_t ptype[MAXCX], pfix[MAXCX];
+    uint64_t ctr_mask;             // bit c: regular simple column c is a counter column (cells merged shard by shard; tables with any use the CX kernels)
     int32_t partitioner;           // 0 Murmur3Partitioner, 1 ByteOrderedPartitioner (tok[] then holds the sign-flipped 8-byte key prefix)
     int64_t now, gc_before, purge_max_ts;
     // optional purge table (b200c_manifest.purge_range_*): ascending token bounds and the threshold that applies up to each of them
@@ -469,6 +470,9 @@ struct CxCol { DT cd; uint32_t ncells; uint8_t pre, post; };                    
 struct CxEmit { const CxVer* ver; int nver; bool as_is; DT active; const CxCol* col; const Purger* pg; };
 template <bool E> __device__ int cx_merge(const CParams& P, const Purger& pg, const CxVer* ver, int nver, bool as_is, DT active, int j,
                                          const Live info, CxCol* sum, Sink<E>* s, bool row_has_cd, const CxCol* known, StatAcc* acc);      // (multi-cell columns, below)
+// a merged counter cell has no bytes in an input stream: MCell.voff says so and carries what the header needs (counter columns, below)
+constexpr uint64_t CTR_SYNTH = 1ull << 63, CTR_LEGACY = 1ull << 62;
+template <bool E> __device__ int ctr_merge(const CParams& P, const CxVer* ver, int nver, DT active, int oc, MCell* sum, Sink<E>* s, int nhdr);
 // row body: UnfilteredSerializer.serializeRowBody :213-269 + Cell.Serializer.serialize S/db/rows/Cell.java:268-305
 template <bool E, bool CX = false> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const CParams& P, int flags, Live info, DT del, const MCell* cells, int ncols, const int32_t* vfix, const CxEmit* cx = nullptr) {
     if (flags & 0x04) s.vint((uint64_t)info.ts - (uint64_t)P.o_min_ts);
@@ -493,6 +497,11 @@ template <bool E, bool CX = false> __device__ __noinline__ uint64_t put_row_body
         if (!use_ts) s.vint((uint64_t)m.ts - (uint64_t)P.o_min_ts);
         if ((deleted || expiring) && !use_ttl) s.vint((uint64_t)(int64_t)(int32_t)(m.ldt - P.o_min_ldt));
         if (expiring && !use_ttl) s.vint((uint64_t)(int64_t)(m.ttl - P.o_min_ttl));
+        if constexpr (CX) if (m.voff & CTR_SYNTH) {      // the merged context is written from the versions' contexts (ctr_merge)
+            s.vint((uint64_t)m.vlen);
+            ctr_merge<E>(P, cx->ver, cx->nver, cx->active, c, nullptr, &s, (int)(m.voff & 0xFFFF));
+            continue;
+        }
         if (has_value) { if (vfix[c] <= 0) s.vint((uint64_t)m.vlen); s.copy(P.U + m.voff, (uint32_t)m.vlen); }
     }
     return s.pos;
@@ -696,6 +705,130 @@ template <bool E> __device__ __noinline__ int cx_merge(const CParams& P, const P
     return 0;
 }
 
+// ---- counter columns (CounterColumnType) -----------------------------------------------------------------------------------------------
+// A counter cell's value is a context: [i16 n][n x i16 header element][shards of 32 bytes: 16-byte counter id, i64 clock, i64 count], shards in id
+// order; element e >= 0 marks shard e LOCAL, e < 0 marks shard e + 32768 GLOBAL, the others are REMOTE (S/db/context/CounterContext.java:40-76).
+// Live counter cells of one row are not picked but merged (Cells.resolveCounter S/db/rows/Cells.java:121-162 -> CounterContext.merge :296-447).
+// The reference folds the versions pairwise; the per-id rules (:66-73: a global shard beats the others, the largest (clock, count) among globals;
+// else the local shards ADD; else the largest (clock, count) among remotes) are associative and commutative, so the fold over the versions is
+// one K-way merge by counter id — done here straight from the versions' bytes, twice: count (the value length and the header precede the
+// shards), then write. The pairwise fold returns an input context UNCHANGED when it covers the other one; that equals the rebuilt context only
+// for contexts in the form the reference itself writes (every header element meets its shard, ids strictly increasing, n >= 0): anything
+// else in a merge is refused (PERR_UNSUPPORTED) rather than guessed at. Cells the active deletion covers are skipped BEFORE the merge
+// (Row.java:838-849) — the merged cell carries the largest timestamp, so filtering afterwards would not be the same.
+__device__ __noinline__ bool ctr_cell(const CParams& P, const CxVer& v, int oc, PCell* out, int* err) {      // the cell of simple column oc in version v
+    const InDesc& in = P.in[v.src];
+    Rd r{P.U, v.cells, v.end, 0};
+    uint64_t missing = 0;
+    if (!(v.flags & 0x20)) missing = r.vint();
+    for (int i = 0; i < in.ncols && !r.err; i++) {
+        if ((missing >> i) & 1) continue;
+        const int oci = in.colmap[i];
+        if (oci >= P.cx_first) break;
+        cx_read_cell(in, r, v, P.vfix[oci], -1, out);
+        if (r.err) break;
+        if (oci == oc) return true;
+    }
+    if (r.err) *err = r.err;
+    return false;
+}
+__device__ __forceinline__ int ctr_be16(const uint8_t* p) { return (int)(int16_t)(((uint32_t)p[0] << 8) | p[1]); }
+// hasLegacyShards :595-608 (the caller has checked vlen >= 2)
+__device__ __noinline__ bool ctr_has_legacy(const uint8_t* c, int len) {
+    int n = ctr_be16(c); if (n < 0) n = -n;
+    const int hl = 2 + 2 * n; if (hl > len) return false;
+    if (n < (len - hl) / 32) return true;
+    for (int i = 0; i < n; i++) if (ctr_be16(c + 2 + 2 * i) >= 0) return true;
+    return false;
+}
+// sum != nullptr: what column oc of the merged row is (MCell; a merged context: voff = CTR_SYNTH | CTR_LEGACY? | header elements, vlen = its length).
+// s != nullptr: write the merged context (the summary said CTR_SYNTH and how many header elements, nhdr). Returns an error code.
+template <bool E> __device__ __noinline__ int ctr_merge(const CParams& P, const CxVer* ver, int nver, DT active, int oc, MCell* sum, Sink<E>* s, int nhdr) {
+    uint64_t base[MAXK]; uint16_t len[MAXK], hl[MAXK], bo[MAXK], ho[MAXK];
+    int err = 0, ncand = 0, first = -1;
+    MCell tomb, empty, one; tomb.present = empty.present = false; one.present = false;
+    int64_t ts_max = I64_MIN;
+    for (int v = 0; v < nver; v++) {
+        base[v] = ~0ull; len[v] = hl[v] = bo[v] = ho[v] = 0;
+        PCell c;
+        if (!ctr_cell(P, ver[v], oc, &c, &err)) { if (err) return err; continue; }
+        if (dt_deletes(active, c.m.ts)) continue;
+        ncand++; if (first < 0) { first = v; one = c.m; }
+        if (c.m.ldt != I64_MAX && c.m.ttl == 0) { if (!tomb.present || !reconcile_keep_left(P, tomb, c.m)) tomb = c.m; continue; }     // tombstones among themselves: resolveRegular
+        if (c.m.vlen == 0) { if (!empty.present || !(empty.ts > c.m.ts)) empty = c.m; continue; }                                    // :142-149
+        if (c.m.ttl != 0) return PERR_UNSUPPORTED;                    // (a counter cell cannot expire)
+        if (c.m.vlen < 2 || c.m.vlen > 0xFFFF) return PERR_CORRUPT;
+        const int n = ctr_be16(P.U + c.m.voff);
+        if (n < 0) return PERR_UNSUPPORTED;                           // "local shards to be cleared" marker (:618-628): only on streamed cells
+        const int h = 2 + 2 * n;
+        if (h > c.m.vlen || (c.m.vlen - h) % 32) return PERR_CORRUPT;
+        base[v] = c.m.voff; len[v] = (uint16_t)c.m.vlen; hl[v] = bo[v] = (uint16_t)h; ho[v] = 2;
+        ts_max = c.m.ts > ts_max ? c.m.ts : ts_max;
+    }
+    if (sum) {
+        sum->present = ncand > 0;
+        if (!ncand) return 0;
+        if (ncand == 1) { *sum = one; return 0; }
+        if (tomb.present) { *sum = tomb; return 0; }                 // a tombstone beats every counter cell whatever the timestamps (CASSANDRA-7346)
+        if (empty.present) { *sum = empty; return 0; }
+    }
+    // K-way merge by counter id
+    int ng = 0, nl = 0, nr = 0;
+    Sink<E> hs{nullptr, 0, false, 0}, bs{nullptr, 0, false, 0};
+    if (s) { hs = *s; bs = *s; bs.pos = s->pos + 2 + 2 * (uint64_t)nhdr; hs.be16((uint32_t)nhdr); }      // header elements and shards are written side by side
+    for (;;) {
+        int b = -1;
+        for (int v = 0; v < nver; v++) {
+            if (base[v] == ~0ull || bo[v] >= len[v]) continue;
+            if (b < 0) { b = v; continue; }
+            const uint8_t* x = P.U + base[v] + bo[v]; const uint8_t* y = P.U + base[b] + bo[b];
+            const uint64_t x0 = load_be64(x), y0 = load_be64(y);
+            if (x0 < y0 || (x0 == y0 && load_be64(x + 8) < load_be64(y + 8))) b = v;
+        }
+        if (b < 0) break;
+        const uint8_t* id = P.U + base[b] + bo[b];
+        const uint64_t id0 = load_be64(id), id1 = load_be64(id + 8);
+        int kind = 0; int64_t clock = 0, count = 0; bool have = false;          // kind: 2 global, 1 local, 0 remote
+        for (int v = 0; v < nver; v++) {
+            if (base[v] == ~0ull || bo[v] >= len[v]) continue;
+            const uint8_t* x = P.U + base[v] + bo[v];
+            if (load_be64(x) != id0 || load_be64(x + 8) != id1) continue;
+            int k = 0;
+            if (ho[v] < hl[v]) {                                                // ContextState.updateIsGlobalOrLocal :810-822
+                const int e = ctr_be16(P.U + base[v] + ho[v]), idx = (bo[v] - hl[v]) / 32;
+                if (e == idx - 32768) k = 2; else if (e == idx) k = 1;
+                if (k) ho[v] += 2;
+            }
+            const int64_t cl = (int64_t)load_be64(x + 16), cn = (int64_t)load_be64(x + 24);
+            bo[v] += 32;
+            if (bo[v] < len[v]) {                                               // ids strictly increasing inside one context
+                const uint8_t* nx = P.U + base[v] + bo[v];
+                const uint64_t n0 = load_be64(nx), n1 = load_be64(nx + 8);
+                if (n0 < id0 || (n0 == id0 && n1 <= id1)) return PERR_UNSUPPORTED;
+            } else if (ho[v] != hl[v]) return PERR_UNSUPPORTED;                 // a header element that met no shard
+            if (!have || k > kind) { kind = k; clock = cl; count = cn; have = true; }
+            else if (k == kind) {
+                if (k == 1) { clock = (int64_t)((uint64_t)clock + (uint64_t)cl); count = (int64_t)((uint64_t)count + (uint64_t)cn); }
+                else if (cl > clock || (cl == clock && cn > count)) { clock = cl; count = cn; }
+            }
+        }
+        const int idx = ng + nl + nr;
+        if (kind == 2) ng++; else if (kind == 1) nl++; else nr++;
+        if (s) {
+            bs.copy(id, 16); bs.be64((uint64_t)clock); bs.be64((uint64_t)count);
+            if (kind) hs.be16((uint32_t)(kind == 2 ? idx - 32768 : idx) & 0xFFFF);
+        }
+    }
+    if (ng + nl + nr > 0x7FFF) return PERR_UNSUPPORTED;                 // (a header element is an i16 shard index)
+    if (sum) {
+        sum->present = true; sum->ts = ts_max; sum->ldt = I64_MAX; sum->ttl = 0;
+        sum->vlen = 2 + 2 * (ng + nl) + 32 * (ng + nl + nr);
+        sum->voff = CTR_SYNTH | ((nl || nr) ? CTR_LEGACY : 0) | (uint64_t)(ng + nl);
+    }
+    if (s) s->pos = bs.pos;
+    return 0;
+}
+
 // Tables with static columns carry a static row in every partition, the empty one included (SortedTableWriter.append :144-146,
 // SortedTablePartitionWriter.addStaticRow :117-126, UnfilteredSerializer.serializeStaticRow :144-149): flags | EXTENSION, extended flags
 // IS_STATIC, no clustering, previous size 0. scells == nullptr: the (merged, purged) static row is empty.
@@ -762,6 +895,11 @@ template <bool EMIT, bool CX = false> __device__ __forceinline__ void write_row(
         w.acc->live(info); w.acc->dt(del);
         const int nsimple = CX ? P.cx_first : P.ncols; int simple_present = 0;
         for (int c = 0; c < nsimple; c++) if (cells[c].present) { w.acc->cell(cells[c]); simple_present++; }
+        if constexpr (CX) for (uint64_t bits = P.ctr_mask; bits; bits &= bits - 1) {                      // Cells.collectStats S/db/rows/Cells.java:44-50: updateHasLegacyCounterShards
+            const MCell& m = cells[__ffsll((long long)bits) - 1];
+            if (!m.present || (m.ldt != I64_MAX && m.ttl == 0)) continue;
+            if ((m.voff & CTR_SYNTH) ? (m.voff & CTR_LEGACY) != 0 : (m.vlen >= 2 && ctr_has_legacy(P.U + m.voff, m.vlen))) w.acc->seen |= 8;
+        }
         w.acc->cols += (unsigned long long)simple_present; w.acc->rows++;
         if constexpr (CX) for (int j = 0; j < P.ncx; j++) if (cells[P.cx_first + j].present)
             cx_merge<EMIT>(P, *cx->pg, cx->ver, cx->nver, cx->as_is, cx->active, j, info, nullptr, (Sink<EMIT>*)nullptr, false, nullptr, w.acc);
@@ -873,6 +1011,12 @@ template <class CUR> __device__ __noinline__ int cx_row_summary(const CParams& P
         if (e) return e;
         merged[P.cx_first + j].present = col[j].post != 0; *pre += col[j].pre; *post += col[j].post;
     }
+    // counter columns of a row with several versions: Cells.resolveCounter instead of the winner fold_cells picked (see ctr_merge)
+    if (!as_is && nv > 1) for (uint64_t bits = P.ctr_mask; bits; bits &= bits - 1) {
+        const int oc = __ffsll((long long)bits) - 1;
+        const int e = ctr_merge<false>(P, ver, nv, active, oc, &merged[oc], (Sink<false>*)nullptr, 0);
+        if (e) return e;
+    }
     *nver_out = nv;
     return 0;
 }
@@ -894,7 +1038,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
     uint64_t sgrp = 0;                                // contributors with a non-empty static row
-    if (m > MAXK || (!CX && P.ncx)) { err = PERR_UNSUPPORTED; return; }
+    if (m > MAXK || (!CX && (P.ncx || P.ctr_mask))) { err = PERR_UNSUPPORTED; return; }
     // prologue in three sweeps so that the m dependent chains (contrib -> upos -> Data bytes) overlap instead of serialising:
     // (1) resolve the input partitions, (2) prefetch their first lines, (3) parse the partition headers
     for (uint32_t v = 0; v < mu; v++) {
@@ -1003,6 +1147,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
                 CxVer cxv[MCAP]; CxCol cxc[MAXCX];
                 int cx_pre = 0, cx_post = 0, cx_nver = 0;
                 { int e = cx_row_summary(P, pg, cur, grp, as_is, active, cxv, cxc, merged, &cx_pre, &cx_post, &cx_nver); if (e) { err = e; break; } }
+                if (P.ctr_mask) { npresent = 0; for (int k = 0; k < nsimple; k++) npresent += merged[k].present; }      // (the counter columns were merged there)
                 if (!(live_is_empty(info) && dt_is_live(del) && npresent + cx_pre == 0)) {
                     st.merged_unfiltereds++;
                     CUR& f = cur[b];

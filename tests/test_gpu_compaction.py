@@ -678,3 +678,44 @@ def test_complex_columns_streamed_and_sharded(ctx, monkeypatch):
     want = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(O.OracleEngine()).outputs[0]
     g = CompactionTask(tabs, CompactionController(NOW), token_range=(lo, hi)).execute(GpuEngine(ctx)).outputs[0]
     assert g.data == want.data and g.index == want.index and g.digest == want.digest
+
+# ---- counter columns ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,ntab,big,cis,legacy", [(1, 5, False, 65536, True), (2, 20, False, 65536, False), (3, 3, True, 2048, True), (4, 40, False, 65536, True)])
+def test_counter_columns_match_oracle(ctx, seed, ntab, big, cis, legacy):
+    """counter contexts merged shard by shard (the K-way merge of partition.cuh against the oracle's pairwise fold): global / local / remote rules,
+    tombstones and empty values, cells under a deletion left out of the merge, the merged timestamp, hasLegacyCounterShards; fan-ins up to 40"""
+    from counter_tables import counter_tables
+    tabs = counter_tables(seed, ntables=ntab, nkeys=60 if not big else 6, cis=cis, big=big, legacy=legacy)
+    both(ctx, tabs, CompactionController(NOW, 864000), column_index_size=cis, with_metadata=True)
+    both(ctx, tabs, CompactionController(NOW, 10 ** 9), column_index_size=cis)
+    both(ctx, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis, with_metadata=True)
+    both(ctx, tabs, CompactionController(NOW, 0), column_index_size=cis, with_metadata=True)
+
+@pytest.mark.parametrize("name", ["legacy_oa_simple_counter", "legacy_oa_clust_counter"])
+def test_golden_counter_tables(ctx, golden_dir, name):
+    """the reference's own counter tables (written by a 5.0 node): identity compaction and the three-way self merge reproduce the files"""
+    base = _golden(golden_dir, name)
+    s = SSTable.open(base)
+    r = CompactionTask([s], CompactionController(NOW), column_index_size=4096).execute(GpuEngine(ctx))
+    comp = r.outputs[0].components()
+    for c in ("Data.db", "Index.db", "CompressionInfo.db", "Digest.crc32"):
+        assert comp[c] == open(base + c, "rb").read(), c
+    r3 = CompactionTask([SSTable.open(base, 1), SSTable.open(base, 2), SSTable.open(base, 3)], CompactionController(NOW), column_index_size=4096).execute(GpuEngine(ctx))
+    assert r3.outputs[0].components()["Data.db"] == open(base + "Data.db", "rb").read()
+
+def test_counter_columns_streamed_and_unsupported_forms(ctx, monkeypatch):
+    from counter_tables import counter_tables, SCTR, ctx as cctx, cid, G, T0
+    from cassandra_b200 import native
+    tabs = counter_tables(9, ntables=6, nkeys=2500)
+    monkeypatch.setenv("B200C_RANGES", "4")
+    both(ctx, tabs, CompactionController(NOW, 864000))
+    monkeypatch.delenv("B200C_RANGES")
+    # a context whose header element meets no shard is not what the reference writes: in a merge the engine refuses it instead of guessing
+    odd = struct.pack(">hh", 1, 5) + cid(1) + struct.pack(">qq", 1, 1)
+    good = cctx([(cid(1), 2, 2, G)])
+    t = [Builder(SCTR).build([Partition(b"k", [Row((struct.pack(">i", 1),), [Cell(0, T0, v)])])]) for v in (odd, good)]
+    for g_, tb in enumerate(t): tb.generation = g_
+    with pytest.raises(native.UnsupportedError):
+        CompactionTask(t, CompactionController(NOW)).execute(GpuEngine(ctx))
+    r = CompactionTask(t[:1], CompactionController(NOW)).execute(GpuEngine(ctx))             # alone it passes through untouched, as in the reference
+    assert odd in decompress_output(r.outputs[0])

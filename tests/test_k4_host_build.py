@@ -81,7 +81,7 @@ def test_k4_source_mixed_types_and_token_range(k4lib):
     check(k4lib, tables, CompactionController(NOW, 10**9), column_index_size=1024)
     check(k4lib, tables, CompactionController(NOW, 10**9), column_index_size=1024, token_range=(-(1 << 62), 1 << 61))
 
-def _corruption_fuzz(lib_path, trials):
+def _corruption_fuzz(lib_path, trials, counters=False):
     """child process body (runs under LD_PRELOAD=libasan): damaged Data.db contents must end in 'corrupt data' / 'unsupported' or in a
     normal result — never outside the buffers (ASan aborts the process on any out-of-bounds access of the K4 source)"""
     L = C.CDLL(lib_path)
@@ -100,6 +100,9 @@ def _corruption_fuzz(lib_path, trials):
             parts.append(Partition(k, us, (1002, NOW) if rng.random() < 0.1 else None))
         return Builder(s, (1000 - t, 0, 0), column_index_size=512).build(parts)
     tables = [table(t) for t in range(3)]
+    if counters:                                     # counter tables: the damage lands in contexts, headers and shard ids (ctr_merge walks them)
+        from counter_tables import counter_tables
+        tables = counter_tables(5, ntables=3, nkeys=40, cis=512)
     for g, t in enumerate(tables): t.generation = g
     outcomes = {"ok": 0, "rejected": 0}
     for trial in range(trials):
@@ -132,7 +135,7 @@ def test_k4_source_survives_damaged_data_under_asan(k4lib, tmp_path):
                         "-Wno-attributes", "-Wno-unknown-pragmas", "-o", out, os.path.join(ROOT, "tests", "native", "k4_host.cc"), os.path.join(ROOT, "oracle", "codec.cc")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
-    code = "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.'); import test_k4_host_build as T; T._corruption_fuzz(%r, 150)" % out
+    code = "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.'); import test_k4_host_build as T; T._corruption_fuzz(%r, 150); T._corruption_fuzz(%r, 150, True)" % (out, out)
     c = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:abort_on_error=0"))
     assert c.returncode == 0 and "k4 corruption fuzz done" in c.stdout, (c.stdout + c.stderr)[-4000:]
@@ -157,3 +160,29 @@ def test_k4_source_complex_columns(k4lib, seed, big, cis):
     check(k4lib, tabs, CompactionController(NOW, 10 ** 9), column_index_size=cis)          # nothing purgeable
     check(k4lib, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)       # single source: pass-through + purge
     check(k4lib, tabs, CompactionController(NOW, 0), column_index_size=cis)
+
+@pytest.mark.parametrize("seed,big,cis,legacy", [(1, False, 65536, True), (2, False, 65536, False), (3, True, 2048, True)])
+def test_k4_source_counter_columns(k4lib, seed, big, cis, legacy):
+    """counter columns: contexts merged shard by shard (global / local / remote rules), tombstones and empty values, cells under a deletion left out
+    of the merge, the merged timestamp, wide partitions — the K4 source's K-way merge against the oracle's pairwise fold"""
+    from counter_tables import counter_tables
+    tabs = counter_tables(seed, ntables=5 if not big else 3, nkeys=60 if not big else 6, cis=cis, big=big, legacy=legacy)
+    check(k4lib, tabs, CompactionController(NOW, 864000), column_index_size=cis)
+    check(k4lib, tabs, CompactionController(NOW, 10 ** 9), column_index_size=cis)
+    check(k4lib, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)
+    check(k4lib, tabs, CompactionController(NOW, 0), column_index_size=cis)
+
+def test_k4_source_refuses_contexts_the_reference_does_not_write(k4lib):
+    """a header element that meets no shard / ids out of order: inside a merge the pairwise fold may hand such a context on unchanged where the K-way
+    merge would rebuild it — refused (unsupported), never guessed; alone (no merge) the cell passes through as in the reference"""
+    from counter_tables import SCTR, ctx as cctx, cid, G, T0
+    good = cctx([(cid(1), 2, 2, G)])
+    for odd in (struct.pack(">hh", 1, 5) + cid(1) + struct.pack(">qq", 1, 1),                         # element index 5, one shard
+                struct.pack(">h", 0) + cid(2) + struct.pack(">qq", 1, 1) + cid(1) + struct.pack(">qq", 1, 1),      # ids descending
+                struct.pack(">hh", -1, -32768) + cid(1) + struct.pack(">qq", 1, 1)):                  # "clear local shards" marker (negative count)
+        t = [Builder(SCTR).build([Partition(b"k", [Row((I32(1),), [Cell(0, T0, v)])])]) for v in (odd, good)]
+        for g_, tb in enumerate(t): tb.generation = g_
+        with pytest.raises(AssertionError, match="unsupported"):
+            host_k4(k4lib, CompactionTask(t, CompactionController(NOW)))
+        data, _, _ = host_k4(k4lib, CompactionTask(t[:1], CompactionController(NOW)))
+        assert odd in data

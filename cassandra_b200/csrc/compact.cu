@@ -45,7 +45,7 @@ enum { IB = 256 };                       // Index.db speculation block
 #ifndef B200C_K1_BATCH_DEFAULT
 #define B200C_K1_BATCH_DEFAULT true
 #endif
-enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220 };      // token-range pieces per call; slots of b200c_ctx::ev_pool
+enum { MAX_RANGES = 16, EV_RANGE = 200, EV_INDEX = 220, EV_K5 = 230 };      // token-range pieces per call; slots of b200c_ctx::ev_pool
 #define NONE64 (~0ull)
 
 enum { WS_U = 16, WS_CD, WS_CO, WS_IDX, WS_PARAMS, WS_BBASE, WS_ISTART, WS_ICNT, WS_IEND, WS_IHIT, WS_IBAD, WS_ISCAN,
@@ -940,7 +940,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     const bool lcs = m->max_sstable_bytes != 0;
     const int K = m->ninputs;
     // whatever way this call ends, nothing may still be copying from or into the caller's buffers
-    struct CopyGuard { b200c_ctx* c; ~CopyGuard() { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->copy_out); } } copy_guard{c};
+    struct CopyGuard { b200c_ctx* c; cudaStream_t main; ~CopyGuard() { c->stream = main; cudaStreamSynchronize(c->stream5); cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->copy_out); } } copy_guard{c, c->stream};
 
     // ---- Index.db slices: a token sub-range with Summary.db samples touches only its part of every Index.db ------------------------------
     bool have_summaries = true;
@@ -1236,6 +1236,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     // stage clock: marks on the main stream; the time between two marks is charged to the stage of the first
     struct Mark { int stage; cudaEvent_t ev; };
     std::vector<Mark> marks;
+    size_t k5_marks = 0;
     auto mark = [&](int stage) {
         size_t k = marks.size();
         if (k >= c->ev_marks.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_marks.push_back(e); }
@@ -1244,6 +1245,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     auto finish_marks = [&]() {
         for (int k = 0; k < 8; k++) c->stage_ms[k] = 0;
         for (size_t k = 0; k + 1 < marks.size(); k++) { float ms = 0; cudaEventElapsedTime(&ms, marks[k].ev, marks[k + 1].ev); if (marks[k].stage >= 0) c->stage_ms[marks[k].stage] += ms; }
+        for (size_t k = 0; k + 1 < k5_marks; k += 2) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev_k5[k], c->ev_k5[k + 1]) == cudaSuccess) c->stage_ms[5] += ms; }      // K5 on stream5: overlaps the next piece's stages
         c->nstages = 6;
     };
     c->nstages = 0;
@@ -1475,6 +1477,9 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     static const bool two_pass = getenv("B200C_K4_TWO_PASS") != nullptr;     // A/B switch: size pass + full emit pass instead of scratch + gather
     b200c_output& out0 = res->outputs[0];
     OutStream os;
+    // B200C_K5_OVERLAP=0: K5 on the main stream, piece after piece (A/B)
+    const bool k5_async = to_host_stream && nr > 1 && []() { const char* e = getenv("B200C_K5_OVERLAP"); return e ? atoi(e) != 0 : true; }();
+    int k5_last = -1;
     if (to_host_stream) B200C_TRY(out_stream_begin(os, c, m->out_compressor, m->out_chunk_len, m->out_max_compressed_len, out0.data, out0.data_cap, WS_CODEC));
     const uint64_t L = (uint64_t)m->out_chunk_len;
     uint64_t ubase_total = 0, ilen_total = 0, ncontrib_total = 0, nparts_total = 0;
@@ -1724,6 +1729,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
         B200C_TRY(check_cancel());
         mark(4);
         // the merged stream of this piece goes behind the unconsumed tail of the previous one; UOUT + tail_len is file offset ubase_total
+        if (k5_async && r >= 2) B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_pool[EV_K5 + 1 + (r & 1)], 0));      // K5 of piece r - 2 has read this buffer
         B200C_TRY(ws_typed(c, (r & 1) ? WS_UOUT2 : WS_UOUT, tail_len + ulen_out + 64, &UOUT));
         if (r) B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_pool[EV_INDEX], 0));          // IOUT of the previous piece has left
         B200C_TRY(ws_typed(c, WS_IOUT, ilen_out + 64, &IOUT));
@@ -1786,7 +1792,24 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
             const uint64_t avail = tail_len + ulen_out;
             uint64_t take = (r == nr - 1) ? avail : avail / L * L;
             const uint64_t slice = std::max<uint64_t>(L, std::max<uint64_t>(512ull << 20, bytes_read / 32) / L * L);      // pieces of ~512 MiB keep the read-back close behind
-            for (uint64_t off = 0; off < take; off += slice) B200C_TRY(out_stream_append(os, UOUT + off, std::min(slice, take - off)));
+            if (k5_async) {
+                // K5 of this piece on its own stream: it needs UOUT only, so K1..K3 of the next piece — and the host->device copies they wait for —
+                // run on top of it; K4 of piece r + 2 waits for it before it reuses this UOUT buffer
+                B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[EV_K5], st));
+                B200C_CUDA_TRY(c, cudaStreamWaitEvent(c->stream5, c->ev_pool[EV_K5], 0));
+                while (c->ev_k5.size() < k5_marks + 2) { cudaEvent_t e; cudaEventCreate(&e); c->ev_k5.push_back(e); }
+                cudaEventRecord(c->ev_k5[k5_marks], c->stream5);
+                c->stream = c->stream5;
+            }
+            int arc = B200C_OK;
+            for (uint64_t off = 0; off < take && arc == B200C_OK; off += slice) arc = out_stream_append(os, UOUT + off, std::min(slice, take - off));
+            if (k5_async) {
+                c->stream = st;
+                cudaEventRecord(c->ev_k5[k5_marks + 1], c->stream5); k5_marks += 2;
+                B200C_CUDA_TRY(c, cudaEventRecord(c->ev_pool[EV_K5 + 1 + (r & 1)], c->stream5));
+                k5_last = EV_K5 + 1 + (r & 1);
+            }
+            B200C_TRY(arc);
             tail_len = avail - take; tail_ptr = UOUT + take;
         }
         ubase_total += ulen_out; ilen_total += ilen_out;
@@ -1879,6 +1902,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     if (to_host_stream) {
         b200c_output& out = out0;
         uint64_t out_len = 0; uint32_t digest = 0; uint64_t* d_ooffs = nullptr;
+        if (k5_last >= 0) B200C_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_pool[k5_last], 0));      // every piece's K5 is done before the digest
         B200C_TRY(out_stream_finish(os, &out_len, &digest, &d_ooffs));
         const uint64_t nchunks_out = os.nchunks;
         RunStats rs; B200C_TRY(finish_common(rs));

@@ -289,6 +289,7 @@ b200c_ctx* b200c_create(int device, size_t workspace_bytes) {
     for (auto& e : c->ev_in) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& e : c->ev_pool) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->stream5, cudaStreamNonBlocking);
     DevTables* h = new DevTables(); build_tables(h);
     if (cudaMalloc(&c->d_tables, sizeof(DevTables)) != cudaSuccess) { delete h; delete c; return nullptr; }
     cudaMemcpy(c->d_tables, h, sizeof(DevTables), cudaMemcpyHostToDevice);
@@ -313,6 +314,8 @@ void b200c_destroy(b200c_ctx* c) {
     for (auto& e : c->ev_in) cudaEventDestroy(e);
     for (auto& e : c->ev_pool) cudaEventDestroy(e);
     for (auto& e : c->ev_marks) cudaEventDestroy(e);
+    if (c->stream5) cudaStreamDestroy(c->stream5);
+    for (auto e : c->ev_k5) cudaEventDestroy(e);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);

@@ -42,6 +42,8 @@ struct b200c_ctx {
     std::vector<cudaEvent_t> ev_marks;             // timed events of the stage clock (grown on demand)
     cudaEvent_t ev_pool[256] = {};                 // untimed events: OutStream pieces (2 each), token-range staging
     cudaStream_t copy_out = nullptr;               // device->host stream of the outputs (the other copy engine)
+    cudaStream_t stream5 = nullptr;                // K5 of streamed piece r runs here, under K1..K3 (and the copies they wait for) of piece r + 1
+    std::vector<cudaEvent_t> ev_k5;                // timed event pairs around each piece's K5 on stream5 (stage clock)
 };
 
 namespace b200c {

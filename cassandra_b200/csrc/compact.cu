@@ -1477,8 +1477,9 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
     static const bool two_pass = getenv("B200C_K4_TWO_PASS") != nullptr;     // A/B switch: size pass + full emit pass instead of scratch + gather
     b200c_output& out0 = res->outputs[0];
     OutStream os;
-    // B200C_K5_OVERLAP=0: K5 on the main stream, piece after piece (A/B)
-    const bool k5_async = to_host_stream && nr > 1 && []() { const char* e = getenv("B200C_K5_OVERLAP"); return e ? atoi(e) != 0 : true; }();
+    // B200C_K5_OVERLAP=1 (A/B, measured: no gain — 489.0 vs 490.6 ms per configs[1] step; K4 and K5 are both bound by shared memory and latency, the
+    // time K5 spends under the next piece's K1..K3 comes back as slower K2..K4): K5 of piece r on its own stream instead of the main one
+    const bool k5_async = to_host_stream && nr > 1 && []() { const char* e = getenv("B200C_K5_OVERLAP"); return e ? atoi(e) != 0 : false; }();
     int k5_last = -1;
     if (to_host_stream) B200C_TRY(out_stream_begin(os, c, m->out_compressor, m->out_chunk_len, m->out_max_compressed_len, out0.data, out0.data_cap, WS_CODEC));
     const uint64_t L = (uint64_t)m->out_chunk_len;

@@ -47,6 +47,7 @@ struct CParams {
     int32_t ncx, cx_first;
     int32_t ptype[MAXCX], pfix[MAXCX];
     uint64_t ctr_mask;             // bit c: regular simple column c is a counter column (cells merged shard by shard; tables with any use the CX kernels)
+    uint64_t sctr_mask;            // the same for the static columns
     int32_t partitioner;           // 0 Murmur3Partitioner, 1 ByteOrderedPartitioner (tok[] then holds the sign-flipped 8-byte key prefix)
     int64_t now, gc_before, purge_max_ts;
     // optional purge table (b200c_manifest.purge_range_*): ascending token bounds and the threshold that applies up to each of them
@@ -467,12 +468,12 @@ template <bool EMIT> __device__ __forceinline__ void pw_end_unf(PWriter<EMIT>& w
 
 struct CxVer { uint64_t cells, end; int64_t its, ildt; int32_t ittl; uint8_t flags, src; };      // one version of the row: where its columns start (behind the row header fields), its liveness (cells may say USE_ROW_TIMESTAMP / USE_ROW_TTL)
 struct CxCol { DT cd; uint32_t ncells; uint8_t pre, post; };                                     // merged + purged complex deletion, cells after the purge; column exists before / after the purge
-struct CxEmit { const CxVer* ver; int nver; bool as_is; DT active; const CxCol* col; const Purger* pg; };
+struct CxEmit { const CxVer* ver; int nver; bool as_is; DT active; const CxCol* col; const Purger* pg; bool stat = false; };      // stat: the static row (its columns are P.sfix / InDesc.smap)
 template <bool E> __device__ int cx_merge(const CParams& P, const Purger& pg, const CxVer* ver, int nver, bool as_is, DT active, int j,
                                          const Live info, CxCol* sum, Sink<E>* s, bool row_has_cd, const CxCol* known, StatAcc* acc);      // (multi-cell columns, below)
 // a merged counter cell has no bytes in an input stream: MCell.voff says so and carries what the header needs (counter columns, below)
 constexpr uint64_t CTR_SYNTH = 1ull << 63, CTR_LEGACY = 1ull << 62;
-template <bool E> __device__ int ctr_merge(const CParams& P, const CxVer* ver, int nver, DT active, int oc, MCell* sum, Sink<E>* s, int nhdr);
+template <bool E> __device__ int ctr_merge(const CParams& P, const CxVer* ver, int nver, DT active, int oc, MCell* sum, Sink<E>* s, int nhdr, bool stat = false);
 // row body: UnfilteredSerializer.serializeRowBody :213-269 + Cell.Serializer.serialize S/db/rows/Cell.java:268-305
 template <bool E, bool CX = false> __device__ __noinline__ uint64_t put_row_body(Sink<E> s, const CParams& P, int flags, Live info, DT del, const MCell* cells, int ncols, const int32_t* vfix, const CxEmit* cx = nullptr) {
     if (flags & 0x04) s.vint((uint64_t)info.ts - (uint64_t)P.o_min_ts);
@@ -485,7 +486,7 @@ template <bool E, bool CX = false> __device__ __noinline__ uint64_t put_row_body
     }
     for (int c = 0; c < ncols; c++) {
         const MCell& m = cells[c]; if (!m.present) continue;
-        if constexpr (CX) if (c >= P.cx_first) {          // writeComplexColumn :271-280 (cells[c].present = the column exists)
+        if constexpr (CX) if (!cx->stat && c >= P.cx_first) {          // writeComplexColumn :271-280 (cells[c].present = the column exists)
             cx_merge<E>(P, *cx->pg, cx->ver, cx->nver, cx->as_is, cx->active, c - P.cx_first, info, nullptr, &s, (flags & 0x40) != 0, &cx->col[c - P.cx_first], nullptr);
             continue;
         }
@@ -499,7 +500,7 @@ template <bool E, bool CX = false> __device__ __noinline__ uint64_t put_row_body
         if (expiring && !use_ttl) s.vint((uint64_t)(int64_t)(m.ttl - P.o_min_ttl));
         if constexpr (CX) if (m.voff & CTR_SYNTH) {      // the merged context is written from the versions' contexts (ctr_merge)
             s.vint((uint64_t)m.vlen);
-            ctr_merge<E>(P, cx->ver, cx->nver, cx->active, c, nullptr, &s, (int)(m.voff & 0xFFFF));
+            ctr_merge<E>(P, cx->ver, cx->nver, cx->active, c, nullptr, &s, (int)(m.voff & 0xFFFF), cx->stat);
             continue;
         }
         if (has_value) { if (vfix[c] <= 0) s.vint((uint64_t)m.vlen); s.copy(P.U + m.voff, (uint32_t)m.vlen); }
@@ -716,16 +717,18 @@ template <bool E> __device__ __noinline__ int cx_merge(const CParams& P, const P
 // for contexts in the form the reference itself writes (every header element meets its shard, ids strictly increasing, n >= 0): anything
 // else in a merge is refused (PERR_UNSUPPORTED) rather than guessed at. Cells the active deletion covers are skipped BEFORE the merge
 // (Row.java:838-849) — the merged cell carries the largest timestamp, so filtering afterwards would not be the same.
-__device__ __noinline__ bool ctr_cell(const CParams& P, const CxVer& v, int oc, PCell* out, int* err) {      // the cell of simple column oc in version v
+__device__ __noinline__ bool ctr_cell(const CParams& P, const CxVer& v, int oc, PCell* out, int* err, bool stat) {      // the cell of simple (or static) column oc in version v
     const InDesc& in = P.in[v.src];
+    const int nin = stat ? in.nstat : in.ncols, lim = stat ? P.nstat : P.cx_first;
+    const int32_t* const map = stat ? in.smap : in.colmap; const int32_t* const vfix = stat ? P.sfix : P.vfix;
     Rd r{P.U, v.cells, v.end, 0};
     uint64_t missing = 0;
     if (!(v.flags & 0x20)) missing = r.vint();
-    for (int i = 0; i < in.ncols && !r.err; i++) {
+    for (int i = 0; i < nin && !r.err; i++) {
         if ((missing >> i) & 1) continue;
-        const int oci = in.colmap[i];
-        if (oci >= P.cx_first) break;
-        cx_read_cell(in, r, v, P.vfix[oci], -1, out);
+        const int oci = map[i];
+        if (oci >= lim) break;
+        cx_read_cell(in, r, v, vfix[oci], -1, out);
         if (r.err) break;
         if (oci == oc) return true;
     }
@@ -743,7 +746,7 @@ __device__ __noinline__ bool ctr_has_legacy(const uint8_t* c, int len) {
 }
 // sum != nullptr: what column oc of the merged row is (MCell; a merged context: voff = CTR_SYNTH | CTR_LEGACY? | header elements, vlen = its length).
 // s != nullptr: write the merged context (the summary said CTR_SYNTH and how many header elements, nhdr). Returns an error code.
-template <bool E> __device__ __noinline__ int ctr_merge(const CParams& P, const CxVer* ver, int nver, DT active, int oc, MCell* sum, Sink<E>* s, int nhdr) {
+template <bool E> __device__ __noinline__ int ctr_merge(const CParams& P, const CxVer* ver, int nver, DT active, int oc, MCell* sum, Sink<E>* s, int nhdr, bool stat) {
     uint64_t base[MAXK]; uint16_t len[MAXK], hl[MAXK], bo[MAXK], ho[MAXK];
     int err = 0, ncand = 0, first = -1;
     MCell tomb, empty, one; tomb.present = empty.present = false; one.present = false;
@@ -751,7 +754,7 @@ template <bool E> __device__ __noinline__ int ctr_merge(const CParams& P, const 
     for (int v = 0; v < nver; v++) {
         base[v] = ~0ull; len[v] = hl[v] = bo[v] = ho[v] = 0;
         PCell c;
-        if (!ctr_cell(P, ver[v], oc, &c, &err)) { if (err) return err; continue; }
+        if (!ctr_cell(P, ver[v], oc, &c, &err, stat)) { if (err) return err; continue; }
         if (dt_deletes(active, c.m.ts)) continue;
         ncand++; if (first < 0) { first = v; one = c.m; }
         if (c.m.ldt != I64_MAX && c.m.ttl == 0) { if (!tomb.present || !reconcile_keep_left(P, tomb, c.m)) tomb = c.m; continue; }     // tombstones among themselves: resolveRegular
@@ -832,7 +835,7 @@ template <bool E> __device__ __noinline__ int ctr_merge(const CParams& P, const 
 // Tables with static columns carry a static row in every partition, the empty one included (SortedTableWriter.append :144-146,
 // SortedTablePartitionWriter.addStaticRow :117-126, UnfilteredSerializer.serializeStaticRow :144-149): flags | EXTENSION, extended flags
 // IS_STATIC, no clustering, previous size 0. scells == nullptr: the (merged, purged) static row is empty.
-template <bool EMIT> __device__ __noinline__ void write_static(PWriter<EMIT>& w, const CParams& P, const Live info, const DT del, const MCell* scells, int present) {
+template <bool EMIT, bool CX = false> __device__ __noinline__ void write_static(PWriter<EMIT>& w, const CParams& P, const Live info, const DT del, const MCell* scells, int present, const CxEmit* cx = nullptr) {
     if (!scells) {                                   // no liveness, no deletion, every column missing
         const uint64_t mask = (1ull << P.nstat) - 1;
         w.d.u8(0x80); w.d.u8(0x01); w.d.vint(vint_size(mask) + 1); w.d.vint(0); w.d.vint(mask);
@@ -845,25 +848,31 @@ template <bool EMIT> __device__ __noinline__ void write_static(PWriter<EMIT>& w,
     if (present == P.nstat) flags |= 0x20;
     const uint64_t p0 = w.d.pos;                     // (size field guessed at one byte, see write_row)
     Sink<EMIT> b = w.d; b.pos = p0 + 2 + 1 + 1;
-    uint64_t end = put_row_body(b, P, flags, info, del, scells, P.nstat, P.sfix);
+    uint64_t end = put_row_body<EMIT, CX>(b, P, flags, info, del, scells, P.nstat, P.sfix, cx);
     const uint64_t body = end - b.pos;
     const int vs = vint_size(body + 1);
-    if (vs != 1) { b.pos = p0 + 2 + vs + 1; end = put_row_body(b, P, flags, info, del, scells, P.nstat, P.sfix); }
+    if (vs != 1) { b.pos = p0 + 2 + vs + 1; end = put_row_body<EMIT, CX>(b, P, flags, info, del, scells, P.nstat, P.sfix, cx); }
     w.d.u8(flags); w.d.u8(0x01);
     w.d.vint(body + 1); w.d.vint(0);
     w.d.pos = end;
     if (w.acc) {                                     // SortedTableWriter.addStaticRow :188-197: Rows.collectStats unless the row is empty
         w.acc->live(info); w.acc->dt(del);
         for (int c = 0; c < P.nstat; c++) if (scells[c].present) w.acc->cell(scells[c]);
+        if constexpr (CX) for (uint64_t bits = P.sctr_mask; bits; bits &= bits - 1) {                     // Cells.collectStats :44-50
+            const MCell& m = scells[__ffsll((long long)bits) - 1];
+            if (!m.present || (m.ldt != I64_MAX && m.ttl == 0)) continue;
+            if ((m.voff & CTR_SYNTH) ? (m.voff & CTR_LEGACY) != 0 : (m.vlen >= 2 && ctr_has_legacy(P.U + m.voff, m.vlen))) w.acc->seen |= 8;
+        }
         w.acc->cols += (unsigned long long)present; w.acc->rows++;
     }
 }
-template <bool EMIT> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, const CParams& P, uint64_t key_off, uint32_t klen, const DT& out_pdel,
-                                                              const MCell* scells = nullptr, const Live& sinfo = Live{I64_MIN, I64_MAX, 0}, const DT& sdel = DT{I64_MIN, I64_MAX}, int spresent = 0) {
+template <bool EMIT, bool CX = false> __device__ __forceinline__ void pw_start(PWriter<EMIT>& w, const CParams& P, uint64_t key_off, uint32_t klen, const DT& out_pdel,
+                                                              const MCell* scells = nullptr, const Live& sinfo = Live{I64_MIN, I64_MAX, 0}, const DT& sdel = DT{I64_MIN, I64_MAX}, int spresent = 0,
+                                                              const CxEmit* scx = nullptr) {
     w.d.be16(klen); w.d.copy(P.U + key_off, klen); write_partition_dt(w.d, out_pdel);      // SortedTablePartitionWriter.start :97-115
     w.started = true;
     if (w.acc) { w.acc->part_cells = 0; if (!dt_is_live(out_pdel)) { w.acc->pdel = 1; w.acc->dt(out_pdel); } }     // updatePartitionDeletion
-    if (P.nstat > 0) write_static(w, P, sinfo, sdel, scells, spresent);
+    if (P.nstat > 0) { if constexpr (CX) { if (scx) write_static<EMIT, true>(w, P, sinfo, sdel, scells, spresent, scx); else write_static(w, P, sinfo, sdel, scells, spresent); } else write_static(w, P, sinfo, sdel, scells, spresent); }
     w.header_len = w.d.pos - w.start;
     // final emit with an Index.db slot: the IndexInfos start behind the entry's fixed part, whose size depends on headerLength
     if (EMIT && w.ix_entry) w.ix.base = w.ix_entry + w.ix_fixed + vint_size(w.header_len);
@@ -984,6 +993,29 @@ template <class CUR> __device__ __noinline__ int merge_static(const CParams& P, 
     return (live_is_empty(info) && dt_is_live(del) && n == 0) ? -1 : n;
 }
 
+// static counter columns of the merged static row: Cells.resolveCounter over the versions' cells (ctr_merge) in place of the winner fold_cells picked.
+// Fills ver[] (the versions of the static row) and the deletion in force, both needed again when the row is written.
+template <class CUR> __device__ __noinline__ int static_counters(const CParams& P, CUR* cur, uint64_t sgrp, uint32_t m, DT pdel, MCell* merged, CxVer* ver, int* nver, DT* active_out) {
+    const bool as_is = m == 1 && dt_is_live(pdel);
+    DT del = dt_live(); int nv = 0;
+    for (uint64_t bits = sgrp; bits; bits &= bits - 1) {
+        const int v = __ffsll((long long)bits) - 1;
+        Live vi; DT vd; Rd r = row_header(P, cur[v], vi, vd); if (r.err) return r.err;
+        if (dt_supersedes(vd, del)) del = vd;
+        ver[nv++] = CxVer{r.p, (uint64_t)cur[v].next, vi.ts, vi.ldt, vi.ttl, (uint8_t)cur[v].flags, (uint8_t)cur[v].src};
+    }
+    DT active = pdel;
+    if (!as_is && dt_supersedes(del, active)) active = del;
+    *nver = nv; *active_out = active;
+    if (as_is || nv < 2) return 0;
+    for (uint64_t bits = P.sctr_mask; bits; bits &= bits - 1) {
+        const int oc = __ffsll((long long)bits) - 1;
+        const int e = ctr_merge<false>(P, ver, nv, active, oc, &merged[oc], (Sink<false>*)nullptr, 0, true);
+        if (e) return e;
+    }
+    return 0;
+}
+
 // The whole life of one output partition. contrib[c0 .. c0+m) are its input partitions in source order.
 // cur[0..m) / open_dt[0..m): per-source cursor state owned by this thread (the caller places it in shared memory);
 // merged[0..ncols): scratch for the merged row.
@@ -1038,7 +1070,7 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
     DT pdel = dt_live();
     uint64_t key_off = 0; uint32_t klen = 0;
     uint64_t sgrp = 0;                                // contributors with a non-empty static row
-    if (m > MAXK || (!CX && (P.ncx || P.ctr_mask))) { err = PERR_UNSUPPORTED; return; }
+    if (m > MAXK || (!CX && (P.ncx || P.ctr_mask || P.sctr_mask))) { err = PERR_UNSUPPORTED; return; }
     // prologue in three sweeps so that the m dependent chains (contrib -> upos -> Data bytes) overlap instead of serialising:
     // (1) resolve the input partitions, (2) prefetch their first lines, (3) parse the partition headers
     for (uint32_t v = 0; v < mu; v++) {
@@ -1099,7 +1131,18 @@ __device__ void process_partition(const CParams& P, const XL& xl, const uint64_t
         Live sinfo; DT sdel;
         int n = merge_static(P, cur, sgrp, m, pdel, merged, &sinfo, &sdel, &err);
         if (err) return;
-        if (n >= 0) { n = purge_row(pg, sinfo, sdel, merged, P.nstat); if (n >= 0) pw_start(w, P, key_off, klen, out_pdel, merged, sinfo, sdel, n); }
+        bool done = false;
+        if constexpr (CX) if (P.sctr_mask && n >= 0) {          // static counter columns: merged contexts, written from the versions (put_row_body<.., true>)
+            CxVer sv[MCAP]; int snv = 0; DT sactive;
+            { const int e = static_counters(P, cur, sgrp, m, pdel, merged, sv, &snv, &sactive); if (e) { err = e; return; } }
+            n = 0; for (int k = 0; k < P.nstat; k++) n += merged[k].present;
+            if (!(live_is_empty(sinfo) && dt_is_live(sdel) && n == 0)) {
+                n = purge_row(pg, sinfo, sdel, merged, P.nstat);
+                if (n >= 0) { CxEmit scx{sv, snv, false, sactive, nullptr, &pg, true}; pw_start<EMIT, true>(w, P, key_off, klen, out_pdel, merged, sinfo, sdel, n, &scx); }
+            }
+            done = true;
+        }
+        if (!done && n >= 0) { n = purge_row(pg, sinfo, sdel, merged, P.nstat); if (n >= 0) pw_start(w, P, key_off, klen, out_pdel, merged, sinfo, sdel, n); }
     }
     if (P.nstat > 0) for (uint32_t v = 0; v < m; v++) if (P.in[cur[v].src].nstat > 0) cur[v].pos = cur[v].next;      // step over the static rows
 

@@ -134,7 +134,7 @@ __device__ void process_partition_tile(const cg::thread_block_tile<G>& tile, con
                                        MCell* s_cells, PartOut& out, PartStats& st, int& err, StatAcc* acc = nullptr) {
     const int lane = tile.thread_rank();
     const bool multi = m > 1;
-    if (P.ncx || P.ctr_mask) { err = PERR_UNSUPPORTED; return; }        // multi-cell columns: the thread kernels only (compact.cu routes every fan-in there)
+    if (P.ncx || P.ctr_mask || P.sctr_mask) { err = PERR_UNSUPPORTED; return; }        // multi-cell columns: the thread kernels only (compact.cu routes every fan-in there)
     Purger pg{P.now, P.gc_before, purge_threshold(P, contrib, c0, pbase, part_tok)};
     Cur cur[S]; bool have[S]; DT my_pd[S];
     int lerr = 0;

@@ -126,7 +126,7 @@ class CompactionTask:
         if sum(1 for _, t in out_cols if sst.is_complex(t)) > native.MAX_COMPLEX_COLUMNS: raise native.UnsupportedError(native.EUNSUPPORTED, "more than %d multi-cell columns" % native.MAX_COMPLEX_COLUMNS)
         if any(sst.is_complex(t) for _, t in out_static): raise native.UnsupportedError(native.EUNSUPPORTED, "multi-cell static column")
         m.nstatic_columns = len(out_static)
-        for k, (_, t) in enumerate(out_static): m.static_columns[k].type, m.static_columns[k].fixed_len = sst.type_class(t)
+        for k, (_, t) in enumerate(out_static): m.static_columns[k].type, m.static_columns[k].fixed_len = sst.column_class(t)      # (simple columns; a static counter: TYPE_COUNTER)
         m.out_stats.min_timestamp, m.out_stats.min_local_deletion_time, m.out_stats.min_ttl = merged_encoding_stats(ins)
         m.out_compressor = self.compression.compressor_id; m.out_chunk_len = self.compression.chunk_length
         m.out_max_compressed_len = self.compression.max_compressed_length; m.column_index_size = self.column_index_size

@@ -650,7 +650,7 @@ static bool merge_rows(std::vector<Unf*>& versions, DT active, Unf& out, const S
     for (int col = 0; col < 64; col++) {
         if (!((cols_present >> col) & 1)) continue;
         const bool complex = sc && !stat && col_complex(sc->cols[col]);
-        if (!complex && sc && !stat && sc->cols[col].type == B200C_TYPE_COUNTER) {
+        if (!complex && sc && (stat ? sc->stat[col] : sc->cols[col]).type == B200C_TYPE_COUNTER) {
             bool have = false; CellV merged{};
             for (size_t i = 0; i < versions.size(); i++) {
                 if (cur[i] < versions[i]->cells.size() && versions[i]->cells[cur[i]].col == col) {
@@ -783,7 +783,7 @@ struct Meta {
     void update(const CellV& c) { cur_cells++; total_cells++; ts(c.ts); ttl(c.ttl); ldt(c.ldt); if (!c.is_live(now)) total_tombstones++; } // :220-228
     void partition_deletion(const DT& d) { if (!d.live()) has_partition_deletions = true; update(d); }                                    // :230-235
     bool has_legacy_counter_shards = false;
-    void row(const Unf& u, const b200c_column* types = nullptr) {           // Rows.collectStats S/db/rows/Rows.java:102-113 (types: the regular columns' — null for a static row)
+    void row(const Unf& u, const b200c_column* types = nullptr) {           // Rows.collectStats S/db/rows/Rows.java:102-113 (types: of the row's columns, regular or static)
         update(u.info); update(u.del);
         if (types) for (const CellV& c : u.cells)                             // Cells.collectStats S/db/rows/Cells.java:44-50
             if (types[c.col].type == B200C_TYPE_COUNTER && !c.tombstone() && c.vlen >= 2 && ctr::has_legacy_shards(c.val, c.vlen)) has_legacy_counter_shards = true;
@@ -1012,7 +1012,7 @@ struct Writer {
             write_row_body(body, u, flags, sc.nstat, sc.stat);
             tmp.vint(body.size() + vint_size(0)); tmp.vint(0);
             write(tmp.b.data(), tmp.b.size()); write(body.b.data(), body.b.size());
-            if (stat) outs.back().meta.row(u);                                // SortedTableWriter.addStaticRow :188-197: collectStats unless empty
+            if (stat) outs.back().meta.row(u, sc.stat);                       // SortedTableWriter.addStaticRow :188-197: collectStats unless empty
         }
         header_len = position - part_start;
         prev_row_start = 0; have_first = false; open_marker = DT(); index_infos.clear(); block_start = 0;
@@ -1097,7 +1097,7 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
         if (col_complex(sc.cols[k]) && (pt < 0 || pt > B200C_TYPE_TIMEUUID)) return B200C_EINVAL;
     }
     if (sc.ncomplex > B200C_MAX_COMPLEX_COLUMNS) return B200C_EUNSUPPORTED;
-    for (int k = 0; k < m->nstatic_columns; k++) if (col_complex(sc.stat[k]) || sc.stat[k].type == B200C_TYPE_COUNTER) return B200C_EUNSUPPORTED;
+    for (int k = 0; k < m->nstatic_columns; k++) if (col_complex(sc.stat[k])) return B200C_EUNSUPPORTED;
     for (int k = 0; k < m->ncolumns; k++) if (col_complex(sc.cols[k]) && col_value_type(sc.cols[k]).type == B200C_TYPE_COUNTER) return B200C_EINVAL;      // (no collections of counters)
     g_partitioner = m->partitioner;
     std::vector<Source> srcs(m->ninputs);
@@ -1144,7 +1144,7 @@ int compact_impl(const b200c_manifest* m, b200c_result* res, RangeOut* ro) {
         Unf stat_out; bool have_static = false;
         if (sc.nstat > 0) {
             std::vector<Unf*> vs; for (int i : group) if (srcs[i].has_stat) vs.push_back(&srcs[i].stat);
-            if (!vs.empty()) have_static = merge_rows(vs, pdel, stat_out) && purge_row(stat_out, pg);
+            if (!vs.empty()) have_static = merge_rows(vs, pdel, stat_out, &sc, true) && purge_row(stat_out, pg);
         }
         auto emit = [&](Unf& u) {
             total_source_rows++;                               // Purger.updateProgress :366-371

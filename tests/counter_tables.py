@@ -20,8 +20,12 @@ def random_context(rng, ids, legacy=True):
     return ctx([(cid(i), rng.choice([1, 2, 2, 3, 1 << 40, -5]), rng.choice([0, 1, 7, -3, 1 << 50, (1 << 63) - 1]), rng.choice(kinds))
                 for i in sorted(rng.sample(ids, rng.randint(0, len(ids))))])
 
-def counter_tables(seed, ntables=4, nkeys=60, cis=65536, big=False, legacy=True):
+SCTR_STATIC = Schema(["Int32Type"], [("a", "CounterColumnType"), ("b", "CounterColumnType")], static_columns=[("s", "CounterColumnType"), ("t", "CounterColumnType")])
+
+def counter_tables(seed, ntables=4, nkeys=60, cis=65536, big=False, legacy=True, static=False):
+    """static: the table also has two static counter columns (a static row per partition, merged with the partition deletion in force)"""
     rng = random.Random(seed)
+    schema = SCTR_STATIC if static else SCTR
     keys = sorted({b"key%05d" % rng.randint(0, 10 ** 5) for _ in range(nkeys)})
     ids = list(range(1, 9 if not big else 40))
     tables = []
@@ -41,7 +45,16 @@ def counter_tables(seed, ntables=4, nkeys=60, cis=65536, big=False, legacy=True)
                 dele = (T0 + rng.randint(0, 60), NOW - rng.choice([5, 30 * 86400])) if rng.random() < 0.12 else None
                 if cells or dele: rows.append(Row((I32(ck),), cells, deletion=dele))
             pdel = (T0 + rng.randint(0, 40), NOW - rng.choice([5, 30 * 86400])) if rng.random() < 0.08 else None
-            if rows or pdel: parts.append(Partition(key, rows, pdel))
-        tables.append(Builder(SCTR, column_index_size=cis).build(parts))
+            st = None
+            if static and rng.random() < 0.7:
+                scells = []
+                for col in (0, 1):
+                    x = rng.random(); ts = T0 + rng.randint(0, 60)
+                    if x < 0.25: continue
+                    if x < 0.33: scells.append(Cell.tombstone(col, ts, NOW - rng.choice([5, 5, 30 * 86400])))
+                    else: scells.append(Cell(col, ts, random_context(rng, ids, legacy)))
+                if scells: st = Row((), scells)
+            if rows or pdel or st: parts.append(Partition(key, rows, pdel, static=st))
+        tables.append(Builder(schema, column_index_size=cis).build(parts))
     for g, tb in enumerate(tables): tb.generation = g
     return tables

@@ -104,6 +104,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
         if ((m->columns[k].type & 0xFF) == B200C_TYPE_COUNTER) P.ctr_mask |= 1ull << k;
     }
     if (!P.ncx) P.cx_first = m->ncolumns;
+    for (int k = 0; k < m->nstatic_columns; k++) if ((m->static_columns[k].type & 0xFF) == B200C_TYPE_COUNTER) P.sctr_mask |= 1ull << k;
     P.nstat = m->nstatic_columns; P.mcols = std::max(m->ncolumns, m->nstatic_columns);
     for (int k = 0; k < m->nstatic_columns; k++) P.sfix[k] = m->static_columns[k].fixed_len;
     P.o_min_ts = m->out_stats.min_timestamp; P.o_min_ldt = m->out_stats.min_local_deletion_time; P.o_min_ttl = m->out_stats.min_ttl;
@@ -121,7 +122,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     std::vector<PartOut> po(nparts); PartStats st{0, 0};
     for (uint64_t j = 0; j < nparts; j++) {
         int e = 0; PartOut out{0, 0, 0, 0, 0};
-        if (P.ncx || P.ctr_mask) process_partition<false, Cur32, XlateGlobal, MAXK, true>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
+        if (P.ncx || P.ctr_mask || P.sctr_mask) process_partition<false, Cur32, XlateGlobal, MAXK, true>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
                                  nullptr, ~0ull, 0, nullptr, 0, 0, 0, cur.data(), open_dt.data(), merged.data(), out, st, e);      // (tables with multi-cell columns: the CX instantiation, as compact.cu launches it)
         else process_partition<false>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
                                  nullptr, ~0ull, 0, nullptr, 0, 0, 0, cur.data(), open_dt.data(), merged.data(), out, st, e);
@@ -140,7 +141,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     for (uint64_t j = 0; j < nparts; j++) {
         if (!po[j].dsize) continue;
         int e = 0; PartOut out{0, 0, 0, 0, 0};
-        if (P.ncx || P.ctr_mask) process_partition<true, Cur32, XlateGlobal, MAXK, true>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
+        if (P.ncx || P.ctr_mask || P.sctr_mask) process_partition<true, Cur32, XlateGlobal, MAXK, true>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
                                 uout + dpos[j], ~0ull, dpos[j], iout + ipos[j], po[j].nblk, po[j].ipay, 0, cur.data(), open_dt.data(), merged.data(), out, st2, e);
         else process_partition<true>(P, XlateGlobal(), contrib.data(), op_first[j], (uint32_t)(op_first[j + 1] - op_first[j]), upos.data(), pbase.data(), kp.data(), klen.data(), tok.data(),
                                 uout + dpos[j], ~0ull, dpos[j], iout + ipos[j], po[j].nblk, po[j].ipay, 0, cur.data(), open_dt.data(), merged.data(), out, st2, e);
@@ -149,7 +150,7 @@ extern "C" int k4host_compact(const b200c_manifest* m, uint8_t* uout, uint64_t u
     }
     // ---- the staged path (k_partition_staged): token-contiguous tiles of output partitions whose input byte ranges (one contiguous
     //      range per source) are copied into a small buffer, P.U pointing at the copy, 32-byte cursors with 32/16-bit offsets -----------
-    if (!P.ncx && !P.ctr_mask) {                               // (tables with multi-cell or counter columns run the thread kernels only)
+    if (!P.ncx && !P.ctr_mask && !P.sctr_mask) {                               // (tables with multi-cell or counter columns run the thread kernels only)
         std::vector<uint8_t> u2(dpos[nparts] + 64, 0), i2(ipos[nparts] + 64, 0);
         std::vector<CurS> curs(MAXK); PartStats st3{0, 0};
         const uint64_t TILE_BYTES = 40000;

@@ -46,7 +46,7 @@ class Schema:
         self.vfixed = [column_class(t)[1] & 0xFFFF for _, t in self.columns]
         self.pfixed = [column_class(t)[1] >> 16 for _, t in self.columns]
         self.complex = [is_complex(t) for _, t in self.columns]
-        self.sfixed = [type_class(t)[1] for _, t in self.static_columns]
+        self.sfixed = [column_class(t)[1] & 0xFFFF for _, t in self.static_columns]
     def col_index(self, name):
         name = name if isinstance(name, bytes) else name.encode()
         return [n for n, _ in self.columns].index(name)

@@ -680,12 +680,13 @@ def test_complex_columns_streamed_and_sharded(ctx, monkeypatch):
     assert g.data == want.data and g.index == want.index and g.digest == want.digest
 
 # ---- counter columns ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("seed,ntab,big,cis,legacy", [(1, 5, False, 65536, True), (2, 20, False, 65536, False), (3, 3, True, 2048, True), (4, 40, False, 65536, True)])
-def test_counter_columns_match_oracle(ctx, seed, ntab, big, cis, legacy):
+@pytest.mark.parametrize("seed,ntab,big,cis,legacy,static", [(1, 5, False, 65536, True, False), (2, 20, False, 65536, False, False), (3, 3, True, 2048, True, False),
+                                                             (4, 40, False, 65536, True, False), (5, 6, False, 65536, True, True), (6, 3, True, 2048, True, True), (7, 24, False, 65536, True, True)])
+def test_counter_columns_match_oracle(ctx, seed, ntab, big, cis, legacy, static):
     """counter contexts merged shard by shard (the K-way merge of partition.cuh against the oracle's pairwise fold): global / local / remote rules,
     tombstones and empty values, cells under a deletion left out of the merge, the merged timestamp, hasLegacyCounterShards; fan-ins up to 40"""
     from counter_tables import counter_tables
-    tabs = counter_tables(seed, ntables=ntab, nkeys=60 if not big else 6, cis=cis, big=big, legacy=legacy)
+    tabs = counter_tables(seed, ntables=ntab, nkeys=60 if not big else 6, cis=cis, big=big, legacy=legacy, static=static)      # static: two static counter columns as well
     both(ctx, tabs, CompactionController(NOW, 864000), column_index_size=cis, with_metadata=True)
     both(ctx, tabs, CompactionController(NOW, 10 ** 9), column_index_size=cis)
     both(ctx, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis, with_metadata=True)

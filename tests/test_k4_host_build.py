@@ -161,12 +161,13 @@ def test_k4_source_complex_columns(k4lib, seed, big, cis):
     check(k4lib, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)       # single source: pass-through + purge
     check(k4lib, tabs, CompactionController(NOW, 0), column_index_size=cis)
 
-@pytest.mark.parametrize("seed,big,cis,legacy", [(1, False, 65536, True), (2, False, 65536, False), (3, True, 2048, True)])
-def test_k4_source_counter_columns(k4lib, seed, big, cis, legacy):
+@pytest.mark.parametrize("seed,big,cis,legacy,static", [(1, False, 65536, True, False), (2, False, 65536, False, False), (3, True, 2048, True, False),
+                                                        (4, False, 65536, True, True), (5, True, 2048, True, True)])
+def test_k4_source_counter_columns(k4lib, seed, big, cis, legacy, static):
     """counter columns: contexts merged shard by shard (global / local / remote rules), tombstones and empty values, cells under a deletion left out
     of the merge, the merged timestamp, wide partitions — the K4 source's K-way merge against the oracle's pairwise fold"""
     from counter_tables import counter_tables
-    tabs = counter_tables(seed, ntables=5 if not big else 3, nkeys=60 if not big else 6, cis=cis, big=big, legacy=legacy)
+    tabs = counter_tables(seed, ntables=5 if not big else 3, nkeys=60 if not big else 6, cis=cis, big=big, legacy=legacy, static=static)
     check(k4lib, tabs, CompactionController(NOW, 864000), column_index_size=cis)
     check(k4lib, tabs, CompactionController(NOW, 10 ** 9), column_index_size=cis)
     check(k4lib, tabs[:1], CompactionController(NOW, 864000), column_index_size=cis)

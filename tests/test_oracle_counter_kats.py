@@ -276,3 +276,71 @@ def test_golden_counter_table_merged_with_itself(golden_dir, name):
     r = CompactionTask([a, b, c], CompactionController(NOW), column_index_size=4096).execute(O.OracleEngine())
     assert r.outputs[0].components()["Data.db"] == open(base + "Data.db", "rb").read()
     assert r.outputs[0].components()["Index.db"] == open(base + "Index.db", "rb").read()
+
+# ---- static counter columns ---------------------------------------------------------------------------------------------------------------
+SCS = Schema(["Int32Type"], [("a", "CounterColumnType")], static_columns=[("s", "CounterColumnType"), ("t", "CounterColumnType")])
+
+def model_compact_static(schema, tables_parts, now=NOW, gc_grace=864000):
+    """model_compact + the static row: merged eagerly with the partition deletion as the active deletion, whatever the fan-in
+    (mergeStaticRows S/db/rows/UnfilteredRowIterators.java:484-505), then purged like a row"""
+    keys = {}
+    for parts in tables_parts:
+        for p in parts: keys.setdefault(p.key, []).append(p)
+    out = []
+    for key in sorted(keys, key=lambda k: (O.token(k), k)):
+        ps = keys[key]; pdel = LIVE_DT
+        for p in ps:
+            if p.deletion is not None and not dt_sup(pdel, p.deletion): pdel = p.deletion
+        svs = [p.static for p in ps if p.static is not None]
+        st = None
+        if svs:
+            st = model_merge_row(svs, pdel, len(schema.static_columns)) if (len(ps) > 1 or pdel != LIVE_DT) else svs[0]
+            if st is not None: st = model_purge(copy.deepcopy(st), now, now - gc_grace)
+        cks = sorted({u.ck for p in ps for u in p.unfiltereds}, key=lambda ck: struct.unpack(">i", ck[0])[0])
+        rows = []
+        for ck in cks:
+            vs = [u for p in ps for u in p.unfiltereds if u.ck == ck]
+            m = model_merge_row(vs, pdel, len(schema.columns)) if len(ps) > 1 else vs[0]
+            if m is not None: m = model_purge(copy.deepcopy(m), now, now - gc_grace)
+            if m is not None: rows.append(m)
+        out_pdel = pdel if pdel != LIVE_DT and not (pdel[1] < now - gc_grace) else None
+        if rows or out_pdel is not None or st is not None: out.append(Partition(key, rows, out_pdel, static=st))
+    return out
+
+def check_static(tables_parts, now=NOW, gc_grace=864000):
+    tabs = [Builder(SCS).build(parts) for parts in tables_parts]
+    got = oracle_compact(tabs, now, gc_grace)
+    want_parts = model_compact_static(SCS, tables_parts, now, gc_grace)
+    want = raw_of(Builder(SCS, merged_encoding_stats(tabs)).build(want_parts)) if want_parts else b""
+    assert got == want
+    return got
+
+def test_static_counter_cells_merge_like_regular_ones():
+    c1 = ctx([(cid(1), 3, 30, G)]); c2 = ctx([(cid(2), 1, 1, G)]); c3 = ctx([(cid(1), 9, 90, G)])
+    t = [[Partition(b"k", [Row((I32(1),), [Cell(0, T0, c1)])], static=Row((), [Cell(0, T0 + 1, c1), Cell(1, T0, c2)]))],
+         [Partition(b"k", [], static=Row((), [Cell(0, T0 + 2, c2)]))],
+         [Partition(b"k", [Row((I32(1),), [Cell(0, T0 + 3, c2)])], static=Row((), [Cell(0, T0, c3), Cell.tombstone(1, T0 - 5, NOW - 5)]))]]
+    raw = check_static(t)
+    assert ctx([(cid(1), 9, 90, G), (cid(2), 1, 1, G)]) in raw                           # static s: three contexts merged; static t: the tombstone wins
+    check_static([t[0], [Partition(b"k", [], (T0 + 1, NOW - 5), static=Row((), [Cell(0, T0 + 7, c2)]))]])      # partition deletion skips the older static cells before the merge
+
+def test_static_counters_randomised_against_the_model():
+    rng = random.Random(0x57A71C)
+    for it in range(60):
+        tables = []
+        for _ in range(rng.randint(1, 4)):
+            parts = []
+            for k in range(4):
+                if rng.random() < 0.3: continue
+                rows = [Row((I32(ck),), [Cell(0, T0 + rng.randint(0, 40), random_context(rng, [1, 2, 3]))]) for ck in range(3) if rng.random() < 0.5]
+                scells = []
+                for col in (0, 1):
+                    x = rng.random(); ts = T0 + rng.randint(0, 40)
+                    if x < 0.3: continue
+                    if x < 0.4: scells.append(Cell.tombstone(col, ts, NOW - rng.choice([5, 30 * 86400])))
+                    else: scells.append(Cell(col, ts, random_context(rng, [1, 2, 3, 4])))
+                st = Row((), scells) if scells else None
+                pdel = (T0 + rng.randint(0, 30), NOW - rng.choice([5, 30 * 86400])) if rng.random() < 0.2 else None
+                if rows or st or pdel: parts.append(Partition(b"key%d" % k, rows, pdel, static=st))
+            if parts: tables.append(parts)
+        if tables: check_static(tables, gc_grace=rng.choice([864000, 1, 10 ** 9]))

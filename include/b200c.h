@@ -132,7 +132,7 @@ enum {
     B200C_TYPE_TIMEUUID = 4,     /* 16 bytes, TimeUUIDType.compareCustom (S/db/marshal/TimeUUIDType.java): timestamp fields first — cell paths of lists only */
     B200C_TYPE_COUNTER = 5       /* CounterColumnType: variable length counter context (S/db/context/CounterContext.java:40-76); live cells of the same
                                     row are MERGED shard by shard (Cells.resolveCounter S/db/rows/Cells.java:121-162) instead of picked. Regular
-                                    simple columns only; static counter columns are refused. */
+                                    and static simple columns. */
 };
 /* A multi-cell (complex) column — non-frozen map / set / list — stores one cell per element, each with a CELL PATH (the map key, the set
  * element, the list's timeuuid), and an optional complex deletion (S/db/rows/ComplexColumnData.java, UnfilteredSerializer.java:271-280,

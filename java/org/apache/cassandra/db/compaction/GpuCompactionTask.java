@@ -77,9 +77,9 @@ public class GpuCompactionTask extends CompactionTask
         TableMetadata t = cfs.metadata();
         if (inputs.isEmpty() || inputs.size() > B200C.MAX_INPUTS) return false;
         if (!(t.partitioner instanceof Murmur3Partitioner) && !(t.partitioner instanceof ByteOrderedPartitioner)) return false;
-        if (t.isIndex() || t.staticColumns().size() > B200C.MAX_STATIC_COLUMNS) return false;      // (counter tables: regular counter columns only — typeClass refuses a static one)
+        if (t.isIndex() || t.staticColumns().size() > B200C.MAX_STATIC_COLUMNS) return false;
         for (ColumnMetadata c : t.staticColumns())
-            if (c.isComplex() || typeClass(c.type) < 0) return false;
+            if (c.isComplex() || columnClass(c.type) < 0) return false;                          // (simple static columns, counters included; multi-cell static columns keep the stock task)
         if (t.clusteringColumns().size() > B200C.MAX_CLUSTERING || t.regularColumns().size() >= B200C.MAX_COLUMNS) return false;
         int complex = 0;
         for (ColumnMetadata c : t.regularColumns())
@@ -276,7 +276,7 @@ public class GpuCompactionTask extends CompactionTask
                     m.putInt(M_COLUMNS + 8 * k, columnClass(outColumns.get(k).type)).putInt(M_COLUMNS + 8 * k + 4, columnFixedLen(outColumns.get(k).type));      // (header order: simple columns, then multi-cell ones)
                 m.putInt(M_NSTATIC_COLUMNS, outStatics.size());
                 for (int k = 0; k < outStatics.size(); k++)
-                    m.putInt(M_STATIC_COLUMNS + 8 * k, typeClass(outStatics.get(k).type)).putInt(M_STATIC_COLUMNS + 8 * k + 4, Math.max(0, outStatics.get(k).type.valueLengthIfFixed()));
+                    m.putInt(M_STATIC_COLUMNS + 8 * k, columnClass(outStatics.get(k).type)).putInt(M_STATIC_COLUMNS + 8 * k + 4, Math.max(0, outStatics.get(k).type.valueLengthIfFixed()));
                 m.putLong(M_OUT_STATS, outStats.minTimestamp).putLong(M_OUT_STATS + 8, outStats.minLocalDeletionTime).putInt(M_OUT_STATS + 16, outStats.minTTL);
                 m.putInt(M_OUT_COMPRESSOR, outComp).putInt(M_OUT_CHUNK_LEN, cp.chunkLength()).putInt(M_OUT_MAX_COMPRESSED_LEN, cp.maxCompressedLength());
                 m.putInt(M_COLUMN_INDEX_SIZE, DatabaseDescriptor.getColumnIndexSize(BigFormat.getInstance().getDefaultColumnIndexSize()));

@@ -1721,7 +1721,7 @@ int b200c_compact(b200c_ctx* c, const b200c_manifest* m, b200c_result* res, int 
                 int kinde = (int)(h[2] >> 56);
                 res->corruption.input = (int)((h[2] >> 48) & 0xFF); res->corruption.kind = 4; res->corruption.chunk = 0; res->corruption.offset = h[2] & 0xFFFFFFFFFFFFull;
                 timing_end(c);
-                if (kinde == 9) { c->err = "unsupported feature in input " + std::to_string(res->corruption.input) + " (static row, complex column or shadowable deletion)"; return B200C_EUNSUPPORTED; }
+                if (kinde == 9) { c->err = "unsupported feature in input " + std::to_string(res->corruption.input) + " (outside the envelope: shadowable deletion, a fan-in or layout the kernels refuse, or a counter context the reference never writes inside a merge)"; return B200C_EUNSUPPORTED; }
                 c->err = "malformed Data.db in input " + std::to_string(res->corruption.input) + " near offset " + std::to_string(res->corruption.offset);
                 return B200C_ECORRUPT;
             }

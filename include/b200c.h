@@ -40,7 +40,7 @@ enum {
     B200C_ECUDA = -2,         /* CUDA error / no device; b200c_last_error has the text */
     B200C_ECORRUPT = -3,      /* checksum mismatch or malformed input; see b200c_corruption */
     B200C_ECANCELLED = -4,
-    B200C_EUNSUPPORTED = -5,  /* schema/feature outside the supported envelope (static rows, complex columns, counters...) */
+    B200C_EUNSUPPORTED = -5,  /* schema/feature outside the supported envelope (multi-cell static columns, non-frozen UDTs, shadowable deletions, a counter context the reference never writes inside a merge ...) */
     B200C_ENOMEM = -6,        /* device or host workspace exhausted */
     B200C_ETOOSMALL = -7      /* a caller-provided output buffer is too small; required sizes are reported */
 };

@@ -760,7 +760,8 @@ template <bool E> __device__ __noinline__ int ctr_merge(const CParams& P, const 
         if (c.m.ldt != I64_MAX && c.m.ttl == 0) { if (!tomb.present || !reconcile_keep_left(P, tomb, c.m)) tomb = c.m; continue; }     // tombstones among themselves: resolveRegular
         if (c.m.vlen == 0) { if (!empty.present || !(empty.ts > c.m.ts)) empty = c.m; continue; }                                    // :142-149
         if (c.m.ttl != 0) return PERR_UNSUPPORTED;                    // (a counter cell cannot expire)
-        if (c.m.vlen < 2 || c.m.vlen > 0xFFFF) return PERR_CORRUPT;
+        if (c.m.vlen < 2) return PERR_CORRUPT;
+        if (c.m.vlen > 0xFFFF) return PERR_UNSUPPORTED;               // (2 047 shards and more: the 16-bit walk state below does not hold it)
         const int n = ctr_be16(P.U + c.m.voff);
         if (n < 0) return PERR_UNSUPPORTED;                           // "local shards to be cleared" marker (:618-628): only on streamed cells
         const int h = 2 + 2 * n;

@@ -402,7 +402,7 @@ def run_b200(args, wl):
             "pipeline_achieved_gbs": round(b_alg / (kms / 1e3) / 1e9, 2), "pipeline_frac": round(b_alg / (kms / 1e3) / 1e9 / peak, 5),
             "algorithmic_bytes_per_step": int(b_alg)}
     line = {"metric": METRIC, "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"] + ", chunk 16 KiB, schema %s, seed %#x" % (wl["schema"], wl["seed"]),
                        "uncompressed_in_bytes": u_in, "l2": "inputs (%.1f GB/step) larger than L2" % ((c_in + u_in) / 1e9),
@@ -526,7 +526,7 @@ def run_reference(args, wl):
           "phase_ms": [round(x / args.steps, 1) for x in tms[:3]], "range_tasks_ms": {"wall_sum": round(tms[3] / args.steps, 1), "thread_cpu_sum": round(tms[4] / args.steps, 1), "longest": round(tms[5] / args.steps, 1)},
           "scaling": curve or None, "host_threads": threads, "host": cpu_note}
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(total / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "ms_per_step": round(total / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"] + ", chunk 16 KiB, schema %s, seed %#x" % (wl["schema"], wl["seed"]), "uncompressed_in_bytes": u_in,
                        "reference_arm": "C++ restatement of the reference algorithm (oracle/; the JVM cannot run in this image: no JDK), same inputs as the b200 arm, "
                                         "as many threads as the container's CPU quota allows (cpu_baseline.host) via token-range parallelism; the reference itself runs one such compaction on ONE thread (cpu_baseline.scaling['1'])"},

@@ -5,7 +5,8 @@ comparison with an independent Python restatement (this file: a K-WAY, per-count
   hasLegacyShards                                           S/db/context/CounterContext.java:595-608
   Cells.reconcile -> resolveCounter                         S/db/rows/Cells.java:68-77, 121-162
   Cells.collectStats (updateHasLegacyCounterShards)         S/db/rows/Cells.java:44-50
-  known answers                                             T/unit/org/apache/cassandra/db/context/CounterContextTest.java:261-380 (testMerge)
+  known answers                                             T/unit/org/apache/cassandra/db/context/CounterContextTest.java:261-380 (testMerge),
+                                                            T/unit/org/apache/cassandra/db/CounterCellTest.java:127-186 (testReconcile)
   golden tables                                             T/data/legacy-sstables/oa/legacy_tables/legacy_oa_{simple,clust}_counter (LegacySSTableTest)"""
 import ctypes as C, os, random, struct, copy, pytest
 import oracle_lib as O
@@ -344,3 +345,29 @@ def test_static_counters_randomised_against_the_model():
                 if rows or st or pdel: parts.append(Partition(b"key%d" % k, rows, pdel, static=st))
             if parts: tables.append(parts)
         if tables: check_static(tables, gc_grace=rng.choice([864000, 1, 10 ** 9]))
+
+# ---- the reference's known answers for Cells.reconcile on counter cells (T/unit/org/apache/cassandra/db/CounterCellTest.java:127-186, testReconcile) --------
+def _one_cell_tables(cells):
+    return [[Partition(b"k", [Row((I32(1),), [c])])] for c in cells]
+def _expect_cell(tables_parts, cell, gc_grace=NOW + 10):
+    """the compaction of the one-cell tables holds exactly `cell` (None: nothing is left); gc_before < 0: the test's tiny deletion times are not purgeable"""
+    tabs = [Builder(SC).build(p) for p in tables_parts]
+    got = oracle_compact(tabs, NOW, gc_grace)
+    want = raw_of(Builder(SC, merged_encoding_stats(tabs)).build([Partition(b"k", [Row((I32(1),), [cell])])])) if cell is not None else b""
+    assert got == want
+
+def test_reference_counter_cell_reconcile():
+    local = lambda count: ctx([(LOCAL_ID, 1, count, L)])                                 # CounterContext.createLocal(count): one local shard, clock 1 (:139-144)
+    dead = lambda ts, ldt: Cell.tombstone(0, ts, ldt)
+    _expect_cell(_one_cell_tables([dead(2, 5), dead(2, 10)]), dead(2, 10))              # :137-140 both deleted, same ts: the later deletion time
+    _expect_cell(_one_cell_tables([dead(2, 5), Cell(0, 10, local(1))]), dead(2, 5))     # :142-144 "diff ts": the tombstone, although older
+    _expect_cell(_one_cell_tables([dead(6, 6), Cell(0, 5, local(1))]), dead(6, 6))      # :146-149
+    _expect_cell(_one_cell_tables([dead(1, 1), Cell(0, 5, local(1))]), dead(1, 1))      # :151-154
+    _expect_cell(_one_cell_tables([dead(8, 8), Cell(0, 8, local(1))]), dead(8, 8))      # :156-159
+    live = [Cell(0, 2, local(1)), Cell(0, 5, local(3))]
+    _expect_cell(_one_cell_tables(live), Cell(0, 5, ctx([(LOCAL_ID, 2, 4, L)])))        # :161-166 live + live: total 4, timestamp 5
+    live.append(Cell(0, 4, local(10)))
+    _expect_cell(_one_cell_tables(live), Cell(0, 5, ctx([(LOCAL_ID, 3, 14, L)])))       # :168-172 add, the timestamp stays
+    live.append(Cell(0, 7, local(3)))
+    _expect_cell(_one_cell_tables(live), Cell(0, 7, ctx([(LOCAL_ID, 4, 17, L)])))       # :174-178 add with a newer timestamp
+    _expect_cell(_one_cell_tables(live + [dead(8, 8)]), dead(8, 8))                     # :183-185 ... and a tombstone ends it

@@ -187,3 +187,15 @@ def test_k4_source_refuses_contexts_the_reference_does_not_write(k4lib):
             host_k4(k4lib, CompactionTask(t, CompactionController(NOW)))
         data, _, _ = host_k4(k4lib, CompactionTask(t[:1], CompactionController(NOW)))
         assert odd in data
+
+def test_k4_source_on_the_reference_counter_cell_answers(k4lib):
+    """CounterCellTest.testReconcile's cases (pinned to their expected cells in tests/test_oracle_counter_kats.py) through the K4 source"""
+    from counter_tables import SCTR, ctx as cctx, L as LOCAL
+    lid = struct.pack(">QQ", 0x0123456789AB11EE, 0x8000000000000077)
+    local = lambda count: cctx([(lid, 1, count, LOCAL)])
+    dead = lambda ts, ldt: Cell.tombstone(0, ts, ldt)
+    live = [Cell(0, 2, local(1)), Cell(0, 5, local(3)), Cell(0, 4, local(10)), Cell(0, 7, local(3))]
+    for cells in ([dead(2, 5), dead(2, 10)], [dead(2, 5), Cell(0, 10, local(1))], [dead(6, 6), Cell(0, 5, local(1))], [dead(8, 8), Cell(0, 8, local(1))],
+                  live[:2], live[:3], live, live + [dead(8, 8)]):
+        tabs = [Builder(SCTR).build([Partition(b"k", [Row((I32(1),), [c])])]) for c in cells]
+        check(k4lib, tabs, CompactionController(NOW, NOW + 10))

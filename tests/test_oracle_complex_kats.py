@@ -7,7 +7,8 @@ Python restatement of the reference's rules (this file), both written from the J
   Cell.Serializer.serialize                          S/db/rows/Cell.java:268-305   (the path precedes the value)
   AbstractTimeUUIDType.compareCustom                 S/db/marshal/AbstractTimeUUIDType.java:58-87   (list cell paths)
 No reference-held `oa` fixture carries a multi-cell column: the expected outputs are produced by sstable_builder.py from the model's rows and compared
-with the oracle's Data.db bytes."""
+with the oracle's Data.db bytes. The reference's own known answers for such rows — RowsTest.merge and mergeComplexDeletionSupersededByRowDeletion
+(T/unit/org/apache/cassandra/db/rows/RowsTest.java:460-508) — are the last two tests."""
 import random, struct, pytest
 import oracle_lib as O
 from sstable_builder import *
@@ -221,3 +222,27 @@ def test_randomised_against_the_model():
                 parts.append(Partition(key, rows, (T0 + rng.randint(0, 40), NOW - 5) if rng.random() < 0.1 else None))
             tables.append(parts)
         check(SM, tables, gc_grace=rng.choice([864000, 10 ** 9, 0]))
+
+# ---- the reference's own known answers for rows with a multi-cell column (T/unit/org/apache/cassandra/db/rows/RowsTest.java) ------------------------------
+# Table kcvm there: clustering c, regular v, m map<..>, (:60-66; IntegerType there, Int32Type here — the cases do not depend on the value comparison).
+SKV = Schema(["Int32Type"], [("v", "Int32Type"), ("m", "MapType(Int32Type,Int32Type)")])
+def _expect_rows(tables_parts, want_rows, schema=SKV):
+    tabs = [Builder(schema).build(p) for p in tables_parts]
+    got = oracle_compact(tabs, NOW, 10 ** 9)
+    want = raw_of(Builder(schema, merged_encoding_stats(tabs)).build([Partition(b"k", want_rows)])) if want_rows else b""
+    assert got == want
+
+def test_reference_rows_merge_with_complex_deletion():
+    """RowsTest.merge :460-489: the update's value and map cell win, its complex deletion shadows the existing map cell"""
+    now1, now2 = NOW - 100, NOW - 99; ts1, ts2 = now1 * 1000000, now2 * 1000000
+    existing = Row((I32(1),), [Cell(0, ts1, I32(1)), Cell(1, ts1, I32(1), path=I32(1))], ts=ts1, complex_deletions={1: (ts1 - 1, now1)})     # createBuilder(c1, now1, BB1, BB1, BB1) :222-238
+    update = Row((I32(1),), [Cell(0, ts2, I32(2)), Cell(1, ts2, I32(2), path=I32(1))], ts=ts2, complex_deletions={1: (ts2 - 1, now2)})
+    merged = Row((I32(1),), [Cell(0, ts2, I32(2)), Cell(1, ts2, I32(2), path=I32(1))], ts=ts2, complex_deletions={1: (ts2 - 1, now2)})
+    _expect_rows([[Partition(b"k", [existing])], [Partition(b"k", [update])]], [merged])
+
+def test_reference_complex_deletion_superseded_by_row_deletion():
+    """RowsTest.mergeComplexDeletionSupersededByRowDeletion :491-508: the row deletion stays, no complex deletion, no cells"""
+    now1 = NOW - 100; now3 = now1 + 2; ts1 = now1 * 1000000
+    existing = Row((I32(1),), [Cell(1, ts1, I32(2), path=I32(2))], ts=ts1, complex_deletions={1: (ts1 - 1, now1)})                           # createBuilder(c1, now1, null, BB2, BB2)
+    update = Row((I32(1),), [], deletion=(now3 * 1000000, now3))
+    _expect_rows([[Partition(b"k", [existing])], [Partition(b"k", [update])]], [Row((I32(1),), [], deletion=(now3 * 1000000, now3))])

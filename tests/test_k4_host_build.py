@@ -59,9 +59,12 @@ def test_k4_source_matches_oracle_on_synthetic_tables(k4lib, schema, n, universe
 
 def test_k4_source_on_golden_files(k4lib, golden_dir):
     from cassandra_b200.io.sstable import SSTable
-    for name in ("legacy_oa_simple", "legacy_oa_clust"):
+    for name in ("legacy_oa_simple", "legacy_oa_clust", "legacy_oa_simple_counter", "legacy_oa_clust_counter"):
         t = SSTable.open(os.path.join(golden_dir, "oa", "legacy_tables", name, "oa-1-big-"))
         check(k4lib, [t], CompactionController(NOW, 0))
+        if name.endswith("counter"):                       # three-way self merge: every context meets its equal
+            base = os.path.join(golden_dir, "oa", "legacy_tables", name, "oa-1-big-")
+            check(k4lib, [SSTable.open(base, 1), SSTable.open(base, 2), SSTable.open(base, 3)], CompactionController(NOW, 0))
 
 def test_k4_source_mixed_types_and_token_range(k4lib):
     rng = random.Random(11)
